@@ -1,0 +1,222 @@
+/*
+ * mqe_b200.h -- C ABI of libmqe_b200.so: the B200-native replacement for the Isaac Gym tensor-API
+ * subset that mqe.envs.go1.Go1.step() drives (reference: mqe/envs/go1/go1.py:35-62,
+ * mqe/envs/base/legged_robot.py:117-157, 394-470, 549-595).
+ *
+ * The reference has no FFI of its own: its "lower" interface is the closed isaacgym Python module.
+ * Each entry point below names the gym call(s) it replaces.  All functions return 0 on success or a
+ * negative MqeStatus; mqe_last_error() returns a thread-local message.  No function throws, none
+ * synchronises the device unless it says so.  Pointers named d_* are DEVICE pointers, h_* HOST pointers.
+ * Every kernel is enqueued on the stream given at creation (or set with mqe_sim_set_stream).
+ *
+ * Layout conventions: env-major, fp32, quaternions xyzw.
+ *   root_states  [N][A+P][13]  pos3 quat4 linvel3(world) angvel3(world)   (gym.acquire_actor_root_state_tensor)
+ *   dof_states   [N][12A+D][2] (pos, vel)                                  (gym.acquire_dof_state_tensor)
+ *   contact_force[N][17A+P][3] net world-frame contact force per rigid body (gym.acquire_net_contact_force_tensor)
+ */
+#ifndef MQE_B200_H
+#define MQE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQE_ABI_VERSION 1
+#define MQE_MAX_PROBES 32
+#define MQE_MAX_CAPS 20
+#define MQE_NUM_DOF 12
+#define MQE_NUM_BODIES 17
+#define MQE_LOC_OBS 70           /* walk-these-ways observation frame (go1.py:64-108)          */
+#define MQE_HIST_FRAMES 30       /* history depth, 30 x 70 = 2100 (go1.py:395)                 */
+#define MQE_OBS_FLOATS 71        /* per-agent observation struct (go1.py:153-196)              */
+
+typedef enum {
+    MQE_OK = 0,
+    MQE_ERR_INVALID = -1,        /* bad argument / descriptor                                  */
+    MQE_ERR_CUDA = -2,           /* a CUDA runtime call failed (message has the cudaError)     */
+    MQE_ERR_NO_DEVICE = -3,      /* no sm_100 device visible: there is NO CPU fallback         */
+    MQE_ERR_UNSUPPORTED = -4
+} MqeStatus;
+
+typedef enum { MQE_NPC_NONE = 0, MQE_NPC_RIGID = 1, MQE_NPC_SEESAW = 2 } MqeNpcKind;
+typedef enum { MQE_NPC_PASSIVE = 0, MQE_NPC_SHEEP = 1 } MqeNpcCtrl;
+typedef enum { MQE_POLICY_FP32 = 0, MQE_POLICY_BF16X3 = 1, MQE_POLICY_BF16 = 2 } MqePolicyMode;
+
+/* Compiled robot tables (model.py; go1.urdf after Isaac Gym's fixed-joint collapse). */
+typedef struct {
+    float base_inertial[10];          /* m, com xyz, Ixx Ixy Ixz Iyy Iyz Izz about the COM, base frame     */
+    float leg_offsets[4][4][3];       /* per leg FL,FR,RL,RR: hip joint pos, thigh off, calf off, foot off */
+    float leg_inertial[4][3][10];     /* hip, thigh, calf(+foot)                                           */
+    float q_lower[12], q_upper[12], qd_limit[12], tau_limit[12], q_default[12];
+    int32_t n_probes, n_caps;
+    float probes[MQE_MAX_PROBES][6];  /* link id, rigid-body id, centre xyz (link frame), radius           */
+    float caps[MQE_MAX_CAPS][9];      /* link id, rigid-body id, p0 xyz, p1 xyz, radius                    */
+} MqeRobotModel;
+
+/* Frozen network weights, row-major [out][in] exactly as the TorchScript state_dicts hold them
+ * (go1.py:367,397-398).  HOST pointers, copied at creation. */
+typedef struct {
+    const float *adapt_w0, *adapt_b0;   /* [256][2100]  */
+    const float *adapt_w1, *adapt_b1;   /* [128][256]   */
+    const float *adapt_w2, *adapt_b2;   /* [2][128]     */
+    const float *body_w0, *body_b0;     /* [512][2102]  */
+    const float *body_w1, *body_b1;     /* [256][512]   */
+    const float *body_w2, *body_b2;     /* [128][256]   */
+    const float *body_w3, *body_b3;     /* [12][128]    */
+    const float *act_w0, *act_b0;       /* [32][6]      */
+    const float *act_w1, *act_b1;       /* [32][32]     */
+    const float *act_w2, *act_b2;       /* [1][32]      */
+} MqeWeights;
+
+/* Simulation descriptor: what gymapi.SimParams + the env cfg carry for this path. */
+typedef struct {
+    int32_t abi_version;
+    int32_t num_envs, num_agents, num_npcs;     /* LOCAL shard sizes                                       */
+    int32_t env_id_offset;                      /* global id of local env 0 (keys the counter-based RNG)   */
+    int32_t npc_kind, npc_ctrl, npc_dofs;       /* MqeNpcKind, MqeNpcCtrl, NPC dofs per env                */
+    int32_t decimation;                         /* go1_config.py:119                                       */
+    int32_t solver_iters;                       /* contact impulse sweeps per substep                      */
+    int32_t max_episode_length;                 /* ceil(episode_length_s / dt), legged_robot.py:1021       */
+    int32_t term_mask;                          /* bit0 roll bit1 pitch bit2 z_low bit3 z_high bit4 base contact */
+    int32_t quat_alias;                         /* 1 iff P==0: obs base_quat/base_rpy alias the sim tensor  */
+    int32_t policy_mode;                        /* MqePolicyMode                                           */
+    int32_t defender;                           /* 1: last agent is the scripted defender (go1_football_defender.py) */
+    int32_t command_vel;                        /* cfg.command.cfg.vel: actions carry (vx, vy, wz) (go1.py:66-68)     */
+    float sim_dt;                               /* legged_robot_config.py:212                              */
+    float gravity_z;
+    float friction, contact_offset, max_depen_vel, erp, cfm;
+    float floor_z, wall_top_z;                  /* barrier_track.py:628-632 ground slab / wall_height       */
+    float limit_margin;                         /* joint-limit rows become active inside this margin [rad]  */
+    float term_roll, term_pitch, term_zlow, term_zhigh;
+    float act_scale[3];                         /* wrapper action scale [2,.5,.5] applied before clip(+-1)  */
+    float cmd_scale[3];                         /* obs_scales lin_vel, lin_vel, ang_vel (go1.py:66-68)      */
+    float action_scale, hip_scale, clip_actions;/* go1_config.py:113,120,108                               */
+    float loc_obs_default[MQE_LOC_OBS];         /* go1.py:411-479                                          */
+    float dof_ratio_lo, dof_ratio_hi;           /* init_dof_pos_ratio_range                                */
+    float base_vel_lo, base_vel_hi;
+    int32_t has_base_pos_range, has_npc_pos_range, has_npc_rpy_range, reserved1;
+    float base_pos_x[2], base_pos_y[2];
+    float npc_pos_x[2], npc_pos_y[2];
+    float npc_rpy_r[2], npc_rpy_p[2], npc_rpy_y[2];
+    float npc_mass, npc_inertia, npc_radius, npc_halflen;
+    float sheep_scale, sheep_randomness;        /* go1_sheep_config.py asset.sheep_movement_*              */
+    float gate_x;                               /* defender: init+plane block length                       */
+    float reserved2;
+    uint64_t seed;
+    /* static world: 2-D signed distance to the wall footprint on the BarrierTrack pixel grid */
+    int32_t sdf_nx, sdf_ny;
+    float sdf_cell, reserved3;
+    const float *h_sdf;                         /* [nx][ny] host, copied                                   */
+    /* per-env constants, host, copied */
+    const float *h_env_origins;                 /* [N][3]                                                  */
+    const float *h_agent_origins;               /* [N][A][3]                                               */
+    const float *h_base_init_state;             /* [N*A][13]                                               */
+    const float *h_npc_init_state;              /* [N*P][13] or NULL                                       */
+    const float *h_npc_dof_default;             /* [D] or NULL                                             */
+    MqeRobotModel model;
+    MqeWeights weights;
+} MqeSimDesc;
+
+typedef struct MqeSim MqeSim;
+
+/* Buffers owned by the engine; mqe_sim_get_buffer returns the device pointer and shape so a host
+ * framework can wrap them zero-copy (replaces gym.acquire_*_tensor + gymtorch.wrap_tensor,
+ * legged_robot.py:554-595). */
+typedef enum {
+    MQE_BUF_ROOT_STATES = 0,    /* f32 [N][A+P][13]                         */
+    MQE_BUF_DOF_STATES,         /* f32 [N][12A+D][2]                        */
+    MQE_BUF_CONTACT_FORCES,     /* f32 [N][17A+P][3]                        */
+    MQE_BUF_TORQUES,            /* f32 [N][12A]                             */
+    MQE_BUF_ACTIONS,            /* f32 [N][12A]   clipped policy output     */
+    MQE_BUF_LAST_ACTIONS,       /* f32 [N][12A]                             */
+    MQE_BUF_OBS,                /* f32 [N*A][71]  see MQE_OBS_* offsets     */
+    MQE_BUF_BASE_LIN_VEL,       /* f32 [N*A][3]                             */
+    MQE_BUF_BASE_ANG_VEL,       /* f32 [N*A][3]                             */
+    MQE_BUF_PROJ_GRAVITY,       /* f32 [N*A][3]                             */
+    MQE_BUF_RESET,              /* u8  [N]                                  */
+    MQE_BUF_TIMEOUT,            /* u8  [N]                                  */
+    MQE_BUF_COLLIDE,            /* u8  [N]                                  */
+    MQE_BUF_ROLL_TERM,          /* u8  [N]                                  */
+    MQE_BUF_PITCH_TERM,         /* u8  [N]                                  */
+    MQE_BUF_ZLOW_TERM,          /* u8  [N]                                  */
+    MQE_BUF_ZHIGH_TERM,         /* u8  [N]                                  */
+    MQE_BUF_EPISODE_LENGTH,     /* i64 [N]                                  */
+    MQE_BUF_COMMANDS,           /* f32 [N*A][3]   clipped command given to the policy */
+    MQE_BUF_LOC_OBS,            /* f32 [N*A][70]                            */
+    MQE_BUF_LOC_ACTION,         /* f32 [N*A][12]  raw policy output (last_locomotion_action) */
+    MQE_BUF_GAIT,               /* f32 [N*A]                                */
+    MQE_BUF_HISTORY,            /* bf16 hi/lo ring, engine-internal layout  */
+    MQE_BUF_SHEEP_STATS,        /* f32 [N][3]     sheep_pos_avg xy, sheep_pos_var */
+    MQE_BUF_STATS,              /* i32 [8]        contact / row statistics of the last step */
+    MQE_BUF_COUNT
+} MqeBuffer;
+
+/* offsets into one agent's MQE_BUF_OBS row (go1.py:153-196) */
+#define MQE_OBS_BASE_POS 0
+#define MQE_OBS_BASE_QUAT 3
+#define MQE_OBS_DOF_POS 7
+#define MQE_OBS_DOF_VEL 19
+#define MQE_OBS_LIN_VEL 31
+#define MQE_OBS_ANG_VEL 34
+#define MQE_OBS_LAST_ACTION 37
+#define MQE_OBS_LAST_LAST_ACTION 49
+#define MQE_OBS_PROJ_GRAVITY 61
+#define MQE_OBS_CLOCK 64
+#define MQE_OBS_BASE_RPY 68
+
+const char *mqe_last_error(void);
+int mqe_abi_version(void);
+int mqe_device_count(void);
+
+/* gymapi.acquire_gym + create_sim + create_env/create_actor loop + prepare_sim
+ * (base_task.py:40-95, legged_robot.py:255-261,754-923).  `stream` is a cudaStream_t (may be NULL). */
+int mqe_sim_create(const MqeSimDesc *desc, int device, void *stream, MqeSim **out);
+int mqe_sim_destroy(MqeSim *sim);
+int mqe_sim_set_stream(MqeSim *sim, void *stream);
+
+/* gym.acquire_*_tensor (legged_robot.py:554-557).  shape[4] is zero padded; elem_size in bytes. */
+int mqe_sim_get_buffer(MqeSim *sim, int which, void **d_ptr, int64_t shape[4], int32_t *elem_size);
+
+/* Go1.reset(): reset_idx(all) + compute_observations (go1.py:147-151). */
+int mqe_sim_reset(MqeSim *sim);
+
+/* One policy step, Go1.step() (go1.py:35-62): command -> obs frame + history -> walk policy ->
+ * decimation x (actuator net -> simulate -> refresh) -> post_physics_step (terminate, NPC step,
+ * indexed reset, observations).  d_actions: f32 [N][A_ctrl][3] wrapper-level actions in [-1,1]
+ * (A_ctrl = A, or A-1 when desc.defender).  Asynchronous on the stream. */
+int mqe_sim_step(MqeSim *sim, const float *d_actions);
+
+/* Same step through HOST buffers: H2D of actions, step, D2H of obs rows / reset flags; blocks until
+ * the results are in host memory.  h_obs: [N*A][71] (may be NULL), h_reset: [N] (may be NULL). */
+int mqe_sim_step_host(MqeSim *sim, const float *h_actions, float *h_obs, uint8_t *h_reset);
+
+/* Finer-grained entry points mirroring the individual gym calls (used by tests and by a host that
+ * wants to keep the reference's loop structure). */
+int mqe_sim_policy(MqeSim *sim, const float *d_actions);     /* preprocess_action, go1.py:64-108              */
+int mqe_sim_substeps(MqeSim *sim, int count);                /* count x {_compute_torques; gym.simulate; refresh_dof_state} go1.py:48-58 */
+int mqe_sim_post_physics(MqeSim *sim);                       /* post_physics_step, legged_robot.py:117-157    */
+
+/* gym.set_actor_root_state_tensor_indexed / set_dof_state_tensor_indexed (legged_robot.py:419-421,
+ * 468-470): the state buffers ARE the engine state, so writes through the wrapped views take effect
+ * directly; these calls exist for hosts that stage state elsewhere.  d_actor_ids: i32 [n] actor
+ * indices (DOMAIN_SIM: env*(A+P)+k). */
+int mqe_sim_set_root_indexed(MqeSim *sim, const float *d_root_states, const int32_t *d_actor_ids, int n);
+int mqe_sim_set_dof_indexed(MqeSim *sim, const float *d_dof_states, const int32_t *d_actor_ids, int n);
+
+/* stand-alone operator entry points (parity tests against the TorchScript goldens) */
+int mqe_policy_forward(MqeSim *sim, const float *d_history /* [rows][2100] */, int rows,
+                       float *d_latent /* [rows][2] */, float *d_action /* [rows][12] */);
+int mqe_actuator_forward(MqeSim *sim, const float *d_x /* [rows][6] */, int rows, float *d_torque);
+int mqe_robot_dynamics(MqeSim *sim, const float *d_q /* [rows][7+12] pos-less: quat4? see .cu */,
+                       const float *d_v, const float *d_tau, int rows, float *d_qdd);
+
+int mqe_sim_synchronize(MqeSim *sim);
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t mqe_sim_launch_count(MqeSim *sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MQE_B200_H */

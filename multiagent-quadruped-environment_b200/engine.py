@@ -1,0 +1,259 @@
+"""ctypes binding of libmqe_b200.so (include/mqe_b200.h) -- the thin host side of the C ABI.
+
+There is deliberately no CPU implementation behind this class: if the CUDA library is missing or no
+sm_100 device is visible, construction raises.  PyTorch is used only to wrap the engine-owned device
+buffers zero-copy (the role `gymtorch.wrap_tensor` plays in the reference, legged_robot.py:567-595).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from .model import MAX_CAPS, MAX_PROBES, RobotModelC  # noqa: F401
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "csrc", "libmqe_b200.so")
+
+ABI_VERSION = 1
+LOC_OBS = 70
+OBS_FLOATS = 71
+
+(BUF_ROOT_STATES, BUF_DOF_STATES, BUF_CONTACT_FORCES, BUF_TORQUES, BUF_ACTIONS, BUF_LAST_ACTIONS, BUF_OBS,
+ BUF_BASE_LIN_VEL, BUF_BASE_ANG_VEL, BUF_PROJ_GRAVITY, BUF_RESET, BUF_TIMEOUT, BUF_COLLIDE, BUF_ROLL_TERM,
+ BUF_PITCH_TERM, BUF_ZLOW_TERM, BUF_ZHIGH_TERM, BUF_EPISODE_LENGTH, BUF_COMMANDS, BUF_LOC_OBS, BUF_LOC_ACTION,
+ BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_COUNT) = range(26)
+
+OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
+    "base_pos": (0, 3), "base_quat": (3, 7), "dof_pos": (7, 19), "dof_vel": (19, 31), "lin_vel": (31, 34),
+    "ang_vel": (34, 37), "last_action": (37, 49), "last_last_action": (49, 61), "projected_gravity": (61, 64),
+    "clock_inputs": (64, 68), "base_rpy": (68, 71),
+}
+
+NPC_NONE, NPC_RIGID, NPC_SEESAW = 0, 1, 2
+NPC_PASSIVE, NPC_SHEEP = 0, 1
+POLICY_FP32, POLICY_BF16X3, POLICY_BF16 = 0, 1, 2
+
+_fp = ctypes.POINTER(ctypes.c_float)
+
+WEIGHT_FIELDS = [                                 # (field, npz key, shape) -- order of MqeWeights
+    ("adapt_w0", "adapt.0.weight", (256, 2100)), ("adapt_b0", "adapt.0.bias", (256,)),
+    ("adapt_w1", "adapt.2.weight", (128, 256)), ("adapt_b1", "adapt.2.bias", (128,)),
+    ("adapt_w2", "adapt.4.weight", (2, 128)), ("adapt_b2", "adapt.4.bias", (2,)),
+    ("body_w0", "body.0.weight", (512, 2102)), ("body_b0", "body.0.bias", (512,)),
+    ("body_w1", "body.2.weight", (256, 512)), ("body_b1", "body.2.bias", (256,)),
+    ("body_w2", "body.4.weight", (128, 256)), ("body_b2", "body.4.bias", (128,)),
+    ("body_w3", "body.6.weight", (12, 128)), ("body_b3", "body.6.bias", (12,)),
+    ("act_w0", "act.0.weight", (32, 6)), ("act_b0", "act.0.bias", (32,)),
+    ("act_w1", "act.2.weight", (32, 32)), ("act_b1", "act.2.bias", (32,)),
+    ("act_w2", "act.4.weight", (1, 32)), ("act_b2", "act.4.bias", (1,)),
+]
+
+
+class WeightsC(ctypes.Structure):
+    _fields_ = [(name, _fp) for name, _, _ in WEIGHT_FIELDS]
+
+
+class SimDescC(ctypes.Structure):
+    """Field-for-field mirror of MqeSimDesc."""
+    _fields_ = [
+        ("abi_version", ctypes.c_int32),
+        ("num_envs", ctypes.c_int32), ("num_agents", ctypes.c_int32), ("num_npcs", ctypes.c_int32),
+        ("env_id_offset", ctypes.c_int32),
+        ("npc_kind", ctypes.c_int32), ("npc_ctrl", ctypes.c_int32), ("npc_dofs", ctypes.c_int32),
+        ("decimation", ctypes.c_int32), ("solver_iters", ctypes.c_int32), ("max_episode_length", ctypes.c_int32),
+        ("term_mask", ctypes.c_int32), ("quat_alias", ctypes.c_int32), ("policy_mode", ctypes.c_int32),
+        ("defender", ctypes.c_int32), ("command_vel", ctypes.c_int32),
+        ("sim_dt", ctypes.c_float), ("gravity_z", ctypes.c_float),
+        ("friction", ctypes.c_float), ("contact_offset", ctypes.c_float), ("max_depen_vel", ctypes.c_float),
+        ("erp", ctypes.c_float), ("cfm", ctypes.c_float),
+        ("floor_z", ctypes.c_float), ("wall_top_z", ctypes.c_float), ("limit_margin", ctypes.c_float),
+        ("term_roll", ctypes.c_float), ("term_pitch", ctypes.c_float), ("term_zlow", ctypes.c_float),
+        ("term_zhigh", ctypes.c_float),
+        ("act_scale", ctypes.c_float * 3), ("cmd_scale", ctypes.c_float * 3),
+        ("action_scale", ctypes.c_float), ("hip_scale", ctypes.c_float), ("clip_actions", ctypes.c_float),
+        ("loc_obs_default", ctypes.c_float * LOC_OBS),
+        ("dof_ratio_lo", ctypes.c_float), ("dof_ratio_hi", ctypes.c_float),
+        ("base_vel_lo", ctypes.c_float), ("base_vel_hi", ctypes.c_float),
+        ("has_base_pos_range", ctypes.c_int32), ("has_npc_pos_range", ctypes.c_int32),
+        ("has_npc_rpy_range", ctypes.c_int32), ("reserved1", ctypes.c_int32),
+        ("base_pos_x", ctypes.c_float * 2), ("base_pos_y", ctypes.c_float * 2),
+        ("npc_pos_x", ctypes.c_float * 2), ("npc_pos_y", ctypes.c_float * 2),
+        ("npc_rpy_r", ctypes.c_float * 2), ("npc_rpy_p", ctypes.c_float * 2), ("npc_rpy_y", ctypes.c_float * 2),
+        ("npc_mass", ctypes.c_float), ("npc_inertia", ctypes.c_float), ("npc_radius", ctypes.c_float),
+        ("npc_halflen", ctypes.c_float),
+        ("sheep_scale", ctypes.c_float), ("sheep_randomness", ctypes.c_float),
+        ("gate_x", ctypes.c_float), ("reserved2", ctypes.c_float),
+        ("seed", ctypes.c_uint64),
+        ("sdf_nx", ctypes.c_int32), ("sdf_ny", ctypes.c_int32), ("sdf_cell", ctypes.c_float), ("reserved3", ctypes.c_float),
+        ("h_sdf", _fp), ("h_env_origins", _fp), ("h_agent_origins", _fp), ("h_base_init_state", _fp),
+        ("h_npc_init_state", _fp), ("h_npc_dof_default", _fp),
+        ("model", RobotModelC),
+        ("weights", WeightsC),
+    ]
+
+
+def as_fp(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_fp)
+
+
+def load_weights(path=None):
+    """walk-these-ways + actuator-net weights (resources/walk_policy.npz, from tools/extract_assets.py)."""
+    path = path or os.path.join(PKG_DIR, "resources", "walk_policy.npz")
+    z = np.load(path)
+    arrays = {}
+    wc = WeightsC()
+    for field, key, shape in WEIGHT_FIELDS:
+        a = np.ascontiguousarray(z[key], dtype=np.float32)
+        assert a.shape == shape, (key, a.shape, shape)
+        arrays[field] = a
+        setattr(wc, field, as_fp(a))
+    return wc, arrays
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libmqe_b200.so and declare prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise EngineError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    lib.mqe_last_error.restype = ctypes.c_char_p
+    lib.mqe_abi_version.restype = i32
+    lib.mqe_device_count.restype = i32
+    lib.mqe_sim_create.argtypes = [ctypes.POINTER(SimDescC), i32, vp, ctypes.POINTER(vp)]
+    lib.mqe_sim_destroy.argtypes = [vp]
+    lib.mqe_sim_set_stream.argtypes = [vp, vp]
+    lib.mqe_sim_get_buffer.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_int32)]
+    lib.mqe_sim_reset.argtypes = [vp]
+    lib.mqe_sim_step.argtypes = [vp, vp]
+    lib.mqe_sim_step_host.argtypes = [vp, vp, vp, vp]
+    lib.mqe_sim_policy.argtypes = [vp, vp]
+    lib.mqe_sim_substeps.argtypes = [vp, i32]
+    lib.mqe_sim_post_physics.argtypes = [vp]
+    lib.mqe_sim_set_root_indexed.argtypes = [vp, vp, vp, i32]
+    lib.mqe_sim_set_dof_indexed.argtypes = [vp, vp, vp, i32]
+    lib.mqe_policy_forward.argtypes = [vp, vp, i32, vp, vp]
+    lib.mqe_actuator_forward.argtypes = [vp, vp, i32, vp]
+    lib.mqe_robot_dynamics.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.mqe_sim_synchronize.argtypes = [vp]
+    lib.mqe_sim_launch_count.argtypes = [vp]
+    lib.mqe_sim_launch_count.restype = i64
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "mqe_last_error", "mqe_abi_version", "mqe_device_count", "mqe_sim_create", "mqe_sim_destroy", "mqe_sim_set_stream",
+    "mqe_sim_get_buffer", "mqe_sim_reset", "mqe_sim_step", "mqe_sim_step_host", "mqe_sim_policy", "mqe_sim_substeps",
+    "mqe_sim_post_physics", "mqe_sim_set_root_indexed", "mqe_sim_set_dof_indexed", "mqe_policy_forward",
+    "mqe_actuator_forward", "mqe_robot_dynamics", "mqe_sim_synchronize", "mqe_sim_launch_count",
+]
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch.as_tensor can alias an engine-owned buffer."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+        self._owner = owner
+
+
+_TYPESTR = {("f", 4): "<f4", ("u", 1): "|u1", ("i", 8): "<i8", ("i", 4): "<i4", ("h", 2): "<u2"}
+_BUF_KIND = {BUF_RESET: "u", BUF_TIMEOUT: "u", BUF_COLLIDE: "u", BUF_ROLL_TERM: "u", BUF_PITCH_TERM: "u",
+             BUF_ZLOW_TERM: "u", BUF_ZHIGH_TERM: "u", BUF_EPISODE_LENGTH: "i", BUF_STATS: "i", BUF_HISTORY: "h"}
+
+
+class Engine:
+    """Owns one MqeSim handle (one process per GPU; `device` is the CUDA ordinal of this rank)."""
+
+    def __init__(self, desc: SimDescC, device: int = 0, stream: int | None = None, keepalive=None):
+        self.lib = load_library()
+        if self.lib.mqe_abi_version() != ABI_VERSION:
+            raise EngineError("libmqe_b200.so ABI version mismatch; rebuild")
+        self._keep = keepalive
+        self.desc = desc
+        self.device = device
+        h = ctypes.c_void_p()
+        self._check(self.lib.mqe_sim_create(ctypes.byref(desc), device, ctypes.c_void_p(stream or 0), ctypes.byref(h)))
+        self.h = h
+        self._views = {}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(f"mqe error {rc}: {self.lib.mqe_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mqe_sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- buffers -------------------------------------------------------------------------------------
+    def buffer_info(self, which):
+        ptr = ctypes.c_void_p()
+        shape = (ctypes.c_int64 * 4)()
+        es = ctypes.c_int32()
+        self._check(self.lib.mqe_sim_get_buffer(self.h, which, ctypes.byref(ptr), shape, ctypes.byref(es)))
+        dims = [int(s) for s in shape if s > 0]
+        return ptr.value, dims, es.value
+
+    def tensor(self, which):
+        """Zero-copy torch view of an engine buffer (gymtorch.wrap_tensor equivalent)."""
+        import torch
+        if which not in self._views:
+            ptr, dims, es = self.buffer_info(which)
+            kind = _BUF_KIND.get(which, "f")
+            arr = _DevArray(ptr, dims, _TYPESTR[(kind, es)], self)
+            self._views[which] = torch.as_tensor(arr, device=f"cuda:{self.device}")
+        return self._views[which]
+
+    # -- stepping ------------------------------------------------------------------------------------
+    def reset(self):
+        self._check(self.lib.mqe_sim_reset(self.h))
+
+    def step(self, actions_ptr: int):
+        self._check(self.lib.mqe_sim_step(self.h, ctypes.c_void_p(actions_ptr)))
+
+    def step_host(self, h_actions: np.ndarray, h_obs: np.ndarray | None, h_reset: np.ndarray | None):
+        self._check(self.lib.mqe_sim_step_host(
+            self.h, h_actions.ctypes.data_as(ctypes.c_void_p),
+            h_obs.ctypes.data_as(ctypes.c_void_p) if h_obs is not None else None,
+            h_reset.ctypes.data_as(ctypes.c_void_p) if h_reset is not None else None))
+
+    def policy(self, actions_ptr: int):
+        self._check(self.lib.mqe_sim_policy(self.h, ctypes.c_void_p(actions_ptr)))
+
+    def substeps(self, count: int):
+        self._check(self.lib.mqe_sim_substeps(self.h, count))
+
+    def post_physics(self):
+        self._check(self.lib.mqe_sim_post_physics(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.mqe_sim_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.mqe_sim_launch_count(self.h))
+
+    def set_stream(self, stream: int):
+        self._check(self.lib.mqe_sim_set_stream(self.h, ctypes.c_void_p(stream)))
