@@ -147,7 +147,7 @@ typedef enum {
     MQE_BUF_LOC_OBS,            /* f32 [N*A][70]                            */
     MQE_BUF_LOC_ACTION,         /* f32 [N*A][12]  raw policy output (last_locomotion_action) */
     MQE_BUF_GAIT,               /* f32 [N*A]                                */
-    MQE_BUF_HISTORY,            /* bf16 hi/lo ring, engine-internal layout  */
+    MQE_BUF_HISTORY,            /* f32 [N*A][30][80] frame ring, see mqe_sim_history_head */
     MQE_BUF_SHEEP_STATS,        /* f32 [N][3]     sheep_pos_avg xy, sheep_pos_var */
     MQE_BUF_STATS,              /* i32 [8]        contact / row statistics of the last step */
     MQE_BUF_COUNT
@@ -175,6 +175,10 @@ int mqe_device_count(void);
 int mqe_sim_create(const MqeSimDesc *desc, int device, void *stream, MqeSim **out);
 int mqe_sim_destroy(MqeSim *sim);
 int mqe_sim_set_stream(MqeSim *sim, void *stream);
+/* Scale applied to incoming actions after clip(+-1) and before Go1.step's own clip(+-1): [2,.5,.5] when the caller
+ * is a task wrapper handing over raw policy actions (wrappers/go1_*_wrapper.py step()), [1,1,1] when the caller is
+ * Go1.step() itself and the wrapper has already scaled (go1.py:38). */
+int mqe_sim_set_action_scale(MqeSim *sim, const float scale[3]);
 
 /* gym.acquire_*_tensor (legged_robot.py:554-557).  shape[4] is zero padded; elem_size in bytes. */
 int mqe_sim_get_buffer(MqeSim *sim, int which, void **d_ptr, int64_t shape[4], int32_t *elem_size);
@@ -209,8 +213,8 @@ int mqe_sim_set_dof_indexed(MqeSim *sim, const float *d_dof_states, const int32_
 int mqe_policy_forward(MqeSim *sim, const float *d_history /* [rows][2100] */, int rows,
                        float *d_latent /* [rows][2] */, float *d_action /* [rows][12] */);
 int mqe_actuator_forward(MqeSim *sim, const float *d_x /* [rows][6] */, int rows, float *d_torque);
-int mqe_robot_dynamics(MqeSim *sim, const float *d_q /* [rows][7+12] pos-less: quat4? see .cu */,
-                       const float *d_v, const float *d_tau, int rows, float *d_qdd);
+/* slot of the 30-frame history ring that holds the newest frame (MQE_BUF_HISTORY is [N*A][30][80], slot-major) */
+int mqe_sim_history_head(MqeSim *sim);
 
 int mqe_sim_synchronize(MqeSim *sim);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */

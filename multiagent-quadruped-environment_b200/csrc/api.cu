@@ -1,0 +1,457 @@
+// api.cu -- the C ABI of libmqe_b200.so (include/mqe_b200.h): engine handle, engine-owned device buffers, and the
+// step / reset entry points that stand where the Isaac Gym tensor API stood in the reference
+// (mqe/envs/go1/go1.py:35-62, mqe/envs/base/legged_robot.py:117-157, 394-470, 549-595).
+// No CPU path exists behind these calls: without an sm_100 device mqe_sim_create fails with MQE_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(MQE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+    } while (0)
+
+struct BufInfo { void *ptr; int64_t shape[4]; int32_t elem; };
+
+struct MqeSim {
+    DevParams p;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int M = 0, actrl = 0, maxpair = MQE_MAX_PAIR;
+    std::vector<void *> allocs;
+    BufInfo bufs[MQE_BUF_COUNT];
+    PolicyWeightsDev pw;
+    PolicyScratch ps;
+    PolicyTcWeights tcw = {nullptr, 0, nullptr, nullptr};
+    unsigned int *pair_table = nullptr;
+    int n_pair = 0;
+    unsigned int step_count = 0;
+    int head = MQE_HIST_FRAMES - 1;      // slot of the newest frame; the next frame goes to (head + 1) % 30
+    long long launches = 0;
+    float *d_actions_stage = nullptr;
+    float *h_actions = nullptr, *h_obs = nullptr;
+    unsigned char *h_reset = nullptr;
+    float *tmp_ring = nullptr;
+    unsigned short *tmp_hi = nullptr, *tmp_lo = nullptr;
+    int tmp_rows = 0;
+};
+
+template <typename T>
+static cudaError_t dalloc(MqeSim *s, T **out, size_t n, bool zero = true) {
+    void *ptr = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e != cudaSuccess) return e;
+    s->allocs.push_back(ptr);
+    if (zero) { e = cudaMemsetAsync(ptr, 0, bytes, s->stream); if (e != cudaSuccess) return e; }
+    *out = (T *)ptr;
+    return cudaSuccess;
+}
+template <typename T>
+static cudaError_t dupload(MqeSim *s, const T **out, const T *h, size_t n) {
+    T *d = nullptr;
+    cudaError_t e = dalloc(s, &d, n, false);
+    if (e != cudaSuccess) return e;
+    *out = d;
+    // pageable source: cudaMemcpyAsync stages it before returning
+    return cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s->stream);
+}
+static void set_buf(MqeSim *s, int which, void *ptr, int elem, int64_t a, int64_t b = 0, int64_t c = 0, int64_t d = 0) {
+    s->bufs[which].ptr = ptr; s->bufs[which].elem = elem;
+    s->bufs[which].shape[0] = a; s->bufs[which].shape[1] = b; s->bufs[which].shape[2] = c; s->bufs[which].shape[3] = d;
+}
+
+extern "C" {
+
+const char *mqe_last_error(void) { return g_err.c_str(); }
+int mqe_abi_version(void) { return MQE_ABI_VERSION; }
+int mqe_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int mqe_sim_destroy(MqeSim *s) {
+    if (!s) return MQE_OK;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    for (void *ptr : s->allocs) cudaFree(ptr);
+    if (s->tcw.blob) cudaFree(s->tcw.blob);
+    if (s->h_actions) cudaFreeHost(s->h_actions);
+    if (s->h_obs) cudaFreeHost(s->h_obs);
+    if (s->h_reset) cudaFreeHost(s->h_reset);
+    if (s->tmp_ring) cudaFree(s->tmp_ring);
+    if (s->tmp_hi) cudaFree(s->tmp_hi);
+    if (s->tmp_lo) cudaFree(s->tmp_lo);
+    delete s;
+    return MQE_OK;
+}
+
+static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MQE_ERR_NO_DEVICE, "no CUDA device visible; libmqe_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(MQE_ERR_INVALID, "device ordinal out of range");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(MQE_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", kernels are built for sm_100a only");
+    CK(cudaSetDevice(device));
+    s->device = device;
+    s->stream = (cudaStream_t)stream;
+    const int N = d->num_envs, A = d->num_agents, P = d->num_npcs, D = d->npc_dofs, G = A + P, M = N * A;
+    if (N <= 0 || A <= 0 || A > 4 || P < 0 || P > 12) return fail(MQE_ERR_INVALID, "num_envs/num_agents/num_npcs out of range (A <= 4, P <= 12)");
+    if (d->defender && !(A == 3 && P >= 1)) return fail(MQE_ERR_INVALID, "defender needs 3 agents and the ball");
+    s->M = M;
+    s->actrl = d->defender ? A - 1 : A;
+    DevParams &p = s->p;
+    memset(&p, 0, sizeof p);
+    p.N = N; p.A = A; p.P = P; p.D = D; p.G = G;
+    p.Pd = (d->npc_kind == MQE_NPC_RIGID) ? P : 0;
+    p.env_off = d->env_id_offset;
+    p.npc_kind = d->npc_kind; p.npc_ctrl = d->npc_ctrl;
+    p.decimation = d->decimation; p.iters = d->solver_iters; p.max_ep_len = d->max_episode_length;
+    p.term_mask = d->term_mask; p.quat_alias = d->quat_alias; p.defender = d->defender; p.command_vel = d->command_vel;
+    p.policy_mode = d->policy_mode;
+    const int lanes = 4 * A + p.Pd;
+    if (lanes > 32) return fail(MQE_ERR_UNSUPPORTED, "4*num_agents + dynamic npcs must fit one warp");
+    p.E = 32 / lanes;
+    p.NB = MQE_NUM_BODIES * A + P;
+    p.dt = d->sim_dt; p.gz = d->gravity_z; p.mu = d->friction; p.coff = d->contact_offset; p.vdep = d->max_depen_vel;
+    p.erp = d->erp; p.cfm = d->cfm; p.floor_z = d->floor_z; p.wall_top = d->wall_top_z; p.limit_margin = d->limit_margin;
+    p.term_roll = d->term_roll; p.term_pitch = d->term_pitch; p.term_zlow = d->term_zlow; p.term_zhigh = d->term_zhigh;
+    for (int i = 0; i < 3; i++) { p.act_scale[i] = d->act_scale[i]; p.cmd_scale[i] = d->cmd_scale[i]; }
+    p.action_scale = d->action_scale; p.hip_scale = d->hip_scale; p.clip_actions = d->clip_actions;
+    p.dof_lo = d->dof_ratio_lo; p.dof_hi = d->dof_ratio_hi; p.bvel_lo = d->base_vel_lo; p.bvel_hi = d->base_vel_hi;
+    p.has_bpos = d->has_base_pos_range; p.has_npos = d->has_npc_pos_range; p.has_nrpy = d->has_npc_rpy_range;
+    for (int i = 0; i < 2; i++) {
+        p.bpos_x[i] = d->base_pos_x[i]; p.bpos_y[i] = d->base_pos_y[i]; p.npos_x[i] = d->npc_pos_x[i]; p.npos_y[i] = d->npc_pos_y[i];
+        p.nrpy_r[i] = d->npc_rpy_r[i]; p.nrpy_p[i] = d->npc_rpy_p[i]; p.nrpy_y[i] = d->npc_rpy_y[i];
+    }
+    p.npc_mass = d->npc_mass; p.npc_inertia = d->npc_inertia; p.npc_radius = d->npc_radius; p.npc_halflen = d->npc_halflen;
+    p.sheep_scale = d->sheep_scale; p.sheep_rand = d->sheep_randomness; p.gate_x = d->gate_x;
+    p.seed = d->seed;
+    p.sdf_nx = d->sdf_nx; p.sdf_ny = d->sdf_ny; p.sdf_cell = d->sdf_cell;
+    if (!d->h_sdf || !d->h_env_origins || !d->h_agent_origins || !d->h_base_init_state) return fail(MQE_ERR_INVALID, "descriptor host arrays missing");
+    if (P && !d->h_npc_init_state) return fail(MQE_ERR_INVALID, "h_npc_init_state missing");
+    if (mqe_substeps_smem_bytes(A, p.Pd, p.E, s->maxpair) > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(MQE_ERR_UNSUPPORTED, "substep kernel working set exceeds shared memory for this A/P");
+
+    // ---- constants ----
+    CK(dupload(s, &p.sdf, d->h_sdf, (size_t)d->sdf_nx * d->sdf_ny));
+    CK(dupload(s, &p.env_origins, d->h_env_origins, (size_t)N * 3));
+    CK(dupload(s, &p.agent_origins, d->h_agent_origins, (size_t)M * 3));
+    CK(dupload(s, &p.base_init, d->h_base_init_state, (size_t)M * 13));
+    if (P) CK(dupload(s, &p.npc_init, d->h_npc_init_state, (size_t)N * P * 13));
+    {
+        std::vector<float> nd(D > 0 ? D : 1, 0.f);
+        if (D && d->h_npc_dof_default) memcpy(nd.data(), d->h_npc_dof_default, D * sizeof(float));
+        CK(dupload(s, &p.npc_dof_default, nd.data(), nd.size()));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    CK(dupload(s, &p.model, &d->model, 1));
+    CK(dupload(s, &p.loc_default, d->loc_obs_default, MQE_LOC_OBS));
+    const MqeWeights &w = d->weights;
+    for (const float *const *pp = (const float *const *)&w; pp < (const float *const *)(&w + 1); pp++)
+        if (!*pp) return fail(MQE_ERR_INVALID, "weights pointer missing");
+    {
+        std::vector<float> aw(1316, 0.f);
+        memcpy(aw.data(), w.act_w0, 192 * 4); memcpy(aw.data() + 192, w.act_b0, 32 * 4);
+        memcpy(aw.data() + 224, w.act_w1, 1024 * 4); memcpy(aw.data() + 1248, w.act_b1, 32 * 4);
+        memcpy(aw.data() + 1280, w.act_w2, 32 * 4); aw[1312] = w.act_b2[0];
+        CK(dupload(s, &p.act_w, aw.data(), aw.size()));
+        // layer 0 of both networks, age-blocked and padded: [768][30][80]
+        const int RR = MQE_HIST_FRAMES * MQE_HIST_PAD;
+        std::vector<float> w0((size_t)768 * RR, 0.f), b0(768), wl(512 * 2);
+        for (int n = 0; n < 768; n++) {
+            const float *src = n < 256 ? w.adapt_w0 + (size_t)n * 2100 : w.body_w0 + (size_t)(n - 256) * 2102;
+            for (int b = 0; b < MQE_HIST_FRAMES; b++)
+                memcpy(&w0[(size_t)n * RR + b * MQE_HIST_PAD], src + b * MQE_LOC_OBS, MQE_LOC_OBS * sizeof(float));
+            b0[n] = n < 256 ? w.adapt_b0[n] : w.body_b0[n - 256];
+            if (n >= 256) { wl[(n - 256) * 2] = src[2100]; wl[(n - 256) * 2 + 1] = src[2101]; }
+        }
+        CK(dupload(s, &s->pw.w0cat, w0.data(), w0.size()));
+        CK(dupload(s, &s->pw.b0cat, b0.data(), b0.size()));
+        CK(dupload(s, &s->pw.wlat, wl.data(), wl.size()));
+        CK(dupload(s, &s->pw.aw1, w.adapt_w1, 128 * 256)); CK(dupload(s, &s->pw.ab1, w.adapt_b1, 128));
+        CK(dupload(s, &s->pw.aw2, w.adapt_w2, 2 * 128)); CK(dupload(s, &s->pw.ab2, w.adapt_b2, 2));
+        CK(dupload(s, &s->pw.bw1, w.body_w1, 256 * 512)); CK(dupload(s, &s->pw.bb1, w.body_b1, 256));
+        CK(dupload(s, &s->pw.bw2, w.body_w2, 128 * 256)); CK(dupload(s, &s->pw.bb2, w.body_b2, 128));
+        CK(dupload(s, &s->pw.bw3, w.body_w3, 12 * 128)); CK(dupload(s, &s->pw.bb3, w.body_b3, 12));
+        CK(cudaStreamSynchronize(s->stream));     // host staging vectors go out of scope
+    }
+    if (p.policy_mode != MQE_POLICY_FP32) {
+        int rc = mqe_policy_tc_prepare(&w, &s->tcw, s->stream);
+        if (rc != 0) return fail(MQE_ERR_CUDA, "tensor-core policy weight preparation failed");
+    }
+    // pair table: groups X < Y, capsule i of X, capsule j of Y -- the oracle's loop order (mqe_oracle.c env_substep)
+    {
+        std::vector<unsigned int> pt;
+        const int Gd = A + p.Pd, nc = d->model.n_caps;
+        for (int X = 0; X < Gd; X++)
+            for (int Y = X + 1; Y < Gd; Y++) {
+                int nx = X < A ? nc : 1, ny = Y < A ? nc : 1;
+                for (int i = 0; i < nx; i++)
+                    for (int j = 0; j < ny; j++) pt.push_back((unsigned)X | ((unsigned)i << 8) | ((unsigned)Y << 16) | ((unsigned)j << 24));
+            }
+        s->n_pair = (int)pt.size();
+        const unsigned int *dpt = nullptr;
+        if (pt.empty()) pt.push_back(0u);
+        CK(dupload(s, &dpt, pt.data(), pt.size()));
+        CK(cudaStreamSynchronize(s->stream));
+        s->pair_table = const_cast<unsigned int *>(dpt);
+    }
+
+    // ---- state ----
+    CK(dalloc(s, &p.root, (size_t)N * G * 13)); CK(dalloc(s, &p.dof, (size_t)N * (12 * A + D) * 2));
+    CK(dalloc(s, &p.contact, (size_t)N * p.NB * 3));
+    CK(dalloc(s, &p.torques, (size_t)M * 12)); CK(dalloc(s, &p.actions, (size_t)M * 12)); CK(dalloc(s, &p.last_actions, (size_t)M * 12));
+    CK(dalloc(s, &p.loc_last, (size_t)M * 12)); CK(dalloc(s, &p.loc_last2, (size_t)M * 12)); CK(dalloc(s, &p.loc_obs, (size_t)M * MQE_LOC_OBS));
+    CK(dalloc(s, &p.err1, (size_t)M * 12)); CK(dalloc(s, &p.err2, (size_t)M * 12)); CK(dalloc(s, &p.vel1, (size_t)M * 12)); CK(dalloc(s, &p.vel2, (size_t)M * 12));
+    CK(dalloc(s, &p.gait, (size_t)M)); CK(dalloc(s, &p.clock, (size_t)M * 4));
+    CK(dalloc(s, &p.base_quat, (size_t)M * 4)); CK(dalloc(s, &p.base_lin_vel, (size_t)M * 3)); CK(dalloc(s, &p.base_ang_vel, (size_t)M * 3));
+    CK(dalloc(s, &p.proj_grav, (size_t)M * 3)); CK(dalloc(s, &p.obs, (size_t)M * MQE_OBS_FLOATS)); CK(dalloc(s, &p.commands, (size_t)M * 3));
+    CK(dalloc(s, &p.last_dof_vel, (size_t)M * 12)); CK(dalloc(s, &p.last_root_vel, (size_t)M * 6)); CK(dalloc(s, &p.sheep_stats, (size_t)N * 3));
+    CK(dalloc(s, &p.ep_len, (size_t)N));
+    CK(dalloc(s, &p.reset_buf, (size_t)N)); CK(dalloc(s, &p.timeout_buf, (size_t)N)); CK(dalloc(s, &p.collide_buf, (size_t)N));
+    CK(dalloc(s, &p.r_term, (size_t)N)); CK(dalloc(s, &p.p_term, (size_t)N)); CK(dalloc(s, &p.zl_term, (size_t)N)); CK(dalloc(s, &p.zh_term, (size_t)N));
+    CK(dalloc(s, &p.episode, (size_t)N)); CK(dalloc(s, &p.hist_dirty, (size_t)N)); CK(dalloc(s, &p.stats, (size_t)8));
+    const size_t ring = (size_t)M * MQE_HIST_FRAMES * MQE_HIST_PAD;
+    CK(dalloc(s, &p.hist_f32, ring));
+    const size_t ring_tc = (size_t)((M + 127) / 128) * 128 * MQE_HIST_FRAMES * MQE_HIST_PAD;     // pre-tiled planes, rows padded to 128
+    if (p.policy_mode != MQE_POLICY_FP32) { CK(dalloc(s, &p.hist_hi, ring_tc)); CK(dalloc(s, &p.hist_lo, ring_tc)); }
+    CK(dalloc(s, &s->ps.Z, (size_t)M * 768)); CK(dalloc(s, &s->ps.T1, (size_t)M * 128)); CK(dalloc(s, &s->ps.T2, (size_t)M * 256));
+    CK(dalloc(s, &s->ps.T3, (size_t)M * 128)); CK(dalloc(s, &s->ps.latent, (size_t)M * 2)); CK(dalloc(s, &s->ps.act, (size_t)M * 12));
+    CK(dalloc(s, &s->d_actions_stage, (size_t)N * s->actrl * 3));
+    CK(cudaMemsetAsync(p.reset_buf, 1, N, s->stream));                      // base_task.py:77: reset_buf starts as ones
+    // _prepare_locomotion_policy: locomotion_obs = default command frame (go1.py:393-394); actors at their start poses
+    {
+        std::vector<float> lo((size_t)M * MQE_LOC_OBS), root((size_t)N * G * 13, 0.f), dof((size_t)N * (12 * A + D) * 2, 0.f);
+        for (int m = 0; m < M; m++) memcpy(&lo[(size_t)m * MQE_LOC_OBS], d->loc_obs_default, MQE_LOC_OBS * sizeof(float));
+        for (int e = 0; e < N; e++) {
+            for (int a = 0; a < A; a++) {
+                float *r = &root[((size_t)e * G + a) * 13];
+                for (int i = 0; i < 13; i++) r[i] = d->h_base_init_state[(e * A + a) * 13 + i];
+                for (int i = 0; i < 3; i++) r[i] += d->h_agent_origins[(e * A + a) * 3 + i];
+                for (int j = 0; j < 12; j++) dof[((size_t)e * (12 * A + D) + 12 * a + j) * 2] = d->model.q_default[j];
+            }
+            for (int n = 0; n < P; n++) {
+                float *r = &root[((size_t)e * G + A + n) * 13];
+                for (int i = 0; i < 13; i++) r[i] = d->h_npc_init_state[(e * P + n) * 13 + i];
+                for (int i = 0; i < 3; i++) r[i] += d->h_env_origins[e * 3 + i];
+            }
+        }
+        CK(cudaMemcpyAsync(p.loc_obs, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(p.root, root.data(), root.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(p.dof, dof.data(), dof.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    CK(cudaMallocHost(&s->h_actions, (size_t)N * s->actrl * 3 * sizeof(float)));
+    CK(cudaMallocHost(&s->h_obs, (size_t)M * MQE_OBS_FLOATS * sizeof(float)));
+    CK(cudaMallocHost(&s->h_reset, (size_t)N));
+
+    set_buf(s, MQE_BUF_ROOT_STATES, p.root, 4, N, G, 13);
+    set_buf(s, MQE_BUF_DOF_STATES, p.dof, 4, N, 12 * A + D, 2);
+    set_buf(s, MQE_BUF_CONTACT_FORCES, p.contact, 4, N, p.NB, 3);
+    set_buf(s, MQE_BUF_TORQUES, p.torques, 4, N, 12 * A);
+    set_buf(s, MQE_BUF_ACTIONS, p.actions, 4, N, 12 * A);
+    set_buf(s, MQE_BUF_LAST_ACTIONS, p.last_actions, 4, N, 12 * A);
+    set_buf(s, MQE_BUF_OBS, p.obs, 4, M, MQE_OBS_FLOATS);
+    set_buf(s, MQE_BUF_BASE_LIN_VEL, p.base_lin_vel, 4, M, 3);
+    set_buf(s, MQE_BUF_BASE_ANG_VEL, p.base_ang_vel, 4, M, 3);
+    set_buf(s, MQE_BUF_PROJ_GRAVITY, p.proj_grav, 4, M, 3);
+    set_buf(s, MQE_BUF_RESET, p.reset_buf, 1, N);
+    set_buf(s, MQE_BUF_TIMEOUT, p.timeout_buf, 1, N);
+    set_buf(s, MQE_BUF_COLLIDE, p.collide_buf, 1, N);
+    set_buf(s, MQE_BUF_ROLL_TERM, p.r_term, 1, N);
+    set_buf(s, MQE_BUF_PITCH_TERM, p.p_term, 1, N);
+    set_buf(s, MQE_BUF_ZLOW_TERM, p.zl_term, 1, N);
+    set_buf(s, MQE_BUF_ZHIGH_TERM, p.zh_term, 1, N);
+    set_buf(s, MQE_BUF_EPISODE_LENGTH, p.ep_len, 8, N);
+    set_buf(s, MQE_BUF_COMMANDS, p.commands, 4, M, 3);
+    set_buf(s, MQE_BUF_LOC_OBS, p.loc_obs, 4, M, MQE_LOC_OBS);
+    set_buf(s, MQE_BUF_LOC_ACTION, p.loc_last, 4, M, 12);
+    set_buf(s, MQE_BUF_GAIT, p.gait, 4, M);
+    set_buf(s, MQE_BUF_HISTORY, p.hist_f32, 4, M, MQE_HIST_FRAMES, MQE_HIST_PAD);
+    set_buf(s, MQE_BUF_SHEEP_STATS, p.sheep_stats, 4, N, 3);
+    set_buf(s, MQE_BUF_STATS, p.stats, 4, 8);
+    return MQE_OK;
+}
+
+int mqe_sim_create(const MqeSimDesc *desc, int device, void *stream, MqeSim **out) {
+    if (!desc || !out) return fail(MQE_ERR_INVALID, "null argument");
+    if (desc->abi_version != MQE_ABI_VERSION) return fail(MQE_ERR_INVALID, "descriptor abi_version mismatch");
+    MqeSim *s = new MqeSim();
+    int rc = create_impl(desc, device, stream, s);
+    if (rc != MQE_OK) { std::string keep = g_err; mqe_sim_destroy(s); g_err = keep; *out = nullptr; return rc; }
+    *out = s;
+    return MQE_OK;
+}
+
+int mqe_sim_set_stream(MqeSim *s, void *stream) {
+    if (!s) return fail(MQE_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    s->stream = (cudaStream_t)stream;
+    return MQE_OK;
+}
+
+int mqe_sim_set_action_scale(MqeSim *s, const float scale[3]) {
+    if (!s || !scale) return fail(MQE_ERR_INVALID, "null argument");
+    for (int i = 0; i < 3; i++) s->p.act_scale[i] = scale[i];
+    return MQE_OK;
+}
+
+int mqe_sim_get_buffer(MqeSim *s, int which, void **d_ptr, int64_t shape[4], int32_t *elem_size) {
+    if (!s || which < 0 || which >= MQE_BUF_COUNT) return fail(MQE_ERR_INVALID, "bad buffer id");
+    if (d_ptr) *d_ptr = s->bufs[which].ptr;
+    if (shape) for (int i = 0; i < 4; i++) shape[i] = s->bufs[which].shape[i];
+    if (elem_size) *elem_size = s->bufs[which].elem;
+    return MQE_OK;
+}
+
+int mqe_sim_history_head(MqeSim *s) { return s ? s->head : -1; }
+
+int mqe_sim_reset(MqeSim *s) {
+    if (!s) return fail(MQE_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(s->device));
+    CK(mqe_launch_reset_all(s->p, s->stream));
+    s->launches += 1;
+    return MQE_OK;
+}
+
+static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, const unsigned short *lo, int head, int rows, float *latent, float *act) {
+    PolicyScratch ps = s->ps;
+    ps.latent = latent; ps.act = act;
+    if (s->p.policy_mode == MQE_POLICY_FP32)
+        CK(mqe_launch_policy_l0_fp32(s->pw, ps, ring, head, rows, s->stream));
+    else
+        CK(mqe_launch_policy_l0_tc(s->tcw, s->pw.b0cat, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, ps.Z, s->stream));
+    int n = 1;
+    CK(mqe_launch_policy_tail(s->pw, ps, rows, s->stream, &n));
+    s->launches += n;
+    return MQE_OK;
+}
+
+int mqe_sim_policy(MqeSim *s, const float *d_actions) {
+    if (!s || !d_actions) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    s->head = (s->head + 1) % MQE_HIST_FRAMES;
+    CK(mqe_launch_policy_frame(s->p, d_actions, s->head, s->stream));
+    int rc = run_network(s, s->p.hist_f32, s->p.hist_hi, s->p.hist_lo, s->head, s->M, s->ps.latent, s->ps.act);
+    if (rc != MQE_OK) return rc;
+    CK(mqe_launch_policy_finish(s->p, s->ps.act, s->stream));
+    s->launches += 2;
+    return MQE_OK;
+}
+
+int mqe_sim_substeps(MqeSim *s, int count) {
+    if (!s || count <= 0) return fail(MQE_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaMemsetAsync(s->p.stats, 0, 8 * sizeof(int), s->stream));
+    CK(mqe_launch_substeps(s->p, count, s->maxpair, s->pair_table, s->n_pair, s->stream));
+    s->launches += 1;
+    return MQE_OK;
+}
+
+int mqe_sim_post_physics(MqeSim *s) {
+    if (!s) return fail(MQE_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(s->device));
+    CK(mqe_launch_post(s->p, s->step_count, s->stream));
+    s->step_count++;
+    s->launches += 1;
+    return MQE_OK;
+}
+
+int mqe_sim_step(MqeSim *s, const float *d_actions) {
+    int rc = mqe_sim_policy(s, d_actions);
+    if (rc != MQE_OK) return rc;
+    rc = mqe_sim_substeps(s, s->p.decimation);
+    if (rc != MQE_OK) return rc;
+    return mqe_sim_post_physics(s);
+}
+
+int mqe_sim_step_host(MqeSim *s, const float *h_actions, float *h_obs, uint8_t *h_reset) {
+    if (!s || !h_actions) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    const size_t na = (size_t)s->p.N * s->actrl * 3 * sizeof(float);
+    memcpy(s->h_actions, h_actions, na);
+    CK(cudaMemcpyAsync(s->d_actions_stage, s->h_actions, na, cudaMemcpyHostToDevice, s->stream));
+    int rc = mqe_sim_step(s, s->d_actions_stage);
+    if (rc != MQE_OK) return rc;
+    const size_t no = (size_t)s->M * MQE_OBS_FLOATS * sizeof(float);
+    if (h_obs) CK(cudaMemcpyAsync(s->h_obs, s->p.obs, no, cudaMemcpyDeviceToHost, s->stream));
+    if (h_reset) CK(cudaMemcpyAsync(s->h_reset, s->p.reset_buf, s->p.N, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (h_obs) memcpy(h_obs, s->h_obs, no);
+    if (h_reset) memcpy(h_reset, s->h_reset, s->p.N);
+    return MQE_OK;
+}
+
+int mqe_sim_set_root_indexed(MqeSim *s, const float *d_root_states, const int32_t *d_actor_ids, int n) {
+    if (!s || !d_root_states || !d_actor_ids) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    if (d_root_states == s->p.root) return MQE_OK;         // the wrapped view IS the engine state
+    CK(mqe_launch_set_root_indexed(s->p, d_root_states, d_actor_ids, n, s->stream));
+    s->launches += 1;
+    return MQE_OK;
+}
+int mqe_sim_set_dof_indexed(MqeSim *s, const float *d_dof_states, const int32_t *d_actor_ids, int n) {
+    if (!s || !d_dof_states || !d_actor_ids) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    if (d_dof_states == s->p.dof) return MQE_OK;
+    CK(mqe_launch_set_dof_indexed(s->p, d_dof_states, d_actor_ids, n, s->stream));
+    s->launches += 1;
+    return MQE_OK;
+}
+
+int mqe_policy_forward(MqeSim *s, const float *d_history, int rows, float *d_latent, float *d_action) {
+    if (!s || !d_history || !d_action || rows <= 0) return fail(MQE_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(s->device));
+    if (rows > s->M) return fail(MQE_ERR_INVALID, "rows exceeds num_envs*num_agents (scratch is sized for the simulation)");
+    const size_t ring = (size_t)rows * MQE_HIST_FRAMES * MQE_HIST_PAD;
+    if (rows > s->tmp_rows) {
+        CK(cudaStreamSynchronize(s->stream));
+        if (s->tmp_ring) cudaFree(s->tmp_ring);
+        if (s->tmp_hi) cudaFree(s->tmp_hi);
+        if (s->tmp_lo) cudaFree(s->tmp_lo);
+        s->tmp_ring = nullptr; s->tmp_hi = s->tmp_lo = nullptr; s->tmp_rows = 0;
+        CK(cudaMalloc(&s->tmp_ring, ring * sizeof(float)));
+        if (s->p.policy_mode != MQE_POLICY_FP32) {
+            const size_t rtc = (size_t)((rows + 127) / 128) * 128 * MQE_HIST_FRAMES * MQE_HIST_PAD * 2;
+            CK(cudaMalloc(&s->tmp_hi, rtc)); CK(cudaMalloc(&s->tmp_lo, rtc));
+            CK(cudaMemsetAsync(s->tmp_hi, 0, rtc, s->stream)); CK(cudaMemsetAsync(s->tmp_lo, 0, rtc, s->stream));
+        }
+        s->tmp_rows = rows;
+    }
+    CK(mqe_launch_history_to_ring(d_history, s->tmp_ring, s->tmp_hi, s->tmp_lo, rows, s->stream));
+    s->launches += 1;
+    float *lat = d_latent ? d_latent : s->ps.latent;
+    return run_network(s, s->tmp_ring, s->tmp_hi, s->tmp_lo, MQE_HIST_FRAMES - 1, rows, lat, d_action);
+}
+
+int mqe_actuator_forward(MqeSim *s, const float *d_x, int rows, float *d_torque) {
+    if (!s || !d_x || !d_torque || rows <= 0) return fail(MQE_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(s->device));
+    CK(mqe_launch_actuator(s->p.act_w, d_x, rows, d_torque, s->stream));
+    s->launches += 1;
+    return MQE_OK;
+}
+
+int mqe_sim_synchronize(MqeSim *s) {
+    if (!s) return fail(MQE_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    return MQE_OK;
+}
+int64_t mqe_sim_launch_count(MqeSim *s) { return s ? s->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// kernels.cuh -- host-side launcher prototypes shared between the kernel translation units and api.cu.
+#pragma once
+#include "common.cuh"
+
+struct PolicyWeightsDev {           // device copies laid out for the kernels (api.cu builds them)
+    const float *w0cat;             // [768][30][80]  rows 0..255 adapt.0, 256..767 body.0[:, :2100]; age blocks padded 70 -> 80
+    const float *b0cat;             // [768]
+    const float *wlat;              // [512][2]      body.0[:, 2100:2102]  (the latent columns of cat(h, latent))
+    const float *aw1, *ab1, *aw2, *ab2;                         // adapt [128][256], [2][128]
+    const float *bw1, *bb1, *bw2, *bb2, *bw3, *bb3;             // body  [256][512], [128][256], [12][128]
+};
+struct PolicyTcWeights { void *blob; size_t bytes; const void *l0_hi, *l0_lo; };   // bf16 hi/lo planes, pre-tiled (policy_tc.cu)
+struct PolicyScratch { float *Z, *T1, *T2, *T3, *latent, *act; };
+
+extern "C" {
+cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, const unsigned int *pair_table, int n_pair_entries, cudaStream_t st);
+cudaError_t mqe_launch_post(const DevParams &p, unsigned int step_count, cudaStream_t st);
+cudaError_t mqe_launch_reset_all(const DevParams &p, cudaStream_t st);
+cudaError_t mqe_launch_set_root_indexed(const DevParams &p, const float *src, const int *ids, int n, cudaStream_t st);
+cudaError_t mqe_launch_set_dof_indexed(const DevParams &p, const float *src, const int *ids, int n, cudaStream_t st);
+cudaError_t mqe_launch_policy_frame(const DevParams &p, const float *d_actions, int head, cudaStream_t st);
+cudaError_t mqe_launch_policy_finish(const DevParams &p, const float *act, cudaStream_t st);
+cudaError_t mqe_launch_policy_l0_fp32(const PolicyWeightsDev &w, const PolicyScratch &s, const float *ring, int head, int M, cudaStream_t st);
+cudaError_t mqe_launch_policy_tail(const PolicyWeightsDev &w, const PolicyScratch &s, int M, cudaStream_t st, int *launches);
+cudaError_t mqe_launch_history_to_ring(const float *hist, float *ring, unsigned short *hi, unsigned short *lo, int rows, cudaStream_t st);
+cudaError_t mqe_launch_actuator(const float *act_w, const float *x, int rows, float *out, cudaStream_t st);
+// tensor-core policy layer 0 (policy_tc.cu)
+int mqe_policy_tc_prepare(const MqeWeights *w, PolicyTcWeights *out, cudaStream_t st);
+cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat, const unsigned short *hist_hi, const unsigned short *hist_lo,
+                                    int head, int rows, int passes, float *Z, cudaStream_t st);
+size_t mqe_substeps_smem_bytes(int A, int Pd, int E, int maxpair);
+}

@@ -1,0 +1,951 @@
+// physics.cu -- the fused decimation kernel: `decimation` x { actuator net -> articulated-body forward dynamics ->
+// contact generation -> projected Gauss-Seidel impulse solve -> integration } for every environment, state held in
+// registers / shared memory for the whole policy step.
+//
+// Replaces (reference) go1.py:48-58: _compute_torques (go1.py:315-354), gym.set_dof_actuation_force_tensor,
+// gym.simulate, gym.fetch_results, gym.refresh_dof_state_tensor, and the net-contact-force / root-state refresh
+// of legged_robot.py:122-124.  Algorithm: DESIGN.md section 4.  The CPU oracle (oracle/mqe_oracle.c) states the same
+// physics with a dense mass matrix; here the mass matrix is never formed:
+//
+//   * one lane per (robot, leg); the four lanes of a robot reduce base-level quantities with xor-shuffles;
+//   * generalized velocity is kept in block-LDL^T coordinates  w = (v_base, u_l = qd_l + G_l^T v_base)  in which
+//     M^-1 = blockdiag(S^-1, H_l^-1) (S = Schur complement of the base), so a contact row is 9+9 floats and one
+//     Gauss-Seidel update costs 18 FMAs;
+//   * all per-robot operators of one substep live in shared memory (4 KB / robot), the persistent state in registers.
+#include "common.cuh"
+#include "kernels.cuh"
+
+#define ROWF 24        // floats per local row: Jb6 Jl3 Yb6 Yl3 dinv bias lambda meta + pad
+#define PROWF 40       // floats per pair row: side A (18) side B (18) dinv bias lambda meta
+// per-robot shared block (floats)
+#define RS_ORIGIN 0
+#define RS_SINV 3
+#define RS_G 24
+#define RS_HINV 96
+#define RS_A 120
+#define RS_P 156
+#define RS_CAP 192
+#define RS_CNT 318     // int nrows, int nlim
+#define RS_ROWS 320
+#define RS_CMETA (RS_ROWS + MQE_MAX_ROWS * ROWF)
+#define RS_FORCE (RS_CMETA + MQE_MAX_LOCAL * 4)
+#define RS_SIZE (RS_FORCE + 52)
+// per-npc shared block
+#define NS_ORIGIN 0
+#define NS_CAP 3       // p0 p1 r
+#define NS_CNT 10
+#define NS_FORCE 12
+#define NS_ROWS 16
+#define NS_CMETA (NS_ROWS + 12 * ROWF)
+#define NS_SIZE (NS_CMETA + 16)
+// per-env shared block
+#define ES_CNT 0
+#define ES_ROWS 4
+#define ES_CMETA(maxpair) (ES_ROWS + (maxpair) * 3 * PROWF)
+#define ES_SIZE(maxpair) (ES_CMETA(maxpair) + (maxpair) * 8)
+
+#define ACTW_FLOATS 1316   // 192 + 32 + 1024 + 32 + 32 + 1 = 1313, padded
+
+__host__ __device__ inline int physics_warp_smem_floats(int A, int P, int E, int maxpair) {
+    return E * A * RS_SIZE + E * P * NS_SIZE + E * ES_SIZE(maxpair);
+}
+__host__ __device__ inline int physics_cta_header_floats() { return (int)(sizeof(MqeRobotModel) / 4) + ACTW_FLOATS; }
+
+struct SV { V3 w, v; };
+struct RBI { float m; V3 h; float I[6]; };   // xx xy xz yy yz zz about O
+
+__device__ __forceinline__ RBI rbi_from_link(const float *in, const M3 &R, V3 p) {
+    RBI o;
+    float m = in[0];
+    V3 c = mul(R, mk(in[1], in[2], in[3])) + p;
+    V3 t0 = in[4] * R.c0 + in[5] * R.c1 + in[6] * R.c2;
+    V3 t1 = in[5] * R.c0 + in[7] * R.c1 + in[8] * R.c2;
+    V3 t2 = in[6] * R.c0 + in[8] * R.c1 + in[9] * R.c2;
+    float cc = dot(c, c);
+    o.m = m;
+    o.h = m * c;
+    o.I[0] = t0.x * R.c0.x + t1.x * R.c1.x + t2.x * R.c2.x + m * (cc - c.x * c.x);
+    o.I[1] = t0.x * R.c0.y + t1.x * R.c1.y + t2.x * R.c2.y - m * c.x * c.y;
+    o.I[2] = t0.x * R.c0.z + t1.x * R.c1.z + t2.x * R.c2.z - m * c.x * c.z;
+    o.I[3] = t0.y * R.c0.y + t1.y * R.c1.y + t2.y * R.c2.y + m * (cc - c.y * c.y);
+    o.I[4] = t0.y * R.c0.z + t1.y * R.c1.z + t2.y * R.c2.z - m * c.y * c.z;
+    o.I[5] = t0.z * R.c0.z + t1.z * R.c1.z + t2.z * R.c2.z + m * (cc - c.z * c.z);
+    return o;
+}
+__device__ __forceinline__ void rbi_add(RBI &o, const RBI &a) {
+    o.m += a.m; o.h = o.h + a.h;
+#pragma unroll
+    for (int i = 0; i < 6; i++) o.I[i] += a.I[i];
+}
+__device__ __forceinline__ SV rbi_mul(const RBI &I, const SV &x) {
+    SV f;
+    V3 hv = cross(I.h, x.v), hw = cross(I.h, x.w);
+    f.w = mk(I.I[0] * x.w.x + I.I[1] * x.w.y + I.I[2] * x.w.z + hv.x,
+             I.I[1] * x.w.x + I.I[3] * x.w.y + I.I[4] * x.w.z + hv.y,
+             I.I[2] * x.w.x + I.I[4] * x.w.y + I.I[5] * x.w.z + hv.z);
+    f.v = I.m * x.v - hw;
+    return f;
+}
+__device__ __forceinline__ SV crm(const SV &a, const SV &b) { SV o; o.w = cross(a.w, b.w); o.v = cross(a.w, b.v) + cross(a.v, b.w); return o; }
+__device__ __forceinline__ SV crf(const SV &a, const SV &f) { SV o; o.w = cross(a.w, f.w) + cross(a.v, f.v); o.v = cross(a.w, f.v); return o; }
+__device__ __forceinline__ float svdot(const SV &a, const SV &b) { return dot(a.w, b.w) + dot(a.v, b.v); }
+__device__ __forceinline__ SV svadd(const SV &a, const SV &b) { SV o; o.w = a.w + b.w; o.v = a.v + b.v; return o; }
+__device__ __forceinline__ SV svscale(float s, const SV &a) { SV o; o.w = s * a.w; o.v = s * a.v; return o; }
+__device__ __forceinline__ float svc(const SV &a, int i) { return i < 3 ? comp(a.w, i) : comp(a.v, i - 3); }
+
+__device__ __forceinline__ float quad_sum(float x, unsigned m) {   // sum over the 4 lanes of a robot
+    x += __shfl_xor_sync(m, x, 1);
+    x += __shfl_xor_sync(m, x, 2);
+    return x;
+}
+__host__ __device__ constexpr int sidx(int i, int j) { return i <= j ? (i * 6 - i * (i - 1) / 2 + (j - i)) : (j * 6 - j * (j - 1) / 2 + (i - j)); }
+__host__ __device__ constexpr int lidx(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// symmetric positive definite 6x6 inverse (Cholesky), all in registers
+__device__ __forceinline__ void spd6_inverse(const float *A /*21 upper*/, float *Ainv /*21*/) {
+    float L[21], rinv[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            float s = A[sidx(j, i)];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= L[lidx(i, k)] * L[lidx(j, k)];
+            if (i == j) { float d = sqrtf(fmaxf(s, 1e-20f)); L[lidx(i, i)] = d; rinv[i] = 1.f / d; }
+            else L[lidx(i, j)] = s * rinv[j];
+        }
+    }
+    float Li[21];   // inverse of L (lower)
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+#pragma unroll
+        for (int i = c; i < 6; i++) {
+            float s = (i == c) ? 1.f : 0.f;
+#pragma unroll
+            for (int k = c; k < i; k++) s -= L[lidx(i, k)] * Li[lidx(k, c)];
+            Li[lidx(i, c)] = s * rinv[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = i; j < 6; j++) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = j; k < 6; k++) s += Li[lidx(k, i)] * Li[lidx(k, j)];
+            Ainv[sidx(i, j)] = s;
+        }
+}
+__device__ __forceinline__ void sym6_mulv(const float *A, const float *x, float *y) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; j++) s += A[sidx(i, j)] * x[j];
+        y[i] = s;
+    }
+}
+// sym 3x3: 00 01 02 11 12 22
+__device__ __forceinline__ void sym3_inverse(const float *H, float *Hi) {
+    float c00 = H[3] * H[5] - H[4] * H[4], c01 = H[2] * H[4] - H[1] * H[5], c02 = H[1] * H[4] - H[2] * H[3];
+    float det = H[0] * c00 + H[1] * c01 + H[2] * c02;
+    float r = 1.f / det;
+    Hi[0] = c00 * r; Hi[1] = c01 * r; Hi[2] = c02 * r;
+    Hi[3] = (H[0] * H[5] - H[2] * H[2]) * r;
+    Hi[4] = (H[1] * H[2] - H[0] * H[4]) * r;
+    Hi[5] = (H[0] * H[3] - H[1] * H[1]) * r;
+}
+__device__ __forceinline__ void sym3_mulv(const float *H, const float *x, float *y) {
+    y[0] = H[0] * x[0] + H[1] * x[1] + H[2] * x[2];
+    y[1] = H[1] * x[0] + H[3] * x[1] + H[4] * x[2];
+    y[2] = H[2] * x[0] + H[4] * x[1] + H[5] * x[2];
+}
+
+__device__ __forceinline__ void tangent_basis(V3 n, V3 &t1, V3 &t2) {
+    V3 e = fabsf(n.x) < 0.9f ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
+    t1 = cross(n, e);
+    t1 = (1.f / sqrtf(dot(t1, t1))) * t1;
+    t2 = cross(n, t1);
+}
+__device__ __forceinline__ float contact_bias(const DevParams &p, float gap) {
+    if (gap > 0.f) return gap / p.dt;
+    return fmaxf(p.erp * gap / p.dt, -p.vdep);
+}
+__device__ __forceinline__ float softsign(float x) { return x / (1.f + fabsf(x)); }
+
+// world probe of a sphere against floor slab + wall footprint; bit0: floor/top contact, bit1: wall contact
+struct ProbeHit { int mask; float gap_f, gap_w; V3 nw; };
+__device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float r) {
+    ProbeHit h;
+    h.mask = 0;
+    SdfSample s = sdf_sample(p, x.x, x.y);
+    bool inside = s.sdf < 0.f, above = x.z >= p.wall_top;
+    float ground = (inside && above) ? p.wall_top : p.floor_z;
+    h.gap_f = x.z - r - ground;
+    if (h.gap_f < p.coff) h.mask |= 1;
+    h.gap_w = s.sdf - r;
+    float gn = sqrtf(s.gx * s.gx + s.gy * s.gy);
+    h.nw = mk(0.f, 0.f, 0.f);
+    if (!above && h.gap_w < p.coff && gn > 1e-6f) { h.mask |= 2; h.nw = mk(s.gx / gn, s.gy / gn, 0.f); }
+    return h;
+}
+
+// closest points of two segments (Ericson 5.1.9); same branch structure as the oracle
+__device__ __forceinline__ void seg_seg(V3 p1, V3 q1, V3 p2, V3 q2, V3 &c1, V3 &c2) {
+    V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+    float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), s, t;
+    const float EPS = 1e-12f;
+    if (a <= EPS && e <= EPS) { s = t = 0.f; }
+    else if (a <= EPS) { s = 0.f; t = fminf(fmaxf(f / e, 0.f), 1.f); }
+    else {
+        float c = dot(d1, r);
+        if (e <= EPS) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+        else {
+            float b = dot(d1, d2), denom = a * e - b * b;
+            s = denom > EPS ? fminf(fmaxf((b * f - c * e) / denom, 0.f), 1.f) : 0.f;
+            t = (b * s + f) / e;
+            if (t < 0.f) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+            else if (t > 1.f) { t = 1.f; s = fminf(fmaxf((b - c) / a, 0.f), 1.f); }
+        }
+    }
+    c1 = p1 + s * d1;
+    c2 = p2 + t * d2;
+}
+
+// Build one side (18 floats: Jb6 Jl3 Yb6 Yl3) of a row for a robot from the operators in shared memory.
+// link: 0 base, 1..12.  Returns the diagonal contribution J.Y.
+__device__ float robot_side_from_smem(const float *rs, int link, V3 r, V3 d, float *out) {
+    V3 rxd = cross(r, d);
+    float Jb[6] = {rxd.x, rxd.y, rxd.z, d.x, d.y, d.z}, Jl[3] = {0.f, 0.f, 0.f};
+    int leg = 0, k = 0;
+    if (link > 0) { leg = (link - 1) / 3; k = (link - 1) % 3 + 1; }
+    for (int j = 0; j < k; j++) {
+        const float *a = rs + RS_A + (3 * leg + j) * 3, *pj = rs + RS_P + (3 * leg + j) * 3;
+        V3 rel = mk(r.x - pj[0], r.y - pj[1], r.z - pj[2]);
+        Jl[j] = dot(mk(a[0], a[1], a[2]), cross(rel, d));
+    }
+    const float *G = rs + RS_G + leg * 18;
+    if (k > 0)
+        for (int i = 0; i < 6; i++) Jb[i] -= G[i * 3] * Jl[0] + G[i * 3 + 1] * Jl[1] + G[i * 3 + 2] * Jl[2];
+    float Yb[6], Yl[3] = {0.f, 0.f, 0.f};
+    sym6_mulv(rs + RS_SINV, Jb, Yb);
+    if (k > 0) sym3_mulv(rs + RS_HINV + leg * 6, Jl, Yl);
+    float dd = 0.f;
+    for (int i = 0; i < 6; i++) { out[i] = Jb[i]; out[9 + i] = Yb[i]; dd += Jb[i] * Yb[i]; }
+    for (int i = 0; i < 3; i++) { out[6 + i] = Jl[i]; out[15 + i] = Yl[i]; dd += Jl[i] * Yl[i]; }
+    return dd;
+}
+__device__ float npc_side(const DevParams &p, V3 r, V3 d, float *out) {
+    V3 rxd = cross(r, d);
+    float iI = 1.f / p.npc_inertia, im = 1.f / p.npc_mass;
+    float up = p.npc_ctrl == MQE_NPC_SHEEP ? 0.f : 1.f;      // sheep stay upright (go1_sheep.py:61 zeroes their tilt)
+    out[0] = rxd.x; out[1] = rxd.y; out[2] = rxd.z; out[3] = d.x; out[4] = d.y; out[5] = d.z;
+    out[6] = out[7] = out[8] = 0.f;
+    out[9] = rxd.x * iI * up; out[10] = rxd.y * iI * up; out[11] = rxd.z * iI;
+    out[12] = d.x * im; out[13] = d.y * im; out[14] = d.z * im;
+    out[15] = out[16] = out[17] = 0.f;
+    float dd = 0.f;
+    for (int i = 0; i < 6; i++) dd += out[i] * out[9 + i];
+    return dd;
+}
+
+__global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int maxpair, const unsigned int *__restrict__ pair_table, int n_pair_entries) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    // ---- CTA header: robot model + actuator weights ----
+    MqeRobotModel *md = reinterpret_cast<MqeRobotModel *>(smem);
+    float *actw = smem + sizeof(MqeRobotModel) / 4;
+    {
+        const float *src = reinterpret_cast<const float *>(p.model);
+        for (int i = threadIdx.x; i < (int)(sizeof(MqeRobotModel) / 4); i += blockDim.x) smem[i] = src[i];
+        for (int i = threadIdx.x; i < 1313; i += blockDim.x) actw[i] = p.act_w[i];
+    }
+    __syncthreads();
+    const int A = p.A, P = p.Pd, E = p.E, G = A + P;   // P: dynamic NPCs only (a seesaw is not a free body)
+    const int GA = p.G;                                 // actors per env in the root-state tensor
+    float *wbase = smem + physics_cta_header_floats() + warp * physics_warp_smem_floats(A, P, E, maxpair);
+    const int first_env = (blockIdx.x * nwarps + warp) * E;
+    if (first_env >= p.N) return;
+
+    // ---- lane roles ----
+    const int nrl = 4 * A * E;
+    const bool is_robot = lane < nrl;
+    const bool is_npc = !is_robot && lane < nrl + P * E;
+    int e_loc = 0, ag = 0, leg = 0, pn = 0;
+    if (is_robot) { e_loc = lane / (4 * A); ag = (lane % (4 * A)) / 4; leg = lane & 3; }
+    else if (is_npc) { e_loc = (lane - nrl) / P; pn = (lane - nrl) % P; }
+    const int env = first_env + e_loc;
+    const bool active = (is_robot || is_npc) && env < p.N;
+    const int grp = is_robot ? ag : A + pn;                              // group index inside the env
+    float *rs = wbase + (e_loc * A + ag) * RS_SIZE;                      // my robot block
+    float *ns = wbase + E * A * RS_SIZE + (e_loc * P + pn) * NS_SIZE;    // my npc block
+    float *es = wbase + E * A * RS_SIZE + E * P * NS_SIZE + e_loc * ES_SIZE(maxpair);
+    const unsigned quad_mask = is_robot ? (0xFu << (lane & ~3)) : (1u << lane);
+    unsigned env_mask = 0;
+    {
+        unsigned rm = (4 * A >= 32) ? FULL : ((1u << (4 * A)) - 1u);
+        env_mask = rm << (e_loc * 4 * A);
+        if (P) env_mask |= ((1u << P) - 1u) << (nrl + e_loc * P);
+        if (!(is_robot || is_npc)) env_mask = 1u << lane;
+    }
+    const int rank_in_env = is_robot ? (lane - e_loc * 4 * A) : (4 * A + pn);
+    const int lanes_per_env = 4 * A + P;
+
+    // ---- persistent state in registers ----
+    V3 pos = mk(0, 0, 0), vlin = mk(0, 0, 0), wang = mk(0, 0, 0);
+    float qx = 0, qy = 0, qz = 0, qw = 1;
+    float q[3] = {0, 0, 0}, qd[3] = {0, 0, 0}, act[3] = {0, 0, 0};
+    float e1[3], e2[3], v1[3], v2[3], tau[3] = {0, 0, 0};
+    const int m_idx = env * A + ag;                                      // agent row
+    if (active) {
+        const float *r = p.root + ((size_t)env * GA + grp) * 13;
+        pos = mk(r[0], r[1], r[2]); qx = r[3]; qy = r[4]; qz = r[5]; qw = r[6];
+        vlin = mk(r[7], r[8], r[9]); wang = mk(r[10], r[11], r[12]);
+    }
+    if (active && is_robot) {
+        const float *d = p.dof + ((size_t)env * (12 * A + p.D) + 12 * ag + 3 * leg) * 2;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            q[k] = d[2 * k]; qd[k] = d[2 * k + 1];
+            int j = m_idx * 12 + 3 * leg + k;
+            act[k] = p.actions[j];
+            e1[k] = p.err1[j]; e2[k] = p.err2[j]; v1[k] = p.vel1[j]; v2[k] = p.vel2[j];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { e1[k] = e2[k] = v1[k] = v2[k] = 0.f; }
+    }
+    int stat_local = 0, stat_lim = 0, stat_pair = 0, stat_rows = 0;
+
+    for (int sub = 0; sub < nsub; sub++) {
+        const bool last = (sub == nsub - 1);
+        // ================================================================ P1: actuator network (go1.py:315-354, 369-380)
+        if (active && is_robot) {
+            float x[3][6], h1[3][32];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                int j = 3 * leg + k;
+                float a = act[k] * p.action_scale;
+                if (k == 0) a *= p.hip_scale;
+                float err = q[k] - (a + md->q_default[j]);
+                x[k][0] = err; x[k][1] = e1[k]; x[k][2] = e2[k]; x[k][3] = qd[k]; x[k][4] = v1[k]; x[k][5] = v2[k];
+                e2[k] = e1[k]; e1[k] = err; v2[k] = v1[k]; v1[k] = qd[k];
+            }
+            const float *W0 = actw, *b0 = actw + 192, *W1 = actw + 224, *b1 = actw + 1248, *W2 = actw + 1280;
+#pragma unroll
+            for (int o = 0; o < 32; o++) {
+                float w0 = W0[o * 6], w1 = W0[o * 6 + 1], w2 = W0[o * 6 + 2], w3 = W0[o * 6 + 3], w4 = W0[o * 6 + 4], w5 = W0[o * 6 + 5], b = b0[o];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    h1[k][o] = softsign(b + w0 * x[k][0] + w1 * x[k][1] + w2 * x[k][2] + w3 * x[k][3] + w4 * x[k][4] + w5 * x[k][5]);
+            }
+            float out[3] = {actw[1312], actw[1312], actw[1312]};
+#pragma unroll 4
+            for (int o = 0; o < 32; o++) {
+                float s0 = b1[o], s1 = s0, s2 = s0;
+                const float4 *wr = reinterpret_cast<const float4 *>(W1 + o * 32);
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++) {
+                    float4 w = wr[kk];
+                    s0 += w.x * h1[0][4 * kk] + w.y * h1[0][4 * kk + 1] + w.z * h1[0][4 * kk + 2] + w.w * h1[0][4 * kk + 3];
+                    s1 += w.x * h1[1][4 * kk] + w.y * h1[1][4 * kk + 1] + w.z * h1[1][4 * kk + 2] + w.w * h1[1][4 * kk + 3];
+                    s2 += w.x * h1[2][4 * kk] + w.y * h1[2][4 * kk + 1] + w.z * h1[2][4 * kk + 2] + w.w * h1[2][4 * kk + 3];
+                }
+                float w2o = W2[o];
+                out[0] += w2o * softsign(s0); out[1] += w2o * softsign(s1); out[2] += w2o * softsign(s2);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float lim = md->tau_limit[3 * leg + k];
+                tau[k] = fminf(fmaxf(out[k], -lim), lim);
+            }
+        }
+
+        // ================================================================ P2: kinematics + dynamics (robot lanes), npc prediction
+        float vb[6] = {0, 0, 0, 0, 0, 0}, u[3] = {0, 0, 0};   // solve coordinates
+        float Gm[18];                                           // my leg's G (6x3 row-major)
+        M3 Rb, R1, R2, R3;
+        V3 p1 = mk(0, 0, 0), p2 = p1, p3 = p1, a1 = p1, a2 = p1;
+        float Sinv[21], Hinv[6];
+        if (is_robot) {   // executed by whole quads (inactive envs compute on zeros; quad shuffles need all four lanes)
+            Rb = quat_to_mat(qx, qy, qz, qw);
+            float s1, c1, s2, c2, s3, c3;
+            sincosf(q[0], &s1, &c1); sincosf(q[1], &s2, &c2); sincosf(q[2], &s3, &c3);
+            const float *off = &md->leg_offsets[leg][0][0];
+            p1 = mul(Rb, mk(off[0], off[1], off[2]));
+            a1 = Rb.c0;
+            R1 = rot_x(Rb, c1, s1);
+            p2 = p1 + mul(R1, mk(off[3], off[4], off[5]));
+            a2 = R1.c1;
+            R2 = rot_y(R1, c2, s2);
+            p3 = p2 + mul(R2, mk(off[6], off[7], off[8]));
+            R3 = rot_y(R2, c3, s3);
+            SV S1, S2, S3;
+            S1.w = a1; S1.v = cross(p1, a1);
+            S2.w = a2; S2.v = cross(p2, a2);
+            S3.w = a2; S3.v = cross(p3, a2);
+            RBI I0 = rbi_from_link(md->base_inertial, Rb, mk(0, 0, 0));
+            RBI I1 = rbi_from_link(md->leg_inertial[leg][0], R1, p1);
+            RBI I2 = rbi_from_link(md->leg_inertial[leg][1], R2, p2);
+            RBI I3 = rbi_from_link(md->leg_inertial[leg][2], R3, p3);
+            // velocities, bias accelerations
+            SV V0; V0.w = wang; V0.v = vlin;
+            SV A0; A0.w = mk(0, 0, 0); A0.v = mk(0, 0, -p.gz);
+            SV sq1 = svscale(qd[0], S1), sq2 = svscale(qd[1], S2), sq3 = svscale(qd[2], S3);
+            SV V1 = svadd(V0, sq1), V2 = svadd(V1, sq2), V3_ = svadd(V2, sq3);
+            SV A1 = svadd(A0, crm(V0, sq1)), A2 = svadd(A1, crm(V1, sq2)), A3 = svadd(A2, crm(V2, sq3));
+            SV f0 = svadd(rbi_mul(I0, A0), crf(V0, rbi_mul(I0, V0)));
+            SV f1 = svadd(rbi_mul(I1, A1), crf(V1, rbi_mul(I1, V1)));
+            SV f2 = svadd(rbi_mul(I2, A2), crf(V2, rbi_mul(I2, V2)));
+            SV f3 = svadd(rbi_mul(I3, A3), crf(V3_, rbi_mul(I3, V3_)));
+            f2 = svadd(f2, f3); f1 = svadd(f1, f2);
+            float cl[3] = {svdot(S1, f1), svdot(S2, f2), svdot(S3, f3)};
+            // composite inertias, F columns, leg block H
+            RBI I2c = I2; rbi_add(I2c, I3);
+            RBI I1c = I1; rbi_add(I1c, I2c);
+            SV F1 = rbi_mul(I1c, S1), F2 = rbi_mul(I2c, S2), F3 = rbi_mul(I3, S3);
+            float H[6] = {svdot(S1, F1), svdot(S1, F2), svdot(S1, F3), svdot(S2, F2), svdot(S2, F3), svdot(S3, F3)};
+            sym3_inverse(H, Hinv);
+            float Fm[18];
+#pragma unroll
+            for (int i = 0; i < 6; i++) { Fm[i * 3] = svc(F1, i); Fm[i * 3 + 1] = svc(F2, i); Fm[i * 3 + 2] = svc(F3, i); }
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                float x0 = Fm[i * 3], x1 = Fm[i * 3 + 1], x2 = Fm[i * 3 + 2];
+                Gm[i * 3] = x0 * Hinv[0] + x1 * Hinv[1] + x2 * Hinv[2];
+                Gm[i * 3 + 1] = x0 * Hinv[1] + x1 * Hinv[3] + x2 * Hinv[4];
+                Gm[i * 3 + 2] = x0 * Hinv[2] + x1 * Hinv[4] + x2 * Hinv[5];
+            }
+            // base-level reductions over the quad
+            RBI Ic = I1c;
+            Ic.m = quad_sum(Ic.m, quad_mask);
+            Ic.h = mk(quad_sum(Ic.h.x, quad_mask), quad_sum(Ic.h.y, quad_mask), quad_sum(Ic.h.z, quad_mask));
+#pragma unroll
+            for (int i = 0; i < 6; i++) Ic.I[i] = quad_sum(Ic.I[i], quad_mask);
+            rbi_add(Ic, I0);
+            float Ssch[21];
+            {
+                const float hx = Ic.h.x, hy = Ic.h.y, hz = Ic.h.z;
+                float M6[21];
+                M6[sidx(0, 0)] = Ic.I[0]; M6[sidx(0, 1)] = Ic.I[1]; M6[sidx(0, 2)] = Ic.I[2];
+                M6[sidx(1, 1)] = Ic.I[3]; M6[sidx(1, 2)] = Ic.I[4]; M6[sidx(2, 2)] = Ic.I[5];
+                M6[sidx(0, 3)] = 0.f; M6[sidx(0, 4)] = -hz; M6[sidx(0, 5)] = hy;
+                M6[sidx(1, 3)] = hz;  M6[sidx(1, 4)] = 0.f; M6[sidx(1, 5)] = -hx;
+                M6[sidx(2, 3)] = -hy; M6[sidx(2, 4)] = hx;  M6[sidx(2, 5)] = 0.f;
+                M6[sidx(3, 3)] = Ic.m; M6[sidx(3, 4)] = 0.f; M6[sidx(3, 5)] = 0.f;
+                M6[sidx(4, 4)] = Ic.m; M6[sidx(4, 5)] = 0.f; M6[sidx(5, 5)] = Ic.m;
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+#pragma unroll
+                    for (int j = i; j < 6; j++) {
+                        float gf = Gm[i * 3] * Fm[j * 3] + Gm[i * 3 + 1] * Fm[j * 3 + 1] + Gm[i * 3 + 2] * Fm[j * 3 + 2];
+                        Ssch[sidx(i, j)] = M6[sidx(i, j)] - quad_sum(gf, quad_mask);
+                    }
+            }
+            spd6_inverse(Ssch, Sinv);
+            // right-hand sides
+            float rl[3] = {tau[0] - cl[0], tau[1] - cl[1], tau[2] - cl[2]};
+            float rb[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                float legpart = svc(f1, i) + Gm[i * 3] * rl[0] + Gm[i * 3 + 1] * rl[1] + Gm[i * 3 + 2] * rl[2];
+                rb[i] = -(svc(f0, i) + quad_sum(legpart, quad_mask));
+            }
+            float ab[6], au[3];
+            sym6_mulv(Sinv, rb, ab);
+            sym3_mulv(Hinv, rl, au);
+            // to solve coordinates and predict
+            V3 wxv = cross(wang, vlin);
+            vb[0] = wang.x + p.dt * ab[0]; vb[1] = wang.y + p.dt * ab[1]; vb[2] = wang.z + p.dt * ab[2];
+            vb[3] = vlin.x + p.dt * (ab[3] + wxv.x); vb[4] = vlin.y + p.dt * (ab[4] + wxv.y); vb[5] = vlin.z + p.dt * (ab[5] + wxv.z);
+            float v0[6] = {wang.x, wang.y, wang.z, vlin.x, vlin.y, vlin.z};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float gt = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; i++) gt += Gm[i * 3 + k] * v0[i];
+                u[k] = qd[k] + gt + p.dt * au[k];
+            }
+            // publish operators for row builders of other lanes (pair contacts) and the capsule endpoints
+            if (leg == 0) {
+                rs[RS_ORIGIN] = pos.x; rs[RS_ORIGIN + 1] = pos.y; rs[RS_ORIGIN + 2] = pos.z;
+#pragma unroll
+                for (int i = 0; i < 21; i++) rs[RS_SINV + i] = Sinv[i];
+                ((int *)rs)[RS_CNT] = 0; ((int *)rs)[RS_CNT + 1] = 0;
+                for (int i = 0; i < 51; i++) rs[RS_FORCE + i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 18; i++) rs[RS_G + leg * 18 + i] = Gm[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++) rs[RS_HINV + leg * 6 + i] = Hinv[i];
+            {
+                float *pa = rs + RS_A + leg * 9, *pp = rs + RS_P + leg * 9;
+                pa[0] = a1.x; pa[1] = a1.y; pa[2] = a1.z; pa[3] = a2.x; pa[4] = a2.y; pa[5] = a2.z; pa[6] = a2.x; pa[7] = a2.y; pa[8] = a2.z;
+                pp[0] = p1.x; pp[1] = p1.y; pp[2] = p1.z; pp[3] = p2.x; pp[4] = p2.y; pp[5] = p2.z; pp[6] = p3.x; pp[7] = p3.y; pp[8] = p3.z;
+            }
+            for (int ci = 0; ci < md->n_caps; ci++) {
+                const float *cp = md->caps[ci];
+                int link = (int)cp[0];
+                bool mine = (link == 0) ? (leg == 0) : ((link - 1) / 3 == leg);
+                if (!mine) continue;
+                int k = link == 0 ? 0 : (link - 1) % 3 + 1;
+                const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
+                V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                V3 w0 = pos + pl + mul(Rl, mk(cp[2], cp[3], cp[4])), w1 = pos + pl + mul(Rl, mk(cp[5], cp[6], cp[7]));
+                float *o = rs + RS_CAP + ci * 7;
+                o[0] = w0.x; o[1] = w0.y; o[2] = w0.z; o[3] = w1.x; o[4] = w1.y; o[5] = w1.z; o[6] = cp[8];
+            }
+        } else if (is_npc) {
+            vb[0] = wang.x; vb[1] = wang.y; vb[2] = wang.z; vb[3] = vlin.x; vb[4] = vlin.y; vb[5] = vlin.z + p.dt * p.gz;
+            Rb = quat_to_mat(qx, qy, qz, qw);
+            V3 ax = p.npc_halflen * Rb.c2;
+            ns[NS_ORIGIN] = pos.x; ns[NS_ORIGIN + 1] = pos.y; ns[NS_ORIGIN + 2] = pos.z;
+            ns[NS_CAP] = pos.x - ax.x; ns[NS_CAP + 1] = pos.y - ax.y; ns[NS_CAP + 2] = pos.z - ax.z;
+            ns[NS_CAP + 3] = pos.x + ax.x; ns[NS_CAP + 4] = pos.y + ax.y; ns[NS_CAP + 5] = pos.z + ax.z; ns[NS_CAP + 6] = p.npc_radius;
+            ((int *)ns)[NS_CNT] = 0;
+            ns[NS_FORCE] = ns[NS_FORCE + 1] = ns[NS_FORCE + 2] = 0.f;
+        }
+        if (rank_in_env == 0) ((int *)es)[ES_CNT] = 0;
+        __syncwarp();
+
+        // ================================================================ P3: rows.  joint limits, then world contacts
+        int nrows = 0, nlim = 0;
+        if (is_robot) {
+            // ---- joint limits: canonical order (dof, lower/upper), cap MQE_MAX_LIMIT ----
+            unsigned lm = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                int j = 3 * leg + k;
+                if (q[k] - md->q_lower[j] < p.limit_margin) lm |= 1u << (2 * j);
+                if (md->q_upper[j] - q[k] < p.limit_margin) lm |= 1u << (2 * j + 1);
+            }
+            if (!active) lm = 0;
+            unsigned lall = lm;
+            lall |= __shfl_xor_sync(quad_mask, lall, 1);
+            lall |= __shfl_xor_sync(quad_mask, lall, 2);
+            nlim = min(__popc(lall), MQE_MAX_LIMIT);
+            while (lm) {
+                int b = __ffs(lm) - 1;
+                lm &= lm - 1;
+                int slot = __popc(lall & ((1u << b) - 1u));
+                if (slot >= MQE_MAX_LIMIT) break;
+                int k = (b >> 1) - 3 * leg, side = b & 1;
+                float sg = side ? -1.f : 1.f;
+                float gap = side ? md->q_upper[3 * leg + k] - q[k] : q[k] - md->q_lower[3 * leg + k];
+                float Jb[6], Yb[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) Jb[i] = -sg * Gm[i * 3 + k];
+                sym6_mulv(Sinv, Jb, Yb);
+                float hk[3] = {Hinv[k == 0 ? 0 : (k == 1 ? 1 : 2)], Hinv[k == 0 ? 1 : (k == 1 ? 3 : 4)], Hinv[k == 0 ? 2 : (k == 1 ? 4 : 5)]};
+                float dd = hk[k];
+#pragma unroll
+                for (int i = 0; i < 6; i++) dd += Jb[i] * Yb[i];
+                float *row = rs + RS_ROWS + slot * ROWF;
+#pragma unroll
+                for (int i = 0; i < 6; i++) { row[i] = Jb[i]; row[9 + i] = Yb[i]; }
+#pragma unroll
+                for (int i = 0; i < 3; i++) { row[6 + i] = (i == k) ? sg : 0.f; row[15 + i] = sg * hk[i]; }
+                row[18] = 1.f / (dd + p.cfm); row[19] = contact_bias(p, gap); row[20] = 0.f;
+                row[21] = __int_as_float(leg | (0 << 4) | (slot << 8));
+            }
+            // ---- world contacts: pass 1 flags ----
+            unsigned long long cm = 0ull;
+            const int np_ = md->n_probes;
+            for (int pi = 0; pi < np_; pi++) {
+                const float *pr = md->probes[pi];
+                int link = (int)pr[0];
+                int nbase = 0;
+                bool mine;
+                if (link == 0) { for (int t = 0; t < pi; t++) nbase += ((int)md->probes[t][0] == 0); mine = (nbase & 3) == leg; }
+                else mine = ((link - 1) / 3 == leg);
+                if (!mine || !active) continue;
+                int k = link == 0 ? 0 : (link - 1) % 3 + 1;
+                const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
+                V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                V3 xw = pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
+                ProbeHit h = probe_world(p, xw, pr[5]);
+                cm |= (unsigned long long)h.mask << (2 * pi);
+            }
+            unsigned long long call = cm;
+            call |= __shfl_xor_sync(quad_mask, call, 1);
+            call |= __shfl_xor_sync(quad_mask, call, 2);
+            int ncon = min(__popcll(call), MQE_MAX_LOCAL);
+            nrows = nlim + 3 * ncon;
+            // ---- pass 2: build rows for my contacts ----
+            while (cm) {
+                int b = __ffsll((long long)cm) - 1;
+                cm &= cm - 1ull;
+                int slot = __popcll(call & ((1ull << b) - 1ull));
+                if (slot >= MQE_MAX_LOCAL) break;
+                int pi = b >> 1, kind = b & 1;
+                const float *pr = md->probes[pi];
+                int link = (int)pr[0], body = (int)pr[1];
+                int k = link == 0 ? 0 : (link - 1) % 3 + 1;
+                const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
+                V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));            // probe centre rel. O
+                ProbeHit h = probe_world(p, pos + xr, pr[5]);
+                V3 n = kind ? h.nw : mk(0, 0, 1);
+                float gap = kind ? h.gap_w : h.gap_f;
+                V3 r = xr - (pr[5] + 0.5f * gap) * n;                     // contact point rel. O
+                V3 t1, t2;
+                tangent_basis(n, t1, t2);
+                float *cmeta = rs + RS_CMETA + slot * 4;
+                cmeta[0] = n.x; cmeta[1] = n.y; cmeta[2] = n.z; cmeta[3] = __int_as_float(body);
+                int r0 = nlim + 3 * slot;
+#pragma unroll
+                for (int dch = 0; dch < 3; dch++) {
+                    V3 d = dch == 0 ? n : (dch == 1 ? t1 : t2);
+                    V3 rxd = cross(r, d);
+                    float Jb[6] = {rxd.x, rxd.y, rxd.z, d.x, d.y, d.z}, Jl[3] = {0, 0, 0}, Yb[6], Yl[3];
+                    if (k >= 1) Jl[0] = dot(a1, cross(r - p1, d));
+                    if (k >= 2) Jl[1] = dot(a2, cross(r - p2, d));
+                    if (k >= 3) Jl[2] = dot(a2, cross(r - p3, d));
+#pragma unroll
+                    for (int i = 0; i < 6; i++) Jb[i] -= Gm[i * 3] * Jl[0] + Gm[i * 3 + 1] * Jl[1] + Gm[i * 3 + 2] * Jl[2];
+                    sym6_mulv(Sinv, Jb, Yb);
+                    sym3_mulv(Hinv, Jl, Yl);
+                    float dd = Jl[0] * Yl[0] + Jl[1] * Yl[1] + Jl[2] * Yl[2];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) dd += Jb[i] * Yb[i];
+                    float *row = rs + RS_ROWS + (r0 + dch) * ROWF;
+#pragma unroll
+                    for (int i = 0; i < 6; i++) { row[i] = Jb[i]; row[9 + i] = Yb[i]; }
+#pragma unroll
+                    for (int i = 0; i < 3; i++) { row[6 + i] = Jl[i]; row[15 + i] = Yl[i]; }
+                    row[18] = 1.f / (dd + p.cfm);
+                    row[19] = dch == 0 ? contact_bias(p, gap) : 0.f;
+                    row[20] = 0.f;
+                    row[21] = __int_as_float(leg | ((dch ? 1 : 0) << 4) | (r0 << 8));
+                }
+            }
+            if (leg == 0 && active) { stat_local += ncon; stat_lim += nlim; }
+        } else if (is_npc && active) {
+            int ends = p.npc_halflen > 0.f ? 2 : 1, ncon = 0;
+            for (int en = 0; en < ends && ncon < MQE_MAX_LOCAL; en++) {
+                V3 xr = ((en == 0 ? -1.f : 1.f) * p.npc_halflen) * Rb.c2;
+                ProbeHit h = probe_world(p, pos + xr, p.npc_radius);
+                for (int kind = 0; kind < 2 && ncon < 4; kind++) {
+                    if (!(h.mask & (1 << kind))) continue;
+                    V3 n = kind ? h.nw : mk(0, 0, 1);
+                    float gap = kind ? h.gap_w : h.gap_f;
+                    V3 r = xr - (p.npc_radius + 0.5f * gap) * n, t1, t2;
+                    tangent_basis(n, t1, t2);
+                    float *cmeta = ns + NS_CMETA + ncon * 4;
+                    cmeta[0] = n.x; cmeta[1] = n.y; cmeta[2] = n.z; cmeta[3] = 0.f;
+                    for (int dch = 0; dch < 3; dch++) {
+                        V3 d = dch == 0 ? n : (dch == 1 ? t1 : t2);
+                        float *row = ns + NS_ROWS + (3 * ncon + dch) * ROWF;
+                        float dd = npc_side(p, r, d, row);
+                        row[18] = 1.f / (dd + p.cfm);
+                        row[19] = dch == 0 ? contact_bias(p, gap) : 0.f;
+                        row[20] = 0.f;
+                        row[21] = __int_as_float(0 | ((dch ? 1 : 0) << 4) | ((3 * ncon) << 8));
+                    }
+                    ncon++;
+                }
+            }
+            nrows = 3 * ncon;
+            stat_local += ncon;
+        }
+        __syncwarp();
+
+        // ================================================================ P3b: dynamic-vs-dynamic pairs (capsule / capsule)
+        int npair = 0;
+        if (G > 1 && (is_robot || is_npc)) {
+            // broadphase over group pairs
+            bool close = false;
+            int ngp = G * (G - 1) / 2;
+            for (int t = rank_in_env; t < ngp; t += lanes_per_env) {
+                int X = 0, rem = t;
+                while (rem >= G - 1 - X) { rem -= G - 1 - X; X++; }
+                int Y = X + 1 + rem;
+                const float *ox = X < A ? wbase + (e_loc * A + X) * RS_SIZE + RS_ORIGIN : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE + NS_ORIGIN;
+                const float *oy = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE + RS_ORIGIN : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE + NS_ORIGIN;
+                float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
+                float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
+                if (dx * dx + dy * dy + dz * dz <= lim * lim) close = true;
+            }
+            if (env >= p.N) close = false;
+            bool any_close = __ballot_sync(env_mask, close) != 0u;
+            if (any_close) {
+                for (int t0 = 0; t0 < n_pair_entries; t0 += lanes_per_env) {
+                    int t = t0 + rank_in_env;
+                    bool hit = false;
+                    V3 cn = mk(0, 0, 0), cpos = mk(0, 0, 0);
+                    float cgap = 0.f;
+                    int X = 0, Y = 0, ci = 0, cj = 0;
+                    if (t < n_pair_entries) {
+                        unsigned ent = __ldg(pair_table + t);
+                        X = ent & 0xff; ci = (ent >> 8) & 0xff; Y = (ent >> 16) & 0xff; cj = ent >> 24;
+                        const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
+                        const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
+                        const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
+                        float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
+                        float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
+                        if (dx * dx + dy * dy + dz * dz <= lim * lim) {
+                            const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
+                            V3 c1, c2;
+                            seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
+                            V3 dv = c1 - c2;
+                            float dist = sqrtf(dot(dv, dv));
+                            cgap = dist - ca[6] - cb[6];
+                            if (cgap < p.coff && dist >= 1e-9f) {
+                                hit = true;
+                                cn = (1.f / dist) * dv;
+                                cpos = c2 + (cb[6] + 0.5f * cgap) * cn;
+                            }
+                        }
+                    }
+                    unsigned hb = __ballot_sync(env_mask, hit);
+                    int slot = npair + __popc(hb & ((1u << lane) - 1u));
+                    npair += __popc(hb);
+                    if (hit && slot < maxpair) {
+                        V3 t1, t2;
+                        tangent_basis(cn, t1, t2);
+                        const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
+                        const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
+                        const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
+                        int la = X < A ? (int)md->caps[ci][0] : 0, lb = Y < A ? (int)md->caps[cj][0] : 0;
+                        int rba = X < A ? X * MQE_NUM_BODIES + (int)md->caps[ci][1] : A * MQE_NUM_BODIES + (X - A);
+                        int rbb = Y < A ? Y * MQE_NUM_BODIES + (int)md->caps[cj][1] : A * MQE_NUM_BODIES + (Y - A);
+                        V3 ra = cpos - mk(ox[0], ox[1], ox[2]), rb_ = cpos - mk(oy[0], oy[1], oy[2]);
+                        float *cmeta = es + ES_CMETA(maxpair) + slot * 8;
+                        cmeta[0] = cn.x; cmeta[1] = cn.y; cmeta[2] = cn.z; cmeta[3] = __int_as_float(rba); cmeta[4] = __int_as_float(rbb);
+                        int lega = la > 0 ? (la - 1) / 3 : 0, legb = lb > 0 ? (lb - 1) / 3 : 0;
+                        for (int dch = 0; dch < 3; dch++) {
+                            V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
+                            float *row = es + ES_ROWS + (3 * slot + dch) * PROWF;
+                            float dd = X < A ? robot_side_from_smem(bx_, la, ra, d, row) : npc_side(p, ra, d, row);
+                            dd += Y < A ? robot_side_from_smem(by_, lb, rb_, -d, row + 18) : npc_side(p, rb_, -d, row + 18);
+                            row[36] = 1.f / (dd + p.cfm);
+                            row[37] = dch == 0 ? contact_bias(p, cgap) : 0.f;
+                            row[38] = 0.f;
+                            row[39] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
+                        }
+                    }
+                }
+                npair = min(npair, maxpair);
+            }
+            if (rank_in_env == 0 && env < p.N) stat_pair += npair;
+        }
+        __syncwarp();
+        if (active && (leg == 0 || is_npc)) stat_rows = max(stat_rows, nrows);
+
+        // ================================================================ P4: projected Gauss-Seidel
+        {
+            float *rows = is_robot ? rs + RS_ROWS : ns + NS_ROWS;
+            const int quad_base = lane & ~3;
+            for (int it = 0; it < p.iters; it++) {
+                for (int i = 0; i < nrows; i++) {
+                    float *row = rows + i * ROWF;
+                    float4 r0 = *reinterpret_cast<const float4 *>(row), r1 = *reinterpret_cast<const float4 *>(row + 4), r2 = *reinterpret_cast<const float4 *>(row + 8);
+                    float4 r3 = *reinterpret_cast<const float4 *>(row + 12), r4 = *reinterpret_cast<const float4 *>(row + 16), r5 = *reinterpret_cast<const float4 *>(row + 20);
+                    int meta = __float_as_int(r5.y), rleg = meta & 15, kind = (meta >> 4) & 1, nrow = meta >> 8;
+                    float pb = r0.x * vb[0] + r0.y * vb[1] + r0.z * vb[2] + r0.w * vb[3] + r1.x * vb[4] + r1.y * vb[5];
+                    float pl = (is_robot && rleg == leg) ? (r1.z * u[0] + r1.w * u[1] + r2.x * u[2]) : 0.f;
+                    if (is_robot) pl = __shfl_sync(quad_mask, pl, quad_base + rleg);
+                    float urel = r4.w + pb + pl;              // bias + J w
+                    float lam_old = r5.x, lam = lam_old - urel * r4.z;
+                    if (kind == 0) lam = fmaxf(lam, 0.f);
+                    else { float lim = p.mu * rows[nrow * ROWF + 20]; lam = fminf(fmaxf(lam, -lim), lim); }
+                    float dl = lam - lam_old;
+                    row[20] = lam;
+                    vb[0] += r2.y * dl; vb[1] += r2.z * dl; vb[2] += r2.w * dl; vb[3] += r3.x * dl; vb[4] += r3.y * dl; vb[5] += r3.z * dl;
+                    if (is_robot && rleg == leg) { u[0] += r3.w * dl; u[1] += r4.x * dl; u[2] += r4.y * dl; }
+                }
+                if (npair > 0) {   // uniform over the env's lanes
+                    __syncwarp(env_mask);
+                    for (int i = 0; i < 3 * npair; i++) {
+                        float *row = es + ES_ROWS + i * PROWF;
+                        int meta = __float_as_int(row[39]);
+                        int ga = meta & 15, la = (meta >> 4) & 15, gb = (meta >> 8) & 15, lb = (meta >> 12) & 15, kind = (meta >> 16) & 1, nrow = meta >> 20;
+                        const float *sa = row, *sb = row + 18;
+                        float pbA = 0.f, plA = 0.f, pbB = 0.f, plB = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) { pbA += sa[k] * vb[k]; pbB += sb[k] * vb[k]; }
+#pragma unroll
+                        for (int k = 0; k < 3; k++) { plA += sa[6 + k] * u[k]; plB += sb[6 + k] * u[k]; }
+                        int srcA = ga < A ? e_loc * 4 * A + 4 * ga : nrl + e_loc * P + (ga - A);
+                        int srcB = gb < A ? e_loc * 4 * A + 4 * gb : nrl + e_loc * P + (gb - A);
+                        float urel = row[37] + __shfl_sync(env_mask, pbA, srcA) + __shfl_sync(env_mask, plA, ga < A ? srcA + la : srcA)
+                                             + __shfl_sync(env_mask, pbB, srcB) + __shfl_sync(env_mask, plB, gb < A ? srcB + lb : srcB);
+                        float lam_old = row[38], lam = lam_old - urel * row[36];
+                        if (kind == 0) lam = fmaxf(lam, 0.f);
+                        else { float lim = p.mu * es[ES_ROWS + nrow * PROWF + 38]; lam = fminf(fmaxf(lam, -lim), lim); }
+                        float dl = lam - lam_old;
+                        __syncwarp(env_mask);
+                        row[38] = lam;
+                        if (grp == ga) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) vb[k] += sa[9 + k] * dl;
+                            if (is_robot && leg == la) { u[0] += sa[15] * dl; u[1] += sa[16] * dl; u[2] += sa[17] * dl; }
+                        }
+                        if (grp == gb) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) vb[k] += sb[9 + k] * dl;
+                            if (is_robot && leg == lb) { u[0] += sb[15] * dl; u[1] += sb[16] * dl; u[2] += sb[17] * dl; }
+                        }
+                        __syncwarp(env_mask);
+                    }
+                }
+            }
+        }
+
+        // ================================================================ P5: contact force report (last substep), integrate
+        if (last) {
+            float idt = 1.f / p.dt;
+            if (is_robot && active) {
+                int ncon = (nrows - nlim) / 3;
+                for (int c = leg; c < ncon; c += 4) {
+                    const float *cmeta = rs + RS_CMETA + c * 4;
+                    V3 n = mk(cmeta[0], cmeta[1], cmeta[2]), t1, t2;
+                    tangent_basis(n, t1, t2);
+                    int body = __float_as_int(cmeta[3]);
+                    const float *row = rs + RS_ROWS + (nlim + 3 * c) * ROWF;
+                    V3 f = (row[20] * idt) * n + (row[ROWF + 20] * idt) * t1 + (row[2 * ROWF + 20] * idt) * t2;
+                    atomicAdd(rs + RS_FORCE + body * 3, f.x); atomicAdd(rs + RS_FORCE + body * 3 + 1, f.y); atomicAdd(rs + RS_FORCE + body * 3 + 2, f.z);
+                }
+            } else if (is_npc && active) {
+                for (int c = 0; c < nrows / 3; c++) {
+                    const float *cmeta = ns + NS_CMETA + c * 4;
+                    V3 n = mk(cmeta[0], cmeta[1], cmeta[2]), t1, t2;
+                    tangent_basis(n, t1, t2);
+                    const float *row = ns + NS_ROWS + 3 * c * ROWF;
+                    V3 f = (row[20] * idt) * n + (row[ROWF + 20] * idt) * t1 + (row[2 * ROWF + 20] * idt) * t2;
+                    ns[NS_FORCE] += f.x; ns[NS_FORCE + 1] += f.y; ns[NS_FORCE + 2] += f.z;
+                }
+            }
+            __syncwarp();
+            if (npair > 0 && active) {
+                for (int c = rank_in_env; c < npair; c += lanes_per_env) {
+                    const float *cmeta = es + ES_CMETA(maxpair) + c * 8;
+                    V3 n = mk(cmeta[0], cmeta[1], cmeta[2]), t1, t2;
+                    tangent_basis(n, t1, t2);
+                    int rba = __float_as_int(cmeta[3]), rbb = __float_as_int(cmeta[4]);
+                    const float *row = es + ES_ROWS + 3 * c * PROWF;
+                    V3 f = (row[38] * idt) * n + (row[PROWF + 38] * idt) * t1 + (row[2 * PROWF + 38] * idt) * t2;
+                    for (int side = 0; side < 2; side++) {
+                        int rb = side ? rbb : rba;
+                        float sg = side ? -1.f : 1.f;
+                        float *dst = rb < A * MQE_NUM_BODIES
+                                         ? wbase + (e_loc * A + rb / MQE_NUM_BODIES) * RS_SIZE + RS_FORCE + (rb % MQE_NUM_BODIES) * 3
+                                         : wbase + E * A * RS_SIZE + (e_loc * P + rb - A * MQE_NUM_BODIES) * NS_SIZE + NS_FORCE;
+                        atomicAdd(dst, sg * f.x); atomicAdd(dst + 1, sg * f.y); atomicAdd(dst + 2, sg * f.z);
+                    }
+                }
+            }
+            __syncwarp();
+            if (active) {
+                float *cf = p.contact + (size_t)env * p.NB * 3;
+                if (is_robot) for (int i = leg; i < 51; i += 4) cf[ag * 51 + i] = rs[RS_FORCE + i];
+                else for (int i = 0; i < 3; i++) cf[(A * MQE_NUM_BODIES + pn) * 3 + i] = ns[NS_FORCE + i];
+            }
+        }
+        if (is_robot) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float gt = 0.f;
+#pragma unroll
+                for (int i = 0; i < 6; i++) gt += Gm[i * 3 + k] * vb[i];
+                float v = u[k] - gt, lim = md->qd_limit[3 * leg + k];
+                v = fminf(fmaxf(v, -lim), lim);
+                qd[k] = v;
+                q[k] += p.dt * v;
+            }
+        }
+        if (is_robot || is_npc) {
+            wang = mk(vb[0], vb[1], vb[2]); vlin = mk(vb[3], vb[4], vb[5]);
+            pos = pos + p.dt * vlin;
+            float wn = sqrtf(dot(wang, wang)), th = wn * p.dt, dx, dy, dz, dw;
+            if (th < 1e-8f) { dx = wang.x * p.dt * 0.5f; dy = wang.y * p.dt * 0.5f; dz = wang.z * p.dt * 0.5f; dw = 1.f; }
+            else { float sn, cs; sincosf(th * 0.5f, &sn, &cs); float s = sn / wn; dx = wang.x * s; dy = wang.y * s; dz = wang.z * s; dw = cs; }
+            float nx = dw * qx + dx * qw + dy * qz - dz * qy;
+            float ny = dw * qy - dx * qz + dy * qw + dz * qx;
+            float nz = dw * qz + dx * qy - dy * qx + dz * qw;
+            float nw = dw * qw - dx * qx - dy * qy - dz * qz;
+            float inv = 1.f / sqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+            qx = nx * inv; qy = ny * inv; qz = nz * inv; qw = nw * inv;
+        }
+        __syncwarp();
+    }
+
+    // ---- write back ----
+    if (active) {
+        if (is_npc || leg == 0) {
+            float *r = p.root + ((size_t)env * GA + grp) * 13;
+            r[0] = pos.x; r[1] = pos.y; r[2] = pos.z; r[3] = qx; r[4] = qy; r[5] = qz; r[6] = qw;
+            r[7] = vlin.x; r[8] = vlin.y; r[9] = vlin.z; r[10] = wang.x; r[11] = wang.y; r[12] = wang.z;
+        }
+        if (is_robot) {
+            float *d = p.dof + ((size_t)env * (12 * A + p.D) + 12 * ag + 3 * leg) * 2;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                d[2 * k] = q[k]; d[2 * k + 1] = qd[k];
+                int j = m_idx * 12 + 3 * leg + k;
+                p.err1[j] = e1[k]; p.err2[j] = e2[k]; p.vel1[j] = v1[k]; p.vel2[j] = v2[k];
+                p.torques[j] = tau[k];
+            }
+        }
+        if (is_npc || leg == 0) {
+            atomicAdd(p.stats + 0, stat_local); atomicAdd(p.stats + 1, stat_lim);
+            atomicMax(p.stats + 3, stat_rows);
+        }
+        if (rank_in_env == 0) atomicAdd(p.stats + 2, stat_pair);
+    }
+}
+
+// stand-alone actuator network (parity tests against unitree_go1.pt): x [rows][6] -> torque [rows], unclipped
+__global__ void k_actuator(const float *__restrict__ aw, const float *__restrict__ x, int rows, float *__restrict__ out) {
+    __shared__ float w[ACTW_FLOATS];
+    for (int i = threadIdx.x; i < 1313; i += blockDim.x) w[i] = aw[i];
+    __syncthreads();
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float xi[6], h0[32];
+    for (int i = 0; i < 6; i++) xi[i] = x[(size_t)r * 6 + i];
+    for (int o = 0; o < 32; o++) {
+        float s = w[192 + o];
+        for (int i = 0; i < 6; i++) s += w[o * 6 + i] * xi[i];
+        h0[o] = softsign(s);
+    }
+    float y = w[1312];
+    for (int o = 0; o < 32; o++) {
+        float s = w[1248 + o];
+        for (int i = 0; i < 32; i++) s += w[224 + o * 32 + i] * h0[i];
+        y += w[1280 + o] * softsign(s);
+    }
+    out[r] = y;
+}
+
+// host-side launchers (api.cu)
+static int substeps_warps_per_cta(int A, int Pd, int E, int maxpair) {
+    const size_t budget = 200 * 1024, hdr = (size_t)physics_cta_header_floats() * 4, per = (size_t)physics_warp_smem_floats(A, Pd, E, maxpair) * 4;
+    int w = (int)((budget - hdr) / per);
+    return w > 4 ? 4 : w;
+}
+extern "C" size_t mqe_substeps_smem_bytes(int A, int Pd, int E, int maxpair) {
+    int w = substeps_warps_per_cta(A, Pd, E, maxpair);
+    if (w < 1) w = 1;
+    return (size_t)(physics_cta_header_floats() + w * physics_warp_smem_floats(A, Pd, E, maxpair)) * sizeof(float);
+}
+extern "C" cudaError_t mqe_launch_actuator(const float *act_w, const float *x, int rows, float *out, cudaStream_t st) {
+    k_actuator<<<(rows + 127) / 128, 128, 0, st>>>(act_w, x, rows, out);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, const unsigned int *pair_table, int n_pair_entries, cudaStream_t st) {
+    int warps_per_cta = substeps_warps_per_cta(p.A, p.Pd, p.E, maxpair);
+    if (warps_per_cta < 1) return cudaErrorInvalidConfiguration;
+    int envs_per_cta = warps_per_cta * p.E;
+    int grid = (p.N + envs_per_cta - 1) / envs_per_cta;
+    size_t smem = mqe_substeps_smem_bytes(p.A, p.Pd, p.E, maxpair);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    k_substeps<<<grid, warps_per_cta * 32, smem, st>>>(p, nsub, maxpair, pair_table, n_pair_entries);
+    return cudaGetLastError();
+}

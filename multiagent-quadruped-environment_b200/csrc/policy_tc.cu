@@ -1,0 +1,230 @@
+// policy_tc.cu -- layer 0 of the walk-these-ways networks on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// The only genuinely dense contraction on the Go1.step() path (go1.py:400-407): for every agent row the 30 x 70
+// observation history against adapt.0 (256 x 2100) and body.0[:, :2100] (512 x 2100), fused into one
+// [M x 2400(padded)] x [2400 x 768] GEMM = 89 % of the policy FLOPs.  fp32 parity is kept by splitting every operand
+// into bf16 hi + lo and issuing three MMAs (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM accumulator
+// ("bf16x3"; the dropped lo*lo term is < 2^-16 relative).  passes == 1 runs plain bf16.
+//
+// Data layout (HBM):  both operands are stored pre-tiled in the tcgen05 no-swizzle K-major canonical layout, so one
+// stage of the pipeline is four contiguous 20 KB bulk copies (cp.async.bulk -> UBLKCP), no tensor maps:
+//     ring  : [M/128 row tiles][30 slots ][10 k-chunks][128 rows][8 bf16]     (hi and lo planes)
+//     weight: [6 col tiles    ][30 blocks][10 k-chunks][128 rows][8 bf16]
+// A core matrix (8 rows x 16 B) is contiguous (128 B); SBO = 128 B between row groups, LBO = 2048 B between k-chunks.
+// The ring never shifts: slot s is contracted with weight block (s - head - 1) mod 30 (its age).
+//
+// CTA = 128 rows x 128 columns, 6 warps: warp 0 producer (bulk copies, mbarrier expect_tx), warp 1 MMA issuer
+// (one elected lane; tcgen05.commit releases stages), warps 2..5 epilogue (tcgen05.ld 32x32b, bias + ELU, store Z).
+#include <vector>
+
+#include "kernels.cuh"
+
+#define TC_TILE_ELEMS (10 * 128 * 8)
+#define TC_TILE_BYTES (TC_TILE_ELEMS * 2)
+#define TC_STAGES 2
+#define TC_STAGE_BYTES (4 * TC_TILE_BYTES)
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 128)
+#define TC_TMEM_COLS 128
+#define TC_LBO 2048u
+#define TC_SBO 128u
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), done = 0;
+    for (unsigned long long spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (spin > (1ull << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float elu1_tc(float x) { return x > 0.f ? x : expm1f(x); }
+
+__global__ void __launch_bounds__(192, 1)
+k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo,
+               const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
+               const float *__restrict__ b0cat, float *__restrict__ Z, int M, int head, int passes) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *accum = empty + TC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntile = blockIdx.x, mtile = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t stage_tx = passes == 3 ? TC_STAGE_BYTES : 2 * TC_TILE_BYTES;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < MQE_HIST_FRAMES; it++) {
+                const int st = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                mbar_expect_tx(&full[st], stage_tx);
+                int blk = it - head - 1;
+                if (blk < 0) blk += MQE_HIST_FRAMES;
+                unsigned char *sb = smem + st * TC_STAGE_BYTES;
+                const size_t ao = ((size_t)mtile * MQE_HIST_FRAMES + it) * TC_TILE_ELEMS;
+                const size_t bo = ((size_t)ntile * MQE_HIST_FRAMES + blk) * TC_TILE_ELEMS;
+                bulk_g2s(sb, a_hi + ao, TC_TILE_BYTES, &full[st]);
+                bulk_g2s(sb + 2 * TC_TILE_BYTES, b_hi + bo, TC_TILE_BYTES, &full[st]);
+                if (passes == 3) {
+                    bulk_g2s(sb + TC_TILE_BYTES, a_lo + ao, TC_TILE_BYTES, &full[st]);
+                    bulk_g2s(sb + 3 * TC_TILE_BYTES, b_lo + bo, TC_TILE_BYTES, &full[st]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B bf16 K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+            for (int it = 0; it < MQE_HIST_FRAMES; it++) {
+                const int st = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(&full[st], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sb = smem_u32(smem + st * TC_STAGE_BYTES);
+                const uint64_t dAh = umma_desc(sb), dAl = umma_desc(sb + TC_TILE_BYTES);
+                const uint64_t dBh = umma_desc(sb + 2 * TC_TILE_BYTES), dBl = umma_desc(sb + 3 * TC_TILE_BYTES);
+#pragma unroll
+                for (int j = 0; j < 5; j++) umma_f16(tmem, dAh + j * 256, dBh + j * 256, idesc, (it | j) ? 1u : 0u);
+                if (passes == 3) {
+#pragma unroll
+                    for (int j = 0; j < 5; j++) umma_f16(tmem, dAh + j * 256, dBl + j * 256, idesc, 1u);
+#pragma unroll
+                    for (int j = 0; j < 5; j++) umma_f16(tmem, dAl + j * 256, dBh + j * 256, idesc, 1u);
+                }
+                umma_commit(&empty[st]);             // implies tcgen05.fence::before_thread_sync
+            }
+            umma_commit(accum);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(accum, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int row = mtile * 128 + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < 4; c++) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int n0 = ntile * 128 + c * 32;
+            if (row < M) {
+                float *dst = Z + (size_t)row * 768 + n0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float4 o;
+                    float t0 = __uint_as_float(v[i]) + __ldg(b0cat + n0 + i), t1 = __uint_as_float(v[i + 1]) + __ldg(b0cat + n0 + i + 1);
+                    float t2 = __uint_as_float(v[i + 2]) + __ldg(b0cat + n0 + i + 2), t3 = __uint_as_float(v[i + 3]) + __ldg(b0cat + n0 + i + 3);
+                    if (n0 < 256) { t0 = elu1_tc(t0); t1 = elu1_tc(t1); t2 = elu1_tc(t2); t3 = elu1_tc(t3); }
+                    o.x = t0; o.y = t1; o.z = t2; o.w = t3;
+                    *reinterpret_cast<float4 *>(dst + i) = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static inline unsigned short f2bf_rne(float v) {
+    uint32_t b;
+    memcpy(&b, &v, 4);
+    return (unsigned short)((b + 0x7fffu + ((b >> 16) & 1u)) >> 16);
+}
+static inline float bf2f(unsigned short h) {
+    uint32_t b = (uint32_t)h << 16;
+    float v;
+    memcpy(&v, &b, 4);
+    return v;
+}
+
+extern "C" int mqe_policy_tc_prepare(const MqeWeights *w, PolicyTcWeights *out, cudaStream_t st) {
+    const size_t n = (size_t)6 * MQE_HIST_FRAMES * TC_TILE_ELEMS;
+    std::vector<unsigned short> hi(n, 0), lo(n, 0);
+    for (int col = 0; col < 768; col++) {
+        const float *src = col < 256 ? w->adapt_w0 + (size_t)col * 2100 : w->body_w0 + (size_t)(col - 256) * 2102;
+        const int nt = col >> 7, r = col & 127;
+        for (int b = 0; b < MQE_HIST_FRAMES; b++)
+            for (int i = 0; i < MQE_LOC_OBS; i++) {
+                float v = src[b * MQE_LOC_OBS + i];
+                unsigned short h = f2bf_rne(v), l = f2bf_rne(v - bf2f(h));
+                size_t o = ((((size_t)nt * MQE_HIST_FRAMES + b) * 10 + (i >> 3)) * 128 + r) * 8 + (i & 7);
+                hi[o] = h; lo[o] = l;
+            }
+    }
+    void *blob = nullptr;
+    if (cudaMalloc(&blob, 2 * n * sizeof(unsigned short)) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(blob, hi.data(), n * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync((unsigned short *)blob + n, lo.data(), n * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_policy_l0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) return -1;
+    out->blob = blob;
+    out->bytes = 2 * n * sizeof(unsigned short);
+    out->l0_hi = blob;
+    out->l0_lo = (unsigned short *)blob + n;
+    return 0;
+}
+
+// layer 0 only: Z[M][768] = act(ring x W0cat^T + b0cat), ELU on the adapt columns (< 256); the body columns stay
+// pre-activation until the latent columns are added (k_body_latent).
+extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat, const unsigned short *hist_hi,
+                                               const unsigned short *hist_lo, int head, int rows, int passes, float *Z, cudaStream_t st) {
+    dim3 grid(6, (rows + 127) / 128);
+    k_policy_l0_tc<<<grid, 192, TC_SMEM_BYTES, st>>>(hist_hi, hist_lo, (const unsigned short *)w.l0_hi, (const unsigned short *)w.l0_lo,
+                                                      b0cat, Z, rows, head, passes);
+    return cudaGetLastError();
+}

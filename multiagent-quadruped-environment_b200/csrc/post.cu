@@ -1,0 +1,240 @@
+// post.cu -- everything Go1.step() does after the decimation loop, one thread per environment:
+//   post_physics_step (legged_robot_field.py:117-119 -> legged_robot.py:117-157): derived base quantities, gait clock
+//   (go1.py:240-279), termination (legged_robot.py:159-169 + legged_robot_field.py:121-146), NPC stepping
+//   (go1_sheep.py:35-64), indexed reset (go1.py:110-145, legged_robot.py:394-470) and compute_observations
+//   (go1.py:153-196), plus Go1.reset() (go1.py:147-151).
+// The reference spends ~100 tiny torch launches, one nonzero() sync and 4 .cpu() syncs here; this is one launch and
+// no host round trip (reset envs are handled in place from the reset mask, never gathered into an index list).
+#include "common.cuh"
+
+__device__ __forceinline__ float lerp_range(const float *r, float u) { return r[0] + (r[1] - r[0]) * u; }
+
+// reset_idx for one env: _reset_dofs, _reset_root_states, _reset_buffers
+__device__ void dev_env_reset(const DevParams &p, int e) {
+    const int A = p.A, P = p.P, G = p.G;
+    const uint32_t ge = (uint32_t)(e + p.env_off), ep = p.episode[e];
+    float *dof = p.dof + (size_t)e * (12 * A + p.D) * 2;
+    for (int a = 0; a < A; a++) {
+        const int m = e * A + a;
+        for (int j = 0; j < 12; j++) {
+            float u = rng_uniform(p.seed, ge, ep, RNG_DOF, a * 12 + j);
+            dof[(12 * a + j) * 2] = p.model->q_default[j] * (p.dof_lo + (p.dof_hi - p.dof_lo) * u);
+            dof[(12 * a + j) * 2 + 1] = 0.f;
+        }
+        float *rs = p.root + ((size_t)e * G + a) * 13;
+        for (int i = 0; i < 13; i++) rs[i] = p.base_init[m * 13 + i];
+        for (int i = 0; i < 3; i++) rs[i] += p.agent_origins[m * 3 + i];
+        if (p.has_bpos) {
+            rs[0] += lerp_range(p.bpos_x, rng_uniform(p.seed, ge, ep, RNG_BASE_POS, a * 2));
+            rs[1] += lerp_range(p.bpos_y, rng_uniform(p.seed, ge, ep, RNG_BASE_POS, a * 2 + 1));
+        }
+        for (int i = 0; i < 6; i++) rs[7 + i] = p.bvel_lo + (p.bvel_hi - p.bvel_lo) * rng_uniform(p.seed, ge, ep, RNG_BASE_VEL, a * 6 + i);
+        for (int j = 0; j < 12; j++) { p.last_actions[m * 12 + j] = 0.f; p.last_dof_vel[m * 12 + j] = 0.f; }
+        p.gait[m] = 0.f;
+    }
+    p.hist_dirty[e] = 1;          // history_locomotion_obs[env_ids] = 0, applied by the next k_policy_frame
+    for (int k = 0; k < p.D; k++) { dof[(12 * A + k) * 2] = p.npc_dof_default[k]; dof[(12 * A + k) * 2 + 1] = 0.f; }
+    for (int n = 0; n < P; n++) {
+        float *rs = p.root + ((size_t)e * G + A + n) * 13;
+        for (int i = 0; i < 13; i++) rs[i] = p.npc_init[(e * P + n) * 13 + i];
+        for (int i = 0; i < 3; i++) rs[i] += p.env_origins[e * 3 + i];
+        if (p.has_npos) {
+            rs[0] += lerp_range(p.npos_x, rng_uniform(p.seed, ge, ep, RNG_NPC_POS, n * 2));
+            rs[1] += lerp_range(p.npos_y, rng_uniform(p.seed, ge, ep, RNG_NPC_POS, n * 2 + 1));
+        }
+        if (p.has_nrpy) {
+            float r = lerp_range(p.nrpy_r, rng_uniform(p.seed, ge, ep, RNG_NPC_RPY, n * 3));
+            float pp = lerp_range(p.nrpy_p, rng_uniform(p.seed, ge, ep, RNG_NPC_RPY, n * 3 + 1));
+            float y = lerp_range(p.nrpy_y, rng_uniform(p.seed, ge, ep, RNG_NPC_RPY, n * 3 + 2));
+            quat_from_euler_xyz(r, pp, y, rs + 3);
+        }
+    }
+    p.ep_len[e] = 0;
+    p.reset_buf[e] = 1;
+    p.episode[e] = ep + 1;
+}
+
+// compute_observations for one env (go1.py:153-196)
+__device__ void dev_env_observations(const DevParams &p, int e) {
+    const int A = p.A, G = p.G;
+    for (int a = 0; a < A; a++) {
+        const int m = e * A + a;
+        float *ob = p.obs + (size_t)m * MQE_OBS_FLOATS;
+        const float *rs = p.root + ((size_t)e * G + a) * 13;
+        const float *dof = p.dof + ((size_t)e * (12 * A + p.D) + 12 * a) * 2;
+        const float *bq = p.quat_alias ? rs + 3 : p.base_quat + m * 4;
+        float q4[4] = {bq[0], bq[1], bq[2], bq[3]};
+        for (int i = 0; i < 3; i++) ob[MQE_OBS_BASE_POS + i] = rs[i] - p.env_origins[e * 3 + i];
+        for (int i = 0; i < 4; i++) ob[MQE_OBS_BASE_QUAT + i] = q4[i];
+        for (int j = 0; j < 12; j++) {
+            ob[MQE_OBS_DOF_POS + j] = dof[j * 2] - p.model->q_default[j];
+            ob[MQE_OBS_DOF_VEL + j] = dof[j * 2 + 1] * 0.05f;
+            ob[MQE_OBS_LAST_ACTION + j] = p.actions[m * 12 + j];
+            ob[MQE_OBS_LAST_LAST_ACTION + j] = p.last_actions[m * 12 + j];
+        }
+        for (int i = 0; i < 3; i++) {
+            ob[MQE_OBS_LIN_VEL + i] = p.base_lin_vel[m * 3 + i] * 2.0f;
+            ob[MQE_OBS_ANG_VEL + i] = p.base_ang_vel[m * 3 + i] * 0.25f;
+            ob[MQE_OBS_PROJ_GRAVITY + i] = p.proj_grav[m * 3 + i];
+        }
+        for (int i = 0; i < 4; i++) ob[MQE_OBS_CLOCK + i] = p.clock[m * 4 + i];
+        float rpy[3];
+        get_euler_xyz(q4, rpy);
+        for (int i = 0; i < 3; i++) ob[MQE_OBS_BASE_RPY + i] = rpy[i];
+    }
+}
+
+// _step_contact_targets (go1.py:240-279)
+__device__ void dev_gait_clock(const DevParams &p, int m, float dt_policy) {
+    const float *lo = p.loc_obs + (size_t)m * MQE_LOC_OBS;
+    float freq = lo[7], phase = lo[8], offset = lo[9], bound = lo[10], dur = lo[11];
+    float g = fmodf(p.gait[m] + dt_policy * freq, 1.0f);
+    if (g < 0.f) g += 1.f;
+    p.gait[m] = g;
+    float fi[4] = {g + phase + offset + bound, g + offset, g + bound, g + phase};
+    for (int i = 0; i < 4; i++) {
+        float r = fmodf(fi[i], 1.0f);
+        if (r < 0.f) r += 1.f;
+        float x = fi[i];
+        if (r < dur) x = r * (0.5f / dur);
+        else if (r > dur) x = 0.5f + (r - dur) * (0.5f / (1.f - dur));
+        p.clock[m * 4 + i] = sinf(6.28318530717958647692f * x);
+    }
+}
+
+// Go1Sheep._step_npc (go1_sheep.py:35-64)
+__device__ void dev_sheep_step(const DevParams &p, int e, uint32_t step_count) {
+    const int A = p.A, P = p.P, G = p.G;
+    float *root = p.root + (size_t)e * G * 13;
+    float avg[3] = {0.f, 0.f, 0.f}, var[2] = {0.f, 0.f};
+    for (int n = 0; n < P; n++) for (int i = 0; i < 3; i++) avg[i] += root[(A + n) * 13 + i] / (float)P;
+    for (int n = 0; n < P; n++) for (int i = 0; i < 2; i++) { float t = root[(A + n) * 13 + i] - avg[i]; var[i] += t * t / (float)P; }
+    p.sheep_stats[e * 3] = avg[0]; p.sheep_stats[e * 3 + 1] = avg[1]; p.sheep_stats[e * 3 + 2] = var[0] + var[1];
+    const uint32_t ge = (uint32_t)(e + p.env_off);
+    for (int n = 0; n < P; n++) {
+        float *rs = root + (A + n) * 13, dv[3];
+        for (int i = 0; i < 3; i++) dv[i] = p.sheep_rand * rng_normal(p.seed, ge, step_count, RNG_SHEEP, n * 3 + i) * 2.f;
+        if (P != 1) {
+            float rel[3] = {avg[0] - rs[0], avg[1] - rs[1], avg[2] - rs[2]};
+            float nn = sqrtf(rel[0] * rel[0] + rel[1] * rel[1] + rel[2] * rel[2]);
+            for (int i = 0; i < 3; i++) dv[i] += p.sheep_rand * rel[i] / nn / 1.5f;
+        }
+        for (int a = 0; a < A; a++) {
+            float rel[3] = {rs[0] - root[a * 13], rs[1] - root[a * 13 + 1], rs[2] - root[a * 13 + 2]};
+            float sq[3] = {rel[0] * rel[0], rel[1] * rel[1], rel[2] * rel[2]};
+            float dis = sqrtf(sq[0] * sq[0] + sq[1] * sq[1] + sq[2] * sq[2]);     // torch.norm(relative_pos ** 2)
+            if (dis > 9.f) continue;
+            float den = powf(dis, 1.4f);
+            for (int i = 0; i < 3; i++) dv[i] += p.sheep_scale * rel[i] / den;
+        }
+        dv[2] = 0.f;
+        for (int i = 0; i < 3; i++) rs[7 + i] += dv[i];
+        for (int i = 0; i < 2; i++) rs[7 + i] = fminf(fmaxf(rs[7 + i], -2.f), 2.f);
+        rs[2] = fminf(fmaxf(rs[2], 0.f), 0.3f);
+        rs[3] = 0.f; rs[4] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_post_physics(DevParams p, unsigned int step_count) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.N) return;
+    const int A = p.A, P = p.P, G = p.G;
+    const float PI = 3.14159265358979323846f;
+    const float dt_policy = p.dt * (float)p.decimation;
+    long long ep = p.ep_len[e] + 1;
+    p.ep_len[e] = ep;
+    int collide = 0, rt = 0, pt = 0, zl = 0, zh = 0;
+    for (int a = 0; a < A; a++) {
+        const int m = e * A + a;
+        const float *rs = p.root + ((size_t)e * G + a) * 13;
+        float q4[4] = {rs[3], rs[4], rs[5], rs[6]};
+        for (int i = 0; i < 4; i++) p.base_quat[m * 4 + i] = q4[i];
+        V3 lv = quat_rotate_inverse(q4, mk(rs[7], rs[8], rs[9]));
+        V3 av = quat_rotate_inverse(q4, mk(rs[10], rs[11], rs[12]));
+        V3 pg = quat_rotate_inverse(q4, mk(0.f, 0.f, -1.f));
+        p.base_lin_vel[m * 3] = lv.x; p.base_lin_vel[m * 3 + 1] = lv.y; p.base_lin_vel[m * 3 + 2] = lv.z;
+        p.base_ang_vel[m * 3] = av.x; p.base_ang_vel[m * 3 + 1] = av.y; p.base_ang_vel[m * 3 + 2] = av.z;
+        p.proj_grav[m * 3] = pg.x; p.proj_grav[m * 3 + 1] = pg.y; p.proj_grav[m * 3 + 2] = pg.z;
+        dev_gait_clock(p, m, dt_policy);
+        const float *cf = p.contact + ((size_t)e * p.NB + a * MQE_NUM_BODIES) * 3;          // body 0 = base
+        if (sqrtf(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]) > 1.f) collide = 1;
+        float rpy[3];
+        get_euler_xyz(q4, rpy);
+        if (rpy[0] > PI) rpy[0] -= 2.f * PI;
+        if (rpy[1] > PI) rpy[1] -= 2.f * PI;
+        float z = rs[2] - p.agent_origins[m * 3 + 2];
+        if (fabsf(rpy[0]) > p.term_roll) rt = 1;
+        if (fabsf(rpy[1]) > p.term_pitch) pt = 1;
+        if (z < p.term_zlow) zl = 1;
+        if (z > p.term_zhigh) zh = 1;
+    }
+    int reset = 0;
+    if (p.term_mask & 16) { p.collide_buf[e] = (unsigned char)collide; reset |= collide; }
+    int to = ep > (long long)p.max_ep_len;
+    p.timeout_buf[e] = (unsigned char)to;
+    reset |= to;
+    if (p.term_mask & 1) { p.r_term[e] = (unsigned char)rt; reset |= rt; }
+    if (p.term_mask & 2) { p.p_term[e] = (unsigned char)pt; reset |= pt; }
+    if (p.term_mask & 4) { p.zl_term[e] = (unsigned char)zl; reset |= zl; }
+    if (p.term_mask & 8) { p.zh_term[e] = (unsigned char)zh; reset |= zh; }
+    p.reset_buf[e] = (unsigned char)reset;
+    if (P && p.npc_ctrl == MQE_NPC_SHEEP) dev_sheep_step(p, e, step_count);
+    if (reset) dev_env_reset(p, e);
+    dev_env_observations(p, e);
+    for (int a = 0; a < A; a++) {
+        const int m = e * A + a;
+        const float *rs = p.root + ((size_t)e * G + a) * 13;
+        const float *dof = p.dof + ((size_t)e * (12 * A + p.D) + 12 * a) * 2;
+        for (int j = 0; j < 12; j++) { p.last_actions[m * 12 + j] = p.actions[m * 12 + j]; p.last_dof_vel[m * 12 + j] = dof[j * 2 + 1]; }
+        for (int i = 0; i < 6; i++) p.last_root_vel[m * 6 + i] = rs[7 + i];
+    }
+}
+
+// Go1.reset(): reset_idx(arange(N)) then compute_observations (go1.py:147-151); no physics step
+__global__ void __launch_bounds__(128) k_reset_all(DevParams p) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.N) return;
+    dev_env_reset(p, e);
+    dev_env_observations(p, e);
+}
+
+// gym.set_actor_root_state_tensor_indexed / set_dof_state_tensor_indexed for hosts that stage state elsewhere
+__global__ void k_set_root_indexed(DevParams p, const float *__restrict__ src, const int *__restrict__ ids, int n) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 13) return;
+    int actor = ids[t / 13];
+    if (actor < 0 || actor >= p.N * p.G) return;
+    p.root[(size_t)actor * 13 + t % 13] = src[(size_t)actor * 13 + t % 13];
+}
+__global__ void k_set_dof_indexed(DevParams p, const float *__restrict__ src, const int *__restrict__ ids, int n) {
+    // actor -> its DOF range inside the env: agents own 12 DOFs each, the NPC block owns p.D
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 24) return;
+    int actor = ids[t / 24], k = t % 24;
+    if (actor < 0 || actor >= p.N * p.G) return;
+    int e = actor / p.G, g = actor % p.G, per_env = 12 * p.A + p.D, first, cnt;
+    if (g < p.A) { first = 12 * g; cnt = 12; }
+    else { int per = p.P ? p.D / p.P : 0; first = 12 * p.A + (g - p.A) * per; cnt = per; }
+    if (k >= 2 * cnt) return;
+    size_t off = ((size_t)e * per_env + first) * 2 + k;
+    p.dof[off] = src[off];
+}
+
+extern "C" cudaError_t mqe_launch_post(const DevParams &p, unsigned int step_count, cudaStream_t st) {
+    k_post_physics<<<(p.N + 127) / 128, 128, 0, st>>>(p, step_count);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t mqe_launch_reset_all(const DevParams &p, cudaStream_t st) {
+    k_reset_all<<<(p.N + 127) / 128, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t mqe_launch_set_root_indexed(const DevParams &p, const float *src, const int *ids, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_set_root_indexed<<<(n * 13 + 255) / 256, 256, 0, st>>>(p, src, ids, n);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t mqe_launch_set_dof_indexed(const DevParams &p, const float *src, const int *ids, int n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_set_dof_indexed<<<(n * 24 + 255) / 256, 256, 0, st>>>(p, src, ids, n);
+    return cudaGetLastError();
+}

@@ -34,6 +34,7 @@ OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
 NPC_NONE, NPC_RIGID, NPC_SEESAW = 0, 1, 2
 NPC_PASSIVE, NPC_SHEEP = 0, 1
 POLICY_FP32, POLICY_BF16X3, POLICY_BF16 = 0, 1, 2
+POLICY_MODE_DEFAULT = int(os.environ.get("MQE_POLICY_MODE", POLICY_FP32))
 
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -137,6 +138,7 @@ def load_library(path=None):
     lib.mqe_sim_create.argtypes = [ctypes.POINTER(SimDescC), i32, vp, ctypes.POINTER(vp)]
     lib.mqe_sim_destroy.argtypes = [vp]
     lib.mqe_sim_set_stream.argtypes = [vp, vp]
+    lib.mqe_sim_set_action_scale.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.mqe_sim_get_buffer.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_int32)]
     lib.mqe_sim_reset.argtypes = [vp]
     lib.mqe_sim_step.argtypes = [vp, vp]
@@ -148,7 +150,8 @@ def load_library(path=None):
     lib.mqe_sim_set_dof_indexed.argtypes = [vp, vp, vp, i32]
     lib.mqe_policy_forward.argtypes = [vp, vp, i32, vp, vp]
     lib.mqe_actuator_forward.argtypes = [vp, vp, i32, vp]
-    lib.mqe_robot_dynamics.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.mqe_sim_history_head.argtypes = [vp]
+    lib.mqe_sim_history_head.restype = i32
     lib.mqe_sim_synchronize.argtypes = [vp]
     lib.mqe_sim_launch_count.argtypes = [vp]
     lib.mqe_sim_launch_count.restype = i64
@@ -158,10 +161,10 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = [
-    "mqe_last_error", "mqe_abi_version", "mqe_device_count", "mqe_sim_create", "mqe_sim_destroy", "mqe_sim_set_stream",
+    "mqe_last_error", "mqe_abi_version", "mqe_device_count", "mqe_sim_create", "mqe_sim_destroy", "mqe_sim_set_stream", "mqe_sim_set_action_scale",
     "mqe_sim_get_buffer", "mqe_sim_reset", "mqe_sim_step", "mqe_sim_step_host", "mqe_sim_policy", "mqe_sim_substeps",
     "mqe_sim_post_physics", "mqe_sim_set_root_indexed", "mqe_sim_set_dof_indexed", "mqe_policy_forward",
-    "mqe_actuator_forward", "mqe_robot_dynamics", "mqe_sim_synchronize", "mqe_sim_launch_count",
+    "mqe_actuator_forward", "mqe_sim_history_head", "mqe_sim_synchronize", "mqe_sim_launch_count",
 ]
 
 
@@ -175,7 +178,7 @@ class _DevArray:
 
 _TYPESTR = {("f", 4): "<f4", ("u", 1): "|u1", ("i", 8): "<i8", ("i", 4): "<i4", ("h", 2): "<u2"}
 _BUF_KIND = {BUF_RESET: "u", BUF_TIMEOUT: "u", BUF_COLLIDE: "u", BUF_ROLL_TERM: "u", BUF_PITCH_TERM: "u",
-             BUF_ZLOW_TERM: "u", BUF_ZHIGH_TERM: "u", BUF_EPISODE_LENGTH: "i", BUF_STATS: "i", BUF_HISTORY: "h"}
+             BUF_ZLOW_TERM: "u", BUF_ZHIGH_TERM: "u", BUF_EPISODE_LENGTH: "i", BUF_STATS: "i"}
 
 
 class Engine:
@@ -254,6 +257,46 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.mqe_sim_launch_count(self.h))
+
+    def set_action_scale(self, scale):
+        arr = (ctypes.c_float * 3)(*[float(x) for x in scale])
+        self._check(self.lib.mqe_sim_set_action_scale(self.h, arr))
+
+    def history_head(self) -> int:
+        return int(self.lib.mqe_sim_history_head(self.h))
+
+    def history(self):
+        """history_locomotion_obs in the reference layout [M, 2100], oldest frame first (go1.py:102)."""
+        import torch
+        ring = self.tensor(BUF_HISTORY)                                    # [M, 30, 80]
+        order = [(self.history_head() + 1 + b) % 30 for b in range(30)]
+        return ring[:, order, :LOC_OBS].reshape(ring.shape[0], -1)
+
+    def policy_forward(self, history, want_latent=True):
+        """Stand-alone network op: history [rows, 2100] (cuda fp32) -> (latent [rows, 2], action [rows, 12])."""
+        import torch
+        h = history.contiguous()
+        rows = h.shape[0]
+        lat = torch.empty((rows, 2), device=h.device, dtype=torch.float32)
+        act = torch.empty((rows, 12), device=h.device, dtype=torch.float32)
+        self._check(self.lib.mqe_policy_forward(self.h, ctypes.c_void_p(h.data_ptr()), rows,
+                                                ctypes.c_void_p(lat.data_ptr()), ctypes.c_void_p(act.data_ptr())))
+        return lat, act
+
+    def actuator_forward(self, x):
+        import torch
+        x = x.contiguous()
+        out = torch.empty((x.shape[0],), device=x.device, dtype=torch.float32)
+        self._check(self.lib.mqe_actuator_forward(self.h, ctypes.c_void_p(x.data_ptr()), x.shape[0], ctypes.c_void_p(out.data_ptr())))
+        return out
+
+    def set_root_indexed(self, root_states, actor_ids):
+        self._check(self.lib.mqe_sim_set_root_indexed(self.h, ctypes.c_void_p(root_states.data_ptr()),
+                                                      ctypes.c_void_p(actor_ids.data_ptr()), int(actor_ids.numel())))
+
+    def set_dof_indexed(self, dof_states, actor_ids):
+        self._check(self.lib.mqe_sim_set_dof_indexed(self.h, ctypes.c_void_p(dof_states.data_ptr()),
+                                                     ctypes.c_void_p(actor_ids.data_ptr()), int(actor_ids.numel())))
 
     def set_stream(self, stream: int):
         self._check(self.lib.mqe_sim_set_stream(self.h, ctypes.c_void_p(stream)))

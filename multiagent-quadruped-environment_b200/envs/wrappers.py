@@ -1,0 +1,290 @@
+"""Task wrappers with the reference's observation / reward definitions (`mqe/envs/wrappers/*.py`).
+
+Differences from the reference that do not change any returned value:
+  * action clip and the [2, .5, .5] scale are applied inside the engine's frame kernel (`Go1.step_from_wrapper`);
+  * `reward_buffer[...]` accumulates device scalars instead of calling `.cpu()` per term per step
+    (e.g. go1_sheep_wrapper.py:77,83,93,105,112) -- `float(v)` / `v.cpu()` still works for loggers;
+  * the device is the env's device instead of a hard-coded "cuda".
+"""
+from __future__ import annotations
+
+import torch
+
+from .gym_shim import Wrapper, spaces
+
+
+class EmptyWrapper(Wrapper):
+    """empty_wrapper.py:4-17"""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.num_envs = self.env.num_envs
+        self.num_agents = self.env.num_agents
+        if hasattr(env.cfg.terrain, "BarrierTrack_kwargs"):
+            self.BarrierTrack_kwargs = env.cfg.terrain.BarrierTrack_kwargs
+        for key in dir(self.env.cfg.rewards.scales):
+            if key[0] != "_" and "scale" in key:
+                setattr(self, key, getattr(self.env.cfg.rewards.scales, key))
+        dev = self.env.device
+        self.obs_ids = torch.eye(self.num_agents, dtype=torch.float32, device=dev).repeat(self.num_envs, 1).reshape(
+            self.num_envs, self.num_agents, -1)
+
+    def _acc(self, key, value):
+        self.reward_buffer[key] = self.reward_buffer[key] + value
+
+    def _base_info(self, obs_buf):
+        return torch.cat([obs_buf.base_pos, obs_buf.base_rpy], dim=1).reshape(self.env.num_envs, self.env.num_agents, -1)
+
+
+class Go1GateWrapper(EmptyWrapper):
+    """go1_gate_wrapper.py.  The shipped reference returns `obs = 0, reward = 0` (its 16-D observation and 8 reward
+    terms are commented out, :68, :155); `legacy_zero_outputs=False` enables the intended definitions (:78-154)."""
+
+    def __init__(self, env, legacy_zero_outputs=True):
+        super().__init__(env)
+        self.legacy_zero_outputs = legacy_zero_outputs
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(14 + self.num_agents,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.reward_buffer = {"target reward": 0, "success reward": 0, "agent distance punishment": 0,
+                              "contact punishment": 0, "step count": 0}
+        self.gate_pos = None
+
+    def _init_extras(self, obs):
+        if self.legacy_zero_outputs:
+            return
+        kw = self.BarrierTrack_kwargs
+        gate = obs.env_info["gate_deviation"].clone()
+        gate[:, 0] += kw["init"]["block_length"] + kw["gate"]["block_length"] / 2
+        self.gate_pos = gate.unsqueeze(1).repeat(1, self.num_agents, 1)
+        self.gate_distance = self.gate_pos.reshape(-1, 2)[:, 0]
+        self.target_pos = torch.zeros_like(self.gate_pos)
+        self.target_pos[:, :, 0] = kw["init"]["block_length"] + kw["gate"]["block_length"] + kw["plane"]["block_length"] / 2
+        self.target_pos[:, 0, 1] = kw["track_width"] / 4
+        self.target_pos[:, 1, 1] = -kw["track_width"] / 4
+        self.target_pos = self.target_pos.reshape(-1, 2)
+
+    def _obs(self, obs_buf):
+        base_info = self._base_info(obs_buf)
+        return torch.cat([self.obs_ids, base_info, torch.flip(base_info, [1]), self.gate_pos], dim=2)
+
+    def reset(self):
+        obs_buf = self.env.reset()
+        if self.gate_pos is None:
+            self._init_extras(obs_buf)
+        return 0 if self.legacy_zero_outputs else self._obs(obs_buf)
+
+    def step(self, action):
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        if self.gate_pos is None:
+            self._init_extras(obs_buf)
+        if self.legacy_zero_outputs:
+            return 0, 0, termination, info
+        obs = self._obs(obs_buf)
+        self._acc("step count", 1)
+        reward = torch.zeros([self.env.num_envs, self.env.num_agents], device=self.env.device)
+        base_pos = obs_buf.base_pos
+        if self.target_reward_scale != 0:                                   # :87-101
+            distance_to_target = torch.norm(base_pos[:, :2] - self.target_pos, p=2, dim=1)
+            if not hasattr(self, "last_distance_to_target"):
+                self.last_distance_to_target = distance_to_target.clone()
+            target_reward = (self.last_distance_to_target - distance_to_target).reshape(self.num_envs, -1).sum(dim=1, keepdim=True)
+            target_reward[self.env.reset_buf] = 0
+            target_reward *= self.target_reward_scale
+            reward += target_reward.repeat(1, self.env.num_agents)
+            self.last_distance_to_target = distance_to_target.clone()
+            self._acc("target reward", torch.sum(target_reward))
+        if self.contact_punishment_scale != 0:                              # :103-107
+            collide_reward = self.contact_punishment_scale * self.env.collide_buf
+            reward += collide_reward.unsqueeze(1).repeat(1, self.num_agents)
+            self._acc("contact punishment", torch.sum(collide_reward))
+        if self.success_reward_scale != 0:                                  # :109-114
+            success_reward = torch.zeros([self.env.num_envs * self.env.num_agents], device=self.env.device)
+            success_reward[base_pos[:, 0] > self.gate_distance + 0.25] = self.success_reward_scale
+            reward += success_reward.reshape([self.env.num_envs, self.env.num_agents])
+            self._acc("success reward", torch.sum(success_reward))
+        if self.agent_distance_punishment_scale != 0:                       # :128-134
+            agent_dis = (base_pos[:, :2] - torch.flip(base_pos[:, :2].reshape(self.num_envs, self.num_agents, 2), dims=[1]).reshape(-1, 2)) ** 2
+            agent_dis = agent_dis.sum(dim=1).reshape(self.num_envs, -1)
+            pun = torch.where(agent_dis < 0.25, self.agent_distance_punishment_scale / agent_dis.clamp_min(1e-12), torch.zeros_like(agent_dis))
+            reward += pun
+            self._acc("agent distance punishment", torch.sum(pun))
+        reward = reward.sum(dim=1).unsqueeze(1).repeat(1, self.num_agents)  # :154
+        return obs, reward, termination, info
+
+
+class Go1SheepWrapper(EmptyWrapper):
+    """go1_sheep_wrapper.py:8-118"""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"),
+                                            shape=(14 + 2 * self.cfg.env.num_npcs + self.num_agents,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.reward_buffer = {"success reward": 0, "contact punishment": 0, "sheep movement reward": 0,
+                              "mixed sheep reward": 0, "sheep pos var punishment": 0, "step count": 0}
+        self.gate_pos = None
+        self.last_sheep_pos_avg = None
+
+    def _init_extras(self, obs):
+        kw = self.BarrierTrack_kwargs
+        gate_pos = obs.env_info["gate_deviation"]                           # mutated in place, as the reference does (:31-32)
+        gate_pos[:, 0] += kw["init"]["block_length"] + kw["plane"]["block_length"] + kw["gate"]["block_length"] / 2
+        self.gate_pos = gate_pos.unsqueeze(1)
+        self.gate_distance = gate_pos[:, 0].unsqueeze(1).repeat(1, self.num_npcs)
+
+    def _obs(self, obs_buf):
+        sheep_pos = self.root_states_npc[:, :3].reshape(self.num_envs, -1, 3) - self.npc_env_origins
+        flat = sheep_pos[..., :2].reshape(self.num_envs, 1, -1).repeat(1, self.num_agents, 1)
+        base_info = self._base_info(obs_buf)
+        obs = torch.cat([self.obs_ids, base_info, torch.flip(base_info, [1]), self.gate_pos.repeat(1, self.num_agents, 1), flat], dim=2)
+        return obs, sheep_pos
+
+    def reset(self):
+        obs_buf = self.env.reset()
+        if self.gate_pos is None:
+            self._init_extras(obs_buf)
+        obs, _ = self._obs(obs_buf)
+        self.last_sheep_pos_avg = None
+        return obs
+
+    def step(self, action):
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        if self.gate_pos is None:
+            self._init_extras(obs_buf)
+        obs, sheep_pos = self._obs(obs_buf)
+        self._acc("step count", 1)
+        reward = torch.zeros([self.env.num_envs, 1], device=self.env.device)
+        if self.success_reward_scale != 0:
+            success_reward = ((sheep_pos[:, :, 0] - self.gate_distance) > 0).sum(dim=1)
+            reward[:, 0] = success_reward
+            self._acc("success reward", torch.sum(success_reward))
+        if self.contact_punishment_scale != 0:
+            collide_reward = self.contact_punishment_scale * self.env.collide_buf
+            reward += collide_reward.unsqueeze(1)
+            self._acc("contact punishment", torch.sum(collide_reward))
+        if self.sheep_movement_reward_scale != 0:
+            if self.last_sheep_pos_avg is not None:
+                x_movement = (self.sheep_pos_avg - self.last_sheep_pos_avg)[:, 0]
+                x_movement[self.delayed_reset_buf] = 0
+                sheep_movement_reward = self.sheep_movement_reward_scale * x_movement
+                reward[:, 0] += sheep_movement_reward
+                self._acc("sheep movement reward", torch.sum(sheep_movement_reward))
+            self.last_sheep_pos_avg = self.sheep_pos_avg.clone()
+        if self.mixed_sheep_reward_scale != 0:
+            distance_to_gate = torch.norm(sheep_pos[..., :-1] - self.gate_pos.repeat(1, self.num_npcs, 1), dim=-1)
+            mixed = torch.exp(-distance_to_gate / 2) * self.mixed_sheep_reward_scale
+            mixed[sheep_pos[..., 0] >= self.gate_distance] = self.mixed_sheep_reward_scale
+            reward[:, 0] += mixed.sum(dim=-1)
+            self._acc("mixed sheep reward", torch.sum(mixed))
+        if self.sheep_pos_var_exp_punishment_scale != 0 or self.sheep_pos_var_lin_punishment_scale != 0:
+            pun = self.sheep_pos_var_lin_punishment_scale * (self.sheep_pos_var - 1) + \
+                self.sheep_pos_var_exp_punishment_scale * torch.exp(self.sheep_pos_var / 2 - 1)
+            reward[:, 0] += pun
+            self._acc("sheep pos var punishment", torch.sum(pun))
+        reward = reward.repeat(1, self.num_agents)
+        self.delayed_reset_buf = self.env.reset_buf.clone()                 # mask form of copy(self.env.reset_ids) (:116)
+        return obs, reward, termination, info
+
+
+class Go1SeesawWrapper(EmptyWrapper):
+    """go1_seesaw_wrapper.py:8-120"""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(12 + self.num_agents,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.reward_buffer = {"height reward": 0, "contact punishment": 0, "x movement reward": 0, "y punishment": 0,
+                              "agent distance punishment": 0, "success reward": 0, "fall punishment": 0, "step count": 0}
+
+    def _obs(self, obs_buf):
+        base_info = self._base_info(obs_buf)
+        return torch.cat([self.obs_ids, base_info, torch.flip(base_info, [1])], dim=2)
+
+    def reset(self):
+        return self._obs(self.env.reset())
+
+    def step(self, action):
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        obs = self._obs(obs_buf)
+        base_pos = obs_buf.base_pos
+        self._acc("step count", 1)
+        reward = torch.zeros([self.env.num_envs, 1], device=self.env.device)
+        if self.x_movement_reward_scale != 0:
+            x_pos = base_pos[:, 0].reshape(self.num_envs, -1)
+            if not hasattr(self, "last_x_pos"):
+                self.last_x_pos = x_pos.clone()
+            x_reward = (x_pos - self.last_x_pos).sum(dim=1, keepdim=True)
+            x_reward[self.env.reset_buf] = 0
+            x_reward *= self.x_movement_reward_scale
+            reward += x_reward
+            self.last_x_pos = x_pos.clone()
+            self._acc("x movement reward", torch.sum(x_reward))
+        if self.height_reward_scale != 0:
+            height_reward = self.height_reward_scale * (base_pos[:, 2].reshape(self.num_envs, -1).sum(dim=1) - 0.56)
+            reward[:, 0] += height_reward
+            self._acc("height reward", torch.sum(height_reward))
+        if self.y_punishment_scale != 0:
+            y_punishment = self.y_punishment_scale * ((base_pos[:, 1].reshape(self.num_envs, -1) ** 2).sum(dim=1) - 0.5)
+            reward[:, 0] += y_punishment
+            self._acc("y punishment", torch.sum(y_punishment))
+        if self.contact_punishment_scale != 0:
+            collide_reward = self.contact_punishment_scale * self.env.collide_buf
+            reward += collide_reward.unsqueeze(1)
+            self._acc("contact punishment", torch.sum(collide_reward))
+        if self.agent_distance_punishment_scale != 0:
+            agent_dis = (base_pos[:, :2] - torch.flip(base_pos[:, :2].reshape(self.num_envs, self.num_agents, 2), dims=[1]).reshape(-1, 2)) ** 2
+            agent_dis = agent_dis.sum(dim=1).reshape(self.num_envs, -1)[:, :1]
+            close = agent_dis < 0.25
+            pun = torch.where(close, self.agent_distance_punishment_scale / agent_dis.clamp_min(1e-12), torch.zeros_like(agent_dis))
+            reward += pun
+            self._acc("agent distance punishment", torch.sum(pun))
+        if self.success_reward_scale != 0:
+            success = (base_pos[:, 0] > 7.7) * (base_pos[:, 2] > 1.3)
+            success_reward = self.success_reward_scale * success.reshape(self.num_envs, -1).sum(dim=1)
+            reward[:, 0] += success_reward
+            self._acc("success reward", torch.sum(success_reward))
+        if self.fall_punishment_scale != 0:
+            fall = self.env.r_term_buff | self.env.p_term_buff
+            reward[fall, 0] += self.fall_punishment_scale
+            self._acc("fall punishment", self.fall_punishment_scale * torch.sum(fall))
+        return obs, reward.repeat(1, self.num_agents), termination, info
+
+
+class Go1FootballDefenderWrapper(EmptyWrapper):
+    """go1_football_wrapper.py:8-91: two controlled agents; the env's third agent is the scripted defender."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.num_agents = 2
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(18 + self.num_agents,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.obs_ids = torch.eye(2, dtype=torch.float32, device=self.env.device).repeat(self.num_envs, 1).reshape(self.num_envs, 2, -1)
+        self.reward_buffer = {"goal reward": 0, "ball gate distance reward": 0, "step count": 0}
+
+    def _obs(self, obs_buf):
+        npc = self.root_states_npc
+        ball_pos = (npc[:, :3].reshape(self.num_envs, 3) - self.env_origins).unsqueeze(1).repeat(1, 2, 1)
+        ball_vel = npc[:, 7:10].reshape(self.num_envs, 3).unsqueeze(1).repeat(1, 2, 1)
+        base_info = self._base_info(obs_buf)[:, :2, :]
+        return torch.cat([self.obs_ids, base_info, torch.flip(base_info, [1]), ball_pos, ball_vel], dim=2), ball_pos
+
+    def reset(self):
+        return self._obs(self.env.reset())[0]
+
+    def step(self, action):
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        obs, ball_pos = self._obs(obs_buf)
+        self._acc("step count", 1)
+        reward = torch.zeros([self.env.num_envs, 1], device=self.env.device)
+        # NOTE the reference compares the env-relative ball x with the WORLD gate x (go1_football_wrapper.py:77)
+        if self.goal_reward_scale != 0:
+            goal_reward = torch.zeros_like(reward)
+            goal_reward[ball_pos[:, 0, 0] > self.gate_pos[:, 0], 0] = self.goal_reward_scale
+            reward += goal_reward
+            self._acc("goal reward", torch.sum(goal_reward))
+        if self.ball_gate_distance_reward_scale != 0:
+            d = torch.norm(ball_pos[:, 0, :2] - self.gate_pos[:, :2], dim=1, keepdim=True)
+            r = self.ball_gate_distance_reward_scale * torch.exp(-d / 3)
+            reward += r
+            self._acc("ball gate distance reward", torch.sum(r))
+        return obs, reward.repeat(1, 2), termination, info

@@ -1,0 +1,277 @@
+"""GPU parity tests proper: the CUDA path through the C ABI against the CPU oracle / the reference's own golden
+vectors.  Run on the B200 box with `-m gpu`.
+
+Tolerances (fp32 path, stated once): network outputs vs TorchScript fp32 goldens rtol 1e-4 / atol 1e-4 for the
+CUDA-core path and rtol 2e-4 / atol 3e-4 for the tensor-core bf16x3 path; one physics substep vs the fp32 oracle
+abs 2e-4 (pos, quat, joint pos) / 5e-3 (velocities); trajectories are compared over a short horizon only because
+contact dynamics amplify rounding differences (the oracle uses a dense mass matrix, the kernel a block-LDL form).
+Bookkeeping (episode counters, time-outs, reset masks, indices) is bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import oracle  # noqa: E402
+from mqe_b200 import engine as E  # noqa: E402
+from mqe_b200 import scene as S  # noqa: E402
+from mqe_b200.envs import configs as C  # noqa: E402
+
+TASKS = {"go1gate": C.Go1GateCfg, "go1sheep-hard": C.NineSheepCfg, "go1sheep-easy": C.SingleSheepCfg,
+         "go1seesaw": C.Go1SeesawCfg, "go1football-defender": C.Go1FootballDefenderCfg, "go1plane": C.Go1PlaneCfg}
+
+
+def make_pair(task, n, mode=E.POLICY_FP32, seed=0, precision="f32"):
+    cfg = TASKS[task]()
+    cfg.env.num_envs = n
+    np.random.seed(seed)
+    sc = S.build_scene(cfg, seed=seed, policy_mode=mode, wrapper_action_scale=(2.0, 0.5, 0.5))
+    eng = E.Engine(sc.desc, device=0, keepalive=sc)
+    orc = oracle.Oracle(sc, precision)
+    return sc, eng, orc
+
+
+def actions_for(sc, step, seed=0):
+    a_ctrl = sc.num_agents - 1 if sc.desc.defender else sc.num_agents
+    rng = np.random.default_rng(seed * 1000 + step)
+    return rng.uniform(-1, 1, size=(sc.num_envs, a_ctrl, 3)).astype(np.float32)
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda:0")
+
+
+def get(eng, which):
+    return eng.tensor(which).cpu().numpy()
+
+
+@pytest.mark.parametrize("mode,rtol,atol", [(E.POLICY_FP32, 1e-4, 1e-4), (E.POLICY_BF16X3, 2e-4, 3e-4)])
+def test_policy_forward_golden(mode, rtol, atol, golden_dir):
+    """walk-these-ways adaptation module + body vs the TorchScript goldens (SURVEY 8(c) known answers)."""
+    z = np.load(os.path.join(golden_dir, "mlp_kat.npz"))
+    sc, eng, orc = make_pair("go1gate", 128, mode)
+    for key_x, key_a, key_l in (("x", "action", "latent"), ("xs", "actions", "latents")):
+        x = z[key_x]
+        lat, act = eng.policy_forward(dev(x))
+        torch.cuda.synchronize()
+        lat, act = lat.cpu().numpy(), act.cpu().numpy()
+        scale = np.abs(z[key_a]).max()
+        assert np.allclose(act, z[key_a], rtol=rtol, atol=atol * max(1.0, scale)), np.abs(act - z[key_a]).max()
+        assert np.allclose(lat, z[key_l], rtol=rtol, atol=atol * max(1.0, np.abs(z[key_l]).max()))
+    lat, act = eng.policy_forward(dev(z["x"]))
+    assert np.allclose(act.cpu().numpy()[0, :4], [165.2033, -166.0023, 104.1395, 131.9488], atol=5e-2)
+    eng.close()
+
+
+def test_policy_bf16_single_pass_is_close(golden_dir):
+    z = np.load(os.path.join(golden_dir, "mlp_kat.npz"))
+    sc, eng, orc = make_pair("go1gate", 128, E.POLICY_BF16)
+    _, act = eng.policy_forward(dev(z["xs"]))
+    ref = z["actions"]
+    rel = np.abs(act.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert rel < 2e-2, rel
+    eng.close()
+
+
+def test_actuator_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "mlp_kat.npz"))
+    sc, eng, orc = make_pair("go1gate", 4)
+    t = eng.actuator_forward(dev(z["xa"])).cpu().numpy()
+    assert np.allclose(t, [19.5816, 22.6831, -19.3611, -4.5704, -15.3245], atol=2e-4)
+    t = eng.actuator_forward(dev(z["xas"])).cpu().numpy()
+    assert np.allclose(t, z["torques"].ravel(), rtol=1e-5, atol=3e-5)
+    eng.close()
+
+
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1plane"])
+def test_reset_matches_oracle(task):
+    """reset_idx + compute_observations: same counter RNG, same arithmetic."""
+    sc, eng, orc = make_pair(task, 64)
+    eng.reset(); orc.reset()
+    torch.cuda.synchronize()
+    for buf in (E.BUF_ROOT_STATES, E.BUF_DOF_STATES, E.BUF_OBS):
+        assert np.allclose(get(eng, buf).ravel(), orc.get(buf), rtol=0, atol=2e-6), buf
+    assert np.array_equal(get(eng, E.BUF_RESET), orc.get(E.BUF_RESET))
+    assert np.array_equal(get(eng, E.BUF_EPISODE_LENGTH), orc.get(E.BUF_EPISODE_LENGTH))
+    eng.close()
+
+
+def _sync_state(eng, orc):
+    root, dof = orc.get(E.BUF_ROOT_STATES), orc.get(E.BUF_DOF_STATES)
+    eng.tensor(E.BUF_ROOT_STATES).copy_(dev(root).view_as(eng.tensor(E.BUF_ROOT_STATES)))
+    eng.tensor(E.BUF_DOF_STATES).copy_(dev(dof).view_as(eng.tensor(E.BUF_DOF_STATES)))
+
+
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender"])
+def test_single_substep_parity(task):
+    """Single physics substeps from IDENTICAL states (engine re-synchronised to the oracle before each one), robots
+    dropped onto the floor so foot / knee / pair contacts and the actuator net are all active."""
+    sc, eng, orc = make_pair(task, 64)
+    eng.reset(); orc.reset()
+    root = orc.get(E.BUF_ROOT_STATES).reshape(sc.num_envs, -1, 13).copy()
+    root[:, :sc.num_agents, 2] = 0.30 + np.linspace(0.0, 0.06, sc.num_envs)[:, None]     # some penetrating, some hovering
+    orc.set(E.BUF_ROOT_STATES, root)
+    a = np.clip(np.random.default_rng(1).normal(0, 1.0, size=(sc.num_envs * sc.num_agents * 12,)), -3, 3).astype(np.float32)
+    orc.set(E.BUF_ACTIONS, a)
+    eng.tensor(E.BUF_ACTIONS).copy_(dev(a).view_as(eng.tensor(E.BUF_ACTIONS)))
+    worst = np.zeros(4)
+    total_contacts = 0
+    for s in range(24):
+        _sync_state(eng, orc)
+        eng.substeps(1); orc.substeps(1)
+        torch.cuda.synchronize()
+        st_g, st_o = get(eng, E.BUF_STATS), orc.get(E.BUF_STATS)
+        r_g, r_o = get(eng, E.BUF_ROOT_STATES).reshape(-1, 13), orc.get(E.BUF_ROOT_STATES).reshape(-1, 13)
+        d_g, d_o = get(eng, E.BUF_DOF_STATES).reshape(-1, 2), orc.get(E.BUF_DOF_STATES).reshape(-1, 2)
+        err = np.array([np.abs(r_g[:, :7] - r_o[:, :7]).max(), np.abs(r_g[:, 7:] - r_o[:, 7:]).max(),
+                        np.abs(d_g[:, 0] - d_o[:, 0]).max(), np.abs(d_g[:, 1] - d_o[:, 1]).max()])
+        worst = np.maximum(worst, err)
+        total_contacts += int(st_o[0])
+        assert tuple(st_g[:3]) == tuple(st_o[:3]), f"substep {s}: contact/limit/pair counts differ gpu {st_g[:4]} oracle {st_o[:4]}"
+        t_g, t_o = get(eng, E.BUF_TORQUES).ravel(), orc.get(E.BUF_TORQUES)
+        assert np.allclose(t_g, t_o, atol=2e-3), np.abs(t_g - t_o).max()
+        cf_g, cf_o = get(eng, E.BUF_CONTACT_FORCES).ravel(), orc.get(E.BUF_CONTACT_FORCES)
+        assert np.allclose(cf_g, cf_o, rtol=2e-2, atol=0.5), np.abs(cf_g - cf_o).max()
+    print(task, "worst one-substep errors (pos/quat, root vel, q, qd):", worst, "contacts seen", total_contacts)
+    assert total_contacts > 0
+    assert worst[0] < 2e-4 and worst[2] < 2e-4 and worst[1] < 5e-3 and worst[3] < 2e-2, worst
+    eng.close()
+
+
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw"])
+def test_short_trajectory_parity(task):
+    """Full Go1.step() x 5 from reset on identical seeds and actions."""
+    sc, eng, orc = make_pair(task, 32)
+    eng.reset(); orc.reset()
+    worst = {}
+    for s in range(5):
+        act = actions_for(sc, s)
+        eng.step(dev(act).data_ptr()); orc.step(act)
+        torch.cuda.synchronize()
+        r_g, r_o = get(eng, E.BUF_ROOT_STATES).reshape(-1, 13), orc.get(E.BUF_ROOT_STATES).reshape(-1, 13)
+        d_g, d_o = get(eng, E.BUF_DOF_STATES).reshape(-1, 2), orc.get(E.BUF_DOF_STATES).reshape(-1, 2)
+        worst[s] = (np.abs(r_g[:, :7] - r_o[:, :7]).max(), np.abs(r_g[:, 7:] - r_o[:, 7:]).max(),
+                    np.abs(d_g[:, 0] - d_o[:, 0]).max(), np.abs(d_g[:, 1] - d_o[:, 1]).max())
+        assert np.array_equal(get(eng, E.BUF_EPISODE_LENGTH), orc.get(E.BUF_EPISODE_LENGTH))
+        assert np.array_equal(get(eng, E.BUF_TIMEOUT), orc.get(E.BUF_TIMEOUT))
+    print(task, {k: tuple(f"{x:.2e}" for x in v) for k, v in worst.items()})
+    assert worst[0][0] < 2e-4 and worst[0][2] < 2e-4, worst[0]          # first policy step (4 substeps)
+    assert worst[0][1] < 2e-2 and worst[0][3] < 5e-2, worst[0]
+    act_g, act_o = get(eng, E.BUF_ACTIONS).ravel(), orc.get(E.BUF_ACTIONS)
+    assert np.isfinite(act_g).all()
+    eng.close()
+
+
+def test_history_ring_equals_shift_concat():
+    """The ring + age-rotated weights reproduce cat(history[:, 70:], obs) (go1.py:102): compare the logical history."""
+    sc, eng, orc = make_pair("go1gate", 16)
+    eng.reset(); orc.reset()
+    for s in range(33):                               # > 30 so the ring wraps
+        act = actions_for(sc, s)
+        eng.policy(dev(act).data_ptr()); orc.policy(act)
+        # keep both on the oracle's trajectory: copy actions so the frames stay comparable
+    torch.cuda.synchronize()
+    h_g = eng.history().cpu().numpy()
+    h_o = orc.get(E.BUF_HISTORY).reshape(h_g.shape)
+    # frames depend on previous network outputs (last actions) -> small fp32 differences accumulate
+    assert np.allclose(h_g[:, -70:-28], h_o[:, -70:-28], atol=1e-5)   # newest frame: gravity/commands/dof parts identical
+    assert np.allclose(h_g, h_o, rtol=1e-3, atol=2e-3)
+    eng.close()
+
+
+def test_episode_bookkeeping_bit_exact():
+    """time-outs, episode counters and reset masks over > one episode (max_episode_length shortened to 20)."""
+    cfg = C.Go1GateCfg(); cfg.env.num_envs = 64; cfg.env.episode_length_s = 0.4
+    np.random.seed(0)
+    sc = S.build_scene(cfg, seed=0, policy_mode=E.POLICY_FP32, wrapper_action_scale=(2.0, 0.5, 0.5))
+    eng = E.Engine(sc.desc, device=0, keepalive=sc)
+    eng.reset()
+    zero = torch.zeros((64, 2, 3), device="cuda:0")
+    ep_prev = np.zeros(64, dtype=np.int64)
+    n_timeouts = 0
+    for s in range(50):
+        eng.step(zero.data_ptr())
+        torch.cuda.synchronize()
+        ep, to, rs = get(eng, E.BUF_EPISODE_LENGTH), get(eng, E.BUF_TIMEOUT), get(eng, E.BUF_RESET)
+        expect_to = (ep_prev + 1) > sc.desc.max_episode_length
+        assert np.array_equal(to.astype(bool), expect_to)
+        assert (rs[to.astype(bool)] == 1).all()
+        assert np.array_equal(ep, np.where(rs.astype(bool), 0, ep_prev + 1))
+        n_timeouts += int(to.sum())
+        ep_prev = ep
+    assert n_timeouts >= 64
+    eng.close()
+
+
+@pytest.mark.parametrize("task,n", [("go1gate", 4096), ("go1sheep-hard", 1024), ("go1football-defender", 1024), ("go1seesaw", 1024)])
+def test_full_size_invariants(task, n):
+    """BASELINE sizes: size-independent properties -- finite state, unit quaternions, joint positions inside the URDF
+    limits (+margin), bounded heights, feet not below the floor, and walking under the frozen policy."""
+    sc, eng, orc = make_pair(task, n)
+    orc.close()
+    eng.reset()
+    a_ctrl = sc.num_agents - 1 if sc.desc.defender else sc.num_agents
+    act = torch.zeros((n, a_ctrl, 3), device="cuda:0"); act[..., 0] = 0.5       # 1 m/s forward
+    x0 = eng.tensor(E.BUF_ROOT_STATES)[:, 0, 0].clone()
+    for s in range(40):
+        eng.step(act.data_ptr())
+    torch.cuda.synchronize()
+    root = get(eng, E.BUF_ROOT_STATES)[:, :sc.num_agents]
+    dofs = get(eng, E.BUF_DOF_STATES)[:, :12 * sc.num_agents]
+    assert np.isfinite(root).all() and np.isfinite(dofs).all()
+    qn = np.linalg.norm(root[..., 3:7], axis=-1)
+    assert np.abs(qn - 1).max() < 1e-4
+    m = sc.model
+    q = dofs[..., 0].reshape(n, sc.num_agents, 12)
+    assert (q > m.q_lower - 0.1).all() and (q < m.q_upper + 0.1).all()
+    z = root[..., 2]
+    assert (z > 0.0).all() and (z < 1.6).all()
+    ep = get(eng, E.BUF_EPISODE_LENGTH)
+    alive = ep == 40
+    frac_alive = alive.mean()
+    dx = (get(eng, E.BUF_ROOT_STATES)[:, 0, 0] - x0.cpu().numpy())[alive]
+    print(task, "alive fraction", frac_alive, "median forward progress of agent 0 in 0.8 s", np.median(dx) if dx.size else None)
+    assert frac_alive > 0.5
+    if task != "go1football-defender":
+        assert np.median(dx) > 0.3                       # commanded 1 m/s for 0.8 s (includes the landing transient)
+    eng.close()
+
+
+def test_env_surface_go1gate():
+    """make_mqe_env / reset / step through the reference-facing VecEnv surface."""
+    from types import SimpleNamespace
+    from mqe_b200.envs import make_mqe_env, custom_cfg
+    args = SimpleNamespace(num_envs=8, seed=0, headless=True, record_video=False, sim_device="cuda:0")
+    env, cfg = make_mqe_env("go1gate", args, custom_cfg(args))
+    assert env.num_envs == 8 and env.num_agents == 2 and cfg.env.num_envs == 8
+    assert env.reset() == 0                               # the shipped gate wrapper returns 0 (go1_gate_wrapper.py:68)
+    a = torch.zeros((8, 2, 3), device="cuda:0")
+    obs, rew, done, info = env.step(a)
+    assert obs == 0 and rew == 0 and done.shape == (8,) and done.dtype == torch.bool
+    ob = env.obs_buf
+    assert ob.base_pos.shape == (16, 3) and ob.base_rpy.shape == (16, 3) and ob.dof_pos.shape == (16, 12)
+    assert ob.env_info["gate_deviation"].shape == (8, 2)
+    assert env.root_states.shape == (16, 13) and env.all_root_states.shape == (16, 13)
+    env.close()
+
+
+@pytest.mark.parametrize("task,D,A", [("go1sheep-hard", 34, 2), ("go1sheep-easy", 18, 2), ("go1seesaw", 14, 2), ("go1football-defender", 20, 2)])
+def test_env_surface_wrappers(task, D, A):
+    from types import SimpleNamespace
+    from mqe_b200.envs import make_mqe_env, custom_cfg
+    args = SimpleNamespace(num_envs=16, seed=0, headless=True, record_video=False, sim_device="cuda:0")
+    env, cfg = make_mqe_env(task, args, custom_cfg(args))
+    obs = env.reset()
+    assert obs.shape == (16, A, D), obs.shape
+    assert env.observation_space.shape == (D,)
+    for s in range(3):
+        a = torch.rand((16, A, 3), device="cuda:0") * 2 - 1
+        obs, rew, done, info = env.step(a)
+    assert obs.shape == (16, A, D) and rew.shape == (16, A) and done.shape == (16,)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert float(env.reward_buffer["step count"]) == 3
+    env.close()
