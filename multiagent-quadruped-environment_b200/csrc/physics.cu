@@ -459,7 +459,9 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             V3 wxv = cross(wang, vlin);
             vb[0] = wang.x + p.dt * ab[0]; vb[1] = wang.y + p.dt * ab[1]; vb[2] = wang.z + p.dt * ab[2];
             vb[3] = vlin.x + p.dt * (ab[3] + wxv.x); vb[4] = vlin.y + p.dt * (ab[4] + wxv.y); vb[5] = vlin.z + p.dt * (ab[5] + wxv.z);
-            float v0[6] = {wang.x, wang.y, wang.z, vlin.x, vlin.y, vlin.z};
+            // u = qd + G^T v_base must be formed with the SAME base velocity the classical-acceleration term w x v
+            // was added to, otherwise qd = u - G^T v_base picks up a spurious -dt G_lin^T (w x v)
+            float v0[6] = {wang.x, wang.y, wang.z, vlin.x + p.dt * wxv.x, vlin.y + p.dt * wxv.y, vlin.z + p.dt * wxv.z};
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 float gt = 0.f;

@@ -1,0 +1,69 @@
+"""Sharding of the environment batch across ranks: one process per GPU, contiguous env blocks,
+no exchange inside the physics step; one collective per step gathers what the learner reads.
+
+`shard_range` / `StepGather` are pure torch.distributed host logic and run on gloo (CPU tests) and nccl alike.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(num_envs_global: int, rank: int, world: int):
+    """env e -> rank floor(e * world / N): contiguous blocks whose sizes differ by at most one."""
+    start = (rank * num_envs_global + world - 1) // world
+    stop = ((rank + 1) * num_envs_global + world - 1) // world
+    return start, stop
+
+
+def owner_of(env_id: int, num_envs_global: int, world: int) -> int:
+    return (env_id * world) // num_envs_global
+
+
+class StepGather:
+    """All-gather of per-step results (observation rows, rewards, done flags) into rank-ordered global tensors.
+
+    Equal shards use one `all_gather_into_tensor`; ragged shards are padded to the largest shard first.
+    Buffers are allocated once and reused every step."""
+
+    def __init__(self, num_envs_global: int, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_global = num_envs_global
+        self.ranges = [shard_range(num_envs_global, r, self.world) for r in range(self.world)]
+        self.equal = len({b - a for a, b in self.ranges}) == 1
+        self._out = {}
+
+    def local_range(self):
+        return self.ranges[self.rank]
+
+    def gather(self, name: str, local: torch.Tensor) -> torch.Tensor:
+        """local: [n_local, ...] -> [n_global, ...] in global env order."""
+        if self.world == 1:
+            return local
+        local = local.contiguous()
+        key = (name, local.dtype, tuple(local.shape[1:]))
+        out = self._out.get(key)
+        if out is None:
+            out = torch.empty((self.n_global,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            self._out[key] = out
+        as_u8 = local.dtype == torch.bool                    # NCCL has no bool
+        if self.equal:
+            src, dst = (local.view(torch.uint8), out.view(torch.uint8)) if as_u8 else (local, out)
+            dist.all_gather_into_tensor(dst, src, group=self.group)
+        else:                                                # ragged: pad every shard to the largest, gather, unpack
+            big = max(b - a for a, b in self.ranges)
+            pkey = key + ("pad",)
+            bufs = self._out.get(pkey)
+            if bufs is None:
+                bufs = (torch.zeros((big,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device),
+                        torch.empty((self.world * big,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device))
+                self._out[pkey] = bufs
+            pad, allbuf = bufs
+            pad[:local.shape[0]].copy_(local)
+            src, dst = (pad.view(torch.uint8), allbuf.view(torch.uint8)) if as_u8 else (pad, allbuf)
+            dist.all_gather_into_tensor(dst, src, group=self.group)
+            for r, (a, b) in enumerate(self.ranges):
+                out[a:b].copy_(allbuf[r * big:r * big + (b - a)])
+        return out

@@ -326,10 +326,20 @@ static inline real softsign(real x) { return x / (1 + fabs(x)); }
 
 static void linear(const float *W, const float *b, int nout, int nin, const real *x, real *y) {
     for (int o = 0; o < nout; o++) {
-        double s = b[o];
         const float *w = W + (size_t)o * nin;
-        for (int i = 0; i < nin; i++) s += (double)w[i] * (double)x[i];
-        y[o] = (real)s;
+        if (sizeof(real) == sizeof(float)) {      /* fp32 build: 8 partial sums so the compiler can vectorise */
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int i = 0;
+            for (; i + 8 <= nin; i += 8)
+                for (int k = 0; k < 8; k++) acc[k] += w[i + k] * (float)x[i + k];
+            float s = ((acc[0] + acc[4]) + (acc[1] + acc[5])) + ((acc[2] + acc[6]) + (acc[3] + acc[7]));
+            for (; i < nin; i++) s += w[i] * (float)x[i];
+            y[o] = (real)(s + b[o]);
+        } else {
+            double s = b[o];
+            for (int i = 0; i < nin; i++) s += (double)w[i] * (double)x[i];
+            y[o] = (real)s;
+        }
     }
 }
 /* go1.py:400-407: latent = AM(h); action = Body(cat(h, latent)) */
@@ -615,7 +625,10 @@ static void group_jacobian(const Oracle *o, const EnvScratch *es, int g, int lin
         real rxd[3];
         v3cross(rxd, r, dir);
         memset(J, 0, NV * sizeof(real)); memset(Y, 0, NV * sizeof(real));
-        for (int i = 0; i < 3; i++) { J[i] = rxd[i]; J[3 + i] = dir[i]; Y[i] = rxd[i] * es->npc_minv[0]; Y[3 + i] = dir[i] * es->npc_minv[1]; }
+        /* sheep are kept upright: go1_sheep.py:61 zeroes their tilt every policy step, so contacts get no roll/pitch
+         * response; the ball is a free sphere */
+        real up = (o->d.npc_ctrl == MQE_NPC_SHEEP) ? 0 : 1;
+        for (int i = 0; i < 3; i++) { J[i] = rxd[i]; J[3 + i] = dir[i]; Y[i] = rxd[i] * es->npc_minv[0] * (i < 2 ? up : 1); Y[3 + i] = dir[i] * es->npc_minv[1]; }
     }
 }
 
