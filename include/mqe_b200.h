@@ -96,7 +96,8 @@ typedef struct {
     float loc_obs_default[MQE_LOC_OBS];         /* go1.py:411-479                                          */
     float dof_ratio_lo, dof_ratio_hi;           /* init_dof_pos_ratio_range                                */
     float base_vel_lo, base_vel_hi;
-    int32_t has_base_pos_range, has_npc_pos_range, has_npc_rpy_range, reserved1;
+    int32_t has_base_pos_range, has_npc_pos_range, has_npc_rpy_range;
+    int32_t max_pair_contacts;                  /* dynamic-vs-dynamic contacts kept per env and substep (1..16; 0 = 16)   */
     float base_pos_x[2], base_pos_y[2];
     float npc_pos_x[2], npc_pos_y[2];
     float npc_rpy_r[2], npc_rpy_p[2], npc_rpy_y[2];

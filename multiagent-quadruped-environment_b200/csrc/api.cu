@@ -112,6 +112,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     if (d->defender && !(A == 3 && P >= 1)) return fail(MQE_ERR_INVALID, "defender needs 3 agents and the ball");
     s->M = M;
     s->actrl = d->defender ? A - 1 : A;
+    s->maxpair = (d->max_pair_contacts > 0 && d->max_pair_contacts < MQE_MAX_PAIR) ? d->max_pair_contacts : MQE_MAX_PAIR;
     DevParams &p = s->p;
     memset(&p, 0, sizeof p);
     p.N = N; p.A = A; p.P = P; p.D = D; p.G = G;

@@ -45,11 +45,12 @@
 #define ES_SIZE(maxpair) (ES_CMETA(maxpair) + (maxpair) * 8)
 
 #define ACTW_FLOATS 1316   // 192 + 32 + 1024 + 32 + 32 + 1 = 1313, padded
+#define TBL_INTS 80        // per-leg probe lists [4][10] (count + 9 ids), per-leg capsule lists [4][10]
 
 __host__ __device__ inline int physics_warp_smem_floats(int A, int P, int E, int maxpair) {
     return E * A * RS_SIZE + E * P * NS_SIZE + E * ES_SIZE(maxpair);
 }
-__host__ __device__ inline int physics_cta_header_floats() { return (int)(sizeof(MqeRobotModel) / 4) + ACTW_FLOATS; }
+__host__ __device__ inline int physics_cta_header_floats() { return (int)(sizeof(MqeRobotModel) / 4) + ACTW_FLOATS + TBL_INTS; }
 
 struct SV { V3 w, v; };
 struct RBI { float m; V3 h; float I[6]; };   // xx xy xz yy yz zz about O
@@ -171,7 +172,13 @@ __device__ __forceinline__ float contact_bias(const DevParams &p, float gap) {
     if (gap > 0.f) return gap / p.dt;
     return fmaxf(p.erp * gap / p.dt, -p.vdep);
 }
-__device__ __forceinline__ float softsign(float x) { return x / (1.f + fabsf(x)); }
+// x / (1 + |x|): reciprocal by MUFU.RCP + one Newton step (d >= 1, so no special cases); <= 1 ulp from the exact quotient
+__device__ __forceinline__ float softsign(float x) {
+    float d = 1.f + fabsf(x), r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    r = fmaf(r, fmaf(-d, r, 1.f), r);
+    return x * r;
+}
 
 // world probe of a sphere against floor slab + wall footprint; bit0: floor/top contact, bit1: wall contact
 struct ProbeHit { int mask; float gap_f, gap_w; V3 nw; };
@@ -260,6 +267,27 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         const float *src = reinterpret_cast<const float *>(p.model);
         for (int i = threadIdx.x; i < (int)(sizeof(MqeRobotModel) / 4); i += blockDim.x) smem[i] = src[i];
         for (int i = threadIdx.x; i < 1313; i += blockDim.x) actw[i] = p.act_w[i];
+    }
+    __syncthreads();
+    // which lane of a robot's quad owns which probe / capsule: leg links belong to their leg, base colliders are dealt
+    // round-robin (probes) or to leg 0 (capsules).  Built once per CTA; lists keep the canonical (table) order.
+    int *tbl = reinterpret_cast<int *>(actw + ACTW_FLOATS);
+    if (threadIdx.x < 4) {
+        const int lg = threadIdx.x;
+        int n = 0, nbase = 0;
+        for (int pi = 0; pi < md->n_probes; pi++) {
+            int link = (int)md->probes[pi][0];
+            bool mine = link == 0 ? ((nbase++ & 3) == lg) : ((link - 1) / 3 == lg);
+            if (mine && n < 9) tbl[lg * 10 + 1 + n++] = pi;
+        }
+        tbl[lg * 10] = n;
+        n = 0;
+        for (int ci = 0; ci < md->n_caps; ci++) {
+            int link = (int)md->caps[ci][0];
+            bool mine = link == 0 ? (lg == 0) : ((link - 1) / 3 == lg);
+            if (mine && n < 9) tbl[40 + lg * 10 + 1 + n++] = ci;
+        }
+        tbl[40 + lg * 10] = n;
     }
     __syncthreads();
     const int A = p.A, P = p.Pd, E = p.E, G = A + P;   // P: dynamic NPCs only (a seesaw is not a free body)
@@ -477,27 +505,6 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 ((int *)rs)[RS_CNT] = 0; ((int *)rs)[RS_CNT + 1] = 0;
                 for (int i = 0; i < 51; i++) rs[RS_FORCE + i] = 0.f;
             }
-#pragma unroll
-            for (int i = 0; i < 18; i++) rs[RS_G + leg * 18 + i] = Gm[i];
-#pragma unroll
-            for (int i = 0; i < 6; i++) rs[RS_HINV + leg * 6 + i] = Hinv[i];
-            {
-                float *pa = rs + RS_A + leg * 9, *pp = rs + RS_P + leg * 9;
-                pa[0] = a1.x; pa[1] = a1.y; pa[2] = a1.z; pa[3] = a2.x; pa[4] = a2.y; pa[5] = a2.z; pa[6] = a2.x; pa[7] = a2.y; pa[8] = a2.z;
-                pp[0] = p1.x; pp[1] = p1.y; pp[2] = p1.z; pp[3] = p2.x; pp[4] = p2.y; pp[5] = p2.z; pp[6] = p3.x; pp[7] = p3.y; pp[8] = p3.z;
-            }
-            for (int ci = 0; ci < md->n_caps; ci++) {
-                const float *cp = md->caps[ci];
-                int link = (int)cp[0];
-                bool mine = (link == 0) ? (leg == 0) : ((link - 1) / 3 == leg);
-                if (!mine) continue;
-                int k = link == 0 ? 0 : (link - 1) % 3 + 1;
-                const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
-                V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
-                V3 w0 = pos + pl + mul(Rl, mk(cp[2], cp[3], cp[4])), w1 = pos + pl + mul(Rl, mk(cp[5], cp[6], cp[7]));
-                float *o = rs + RS_CAP + ci * 7;
-                o[0] = w0.x; o[1] = w0.y; o[2] = w0.z; o[3] = w1.x; o[4] = w1.y; o[5] = w1.z; o[6] = cp[8];
-            }
         } else if (is_npc) {
             vb[0] = wang.x; vb[1] = wang.y; vb[2] = wang.z; vb[3] = vlin.x; vb[4] = vlin.y; vb[5] = vlin.z + p.dt * p.gz;
             Rb = quat_to_mat(qx, qy, qz, qw);
@@ -553,22 +560,19 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             }
             // ---- world contacts: pass 1 flags ----
             unsigned long long cm = 0ull;
-            const int np_ = md->n_probes;
-            for (int pi = 0; pi < np_; pi++) {
-                const float *pr = md->probes[pi];
-                int link = (int)pr[0];
-                int nbase = 0;
-                bool mine;
-                if (link == 0) { for (int t = 0; t < pi; t++) nbase += ((int)md->probes[t][0] == 0); mine = (nbase & 3) == leg; }
-                else mine = ((link - 1) / 3 == leg);
-                if (!mine || !active) continue;
-                int k = link == 0 ? 0 : (link - 1) % 3 + 1;
-                const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
-                V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
-                V3 xw = pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
-                ProbeHit h = probe_world(p, xw, pr[5]);
-                cm |= (unsigned long long)h.mask << (2 * pi);
-            }
+            const int *pl_ = tbl + leg * 10;
+            if (active)
+                for (int t = 0; t < pl_[0]; t++) {
+                    const int pi = pl_[1 + t];
+                    const float *pr = md->probes[pi];
+                    const int link = (int)pr[0];
+                    const int k = link == 0 ? 0 : link - 3 * leg;
+                    const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
+                    V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                    V3 xw = pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
+                    ProbeHit h = probe_world(p, xw, pr[5]);
+                    cm |= (unsigned long long)h.mask << (2 * pi);
+                }
             unsigned long long call = cm;
             call |= __shfl_xor_sync(quad_mask, call, 1);
             call |= __shfl_xor_sync(quad_mask, call, 2);
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 int pi = b >> 1, kind = b & 1;
                 const float *pr = md->probes[pi];
                 int link = (int)pr[0], body = (int)pr[1];
-                int k = link == 0 ? 0 : (link - 1) % 3 + 1;
+                int k = link == 0 ? 0 : link - 3 * leg;
                 const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
                 V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
                 V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));            // probe centre rel. O
@@ -672,6 +676,30 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             if (env >= p.N) close = false;
             bool any_close = __ballot_sync(env_mask, close) != 0u;
             if (any_close) {
+                // publish the operators other lanes need to build pair rows, and the capsule end points (only now:
+                // most substeps have no dynamic pair in range)
+                if (is_robot) {
+#pragma unroll
+                    for (int i = 0; i < 18; i++) rs[RS_G + leg * 18 + i] = Gm[i];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) rs[RS_HINV + leg * 6 + i] = Hinv[i];
+                    float *pa = rs + RS_A + leg * 9, *pp = rs + RS_P + leg * 9;
+                    pa[0] = a1.x; pa[1] = a1.y; pa[2] = a1.z; pa[3] = a2.x; pa[4] = a2.y; pa[5] = a2.z; pa[6] = a2.x; pa[7] = a2.y; pa[8] = a2.z;
+                    pp[0] = p1.x; pp[1] = p1.y; pp[2] = p1.z; pp[3] = p2.x; pp[4] = p2.y; pp[5] = p2.z; pp[6] = p3.x; pp[7] = p3.y; pp[8] = p3.z;
+                    const int *cl_ = tbl + 40 + leg * 10;
+                    for (int t = 0; t < cl_[0]; t++) {
+                        const int ci = cl_[1 + t];
+                        const float *cp = md->caps[ci];
+                        const int link = (int)cp[0];
+                        const int k = link == 0 ? 0 : link - 3 * leg;
+                        const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
+                        V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                        V3 w0 = pos + pl + mul(Rl, mk(cp[2], cp[3], cp[4])), w1 = pos + pl + mul(Rl, mk(cp[5], cp[6], cp[7]));
+                        float *o = rs + RS_CAP + ci * 7;
+                        o[0] = w0.x; o[1] = w0.y; o[2] = w0.z; o[3] = w1.x; o[4] = w1.y; o[5] = w1.z; o[6] = cp[8];
+                    }
+                }
+                __syncwarp(env_mask);
                 for (int t0 = 0; t0 < n_pair_entries; t0 += lanes_per_env) {
                     int t = t0 + rank_in_env;
                     bool hit = false;
@@ -923,7 +951,7 @@ __global__ void k_actuator(const float *__restrict__ aw, const float *__restrict
 
 // host-side launchers (api.cu)
 static int substeps_warps_per_cta(int A, int Pd, int E, int maxpair) {
-    const size_t budget = 200 * 1024, hdr = (size_t)physics_cta_header_floats() * 4, per = (size_t)physics_warp_smem_floats(A, Pd, E, maxpair) * 4;
+    const size_t budget = 227 * 1024, hdr = (size_t)physics_cta_header_floats() * 4, per = (size_t)physics_warp_smem_floats(A, Pd, E, maxpair) * 4;
     int w = (int)((budget - hdr) / per);
     return w > 4 ? 4 : w;
 }

@@ -78,7 +78,7 @@ class SimDescC(ctypes.Structure):
         ("dof_ratio_lo", ctypes.c_float), ("dof_ratio_hi", ctypes.c_float),
         ("base_vel_lo", ctypes.c_float), ("base_vel_hi", ctypes.c_float),
         ("has_base_pos_range", ctypes.c_int32), ("has_npc_pos_range", ctypes.c_int32),
-        ("has_npc_rpy_range", ctypes.c_int32), ("reserved1", ctypes.c_int32),
+        ("has_npc_rpy_range", ctypes.c_int32), ("max_pair_contacts", ctypes.c_int32),
         ("base_pos_x", ctypes.c_float * 2), ("base_pos_y", ctypes.c_float * 2),
         ("npc_pos_x", ctypes.c_float * 2), ("npc_pos_y", ctypes.c_float * 2),
         ("npc_rpy_r", ctypes.c_float * 2), ("npc_rpy_p", ctypes.c_float * 2), ("npc_rpy_y", ctypes.c_float * 2),

@@ -214,6 +214,8 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     if r is not None:
         d.npc_rpy_r[:], d.npc_rpy_p[:], d.npc_rpy_y[:] = list(map(float, r["r"])), list(map(float, r["p"])), list(map(float, r["y"]))
     d.npc_mass, d.npc_inertia, d.npc_radius, d.npc_halflen = npc_m, npc_I, npc_r, npc_hl
+    # pair-contact budget per env and substep: two robots alone rarely touch in more than a few capsule pairs
+    d.max_pair_contacts = 8 if (A <= 2 and npc_kind != E.NPC_RIGID) else 16
     d.sheep_scale = float(getattr(cfg.asset, "sheep_movement_scale", 0.0))
     d.sheep_randomness = float(getattr(cfg.asset, "sheep_movement_randomness", 0.0))
     if d.defender:

@@ -791,6 +791,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
     }
     /* pairs: groups X<Y, capsules i of X, j of Y */
     int npair = 0;
+    const int max_pair = (d->max_pair_contacts > 0 && d->max_pair_contacts < MAX_PAIR_CONTACTS) ? d->max_pair_contacts : MAX_PAIR_CONTACTS;
     for (int X = 0; X < G; X++)
         for (int Y = X + 1; Y < G; Y++) {
             if (X >= A && d->npc_kind != MQE_NPC_RIGID) continue;
@@ -835,7 +836,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
                     v3sub(dv, ca, cb);
                     real dist = sqrt(v3dot(dv, dv));
                     real gap = dist - ra - rb;
-                    if (gap >= d->contact_offset || dist < (real)1e-9 || npair >= MAX_PAIR_CONTACTS) continue;
+                    if (gap >= d->contact_offset || dist < (real)1e-9 || npair >= max_pair) continue;
                     Contact *c = &contacts[nc];
                     c->ga = X; c->la = la; c->rba = rba; c->gb = Y; c->lb = lb; c->rbb = rbb;
                     for (int k = 0; k < 3; k++) { c->n[k] = dv[k] / dist; c->pos[k] = cb[k] + c->n[k] * (rb + gap * (real)0.5); }
