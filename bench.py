@@ -103,6 +103,7 @@ def time_oracle(n_envs, steps, warmup, threads=None):
     np.random.seed(0)
     sc = S.build_scene(cfg, seed=0, wrapper_action_scale=(2.0, 0.5, 0.5))
     orc = oracle.Oracle(sc, "f32")
+    oracle.set_threads(threads, "f32")
     orc.reset()
     acts = synth_actions(n_envs, 2, steps + warmup)
     for s in range(warmup):

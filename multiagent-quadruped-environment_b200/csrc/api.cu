@@ -3,6 +3,7 @@
 // (mqe/envs/go1/go1.py:35-62, mqe/envs/base/legged_robot.py:117-157, 394-470, 549-595).
 // No CPU path exists behind these calls: without an sm_100 device mqe_sim_create fails with MQE_ERR_NO_DEVICE.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,7 +30,7 @@ struct MqeSim {
     BufInfo bufs[MQE_BUF_COUNT];
     PolicyWeightsDev pw;
     PolicyScratch ps;
-    PolicyTcWeights tcw = {nullptr, 0, nullptr, nullptr};
+    PolicyTcWeights tcw = {};
     unsigned int *pair_table = nullptr;
     int n_pair = 0;
     unsigned int step_count = 0;
@@ -41,6 +42,7 @@ struct MqeSim {
     float *tmp_ring = nullptr;
     unsigned short *tmp_hi = nullptr, *tmp_lo = nullptr;
     int tmp_rows = 0;
+    bool tail_fp32 = false;              // MQE_TC_TAIL=0: keep layers 1.. on the CUDA-core path (debug cross-check)
 };
 
 template <typename T>
@@ -189,8 +191,9 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
         CK(dupload(s, &s->pw.bw3, w.body_w3, 12 * 128)); CK(dupload(s, &s->pw.bb3, w.body_b3, 12));
         CK(cudaStreamSynchronize(s->stream));     // host staging vectors go out of scope
     }
+    { const char *e = getenv("MQE_TC_TAIL"); s->tail_fp32 = e && e[0] == '0'; }
     if (p.policy_mode != MQE_POLICY_FP32) {
-        int rc = mqe_policy_tc_prepare(&w, &s->tcw, s->stream);
+        int rc = mqe_policy_tc_prepare(&w, M, &s->tcw, s->stream);
         if (rc != 0) return fail(MQE_ERR_CUDA, "tensor-core policy weight preparation failed");
     }
     // pair table: groups X < Y, capsule i of X, capsule j of Y -- the oracle's loop order (mqe_oracle.c env_substep)
@@ -335,9 +338,12 @@ static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, c
     if (s->p.policy_mode == MQE_POLICY_FP32)
         CK(mqe_launch_policy_l0_fp32(s->pw, ps, ring, head, rows, s->stream));
     else
-        CK(mqe_launch_policy_l0_tc(s->tcw, s->pw.b0cat, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, ps.Z, s->stream));
+        CK(mqe_launch_policy_l0_tc(s->tcw, s->pw.b0cat, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, ps.Z, s->tail_fp32 ? 0 : 1, s->stream));
     int n = 1;
-    CK(mqe_launch_policy_tail(s->pw, ps, rows, s->stream, &n));
+    if (s->p.policy_mode == MQE_POLICY_FP32 || s->tail_fp32)
+        CK(mqe_launch_policy_tail(s->pw, ps, rows, s->stream, &n));
+    else
+        CK(mqe_launch_policy_tail_tc(s->tcw, s->pw, ps, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->stream, &n));
     s->launches += n;
     return MQE_OK;
 }

@@ -9,7 +9,12 @@ struct PolicyWeightsDev {           // device copies laid out for the kernels (a
     const float *aw1, *ab1, *aw2, *ab2;                         // adapt [128][256], [2][128]
     const float *bw1, *bb1, *bw2, *bb2, *bw3, *bb3;             // body  [256][512], [128][256], [12][128]
 };
-struct PolicyTcWeights { void *blob; size_t bytes; const void *l0_hi, *l0_lo; };   // bf16 hi/lo planes, pre-tiled (policy_tc.cu)
+struct PolicyTcWeights {            // bf16 hi/lo planes, pre-tiled (policy_tc.cu)
+    void *blob; size_t bytes; int rows;
+    const void *l0_hi, *l0_lo;       // layer 0 weights
+    const void *t_hi[5], *t_lo[5];   // tail layer weights
+    void *p_hi[5], *p_lo[5];         // activation planes between layers (sized for `rows`)
+};
 struct PolicyScratch { float *Z, *T1, *T2, *T3, *latent, *act; };
 
 extern "C" {
@@ -25,8 +30,10 @@ cudaError_t mqe_launch_policy_tail(const PolicyWeightsDev &w, const PolicyScratc
 cudaError_t mqe_launch_history_to_ring(const float *hist, float *ring, unsigned short *hi, unsigned short *lo, int rows, cudaStream_t st);
 cudaError_t mqe_launch_actuator(const float *act_w, const float *x, int rows, float *out, cudaStream_t st);
 // tensor-core policy layer 0 (policy_tc.cu)
-int mqe_policy_tc_prepare(const MqeWeights *w, PolicyTcWeights *out, cudaStream_t st);
+int mqe_policy_tc_prepare(const MqeWeights *w, int rows, PolicyTcWeights *out, cudaStream_t st);
 cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat, const unsigned short *hist_hi, const unsigned short *hist_lo,
-                                    int head, int rows, int passes, float *Z, cudaStream_t st);
+                                    int head, int rows, int passes, float *Z, int planes_out, cudaStream_t st);
+cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, int M, int passes,
+                                      cudaStream_t st, int *launches);
 size_t mqe_substeps_smem_bytes(int A, int Pd, int E, int maxpair);
 }

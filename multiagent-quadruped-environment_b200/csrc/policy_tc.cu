@@ -65,11 +65,30 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ float elu1_tc(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ void split_bf16x8(const float *v, uint4 &hi, uint4 &lo) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t b = __float_as_uint(v[i]);
+        uint32_t hb = (b + 0x7fffu + ((b >> 16) & 1u)) & 0xffff0000u;
+        uint32_t rb = __float_as_uint(v[i] - __uint_as_float(hb));
+        h[i] = hb >> 16;
+        l[i] = (rb + 0x7fffu + ((rb >> 16) & 1u)) >> 16;
+    }
+    hi = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    lo = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+}
+// element offset of (row m, column k) in an activation plane with `kchunks` = K/8 chunks per row tile
+__device__ __forceinline__ size_t plane_index(int m, int k, int kchunks) {
+    return (((size_t)(m >> 7) * kchunks + (k >> 3)) * 128 + (m & 127)) * 8 + (k & 7);
+}
+
 
 __global__ void __launch_bounds__(192, 1)
 k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo,
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
-               const float *__restrict__ b0cat, float *__restrict__ Z, int M, int head, int passes) {
+               const float *__restrict__ b0cat, float *__restrict__ Z, unsigned short *__restrict__ a0_hi,
+               unsigned short *__restrict__ a0_lo, int M, int head, int passes) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t *empty = full + TC_STAGES;
@@ -157,7 +176,19 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int n0 = ntile * 128 + c * 32;
-            if (row < M) {
+            if (n0 < 256 && a0_hi) {                        // adapt.0: bias + ELU, emitted as bf16 hi/lo planes for adapt.2
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) f[i] = elu1_tc(__uint_as_float(v[i]) + __ldg(b0cat + n0 + i));
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    uint4 hi, lo;
+                    split_bf16x8(f + 8 * g, hi, lo);
+                    const size_t o = plane_index(row, n0 + 8 * g, 32);
+                    *reinterpret_cast<uint4 *>(a0_hi + o) = hi;
+                    *reinterpret_cast<uint4 *>(a0_lo + o) = lo;
+                }
+            } else if (row < M) {
                 float *dst = Z + (size_t)row * 768 + n0;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -179,6 +210,172 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- generic tensor-core layer
+// Y = act(A W^T + bias) with BOTH operands arriving as pre-tiled bf16 hi/lo planes by bulk copy (the layer-0 recipe):
+//   A planes: [M/128 row tiles][K/8 k-chunks][128 rows][8 bf16]    written by the previous layer's epilogue
+//   W planes: [N/NCTA col tiles][K/64][8 k-chunks][NCTA rows][8 bf16]
+// Output either fp32 row-major (the two network heads: latent, action) or bias + ELU'd hi/lo planes for the next layer.
+// Activations never exist in fp32 in memory between layers; the only fp32 intermediate is body.0's pre-activation,
+// which has to wait for the latent (k_body_latent_planes).
+#define LT_BK 64
+#define LT_STAGES 3
+#define LT_A_PLANE (128 * LT_BK * 2)                       // 16 KB
+__host__ __device__ constexpr int lt_stage_bytes(int ncta) { return 2 * LT_A_PLANE + 2 * ncta * LT_BK * 2; }
+__host__ __device__ constexpr int lt_smem_bytes(int ncta) { return LT_STAGES * lt_stage_bytes(ncta) + 128; }
+
+template <int NCTA>
+__global__ void __launch_bounds__(192, 1)
+k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo, int K,
+            const unsigned short *__restrict__ w_hi, const unsigned short *__restrict__ w_lo, const float *__restrict__ bias,
+            float *__restrict__ Y, int ldy, int n_valid,                       // fp32 output (heads) when Y != nullptr
+            unsigned short *__restrict__ o_hi, unsigned short *__restrict__ o_lo, int out_kchunks,   // plane output otherwise
+            int M, int elu, int passes) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int STAGE = lt_stage_bytes(NCTA);
+    constexpr int W_PLANE = NCTA * LT_BK * 2;
+    constexpr uint32_t TCOLS = NCTA < 32 ? 32 : NCTA;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + LT_STAGES * STAGE);
+    uint64_t *empty = full + LT_STAGES;
+    uint64_t *accum = empty + LT_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntile = blockIdx.x, mtile = blockIdx.y;
+    const int nk = K / LT_BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < LT_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nk; it++) {
+                const int st = it % LT_STAGES, ph = (it / LT_STAGES) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                mbar_expect_tx(&full[st], passes == 3 ? 2 * (LT_A_PLANE + W_PLANE) : (LT_A_PLANE + W_PLANE));
+                unsigned char *sb = smem + st * STAGE;
+                const size_t ao = ((size_t)mtile * nk + it) * (128 * LT_BK);
+                const size_t wo = ((size_t)ntile * nk + it) * (NCTA * LT_BK);
+                bulk_g2s(sb, a_hi + ao, LT_A_PLANE, &full[st]);
+                bulk_g2s(sb + 2 * LT_A_PLANE, w_hi + wo, W_PLANE, &full[st]);
+                if (passes == 3) {
+                    bulk_g2s(sb + LT_A_PLANE, a_lo + ao, LT_A_PLANE, &full[st]);
+                    bulk_g2s(sb + 2 * LT_A_PLANE + W_PLANE, w_lo + wo, W_PLANE, &full[st]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NCTA >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t hiA = ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+            const uint64_t hiB = ((uint64_t)((NCTA * 16u) >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+            for (int it = 0; it < nk; it++) {
+                const int st = it % LT_STAGES, ph = (it / LT_STAGES) & 1;
+                mbar_wait(&full[st], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sb = smem_u32(smem + st * STAGE);
+                const uint64_t dAh = hiA | ((sb & 0x3FFFFu) >> 4), dAl = hiA | (((sb + LT_A_PLANE) & 0x3FFFFu) >> 4);
+                const uint64_t dBh = hiB | (((sb + 2 * LT_A_PLANE) & 0x3FFFFu) >> 4), dBl = hiB | (((sb + 2 * LT_A_PLANE + W_PLANE) & 0x3FFFFu) >> 4);
+                constexpr uint32_t aStep = (2 * 2048) >> 4, bStep = (2 * NCTA * 16) >> 4;      // two 8-wide k-chunks per MMA
+#pragma unroll
+                for (int j = 0; j < LT_BK / 16; j++) umma_f16(tmem, dAh + j * aStep, dBh + j * bStep, idesc, (it | j) ? 1u : 0u);
+                if (passes == 3) {
+#pragma unroll
+                    for (int j = 0; j < LT_BK / 16; j++) umma_f16(tmem, dAh + j * aStep, dBl + j * bStep, idesc, 1u);
+#pragma unroll
+                    for (int j = 0; j < LT_BK / 16; j++) umma_f16(tmem, dAl + j * aStep, dBh + j * bStep, idesc, 1u);
+                }
+                umma_commit(&empty[st]);
+            }
+            umma_commit(accum);
+        }
+        __syncwarp();
+    } else {
+        mbar_wait(accum, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int orow = mtile * 128 + q * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < NCTA / 16; c++) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int n0 = ntile * NCTA + c * 16;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                float t = __uint_as_float(v[i]) + ((n0 + i < n_valid) ? __ldg(bias + n0 + i) : 0.f);
+                f[i] = elu ? elu1_tc(t) : t;
+            }
+            if (Y) {
+                if (orow < M)
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (n0 + i < n_valid) Y[(size_t)orow * ldy + n0 + i] = f[i];
+            } else {                                         // rows >= M of the last tile are written too (planes are padded)
+                uint4 hi, lo;
+                split_bf16x8(f, hi, lo);
+                size_t o = plane_index(orow, n0, out_kchunks);
+                *reinterpret_cast<uint4 *>(o_hi + o) = hi; *reinterpret_cast<uint4 *>(o_lo + o) = lo;
+                split_bf16x8(f + 8, hi, lo);
+                o = plane_index(orow, n0 + 8, out_kchunks);
+                *reinterpret_cast<uint4 *>(o_hi + o) = hi; *reinterpret_cast<uint4 *>(o_lo + o) = lo;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS) : "memory");
+    }
+}
+
+// body.0 tail: planes(ELU(Zbody + Wlat latent)) -- the two latent columns of cat(h, latent) (go1.py:404-406).
+// One thread per (row, 8-column chunk); consecutive threads take consecutive rows so plane stores coalesce.
+__global__ void k_body_latent_planes(const float *__restrict__ Z, const float *__restrict__ latent, const float *__restrict__ wlat,
+                                     unsigned short *__restrict__ o_hi, unsigned short *__restrict__ o_lo, int M, int Mpad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Mpad * 64) return;
+    const int chunk = t / Mpad, m = t % Mpad;          // 64 chunks of 8 columns
+    float v[8];
+    if (m < M) {
+        const float *z = Z + (size_t)m * 768 + 256 + chunk * 8;
+        float4 a = *reinterpret_cast<const float4 *>(z), b = *reinterpret_cast<const float4 *>(z + 4);
+        const float l0 = latent[(size_t)m * 2], l1 = latent[(size_t)m * 2 + 1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int n = chunk * 8 + i;
+            v[i] = elu1_tc(v[i] + __ldg(wlat + n * 2) * l0 + __ldg(wlat + n * 2 + 1) * l1);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 0.f;
+    }
+    uint4 hi, lo;
+    split_bf16x8(v, hi, lo);
+    const size_t o = plane_index(m, chunk * 8, 64);
+    *reinterpret_cast<uint4 *>(o_hi + o) = hi;
+    *reinterpret_cast<uint4 *>(o_lo + o) = lo;
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 static inline unsigned short f2bf_rne(float v) {
     uint32_t b;
@@ -192,7 +389,22 @@ static inline float bf2f(unsigned short h) {
     return v;
 }
 
-extern "C" int mqe_policy_tc_prepare(const MqeWeights *w, PolicyTcWeights *out, cudaStream_t st) {
+// [N][K] row-major fp32 -> bf16 hi/lo planes tiled [n-tile][k-chunk 64][8 sub-chunks][ncta rows][8], rows padded with zeros
+static void tile_layer(const float *W, int N, int K, int ncta, std::vector<unsigned short> &hi, std::vector<unsigned short> &lo) {
+    const int ntiles = (N + ncta - 1) / ncta, nk = K / LT_BK;
+    hi.assign((size_t)ntiles * nk * ncta * LT_BK, 0);
+    lo.assign(hi.size(), 0);
+    for (int n = 0; n < N; n++)
+        for (int k = 0; k < K; k++) {
+            float v = W[(size_t)n * K + k];
+            unsigned short h = f2bf_rne(v), l = f2bf_rne(v - bf2f(h));
+            int nt = n / ncta, r = n % ncta, kc = k / LT_BK, c = (k % LT_BK) / 8, w = k % 8;
+            size_t o = ((((size_t)nt * nk + kc) * 8 + c) * ncta + r) * 8 + w;
+            hi[o] = h; lo[o] = l;
+        }
+}
+
+extern "C" int mqe_policy_tc_prepare(const MqeWeights *w, int rows, PolicyTcWeights *out, cudaStream_t st) {
     const size_t n = (size_t)6 * MQE_HIST_FRAMES * TC_TILE_ELEMS;
     std::vector<unsigned short> hi(n, 0), lo(n, 0);
     for (int col = 0; col < 768; col++) {
@@ -206,25 +418,70 @@ extern "C" int mqe_policy_tc_prepare(const MqeWeights *w, PolicyTcWeights *out, 
                 hi[o] = h; lo[o] = l;
             }
     }
+    // tail layers: adapt.2 (128x256), adapt.4 (2x128 -> 16 rows), body.2 (256x512), body.4 (128x256), body.6 (12x128 -> 16 rows)
+    const float *Ws[5] = {w->adapt_w1, w->adapt_w2, w->body_w1, w->body_w2, w->body_w3};
+    const int Ns[5] = {128, 2, 256, 128, 12}, Ks[5] = {256, 128, 512, 256, 128}, Cs[5] = {128, 16, 128, 128, 16};
+    std::vector<unsigned short> thi[5], tlo[5];
+    size_t total = 2 * n;
+    for (int i = 0; i < 5; i++) { tile_layer(Ws[i], Ns[i], Ks[i], Cs[i], thi[i], tlo[i]); total += 2 * thi[i].size(); }
+    // activation planes between layers: adapt.0 out (256), adapt.2 out (128), body.0 out (512), body.2 out (256), body.4 out (128)
+    const int mpad = (rows + 127) / 128 * 128;
+    const int act_k[5] = {256, 128, 512, 256, 128};
+    size_t act_off[5];
+    for (int i = 0; i < 5; i++) { act_off[i] = total; total += 2 * (size_t)mpad * act_k[i]; }
     void *blob = nullptr;
-    if (cudaMalloc(&blob, 2 * n * sizeof(unsigned short)) != cudaSuccess) return -1;
-    if (cudaMemcpyAsync(blob, hi.data(), n * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
-    if (cudaMemcpyAsync((unsigned short *)blob + n, lo.data(), n * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    if (cudaMalloc(&blob, total * sizeof(unsigned short)) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(blob, 0, total * sizeof(unsigned short), st) != cudaSuccess) return -1;
+    unsigned short *base = (unsigned short *)blob;
+    if (cudaMemcpyAsync(base, hi.data(), n * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(base + n, lo.data(), n * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+    size_t off = 2 * n;
+    for (int i = 0; i < 5; i++) {
+        const size_t m = thi[i].size();
+        if (cudaMemcpyAsync(base + off, thi[i].data(), m * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        if (cudaMemcpyAsync(base + off + m, tlo[i].data(), m * 2, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        out->t_hi[i] = base + off; out->t_lo[i] = base + off + m;
+        off += 2 * m;
+        out->p_hi[i] = base + act_off[i]; out->p_lo[i] = base + act_off[i] + (size_t)mpad * act_k[i];
+    }
+    out->rows = rows;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_policy_l0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_linear_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(128)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_linear_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(16)) != cudaSuccess) return -1;
     out->blob = blob;
-    out->bytes = 2 * n * sizeof(unsigned short);
+    out->bytes = total * sizeof(unsigned short);
     out->l0_hi = blob;
-    out->l0_lo = (unsigned short *)blob + n;
+    out->l0_lo = base + n;
     return 0;
 }
 
 // layer 0 only: Z[M][768] = act(ring x W0cat^T + b0cat), ELU on the adapt columns (< 256); the body columns stay
-// pre-activation until the latent columns are added (k_body_latent).
+// pre-activation until the latent columns are added (prologue of the first tail layer).
 extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat, const unsigned short *hist_hi,
-                                               const unsigned short *hist_lo, int head, int rows, int passes, float *Z, cudaStream_t st) {
+                                               const unsigned short *hist_lo, int head, int rows, int passes, float *Z, int planes_out,
+                                               cudaStream_t st) {
     dim3 grid(6, (rows + 127) / 128);
     k_policy_l0_tc<<<grid, 192, TC_SMEM_BYTES, st>>>(hist_hi, hist_lo, (const unsigned short *)w.l0_hi, (const unsigned short *)w.l0_lo,
-                                                      b0cat, Z, rows, head, passes);
+                                                      b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : nullptr,
+                                                      planes_out ? (unsigned short *)w.p_lo[0] : nullptr, rows, head, passes);
+    return cudaGetLastError();
+}
+
+// layers 1.. on the tensor cores: operands are bf16 hi/lo planes end to end (needs layer 0 launched with planes_out = 1)
+extern "C" cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, int M, int passes,
+                                                 cudaStream_t st, int *launches) {
+    const int mt = (M + 127) / 128, mpad = mt * 128;
+    auto H = [&](int i) { return (const unsigned short *)w.t_hi[i]; };
+    auto L = [&](int i) { return (const unsigned short *)w.t_lo[i]; };
+    auto PH = [&](int i) { return (unsigned short *)w.p_hi[i]; };
+    auto PL = [&](int i) { return (unsigned short *)w.p_lo[i]; };
+    k_linear_tc<128><<<dim3(1, mt), 192, lt_smem_bytes(128), st>>>(PH(0), PL(0), 256, H(0), L(0), pw.ab1, nullptr, 0, 128, PH(1), PL(1), 16, M, 1, passes);
+    k_linear_tc<16><<<dim3(1, mt), 192, lt_smem_bytes(16), st>>>(PH(1), PL(1), 128, H(1), L(1), pw.ab2, s.latent, 2, 2, nullptr, nullptr, 0, M, 0, passes);
+    k_body_latent_planes<<<(mpad * 64 + 255) / 256, 256, 0, st>>>(s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad);
+    k_linear_tc<128><<<dim3(2, mt), 192, lt_smem_bytes(128), st>>>(PH(2), PL(2), 512, H(2), L(2), pw.bb1, nullptr, 0, 256, PH(3), PL(3), 32, M, 1, passes);
+    k_linear_tc<128><<<dim3(1, mt), 192, lt_smem_bytes(128), st>>>(PH(3), PL(3), 256, H(3), L(3), pw.bb2, nullptr, 0, 128, PH(4), PL(4), 16, M, 1, passes);
+    k_linear_tc<16><<<dim3(1, mt), 192, lt_smem_bytes(16), st>>>(PH(4), PL(4), 128, H(4), L(4), pw.bb3, s.act, 12, 12, nullptr, nullptr, 0, M, 0, passes);
+    *launches += 6;
     return cudaGetLastError();
 }

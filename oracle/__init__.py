@@ -49,6 +49,7 @@ def load(precision="f64"):
         lib.orc_set.argtypes = [vp, ctypes.c_int, vp]
         lib.orc_set.restype = ctypes.c_int64
         lib.orc_real_size.restype = ctypes.c_int
+        lib.orc_set_threads.argtypes = [ctypes.c_int]
         lib.orc_policy_forward.argtypes = [ctypes.POINTER(E.WeightsC), vp, ctypes.c_int, vp, vp]
         lib.orc_actuator_forward.argtypes = [ctypes.POINTER(E.WeightsC), vp, ctypes.c_int, vp]
         lib.orc_robot_dynamics.argtypes = [vp, ctypes.c_double if precision == "f64" else ctypes.c_float, vp, vp, vp, vp, vp, vp, vp]
@@ -130,6 +131,10 @@ class Oracle:
 
     def obs(self):
         return self.get(self.E.BUF_OBS).reshape(self.N * self.A, self.E.OBS_FLOATS)
+
+
+def set_threads(n, precision="f32"):
+    load(precision).orc_set_threads(int(n))
 
 
 def policy_forward(weights_c, hist, precision="f64"):

@@ -1245,6 +1245,15 @@ int64_t orc_set(Oracle *o, int which, const float *in) {
 
 int orc_real_size(void) { return (int)sizeof(real); }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU-baseline legs ask for the host's cores explicitly */
+void orc_set_threads(int n) {
+#if defined(_OPENMP)
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------------ unit entry points */
 void orc_policy_forward(const MqeWeights *w, const float *hist, int rows, float *latent, float *action) {
 #pragma omp parallel for schedule(static)
