@@ -20,16 +20,19 @@ for i in range(30):
     eng.step(act.data_ptr())
 torch.cuda.synchronize()
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-for do_flush in (False, True):
+flush_i32 = flush.view(torch.int32)
+for do_flush in (False, True, "read"):
     acc = np.zeros(3)
     R = 30
     for i in range(R):
-        if do_flush:
+        if do_flush == "read":
+            _ = flush_i32.sum()
+        elif do_flush:
             flush.zero_()
         ev[0].record(); eng.policy(act.data_ptr()); ev[1].record(); eng.substeps(4); ev[2].record(); eng.post_physics(); ev[3].record()
         torch.cuda.synchronize()
         acc += [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])]
-    print(task, n, "flush" if do_flush else "noflush", "policy/substeps/post ms:", np.round(acc / R, 4), "stats", eng.tensor(E.BUF_STATS).cpu().numpy()[:4])
+    print(task, n, {False: "noflush", True: "flush-write", "read": "flush-read"}[do_flush], "policy/substeps/post ms:", np.round(acc / R, 4), "stats", eng.tensor(E.BUF_STATS).cpu().numpy()[:4])
 # whole steps back to back
 ev[0].record()
 for i in range(50):
