@@ -25,7 +25,8 @@
 #define RS_A 120
 #define RS_P 156
 #define RS_CAP 192
-#define RS_CNT 318     // int nrows, int nlim
+#define RS_CNT 318     // int scratch
+#define RS_BOUND 319   // true bounding radius of the robot's capsules about its origin (this substep)
 #define RS_ROWS 320
 #define RS_CMETA (RS_ROWS + MQE_MAX_ROWS * ROWF)
 #define RS_FORCE (RS_CMETA + MQE_MAX_LOCAL * 4)
@@ -34,6 +35,7 @@
 #define NS_ORIGIN 0
 #define NS_CAP 3       // p0 p1 r
 #define NS_CNT 10
+#define NS_BOUND 11
 #define NS_FORCE 12
 #define NS_ROWS 16
 #define NS_CMETA (NS_ROWS + 12 * ROWF)
@@ -42,13 +44,14 @@
 #define ES_CNT 0
 #define ES_ROWS 4
 #define ES_CMETA(maxpair) (ES_ROWS + (maxpair) * 3 * PROWF)
-#define ES_SIZE(maxpair) (ES_CMETA(maxpair) + (maxpair) * 8)
+#define ES_MASK(maxpair) (ES_CMETA(maxpair) + (maxpair) * 8)      // int capmask[G][G]: capsules of X within reach of group Y
+#define ES_SIZE(maxpair, G) (ES_MASK(maxpair) + (((G) * (G) + 3) & ~3))
 
 #define ACTW_FLOATS 1316   // 192 + 32 + 1024 + 32 + 32 + 1 = 1313, padded
 #define TBL_INTS 80        // per-leg probe lists [4][10] (count + 9 ids), per-leg capsule lists [4][10]
 
 __host__ __device__ inline int physics_warp_smem_floats(int A, int P, int E, int maxpair) {
-    return E * A * RS_SIZE + E * P * NS_SIZE + E * ES_SIZE(maxpair);
+    return E * A * RS_SIZE + E * P * NS_SIZE + E * ES_SIZE(maxpair, A + P);
 }
 __host__ __device__ inline int physics_cta_header_floats() { return (int)(sizeof(MqeRobotModel) / 4) + ACTW_FLOATS + TBL_INTS; }
 
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
     const int grp = is_robot ? ag : A + pn;                              // group index inside the env
     float *rs = wbase + (e_loc * A + ag) * RS_SIZE;                      // my robot block
     float *ns = wbase + E * A * RS_SIZE + (e_loc * P + pn) * NS_SIZE;    // my npc block
-    float *es = wbase + E * A * RS_SIZE + E * P * NS_SIZE + e_loc * ES_SIZE(maxpair);
+    float *es = wbase + E * A * RS_SIZE + E * P * NS_SIZE + e_loc * ES_SIZE(maxpair, G);
     const unsigned quad_mask = is_robot ? (0xFu << (lane & ~3)) : (1u << lane);
     unsigned env_mask = 0;
     {
@@ -502,7 +505,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 rs[RS_ORIGIN] = pos.x; rs[RS_ORIGIN + 1] = pos.y; rs[RS_ORIGIN + 2] = pos.z;
 #pragma unroll
                 for (int i = 0; i < 21; i++) rs[RS_SINV + i] = Sinv[i];
-                ((int *)rs)[RS_CNT] = 0; ((int *)rs)[RS_CNT + 1] = 0;
+                ((int *)rs)[RS_CNT] = 0;
                 for (int i = 0; i < 51; i++) rs[RS_FORCE + i] = 0.f;
             }
         } else if (is_npc) {
@@ -513,6 +516,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             ns[NS_CAP] = pos.x - ax.x; ns[NS_CAP + 1] = pos.y - ax.y; ns[NS_CAP + 2] = pos.z - ax.z;
             ns[NS_CAP + 3] = pos.x + ax.x; ns[NS_CAP + 4] = pos.y + ax.y; ns[NS_CAP + 5] = pos.z + ax.z; ns[NS_CAP + 6] = p.npc_radius;
             ((int *)ns)[NS_CNT] = 0;
+            ns[NS_BOUND] = p.npc_radius + p.npc_halflen;
             ns[NS_FORCE] = ns[NS_FORCE + 1] = ns[NS_FORCE + 2] = 0.f;
         }
         if (rank_in_env == 0) ((int *)es)[ES_CNT] = 0;
@@ -687,6 +691,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     pa[0] = a1.x; pa[1] = a1.y; pa[2] = a1.z; pa[3] = a2.x; pa[4] = a2.y; pa[5] = a2.z; pa[6] = a2.x; pa[7] = a2.y; pa[8] = a2.z;
                     pp[0] = p1.x; pp[1] = p1.y; pp[2] = p1.z; pp[3] = p2.x; pp[4] = p2.y; pp[5] = p2.z; pp[6] = p3.x; pp[7] = p3.y; pp[8] = p3.z;
                     const int *cl_ = tbl + 40 + leg * 10;
+                    float bound = 0.f;
                     for (int t = 0; t < cl_[0]; t++) {
                         const int ci = cl_[1 + t];
                         const float *cp = md->caps[ci];
@@ -694,12 +699,56 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                         const int k = link == 0 ? 0 : link - 3 * leg;
                         const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
                         V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
-                        V3 w0 = pos + pl + mul(Rl, mk(cp[2], cp[3], cp[4])), w1 = pos + pl + mul(Rl, mk(cp[5], cp[6], cp[7]));
+                        V3 l0 = pl + mul(Rl, mk(cp[2], cp[3], cp[4])), l1 = pl + mul(Rl, mk(cp[5], cp[6], cp[7]));
+                        V3 w0 = pos + l0, w1 = pos + l1;
                         float *o = rs + RS_CAP + ci * 7;
                         o[0] = w0.x; o[1] = w0.y; o[2] = w0.z; o[3] = w1.x; o[4] = w1.y; o[5] = w1.z; o[6] = cp[8];
+                        bound = fmaxf(bound, sqrtf(fmaxf(dot(l0, l0), dot(l1, l1))) + cp[8]);
                     }
+                    bound = fmaxf(bound, __shfl_xor_sync(quad_mask, bound, 1));
+                    bound = fmaxf(bound, __shfl_xor_sync(quad_mask, bound, 2));
+                    if (leg == 0) rs[RS_BOUND] = bound * 1.0001f + 1e-5f;
                 }
                 __syncwarp(env_mask);
+                // capsule culling: bit ci of capmask[X][Y] = capsule ci of group X reaches into the true bounding sphere of
+                // group Y (+ contact offset).  A pair (X,ci,Y,cj) can only touch if both bits are set, so the narrow phase
+                // below skips everything else -- exact, it never drops a pair the full enumeration would accept.
+                int *capmask = reinterpret_cast<int *>(es + ES_MASK(maxpair));
+                bool live_any = false;
+                for (int Y = 0; Y < G; Y++) {
+                    if (Y == grp) continue;
+                    const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
+                    const float *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
+                    const float reach = by_[Y < A ? RS_BOUND : NS_BOUND] + p.coff;
+                    const V3 cy = mk(oy[0], oy[1], oy[2]);
+                    int m = 0;
+                    if (is_robot) {
+                        const int *cl_ = tbl + 40 + leg * 10;
+                        for (int t = 0; t < cl_[0]; t++) {
+                            const int ci = cl_[1 + t];
+                            const float *o = rs + RS_CAP + ci * 7;
+                            V3 a0 = mk(o[0], o[1], o[2]), d = mk(o[3], o[4], o[5]) - a0, w = cy - a0;
+                            float dd = dot(d, d), tpar = dd > 1e-12f ? fminf(fmaxf(dot(w, d) / dd, 0.f), 1.f) : 0.f;
+                            V3 c = w - tpar * d;
+                            float lim = reach + o[6];
+                            if (dot(c, c) <= lim * lim) m |= 1 << ci;
+                        }
+                        m |= __shfl_xor_sync(quad_mask, m, 1);
+                        m |= __shfl_xor_sync(quad_mask, m, 2);
+                    } else {
+                        V3 a0 = mk(ns[NS_CAP], ns[NS_CAP + 1], ns[NS_CAP + 2]), d = mk(ns[NS_CAP + 3], ns[NS_CAP + 4], ns[NS_CAP + 5]) - a0, w = cy - a0;
+                        float dd = dot(d, d), tpar = dd > 1e-12f ? fminf(fmaxf(dot(w, d) / dd, 0.f), 1.f) : 0.f;
+                        V3 c = w - tpar * d;
+                        float lim = reach + ns[NS_CAP + 6];
+                        if (dot(c, c) <= lim * lim) m = 1;
+                    }
+                    if (is_npc || leg == 0) capmask[grp * G + Y] = m;
+                    live_any |= (m != 0);
+                }
+                if (env >= p.N) live_any = false;
+                __syncwarp(env_mask);
+                const bool any_live = __ballot_sync(env_mask, live_any) != 0u;
+                if (any_live)
                 for (int t0 = 0; t0 < n_pair_entries; t0 += lanes_per_env) {
                     int t = t0 + rank_in_env;
                     bool hit = false;
@@ -714,7 +763,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                         const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
                         float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
                         float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
-                        if (dx * dx + dy * dy + dz * dz <= lim * lim) {
+                        if (dx * dx + dy * dy + dz * dz <= lim * lim && ((capmask[X * G + Y] >> ci) & 1) && ((capmask[Y * G + X] >> cj) & 1)) {
                             const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
                             V3 c1, c2;
                             seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
@@ -767,25 +816,41 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         {
             float *rows = is_robot ? rs + RS_ROWS : ns + NS_ROWS;
             const int quad_base = lane & ~3;
+            // every lane of a quad keeps all four legs' u (12 floats): a row's leg term J_l . u_leg is then local arithmetic
+            // instead of a shuffle on the critical path of the sweep
+            float ua[4][3];
+#pragma unroll
+            for (int L = 0; L < 4; L++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) ua[L][k] = is_robot ? __shfl_sync(quad_mask, u[k], quad_base + L) : 0.f;
             for (int it = 0; it < p.iters; it++) {
+                float lam_n = 0.f;                                  // multiplier of the last normal row (friction rows follow it)
                 for (int i = 0; i < nrows; i++) {
                     float *row = rows + i * ROWF;
                     float4 r0 = *reinterpret_cast<const float4 *>(row), r1 = *reinterpret_cast<const float4 *>(row + 4), r2 = *reinterpret_cast<const float4 *>(row + 8);
                     float4 r3 = *reinterpret_cast<const float4 *>(row + 12), r4 = *reinterpret_cast<const float4 *>(row + 16), r5 = *reinterpret_cast<const float4 *>(row + 20);
-                    int meta = __float_as_int(r5.y), rleg = meta & 15, kind = (meta >> 4) & 1, nrow = meta >> 8;
+                    const int meta = __float_as_int(r5.y), rleg = meta & 15, kind = (meta >> 4) & 1;
                     float pb = r0.x * vb[0] + r0.y * vb[1] + r0.z * vb[2] + r0.w * vb[3] + r1.x * vb[4] + r1.y * vb[5];
-                    float pl = (is_robot && rleg == leg) ? (r1.z * u[0] + r1.w * u[1] + r2.x * u[2]) : 0.f;
-                    if (is_robot) pl = __shfl_sync(quad_mask, pl, quad_base + rleg);
+                    float pl = 0.f;
+#pragma unroll
+                    for (int L = 0; L < 4; L++) {
+                        float t = r1.z * ua[L][0] + r1.w * ua[L][1] + r2.x * ua[L][2];
+                        pl = rleg == L ? t : pl;
+                    }
                     float urel = r4.w + pb + pl;              // bias + J w
                     float lam_old = r5.x, lam = lam_old - urel * r4.z;
-                    if (kind == 0) lam = fmaxf(lam, 0.f);
-                    else { float lim = p.mu * rows[nrow * ROWF + 20]; lam = fminf(fmaxf(lam, -lim), lim); }
+                    if (kind == 0) { lam = fmaxf(lam, 0.f); lam_n = lam; }
+                    else { float lim = p.mu * lam_n; lam = fminf(fmaxf(lam, -lim), lim); }
                     float dl = lam - lam_old;
                     row[20] = lam;
                     vb[0] += r2.y * dl; vb[1] += r2.z * dl; vb[2] += r2.w * dl; vb[3] += r3.x * dl; vb[4] += r3.y * dl; vb[5] += r3.z * dl;
-                    if (is_robot && rleg == leg) { u[0] += r3.w * dl; u[1] += r4.x * dl; u[2] += r4.y * dl; }
+#pragma unroll
+                    for (int L = 0; L < 4; L++)
+                        if (rleg == L) { ua[L][0] += r3.w * dl; ua[L][1] += r4.x * dl; ua[L][2] += r4.y * dl; }
                 }
                 if (npair > 0) {   // uniform over the env's lanes
+#pragma unroll
+                    for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));
                     __syncwarp(env_mask);
                     for (int i = 0; i < 3 * npair; i++) {
                         float *row = es + ES_ROWS + i * PROWF;
@@ -819,8 +884,16 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                         }
                         __syncwarp(env_mask);
                     }
+                    if (is_robot) {
+#pragma unroll
+                        for (int L = 0; L < 4; L++)
+#pragma unroll
+                            for (int k = 0; k < 3; k++) ua[L][k] = __shfl_sync(quad_mask, u[k], quad_base + L);
+                    }
                 }
             }
+#pragma unroll
+            for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));
         }
 
         // ================================================================ P5: contact force report (last substep), integrate
