@@ -105,6 +105,10 @@ typedef struct {
     float sheep_scale, sheep_randomness;        /* go1_sheep_config.py asset.sheep_movement_*              */
     float gate_x;                               /* defender: init+plane block length                       */
     float reserved2;
+    /* MQE_NPC_SEESAW geometry (resources/objects/seesaw.urdf): [0..2] revolute-y joint origin rel. the fixed base,
+     * [3] plank box / COM x offset in the plank frame, [4..6] plank half extents, [7..9] platform (base box) half extents,
+     * [10] column radius, [11] column length, [12] joint velocity limit [rad/s]; rest unused. */
+    float npc_geom[16];
     uint64_t seed;
     /* static world: 2-D signed distance to the wall footprint on the BarrierTrack pixel grid */
     int32_t sdf_nx, sdf_ny;

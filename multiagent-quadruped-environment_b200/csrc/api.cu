@@ -118,7 +118,9 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     DevParams &p = s->p;
     memset(&p, 0, sizeof p);
     p.N = N; p.A = A; p.P = P; p.D = D; p.G = G;
-    p.Pd = (d->npc_kind == MQE_NPC_RIGID) ? P : 0;
+    p.Pd = (d->npc_kind == MQE_NPC_RIGID || d->npc_kind == MQE_NPC_SEESAW) ? P : 0;   // NPCs that own a lane of the substep kernel
+    if (d->npc_kind == MQE_NPC_SEESAW && (P != 1 || D != 1)) return fail(MQE_ERR_UNSUPPORTED, "seesaw: exactly one NPC with one DOF");
+    for (int i = 0; i < 16; i++) p.geom[i] = d->npc_geom[i];
     p.env_off = d->env_id_offset;
     p.npc_kind = d->npc_kind; p.npc_ctrl = d->npc_ctrl;
     p.decimation = d->decimation; p.iters = d->solver_iters; p.max_ep_len = d->max_episode_length;
@@ -199,7 +201,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     // pair table: groups X < Y, capsule i of X, capsule j of Y -- the oracle's loop order (mqe_oracle.c env_substep)
     {
         std::vector<unsigned int> pt;
-        const int Gd = A + p.Pd, nc = d->model.n_caps;
+        const int Gd = A + (d->npc_kind == MQE_NPC_RIGID ? P : 0), nc = d->model.n_caps;    // capsule groups only
         for (int X = 0; X < Gd; X++)
             for (int Y = X + 1; Y < Gd; Y++) {
                 int nx = X < A ? nc : 1, ny = Y < A ? nc : 1;

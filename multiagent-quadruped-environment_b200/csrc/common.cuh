@@ -32,6 +32,7 @@ struct DevParams {
     float bpos_x[2], bpos_y[2], npos_x[2], npos_y[2], nrpy_r[2], nrpy_p[2], nrpy_y[2];
     float npc_mass, npc_inertia, npc_radius, npc_halflen;
     float sheep_scale, sheep_rand, gate_x;
+    float geom[16];               // MQE_NPC_SEESAW geometry (MqeSimDesc.npc_geom)
     unsigned long long seed;
     int sdf_nx, sdf_ny;
     float sdf_cell;

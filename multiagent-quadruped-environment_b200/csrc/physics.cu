@@ -185,19 +185,58 @@ __device__ __forceinline__ float softsign(float x) {
 
 // world probe of a sphere against floor slab + wall footprint; bit0: floor/top contact, bit1: wall contact
 struct ProbeHit { int mask; float gap_f, gap_w; V3 nw; };
-__device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float r) {
+// `fix`: position of the seesaw's fixed base when the env has one (platform top is ground inside its footprint, the column
+// below it is a vertical cylinder that competes with the wall footprint for the wall-like contact); seesaw.urdf.
+__device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float r, bool has_fix = false, V3 fix = V3{0.f, 0.f, 0.f}) {
     ProbeHit h;
     h.mask = 0;
     SdfSample s = sdf_sample(p, x.x, x.y);
     bool inside = s.sdf < 0.f, above = x.z >= p.wall_top;
     float ground = (inside && above) ? p.wall_top : p.floor_z;
+    float gw = s.sdf - r, gn = sqrtf(s.gx * s.gx + s.gy * s.gy);
+    bool wall_ok = !above && gn > 1e-6f;
+    h.nw = wall_ok ? mk(s.gx / gn, s.gy / gn, 0.f) : mk(0.f, 0.f, 0.f);
+    if (has_fix) {
+        const float *g = p.geom;
+        float px = x.x - fix.x, py = x.y - fix.y;
+        if (fabsf(px) <= g[7] && fabsf(py) <= g[8] && x.z >= fix.z) ground = fmaxf(ground, fix.z + g[9]);
+        if (x.z < fix.z && x.z > fix.z - g[11] - r) {
+            float dh = sqrtf(px * px + py * py), gc = dh - g[10] - r;
+            if (dh > 1e-6f && (!wall_ok || gc < gw)) { wall_ok = true; gw = gc; h.nw = mk(px / dh, py / dh, 0.f); }
+        }
+    }
     h.gap_f = x.z - r - ground;
     if (h.gap_f < p.coff) h.mask |= 1;
-    h.gap_w = s.sdf - r;
-    float gn = sqrtf(s.gx * s.gx + s.gy * s.gy);
-    h.nw = mk(0.f, 0.f, 0.f);
-    if (!above && h.gap_w < p.coff && gn > 1e-6f) { h.mask |= 2; h.nw = mk(s.gx / gn, s.gy / gn, 0.f); }
+    h.gap_w = gw;
+    if (wall_ok && gw < p.coff) h.mask |= 2;
     return h;
+}
+
+// sphere vs the seesaw plank (oriented box in the frame pivot; ex = (c,0,-s), ey, ez = (s,0,c)); normal plank -> sphere
+__device__ __forceinline__ bool sphere_plank(const DevParams &p, V3 pivot, float c, float s, V3 x, float r, V3 &nrm, float &gap, V3 &pos) {
+    const float *g = p.geom;
+    V3 dx = x - pivot;
+    float loc[3] = {dx.x * c - dx.z * s - g[3], dx.y, dx.x * s + dx.z * c}, h[3] = {g[4], g[5], g[6]}, df[3], nl[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; i++) df[i] = loc[i] - fminf(fmaxf(loc[i], -h[i]), h[i]);
+    float d2 = df[0] * df[0] + df[1] * df[1] + df[2] * df[2];
+    if (d2 > 1e-12f) {
+        float dist = sqrtf(d2);
+        nl[0] = df[0] / dist; nl[1] = df[1] / dist; nl[2] = df[2] / dist;
+        gap = dist - r;
+    } else {
+        int ax = 0;
+        float best = h[0] - fabsf(loc[0]);
+#pragma unroll
+        for (int i = 1; i < 3; i++) { float pen = h[i] - fabsf(loc[i]); if (pen < best) { best = pen; ax = i; } }
+        float sg = (ax == 0 ? loc[0] : (ax == 1 ? loc[1] : loc[2])) >= 0.f ? 1.f : -1.f;
+        nl[0] = ax == 0 ? sg : 0.f; nl[1] = ax == 1 ? sg : 0.f; nl[2] = ax == 2 ? sg : 0.f;
+        gap = -best - r;
+    }
+    if (gap >= p.coff) return false;
+    nrm = mk(nl[0] * c + nl[2] * s, nl[1], -nl[0] * s + nl[2] * c);
+    pos = x - (r + 0.5f * gap) * nrm;
+    return true;
 }
 
 // closest points of two segments (Ericson 5.1.9); same branch structure as the oracle
@@ -254,8 +293,33 @@ __device__ float npc_side(const DevParams &p, V3 r, V3 d, float *out) {
     out[9] = rxd.x * iI * up; out[10] = rxd.y * iI * up; out[11] = rxd.z * iI;
     out[12] = d.x * im; out[13] = d.y * im; out[14] = d.z * im;
     out[15] = out[16] = out[17] = 0.f;
+    if (p.npc_kind == MQE_NPC_SEESAW) {      // one revolute-y DOF about the pivot: only w_y responds, with 1 / I_pivot
+        const float iIp = 1.f / (p.npc_inertia + p.npc_mass * p.geom[3] * p.geom[3]);
+#pragma unroll
+        for (int i = 9; i < 15; i++) out[i] = 0.f;
+        out[10] = rxd.y * iIp;
+    }
     float dd = 0.f;
     for (int i = 0; i < 6; i++) dd += out[i] * out[9 + i];
+    return dd;
+}
+// one side of a row for a robot from the lane's OWN operators (registers); k = link depth in the lane's leg (0 base .. 3 calf)
+__device__ __forceinline__ float robot_side_regs(int k, V3 r, V3 d, V3 a1, V3 a2, V3 p1, V3 p2, V3 p3, const float *Gm, const float *Sinv,
+                                                 const float *Hinv, float *out) {
+    V3 rxd = cross(r, d);
+    float Jb[6] = {rxd.x, rxd.y, rxd.z, d.x, d.y, d.z}, Jl[3] = {0.f, 0.f, 0.f}, Yb[6], Yl[3];
+    if (k >= 1) Jl[0] = dot(a1, cross(r - p1, d));
+    if (k >= 2) Jl[1] = dot(a2, cross(r - p2, d));
+    if (k >= 3) Jl[2] = dot(a2, cross(r - p3, d));
+#pragma unroll
+    for (int i = 0; i < 6; i++) Jb[i] -= Gm[i * 3] * Jl[0] + Gm[i * 3 + 1] * Jl[1] + Gm[i * 3 + 2] * Jl[2];
+    sym6_mulv(Sinv, Jb, Yb);
+    sym3_mulv(Hinv, Jl, Yl);
+    float dd = Jl[0] * Yl[0] + Jl[1] * Yl[1] + Jl[2] * Yl[2];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { dd += Jb[i] * Yb[i]; out[i] = Jb[i]; out[9 + i] = Yb[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { out[6 + i] = Jl[i]; out[15 + i] = Yl[i]; }
     return dd;
 }
 
@@ -295,6 +359,8 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
     __syncthreads();
     const int A = p.A, P = p.Pd, E = p.E, G = A + P;   // P: dynamic NPCs only (a seesaw is not a free body)
     const int GA = p.G;                                 // actors per env in the root-state tensor
+    const bool seesaw = p.npc_kind == MQE_NPC_SEESAW;   // the NPC lane is a 1-DOF plank on a fixed base (seesaw.urdf)
+    const int Gc = seesaw ? A : G;                      // groups that take part in the capsule / capsule phase
     float *wbase = smem + physics_cta_header_floats() + warp * physics_warp_smem_floats(A, P, E, maxpair);
     const int first_env = (blockIdx.x * nwarps + warp) * E;
     if (first_env >= p.N) return;
@@ -346,6 +412,12 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
     } else {
 #pragma unroll
         for (int k = 0; k < 3; k++) { e1[k] = e2[k] = v1[k] = v2[k] = 0.f; }
+    }
+    V3 fixb = mk(0, 0, 0);                                               // seesaw: position of the fixed base (platform)
+    if (seesaw && env < p.N) {
+        const float *r = p.root + ((size_t)env * GA + A) * 13;
+        fixb = mk(r[0], r[1], r[2]);
+        if (is_npc) { const float *d = p.dof + ((size_t)env * (12 * A + p.D) + 12 * A) * 2; q[0] = d[0]; qd[0] = d[1]; }
     }
     int stat_local = 0, stat_lim = 0, stat_pair = 0, stat_rows = 0;
 
@@ -508,6 +580,17 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 ((int *)rs)[RS_CNT] = 0;
                 for (int i = 0; i < 51; i++) rs[RS_FORCE + i] = 0.f;
             }
+        } else if (is_npc && seesaw) {
+            // passive revolute-y plank: gravity torque r_x m g about the pivot, I_pivot = I_yy + m r_x^2
+            float sn, cs;
+            sincosf(q[0], &sn, &cs);
+            const float Ip = p.npc_inertia + p.npc_mass * p.geom[3] * p.geom[3];
+            vb[1] = qd[0] + p.dt * (p.geom[3] * cs * p.npc_mass * (-p.gz)) / Ip;
+            ns[NS_ORIGIN] = pos.x + p.geom[0]; ns[NS_ORIGIN + 1] = pos.y + p.geom[1]; ns[NS_ORIGIN + 2] = pos.z + p.geom[2];
+            ns[NS_CAP] = cs; ns[NS_CAP + 1] = sn;
+            ((int *)ns)[NS_CNT] = 0;
+            ns[NS_BOUND] = 0.f;
+            ns[NS_FORCE] = ns[NS_FORCE + 1] = ns[NS_FORCE + 2] = 0.f;
         } else if (is_npc) {
             vb[0] = wang.x; vb[1] = wang.y; vb[2] = wang.z; vb[3] = vlin.x; vb[4] = vlin.y; vb[5] = vlin.z + p.dt * p.gz;
             Rb = quat_to_mat(qx, qy, qz, qw);
@@ -574,7 +657,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
                     V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
                     V3 xw = pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
-                    ProbeHit h = probe_world(p, xw, pr[5]);
+                    ProbeHit h = probe_world(p, xw, pr[5], seesaw, fixb);
                     cm |= (unsigned long long)h.mask << (2 * pi);
                 }
             unsigned long long call = cm;
@@ -595,7 +678,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
                 V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
                 V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));            // probe centre rel. O
-                ProbeHit h = probe_world(p, pos + xr, pr[5]);
+                ProbeHit h = probe_world(p, pos + xr, pr[5], seesaw, fixb);
                 V3 n = kind ? h.nw : mk(0, 0, 1);
                 float gap = kind ? h.gap_w : h.gap_f;
                 V3 r = xr - (pr[5] + 0.5f * gap) * n;                     // contact point rel. O
@@ -631,6 +714,32 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 }
             }
             if (leg == 0 && active) { stat_local += ncon; stat_lim += nlim; }
+        } else if (is_npc && active && seesaw) {
+            int ncon = 0;
+            const float cs = ns[NS_CAP], sn = ns[NS_CAP + 1];
+            for (int en = 0; en < 2; en++) {
+                const float xe = p.geom[3] + (en == 0 ? -1.f : 1.f) * p.geom[4];
+                V3 r = mk(xe * cs, 0.f, -xe * sn);                       // plank end rel. the pivot
+                float gap = ns[NS_ORIGIN + 2] + r.z - p.geom[6] - p.floor_z;
+                if (gap >= p.coff) continue;
+                V3 n = mk(0, 0, 1), t1, t2;
+                r.z -= p.geom[6] + 0.5f * gap;
+                tangent_basis(n, t1, t2);
+                float *cmeta = ns + NS_CMETA + ncon * 4;
+                cmeta[0] = n.x; cmeta[1] = n.y; cmeta[2] = n.z; cmeta[3] = 0.f;
+                for (int dch = 0; dch < 3; dch++) {
+                    V3 d = dch == 0 ? n : (dch == 1 ? t1 : t2);
+                    float *row = ns + NS_ROWS + (3 * ncon + dch) * ROWF;
+                    float dd = npc_side(p, r, d, row);
+                    row[18] = 1.f / (dd + p.cfm);
+                    row[19] = dch == 0 ? contact_bias(p, gap) : 0.f;
+                    row[20] = 0.f;
+                    row[21] = __int_as_float(0 | ((dch ? 1 : 0) << 4) | ((3 * ncon) << 8));
+                }
+                ncon++;
+            }
+            nrows = 3 * ncon;
+            stat_local += ncon;
         } else if (is_npc && active) {
             int ends = p.npc_halflen > 0.f ? 2 : 1, ncon = 0;
             for (int en = 0; en < ends && ncon < MQE_MAX_LOCAL; en++) {
@@ -666,10 +775,10 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         if (G > 1 && (is_robot || is_npc)) {
             // broadphase over group pairs
             bool close = false;
-            int ngp = G * (G - 1) / 2;
+            int ngp = Gc * (Gc - 1) / 2;
             for (int t = rank_in_env; t < ngp; t += lanes_per_env) {
                 int X = 0, rem = t;
-                while (rem >= G - 1 - X) { rem -= G - 1 - X; X++; }
+                while (rem >= Gc - 1 - X) { rem -= Gc - 1 - X; X++; }
                 int Y = X + 1 + rem;
                 const float *ox = X < A ? wbase + (e_loc * A + X) * RS_SIZE + RS_ORIGIN : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE + NS_ORIGIN;
                 const float *oy = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE + RS_ORIGIN : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE + NS_ORIGIN;
@@ -715,8 +824,8 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 // below skips everything else -- exact, it never drops a pair the full enumeration would accept.
                 int *capmask = reinterpret_cast<int *>(es + ES_MASK(maxpair));
                 bool live_any = false;
-                for (int Y = 0; Y < G; Y++) {
-                    if (Y == grp) continue;
+                for (int Y = 0; Y < Gc; Y++) {
+                    if (Y == grp || grp >= Gc) continue;
                     const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
                     const float *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
                     const float reach = by_[Y < A ? RS_BOUND : NS_BOUND] + p.coff;
@@ -806,6 +915,64 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     }
                 }
                 npair = min(npair, maxpair);
+            }
+            if (seesaw) {
+                // robot probes on the plank: canonical order = robot ascending, probe-table order (two-pass compaction)
+                const float *nsS = wbase + E * A * RS_SIZE + (e_loc * P) * NS_SIZE;
+                const V3 pivot = mk(nsS[NS_ORIGIN], nsS[NS_ORIGIN + 1], nsS[NS_ORIGIN + 2]);
+                const float cs = nsS[NS_CAP], sn = nsS[NS_CAP + 1];
+                unsigned sm = 0;
+                const int *pl_ = tbl + leg * 10;
+                if (is_robot && active)
+                    for (int t = 0; t < pl_[0]; t++) {
+                        const int pi = pl_[1 + t];
+                        const float *pr = md->probes[pi];
+                        const int link = (int)pr[0];
+                        const int k = link == 0 ? 0 : link - 3 * leg;
+                        const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
+                        V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                        V3 nn, pp;
+                        float gg;
+                        if (sphere_plank(p, pivot, cs, sn, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], nn, gg, pp)) sm |= 1u << pi;
+                    }
+                unsigned sall = sm;
+                if (is_robot) { sall |= __shfl_xor_sync(quad_mask, sall, 1); sall |= __shfl_xor_sync(quad_mask, sall, 2); }
+                int base_slot = npair, total = 0;
+                for (int X = 0; X < A; X++) {
+                    int cnt = __popc(__shfl_sync(env_mask, sall, e_loc * 4 * A + 4 * X));
+                    if (is_robot && X < ag) base_slot += cnt;
+                    total += cnt;
+                }
+                while (sm) {
+                    const int b = __ffs(sm) - 1;
+                    sm &= sm - 1u;
+                    const int slot = base_slot + __popc(sall & ((1u << b) - 1u));
+                    if (slot >= maxpair) break;
+                    const float *pr = md->probes[b];
+                    const int link = (int)pr[0], body = (int)pr[1];
+                    const int k = link == 0 ? 0 : link - 3 * leg;
+                    const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
+                    V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                    V3 cn, cpos, t1, t2;
+                    float cgap;
+                    sphere_plank(p, pivot, cs, sn, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], cn, cgap, cpos);
+                    tangent_basis(cn, t1, t2);
+                    const V3 ra = cpos - pos, rb_ = cpos - pivot;
+                    float *cmeta = es + ES_CMETA(maxpair) + slot * 8;
+                    cmeta[0] = cn.x; cmeta[1] = cn.y; cmeta[2] = cn.z;
+                    cmeta[3] = __int_as_float(ag * MQE_NUM_BODIES + body); cmeta[4] = __int_as_float(A * MQE_NUM_BODIES);
+                    for (int dch = 0; dch < 3; dch++) {
+                        V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
+                        float *row = es + ES_ROWS + (3 * slot + dch) * PROWF;
+                        float dd = robot_side_regs(k, ra, d, a1, a2, p1, p2, p3, Gm, Sinv, Hinv, row);
+                        dd += npc_side(p, rb_, -d, row + 18);
+                        row[36] = 1.f / (dd + p.cfm);
+                        row[37] = dch == 0 ? contact_bias(p, cgap) : 0.f;
+                        row[38] = 0.f;
+                        row[39] = __int_as_float(ag | (leg << 4) | (A << 8) | (0 << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
+                    }
+                }
+                npair = min(npair + total, maxpair);
             }
             if (rank_in_env == 0 && env < p.N) stat_pair += npair;
         }
@@ -958,7 +1125,11 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 q[k] += p.dt * v;
             }
         }
-        if (is_robot || is_npc) {
+        if (is_npc && seesaw) {
+            const float lim = p.geom[12];                                    // URDF joint velocity limit
+            qd[0] = fminf(fmaxf(vb[1], -lim), lim);
+            q[0] += p.dt * qd[0];
+        } else if (is_robot || is_npc) {
             wang = mk(vb[0], vb[1], vb[2]); vlin = mk(vb[3], vb[4], vb[5]);
             pos = pos + p.dt * vlin;
             float wn = sqrtf(dot(wang, wang)), th = wn * p.dt, dx, dy, dz, dw;
@@ -976,7 +1147,10 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
 
     // ---- write back ----
     if (active) {
-        if (is_npc || leg == 0) {
+        if (is_npc && seesaw) {
+            float *d = p.dof + ((size_t)env * (12 * A + p.D) + 12 * A) * 2;
+            d[0] = q[0]; d[1] = qd[0];
+        } else if (is_npc || leg == 0) {
             float *r = p.root + ((size_t)env * GA + grp) * 13;
             r[0] = pos.x; r[1] = pos.y; r[2] = pos.z; r[3] = qx; r[4] = qy; r[5] = qz; r[6] = qw;
             r[7] = vlin.x; r[8] = vlin.y; r[9] = vlin.z; r[10] = wang.x; r[11] = wang.y; r[12] = wang.z;

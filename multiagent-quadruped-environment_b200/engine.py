@@ -86,6 +86,7 @@ class SimDescC(ctypes.Structure):
         ("npc_halflen", ctypes.c_float),
         ("sheep_scale", ctypes.c_float), ("sheep_randomness", ctypes.c_float),
         ("gate_x", ctypes.c_float), ("reserved2", ctypes.c_float),
+        ("npc_geom", ctypes.c_float * 16),
         ("seed", ctypes.c_uint64),
         ("sdf_nx", ctypes.c_int32), ("sdf_ny", ctypes.c_int32), ("sdf_cell", ctypes.c_float), ("reserved3", ctypes.c_float),
         ("h_sdf", _fp), ("h_env_origins", _fp), ("h_agent_origins", _fp), ("h_base_init_state", _fp),

@@ -535,13 +535,26 @@ static void tangent_basis(const real *n, real *t1, real *t2) {
 
 /* world probe of a sphere (centre x world, radius r) against floor slab + wall footprint.
  * Emits up to 2 contacts (floor/top, wall side). */
-static int probe_world(const Oracle *o, const real *x, real r, Contact *out) {
+static int probe_world(const Oracle *o, const real *x, real r, const real *fix, Contact *out) {
     const MqeSimDesc *d = &o->d;
     int n = 0;
     SdfSample s = sdf_sample(o, x[0], x[1]);
     int inside = s.sdf < 0;
     int above_top = x[2] >= d->wall_top_z;
     real ground = (inside && above_top) ? d->wall_top_z : d->floor_z;
+    /* wall-like candidate: BarrierTrack footprint ... */
+    real gw = s.sdf - r, gn = sqrt(s.gx * s.gx + s.gy * s.gy), wn[2] = {0, 0};
+    int wall_ok = !above_top && gn > (real)1e-6;
+    if (wall_ok) { wn[0] = s.gx / gn; wn[1] = s.gy / gn; }
+    if (fix) { /* seesaw.urdf statics: platform top is ground inside its footprint, the column is a vertical cylinder */
+        const float *g = d->npc_geom;
+        real px = x[0] - fix[0], py = x[1] - fix[1];
+        if (fabs(px) <= g[7] && fabs(py) <= g[8] && x[2] >= fix[2]) { real top = fix[2] + g[9]; if (top > ground) ground = top; }
+        if (x[2] < fix[2] && x[2] > fix[2] - g[11] - r) {
+            real dh = sqrt(px * px + py * py), gc = dh - g[10] - r;
+            if (dh > (real)1e-6 && (!wall_ok || gc < gw)) { wall_ok = 1; gw = gc; wn[0] = px / dh; wn[1] = py / dh; }
+        }
+    }
     real gap = x[2] - r - ground;
     if (gap < d->contact_offset) {
         Contact *c = &out[n++];
@@ -549,17 +562,40 @@ static int probe_world(const Oracle *o, const real *x, real r, Contact *out) {
         c->gap = gap;
         v3set(c->pos, x[0], x[1], x[2] - r - gap * (real)0.5);
     }
-    if (!above_top) {
-        real gw = s.sdf - r;
-        real gn = sqrt(s.gx * s.gx + s.gy * s.gy);
-        if (gw < d->contact_offset && gn > (real)1e-6) {
-            Contact *c = &out[n++];
-            v3set(c->n, s.gx / gn, s.gy / gn, 0);
-            c->gap = gw;
-            for (int i = 0; i < 3; i++) c->pos[i] = x[i] - c->n[i] * (r + gw * (real)0.5);
-        }
+    if (wall_ok && gw < d->contact_offset) {
+        Contact *c = &out[n++];
+        v3set(c->n, wn[0], wn[1], 0);
+        c->gap = gw;
+        for (int i = 0; i < 3; i++) c->pos[i] = x[i] - c->n[i] * (r + gw * (real)0.5);
     }
     return n;
+}
+
+/* sphere (centre x, radius r) vs the seesaw plank: oriented box in the frame (pivot; ex = (c,0,-s), ey, ez = (s,0,c)).
+ * Returns 1 and fills normal (plank -> sphere), gap, contact point when gap < contact_offset. */
+static int sphere_plank(const MqeSimDesc *d, const real *pivot, real c, real s, const real *x, real r, real *nrm, real *gap_out, real *pos) {
+    const float *g = d->npc_geom;
+    real dx[3] = {x[0] - pivot[0], x[1] - pivot[1], x[2] - pivot[2]};
+    real loc[3] = {dx[0] * c - dx[2] * s - g[3], dx[1], dx[0] * s + dx[2] * c};
+    real h[3] = {g[4], g[5], g[6]}, q[3], df[3], nl[3] = {0, 0, 0}, gap;
+    for (int i = 0; i < 3; i++) { q[i] = loc[i] < -h[i] ? -h[i] : (loc[i] > h[i] ? h[i] : loc[i]); df[i] = loc[i] - q[i]; }
+    real d2 = df[0] * df[0] + df[1] * df[1] + df[2] * df[2];
+    if (d2 > (real)1e-12) {
+        real dist = sqrt(d2);
+        for (int i = 0; i < 3; i++) nl[i] = df[i] / dist;
+        gap = dist - r;
+    } else {            /* centre inside the box: push out along the axis of least penetration */
+        int ax = 0;
+        real best = h[0] - fabs(loc[0]);
+        for (int i = 1; i < 3; i++) { real pen = h[i] - fabs(loc[i]); if (pen < best) { best = pen; ax = i; } }
+        nl[ax] = loc[ax] >= 0 ? 1 : -1;
+        gap = -best - r;
+    }
+    if (gap >= d->contact_offset) return 0;
+    nrm[0] = nl[0] * c + nl[2] * s; nrm[1] = nl[1]; nrm[2] = -nl[0] * s + nl[2] * c;
+    for (int i = 0; i < 3; i++) pos[i] = x[i] - nrm[i] * (r + gap * (real)0.5);
+    *gap_out = gap;
+    return 1;
 }
 
 /* closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9) */
@@ -629,6 +665,10 @@ static void group_jacobian(const Oracle *o, const EnvScratch *es, int g, int lin
          * response; the ball is a free sphere */
         real up = (o->d.npc_ctrl == MQE_NPC_SHEEP) ? 0 : 1;
         for (int i = 0; i < 3; i++) { J[i] = rxd[i]; J[3 + i] = dir[i]; Y[i] = rxd[i] * es->npc_minv[0] * (i < 2 ? up : 1); Y[3 + i] = dir[i] * es->npc_minv[1]; }
+        if (o->d.npc_kind == MQE_NPC_SEESAW) {   /* one revolute-y DOF about the pivot (= group origin): only w_y responds */
+            memset(Y, 0, NV * sizeof(real));
+            Y[1] = rxd[1] * es->npc_minv[0];
+        }
     }
 }
 
@@ -727,6 +767,23 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         }
     }
 
+    const int seesaw = P && d->npc_kind == MQE_NPC_SEESAW;
+    real ss_c = 1, ss_s = 0;
+    const real *ss_fix = NULL;
+    if (seesaw) {   /* resources/objects/seesaw.urdf: fixed base, plank on a passive revolute-y joint */
+        const float *gm = d->npc_geom;
+        const real *rs = root + A * 13;
+        real th = dof[(12 * A) * 2], thd = dof[(12 * A) * 2 + 1];
+        real Ip = d->npc_inertia + d->npc_mass * gm[3] * gm[3];
+        ss_fix = rs;
+        ss_c = cos(th); ss_s = sin(th);
+        for (int i = 0; i < 3; i++) es.origin[A][i] = rs[i] + gm[i];
+        es.npc_minv[0] = 1 / Ip; es.npc_minv[1] = 0;
+        real tau_g = gm[3] * ss_c * d->npc_mass * (-d->gravity_z);       /* r_x m g about +y */
+        es.vel[A][1] = thd + dt * tau_g / Ip;
+        es.ndof[A] = 6;
+    }
+
     /* 2. rows: per robot joint limits, then world contacts (probe order); per npc world contacts; then pairs */
     for (int a = 0; a < A; a++) {
         RobotDyn *rd = &es.rd[a];
@@ -756,7 +813,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
             v3add(x, x, rd->p[link]);
             v3add(x, x, es.origin[a]);
             Contact cand[2];
-            int k = probe_world(o, x, pr[5], cand);
+            int k = probe_world(o, x, pr[5], ss_fix, cand);
             for (int i = 0; i < k && nloc < MAX_LOCAL_CONTACTS; i++) {
                 Contact *c = &contacts[nc];
                 *c = cand[i];
@@ -778,7 +835,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
             m3mulv(x, npcR[g], loc);
             v3add(x, x, es.origin[g]);
             Contact cand[2];
-            int k = probe_world(o, x, d->npc_radius, cand);
+            int k = probe_world(o, x, d->npc_radius, NULL, cand);
             for (int i = 0; i < k && nloc < MAX_LOCAL_CONTACTS; i++) {
                 Contact *c = &contacts[nc];
                 *c = cand[i];
@@ -845,6 +902,41 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
                     nc++; npair++;
                 }
         }
+    if (seesaw) {
+        const float *gm = d->npc_geom;
+        /* plank ends resting on the floor (local rows of the seesaw group) */
+        int nloc = 0;
+        for (int en = 0; en < 2; en++) {
+            real xe = gm[3] + (en == 0 ? -1 : 1) * gm[4];
+            real x[3] = {es.origin[A][0] + xe * ss_c, es.origin[A][1], es.origin[A][2] - xe * ss_s};
+            real gap = x[2] - gm[6] - d->floor_z;
+            if (gap >= d->contact_offset) continue;
+            Contact *c = &contacts[nc];
+            v3set(c->n, 0, 0, 1);
+            c->gap = gap;
+            v3set(c->pos, x[0], x[1], x[2] - gm[6] - gap * (real)0.5);
+            c->ga = A; c->la = 0; c->rba = A * MQE_NUM_BODIES; c->gb = -1; c->lb = 0; c->rbb = -1;
+            nr = add_contact_rows(o, &es, c, nc, rows, nr);
+            nc++; nloc++;
+        }
+        stats[0] += nloc;
+        /* robot probes on the plank: robot X ascending, probe table order */
+        for (int X = 0; X < A; X++)
+            for (int pi = 0; pi < md->n_probes; pi++) {
+                const float *pr = md->probes[pi];
+                int link = (int)pr[0], body = (int)pr[1];
+                real loc[3] = {pr[2], pr[3], pr[4]}, x[3], nrm[3], pos[3], gap;
+                m3mulv(x, es.rd[X].R[link], loc);
+                v3add(x, x, es.rd[X].p[link]);
+                v3add(x, x, es.origin[X]);
+                if (npair >= max_pair || !sphere_plank(d, es.origin[A], ss_c, ss_s, x, pr[5], nrm, &gap, pos)) continue;
+                Contact *c = &contacts[nc];
+                c->ga = X; c->la = link; c->rba = X * MQE_NUM_BODIES + body; c->gb = A; c->lb = 0; c->rbb = A * MQE_NUM_BODIES;
+                v3cpy(c->n, nrm); v3cpy(c->pos, pos); c->gap = gap;
+                nr = add_contact_rows(o, &es, c, nc, rows, nr);
+                nc++; npair++;
+            }
+    }
     stats[2] += npair;
     if (nr > stats[3]) stats[3] = nr;
 
@@ -865,6 +957,12 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         }
     }
 
+    if (seesaw) {
+        real lim = d->npc_geom[12], thd = es.vel[A][1];
+        thd = thd > lim ? lim : (thd < -lim ? -lim : thd);         /* URDF joint velocity limit */
+        dof[(12 * A) * 2] += dt * thd;
+        dof[(12 * A) * 2 + 1] = thd;
+    }
     /* 5. integrate (semi-implicit Euler; exponential map for orientation) */
     for (int g = 0; g < G; g++) {
         if (g >= A && d->npc_kind != MQE_NPC_RIGID) continue;

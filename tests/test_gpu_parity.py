@@ -114,7 +114,7 @@ def _state_err(a_root, a_dof, b_root, b_dof):
             np.abs(a_dof[:, 0] - b_dof[:, 0]), np.abs(a_dof[:, 1] - b_dof[:, 1]))
 
 
-@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender"])
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw"])
 def test_single_substep_parity(task):
     """Single physics substeps from IDENTICAL states, robots dropped onto the floor so foot / knee / pair contacts,
     joint limits and the actuator net are all active.  Truth = the fp64 oracle; the fp32 oracle (dense Cholesky) run
@@ -125,6 +125,21 @@ def test_single_substep_parity(task):
     eng.reset(); o32.reset(); o64.reset()
     root = o64.get(E.BUF_ROOT_STATES).reshape(sc.num_envs, -1, 13).copy()
     root[:, :sc.num_agents, 2] = 0.30 + np.linspace(0.0, 0.06, sc.num_envs)[:, None]     # some penetrating, some hovering
+    if task == "go1seesaw":       # half of the envs: robots standing on the plank (ramp from x = 3.5 to 7.5, pivot at 5.6 / 0.545)
+        n = sc.num_envs
+        dofs = o64.get(E.BUF_DOF_STATES).reshape(n, -1, 2).copy()
+        dofs[:, 24, 0] = -0.238
+        xs = np.linspace(3.7, 7.2, n)
+        for a in range(2):
+            on = np.arange(n) % 2 == 0
+            xa = xs + 0.3 * a
+            zpl = 0.545 + (xa - 5.6) * np.tan(0.238) + 0.015 / np.cos(0.238)
+            root[on, a, 0] = sc.env_origins[on, 0] + xa[on]
+            root[on, a, 1] = sc.env_origins[on, 1] + (0.25 if a else -0.25)
+            root[on, a, 2] = zpl[on] + 0.29 + 0.02 * (np.arange(n)[on] % 3)
+        for o in (o32, o64):
+            o.set(E.BUF_DOF_STATES, dofs)
+        eng.tensor(E.BUF_DOF_STATES).copy_(dev(dofs).view_as(eng.tensor(E.BUF_DOF_STATES)))
     o64.set(E.BUF_ROOT_STATES, root)
     a = np.clip(np.random.default_rng(1).normal(0, 1.0, size=(sc.num_envs * sc.num_agents * 12,)), -3, 3).astype(np.float32)
     for o in (o32, o64):
@@ -157,7 +172,9 @@ def test_single_substep_parity(task):
         print(f"{task} {name}: |gpu-f64| p50/p99/max = {pg[0]:.2e}/{pg[1]:.2e}/{pg[2]:.2e}   |f32 oracle-f64| = {pf[0]:.2e}/{pf[1]:.2e}/{pf[2]:.2e}")
         assert pg[1] <= max(3.0 * pf[1], 1e-5), (name, pg, pf)           # as accurate as the fp32 restatement
         assert pg[2] <= max(5.0 * pf[2], 1e-4), (name, pg, pf)
-    print(task, "contact-force err / max force:", cf_err, "contacts seen", total_contacts)
+    print(task, "contact-force err / max force:", cf_err, "contacts seen", total_contacts, "last stats", st_o[:4])
+    if task == "go1seesaw":
+        assert st_o[2] > 0, "no robot-on-plank contacts were exercised"
     assert cf_err < 3e-2, cf_err
     eng.close()
 
