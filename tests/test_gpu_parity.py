@@ -314,3 +314,27 @@ def test_env_surface_wrappers(task, D, A):
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     assert float(env.reward_buffer["step count"]) == 3
     env.close()
+
+
+def test_openrl_adapter_numpy_surface():
+    """openrl_ws/utils.py surface: numpy in / numpy out, 0.5 action pre-scale, dones repeated per agent, batch_rewards."""
+    from types import SimpleNamespace
+    from mqe_b200.openrl_adapter import make_env
+    args = SimpleNamespace(task="go1sheep-easy", num_envs=8, seed=0, headless=True, record_video=False, sim_device="cuda:0")
+    env, cfg = make_env(args)
+    assert env.agent_num == 2 and env.parallel_env_num == 8
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (8, 2, 18)
+    for _ in range(3):
+        obs, rew, done, infos = env.step(np.random.uniform(-1, 1, size=(8, 2, 3)).astype(np.float32))
+    assert obs.shape == (8, 2, 18) and rew.shape == (8, 2, 1) and done.shape == (8, 2) and done.dtype == bool and len(infos) == 8
+    r = env.batch_rewards(None)
+    assert "average step reward" in r and float(env.env.reward_buffer["step count"]) == 0
+    env.close()
+    args.task = "go1seesaw"
+    env, cfg = make_env(args, single_agent=True)
+    obs = env.reset()
+    assert obs.shape == (16, 1, 14)
+    obs, rew, done, infos = env.step(np.zeros((16, 1, 3), dtype=np.float32))
+    assert obs.shape == (16, 1, 14) and rew.shape == (16, 1, 1) and done.shape == (16, 1)
+    env.close()
