@@ -1012,8 +1012,10 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     row[20] = lam;
                     vb[0] += r2.y * dl; vb[1] += r2.z * dl; vb[2] += r2.w * dl; vb[3] += r3.x * dl; vb[4] += r3.y * dl; vb[5] += r3.z * dl;
 #pragma unroll
-                    for (int L = 0; L < 4; L++)
-                        if (rleg == L) { ua[L][0] += r3.w * dl; ua[L][1] += r4.x * dl; ua[L][2] += r4.y * dl; }
+                    for (int L = 0; L < 4; L++) {                       // branch-free: only the row's leg sees a non-zero dl
+                        const float dlL = rleg == L ? dl : 0.f;
+                        ua[L][0] = fmaf(r3.w, dlL, ua[L][0]); ua[L][1] = fmaf(r4.x, dlL, ua[L][1]); ua[L][2] = fmaf(r4.y, dlL, ua[L][2]);
+                    }
                 }
                 if (npair > 0) {   // uniform over the env's lanes
 #pragma unroll
