@@ -170,7 +170,9 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     {
         std::vector<float> aw(1316, 0.f);
         memcpy(aw.data(), w.act_w0, 192 * 4); memcpy(aw.data() + 192, w.act_b0, 32 * 4);
-        memcpy(aw.data() + 224, w.act_w1, 1024 * 4); memcpy(aw.data() + 1248, w.act_b1, 32 * 4);
+        for (int o = 0; o < 32; o++)                                   // W1 transposed: [in][out], see k_substeps P1
+            for (int i = 0; i < 32; i++) aw[224 + i * 32 + o] = w.act_w1[o * 32 + i];
+        memcpy(aw.data() + 1248, w.act_b1, 32 * 4);
         memcpy(aw.data() + 1280, w.act_w2, 32 * 4); aw[1312] = w.act_b2[0];
         CK(dupload(s, &p.act_w, aw.data(), aw.size()));
         // layer 0 of both networks, age-blocked and padded: [768][30][80]

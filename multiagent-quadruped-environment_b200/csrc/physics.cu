@@ -165,6 +165,16 @@ __device__ __forceinline__ void sym3_mulv(const float *H, const float *x, float 
     y[2] = H[2] * x[0] + H[4] * x[1] + H[5] * x[2];
 }
 
+// packed fp32 pairs for FFMA2 (fma.rn.f32x2, sm_100+): two independent round-to-nearest fp32 FMAs per instruction
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ void tangent_basis(V3 n, V3 &t1, V3 &t2) {
     V3 e = fabsf(n.x) < 0.9f ? mk(1.f, 0.f, 0.f) : mk(0.f, 1.f, 0.f);
     t1 = cross(n, e);
@@ -425,7 +435,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         const bool last = (sub == nsub - 1);
         // ================================================================ P1: actuator network (go1.py:315-354, 369-380)
         if (active && is_robot) {
-            float x[3][6], h1[3][32];
+            float x[3][6];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 int j = 3 * leg + k;
@@ -435,28 +445,45 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 x[k][0] = err; x[k][1] = e1[k]; x[k][2] = e2[k]; x[k][3] = qd[k]; x[k][4] = v1[k]; x[k][5] = v2[k];
                 e2[k] = e1[k]; e1[k] = err; v2[k] = v1[k]; v1[k] = qd[k];
             }
-            const float *W0 = actw, *b0 = actw + 192, *W1 = actw + 224, *b1 = actw + 1248, *W2 = actw + 1280;
+            // Rank-1 formulation: for every hidden unit i of layer 1, h_i (3 joints) updates all 32 layer-2 pre-activations at
+            // once.  96 independent accumulators instead of 3 dependent chains (the kernel is latency-bound), a 32-trip loop
+            // whose body stays in the instruction cache, and packed FFMA2 (two fp32 FMAs per instruction on sm_100).
+            // Packed weights: W0[32][6] b0[32] W1T[32 in][32 out] b1[32] W2[32] b2.
+            const float *W0 = actw, *b0 = actw + 192, *W1T = actw + 224, *b1 = actw + 1248, *W2 = actw + 1280;
+            unsigned long long acc[3][16];
 #pragma unroll
-            for (int o = 0; o < 32; o++) {
-                float w0 = W0[o * 6], w1 = W0[o * 6 + 1], w2 = W0[o * 6 + 2], w3 = W0[o * 6 + 3], w4 = W0[o * 6 + 4], w5 = W0[o * 6 + 5], b = b0[o];
+            for (int o2 = 0; o2 < 16; o2++) {
+                const unsigned long long bb = pack2(b1[2 * o2], b1[2 * o2 + 1]);
+                acc[0][o2] = bb; acc[1][o2] = bb; acc[2][o2] = bb;
+            }
+#pragma unroll 2
+            for (int i = 0; i < 32; i++) {
+                const float w0 = W0[i * 6], w1 = W0[i * 6 + 1], w2 = W0[i * 6 + 2], w3 = W0[i * 6 + 3], w4 = W0[i * 6 + 4], w5 = W0[i * 6 + 5], b = b0[i];
+                unsigned long long hh[3];
 #pragma unroll
-                for (int k = 0; k < 3; k++)
-                    h1[k][o] = softsign(b + w0 * x[k][0] + w1 * x[k][1] + w2 * x[k][2] + w3 * x[k][3] + w4 * x[k][4] + w5 * x[k][5]);
+                for (int k = 0; k < 3; k++) {
+                    const float h = softsign(b + w0 * x[k][0] + w1 * x[k][1] + w2 * x[k][2] + w3 * x[k][3] + w4 * x[k][4] + w5 * x[k][5]);
+                    hh[k] = pack2(h, h);
+                }
+                const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(W1T + i * 32);
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const ulonglong2 w = wr[g];                      // (W1[4g][i], W1[4g+1][i]), (W1[4g+2][i], W1[4g+3][i])
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { ffma2(acc[k][2 * g], w.x, hh[k]); ffma2(acc[k][2 * g + 1], w.y, hh[k]); }
+                }
             }
             float out[3] = {actw[1312], actw[1312], actw[1312]};
-#pragma unroll 4
-            for (int o = 0; o < 32; o++) {
-                float s0 = b1[o], s1 = s0, s2 = s0;
-                const float4 *wr = reinterpret_cast<const float4 *>(W1 + o * 32);
 #pragma unroll
-                for (int kk = 0; kk < 8; kk++) {
-                    float4 w = wr[kk];
-                    s0 += w.x * h1[0][4 * kk] + w.y * h1[0][4 * kk + 1] + w.z * h1[0][4 * kk + 2] + w.w * h1[0][4 * kk + 3];
-                    s1 += w.x * h1[1][4 * kk] + w.y * h1[1][4 * kk + 1] + w.z * h1[1][4 * kk + 2] + w.w * h1[1][4 * kk + 3];
-                    s2 += w.x * h1[2][4 * kk] + w.y * h1[2][4 * kk + 1] + w.z * h1[2][4 * kk + 2] + w.w * h1[2][4 * kk + 3];
+            for (int o2 = 0; o2 < 16; o2++) {
+                const float wa = W2[2 * o2], wb = W2[2 * o2 + 1];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    float lo, hi;
+                    unpack2(acc[k][o2], lo, hi);
+                    out[k] = fmaf(wa, softsign(lo), out[k]);
+                    out[k] = fmaf(wb, softsign(hi), out[k]);
                 }
-                float w2o = W2[o];
-                out[0] += w2o * softsign(s0); out[1] += w2o * softsign(s1); out[2] += w2o * softsign(s2);
             }
 #pragma unroll
             for (int k = 0; k < 3; k++) {
@@ -1192,7 +1219,7 @@ __global__ void k_actuator(const float *__restrict__ aw, const float *__restrict
     float y = w[1312];
     for (int o = 0; o < 32; o++) {
         float s = w[1248 + o];
-        for (int i = 0; i < 32; i++) s += w[224 + o * 32 + i] * h0[i];
+        for (int i = 0; i < 32; i++) s += w[224 + i * 32 + o] * h0[i];      // W1 is stored transposed ([in][out])
         y += w[1280 + o] * softsign(s);
     }
     out[r] = y;
