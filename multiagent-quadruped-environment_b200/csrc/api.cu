@@ -364,14 +364,15 @@ int mqe_sim_policy(MqeSim *s, const float *d_actions) {
     return MQE_OK;
 }
 
-int mqe_sim_substeps(MqeSim *s, int count) {
+static int substeps_impl(MqeSim *s, int count, bool zero_stats) {
     if (!s || count <= 0) return fail(MQE_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(s->device));
-    CK(cudaMemsetAsync(s->p.stats, 0, 8 * sizeof(int), s->stream));
+    if (zero_stats) CK(cudaMemsetAsync(s->p.stats, 0, 8 * sizeof(int), s->stream));   // inside mqe_sim_step k_policy_finish did it
     CK(mqe_launch_substeps(s->p, count, s->maxpair, s->pair_table, s->n_pair, s->stream));
     s->launches += 1;
     return MQE_OK;
 }
+int mqe_sim_substeps(MqeSim *s, int count) { return substeps_impl(s, count, true); }
 
 int mqe_sim_post_physics(MqeSim *s) {
     if (!s) return fail(MQE_ERR_INVALID, "null handle");
@@ -385,7 +386,7 @@ int mqe_sim_post_physics(MqeSim *s) {
 int mqe_sim_step(MqeSim *s, const float *d_actions) {
     int rc = mqe_sim_policy(s, d_actions);
     if (rc != MQE_OK) return rc;
-    rc = mqe_sim_substeps(s, s->p.decimation);
+    rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: keeps the programmatic launch chain intact
     if (rc != MQE_OK) return rc;
     return mqe_sim_post_physics(s);
 }

@@ -3,6 +3,7 @@
 // /root/reference (ziyanx02/multiagent-quadruped-environment).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "../../include/mqe_b200.h"
@@ -54,6 +55,41 @@ struct DevParams {
     float *hist_f32;              // [M][30][80] fp32 ring: slot s holds one padded 70-float frame
     unsigned short *hist_hi, *hist_lo;  // bf16 split ring, blocked layout (tensor-core modes)
 };
+
+// ---------------------------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the step is launched with programmatic stream serialization: it may be scheduled while its predecessor
+// is still running and does its own set-up (barrier init, TMEM allocation, constant staging) in that shadow; pdl_wait()
+// blocks until the predecessor grid has completed and its writes are visible, so it must precede the first access to
+// anything another kernel of the step produces or consumes.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifdef __CUDACC__
+// MQE_PDL = 0: plain stream order everywhere; 1 (default): only the short policy-tail kernels overlap their set-up with
+// the predecessor (measured: letting the 211 KB-per-CTA substep grid or the 384-CTA layer-0 grid become resident early costs
+// more than the launch gaps it hides); 2: every kernel of the step.
+static inline int mqe_pdl_level() {
+    static const int level = [] { const char *e = getenv("MQE_PDL"); return e ? atoi(e) : 1; }();
+    return level;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_if(bool allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = allow ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>      // short kernels of the policy tail
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    return launch_pdl_if(mqe_pdl_level() >= 1, kernel, grid, block, smem, st, args...);
+}
+template <typename... KArgs, typename... Args>      // heavy grids: frame, layer 0, substeps, post
+static inline cudaError_t launch_heavy(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    return launch_pdl_if(mqe_pdl_level() >= 2, kernel, grid, block, smem, st, args...);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------- vec3
 struct V3 { float x, y, z; };

@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
+    pdl_launch_dependents();
     // ---- CTA header: robot model + actuator weights ----
     MqeRobotModel *md = reinterpret_cast<MqeRobotModel *>(smem);
     float *actw = smem + sizeof(MqeRobotModel) / 4;
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         tbl[40 + lg * 10] = n;
     }
     __syncthreads();
-    const int A = p.A, P = p.Pd, E = p.E, G = A + P;   // P: dynamic NPCs only (a seesaw is not a free body)
+    pdl_wait();                                         // constants above were staged in the predecessor's shadow
+    const int A = p.A, P = p.Pd, E = p.E, G = A + P;   // P: NPCs that own a lane
     const int GA = p.G;                                 // actors per env in the root-state tensor
     const bool seesaw = p.npc_kind == MQE_NPC_SEESAW;   // the NPC lane is a 1-DOF plank on a fixed base (seesaw.urdf)
     const int Gc = seesaw ? A : G;                      // groups that take part in the capsule / capsule phase
@@ -1252,6 +1254,5 @@ extern "C" cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int max
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    k_substeps<<<grid, warps_per_cta * 32, smem, st>>>(p, nsub, maxpair, pair_table, n_pair_entries);
-    return cudaGetLastError();
+    return launch_heavy(k_substeps, dim3(grid), dim3(warps_per_cta * 32), smem, st, p, nsub, maxpair, pair_table, n_pair_entries);
 }

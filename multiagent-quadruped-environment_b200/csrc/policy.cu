@@ -43,6 +43,8 @@ __device__ void dev_defender_command(const DevParams &p, int e, float *cmd) {
 // One warp per agent row: wrapper scaling + clip (wrappers/*.py step(), go1.py:38), command -> frame, ring append.
 // d_actions: [N][A_ctrl][3].  Also maintains the bf16 hi/lo ring when p.hist_hi != nullptr.
 __global__ void __launch_bounds__(256) k_policy_frame(DevParams p, const float *__restrict__ d_actions, int head) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int M = p.N * p.A;
     if (m >= M) return;
@@ -105,6 +107,8 @@ __global__ void __launch_bounds__(256) k_policy_frame(DevParams p, const float *
 
 // after the network: last_locomotion_action(s) shift, clip to +-clip_actions (go1.py:40-41, 104-106)
 __global__ void k_policy_finish(DevParams p, const float *__restrict__ act) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int M = p.N * p.A;
     if (t < M * 12) {
@@ -114,6 +118,7 @@ __global__ void k_policy_finish(DevParams p, const float *__restrict__ act) {
         p.actions[t] = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);
     }
     if (t < p.N) p.hist_dirty[t] = 0;
+    if (t < 8) p.stats[t] = 0;                               // contact statistics of the step that follows (k_substeps accumulates)
 }
 
 // ---------------------------------------------------------------------------------------------- fp32 SGEMM chain
@@ -221,13 +226,11 @@ extern "C" cudaError_t mqe_launch_policy_tail(const PolicyWeightsDev &w, const P
 }
 extern "C" cudaError_t mqe_launch_policy_frame(const DevParams &p, const float *d_actions, int head, cudaStream_t st) {
     const int M = p.N * p.A;
-    k_policy_frame<<<(M * 32 + 255) / 256, 256, 0, st>>>(p, d_actions, head);
-    return cudaGetLastError();
+    return launch_heavy(k_policy_frame, dim3((M * 32 + 255) / 256), dim3(256), 0, st, p, d_actions, head);
 }
 extern "C" cudaError_t mqe_launch_policy_finish(const DevParams &p, const float *act, cudaStream_t st) {
     const int M = p.N * p.A, n = M * 12 > p.N ? M * 12 : p.N;
-    k_policy_finish<<<(n + 255) / 256, 256, 0, st>>>(p, act);
-    return cudaGetLastError();
+    return launch_pdl(k_policy_finish, dim3((n + 255) / 256), dim3(256), 0, st, p, act);
 }
 extern "C" cudaError_t mqe_launch_history_to_ring(const float *hist, float *ring, unsigned short *hi, unsigned short *lo, int rows, cudaStream_t st) {
     size_t n = (size_t)rows * RING_ROW;

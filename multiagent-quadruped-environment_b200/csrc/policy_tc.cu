@@ -96,6 +96,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntile = blockIdx.x, mtile = blockIdx.y;
+    pdl_launch_dependents();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -110,6 +111,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                              // set-up above ran in the predecessor's shadow
     const uint32_t stage_tx = passes == 3 ? TC_STAGE_BYTES : 2 * TC_TILE_BYTES;
 
     if (warp == 0) {
@@ -241,6 +243,7 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntile = blockIdx.x, mtile = blockIdx.y;
+    pdl_launch_dependents();
     const int nk = K / LT_BK;
 
     if (threadIdx.x == 0) {
@@ -256,6 +259,7 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                              // set-up above ran in the predecessor's shadow
 
     if (warp == 0) {
         if (lane == 0) {
@@ -351,6 +355,8 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
 // One thread per (row, 8-column chunk); consecutive threads take consecutive rows so plane stores coalesce.
 __global__ void k_body_latent_planes(const float *__restrict__ Z, const float *__restrict__ latent, const float *__restrict__ wlat,
                                      unsigned short *__restrict__ o_hi, unsigned short *__restrict__ o_lo, int M, int Mpad) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Mpad * 64) return;
     const int chunk = t / Mpad, m = t % Mpad;          // 64 chunks of 8 columns
@@ -462,10 +468,9 @@ extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const f
                                                const unsigned short *hist_lo, int head, int rows, int passes, float *Z, int planes_out,
                                                cudaStream_t st) {
     dim3 grid(6, (rows + 127) / 128);
-    k_policy_l0_tc<<<grid, 192, TC_SMEM_BYTES, st>>>(hist_hi, hist_lo, (const unsigned short *)w.l0_hi, (const unsigned short *)w.l0_lo,
-                                                      b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : nullptr,
-                                                      planes_out ? (unsigned short *)w.p_lo[0] : nullptr, rows, head, passes);
-    return cudaGetLastError();
+    return launch_heavy(k_policy_l0_tc, grid, dim3(192), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+                      (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
+                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes);
 }
 
 // layers 1.. on the tensor cores: operands are bf16 hi/lo planes end to end (needs layer 0 launched with planes_out = 1)
@@ -476,12 +481,15 @@ extern "C" cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const
     auto L = [&](int i) { return (const unsigned short *)w.t_lo[i]; };
     auto PH = [&](int i) { return (unsigned short *)w.p_hi[i]; };
     auto PL = [&](int i) { return (unsigned short *)w.p_lo[i]; };
-    k_linear_tc<128><<<dim3(1, mt), 192, lt_smem_bytes(128), st>>>(PH(0), PL(0), 256, H(0), L(0), pw.ab1, nullptr, 0, 128, PH(1), PL(1), 16, M, 1, passes);
-    k_linear_tc<16><<<dim3(1, mt), 192, lt_smem_bytes(16), st>>>(PH(1), PL(1), 128, H(1), L(1), pw.ab2, s.latent, 2, 2, nullptr, nullptr, 0, M, 0, passes);
-    k_body_latent_planes<<<(mpad * 64 + 255) / 256, 256, 0, st>>>(s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad);
-    k_linear_tc<128><<<dim3(2, mt), 192, lt_smem_bytes(128), st>>>(PH(2), PL(2), 512, H(2), L(2), pw.bb1, nullptr, 0, 256, PH(3), PL(3), 32, M, 1, passes);
-    k_linear_tc<128><<<dim3(1, mt), 192, lt_smem_bytes(128), st>>>(PH(3), PL(3), 256, H(3), L(3), pw.bb2, nullptr, 0, 128, PH(4), PL(4), 16, M, 1, passes);
-    k_linear_tc<16><<<dim3(1, mt), 192, lt_smem_bytes(16), st>>>(PH(4), PL(4), 128, H(4), L(4), pw.bb3, s.act, 12, 12, nullptr, nullptr, 0, M, 0, passes);
+    float *const nof = nullptr;
+    unsigned short *const nou = nullptr;
+    cudaError_t e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(192), lt_smem_bytes(128), st, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, PH(1), PL(1), 16, M, 1, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(192), lt_smem_bytes(16), st, PH(1), PL(1), 128, H(1), L(1), pw.ab2, s.latent, 2, 2, nou, nou, 0, M, 0, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(192), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(192), lt_smem_bytes(128), st, PH(3), PL(3), 256, H(3), L(3), pw.bb2, nof, 0, 128, PH(4), PL(4), 16, M, 1, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(192), lt_smem_bytes(16), st, PH(4), PL(4), 128, H(4), L(4), pw.bb3, s.act, 12, 12, nou, nou, 0, M, 0, passes)) != cudaSuccess) return e;
     *launches += 6;
     return cudaGetLastError();
 }

@@ -136,6 +136,8 @@ __device__ void dev_sheep_step(const DevParams &p, int e, uint32_t step_count) {
 }
 
 __global__ void __launch_bounds__(128) k_post_physics(DevParams p, unsigned int step_count) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.N) return;
     const int A = p.A, P = p.P, G = p.G;
@@ -221,8 +223,7 @@ __global__ void k_set_dof_indexed(DevParams p, const float *__restrict__ src, co
 }
 
 extern "C" cudaError_t mqe_launch_post(const DevParams &p, unsigned int step_count, cudaStream_t st) {
-    k_post_physics<<<(p.N + 127) / 128, 128, 0, st>>>(p, step_count);
-    return cudaGetLastError();
+    return launch_heavy(k_post_physics, dim3((p.N + 127) / 128), dim3(128), 0, st, p, step_count);
 }
 extern "C" cudaError_t mqe_launch_reset_all(const DevParams &p, cudaStream_t st) {
     k_reset_all<<<(p.N + 127) / 128, 128, 0, st>>>(p);
