@@ -64,7 +64,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ float elu1_tc(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(alpha = 1) without the ~30-instruction expm1f: degree-7 Taylor for -0.25 < x <= 0 (|err| < 2e-8 relative),
+// ex2.approx-based exp(x) - 1 below that (result magnitude >= 0.22, so the absolute 1e-7 is <= 5e-7 relative).
+__device__ __forceinline__ float elu1_tc(float x) {
+    const float t = fminf(x, 0.f);
+    float pz = fmaf(t, 1.f / 5040.f, 1.f / 720.f);
+    pz = fmaf(pz, t, 1.f / 120.f); pz = fmaf(pz, t, 1.f / 24.f); pz = fmaf(pz, t, 1.f / 6.f); pz = fmaf(pz, t, 0.5f); pz = fmaf(pz, t, 1.f);
+    const float small = pz * t, big = __expf(t) - 1.f;
+    const float neg = t > -0.25f ? small : big;
+    return x > 0.f ? x : neg;
+}
 __device__ __forceinline__ void split_bf16x8(const float *v, uint4 &hi, uint4 &lo) {
     uint32_t h[8], l[8];
 #pragma unroll
@@ -84,7 +93,7 @@ __device__ __forceinline__ size_t plane_index(int m, int k, int kchunks) {
 }
 
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo,
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
                const float *__restrict__ b0cat, float *__restrict__ Z, unsigned short *__restrict__ a0_hi,
@@ -162,9 +171,10 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
         mbar_wait(accum, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;             // two epilogue warps per quarter, two 32-column chunks each
         const int row = mtile * 128 + q * 32 + lane;
 #pragma unroll 1
-        for (int c = 0; c < 4; c++) {
+        for (int c = 2 * half; c < 2 * half + 2; c++) {
             uint32_t v[32];
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
             asm volatile(
@@ -226,8 +236,9 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
 __host__ __device__ constexpr int lt_stage_bytes(int ncta) { return 2 * LT_A_PLANE + 2 * ncta * LT_BK * 2; }
 __host__ __device__ constexpr int lt_smem_bytes(int ncta) { return LT_STAGES * lt_stage_bytes(ncta) + 128; }
 
+#define LT_THREADS 320                                       // producer warp, MMA warp, 8 epilogue warps
 template <int NCTA>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(LT_THREADS, 1)
 k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo, int K,
             const unsigned short *__restrict__ w_hi, const unsigned short *__restrict__ w_lo, const float *__restrict__ bias,
             float *__restrict__ Y, int ldy, int n_valid,                       // fp32 output (heads) when Y != nullptr
@@ -241,10 +252,12 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
     uint64_t *empty = full + LT_STAGES;
     uint64_t *accum = empty + LT_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
+    __shared__ float s_bias[NCTA];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntile = blockIdx.x, mtile = blockIdx.y;
     pdl_launch_dependents();
     const int nk = K / LT_BK;
+    for (int i = threadIdx.x; i < NCTA; i += blockDim.x) s_bias[i] = (ntile * NCTA + i < n_valid) ? bias[ntile * NCTA + i] : 0.f;   // constants
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < LT_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -308,10 +321,12 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
     } else {
         mbar_wait(accum, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;
+        const int q = warp & 3;                              // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                    // the two epilogue warps of a quarter split the columns
         const int orow = mtile * 128 + q * 32 + lane;
+        constexpr int NCH = NCTA / 16, CH0 = (NCH + 1) / 2;
 #pragma unroll 1
-        for (int c = 0; c < NCTA / 16; c++) {
+        for (int c = half ? CH0 : 0; c < (half ? NCH : CH0); c++) {
             uint32_t v[16];
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
             asm volatile(
@@ -324,7 +339,7 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                float t = __uint_as_float(v[i]) + ((n0 + i < n_valid) ? __ldg(bias + n0 + i) : 0.f);
+                float t = __uint_as_float(v[i]) + s_bias[c * 16 + i];
                 f[i] = elu ? elu1_tc(t) : t;
             }
             if (Y) {
@@ -468,7 +483,7 @@ extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const f
                                                const unsigned short *hist_lo, int head, int rows, int passes, float *Z, int planes_out,
                                                cudaStream_t st) {
     dim3 grid(6, (rows + 127) / 128);
-    return launch_heavy(k_policy_l0_tc, grid, dim3(192), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+    return launch_heavy(k_policy_l0_tc, grid, dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                       (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
                       planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes);
 }
@@ -484,12 +499,12 @@ extern "C" cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const
     float *const nof = nullptr;
     unsigned short *const nou = nullptr;
     cudaError_t e;
-    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(192), lt_smem_bytes(128), st, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, PH(1), PL(1), 16, M, 1, passes)) != cudaSuccess) return e;
-    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(192), lt_smem_bytes(16), st, PH(1), PL(1), 128, H(1), L(1), pw.ab2, s.latent, 2, 2, nou, nou, 0, M, 0, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, PH(1), PL(1), 16, M, 1, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(16), st, PH(1), PL(1), 128, H(1), L(1), pw.ab2, s.latent, 2, 2, nou, nou, 0, M, 0, passes)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
-    if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(192), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes)) != cudaSuccess) return e;
-    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(192), lt_smem_bytes(128), st, PH(3), PL(3), 256, H(3), L(3), pw.bb2, nof, 0, 128, PH(4), PL(4), 16, M, 1, passes)) != cudaSuccess) return e;
-    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(192), lt_smem_bytes(16), st, PH(4), PL(4), 128, H(4), L(4), pw.bb3, s.act, 12, 12, nou, nou, 0, M, 0, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(3), PL(3), 256, H(3), L(3), pw.bb2, nof, 0, 128, PH(4), PL(4), 16, M, 1, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(16), st, PH(4), PL(4), 128, H(4), L(4), pw.bb3, s.act, 12, 12, nou, nou, 0, M, 0, passes)) != cudaSuccess) return e;
     *launches += 6;
     return cudaGetLastError();
 }
