@@ -54,34 +54,35 @@ __device__ void dev_env_reset(const DevParams &p, int e) {
     p.episode[e] = ep + 1;
 }
 
-// compute_observations for one env (go1.py:153-196)
-__device__ void dev_env_observations(const DevParams &p, int e) {
+// compute_observations for one agent (go1.py:153-196)
+__device__ void dev_agent_observations(const DevParams &p, int e, int a) {
     const int A = p.A, G = p.G;
-    for (int a = 0; a < A; a++) {
-        const int m = e * A + a;
-        float *ob = p.obs + (size_t)m * MQE_OBS_FLOATS;
-        const float *rs = p.root + ((size_t)e * G + a) * 13;
-        const float *dof = p.dof + ((size_t)e * (12 * A + p.D) + 12 * a) * 2;
-        const float *bq = p.quat_alias ? rs + 3 : p.base_quat + m * 4;
-        float q4[4] = {bq[0], bq[1], bq[2], bq[3]};
-        for (int i = 0; i < 3; i++) ob[MQE_OBS_BASE_POS + i] = rs[i] - p.env_origins[e * 3 + i];
-        for (int i = 0; i < 4; i++) ob[MQE_OBS_BASE_QUAT + i] = q4[i];
-        for (int j = 0; j < 12; j++) {
-            ob[MQE_OBS_DOF_POS + j] = dof[j * 2] - p.model->q_default[j];
-            ob[MQE_OBS_DOF_VEL + j] = dof[j * 2 + 1] * 0.05f;
-            ob[MQE_OBS_LAST_ACTION + j] = p.actions[m * 12 + j];
-            ob[MQE_OBS_LAST_LAST_ACTION + j] = p.last_actions[m * 12 + j];
-        }
-        for (int i = 0; i < 3; i++) {
-            ob[MQE_OBS_LIN_VEL + i] = p.base_lin_vel[m * 3 + i] * 2.0f;
-            ob[MQE_OBS_ANG_VEL + i] = p.base_ang_vel[m * 3 + i] * 0.25f;
-            ob[MQE_OBS_PROJ_GRAVITY + i] = p.proj_grav[m * 3 + i];
-        }
-        for (int i = 0; i < 4; i++) ob[MQE_OBS_CLOCK + i] = p.clock[m * 4 + i];
-        float rpy[3];
-        get_euler_xyz(q4, rpy);
-        for (int i = 0; i < 3; i++) ob[MQE_OBS_BASE_RPY + i] = rpy[i];
+    const int m = e * A + a;
+    float *ob = p.obs + (size_t)m * MQE_OBS_FLOATS;
+    const float *rs = p.root + ((size_t)e * G + a) * 13;
+    const float *dof = p.dof + ((size_t)e * (12 * A + p.D) + 12 * a) * 2;
+    const float *bq = p.quat_alias ? rs + 3 : p.base_quat + m * 4;
+    float q4[4] = {bq[0], bq[1], bq[2], bq[3]};
+    for (int i = 0; i < 3; i++) ob[MQE_OBS_BASE_POS + i] = rs[i] - p.env_origins[e * 3 + i];
+    for (int i = 0; i < 4; i++) ob[MQE_OBS_BASE_QUAT + i] = q4[i];
+    for (int j = 0; j < 12; j++) {
+        ob[MQE_OBS_DOF_POS + j] = dof[j * 2] - p.model->q_default[j];
+        ob[MQE_OBS_DOF_VEL + j] = dof[j * 2 + 1] * 0.05f;
+        ob[MQE_OBS_LAST_ACTION + j] = p.actions[m * 12 + j];
+        ob[MQE_OBS_LAST_LAST_ACTION + j] = p.last_actions[m * 12 + j];
     }
+    for (int i = 0; i < 3; i++) {
+        ob[MQE_OBS_LIN_VEL + i] = p.base_lin_vel[m * 3 + i] * 2.0f;
+        ob[MQE_OBS_ANG_VEL + i] = p.base_ang_vel[m * 3 + i] * 0.25f;
+        ob[MQE_OBS_PROJ_GRAVITY + i] = p.proj_grav[m * 3 + i];
+    }
+    for (int i = 0; i < 4; i++) ob[MQE_OBS_CLOCK + i] = p.clock[m * 4 + i];
+    float rpy[3];
+    get_euler_xyz(q4, rpy);
+    for (int i = 0; i < 3; i++) ob[MQE_OBS_BASE_RPY + i] = rpy[i];
+}
+__device__ void dev_env_observations(const DevParams &p, int e) {
+    for (int a = 0; a < p.A; a++) dev_agent_observations(p, e, a);
 }
 
 // _step_contact_targets (go1.py:240-279)
@@ -135,18 +136,24 @@ __device__ void dev_sheep_step(const DevParams &p, int e, uint32_t step_count) {
     }
 }
 
-__global__ void __launch_bounds__(128) k_post_physics(DevParams p, unsigned int step_count) {
+// One thread per (env, agent); a block handles 128 / A whole envs.  Per-agent work (base-frame velocities, gait clock,
+// termination tests, observation row) runs in parallel, the env-level decisions (time-out, reset, NPC step) on the
+// env's first agent thread between two block barriers.
+#define POST_THREADS 128
+__global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsigned int step_count) {
     pdl_launch_dependents();
     pdl_wait();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= p.N) return;
+    __shared__ int s_flags[POST_THREADS];
     const int A = p.A, P = p.P, G = p.G;
+    const int envs_per_block = POST_THREADS / A;
+    const int el = threadIdx.x / A, a = threadIdx.x % A;
+    const int e = blockIdx.x * envs_per_block + el;
+    const bool live = el < envs_per_block && e < p.N;
     const float PI = 3.14159265358979323846f;
     const float dt_policy = p.dt * (float)p.decimation;
-    long long ep = p.ep_len[e] + 1;
-    p.ep_len[e] = ep;
-    int collide = 0, rt = 0, pt = 0, zl = 0, zh = 0;
-    for (int a = 0; a < A; a++) {
+    s_flags[threadIdx.x] = 0;
+    __syncthreads();
+    if (live) {
         const int m = e * A + a;
         const float *rs = p.root + ((size_t)e * G + a) * 13;
         float q4[4] = {rs[3], rs[4], rs[5], rs[6]};
@@ -158,33 +165,42 @@ __global__ void __launch_bounds__(128) k_post_physics(DevParams p, unsigned int 
         p.base_ang_vel[m * 3] = av.x; p.base_ang_vel[m * 3 + 1] = av.y; p.base_ang_vel[m * 3 + 2] = av.z;
         p.proj_grav[m * 3] = pg.x; p.proj_grav[m * 3 + 1] = pg.y; p.proj_grav[m * 3 + 2] = pg.z;
         dev_gait_clock(p, m, dt_policy);
+        int f = 0;
         const float *cf = p.contact + ((size_t)e * p.NB + a * MQE_NUM_BODIES) * 3;          // body 0 = base
-        if (sqrtf(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]) > 1.f) collide = 1;
+        if (sqrtf(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]) > 1.f) f |= 16;
         float rpy[3];
         get_euler_xyz(q4, rpy);
         if (rpy[0] > PI) rpy[0] -= 2.f * PI;
         if (rpy[1] > PI) rpy[1] -= 2.f * PI;
         float z = rs[2] - p.agent_origins[m * 3 + 2];
-        if (fabsf(rpy[0]) > p.term_roll) rt = 1;
-        if (fabsf(rpy[1]) > p.term_pitch) pt = 1;
-        if (z < p.term_zlow) zl = 1;
-        if (z > p.term_zhigh) zh = 1;
+        if (fabsf(rpy[0]) > p.term_roll) f |= 1;
+        if (fabsf(rpy[1]) > p.term_pitch) f |= 2;
+        if (z < p.term_zlow) f |= 4;
+        if (z > p.term_zhigh) f |= 8;
+        if (f) atomicOr(&s_flags[el], f);
     }
-    int reset = 0;
-    if (p.term_mask & 16) { p.collide_buf[e] = (unsigned char)collide; reset |= collide; }
-    int to = ep > (long long)p.max_ep_len;
-    p.timeout_buf[e] = (unsigned char)to;
-    reset |= to;
-    if (p.term_mask & 1) { p.r_term[e] = (unsigned char)rt; reset |= rt; }
-    if (p.term_mask & 2) { p.p_term[e] = (unsigned char)pt; reset |= pt; }
-    if (p.term_mask & 4) { p.zl_term[e] = (unsigned char)zl; reset |= zl; }
-    if (p.term_mask & 8) { p.zh_term[e] = (unsigned char)zh; reset |= zh; }
-    p.reset_buf[e] = (unsigned char)reset;
-    if (P && p.npc_ctrl == MQE_NPC_SHEEP) dev_sheep_step(p, e, step_count);
-    if (reset) dev_env_reset(p, e);
-    dev_env_observations(p, e);
-    for (int a = 0; a < A; a++) {
+    __syncthreads();
+    if (live && a == 0) {
+        const int f = s_flags[el];
+        long long ep = p.ep_len[e] + 1;
+        p.ep_len[e] = ep;
+        int reset = 0;
+        if (p.term_mask & 16) { p.collide_buf[e] = (unsigned char)((f >> 4) & 1); reset |= (f >> 4) & 1; }
+        int to = ep > (long long)p.max_ep_len;
+        p.timeout_buf[e] = (unsigned char)to;
+        reset |= to;
+        if (p.term_mask & 1) { p.r_term[e] = (unsigned char)(f & 1); reset |= f & 1; }
+        if (p.term_mask & 2) { p.p_term[e] = (unsigned char)((f >> 1) & 1); reset |= (f >> 1) & 1; }
+        if (p.term_mask & 4) { p.zl_term[e] = (unsigned char)((f >> 2) & 1); reset |= (f >> 2) & 1; }
+        if (p.term_mask & 8) { p.zh_term[e] = (unsigned char)((f >> 3) & 1); reset |= (f >> 3) & 1; }
+        p.reset_buf[e] = (unsigned char)reset;
+        if (P && p.npc_ctrl == MQE_NPC_SHEEP) dev_sheep_step(p, e, step_count);
+        if (reset) dev_env_reset(p, e);
+    }
+    __syncthreads();                                     // reset wrote state / last_actions of every agent of the env
+    if (live) {
         const int m = e * A + a;
+        dev_agent_observations(p, e, a);
         const float *rs = p.root + ((size_t)e * G + a) * 13;
         const float *dof = p.dof + ((size_t)e * (12 * A + p.D) + 12 * a) * 2;
         for (int j = 0; j < 12; j++) { p.last_actions[m * 12 + j] = p.actions[m * 12 + j]; p.last_dof_vel[m * 12 + j] = dof[j * 2 + 1]; }
@@ -223,7 +239,8 @@ __global__ void k_set_dof_indexed(DevParams p, const float *__restrict__ src, co
 }
 
 extern "C" cudaError_t mqe_launch_post(const DevParams &p, unsigned int step_count, cudaStream_t st) {
-    return launch_heavy(k_post_physics, dim3((p.N + 127) / 128), dim3(128), 0, st, p, step_count);
+    const int envs_per_block = POST_THREADS / p.A;
+    return launch_heavy(k_post_physics, dim3((p.N + envs_per_block - 1) / envs_per_block), dim3(POST_THREADS), 0, st, p, step_count);
 }
 extern "C" cudaError_t mqe_launch_reset_all(const DevParams &p, cudaStream_t st) {
     k_reset_all<<<(p.N + 127) / 128, 128, 0, st>>>(p);
