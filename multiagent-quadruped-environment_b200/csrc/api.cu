@@ -43,6 +43,12 @@ struct MqeSim {
     unsigned short *tmp_hi = nullptr, *tmp_lo = nullptr;
     int tmp_rows = 0;
     bool tail_fp32 = false;              // MQE_TC_TAIL=0: keep layers 1.. on the CUDA-core path (debug cross-check)
+    // CUDA graph of one whole policy step (tensor-core modes): captured once per action scale, replayed every step
+    struct StepGraph { float scale[3]; cudaGraphExec_t exec; int launches; };
+    std::vector<StepGraph> graphs;
+    cudaStream_t cap_stream = nullptr;
+    bool use_graph = false;
+    long long plain_steps = 0;
 };
 
 template <typename T>
@@ -84,6 +90,8 @@ int mqe_sim_destroy(MqeSim *s) {
     if (!s) return MQE_OK;
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
+    for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);
+    if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     for (void *ptr : s->allocs) cudaFree(ptr);
     if (s->tcw.blob) cudaFree(s->tcw.blob);
     if (s->h_actions) cudaFreeHost(s->h_actions);
@@ -196,6 +204,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
         CK(cudaStreamSynchronize(s->stream));     // host staging vectors go out of scope
     }
     { const char *e = getenv("MQE_TC_TAIL"); s->tail_fp32 = e && e[0] == '0'; }
+    { const char *e = getenv("MQE_GRAPH"); s->use_graph = (p.policy_mode != MQE_POLICY_FP32) && !(e && e[0] == '0'); }
     if (p.policy_mode != MQE_POLICY_FP32) {
         int rc = mqe_policy_tc_prepare(&w, M, &s->tcw, s->stream);
         if (rc != 0) return fail(MQE_ERR_CUDA, "tensor-core policy weight preparation failed");
@@ -232,6 +241,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     CK(dalloc(s, &p.reset_buf, (size_t)N)); CK(dalloc(s, &p.timeout_buf, (size_t)N)); CK(dalloc(s, &p.collide_buf, (size_t)N));
     CK(dalloc(s, &p.r_term, (size_t)N)); CK(dalloc(s, &p.p_term, (size_t)N)); CK(dalloc(s, &p.zl_term, (size_t)N)); CK(dalloc(s, &p.zh_term, (size_t)N));
     CK(dalloc(s, &p.episode, (size_t)N)); CK(dalloc(s, &p.hist_dirty, (size_t)N)); CK(dalloc(s, &p.stats, (size_t)8));
+    CK(dalloc(s, &p.ctr, (size_t)4));
     const size_t ring = (size_t)M * MQE_HIST_FRAMES * MQE_HIST_PAD;
     CK(dalloc(s, &p.hist_f32, ring));
     const size_t ring_tc = (size_t)((M + 127) / 128) * 128 * MQE_HIST_FRAMES * MQE_HIST_PAD;     // pre-tiled planes, rows padded to 128
@@ -342,7 +352,7 @@ static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, c
     if (s->p.policy_mode == MQE_POLICY_FP32)
         CK(mqe_launch_policy_l0_fp32(s->pw, ps, ring, head, rows, s->stream));
     else
-        CK(mqe_launch_policy_l0_tc(s->tcw, s->pw.b0cat, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, ps.Z, s->tail_fp32 ? 0 : 1, s->stream));
+        CK(mqe_launch_policy_l0_tc(s->tcw, s->pw.b0cat, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, ps.Z, s->tail_fp32 ? 0 : 1, s->p.ctr, s->stream));
     int n = 1;
     if (s->p.policy_mode == MQE_POLICY_FP32 || s->tail_fp32)
         CK(mqe_launch_policy_tail(s->pw, ps, rows, s->stream, &n));
@@ -352,16 +362,22 @@ static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, c
     return MQE_OK;
 }
 
-int mqe_sim_policy(MqeSim *s, const float *d_actions) {
+// device_ctr: kernels take the ring slot from the device counter (graph capture) instead of the host mirror
+static int policy_impl(MqeSim *s, const float *d_actions, bool device_ctr) {
     if (!s || !d_actions) return fail(MQE_ERR_INVALID, "null argument");
     CK(cudaSetDevice(s->device));
-    s->head = (s->head + 1) % MQE_HIST_FRAMES;
-    CK(mqe_launch_policy_frame(s->p, d_actions, s->head, s->stream));
-    int rc = run_network(s, s->p.hist_f32, s->p.hist_hi, s->p.hist_lo, s->head, s->M, s->ps.latent, s->ps.act);
+    const int slot = (s->head + 1) % MQE_HIST_FRAMES;
+    CK(mqe_launch_policy_frame(s->p, d_actions, device_ctr ? -1 : slot, s->stream));
+    int rc = run_network(s, s->p.hist_f32, s->p.hist_hi, s->p.hist_lo, device_ctr ? -1 : slot, s->M, s->ps.latent, s->ps.act);
     if (rc != MQE_OK) return rc;
     CK(mqe_launch_policy_finish(s->p, s->ps.act, s->stream));
     s->launches += 2;
     return MQE_OK;
+}
+int mqe_sim_policy(MqeSim *s, const float *d_actions) {
+    int rc = policy_impl(s, d_actions, false);
+    if (rc == MQE_OK) s->head = (s->head + 1) % MQE_HIST_FRAMES;
+    return rc;
 }
 
 static int substeps_impl(MqeSim *s, int count, bool zero_stats) {
@@ -374,21 +390,68 @@ static int substeps_impl(MqeSim *s, int count, bool zero_stats) {
 }
 int mqe_sim_substeps(MqeSim *s, int count) { return substeps_impl(s, count, true); }
 
-int mqe_sim_post_physics(MqeSim *s) {
+static int post_impl(MqeSim *s, bool device_ctr) {
     if (!s) return fail(MQE_ERR_INVALID, "null handle");
     CK(cudaSetDevice(s->device));
-    CK(mqe_launch_post(s->p, s->step_count, s->stream));
-    s->step_count++;
+    CK(mqe_launch_post(s->p, device_ctr ? 0xffffffffu : s->step_count, s->stream));
     s->launches += 1;
     return MQE_OK;
 }
+int mqe_sim_post_physics(MqeSim *s) {
+    int rc = post_impl(s, false);
+    if (rc == MQE_OK) s->step_count++;
+    return rc;
+}
+
+static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
+    int rc = policy_impl(s, d_actions, device_ctr);
+    if (rc != MQE_OK) return rc;
+    rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: k_policy_finish zeroed the statistics
+    if (rc != MQE_OK) return rc;
+    return post_impl(s, device_ctr);
+}
 
 int mqe_sim_step(MqeSim *s, const float *d_actions) {
-    int rc = mqe_sim_policy(s, d_actions);
-    if (rc != MQE_OK) return rc;
-    rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: keeps the programmatic launch chain intact
-    if (rc != MQE_OK) return rc;
-    return mqe_sim_post_physics(s);
+    if (!s || !d_actions) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    int rc;
+    if (!s->use_graph || s->plain_steps < 2) {           // first steps run plainly (lazy function attributes, module load)
+        rc = step_plain(s, d_actions, false);
+        s->plain_steps++;
+    } else {
+        const size_t na = (size_t)s->p.N * s->actrl * 3 * sizeof(float);
+        if (d_actions != s->d_actions_stage) CK(cudaMemcpyAsync(s->d_actions_stage, d_actions, na, cudaMemcpyDeviceToDevice, s->stream));
+        MqeSim::StepGraph *g = nullptr;
+        for (auto &c : s->graphs)
+            if (c.scale[0] == s->p.act_scale[0] && c.scale[1] == s->p.act_scale[1] && c.scale[2] == s->p.act_scale[2]) g = &c;
+        if (!g) {                                         // capture once per action scale; arguments are constant from here on
+            if (!s->cap_stream) CK(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+            cudaStream_t user = s->stream;
+            const long long l0 = s->launches;
+            CK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+            s->stream = s->cap_stream;
+            rc = step_plain(s, s->d_actions_stage, true);
+            s->stream = user;
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(s->cap_stream, &graph);
+            if (rc != MQE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(MQE_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            MqeSim::StepGraph ng;
+            for (int i = 0; i < 3; i++) ng.scale[i] = s->p.act_scale[i];
+            ng.launches = (int)(s->launches - l0);
+            s->launches = l0;
+            ce = cudaGraphInstantiate(&ng.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(MQE_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+            s->graphs.push_back(ng);
+            g = &s->graphs.back();
+        }
+        CK(cudaGraphLaunch(g->exec, s->stream));
+        s->launches += g->launches;
+        rc = MQE_OK;
+    }
+    if (rc == MQE_OK) { s->head = (s->head + 1) % MQE_HIST_FRAMES; s->step_count++; }
+    return rc;
 }
 
 int mqe_sim_step_host(MqeSim *s, const float *h_actions, float *h_obs, uint8_t *h_reset) {

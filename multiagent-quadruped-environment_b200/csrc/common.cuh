@@ -51,6 +51,9 @@ struct DevParams {
     unsigned int *episode;
     unsigned char *hist_dirty;    // [N] history must be zeroed before the next frame is appended (go1.py:141-145)
     int *stats;                   // [8]
+    int *ctr;                     // device-side step counters: [0] ring slot that receives the next frame, [1] policy steps done
+                                  // (sheep RNG key), [2] scratch (blocks of k_post_physics finished); let a captured CUDA graph of
+                                  // the whole step be replayed with constant kernel arguments
     // history ring for the policy (policy.cu)
     float *hist_f32;              // [M][30][80] fp32 ring: slot s holds one padded 70-float frame
     unsigned short *hist_hi, *hist_lo;  // bf16 split ring, blocked layout (tensor-core modes)

@@ -32,7 +32,7 @@ cudaError_t mqe_launch_actuator(const float *act_w, const float *x, int rows, fl
 // tensor-core policy layer 0 (policy_tc.cu)
 int mqe_policy_tc_prepare(const MqeWeights *w, int rows, PolicyTcWeights *out, cudaStream_t st);
 cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat, const unsigned short *hist_hi, const unsigned short *hist_lo,
-                                    int head, int rows, int passes, float *Z, int planes_out, cudaStream_t st);
+                                    int head, int rows, int passes, float *Z, int planes_out, const int *ctr, cudaStream_t st);
 cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, int M, int passes,
                                       cudaStream_t st, int *launches);
 size_t mqe_substeps_smem_bytes(int A, int Pd, int E, int maxpair);

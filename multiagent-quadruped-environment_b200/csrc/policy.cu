@@ -45,6 +45,7 @@ __device__ void dev_defender_command(const DevParams &p, int e, float *cmd) {
 __global__ void __launch_bounds__(256) k_policy_frame(DevParams p, const float *__restrict__ d_actions, int head) {
     pdl_launch_dependents();
     pdl_wait();
+    if (head < 0) head = p.ctr[0];                           // graph replay: the slot comes from the device counter
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int M = p.N * p.A;
     if (m >= M) return;
@@ -118,7 +119,8 @@ __global__ void k_policy_finish(DevParams p, const float *__restrict__ act) {
         p.actions[t] = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);
     }
     if (t < p.N) p.hist_dirty[t] = 0;
-    if (t < 8) p.stats[t] = 0;                               // contact statistics of the step that follows (k_substeps accumulates)
+    if (t < 8) p.stats[t] = 0;
+    if (t == 0) p.ctr[0] = (p.ctr[0] + 1) % MQE_HIST_FRAMES;  // nobody reads the slot counter after this point of the step                               // contact statistics of the step that follows (k_substeps accumulates)
 }
 
 // ---------------------------------------------------------------------------------------------- fp32 SGEMM chain

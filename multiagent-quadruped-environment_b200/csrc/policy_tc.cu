@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(320, 1)
 k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo,
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
                const float *__restrict__ b0cat, float *__restrict__ Z, unsigned short *__restrict__ a0_hi,
-               unsigned short *__restrict__ a0_lo, int M, int head, int passes) {
+               unsigned short *__restrict__ a0_lo, int M, int head, int passes, const int *__restrict__ ctr) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t *empty = full + TC_STAGES;
@@ -121,6 +121,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     pdl_wait();                                              // set-up above ran in the predecessor's shadow
+    if (head < 0) head = ctr[0];                             // graph replay: newest slot = the one k_policy_frame just wrote
     const uint32_t stage_tx = passes == 3 ? TC_STAGE_BYTES : 2 * TC_TILE_BYTES;
 
     if (warp == 0) {
@@ -481,11 +482,11 @@ extern "C" int mqe_policy_tc_prepare(const MqeWeights *w, int rows, PolicyTcWeig
 // pre-activation until the latent columns are added (prologue of the first tail layer).
 extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat, const unsigned short *hist_hi,
                                                const unsigned short *hist_lo, int head, int rows, int passes, float *Z, int planes_out,
-                                               cudaStream_t st) {
+                                               const int *ctr, cudaStream_t st) {
     dim3 grid(6, (rows + 127) / 128);
     return launch_heavy(k_policy_l0_tc, grid, dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                       (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
-                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes);
+                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr);
 }
 
 // layers 1.. on the tensor cores: operands are bf16 hi/lo planes end to end (needs layer 0 launched with planes_out = 1)

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
     pdl_launch_dependents();
     pdl_wait();
     __shared__ int s_flags[POST_THREADS];
+    if (step_count == 0xffffffffu) step_count = (unsigned int)p.ctr[1];     // graph replay: device counter
     const int A = p.A, P = p.P, G = p.G;
     const int envs_per_block = POST_THREADS / A;
     const int el = threadIdx.x / A, a = threadIdx.x % A;
@@ -205,6 +206,12 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
         const float *dof = p.dof + ((size_t)e * (12 * A + p.D) + 12 * a) * 2;
         for (int j = 0; j < 12; j++) { p.last_actions[m * 12 + j] = p.actions[m * 12 + j]; p.last_dof_vel[m * 12 + j] = dof[j * 2 + 1]; }
         for (int i = 0; i < 6; i++) p.last_root_vel[m * 6 + i] = rs[7 + i];
+    }
+    // the last block to finish advances the step counter (every block read it at its start, so nobody still needs it)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&p.ctr[2], 1) == (int)gridDim.x - 1) { p.ctr[2] = 0; p.ctr[1] += 1; }
     }
 }
 
