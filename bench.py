@@ -234,8 +234,14 @@ def run_gpu(args):
     algo_bytes = n_local * (A * BYTES_PER_AGENT_SUBSTEPS + base.num_npcs * BYTES_PER_NPC)
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / sub_t / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and args.task == TASK and args.num_envs == ENVS_PER_GPU:      # captured on this workload only
+        with open(tpath) as f:
+            t_ = json.load(f).get("k_substeps", {})
+        traffic = t_.get("dram_bytes_read", 0) + t_.get("dram_bytes_write", 0)
     roofline = {"bound": "hbm", "kernel": "k_substeps", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": sub_t * 1e3, "policy_ms": float(np.mean(pol_ms)), "post_ms": float(np.mean(post_ms)),
                 "contacts_per_env_substep": float(stats[0]) / max(1, n_local * base.decimation),
                 "note": "scalar-fp32 / latency-bound articulated dynamics + PGS: algorithmic bytes per launch are tiny against the time"}
