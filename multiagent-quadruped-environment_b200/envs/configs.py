@@ -272,6 +272,39 @@ def Go1FootballDefenderCfg() -> Cfg:
     return c
 
 
+def _football_game(num_agents, init_xy, episode_length_s):
+    """go1_football_config.py:133-371 (1 vs 1 and 2 vs 2): free-play football, ball at (7, 0, 0.2)."""
+    c = go1_base()
+    c.env.update(env_name="go1football", num_envs=1, num_agents=num_agents, num_npcs=1, episode_length_s=episode_length_s)
+    c.asset.update(file_npc="{LEGGED_GYM_ROOT_DIR}/resources/objects/ball.urdf", name_npc="ball",
+                   terminate_after_contacts_on=[], npc_collision=True, fix_npc_base_link=False, npc_gravity=True)
+    c.terrain.update(num_rows=1, num_cols=1, BarrierTrack_kwargs=_track(
+        options=["init", "gate", "plane", "gate", "wall"], track_width=9.0,
+        init=dict(block_length=1.0, room_size=(0.0, 0.0), border_width=0.0, offset=(0.5, 0)),
+        plane=dict(block_length=10.0),
+        gate=dict(block_length=1.0, width=2.0, depth=1.0, offset=(0, 0), random=(0, 0.0)),
+        wall=dict(block_length=0.1), wall_height=1.0))
+    c.command.cfg.vel = True
+    c.init_state.multi_init_state = True
+    c.init_state.init_states = [InitState(pos=(x, y, 0.42), rot=(0.0, 0.0, 0.0, 1.0) if x < 6 else (0.0, 0.0, 1.0, 0.0)) for x, y in init_xy]
+    c.init_state.init_states_npc = [InitState(pos=(7.0, 0.0, 0.2))]
+    c.termination.update(check_obstacle_conditioned_threshold=False, termination_terms=["roll", "pitch"])
+    c.domain_rand.init_base_pos_range = dict(x=[-0.1, 0.1], y=[-0.1, 0.1])
+    c.rewards.scales = Cfg(goal_reward_scale=1)
+    c.viewer.update(pos=[2.0, 2.0, 2.0], lookat=[6.0, 5.0, 0.0])
+    return c
+
+
+def Go1Football1vs1Cfg() -> Cfg:
+    """go1_football_config.py:133-250 (episode_length_s = 1 there)"""
+    return _football_game(2, [(3.0, 0.0), (9.0, 0.0)], 1)
+
+
+def Go1Football2vs2Cfg() -> Cfg:
+    """go1_football_config.py:252-371"""
+    return _football_game(4, [(3.0, 2.0), (3.0, -2.0), (9.0, 2.0), (9.0, -2.0)], 20)
+
+
 def class_to_dict(obj):
     """helpers.py:46-61 for Cfg trees."""
     if isinstance(obj, Cfg):

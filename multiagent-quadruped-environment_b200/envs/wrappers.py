@@ -288,3 +288,32 @@ class Go1FootballDefenderWrapper(EmptyWrapper):
             reward += r
             self._acc("ball gate distance reward", torch.sum(r))
         return obs, reward.repeat(1, 2), termination, info
+
+
+class Go1FootballGameWrapper(EmptyWrapper):
+    """go1_football_wrapper.py:93-157 (1 vs 1 / 2 vs 2).  The reference leaves this wrapper unfinished: `reset()` returns
+    None, `step()` returns `None` observations and zero rewards repeated 4 times (:128, :157); reproduced as is, with the
+    quantities it computes on the way (`ball_pos`, `ball_vel`, `base_info`) kept as attributes for callers."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(18 + self.num_agents,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.reward_buffer = {"goal reward": 0, "step count": 0}
+
+    def _gather(self, obs_buf):
+        npc = self.root_states_npc
+        self.ball_pos = (npc[:, :3].reshape(self.num_envs, 3) - self.env_origins).unsqueeze(1).repeat(1, 2, 1)
+        self.ball_vel = npc[:, 7:10].reshape(self.num_envs, 3).unsqueeze(1).repeat(1, 2, 1)
+        self.base_info = self._base_info(obs_buf)[:, :2, :]
+
+    def reset(self):
+        self._gather(self.env.reset())
+        return None
+
+    def step(self, action):
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        self._gather(obs_buf)
+        self._acc("step count", 1)
+        reward = torch.zeros([self.env.num_envs, 1], device=self.env.device)
+        return None, reward.repeat(1, 4), termination, info

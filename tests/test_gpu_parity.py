@@ -338,3 +338,26 @@ def test_openrl_adapter_numpy_surface():
     obs, rew, done, infos = env.step(np.zeros((16, 1, 3), dtype=np.float32))
     assert obs.shape == (16, 1, 14) and rew.shape == (16, 1, 1) and done.shape == (16, 1)
     env.close()
+
+
+@pytest.mark.parametrize("task,A", [("go1football-1vs1", 2), ("go1football-2vs2", 4)])
+def test_football_game_tasks(task, A):
+    """go1football-1vs1 / -2vs2: free robots + ball; the reference wrapper returns None observations and zero rewards."""
+    from types import SimpleNamespace
+    from mqe_b200.envs import make_mqe_env, custom_cfg
+    args = SimpleNamespace(num_envs=32, seed=0, headless=True, record_video=False, sim_device="cuda:0")
+    env, cfg = make_mqe_env(task, args, custom_cfg(args))
+    assert env.reset() is None and env.num_agents == A
+    x0 = env.root_states[:, 0].clone().view(32, A)
+    for s in range(30):
+        a = torch.zeros((32, A, 3), device="cuda:0"); a[..., 0] = 0.5
+        obs, rew, done, info = env.step(a)
+    assert obs is None and rew.shape == (32, 4) and float(rew.abs().sum()) == 0.0 and done.shape == (32,)
+    rs = env.root_states
+    assert torch.isfinite(rs).all() and torch.isfinite(env.root_states_npc).all()
+    alive = env.episode_length_buf == 30 if task.endswith("2vs2") else torch.ones(32, dtype=torch.bool, device="cuda:0")
+    dx = (rs[:, 0].view(32, A) - x0)[alive]
+    # first team walks +x, the mirrored team (yaw = pi) walks -x; 0.6 s includes the landing transient
+    assert (dx[:, 0] > 0).all() and dx[:, 0].median() > 0.1 and (dx[:, A - 1] < 0).all() and dx[:, A - 1].median() < -0.1
+    assert env.ball_pos.shape == (32, 2, 3)
+    env.close()
