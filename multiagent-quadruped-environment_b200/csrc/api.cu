@@ -301,6 +301,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     set_buf(s, MQE_BUF_HISTORY, p.hist_f32, 4, M, MQE_HIST_FRAMES, MQE_HIST_PAD);
     set_buf(s, MQE_BUF_SHEEP_STATS, p.sheep_stats, 4, N, 3);
     set_buf(s, MQE_BUF_STATS, p.stats, 4, 8);
+    set_buf(s, MQE_BUF_CLOCK, p.clock, 4, M, 4);
     return MQE_OK;
 }
 

@@ -195,6 +195,9 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
         if (p.term_mask & 4) { p.zl_term[e] = (unsigned char)((f >> 2) & 1); reset |= (f >> 2) & 1; }
         if (p.term_mask & 8) { p.zh_term[e] = (unsigned char)((f >> 3) & 1); reset |= (f >> 3) & 1; }
         p.reset_buf[e] = (unsigned char)reset;
+        // legged_robot.py:164-169 binds reset_buf and collide_buf to ONE tensor and ORs every later cause in place, so the
+        // reference's collide_buf equals the full reset mask whenever base contacts terminate
+        if (p.term_mask & 16) p.collide_buf[e] = (unsigned char)reset;
         if (P && p.npc_ctrl == MQE_NPC_SHEEP) dev_sheep_step(p, e, step_count);
         if (reset) dev_env_reset(p, e);
     }

@@ -23,7 +23,7 @@ OBS_FLOATS = 71
 (BUF_ROOT_STATES, BUF_DOF_STATES, BUF_CONTACT_FORCES, BUF_TORQUES, BUF_ACTIONS, BUF_LAST_ACTIONS, BUF_OBS,
  BUF_BASE_LIN_VEL, BUF_BASE_ANG_VEL, BUF_PROJ_GRAVITY, BUF_RESET, BUF_TIMEOUT, BUF_COLLIDE, BUF_ROLL_TERM,
  BUF_PITCH_TERM, BUF_ZLOW_TERM, BUF_ZHIGH_TERM, BUF_EPISODE_LENGTH, BUF_COMMANDS, BUF_LOC_OBS, BUF_LOC_ACTION,
- BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_COUNT) = range(26)
+ BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_CLOCK, BUF_COUNT) = range(27)
 
 OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
     "base_pos": (0, 3), "base_quat": (3, 7), "dof_pos": (7, 19), "dof_vel": (19, 31), "lin_vel": (31, 34),

@@ -50,6 +50,9 @@ def load(precision="f64"):
         lib.orc_set.restype = ctypes.c_int64
         lib.orc_real_size.restype = ctypes.c_int
         lib.orc_set_threads.argtypes = [ctypes.c_int]
+        lib.orc_set_reset_state.argtypes = [vp, ctypes.c_int]
+        lib.orc_torques.argtypes = [vp]
+        lib.orc_observe.argtypes = [vp]
         lib.orc_policy_forward.argtypes = [ctypes.POINTER(E.WeightsC), vp, ctypes.c_int, vp, vp]
         lib.orc_actuator_forward.argtypes = [ctypes.POINTER(E.WeightsC), vp, ctypes.c_int, vp]
         lib.orc_robot_dynamics.argtypes = [vp, ctypes.c_double if precision == "f64" else ctypes.c_float, vp, vp, vp, vp, vp, vp, vp]
@@ -99,6 +102,16 @@ class Oracle:
 
     def post_physics(self):
         self.lib.orc_post_physics(self.h)
+
+    # test hooks (golden replays)
+    def torques(self):
+        self.lib.orc_torques(self.h)
+
+    def observe(self):
+        self.lib.orc_observe(self.h)
+
+    def set_reset_state(self, on):
+        self.lib.orc_set_reset_state(self.h, int(bool(on)))
 
     def get(self, which):
         E = self.E

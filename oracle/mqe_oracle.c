@@ -6,8 +6,10 @@
  *
  * PARITY STATUS
  *   - bookkeeping (go1.py, legged_robot.py, legged_robot_field.py, the npc modules): restated line by line from the
- *     reference sources cited at each function; pinned by the TorchScript known-answer vectors
- *     (tests/golden/mlp_kat.npz) for the two networks and by tests/golden/terrain_*.npz for BarrierTrack.
+ *     reference sources cited at each function; PINNED by golden vectors that the reference's own methods produced in
+ *     this container (tests/golden/bookkeeping_*.npz via tools/gen_bookkeeping_golden.py, replayed by
+ *     tests/test_oracle_bookkeeping.py), by the TorchScript known-answer vectors (tests/golden/mlp_kat.npz) for the two
+ *     networks and by tests/golden/terrain_*.npz for BarrierTrack.
  *   - rigid-body physics (gym.simulate, go1.py:52-56): the arithmetic lives in NVIDIA Isaac Gym Preview 4
  *     (closed PhysX binary, un-vendored, unversioned in setup.py:11).  It cannot be run or inspected here
  *     and the reference ships no tests or golden trajectories => PARITY UNPINNED against PhysX.  What is
@@ -399,6 +401,7 @@ typedef struct {
     uint32_t *episode;                      /* reset counter per env (RNG key)  */
     uint32_t step_count;
     int32_t stats[8];
+    int reset_state;   /* 1 (default): reset_idx re-initialises DOF / root state from the counter RNG; 0 (golden replays): only _reset_buffers */
 } Oracle;
 
 static void *xcalloc(size_t n, size_t s) { void *p = calloc(n ? n : 1, s); if (!p) abort(); return p; }
@@ -450,6 +453,7 @@ Oracle *orc_create(const MqeSimDesc *desc) {
     o->p_term = (uint8_t *)xcalloc(N, 1); o->zl_term = (uint8_t *)xcalloc(N, 1); o->zh_term = (uint8_t *)xcalloc(N, 1);
     o->episode = (uint32_t *)xcalloc(N, sizeof(uint32_t));
     memset(o->reset_buf, 1, N); /* base_task.py:77 */
+    o->reset_state = 1;
     /* _prepare_locomotion_policy: locomotion_obs = default command frame repeated (go1.py:393-394) */
     for (int m = 0; m < M; m++)
         for (int i = 0; i < 70; i++) o->loc_obs[m * 70 + i] = desc->loc_obs_default[i];
@@ -1049,6 +1053,13 @@ static void env_reset(Oracle *o, int e) {
     int A = o->A, P = o->P, G = A + P;
     uint32_t ge = (uint32_t)(e + d->env_id_offset), ep = o->episode[e];
     real *dof = o->dof + (size_t)e * (12 * A + o->D) * 2;
+    for (int a = 0; a < A && !o->reset_state; a++) {      /* golden replays: the RNG-free part only (_reset_buffers) */
+        int m = e * A + a;
+        for (int j = 0; j < 12; j++) { o->last_actions[m * 12 + j] = 0; o->last_dof_vel[m * 12 + j] = 0; }
+        o->gait[m] = 0;
+        memset(o->hist + (size_t)m * 2100, 0, 2100 * sizeof(real));
+    }
+    if (!o->reset_state) { o->ep_len[e] = 0; o->reset_buf[e] = 1; o->episode[e] = ep + 1; return; }
     for (int a = 0; a < A; a++) {
         int m = e * A + a;
         for (int j = 0; j < 12; j++) {
@@ -1269,6 +1280,9 @@ void orc_post_physics(Oracle *o) {
         if (d->term_mask & 4) { o->zl_term[e] = (uint8_t)zl; reset |= zl; }
         if (d->term_mask & 8) { o->zh_term[e] = (uint8_t)zh; reset |= zh; }
         o->reset_buf[e] = (uint8_t)reset;
+        /* legged_robot.py:164-169: `self.reset_buf = self.collide_buf` binds ONE tensor to both names and every later
+         * `reset_buf |= ...` is in place, so the reference's collide_buf ends up equal to the full reset mask */
+        if (d->term_mask & 16) o->collide_buf[e] = (uint8_t)reset;
         if (P && d->npc_ctrl == MQE_NPC_SHEEP) sheep_step(o, e);
         if (reset) env_reset(o, e);
         env_observations(o, e);
@@ -1312,6 +1326,7 @@ int64_t orc_get(Oracle *o, int which, void *out) {
     case MQE_BUF_LOC_OBS: src = o->loc_obs; n = (size_t)M * 70; break;
     case MQE_BUF_LOC_ACTION: src = o->loc_last; n = (size_t)M * 12; break;
     case MQE_BUF_GAIT: src = o->gait; n = (size_t)M; break;
+    case MQE_BUF_CLOCK: src = o->clock; n = (size_t)M * 4; break;
     case MQE_BUF_HISTORY: src = o->hist; n = (size_t)M * 2100; break;
     case MQE_BUF_SHEEP_STATS: src = o->sheep_stats; n = (size_t)N * 3; break;
     case MQE_BUF_RESET: if (out) memcpy(out, o->reset_buf, N); return N;
@@ -1337,11 +1352,29 @@ int64_t orc_set(Oracle *o, int which, const float *in) {
     case MQE_BUF_DOF_STATES: from_f32(o->dof, in, (size_t)N * (12 * A + o->D) * 2); return 0;
     case MQE_BUF_ACTIONS: from_f32(o->actions, in, (size_t)M * 12); return 0;
     case MQE_BUF_HISTORY: from_f32(o->hist, in, (size_t)M * 2100); return 0;
+    case MQE_BUF_CONTACT_FORCES: from_f32(o->contact, in, (size_t)N * o->NB * 3); return 0;
+    case MQE_BUF_EPISODE_LENGTH: for (int e = 0; e < N; e++) o->ep_len[e] = (int64_t)in[e]; return 0;
     default: return -1;
     }
 }
 
 int orc_real_size(void) { return (int)sizeof(real); }
+
+/* ---- test hooks for the golden replays (tests/test_oracle_bookkeeping.py) ---- */
+void orc_set_reset_state(Oracle *o, int on) { o->reset_state = on; }
+/* _compute_torques for every env, no physics (go1.py:315-354) */
+void orc_torques(Oracle *o) {
+    for (int e = 0; e < o->N; e++) { real tau[48]; env_torques(o, e, tau); }
+}
+/* base_quat <- root quaternion, then compute_observations: the state Go1.reset() leaves behind */
+void orc_observe(Oracle *o) {
+    int A = o->A, G = o->A + o->P;
+    for (int e = 0; e < o->N; e++) {
+        for (int a = 0; a < A; a++)
+            for (int i = 0; i < 4; i++) o->base_quat[(e * A + a) * 4 + i] = o->root[((size_t)e * G + a) * 13 + 3 + i];
+        env_observations(o, e);
+    }
+}
 
 /* torchrun exports OMP_NUM_THREADS=1; the CPU-baseline legs ask for the host's cores explicitly */
 void orc_set_threads(int n) {
