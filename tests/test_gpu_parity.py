@@ -179,10 +179,11 @@ def test_single_substep_parity(task):
     eng.close()
 
 
+@pytest.mark.parametrize("mode", [E.POLICY_FP32, E.POLICY_BF16X3], ids=["fp32", "tcgen05-bf16x3"])
 @pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw"])
-def test_short_trajectory_parity(task):
-    """Full Go1.step() x 5 from reset on identical seeds and actions."""
-    sc, eng, orc = make_pair(task, 32)
+def test_short_trajectory_parity(task, mode):
+    """Full Go1.step() x 5 from reset on identical seeds and actions (tensor-core mode: steps 3.. are CUDA-graph replays)."""
+    sc, eng, orc = make_pair(task, 32, mode)
     eng.reset(); orc.reset()
     worst = {}
     for s in range(5):
@@ -193,8 +194,16 @@ def test_short_trajectory_parity(task):
         d_g, d_o = get(eng, E.BUF_DOF_STATES).reshape(-1, 2), orc.get(E.BUF_DOF_STATES).reshape(-1, 2)
         worst[s] = (np.abs(r_g[:, :7] - r_o[:, :7]).max(), np.abs(r_g[:, 7:] - r_o[:, 7:]).max(),
                     np.abs(d_g[:, 0] - d_o[:, 0]).max(), np.abs(d_g[:, 1] - d_o[:, 1]).max())
-        assert np.array_equal(get(eng, E.BUF_EPISODE_LENGTH), orc.get(E.BUF_EPISODE_LENGTH))
-        assert np.array_equal(get(eng, E.BUF_TIMEOUT), orc.get(E.BUF_TIMEOUT))
+        for buf in (E.BUF_EPISODE_LENGTH, E.BUF_TIMEOUT, E.BUF_RESET, E.BUF_COLLIDE, E.BUF_ROLL_TERM, E.BUF_PITCH_TERM,
+                    E.BUF_ZLOW_TERM, E.BUF_ZHIGH_TERM):
+            assert np.array_equal(get(eng, buf), orc.get(buf)), (task, s, buf)          # bookkeeping: bit-exact
+        ob_g, ob_o = get(eng, E.BUF_OBS), orc.obs()
+        rpy = slice(*E.OBS_SLICES["base_rpy"])
+        d_rpy = np.abs(((ob_g[:, rpy] - ob_o[:, rpy] + np.pi) % (2 * np.pi)) - np.pi)   # angles live on the circle
+        ob_g[:, rpy] = ob_o[:, rpy]
+        assert d_rpy.max() < 1e-4 and np.allclose(ob_g, ob_o, rtol=1e-4, atol=2e-4), (task, s, "obs rows")
+        assert np.allclose(get(eng, E.BUF_LOC_OBS), orc.get(E.BUF_LOC_OBS).reshape(-1, 70), rtol=1e-4, atol=2e-4)
+        assert np.allclose(get(eng, E.BUF_CLOCK).ravel(), orc.get(E.BUF_CLOCK), atol=1e-5)
     print(task, {k: tuple(f"{x:.2e}" for x in v) for k, v in worst.items()})
     # measured on B200: ~1e-7 (pos, q), ~2e-6 (root vel), ~1e-5 (qd) after the first policy step, ~1e-4 (qd) after five
     assert worst[0][0] < 5e-6 and worst[0][2] < 5e-6, worst[0]
