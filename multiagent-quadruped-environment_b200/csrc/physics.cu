@@ -1038,7 +1038,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     if (kind == 0) { lam = fmaxf(lam, 0.f); lam_n = lam; }
                     else { float lim = p.mu * lam_n; lam = fminf(fmaxf(lam, -lim), lim); }
                     float dl = lam - lam_old;
-                    row[20] = lam;
+                    row[20] = lam;                               // all four lanes of the quad store the SAME value (benign same-value race)
                     vb[0] += r2.y * dl; vb[1] += r2.z * dl; vb[2] += r2.w * dl; vb[3] += r3.x * dl; vb[4] += r3.y * dl; vb[5] += r3.z * dl;
 #pragma unroll
                     for (int L = 0; L < 4; L++) {                       // branch-free: only the row's leg sees a non-zero dl
@@ -1097,6 +1097,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         // ================================================================ P5: contact force report (last substep), integrate
         if (last) {
             float idt = 1.f / p.dt;
+            __syncwarp();                                        // multipliers written by other lanes of the quad are read below
             if (is_robot && active) {
                 int ncon = (nrows - nlim) / 3;
                 for (int c = leg; c < ncon; c += 4) {

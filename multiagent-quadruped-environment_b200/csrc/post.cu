@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
         if (fabsf(rpy[1]) > p.term_pitch) f |= 2;
         if (z < p.term_zlow) f |= 4;
         if (z > p.term_zhigh) f |= 8;
+        // safety net outside the reference's semantics: a non-finite or exploding state can never terminate on its own (every
+        // comparison with NaN is false), so it is reset here.  Never taken in the parity tests or in 3000-step soak runs.
+        float chk = rs[0] + rs[1] + rs[2] + q4[0] + q4[1] + q4[2] + q4[3] + lv.x + lv.y + lv.z + av.x + av.y + av.z;
+        if (!(fabsf(chk) < 1e6f)) f |= 32;
         if (f) atomicOr(&s_flags[el], f);
     }
     __syncthreads();
@@ -194,6 +198,11 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
         if (p.term_mask & 2) { p.p_term[e] = (unsigned char)((f >> 1) & 1); reset |= (f >> 1) & 1; }
         if (p.term_mask & 4) { p.zl_term[e] = (unsigned char)((f >> 2) & 1); reset |= (f >> 2) & 1; }
         if (p.term_mask & 8) { p.zh_term[e] = (unsigned char)((f >> 3) & 1); reset |= (f >> 3) & 1; }
+        if (f & 32) {                                    // blown-up env: also clear what a normal reset keeps (actuator / action histories)
+            reset = 1;
+            atomicAdd(p.stats + 4, 1);
+            for (int i = e * A * 12; i < (e + 1) * A * 12; i++) { p.err1[i] = p.err2[i] = p.vel1[i] = p.vel2[i] = 0.f; p.loc_last[i] = p.loc_last2[i] = 0.f; p.actions[i] = 0.f; }
+        }
         p.reset_buf[e] = (unsigned char)reset;
         // legged_robot.py:164-169 binds reset_buf and collide_buf to ONE tensor and ORs every later cause in place, so the
         // reference's collide_buf equals the full reset mask whenever base contacts terminate
