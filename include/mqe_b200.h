@@ -40,7 +40,7 @@ typedef enum {
     MQE_ERR_UNSUPPORTED = -4
 } MqeStatus;
 
-typedef enum { MQE_NPC_NONE = 0, MQE_NPC_RIGID = 1, MQE_NPC_SEESAW = 2 } MqeNpcKind;
+typedef enum { MQE_NPC_NONE = 0, MQE_NPC_RIGID = 1, MQE_NPC_SEESAW = 2, MQE_NPC_BOX = 3 } MqeNpcKind;   /* RIGID: capsule / sphere; BOX: free box */
 typedef enum { MQE_NPC_PASSIVE = 0, MQE_NPC_SHEEP = 1 } MqeNpcCtrl;
 typedef enum { MQE_POLICY_FP32 = 0, MQE_POLICY_BF16X3 = 1, MQE_POLICY_BF16 = 2 } MqePolicyMode;
 
@@ -107,7 +107,8 @@ typedef struct {
     float reserved2;
     /* MQE_NPC_SEESAW geometry (resources/objects/seesaw.urdf): [0..2] revolute-y joint origin rel. the fixed base,
      * [3] plank box / COM x offset in the plank frame, [4..6] plank half extents, [7..9] platform (base box) half extents,
-     * [10] column radius, [11] column length, [12] joint velocity limit [rad/s]; rest unused. */
+     * [10] column radius, [11] column length, [12] joint velocity limit [rad/s]; rest unused.
+     * MQE_NPC_BOX (resources/objects/box.urdf): [4..6] box half extents. */
     float npc_geom[16];
     uint64_t seed;
     /* static world: 2-D signed distance to the wall footprint on the BarrierTrack pixel grid */

@@ -126,8 +126,9 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     DevParams &p = s->p;
     memset(&p, 0, sizeof p);
     p.N = N; p.A = A; p.P = P; p.D = D; p.G = G;
-    p.Pd = (d->npc_kind == MQE_NPC_RIGID || d->npc_kind == MQE_NPC_SEESAW) ? P : 0;   // NPCs that own a lane of the substep kernel
+    p.Pd = (d->npc_kind == MQE_NPC_RIGID || d->npc_kind == MQE_NPC_SEESAW || d->npc_kind == MQE_NPC_BOX) ? P : 0;   // NPCs that own a lane of the substep kernel
     if (d->npc_kind == MQE_NPC_SEESAW && (P != 1 || D != 1)) return fail(MQE_ERR_UNSUPPORTED, "seesaw: exactly one NPC with one DOF");
+    if (d->npc_kind == MQE_NPC_BOX && P != 1) return fail(MQE_ERR_UNSUPPORTED, "box: exactly one NPC");
     for (int i = 0; i < 16; i++) p.geom[i] = d->npc_geom[i];
     p.env_off = d->env_id_offset;
     p.npc_kind = d->npc_kind; p.npc_ctrl = d->npc_ctrl;

@@ -33,11 +33,12 @@
 #define RS_SIZE (RS_FORCE + 52)
 // per-npc shared block
 #define NS_ORIGIN 0
-#define NS_CAP 3       // p0 p1 r
+#define NS_CAP 3       // p0 p1 r   (seesaw: cos, sin of the plank angle)
 #define NS_CNT 10
 #define NS_BOUND 11
 #define NS_FORCE 12
-#define NS_ROWS 16
+#define NS_ROT 16      // box: rotation matrix, columns ex ey ez (9 floats)
+#define NS_ROWS 28
 #define NS_CMETA (NS_ROWS + 12 * ROWF)
 #define NS_SIZE (NS_CMETA + 16)
 // per-env shared block
@@ -222,11 +223,11 @@ __device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float 
     return h;
 }
 
-// sphere vs the seesaw plank (oriented box in the frame pivot; ex = (c,0,-s), ey, ez = (s,0,c)); normal plank -> sphere
-__device__ __forceinline__ bool sphere_plank(const DevParams &p, V3 pivot, float c, float s, V3 x, float r, V3 &nrm, float &gap, V3 &pos) {
-    const float *g = p.geom;
-    V3 dx = x - pivot;
-    float loc[3] = {dx.x * c - dx.z * s - g[3], dx.y, dx.x * s + dx.z * c}, h[3] = {g[4], g[5], g[6]}, df[3], nl[3] = {0.f, 0.f, 0.f};
+// sphere (centre x, radius r) vs an oriented box (centre c, axes ex ey ez, half extents h); normal box -> sphere.
+// Used for the seesaw plank and the push box; same arithmetic as the oracle's sphere_obb.
+__device__ __forceinline__ bool sphere_obb(const DevParams &p, V3 c, V3 ex, V3 ey, V3 ez, const float *h, V3 x, float r, V3 &nrm, float &gap, V3 &pos) {
+    V3 dx = x - c;
+    float loc[3] = {dot(dx, ex), dot(dx, ey), dot(dx, ez)}, df[3], nl[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 3; i++) df[i] = loc[i] - fminf(fmaxf(loc[i], -h[i]), h[i]);
     float d2 = df[0] * df[0] + df[1] * df[1] + df[2] * df[2];
@@ -244,7 +245,7 @@ __device__ __forceinline__ bool sphere_plank(const DevParams &p, V3 pivot, float
         gap = -best - r;
     }
     if (gap >= p.coff) return false;
-    nrm = mk(nl[0] * c + nl[2] * s, nl[1], -nl[0] * s + nl[2] * c);
+    nrm = nl[0] * ex + nl[1] * ey + nl[2] * ez;
     pos = x - (r + 0.5f * gap) * nrm;
     return true;
 }
@@ -372,7 +373,9 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
     const int A = p.A, P = p.Pd, E = p.E, G = A + P;   // P: NPCs that own a lane
     const int GA = p.G;                                 // actors per env in the root-state tensor
     const bool seesaw = p.npc_kind == MQE_NPC_SEESAW;   // the NPC lane is a 1-DOF plank on a fixed base (seesaw.urdf)
-    const int Gc = seesaw ? A : G;                      // groups that take part in the capsule / capsule phase
+    const bool box = p.npc_kind == MQE_NPC_BOX;         // the NPC lane is a free box (box.urdf)
+    const bool obb = seesaw || box;                     // robot probes collide with an oriented box instead of capsules
+    const int Gc = obb ? A : G;                         // groups that take part in the capsule / capsule phase
     float *wbase = smem + physics_cta_header_floats() + warp * physics_warp_smem_floats(A, P, E, maxpair);
     const int first_env = (blockIdx.x * nwarps + warp) * E;
     if (first_env >= p.N) return;
@@ -629,6 +632,10 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             ns[NS_CAP + 3] = pos.x + ax.x; ns[NS_CAP + 4] = pos.y + ax.y; ns[NS_CAP + 5] = pos.z + ax.z; ns[NS_CAP + 6] = p.npc_radius;
             ((int *)ns)[NS_CNT] = 0;
             ns[NS_BOUND] = p.npc_radius + p.npc_halflen;
+            if (box) {
+                ns[NS_ROT] = Rb.c0.x; ns[NS_ROT + 1] = Rb.c0.y; ns[NS_ROT + 2] = Rb.c0.z; ns[NS_ROT + 3] = Rb.c1.x; ns[NS_ROT + 4] = Rb.c1.y;
+                ns[NS_ROT + 5] = Rb.c1.z; ns[NS_ROT + 6] = Rb.c2.x; ns[NS_ROT + 7] = Rb.c2.y; ns[NS_ROT + 8] = Rb.c2.z;
+            }
             ns[NS_FORCE] = ns[NS_FORCE + 1] = ns[NS_FORCE + 2] = 0.f;
         }
         if (rank_in_env == 0) ((int *)es)[ES_CNT] = 0;
@@ -770,15 +777,17 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             nrows = 3 * ncon;
             stat_local += ncon;
         } else if (is_npc && active) {
-            int ends = p.npc_halflen > 0.f ? 2 : 1, ncon = 0;
-            for (int en = 0; en < ends && ncon < MQE_MAX_LOCAL; en++) {
+            int ends = box ? 8 : (p.npc_halflen > 0.f ? 2 : 1), ncon = 0;    // box: its 8 corners as point probes
+            const float prad = box ? 0.f : p.npc_radius;
+            for (int en = 0; en < ends && ncon < 4; en++) {
                 V3 xr = ((en == 0 ? -1.f : 1.f) * p.npc_halflen) * Rb.c2;
-                ProbeHit h = probe_world(p, pos + xr, p.npc_radius);
+                if (box) xr = (((en & 1) ? 1.f : -1.f) * p.geom[4]) * Rb.c0 + (((en & 2) ? 1.f : -1.f) * p.geom[5]) * Rb.c1 + (((en & 4) ? 1.f : -1.f) * p.geom[6]) * Rb.c2;
+                ProbeHit h = probe_world(p, pos + xr, prad);
                 for (int kind = 0; kind < 2 && ncon < 4; kind++) {
                     if (!(h.mask & (1 << kind))) continue;
                     V3 n = kind ? h.nw : mk(0, 0, 1);
                     float gap = kind ? h.gap_w : h.gap_f;
-                    V3 r = xr - (p.npc_radius + 0.5f * gap) * n, t1, t2;
+                    V3 r = xr - (prad + 0.5f * gap) * n, t1, t2;
                     tangent_basis(n, t1, t2);
                     float *cmeta = ns + NS_CMETA + ncon * 4;
                     cmeta[0] = n.x; cmeta[1] = n.y; cmeta[2] = n.z; cmeta[3] = 0.f;
@@ -945,11 +954,21 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 }
                 npair = min(npair, maxpair);
             }
-            if (seesaw) {
-                // robot probes on the plank: canonical order = robot ascending, probe-table order (two-pass compaction)
+            if (obb) {
+                // robot probes on the plank / the push box: canonical order = robot ascending, probe-table order (two-pass compaction)
                 const float *nsS = wbase + E * A * RS_SIZE + (e_loc * P) * NS_SIZE;
-                const V3 pivot = mk(nsS[NS_ORIGIN], nsS[NS_ORIGIN + 1], nsS[NS_ORIGIN + 2]);
-                const float cs = nsS[NS_CAP], sn = nsS[NS_CAP + 1];
+                const V3 pivot = mk(nsS[NS_ORIGIN], nsS[NS_ORIGIN + 1], nsS[NS_ORIGIN + 2]);   // group origin: seesaw pivot / box COM
+                V3 oex, oey, oez, oc;
+                const float oh[3] = {p.geom[4], p.geom[5], p.geom[6]};
+                if (seesaw) {
+                    const float cs = nsS[NS_CAP], sn = nsS[NS_CAP + 1];
+                    oex = mk(cs, 0.f, -sn); oey = mk(0.f, 1.f, 0.f); oez = mk(sn, 0.f, cs);
+                    oc = pivot + p.geom[3] * oex;
+                } else {
+                    oex = mk(nsS[NS_ROT], nsS[NS_ROT + 1], nsS[NS_ROT + 2]); oey = mk(nsS[NS_ROT + 3], nsS[NS_ROT + 4], nsS[NS_ROT + 5]);
+                    oez = mk(nsS[NS_ROT + 6], nsS[NS_ROT + 7], nsS[NS_ROT + 8]);
+                    oc = pivot;
+                }
                 unsigned sm = 0;
                 const int *pl_ = tbl + leg * 10;
                 if (is_robot && active)
@@ -962,7 +981,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                         V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
                         V3 nn, pp;
                         float gg;
-                        if (sphere_plank(p, pivot, cs, sn, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], nn, gg, pp)) sm |= 1u << pi;
+                        if (sphere_obb(p, oc, oex, oey, oez, oh, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], nn, gg, pp)) sm |= 1u << pi;
                     }
                 unsigned sall = sm;
                 if (is_robot) { sall |= __shfl_xor_sync(quad_mask, sall, 1); sall |= __shfl_xor_sync(quad_mask, sall, 2); }
@@ -984,7 +1003,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
                     V3 cn, cpos, t1, t2;
                     float cgap;
-                    sphere_plank(p, pivot, cs, sn, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], cn, cgap, cpos);
+                    sphere_obb(p, oc, oex, oey, oez, oh, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], cn, cgap, cpos);
                     tangent_basis(cn, t1, t2);
                     const V3 ra = cpos - pos, rb_ = cpos - pivot;
                     float *cmeta = es + ES_CMETA(maxpair) + slot * 8;

@@ -272,6 +272,29 @@ def Go1FootballDefenderCfg() -> Cfg:
     return c
 
 
+def Go1PushboxCfg() -> Cfg:
+    """go1_pushbox_config.py: two robots push a 1 m, 6 kg box along the track."""
+    c = go1_base()
+    c.env.update(env_name="go1pushbox", num_envs=1, num_agents=2, num_npcs=1, episode_length_s=15)
+    c.asset.update(terminate_after_contacts_on=[], file_npc="{LEGGED_GYM_ROOT_DIR}/resources/objects/box.urdf", name_npc="box",
+                   npc_collision=True, fix_npc_base_link=False, npc_gravity=True)
+    c.terrain.update(num_rows=1, num_cols=1, BarrierTrack_kwargs=_track(
+        options=["init", "gate", "wall"], track_width=5.0,
+        init=dict(block_length=2.0, room_size=(1.0, 2.5), border_width=0.0, offset=(0, 0)),
+        gate=dict(block_length=5.0, width=1.5, depth=0.1, offset=(0, 0), random=(0, 0.5)),
+        wall=dict(block_length=0.1), wall_height=0.5))
+    c.command.cfg.vel = True
+    c.init_state.multi_init_state = True
+    c.init_state.init_states = [InitState(pos=(0.0, 0.0, 0.42)), InitState(pos=(0.0, 0.0, 0.42))]
+    c.init_state.init_states_npc = [InitState(pos=(2.5, 0.0, 0.6))]
+    c.termination.update(check_obstacle_conditioned_threshold=False, termination_terms=["roll", "pitch"])
+    c.domain_rand.init_base_pos_range = dict(x=[-0.1, 0.1], y=[-0.1, 0.1])
+    c.domain_rand.init_npc_base_pos_range = dict(x=[-0.5, 0.5], y=[-0.5, 0.5])
+    c.rewards.scales = Cfg(box_x_movement_reward_scale=10)
+    c.viewer.update(pos=[0.0, 6.0, 5.0], lookat=[4.0, 6.0, 0.0])
+    return c
+
+
 def _football_game(num_agents, init_xy, episode_length_s):
     """go1_football_config.py:133-371 (1 vs 1 and 2 vs 2): free-play football, ball at (7, 0, 0.2)."""
     c = go1_base()

@@ -9,8 +9,8 @@ import numpy as np
 
 from . import configs as C
 from .go1 import Go1, Go1FootballDefender, Go1Object, Go1Sheep
-from .wrappers import (EmptyWrapper, Go1FootballDefenderWrapper, Go1FootballGameWrapper, Go1GateWrapper, Go1SeesawWrapper,
-                       Go1SheepWrapper)
+from .wrappers import (EmptyWrapper, Go1FootballDefenderWrapper, Go1FootballGameWrapper, Go1GateWrapper, Go1PushboxWrapper,
+                       Go1SeesawWrapper, Go1SheepWrapper)
 
 ENV_DICT = {
     "go1plane": {"class": Go1, "config": C.Go1PlaneCfg, "wrapper": EmptyWrapper},
@@ -21,9 +21,10 @@ ENV_DICT = {
     "go1football-1vs1": {"class": Go1Object, "config": C.Go1Football1vs1Cfg, "wrapper": Go1FootballGameWrapper},
     "go1football-2vs2": {"class": Go1Object, "config": C.Go1Football2vs2Cfg, "wrapper": Go1FootballGameWrapper},
     "go1seesaw": {"class": Go1Object, "config": C.Go1SeesawCfg, "wrapper": Go1SeesawWrapper},
+    "go1pushbox": {"class": Go1Object, "config": C.Go1PushboxCfg, "wrapper": Go1PushboxWrapper},
 }
 # tasks of the reference registry that are outside the hot-path scope of this round
-NOT_YET = ("go1pushbox", "go1tug", "go1wrestling", "go1revolvingdoor", "go1bridge")
+NOT_YET = ("go1tug", "go1wrestling", "go1revolvingdoor", "go1bridge")
 
 
 def set_seed(seed):

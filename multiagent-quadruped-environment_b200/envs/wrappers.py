@@ -317,3 +317,56 @@ class Go1FootballGameWrapper(EmptyWrapper):
         self._acc("step count", 1)
         reward = torch.zeros([self.env.num_envs, 1], device=self.env.device)
         return None, reward.repeat(1, 4), termination, info
+
+
+class Go1PushboxWrapper(EmptyWrapper):
+    """go1_pushbox_wrapper.py: obs = ids, (pos, rpy) self / other, gate xy, box xy, box quaternion (20 + A); reward = box x progress."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(20 + self.num_agents,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.box_x_movement_reward_scale = 1                 # the reference overrides the config value (10) here (:17)
+        self.reward_buffer = {"box movement reward": 0, "step count": 0}
+        self.gate_pos = None
+        self.last_box_pos = None
+
+    def _init_extras(self, obs):
+        kw = self.BarrierTrack_kwargs
+        gate = obs.env_info["gate_deviation"]                # mutated in place, as the reference does
+        gate[:, 0] += kw["init"]["block_length"] + kw["gate"]["block_length"] / 2
+        self.gate_pos = gate.unsqueeze(1).repeat(1, self.num_agents, 1)
+        self.gate_distance = self.gate_pos.reshape(-1, 2)[:, 0]
+
+    def _obs(self, obs_buf):
+        npc = self.root_states_npc
+        box_pos = npc[:, :3] - self.env.env_origins
+        base_info = self._base_info(obs_buf)
+        obs = torch.cat([self.obs_ids, base_info, torch.flip(base_info, [1]), self.gate_pos,
+                         box_pos[:, :2].unsqueeze(1).repeat(1, self.num_agents, 1),
+                         npc[:, 3:7].unsqueeze(1).repeat(1, self.num_agents, 1)], dim=2)
+        return obs, box_pos
+
+    def reset(self):
+        obs_buf = self.env.reset()
+        if self.gate_pos is None:
+            self._init_extras(obs_buf)
+        self.last_box_pos = None
+        return self._obs(obs_buf)[0]
+
+    def step(self, action):
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        if self.gate_pos is None:
+            self._init_extras(obs_buf)
+        obs, box_pos = self._obs(obs_buf)
+        self._acc("step count", 1)
+        reward = torch.zeros([self.env.num_envs, 1], device=self.env.device)
+        if self.box_x_movement_reward_scale != 0:
+            if self.last_box_pos is not None:
+                x_movement = (box_pos - self.last_box_pos)[:, 0]
+                x_movement[self.env.reset_buf] = 0
+                r = self.box_x_movement_reward_scale * x_movement
+                reward[:, 0] += r
+                self._acc("box movement reward", torch.sum(r))
+        self.last_box_pos = box_pos.clone()
+        return obs, reward.repeat(1, self.num_agents), termination, info

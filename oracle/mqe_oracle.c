@@ -575,13 +575,12 @@ static int probe_world(const Oracle *o, const real *x, real r, const real *fix, 
     return n;
 }
 
-/* sphere (centre x, radius r) vs the seesaw plank: oriented box in the frame (pivot; ex = (c,0,-s), ey, ez = (s,0,c)).
- * Returns 1 and fills normal (plank -> sphere), gap, contact point when gap < contact_offset. */
-static int sphere_plank(const MqeSimDesc *d, const real *pivot, real c, real s, const real *x, real r, real *nrm, real *gap_out, real *pos) {
-    const float *g = d->npc_geom;
-    real dx[3] = {x[0] - pivot[0], x[1] - pivot[1], x[2] - pivot[2]};
-    real loc[3] = {dx[0] * c - dx[2] * s - g[3], dx[1], dx[0] * s + dx[2] * c};
-    real h[3] = {g[4], g[5], g[6]}, q[3], df[3], nl[3] = {0, 0, 0}, gap;
+/* sphere (centre x, radius r) vs an oriented box (centre c, axes ex ey ez, half extents h).  Returns 1 and fills the
+ * normal (box -> sphere), gap and contact point when gap < contact_offset.  Used for the seesaw plank and the push box. */
+static int sphere_obb(const MqeSimDesc *d, const real *c, const real *ex, const real *ey, const real *ez, const real *h,
+                      const real *x, real r, real *nrm, real *gap_out, real *pos) {
+    real dx[3] = {x[0] - c[0], x[1] - c[1], x[2] - c[2]};
+    real loc[3] = {v3dot(dx, ex), v3dot(dx, ey), v3dot(dx, ez)}, q[3], df[3], nl[3] = {0, 0, 0}, gap;
     for (int i = 0; i < 3; i++) { q[i] = loc[i] < -h[i] ? -h[i] : (loc[i] > h[i] ? h[i] : loc[i]); df[i] = loc[i] - q[i]; }
     real d2 = df[0] * df[0] + df[1] * df[1] + df[2] * df[2];
     if (d2 > (real)1e-12) {
@@ -596,7 +595,7 @@ static int sphere_plank(const MqeSimDesc *d, const real *pivot, real c, real s, 
         gap = -best - r;
     }
     if (gap >= d->contact_offset) return 0;
-    nrm[0] = nl[0] * c + nl[2] * s; nrm[1] = nl[1]; nrm[2] = -nl[0] * s + nl[2] * c;
+    for (int i = 0; i < 3; i++) nrm[i] = nl[0] * ex[i] + nl[1] * ey[i] + nl[2] * ez[i];
     for (int i = 0; i < 3; i++) pos[i] = x[i] - nrm[i] * (r + gap * (real)0.5);
     *gap_out = gap;
     return 1;
@@ -725,6 +724,30 @@ static void solve_row(Row *r, Row *rows, EnvScratch *es, real mu) {
     if (r->gb >= 0) for (int i = 0; i < NV; i++) es->vel[r->gb][i] += r->Yb[i] * dl;
 }
 
+/* contacts of every robot probe (robot X ascending, probe-table order) with the oriented box of NPC group A */
+static int obb_probe_contacts(const Oracle *o, const EnvScratch *es, const MqeRobotModel *md, const real *c, const real *ex, const real *ey,
+                              const real *ez, const real *h, Contact *contacts, int *nc_io, Row *rows, int *nr_io, int npair, int max_pair) {
+    const MqeSimDesc *d = &o->d;
+    int A = o->A, nc = *nc_io, nr = *nr_io;
+    for (int X = 0; X < A; X++)
+        for (int pi = 0; pi < md->n_probes; pi++) {
+            const float *pr = md->probes[pi];
+            int link = (int)pr[0], body = (int)pr[1];
+            real loc[3] = {pr[2], pr[3], pr[4]}, x[3], nrm[3], pos[3], gap;
+            m3mulv(x, es->rd[X].R[link], loc);
+            v3add(x, x, es->rd[X].p[link]);
+            v3add(x, x, es->origin[X]);
+            if (npair >= max_pair || !sphere_obb(d, c, ex, ey, ez, h, x, pr[5], nrm, &gap, pos)) continue;
+            Contact *ct = &contacts[nc];
+            ct->ga = X; ct->la = link; ct->rba = X * MQE_NUM_BODIES + body; ct->gb = A; ct->lb = 0; ct->rbb = A * MQE_NUM_BODIES;
+            v3cpy(ct->n, nrm); v3cpy(ct->pos, pos); ct->gap = gap;
+            nr = add_contact_rows(o, es, ct, nc, rows, nr);
+            nc++; npair++;
+        }
+    *nc_io = nc; *nr_io = nr;
+    return npair;
+}
+
 /* ------------------------------------------------------------------------------------------------ one physics substep of one env
  * Replaces gym.set_dof_actuation_force_tensor + gym.simulate + gym.refresh_dof_state_tensor (go1.py:52-56). */
 static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *stats) {
@@ -760,7 +783,8 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         for (int i = 0; i < 3; i++) es.vel[a][3 + i] += dt * wxv[i];
         es.ndof[a] = NV;
     }
-    if (P && d->npc_kind == MQE_NPC_RIGID) {
+    const int rigid = d->npc_kind == MQE_NPC_RIGID || d->npc_kind == MQE_NPC_BOX;   /* free 6-DOF NPC bodies */
+    if (P && rigid) {
         es.npc_minv[0] = 1 / d->npc_inertia; es.npc_minv[1] = 1 / d->npc_mass;
         for (int p = 0; p < P; p++) {
             real *rs = root + (A + p) * 13;
@@ -829,18 +853,20 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         stats[0] += nloc; stats[1] += nl;
     }
     real npcR[16][9];
-    for (int p = 0; p < P && d->npc_kind == MQE_NPC_RIGID; p++) {
+    for (int p = 0; p < P && rigid; p++) {
         int g = A + p, nloc = 0;
         real *rs = root + g * 13;
         quat_to_mat(npcR[g], rs + 3);
-        int ends = d->npc_halflen > 0 ? 2 : 1;
-        for (int en = 0; en < ends && nloc < MAX_LOCAL_CONTACTS; en++) {
+        const int box = d->npc_kind == MQE_NPC_BOX;
+        int ends = box ? 8 : (d->npc_halflen > 0 ? 2 : 1);             /* box: its 8 corners as point probes */
+        for (int en = 0; en < ends && nloc < 4; en++) {
             real loc[3] = {0, 0, (en == 0 ? -1 : 1) * d->npc_halflen}, x[3];
+            if (box) for (int i = 0; i < 3; i++) loc[i] = ((en >> i) & 1 ? 1 : -1) * d->npc_geom[4 + i];
             m3mulv(x, npcR[g], loc);
             v3add(x, x, es.origin[g]);
             Contact cand[2];
-            int k = probe_world(o, x, d->npc_radius, NULL, cand);
-            for (int i = 0; i < k && nloc < MAX_LOCAL_CONTACTS; i++) {
+            int k = probe_world(o, x, box ? 0 : d->npc_radius, NULL, cand);
+            for (int i = 0; i < k && nloc < 4; i++) {
                 Contact *c = &contacts[nc];
                 *c = cand[i];
                 c->ga = g; c->la = 0; c->rba = A * MQE_NUM_BODIES + p; c->gb = -1; c->lb = 0; c->rbb = -1;
@@ -925,21 +951,17 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         }
         stats[0] += nloc;
         /* robot probes on the plank: robot X ascending, probe table order */
-        for (int X = 0; X < A; X++)
-            for (int pi = 0; pi < md->n_probes; pi++) {
-                const float *pr = md->probes[pi];
-                int link = (int)pr[0], body = (int)pr[1];
-                real loc[3] = {pr[2], pr[3], pr[4]}, x[3], nrm[3], pos[3], gap;
-                m3mulv(x, es.rd[X].R[link], loc);
-                v3add(x, x, es.rd[X].p[link]);
-                v3add(x, x, es.origin[X]);
-                if (npair >= max_pair || !sphere_plank(d, es.origin[A], ss_c, ss_s, x, pr[5], nrm, &gap, pos)) continue;
-                Contact *c = &contacts[nc];
-                c->ga = X; c->la = link; c->rba = X * MQE_NUM_BODIES + body; c->gb = A; c->lb = 0; c->rbb = A * MQE_NUM_BODIES;
-                v3cpy(c->n, nrm); v3cpy(c->pos, pos); c->gap = gap;
-                nr = add_contact_rows(o, &es, c, nc, rows, nr);
-                nc++; npair++;
-            }
+        {
+            real ex[3] = {ss_c, 0, -ss_s}, ey[3] = {0, 1, 0}, ez[3] = {ss_s, 0, ss_c}, h[3] = {gm[4], gm[5], gm[6]}, c[3];
+            for (int i = 0; i < 3; i++) c[i] = es.origin[A][i] + gm[3] * ex[i];
+            npair = obb_probe_contacts(o, &es, md, c, ex, ey, ez, h, contacts, &nc, rows, &nr, npair, max_pair);
+        }
+    }
+    if (P && d->npc_kind == MQE_NPC_BOX) {   /* robot probes on the push box (resources/objects/box.urdf) */
+        const real *R = npcR[A];
+        real ex[3] = {R[0], R[3], R[6]}, ey[3] = {R[1], R[4], R[7]}, ez[3] = {R[2], R[5], R[8]};
+        real h[3] = {d->npc_geom[4], d->npc_geom[5], d->npc_geom[6]};
+        npair = obb_probe_contacts(o, &es, md, es.origin[A], ex, ey, ez, h, contacts, &nc, rows, &nr, npair, max_pair);
     }
     stats[2] += npair;
     if (nr > stats[3]) stats[3] = nr;
@@ -969,7 +991,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
     }
     /* 5. integrate (semi-implicit Euler; exponential map for orientation) */
     for (int g = 0; g < G; g++) {
-        if (g >= A && d->npc_kind != MQE_NPC_RIGID) continue;
+        if (g >= A && !rigid) continue;
         real *rs = root + g * 13;
         real *v = es.vel[g];
         if (g < A)

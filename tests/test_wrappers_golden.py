@@ -15,6 +15,7 @@ CASES = {
     "go1sheep-easy": (W.Go1SheepWrapper, C.SingleSheepCfg, 2, 1),
     "go1seesaw": (W.Go1SeesawWrapper, C.Go1SeesawCfg, 2, 1),
     "go1football-defender": (W.Go1FootballDefenderWrapper, C.Go1FootballDefenderCfg, 3, 1),
+    "go1pushbox": (W.Go1PushboxWrapper, C.Go1PushboxCfg, 2, 1),
 }
 
 

@@ -40,8 +40,9 @@ def stub_modules():
     spaces.Box = Box
     gym.Wrapper, gym.spaces = Wrapper, spaces
     sys.modules["gym"], sys.modules["gym.spaces"] = gym, spaces
-    for name in ("mqe", "mqe.envs", "mqe.envs.wrappers"):
+    for name in ("mqe", "mqe.envs", "mqe.envs.wrappers", "isaacgym", "isaacgym.torch_utils"):
         sys.modules[name] = types.ModuleType(name)
+    sys.modules["isaacgym.torch_utils"].__all__ = []
 
 
 def load(name):
@@ -172,6 +173,7 @@ def main():
     run("go1sheep-easy", sheep, C.SingleSheepCfg(), 2, 1, 2)
     run("go1seesaw", seesaw, C.Go1SeesawCfg(), 2, 1, 3)
     run("go1football-defender", fb.Go1FootballDefenderWrapper, C.Go1FootballDefenderCfg(), 3, 1, 4, with_gate=True)
+    run("go1pushbox", load("go1_pushbox_wrapper").Go1PushboxWrapper, C.Go1PushboxCfg(), 2, 1, 5)
 
 
 if __name__ == "__main__":
