@@ -107,7 +107,8 @@ typedef struct {
     float reserved2;
     /* MQE_NPC_SEESAW geometry (resources/objects/seesaw.urdf): [0..2] revolute-y joint origin rel. the fixed base,
      * [3] plank box / COM x offset in the plank frame, [4..6] plank half extents, [7..9] platform (base box) half extents,
-     * [10] column radius, [11] column length, [12] joint velocity limit [rad/s]; rest unused.
+     * [10] column radius, [11] column length (0: none), [12] joint velocity limit [rad/s], [13] hinge axis (0: y seesaw,
+     * 1: z revolving door, rotation_door.urdf), [14], [15] box centre y, z in the hinged frame.
      * MQE_NPC_BOX (resources/objects/box.urdf): [4..6] box half extents. */
     float npc_geom[16];
     uint64_t seed;

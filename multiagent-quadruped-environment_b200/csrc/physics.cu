@@ -210,8 +210,8 @@ __device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float 
     if (has_fix) {
         const float *g = p.geom;
         float px = x.x - fix.x, py = x.y - fix.y;
-        if (fabsf(px) <= g[7] && fabsf(py) <= g[8] && x.z >= fix.z) ground = fmaxf(ground, fix.z + g[9]);
-        if (x.z < fix.z && x.z > fix.z - g[11] - r) {
+        if (g[7] > 0.f && fabsf(px) <= g[7] && fabsf(py) <= g[8] && x.z >= fix.z) ground = fmaxf(ground, fix.z + g[9]);
+        if (g[10] > 0.f && x.z < fix.z && x.z > fix.z - g[11] - r) {
             float dh = sqrtf(px * px + py * py), gc = dh - g[10] - r;
             if (dh > 1e-6f && (!wall_ok || gc < gw)) { wall_ok = true; gw = gc; h.nw = mk(px / dh, py / dh, 0.f); }
         }
@@ -304,11 +304,13 @@ __device__ float npc_side(const DevParams &p, V3 r, V3 d, float *out) {
     out[9] = rxd.x * iI * up; out[10] = rxd.y * iI * up; out[11] = rxd.z * iI;
     out[12] = d.x * im; out[13] = d.y * im; out[14] = d.z * im;
     out[15] = out[16] = out[17] = 0.f;
-    if (p.npc_kind == MQE_NPC_SEESAW) {      // one revolute-y DOF about the pivot: only w_y responds, with 1 / I_pivot
-        const float iIp = 1.f / (p.npc_inertia + p.npc_mass * p.geom[3] * p.geom[3]);
+    if (p.npc_kind == MQE_NPC_SEESAW) {      // one revolute DOF about the pivot (seesaw: y, revolving door: z): only w_axis responds
+        const bool hz = p.geom[13] > 0.5f;
+        const float r2 = hz ? p.geom[3] * p.geom[3] + p.geom[14] * p.geom[14] : p.geom[3] * p.geom[3] + p.geom[15] * p.geom[15];
+        const float iIp = 1.f / (p.npc_inertia + p.npc_mass * r2);
 #pragma unroll
         for (int i = 9; i < 15; i++) out[i] = 0.f;
-        out[10] = rxd.y * iIp;
+        if (hz) out[11] = rxd.z * iIp; else out[10] = rxd.y * iIp;
     }
     float dd = 0.f;
     for (int i = 0; i < 6; i++) dd += out[i] * out[9 + i];
@@ -613,11 +615,15 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 for (int i = 0; i < 51; i++) rs[RS_FORCE + i] = 0.f;
             }
         } else if (is_npc && seesaw) {
-            // passive revolute-y plank: gravity torque r_x m g about the pivot, I_pivot = I_yy + m r_x^2
+            // passive revolute joint: y hinge (seesaw plank, gravity torque r_x m g) or z hinge (revolving door, no gravity torque);
+            // I_pivot = I_axis + m r_perp^2
             float sn, cs;
             sincosf(q[0], &sn, &cs);
-            const float Ip = p.npc_inertia + p.npc_mass * p.geom[3] * p.geom[3];
-            vb[1] = qd[0] + p.dt * (p.geom[3] * cs * p.npc_mass * (-p.gz)) / Ip;
+            const bool hz = p.geom[13] > 0.5f;
+            const float r2 = hz ? p.geom[3] * p.geom[3] + p.geom[14] * p.geom[14] : p.geom[3] * p.geom[3] + p.geom[15] * p.geom[15];
+            const float Ip = p.npc_inertia + p.npc_mass * r2;
+            const float tau_g = hz ? 0.f : p.geom[3] * cs * p.npc_mass * (-p.gz);
+            vb[hz ? 2 : 1] = qd[0] + p.dt * tau_g / Ip;
             ns[NS_ORIGIN] = pos.x + p.geom[0]; ns[NS_ORIGIN + 1] = pos.y + p.geom[1]; ns[NS_ORIGIN + 2] = pos.z + p.geom[2];
             ns[NS_CAP] = cs; ns[NS_CAP + 1] = sn;
             ((int *)ns)[NS_CNT] = 0;
@@ -753,7 +759,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         } else if (is_npc && active && seesaw) {
             int ncon = 0;
             const float cs = ns[NS_CAP], sn = ns[NS_CAP + 1];
-            for (int en = 0; en < 2; en++) {
+            for (int en = 0; en < 2 && !(p.geom[13] > 0.5f); en++) {
                 const float xe = p.geom[3] + (en == 0 ? -1.f : 1.f) * p.geom[4];
                 V3 r = mk(xe * cs, 0.f, -xe * sn);                       // plank end rel. the pivot
                 float gap = ns[NS_ORIGIN + 2] + r.z - p.geom[6] - p.floor_z;
@@ -962,8 +968,9 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 const float oh[3] = {p.geom[4], p.geom[5], p.geom[6]};
                 if (seesaw) {
                     const float cs = nsS[NS_CAP], sn = nsS[NS_CAP + 1];
-                    oex = mk(cs, 0.f, -sn); oey = mk(0.f, 1.f, 0.f); oez = mk(sn, 0.f, cs);
-                    oc = pivot + p.geom[3] * oex;
+                    if (p.geom[13] > 0.5f) { oex = mk(cs, sn, 0.f); oey = mk(-sn, cs, 0.f); oez = mk(0.f, 0.f, 1.f); }
+                    else { oex = mk(cs, 0.f, -sn); oey = mk(0.f, 1.f, 0.f); oez = mk(sn, 0.f, cs); }
+                    oc = pivot + p.geom[3] * oex + p.geom[14] * oey + p.geom[15] * oez;
                 } else {
                     oex = mk(nsS[NS_ROT], nsS[NS_ROT + 1], nsS[NS_ROT + 2]); oey = mk(nsS[NS_ROT + 3], nsS[NS_ROT + 4], nsS[NS_ROT + 5]);
                     oez = mk(nsS[NS_ROT + 6], nsS[NS_ROT + 7], nsS[NS_ROT + 8]);
@@ -1178,7 +1185,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         }
         if (is_npc && seesaw) {
             const float lim = p.geom[12];                                    // URDF joint velocity limit
-            qd[0] = fminf(fmaxf(vb[1], -lim), lim);
+            qd[0] = fminf(fmaxf(p.geom[13] > 0.5f ? vb[2] : vb[1], -lim), lim);
             q[0] += p.dt * qd[0];
         } else if (is_robot || is_npc) {
             wang = mk(vb[0], vb[1], vb[2]); vlin = mk(vb[3], vb[4], vb[5]);

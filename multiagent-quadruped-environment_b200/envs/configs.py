@@ -295,6 +295,31 @@ def Go1PushboxCfg() -> Cfg:
     return c
 
 
+def Go1RotationCfg() -> Cfg:
+    """go1_rotation_config.py (task go1revolvingdoor): a door panel on a vertical hinge stands in the gate opening."""
+    c = go1_base()
+    c.env.update(env_name="go1rotationCfg", num_envs=1, num_agents=2, num_npcs=1, num_actions_npc=1, episode_length_s=5)
+    c.asset.update(terminate_after_contacts_on=[], file_npc="{LEGGED_GYM_ROOT_DIR}/resources/objects/rotation_door.urdf",
+                   name_npc="rotation", npc_collision=True, fix_npc_base_link=True)
+    c.terrain.update(num_rows=1, num_cols=1, x_limits=[5.0], y_limits=[-1.5, 1.5], BarrierTrack_kwargs=_track(
+        options=["init", "wall", "gate", "wall"], randomize_obstacle_order=False, track_width=3.5,
+        init=dict(block_length=0, room_size=(0.0, 0.0), border_width=0.0, offset=(0, 0)),
+        gate=dict(block_length=5.0, width=2.0, depth=0.1, offset=(0, 0), random=(0, 0)),
+        rotation=dict(block_length=5, depth=0.1, offset=(0, 0), wide_px=(0.84, 0.2)),
+        wall=dict(block_length=0.1), wall_height=0.85))
+    c.command.cfg.vel = True
+    c.init_state.multi_init_state = True
+    c.init_state.init_states = [InitState(pos=(0.5, -1.0, 0.42)), InitState(pos=(0.5, 1.0, 0.42))]
+    c.init_state.init_states_npc = [InitState(pos=(2.59, -0.01, 0.04))]
+    c.init_state.default_npc_joint_angles = [0.0]
+    c.termination.update(termination_terms=["roll", "pitch", "z_low", "z_high"])
+    c.domain_rand.init_base_pos_range = None
+    c.domain_rand.init_npc_base_pos_range = None
+    c.rewards.scales = Cfg(punishment_scale=1, success_reward_scale=10, distance_reward_scale=1)
+    c.viewer.update(pos=[12.0, 20.0, 20.0], lookat=[13.0, 20.0, 0.0])
+    return c
+
+
 def _football_game(num_agents, init_xy, episode_length_s):
     """go1_football_config.py:133-371 (1 vs 1 and 2 vs 2): free-play football, ball at (7, 0, 0.2)."""
     c = go1_base()

@@ -9,7 +9,7 @@ import numpy as np
 
 from . import configs as C
 from .go1 import Go1, Go1FootballDefender, Go1Object, Go1Sheep
-from .wrappers import (EmptyWrapper, Go1FootballDefenderWrapper, Go1FootballGameWrapper, Go1GateWrapper, Go1PushboxWrapper,
+from .wrappers import (EmptyWrapper, Go1FootballDefenderWrapper, Go1FootballGameWrapper, Go1GateWrapper, Go1PushboxWrapper, Go1RotationWrapper,
                        Go1SeesawWrapper, Go1SheepWrapper)
 
 ENV_DICT = {
@@ -22,9 +22,10 @@ ENV_DICT = {
     "go1football-2vs2": {"class": Go1Object, "config": C.Go1Football2vs2Cfg, "wrapper": Go1FootballGameWrapper},
     "go1seesaw": {"class": Go1Object, "config": C.Go1SeesawCfg, "wrapper": Go1SeesawWrapper},
     "go1pushbox": {"class": Go1Object, "config": C.Go1PushboxCfg, "wrapper": Go1PushboxWrapper},
+    "go1revolvingdoor": {"class": Go1Object, "config": C.Go1RotationCfg, "wrapper": Go1RotationWrapper},
 }
 # tasks of the reference registry that are outside the hot-path scope of this round
-NOT_YET = ("go1tug", "go1wrestling", "go1revolvingdoor", "go1bridge")
+NOT_YET = ("go1tug", "go1wrestling", "go1bridge")
 
 
 def set_seed(seed):

@@ -370,3 +370,64 @@ class Go1PushboxWrapper(EmptyWrapper):
                 self._acc("box movement reward", torch.sum(r))
         self.last_box_pos = box_pos.clone()
         return obs, reward.repeat(1, self.num_agents), termination, info
+
+
+class Go1RotationWrapper(EmptyWrapper):
+    """go1_rotation_wrapper.py:8-103 (revolving door): obs = (pos, rpy) self / other with agent 1 mirrored in y (12);
+    reward on agent 0 only: success when agent 0 is past the door, punishment when agent 1 is, +1 whenever agent 0's
+    distance to the target shrank.  Returned reward is [N, A, 1] as in the reference.
+
+    Reference quirk kept: step() subtracts the (per-env, all equal) target x from BOTH x and y of every agent
+    (`dis[:, :] -= self.target_pos`, :77), which only broadcasts for num_envs <= 2 there; here the same arithmetic is
+    applied for any num_envs.  reset() (:38-39) subtracts it from x only."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(12,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.success_reward_scale = 5
+        self.distance_reward_scale = 1
+        self.punishment_scale = 1
+        self.reward_buffer = {"punishment": 0, "success reward": 0, "distance reward": 0, "step count": 0}
+
+    def _init_extras(self, obs):
+        kw = self.BarrierTrack_kwargs
+        self.target_pos = torch.full((self.env.num_envs,), kw["rotation"]["block_length"] * 0.75 + kw["wall"]["block_length"],
+                                     dtype=torch.float, device=self.env.device)
+        dis = obs.base_pos.reshape(self.env.num_envs, self.env.num_agents, -1)[:, :, :2].clone()
+        dis[:, :, 0] -= self.target_pos.unsqueeze(1)
+        self.last_dis = dis.norm(p=2, dim=-1)
+
+    def _obs(self, obs_buf):
+        base_info = self._base_info(obs_buf)
+        obs = torch.cat([base_info, torch.flip(base_info, [1])], dim=2)
+        obs[:, 1, 1::3] = -obs[:, 1, 1::3]                    # y and pitch of both halves, as seen by the mirrored agent
+        return obs
+
+    def reset(self):
+        obs_buf = self.env.reset()
+        self._init_extras(obs_buf)
+        return self._obs(obs_buf)
+
+    def step(self, action):
+        action[:, 1, 1:] = -action[:, 1, 1:]                  # in place, as the reference does; commutes with the clip
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        N, A = self.env.num_envs, self.env.num_agents
+        base_pos = obs_buf.base_pos.reshape(N, A, -1)
+        reward = torch.zeros([N, A], device=self.env.device)
+        if self.success_reward_scale != 0:
+            success = (base_pos[:, 0, 0] > self.target_pos) * float(self.success_reward_scale)
+            reward[:, 0] += success
+            self._acc("success reward", torch.sum(success))
+        if self.punishment_scale != 0:
+            punishment = (base_pos[:, 1, 0] > self.target_pos) * float(self.punishment_scale)
+            reward[:, 0] -= punishment
+            self._acc("punishment", torch.sum(punishment))
+        if self.distance_reward_scale != 0:
+            dis = (base_pos[:, :, :2] - self.target_pos.view(N, 1, 1)).norm(p=2, dim=-1)
+            dis_reward = (dis[:, 0] < self.last_dis[:, 0]) * float(self.distance_reward_scale)
+            reward[:, 0] += dis_reward
+            self._acc("distance reward", torch.sum(dis_reward))
+            self.last_dis = dis
+        self._acc("step count", 1)
+        return self._obs(obs_buf), reward.reshape(N, A, 1), termination, info

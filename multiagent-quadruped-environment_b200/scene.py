@@ -22,10 +22,14 @@ TASK_NPC = {            # npc asset -> (kind, ctrl, radius, half length of the c
     "ball": (E.NPC_RIGID, E.NPC_PASSIVE, 0.1, 0.0, 0.318, 0.00462),  # resources/objects/ball.urdf
     "seesaw": (E.NPC_SEESAW, E.NPC_PASSIVE, 0.0, 0.0, 100.0, 100.0), # resources/objects/seesaw.urdf
     "box": (E.NPC_BOX, E.NPC_PASSIVE, 0.0, 0.0, 6.0, 0.25),          # resources/objects/box.urdf (1 x 1 x 1 m, 6 kg)
+    "rotation": (E.NPC_SEESAW, E.NPC_PASSIVE, 0.0, 0.0, 4.0, 1.232),  # resources/objects/rotation_door.urdf (izz of the panel)
 }
+# rotation_door.urdf: joint "rot1" at the base origin, axis z, velocity limit 28; panel box 0.08 x 1.95 x 0.8 centred 0.4 above it
+DOOR_GEOM = [0.0, 0.0, 0.0, 0.0, 0.04, 0.975, 0.4, 0.0, 0.0, 0.0, 0.0, 0.0, 28.0, 1.0, 0.0, 0.4]
 BOX_GEOM = [0.0] * 4 + [0.5, 0.5, 0.5] + [0.0] * 9
 # resources/objects/seesaw.urdf: joint "link" origin (-2.4, 0, -0.455), axis y, velocity limit 0.2; plank box 4.123 x 1 x 0.03 at
-# x = -0.1031 (its COM too); fixed base box 1 x 1 x 0.03; column cylinder r 0.2, length 1 hanging below the base
+# x = -0.1031 (its COM too); fixed base box 1 x 1 x 0.03; column cylinder r 0.2, length 1 hanging below the base.
+# Layout: MqeSimDesc.npc_geom ([13] = hinge axis 0: y / 1: z, [3], [14], [15] = box centre in the hinged frame)
 SEESAW_GEOM = [-2.4, 0.0, -0.455, -0.1031, 4.123 / 2, 0.5, 0.015, 0.5, 0.5, 0.015, 0.2, 1.0, 0.2, 0.0, 0.0, 0.0]
 
 
@@ -221,7 +225,8 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     d.npc_mass, d.npc_inertia, d.npc_radius, d.npc_halflen = npc_m, npc_I, npc_r, npc_hl
     # pair-contact budget per env and substep: two robots alone rarely touch in more than a few capsule pairs
     d.max_pair_contacts = 8 if (A <= 2 and npc_kind == E.NPC_NONE) else 16
-    d.npc_geom[:] = SEESAW_GEOM if npc_kind == E.NPC_SEESAW else (BOX_GEOM if npc_kind == E.NPC_BOX else [0.0] * 16)
+    geom = {"seesaw": SEESAW_GEOM, "rotation": DOOR_GEOM, "box": BOX_GEOM}.get(cfg.asset.name_npc if P else "", [0.0] * 16)
+    d.npc_geom[:] = geom
     d.sheep_scale = float(getattr(cfg.asset, "sheep_movement_scale", 0.0))
     d.sheep_randomness = float(getattr(cfg.asset, "sheep_movement_randomness", 0.0))
     if d.defender:

@@ -553,8 +553,8 @@ static int probe_world(const Oracle *o, const real *x, real r, const real *fix, 
     if (fix) { /* seesaw.urdf statics: platform top is ground inside its footprint, the column is a vertical cylinder */
         const float *g = d->npc_geom;
         real px = x[0] - fix[0], py = x[1] - fix[1];
-        if (fabs(px) <= g[7] && fabs(py) <= g[8] && x[2] >= fix[2]) { real top = fix[2] + g[9]; if (top > ground) ground = top; }
-        if (x[2] < fix[2] && x[2] > fix[2] - g[11] - r) {
+        if (g[7] > 0 && fabs(px) <= g[7] && fabs(py) <= g[8] && x[2] >= fix[2]) { real top = fix[2] + g[9]; if (top > ground) ground = top; }
+        if (g[10] > 0 && x[2] < fix[2] && x[2] > fix[2] - g[11] - r) {
             real dh = sqrt(px * px + py * py), gc = dh - g[10] - r;
             if (dh > (real)1e-6 && (!wall_ok || gc < gw)) { wall_ok = 1; gw = gc; wn[0] = px / dh; wn[1] = py / dh; }
         }
@@ -668,9 +668,10 @@ static void group_jacobian(const Oracle *o, const EnvScratch *es, int g, int lin
          * response; the ball is a free sphere */
         real up = (o->d.npc_ctrl == MQE_NPC_SHEEP) ? 0 : 1;
         for (int i = 0; i < 3; i++) { J[i] = rxd[i]; J[3 + i] = dir[i]; Y[i] = rxd[i] * es->npc_minv[0] * (i < 2 ? up : 1); Y[3 + i] = dir[i] * es->npc_minv[1]; }
-        if (o->d.npc_kind == MQE_NPC_SEESAW) {   /* one revolute-y DOF about the pivot (= group origin): only w_y responds */
+        if (o->d.npc_kind == MQE_NPC_SEESAW) {   /* one revolute DOF about the pivot (= group origin): only w_axis responds */
+            int ax = o->d.npc_geom[13] > 0.5f ? 2 : 1;   /* seesaw: y, revolving door: z */
             memset(Y, 0, NV * sizeof(real));
-            Y[1] = rxd[1] * es->npc_minv[0];
+            Y[ax] = rxd[ax] * es->npc_minv[0];
         }
     }
 }
@@ -795,20 +796,27 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         }
     }
 
-    const int seesaw = P && d->npc_kind == MQE_NPC_SEESAW;
+    const int seesaw = P && d->npc_kind == MQE_NPC_SEESAW;      /* hinged box on a fixed base: seesaw plank (y) or revolving door (z) */
+    const int hz = seesaw && d->npc_geom[13] > 0.5f;            /* hinge axis z */
     real ss_c = 1, ss_s = 0;
+    real h_ex[3] = {1, 0, 0}, h_ey[3] = {0, 1, 0}, h_ez[3] = {0, 0, 1}, h_c[3] = {0, 0, 0};
     const real *ss_fix = NULL;
-    if (seesaw) {   /* resources/objects/seesaw.urdf: fixed base, plank on a passive revolute-y joint */
+    if (seesaw) {   /* resources/objects/seesaw.urdf, rotation_door.urdf: fixed base, box on a passive revolute joint */
         const float *gm = d->npc_geom;
         const real *rs = root + A * 13;
         real th = dof[(12 * A) * 2], thd = dof[(12 * A) * 2 + 1];
-        real Ip = d->npc_inertia + d->npc_mass * gm[3] * gm[3];
+        real cx = gm[3], cy = gm[14], cz = gm[15];
+        real r2 = hz ? cx * cx + cy * cy : cx * cx + cz * cz;      /* squared distance of the box centre (= COM) from the axis */
+        real Ip = d->npc_inertia + d->npc_mass * r2;
         ss_fix = rs;
         ss_c = cos(th); ss_s = sin(th);
         for (int i = 0; i < 3; i++) es.origin[A][i] = rs[i] + gm[i];
+        if (hz) { v3set(h_ex, ss_c, ss_s, 0); v3set(h_ey, -ss_s, ss_c, 0); v3set(h_ez, 0, 0, 1); }
+        else    { v3set(h_ex, ss_c, 0, -ss_s); v3set(h_ey, 0, 1, 0); v3set(h_ez, ss_s, 0, ss_c); }
+        for (int i = 0; i < 3; i++) h_c[i] = es.origin[A][i] + cx * h_ex[i] + cy * h_ey[i] + cz * h_ez[i];
         es.npc_minv[0] = 1 / Ip; es.npc_minv[1] = 0;
-        real tau_g = gm[3] * ss_c * d->npc_mass * (-d->gravity_z);       /* r_x m g about +y */
-        es.vel[A][1] = thd + dt * tau_g / Ip;
+        real tau_g = hz ? 0 : gm[3] * ss_c * d->npc_mass * (-d->gravity_z);       /* r_x m g about +y; none about a vertical axis */
+        es.vel[A][hz ? 2 : 1] = thd + dt * tau_g / Ip;
         es.ndof[A] = 6;
     }
 
@@ -936,7 +944,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         const float *gm = d->npc_geom;
         /* plank ends resting on the floor (local rows of the seesaw group) */
         int nloc = 0;
-        for (int en = 0; en < 2; en++) {
+        for (int en = 0; en < 2 && !hz; en++) {
             real xe = gm[3] + (en == 0 ? -1 : 1) * gm[4];
             real x[3] = {es.origin[A][0] + xe * ss_c, es.origin[A][1], es.origin[A][2] - xe * ss_s};
             real gap = x[2] - gm[6] - d->floor_z;
@@ -952,9 +960,8 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         stats[0] += nloc;
         /* robot probes on the plank: robot X ascending, probe table order */
         {
-            real ex[3] = {ss_c, 0, -ss_s}, ey[3] = {0, 1, 0}, ez[3] = {ss_s, 0, ss_c}, h[3] = {gm[4], gm[5], gm[6]}, c[3];
-            for (int i = 0; i < 3; i++) c[i] = es.origin[A][i] + gm[3] * ex[i];
-            npair = obb_probe_contacts(o, &es, md, c, ex, ey, ez, h, contacts, &nc, rows, &nr, npair, max_pair);
+            real h[3] = {gm[4], gm[5], gm[6]};
+            npair = obb_probe_contacts(o, &es, md, h_c, h_ex, h_ey, h_ez, h, contacts, &nc, rows, &nr, npair, max_pair);
         }
     }
     if (P && d->npc_kind == MQE_NPC_BOX) {   /* robot probes on the push box (resources/objects/box.urdf) */
@@ -984,7 +991,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
     }
 
     if (seesaw) {
-        real lim = d->npc_geom[12], thd = es.vel[A][1];
+        real lim = d->npc_geom[12], thd = es.vel[A][hz ? 2 : 1];
         thd = thd > lim ? lim : (thd < -lim ? -lim : thd);         /* URDF joint velocity limit */
         dof[(12 * A) * 2] += dt * thd;
         dof[(12 * A) * 2 + 1] = thd;

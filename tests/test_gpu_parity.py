@@ -23,7 +23,7 @@ from mqe_b200 import scene as S  # noqa: E402
 from mqe_b200.envs import configs as C  # noqa: E402
 
 TASKS = {"go1pushbox": C.Go1PushboxCfg, "go1gate": C.Go1GateCfg, "go1sheep-hard": C.NineSheepCfg, "go1sheep-easy": C.SingleSheepCfg,
-         "go1seesaw": C.Go1SeesawCfg, "go1football-defender": C.Go1FootballDefenderCfg, "go1plane": C.Go1PlaneCfg}
+         "go1revolvingdoor": C.Go1RotationCfg, "go1seesaw": C.Go1SeesawCfg, "go1football-defender": C.Go1FootballDefenderCfg, "go1plane": C.Go1PlaneCfg}
 
 
 def make_pair(task, n, mode=E.POLICY_FP32, seed=0, precision="f32"):
@@ -114,7 +114,7 @@ def _state_err(a_root, a_dof, b_root, b_dof):
             np.abs(a_dof[:, 0] - b_dof[:, 0]), np.abs(a_dof[:, 1] - b_dof[:, 1]))
 
 
-@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1pushbox"])
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1pushbox", "go1revolvingdoor"])
 def test_single_substep_parity(task):
     """Single physics substeps from IDENTICAL states, robots dropped onto the floor so foot / knee / pair contacts,
     joint limits and the actuator net are all active.  Truth = the fp64 oracle; the fp32 oracle (dense Cholesky) run
@@ -147,6 +147,18 @@ def test_single_substep_parity(task):
         root[on, 0, 0] = bx[on, 0] - 0.5 - 0.28 + 0.02 * (np.arange(n)[on] % 4); root[on, 0, 1] = bx[on, 1] - 0.2
         root[on, 1, 0] = bx[on, 0] + 0.1; root[on, 1, 1] = bx[on, 1] - 0.5 - 0.15
         root[on, 2, 2] = 0.52
+    if task == "go1revolvingdoor":   # half of the envs: one robot pressed on each face of the (already turning) door panel
+        n = sc.num_envs
+        on = np.arange(n) % 2 == 0
+        dofs = o64.get(E.BUF_DOF_STATES).reshape(n, -1, 2).copy()
+        dofs[:, 24, 0] = np.linspace(-0.3, 0.3, n); dofs[:, 24, 1] = np.linspace(-1.0, 1.0, n)
+        hinge = root[:, 2, :3]
+        root[on, 0, 0] = hinge[on, 0] - 0.04 - 0.28 + 0.02 * (np.arange(n)[on] % 4); root[on, 0, 1] = hinge[on, 1] - 0.55
+        root[on, 1, 0] = hinge[on, 0] + 0.04 + 0.28 - 0.02 * (np.arange(n)[on] % 3); root[on, 1, 1] = hinge[on, 1] + 0.55
+        root[on, 1, 3:7] = (0.0, 0.0, 1.0, 0.0)                                       # facing -x, nose on the far face
+        for o in (o32, o64):
+            o.set(E.BUF_DOF_STATES, dofs)
+        eng.tensor(E.BUF_DOF_STATES).copy_(dev(dofs).view_as(eng.tensor(E.BUF_DOF_STATES)))
     o64.set(E.BUF_ROOT_STATES, root)
     a = np.clip(np.random.default_rng(1).normal(0, 1.0, size=(sc.num_envs * sc.num_agents * 12,)), -3, 3).astype(np.float32)
     for o in (o32, o64):
@@ -180,14 +192,14 @@ def test_single_substep_parity(task):
         assert pg[1] <= max(3.0 * pf[1], 1e-5), (name, pg, pf)           # as accurate as the fp32 restatement
         assert pg[2] <= max(5.0 * pf[2], 1e-4), (name, pg, pf)
     print(task, "contact-force err / max force:", cf_err, "contacts seen", total_contacts, "last stats", st_o[:4])
-    if task in ("go1seesaw", "go1pushbox"):
+    if task in ("go1seesaw", "go1pushbox", "go1revolvingdoor"):
         assert st_o[2] > 0, "no robot-on-box contacts were exercised"
     assert cf_err < 3e-2, cf_err
     eng.close()
 
 
 @pytest.mark.parametrize("mode", [E.POLICY_FP32, E.POLICY_BF16X3], ids=["fp32", "tcgen05-bf16x3"])
-@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1pushbox"])
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1pushbox", "go1revolvingdoor"])
 def test_short_trajectory_parity(task, mode):
     """Full Go1.step() x 5 from reset on identical seeds and actions (tensor-core mode: steps 3.. are CUDA-graph replays)."""
     sc, eng, orc = make_pair(task, 32, mode)
@@ -315,7 +327,7 @@ def test_env_surface_go1gate():
 
 
 @pytest.mark.parametrize("task,D,A", [("go1sheep-hard", 34, 2), ("go1sheep-easy", 18, 2), ("go1seesaw", 14, 2), ("go1football-defender", 20, 2),
-                                      ("go1pushbox", 22, 2)])
+                                      ("go1pushbox", 22, 2), ("go1revolvingdoor", 12, 2)])
 def test_env_surface_wrappers(task, D, A):
     from types import SimpleNamespace
     from mqe_b200.envs import make_mqe_env, custom_cfg
@@ -327,7 +339,7 @@ def test_env_surface_wrappers(task, D, A):
     for s in range(3):
         a = torch.rand((16, A, 3), device="cuda:0") * 2 - 1
         obs, rew, done, info = env.step(a)
-    assert obs.shape == (16, A, D) and rew.shape == (16, A) and done.shape == (16,)
+    assert obs.shape == (16, A, D) and rew.shape[:2] == (16, A) and done.shape == (16,)      # revolving door: [N, A, 1]
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
     assert float(env.reward_buffer["step count"]) == 3
     env.close()

@@ -16,6 +16,7 @@ CASES = {
     "go1seesaw": (W.Go1SeesawWrapper, C.Go1SeesawCfg, 2, 1),
     "go1football-defender": (W.Go1FootballDefenderWrapper, C.Go1FootballDefenderCfg, 3, 1),
     "go1pushbox": (W.Go1PushboxWrapper, C.Go1PushboxCfg, 2, 1),
+    "go1revolvingdoor": (W.Go1RotationWrapper, C.Go1RotationCfg, 2, 1),
 }
 
 
@@ -72,7 +73,7 @@ def test_wrapper_matches_reference_code(task, golden_dir):
     assert np.allclose(obs0.numpy(), z["obs_reset"], rtol=1e-6, atol=1e-6)
     T = z["obs"].shape[0]
     for t in range(T):
-        obs, rew, done, info = w.step(torch.as_tensor(z["in_actions"][t]))
+        obs, rew, done, info = w.step(torch.as_tensor(z["in_actions"][t]).clone())
         assert np.allclose(obs.numpy(), z["obs"][t], rtol=1e-6, atol=1e-6), (task, t)
         assert np.allclose(rew.numpy(), z["reward"][t], rtol=1e-5, atol=1e-5), (task, t, np.abs(rew.numpy() - z["reward"][t]).max())
         assert torch.equal(done, torch.as_tensor(z["in_reset"][t + 1]))

@@ -145,7 +145,7 @@ def run(task, wrapper_cls, cfg, A, P, seed, with_gate=False, T=6, N=5):
     out = {"obs_reset": obs0.numpy() if torch.is_tensor(obs0) else np.zeros(0)}
     obs_l, rew_l = [], []
     for t in range(T):
-        obs, rew, done, info = w.step(torch.as_tensor(rec["actions"][t]))
+        obs, rew, done, info = w.step(torch.as_tensor(rec["actions"][t]).clone())     # the rotation wrapper flips signs in place
         obs_l.append(obs.numpy().copy() if torch.is_tensor(obs) else np.zeros(0))
         rew_l.append(rew.numpy().copy() if torch.is_tensor(rew) else np.zeros(0))
         assert torch.equal(done, torch.as_tensor(rec["reset"][t + 1]))
@@ -174,6 +174,8 @@ def main():
     run("go1seesaw", seesaw, C.Go1SeesawCfg(), 2, 1, 3)
     run("go1football-defender", fb.Go1FootballDefenderWrapper, C.Go1FootballDefenderCfg(), 3, 1, 4, with_gate=True)
     run("go1pushbox", load("go1_pushbox_wrapper").Go1PushboxWrapper, C.Go1PushboxCfg(), 2, 1, 5)
+    # the reference's rotation wrapper only broadcasts for num_envs <= 2 (go1_rotation_wrapper.py:77)
+    run("go1revolvingdoor", load("go1_rotation_wrapper").Go1RotationWrapper, C.Go1RotationCfg(), 2, 1, 6, N=2, T=12)
 
 
 if __name__ == "__main__":
