@@ -31,8 +31,6 @@ struct MqeSim {
     PolicyWeightsDev pw;
     PolicyScratch ps;
     PolicyTcWeights tcw = {};
-    unsigned int *pair_table = nullptr;
-    int n_pair = 0;
     unsigned int step_count = 0;
     int head = MQE_HIST_FRAMES - 1;      // slot of the newest frame; the next frame goes to (head + 1) % 30
     long long launches = 0;
@@ -156,7 +154,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     p.sdf_nx = d->sdf_nx; p.sdf_ny = d->sdf_ny; p.sdf_cell = d->sdf_cell;
     if (!d->h_sdf || !d->h_env_origins || !d->h_agent_origins || !d->h_base_init_state) return fail(MQE_ERR_INVALID, "descriptor host arrays missing");
     if (P && !d->h_npc_init_state) return fail(MQE_ERR_INVALID, "h_npc_init_state missing");
-    if (mqe_substeps_smem_bytes(A, p.Pd, p.E, s->maxpair) > (size_t)prop.sharedMemPerBlockOptin)
+    if (mqe_substeps_smem_bytes(N, A, p.Pd, p.E, s->maxpair) > (size_t)prop.sharedMemPerBlockOptin)
         return fail(MQE_ERR_UNSUPPORTED, "substep kernel working set exceeds shared memory for this A/P");
 
     // ---- constants ----
@@ -210,24 +208,6 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
         int rc = mqe_policy_tc_prepare(&w, M, &s->tcw, s->stream);
         if (rc != 0) return fail(MQE_ERR_CUDA, "tensor-core policy weight preparation failed");
     }
-    // pair table: groups X < Y, capsule i of X, capsule j of Y -- the oracle's loop order (mqe_oracle.c env_substep)
-    {
-        std::vector<unsigned int> pt;
-        const int Gd = A + (d->npc_kind == MQE_NPC_RIGID ? P : 0), nc = d->model.n_caps;    // capsule groups only
-        for (int X = 0; X < Gd; X++)
-            for (int Y = X + 1; Y < Gd; Y++) {
-                int nx = X < A ? nc : 1, ny = Y < A ? nc : 1;
-                for (int i = 0; i < nx; i++)
-                    for (int j = 0; j < ny; j++) pt.push_back((unsigned)X | ((unsigned)i << 8) | ((unsigned)Y << 16) | ((unsigned)j << 24));
-            }
-        s->n_pair = (int)pt.size();
-        const unsigned int *dpt = nullptr;
-        if (pt.empty()) pt.push_back(0u);
-        CK(dupload(s, &dpt, pt.data(), pt.size()));
-        CK(cudaStreamSynchronize(s->stream));
-        s->pair_table = const_cast<unsigned int *>(dpt);
-    }
-
     // ---- state ----
     CK(dalloc(s, &p.root, (size_t)N * G * 13)); CK(dalloc(s, &p.dof, (size_t)N * (12 * A + D) * 2));
     CK(dalloc(s, &p.contact, (size_t)N * p.NB * 3));
@@ -243,6 +223,11 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     CK(dalloc(s, &p.r_term, (size_t)N)); CK(dalloc(s, &p.p_term, (size_t)N)); CK(dalloc(s, &p.zl_term, (size_t)N)); CK(dalloc(s, &p.zh_term, (size_t)N));
     CK(dalloc(s, &p.episode, (size_t)N)); CK(dalloc(s, &p.hist_dirty, (size_t)N)); CK(dalloc(s, &p.stats, (size_t)8));
     CK(dalloc(s, &p.ctr, (size_t)4));
+    CK(dalloc(s, &p.warp_trace, (size_t)((N + p.E - 1) / p.E) * MQE_TRACE_COLS));
+    { const char *e = getenv("MQE_TRACE"); p.trace = (e && e[0] == '1') ? 1 : 0; }
+    CK(dalloc(s, &p.row_scratch, mqe_substeps_row_scratch_floats(N, A), false));
+    CK(dalloc(s, &p.prow_scratch, mqe_substeps_prow_scratch_floats(N, s->maxpair), false));
+    CK(dalloc(s, &p.pdesc_scratch, mqe_substeps_pdesc_scratch_floats(N, s->maxpair), false));
     const size_t ring = (size_t)M * MQE_HIST_FRAMES * MQE_HIST_PAD;
     CK(dalloc(s, &p.hist_f32, ring));
     const size_t ring_tc = (size_t)((M + 127) / 128) * 128 * MQE_HIST_FRAMES * MQE_HIST_PAD;     // pre-tiled planes, rows padded to 128
@@ -303,6 +288,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     set_buf(s, MQE_BUF_SHEEP_STATS, p.sheep_stats, 4, N, 3);
     set_buf(s, MQE_BUF_STATS, p.stats, 4, 8);
     set_buf(s, MQE_BUF_CLOCK, p.clock, 4, M, 4);
+    set_buf(s, MQE_BUF_WARP_TRACE, p.warp_trace, 8, (N + p.E - 1) / p.E, MQE_TRACE_COLS);
     return MQE_OK;
 }
 
@@ -386,7 +372,7 @@ static int substeps_impl(MqeSim *s, int count, bool zero_stats) {
     if (!s || count <= 0) return fail(MQE_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(s->device));
     if (zero_stats) CK(cudaMemsetAsync(s->p.stats, 0, 8 * sizeof(int), s->stream));   // inside mqe_sim_step k_policy_finish did it
-    CK(mqe_launch_substeps(s->p, count, s->maxpair, s->pair_table, s->n_pair, s->stream));
+    CK(mqe_launch_substeps(s->p, count, s->maxpair, s->stream));
     s->launches += 1;
     return MQE_OK;
 }

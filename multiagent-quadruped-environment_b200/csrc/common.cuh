@@ -15,6 +15,7 @@
 #define MQE_ROBOT_BOUND 0.60f
 #define MQE_HIST_PAD 80          // one 70-float frame padded to 5 x 16 for the tensor-core K loop
 #define MQE_NV 18
+#define MQE_TRACE_COLS 12       // start ns, end ns, pair contacts, widest row count, cycles of P1..P5, integrate, prologue, epilogue
 
 struct DevParams {
     int N, A, P, D, G;            // envs (local), agents, npcs, npc dofs per env, actors per env (A+P)
@@ -50,6 +51,9 @@ struct DevParams {
     unsigned char *reset_buf, *timeout_buf, *collide_buf, *r_term, *p_term, *zl_term, *zh_term;
     unsigned int *episode;
     unsigned char *hist_dirty;    // [N] history must be zeroed before the next frame is appended (go1.py:141-145)
+    float *row_scratch, *prow_scratch, *pdesc_scratch;   // k_substeps: local / pair constraint rows that do not fit in shared memory
+    long long *warp_trace;        // [ceil(N/E)][MQE_TRACE_COLS] k_substeps per-warp trace
+    int trace;                    // MQE_TRACE=1: also accumulate per-phase cycles into the trace rows
     int *stats;                   // [8]
     int *ctr;                     // device-side step counters: [0] ring slot that receives the next frame, [1] policy steps done
                                   // (sheep RNG key), [2] scratch (blocks of k_post_physics finished); let a captured CUDA graph of

@@ -18,7 +18,7 @@ struct PolicyTcWeights {            // bf16 hi/lo planes, pre-tiled (policy_tc.c
 struct PolicyScratch { float *Z, *T1, *T2, *T3, *latent, *act; };
 
 extern "C" {
-cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, const unsigned int *pair_table, int n_pair_entries, cudaStream_t st);
+cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, cudaStream_t st);
 cudaError_t mqe_launch_post(const DevParams &p, unsigned int step_count, cudaStream_t st);
 cudaError_t mqe_launch_reset_all(const DevParams &p, cudaStream_t st);
 cudaError_t mqe_launch_set_root_indexed(const DevParams &p, const float *src, const int *ids, int n, cudaStream_t st);
@@ -35,5 +35,8 @@ cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat
                                     int head, int rows, int passes, float *Z, int planes_out, const int *ctr, cudaStream_t st);
 cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, int M, int passes,
                                       cudaStream_t st, int *launches);
-size_t mqe_substeps_smem_bytes(int A, int Pd, int E, int maxpair);
+size_t mqe_substeps_smem_bytes(int N, int A, int Pd, int E, int maxpair);
+size_t mqe_substeps_row_scratch_floats(int N, int A);
+size_t mqe_substeps_prow_scratch_floats(int N, int maxpair);
+size_t mqe_substeps_pdesc_scratch_floats(int N, int maxpair);
 }

@@ -28,7 +28,9 @@
 #define RS_CNT 318     // int scratch
 #define RS_BOUND 319   // true bounding radius of the robot's capsules about its origin (this substep)
 #define RS_ROWS 320
-#define RS_CMETA (RS_ROWS + MQE_MAX_ROWS * ROWF)
+#define SROWS 19       // local rows of a robot kept in shared memory; rows past that (a robot lying on the ground) go to a
+                       // per-robot global scratch with the same arithmetic -- shared memory per env sets the residency
+#define RS_CMETA (RS_ROWS + SROWS * ROWF)
 #define RS_FORCE (RS_CMETA + MQE_MAX_LOCAL * 4)
 #define RS_SIZE (RS_FORCE + 52)
 // per-npc shared block
@@ -44,15 +46,16 @@
 // per-env shared block
 #define ES_CNT 0
 #define ES_ROWS 4
-#define ES_CMETA(maxpair) (ES_ROWS + (maxpair) * 3 * PROWF)
-#define ES_MASK(maxpair) (ES_CMETA(maxpair) + (maxpair) * 8)      // int capmask[G][G]: capsules of X within reach of group Y
-#define ES_SIZE(maxpair, G) (ES_MASK(maxpair) + (((G) * (G) + 3) & ~3))
+// the first `spair` pair contacts keep their rows in shared memory, the rest (up to maxpair) in a per-env global scratch
+#define ES_MASK(spair) (ES_ROWS + (spair) * 3 * PROWF)      // int capmask[G][G]: capsules of X within reach of group Y
+#define ES_SIZE(spair, G) (ES_MASK(spair) + (((G) * (G) + 3) & ~3))
+#define PDESCF 12      // pair-contact descriptor (global scratch): n3, body a, body b, point3, gap, packed (X, ci, Y, cj)
 
 #define ACTW_FLOATS 1316   // 192 + 32 + 1024 + 32 + 32 + 1 = 1313, padded
 #define TBL_INTS 80        // per-leg probe lists [4][10] (count + 9 ids), per-leg capsule lists [4][10]
 
-__host__ __device__ inline int physics_warp_smem_floats(int A, int P, int E, int maxpair) {
-    return E * A * RS_SIZE + E * P * NS_SIZE + E * ES_SIZE(maxpair, A + P);
+__host__ __device__ inline int physics_warp_smem_floats(int A, int P, int E, int spair, int maxpair) {
+    return E * A * RS_SIZE + E * P * NS_SIZE + E * ES_SIZE(spair, A + P);
 }
 __host__ __device__ inline int physics_cta_header_floats() { return (int)(sizeof(MqeRobotModel) / 4) + ACTW_FLOATS + TBL_INTS; }
 
@@ -198,10 +201,14 @@ __device__ __forceinline__ float softsign(float x) {
 struct ProbeHit { int mask; float gap_f, gap_w; V3 nw; };
 // `fix`: position of the seesaw's fixed base when the env has one (platform top is ground inside its footprint, the column
 // below it is a vertical cylinder that competes with the wall footprint for the wall-like contact); seesaw.urdf.
-__device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float r, bool has_fix = false, V3 fix = V3{0.f, 0.f, 0.f}) {
+// `far`: the caller has proved sdf(x) - r >= contact offset (wall_is_far below), so the four SDF loads are skipped; every
+// output that matters is the same as with the real sample (no wall bit, not inside the footprint).
+__device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float r, bool has_fix = false, V3 fix = V3{0.f, 0.f, 0.f}, bool far = false) {
     ProbeHit h;
     h.mask = 0;
-    SdfSample s = sdf_sample(p, x.x, x.y);
+    SdfSample s;
+    if (far) { s.sdf = 1.0e3f; s.gx = 0.f; s.gy = 0.f; }
+    else s = sdf_sample(p, x.x, x.y);
     bool inside = s.sdf < 0.f, above = x.z >= p.wall_top;
     float ground = (inside && above) ? p.wall_top : p.floor_z;
     float gw = s.sdf - r, gn = sqrtf(s.gx * s.gx + s.gy * s.gy);
@@ -221,6 +228,13 @@ __device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float 
     h.gap_w = gw;
     if (wall_ok && gw < p.coff) h.mask |= 2;
     return h;
+}
+
+// Wall cull.  The SDF grid is a Euclidean distance transform (1-Lipschitz); its bilinear interpolant has |grad| <= sqrt(2).
+// With sdf_o sampled at the robot origin, a probe whose centre is xr (relative to the origin) and radius r cannot reach a wall,
+// nor be inside the footprint, if sdf_o - 1.5 |xr_xy| - r - 2 cells > contact offset.
+__device__ __forceinline__ bool wall_is_far(const DevParams &p, float sdf_o, V3 xr, float r) {
+    return sdf_o - 1.5f * sqrtf(xr.x * xr.x + xr.y * xr.y) - r - 2.f * p.sdf_cell > p.coff;
 }
 
 // sphere (centre x, radius r) vs an oriented box (centre c, axes ex ey ez, half extents h); normal box -> sphere.
@@ -336,7 +350,7 @@ __device__ __forceinline__ float robot_side_regs(int k, V3 r, V3 d, V3 a1, V3 a2
     return dd;
 }
 
-__global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int maxpair, const unsigned int *__restrict__ pair_table, int n_pair_entries) {
+__global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int maxpair, int spair) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -378,9 +392,24 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
     const bool box = p.npc_kind == MQE_NPC_BOX;         // the NPC lane is a free box (box.urdf)
     const bool obb = seesaw || box;                     // robot probes collide with an oriented box instead of capsules
     const int Gc = obb ? A : G;                         // groups that take part in the capsule / capsule phase
-    float *wbase = smem + physics_cta_header_floats() + warp * physics_warp_smem_floats(A, P, E, maxpair);
+    float *wbase = smem + physics_cta_header_floats() + warp * physics_warp_smem_floats(A, P, E, spair, maxpair);
     const int first_env = (blockIdx.x * nwarps + warp) * E;
     if (first_env >= p.N) return;
+    long long t_start;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    // optional per-phase cycle trace (MQE_TRACE=1): lane 0 accumulates clock deltas straight into the warp's trace row
+    long long *const tr = p.warp_trace + (size_t)(first_env / E) * MQE_TRACE_COLS;
+    unsigned t_phase = 0;
+    if (p.trace && lane == 0) {
+        for (int i = 4; i < MQE_TRACE_COLS; i++) tr[i] = 0;
+        t_phase = (unsigned)clock();
+    }
+#define PHASE_MARK(k)                                                                   \
+    if (p.trace && lane == 0) {                                                         \
+        const unsigned now_ = (unsigned)clock();                                        \
+        tr[4 + (k)] += (long long)(now_ - t_phase);                                     \
+        t_phase = now_;                                                                 \
+    }
 
     // ---- lane roles ----
     const int nrl = 4 * A * E;
@@ -394,7 +423,13 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
     const int grp = is_robot ? ag : A + pn;                              // group index inside the env
     float *rs = wbase + (e_loc * A + ag) * RS_SIZE;                      // my robot block
     float *ns = wbase + E * A * RS_SIZE + (e_loc * P + pn) * NS_SIZE;    // my npc block
-    float *es = wbase + E * A * RS_SIZE + E * P * NS_SIZE + e_loc * ES_SIZE(maxpair, G);
+    float *es = wbase + E * A * RS_SIZE + E * P * NS_SIZE + e_loc * ES_SIZE(spair, G);
+    // row stores: shared memory first, global scratch for the overflow (generic pointers; same layout in both)
+    float *const grows = p.row_scratch + (size_t)(env * A + ag) * ((MQE_MAX_ROWS - SROWS) * ROWF);
+    float *const gprows = p.prow_scratch + (size_t)env * ((size_t)(maxpair - spair) * 3 * PROWF);
+    float *const pdesc = p.pdesc_scratch + (size_t)env * ((size_t)maxpair * PDESCF);
+    auto lrow = [&](int i) -> float * { return i < SROWS ? rs + RS_ROWS + i * ROWF : grows + (i - SROWS) * ROWF; };
+    auto prow = [&](int i) -> float * { return i < 3 * spair ? es + ES_ROWS + i * PROWF : gprows + (i - 3 * spair) * PROWF; };
     const unsigned quad_mask = is_robot ? (0xFu << (lane & ~3)) : (1u << lane);
     unsigned env_mask = 0;
     {
@@ -438,6 +473,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
     }
     int stat_local = 0, stat_lim = 0, stat_pair = 0, stat_rows = 0;
 
+    PHASE_MARK(6);
     for (int sub = 0; sub < nsub; sub++) {
         const bool last = (sub == nsub - 1);
         // ================================================================ P1: actuator network (go1.py:315-354, 369-380)
@@ -499,6 +535,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             }
         }
 
+        PHASE_MARK(0);
         // ================================================================ P2: kinematics + dynamics (robot lanes), npc prediction
         float vb[6] = {0, 0, 0, 0, 0, 0}, u[3] = {0, 0, 0};   // solve coordinates
         float Gm[18];                                           // my leg's G (6x3 row-major)
@@ -647,6 +684,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         if (rank_in_env == 0) ((int *)es)[ES_CNT] = 0;
         __syncwarp();
 
+        PHASE_MARK(1);
         // ================================================================ P3: rows.  joint limits, then world contacts
         int nrows = 0, nlim = 0;
         if (is_robot) {
@@ -679,7 +717,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 float dd = hk[k];
 #pragma unroll
                 for (int i = 0; i < 6; i++) dd += Jb[i] * Yb[i];
-                float *row = rs + RS_ROWS + slot * ROWF;
+                float *row = lrow(slot);
 #pragma unroll
                 for (int i = 0; i < 6; i++) { row[i] = Jb[i]; row[9 + i] = Yb[i]; }
 #pragma unroll
@@ -688,6 +726,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 row[21] = __int_as_float(leg | (0 << 4) | (slot << 8));
             }
             // ---- world contacts: pass 1 flags ----
+            const float sdf_o = active ? sdf_sample(p, pos.x, pos.y).sdf : 0.f;     // same address in all four lanes of the quad
             unsigned long long cm = 0ull;
             const int *pl_ = tbl + leg * 10;
             if (active)
@@ -698,8 +737,8 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     const int k = link == 0 ? 0 : link - 3 * leg;
                     const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
                     V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
-                    V3 xw = pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
-                    ProbeHit h = probe_world(p, xw, pr[5], seesaw, fixb);
+                    V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
+                    ProbeHit h = probe_world(p, pos + xr, pr[5], seesaw, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
                     cm |= (unsigned long long)h.mask << (2 * pi);
                 }
             unsigned long long call = cm;
@@ -720,7 +759,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
                 V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
                 V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));            // probe centre rel. O
-                ProbeHit h = probe_world(p, pos + xr, pr[5], seesaw, fixb);
+                ProbeHit h = probe_world(p, pos + xr, pr[5], seesaw, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
                 V3 n = kind ? h.nw : mk(0, 0, 1);
                 float gap = kind ? h.gap_w : h.gap_f;
                 V3 r = xr - (pr[5] + 0.5f * gap) * n;                     // contact point rel. O
@@ -744,7 +783,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     float dd = Jl[0] * Yl[0] + Jl[1] * Yl[1] + Jl[2] * Yl[2];
 #pragma unroll
                     for (int i = 0; i < 6; i++) dd += Jb[i] * Yb[i];
-                    float *row = rs + RS_ROWS + (r0 + dch) * ROWF;
+                    float *row = lrow(r0 + dch);
 #pragma unroll
                     for (int i = 0; i < 6; i++) { row[i] = Jb[i]; row[9 + i] = Yb[i]; }
 #pragma unroll
@@ -814,6 +853,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         }
         __syncwarp();
 
+        PHASE_MARK(2);
         // ================================================================ P3b: dynamic-vs-dynamic pairs (capsule / capsule)
         int npair = 0;
         if (G > 1 && (is_robot || is_npc)) {
@@ -866,7 +906,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 // capsule culling: bit ci of capmask[X][Y] = capsule ci of group X reaches into the true bounding sphere of
                 // group Y (+ contact offset).  A pair (X,ci,Y,cj) can only touch if both bits are set, so the narrow phase
                 // below skips everything else -- exact, it never drops a pair the full enumeration would accept.
-                int *capmask = reinterpret_cast<int *>(es + ES_MASK(maxpair));
+                int *capmask = reinterpret_cast<int *>(es + ES_MASK(spair));
                 bool live_any = false;
                 for (int Y = 0; Y < Gc; Y++) {
                     if (Y == grp || grp >= Gc) continue;
@@ -901,64 +941,83 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                 if (env >= p.N) live_any = false;
                 __syncwarp(env_mask);
                 const bool any_live = __ballot_sync(env_mask, live_any) != 0u;
-                if (any_live)
-                for (int t0 = 0; t0 < n_pair_entries; t0 += lanes_per_env) {
-                    int t = t0 + rank_in_env;
-                    bool hit = false;
-                    V3 cn = mk(0, 0, 0), cpos = mk(0, 0, 0);
-                    float cgap = 0.f;
-                    int X = 0, Y = 0, ci = 0, cj = 0;
-                    if (t < n_pair_entries) {
-                        unsigned ent = __ldg(pair_table + t);
-                        X = ent & 0xff; ci = (ent >> 8) & 0xff; Y = (ent >> 16) & 0xff; cj = ent >> 24;
-                        const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
-                        const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
-                        const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
-                        float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
-                        float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
-                        if (dx * dx + dy * dy + dz * dz <= lim * lim && ((capmask[X * G + Y] >> ci) & 1) && ((capmask[Y * G + X] >> cj) & 1)) {
-                            const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
-                            V3 c1, c2;
-                            seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
-                            V3 dv = c1 - c2;
-                            float dist = sqrtf(dot(dv, dv));
-                            cgap = dist - ca[6] - cb[6];
-                            if (cgap < p.coff && dist >= 1e-9f) {
-                                hit = true;
-                                cn = (1.f / dist) * dv;
-                                cpos = c2 + (cb[6] + 0.5f * cgap) * cn;
+                if (any_live) {
+                    // ---- narrow phase.  Candidates are enumerated from the masks -- capsule ci of X (bit set in mask[X][Y])
+                    // against capsule cj of Y (bit set in mask[Y][X]), groups X < Y, ci then cj ascending: the oracle's loop
+                    // order restricted to pairs that can touch, so contact slots come out in the same canonical order.
+                    // Hits only record a descriptor; rows are built afterwards by all lanes of the env.
+                    for (int X = 0; X < Gc - 1; X++)
+                        for (int Y = X + 1; Y < Gc; Y++) {
+                            const unsigned mXY = (unsigned)capmask[X * G + Y], mYX = (unsigned)capmask[Y * G + X];
+                            if (!mXY || !mYX) continue;                                  // uniform over the env's lanes
+                            const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
+                            const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
+                            const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
+                            const float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
+                            const float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
+                            if (!(dx * dx + dy * dy + dz * dz <= lim * lim)) continue;
+                            const int ny = __popc(mYX), ncombo = __popc(mXY) * ny;
+                            for (int t0 = 0; t0 < ncombo; t0 += lanes_per_env) {
+                                const int c = t0 + rank_in_env;
+                                bool hit = false;
+                                V3 cn = mk(0, 0, 0), cpos = mk(0, 0, 0);
+                                float cgap = 0.f;
+                                int ci = 0, cj = 0;
+                                if (c < ncombo) {
+                                    ci = __fns(mXY, 0, c / ny + 1); cj = __fns(mYX, 0, c % ny + 1);
+                                    const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
+                                    V3 c1, c2;
+                                    seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
+                                    V3 dv = c1 - c2;
+                                    float dist = sqrtf(dot(dv, dv));
+                                    cgap = dist - ca[6] - cb[6];
+                                    if (cgap < p.coff && dist >= 1e-9f) {
+                                        hit = true;
+                                        cn = (1.f / dist) * dv;
+                                        cpos = c2 + (cb[6] + 0.5f * cgap) * cn;
+                                    }
+                                }
+                                const unsigned hb = __ballot_sync(env_mask, hit);
+                                const int slot = npair + __popc(hb & ((1u << lane) - 1u));
+                                npair += __popc(hb);
+                                if (hit && slot < maxpair) {
+                                    float *ds = pdesc + slot * PDESCF;
+                                    const int rba = X < A ? X * MQE_NUM_BODIES + (int)md->caps[ci][1] : A * MQE_NUM_BODIES + (X - A);
+                                    const int rbb = Y < A ? Y * MQE_NUM_BODIES + (int)md->caps[cj][1] : A * MQE_NUM_BODIES + (Y - A);
+                                    ds[0] = cn.x; ds[1] = cn.y; ds[2] = cn.z; ds[3] = __int_as_float(rba); ds[4] = __int_as_float(rbb);
+                                    ds[5] = cpos.x; ds[6] = cpos.y; ds[7] = cpos.z; ds[8] = cgap;
+                                    ds[9] = __int_as_float(X | (ci << 8) | (Y << 16) | (cj << 24));
+                                }
                             }
                         }
-                    }
-                    unsigned hb = __ballot_sync(env_mask, hit);
-                    int slot = npair + __popc(hb & ((1u << lane) - 1u));
-                    npair += __popc(hb);
-                    if (hit && slot < maxpair) {
+                    npair = min(npair, maxpair);
+                    __syncwarp(env_mask);
+                    // ---- rows: one (contact, direction) per lane and round instead of all six sides in the lane that found the hit
+                    for (int item = rank_in_env; item < 3 * npair; item += lanes_per_env) {
+                        const int slot = item / 3, dch = item - 3 * slot;
+                        const float *ds = pdesc + slot * PDESCF;
+                        const V3 cn = mk(ds[0], ds[1], ds[2]), cpos = mk(ds[5], ds[6], ds[7]);
+                        const float cgap = ds[8];
+                        const unsigned ent = (unsigned)__float_as_int(ds[9]);
+                        const int X = ent & 0xff, ci = (ent >> 8) & 0xff, Y = (ent >> 16) & 0xff, cj = ent >> 24;
                         V3 t1, t2;
                         tangent_basis(cn, t1, t2);
                         const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
                         const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
                         const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
-                        int la = X < A ? (int)md->caps[ci][0] : 0, lb = Y < A ? (int)md->caps[cj][0] : 0;
-                        int rba = X < A ? X * MQE_NUM_BODIES + (int)md->caps[ci][1] : A * MQE_NUM_BODIES + (X - A);
-                        int rbb = Y < A ? Y * MQE_NUM_BODIES + (int)md->caps[cj][1] : A * MQE_NUM_BODIES + (Y - A);
-                        V3 ra = cpos - mk(ox[0], ox[1], ox[2]), rb_ = cpos - mk(oy[0], oy[1], oy[2]);
-                        float *cmeta = es + ES_CMETA(maxpair) + slot * 8;
-                        cmeta[0] = cn.x; cmeta[1] = cn.y; cmeta[2] = cn.z; cmeta[3] = __int_as_float(rba); cmeta[4] = __int_as_float(rbb);
-                        int lega = la > 0 ? (la - 1) / 3 : 0, legb = lb > 0 ? (lb - 1) / 3 : 0;
-                        for (int dch = 0; dch < 3; dch++) {
-                            V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
-                            float *row = es + ES_ROWS + (3 * slot + dch) * PROWF;
-                            float dd = X < A ? robot_side_from_smem(bx_, la, ra, d, row) : npc_side(p, ra, d, row);
-                            dd += Y < A ? robot_side_from_smem(by_, lb, rb_, -d, row + 18) : npc_side(p, rb_, -d, row + 18);
-                            row[36] = 1.f / (dd + p.cfm);
-                            row[37] = dch == 0 ? contact_bias(p, cgap) : 0.f;
-                            row[38] = 0.f;
-                            row[39] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
-                        }
+                        const int la = X < A ? (int)md->caps[ci][0] : 0, lb = Y < A ? (int)md->caps[cj][0] : 0;
+                        const V3 ra = cpos - mk(ox[0], ox[1], ox[2]), rb_ = cpos - mk(oy[0], oy[1], oy[2]);
+                        const int lega = la > 0 ? (la - 1) / 3 : 0, legb = lb > 0 ? (lb - 1) / 3 : 0;
+                        const V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
+                        float *row = prow(item);
+                        float dd = X < A ? robot_side_from_smem(bx_, la, ra, d, row) : npc_side(p, ra, d, row);
+                        dd += Y < A ? robot_side_from_smem(by_, lb, rb_, -d, row + 18) : npc_side(p, rb_, -d, row + 18);
+                        row[36] = 1.f / (dd + p.cfm);
+                        row[37] = dch == 0 ? contact_bias(p, cgap) : 0.f;
+                        row[38] = 0.f;
+                        row[39] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
                     }
                 }
-                npair = min(npair, maxpair);
             }
             if (obb) {
                 // robot probes on the plank / the push box: canonical order = robot ascending, probe-table order (two-pass compaction)
@@ -1013,12 +1072,12 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     sphere_obb(p, oc, oex, oey, oez, oh, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], cn, cgap, cpos);
                     tangent_basis(cn, t1, t2);
                     const V3 ra = cpos - pos, rb_ = cpos - pivot;
-                    float *cmeta = es + ES_CMETA(maxpair) + slot * 8;
+                    float *cmeta = pdesc + slot * PDESCF;
                     cmeta[0] = cn.x; cmeta[1] = cn.y; cmeta[2] = cn.z;
                     cmeta[3] = __int_as_float(ag * MQE_NUM_BODIES + body); cmeta[4] = __int_as_float(A * MQE_NUM_BODIES);
                     for (int dch = 0; dch < 3; dch++) {
                         V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
-                        float *row = es + ES_ROWS + (3 * slot + dch) * PROWF;
+                        float *row = prow(3 * slot + dch);
                         float dd = robot_side_regs(k, ra, d, a1, a2, p1, p2, p3, Gm, Sinv, Hinv, row);
                         dd += npc_side(p, rb_, -d, row + 18);
                         row[36] = 1.f / (dd + p.cfm);
@@ -1034,9 +1093,9 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         __syncwarp();
         if (active && (leg == 0 || is_npc)) stat_rows = max(stat_rows, nrows);
 
+        PHASE_MARK(3);
         // ================================================================ P4: projected Gauss-Seidel
         {
-            float *rows = is_robot ? rs + RS_ROWS : ns + NS_ROWS;
             const int quad_base = lane & ~3;
             // every lane of a quad keeps all four legs' u (12 floats): a row's leg term J_l . u_leg is then local arithmetic
             // instead of a shuffle on the critical path of the sweep
@@ -1045,24 +1104,29 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             for (int L = 0; L < 4; L++)
 #pragma unroll
                 for (int k = 0; k < 3; k++) ua[L][k] = is_robot ? __shfl_sync(quad_mask, u[k], quad_base + L) : 0.f;
+            // row i lives at rowS + i*ROWF (shared memory; generic pointer) or, past SROWS (robots only), at rowG + i*ROWF
+            float *const rowS = is_robot ? rs + RS_ROWS : ns + NS_ROWS;
+            float *const rowG = grows - SROWS * ROWF;
             for (int it = 0; it < p.iters; it++) {
                 float lam_n = 0.f;                                  // multiplier of the last normal row (friction rows follow it)
                 for (int i = 0; i < nrows; i++) {
-                    float *row = rows + i * ROWF;
+                    float *row = (i < SROWS ? rowS : rowG) + i * ROWF;
                     float4 r0 = *reinterpret_cast<const float4 *>(row), r1 = *reinterpret_cast<const float4 *>(row + 4), r2 = *reinterpret_cast<const float4 *>(row + 8);
                     float4 r3 = *reinterpret_cast<const float4 *>(row + 12), r4 = *reinterpret_cast<const float4 *>(row + 16), r5 = *reinterpret_cast<const float4 *>(row + 20);
                     const int meta = __float_as_int(r5.y), rleg = meta & 15, kind = (meta >> 4) & 1;
-                    float pb = r0.x * vb[0] + r0.y * vb[1] + r0.z * vb[2] + r0.w * vb[3] + r1.x * vb[4] + r1.y * vb[5];
+                    // J.w as a balanced tree: the sweep is one long dependency chain through vb / ua, so depth is what counts
+                    const float pb = (fmaf(r0.x, vb[0], r0.y * vb[1]) + fmaf(r0.z, vb[2], r0.w * vb[3])) + fmaf(r1.x, vb[4], r1.y * vb[5]);
                     float pl = 0.f;
 #pragma unroll
                     for (int L = 0; L < 4; L++) {
-                        float t = r1.z * ua[L][0] + r1.w * ua[L][1] + r2.x * ua[L][2];
+                        float t = fmaf(r1.z, ua[L][0], fmaf(r1.w, ua[L][1], r2.x * ua[L][2]));
                         pl = rleg == L ? t : pl;
                     }
-                    float urel = r4.w + pb + pl;              // bias + J w
+                    float urel = (r4.w + pl) + pb;            // bias + J w
                     float lam_old = r5.x, lam = lam_old - urel * r4.z;
-                    if (kind == 0) { lam = fmaxf(lam, 0.f); lam_n = lam; }
-                    else { float lim = p.mu * lam_n; lam = fminf(fmaxf(lam, -lim), lim); }
+                    const float lo = kind == 0 ? 0.f : -p.mu * lam_n, hi = kind == 0 ? 3.0e38f : p.mu * lam_n;
+                    lam = fminf(fmaxf(lam, lo), hi);
+                    lam_n = kind == 0 ? lam : lam_n;
                     float dl = lam - lam_old;
                     row[20] = lam;                               // all four lanes of the quad store the SAME value (benign same-value race)
                     vb[0] += r2.y * dl; vb[1] += r2.z * dl; vb[2] += r2.w * dl; vb[3] += r3.x * dl; vb[4] += r3.y * dl; vb[5] += r3.z * dl;
@@ -1077,7 +1141,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));
                     __syncwarp(env_mask);
                     for (int i = 0; i < 3 * npair; i++) {
-                        float *row = es + ES_ROWS + i * PROWF;
+                        float *row = prow(i);
                         int meta = __float_as_int(row[39]);
                         int ga = meta & 15, la = (meta >> 4) & 15, gb = (meta >> 8) & 15, lb = (meta >> 12) & 15, kind = (meta >> 16) & 1, nrow = meta >> 20;
                         const float *sa = row, *sb = row + 18;
@@ -1092,7 +1156,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                                              + __shfl_sync(env_mask, pbB, srcB) + __shfl_sync(env_mask, plB, gb < A ? srcB + lb : srcB);
                         float lam_old = row[38], lam = lam_old - urel * row[36];
                         if (kind == 0) lam = fmaxf(lam, 0.f);
-                        else { float lim = p.mu * es[ES_ROWS + nrow * PROWF + 38]; lam = fminf(fmaxf(lam, -lim), lim); }
+                        else { float lim = p.mu * prow(nrow)[38]; lam = fminf(fmaxf(lam, -lim), lim); }
                         float dl = lam - lam_old;
                         __syncwarp(env_mask);
                         row[38] = lam;
@@ -1120,6 +1184,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));
         }
 
+        PHASE_MARK(4);
         // ================================================================ P5: contact force report (last substep), integrate
         if (last) {
             float idt = 1.f / p.dt;
@@ -1131,8 +1196,8 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
                     V3 n = mk(cmeta[0], cmeta[1], cmeta[2]), t1, t2;
                     tangent_basis(n, t1, t2);
                     int body = __float_as_int(cmeta[3]);
-                    const float *row = rs + RS_ROWS + (nlim + 3 * c) * ROWF;
-                    V3 f = (row[20] * idt) * n + (row[ROWF + 20] * idt) * t1 + (row[2 * ROWF + 20] * idt) * t2;
+                    const int r0 = nlim + 3 * c;
+                    V3 f = (lrow(r0)[20] * idt) * n + (lrow(r0 + 1)[20] * idt) * t1 + (lrow(r0 + 2)[20] * idt) * t2;
                     atomicAdd(rs + RS_FORCE + body * 3, f.x); atomicAdd(rs + RS_FORCE + body * 3 + 1, f.y); atomicAdd(rs + RS_FORCE + body * 3 + 2, f.z);
                 }
             } else if (is_npc && active) {
@@ -1148,12 +1213,11 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             __syncwarp();
             if (npair > 0 && active) {
                 for (int c = rank_in_env; c < npair; c += lanes_per_env) {
-                    const float *cmeta = es + ES_CMETA(maxpair) + c * 8;
+                    const float *cmeta = pdesc + c * PDESCF;
                     V3 n = mk(cmeta[0], cmeta[1], cmeta[2]), t1, t2;
                     tangent_basis(n, t1, t2);
                     int rba = __float_as_int(cmeta[3]), rbb = __float_as_int(cmeta[4]);
-                    const float *row = es + ES_ROWS + 3 * c * PROWF;
-                    V3 f = (row[38] * idt) * n + (row[PROWF + 38] * idt) * t1 + (row[2 * PROWF + 38] * idt) * t2;
+                    V3 f = (prow(3 * c)[38] * idt) * n + (prow(3 * c + 1)[38] * idt) * t1 + (prow(3 * c + 2)[38] * idt) * t2;
                     for (int side = 0; side < 2; side++) {
                         int rb = side ? rbb : rba;
                         float sg = side ? -1.f : 1.f;
@@ -1201,6 +1265,7 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
             qx = nx * inv; qy = ny * inv; qz = nz * inv; qw = nw * inv;
         }
         __syncwarp();
+        PHASE_MARK(5);
     }
 
     // ---- write back ----
@@ -1229,6 +1294,18 @@ __global__ void __launch_bounds__(128) k_substeps(DevParams p, int nsub, int max
         }
         if (rank_in_env == 0) atomicAdd(p.stats + 2, stat_pair);
     }
+    // per-warp trace (MQE_BUF_WARP_TRACE): start / end on the global timer [ns], pair contacts and widest row count of the warp
+    {
+        int wp = stat_pair, wr = stat_rows;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { wp += __shfl_xor_sync(FULL, wp, o); wr = max(wr, __shfl_xor_sync(FULL, wr, o)); }
+        if (lane == 0) {
+            long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            PHASE_MARK(7);
+            tr[0] = t_start; tr[1] = t_end; tr[2] = wp; tr[3] = wr;
+        }
+    }
 }
 
 // stand-alone actuator network (parity tests against unitree_go1.pt): x [rows][6] -> torque [rows], unclipped
@@ -1255,31 +1332,50 @@ __global__ void k_actuator(const float *__restrict__ aw, const float *__restrict
 }
 
 // host-side launchers (api.cu)
-static int substeps_warps_per_cta(int A, int Pd, int E, int maxpair) {
-    const size_t budget = 227 * 1024, hdr = (size_t)physics_cta_header_floats() * 4, per = (size_t)physics_warp_smem_floats(A, Pd, E, maxpair) * 4;
-    int w = (int)((budget - hdr) / per);
-    return w > 4 ? 4 : w;
+// Launch plan.  Shared memory per warp sets how many warps an SM holds (registers allow 8); the kernel is latency-bound, so
+// residency is throughput.  spair (pair contacts whose rows stay in shared memory) is the largest value that does not cost a
+// resident warp; warps per CTA are then balanced so the grid fills whole waves of one CTA per SM (C2: 1024 warps of 4 envs
+// = 147 CTAs x 7 warps = one wave on 148 SMs).
+struct SubstepPlan { int warps, spair, grid; size_t smem; };
+static SubstepPlan substeps_plan(int N, int A, int Pd, int E, int maxpair) {
+    static const int sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        return n;
+    }();
+    const size_t budget = 227 * 1024, hdr = (size_t)physics_cta_header_floats() * 4;
+    auto fit = [&](int sp) { int w = (int)((budget - hdr) / ((size_t)physics_warp_smem_floats(A, Pd, E, sp, maxpair) * 4)); return w > 8 ? 8 : w; };
+    SubstepPlan pl;
+    const int spmin = maxpair < 2 ? maxpair : 2;
+    pl.spair = maxpair;
+    while (pl.spair > spmin && fit(pl.spair) < fit(spmin)) pl.spair--;
+    const int wmax = fit(pl.spair);
+    pl.warps = wmax;
+    if (wmax >= 1) {
+        const int tasks = (N + E - 1) / E, waves = (tasks + sms * wmax - 1) / (sms * wmax);
+        int w = (tasks + sms * waves - 1) / (sms * waves);
+        pl.warps = w < 1 ? 1 : (w > wmax ? wmax : w);
+        pl.grid = (tasks + pl.warps - 1) / pl.warps;
+    } else pl.grid = 0;
+    pl.smem = (size_t)(physics_cta_header_floats() + (pl.warps < 1 ? 1 : pl.warps) * physics_warp_smem_floats(A, Pd, E, pl.spair, maxpair)) * sizeof(float);
+    return pl;
 }
-extern "C" size_t mqe_substeps_smem_bytes(int A, int Pd, int E, int maxpair) {
-    int w = substeps_warps_per_cta(A, Pd, E, maxpair);
-    if (w < 1) w = 1;
-    return (size_t)(physics_cta_header_floats() + w * physics_warp_smem_floats(A, Pd, E, maxpair)) * sizeof(float);
-}
+extern "C" size_t mqe_substeps_smem_bytes(int N, int A, int Pd, int E, int maxpair) { return substeps_plan(N, A, Pd, E, maxpair).smem; }
+extern "C" size_t mqe_substeps_row_scratch_floats(int N, int A) { return (size_t)N * A * (MQE_MAX_ROWS - SROWS) * ROWF; }
+extern "C" size_t mqe_substeps_prow_scratch_floats(int N, int maxpair) { return (size_t)N * maxpair * 3 * PROWF; }
+extern "C" size_t mqe_substeps_pdesc_scratch_floats(int N, int maxpair) { return (size_t)N * maxpair * PDESCF; }
 extern "C" cudaError_t mqe_launch_actuator(const float *act_w, const float *x, int rows, float *out, cudaStream_t st) {
     k_actuator<<<(rows + 127) / 128, 128, 0, st>>>(act_w, x, rows, out);
     return cudaGetLastError();
 }
-extern "C" cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, const unsigned int *pair_table, int n_pair_entries, cudaStream_t st) {
-    int warps_per_cta = substeps_warps_per_cta(p.A, p.Pd, p.E, maxpair);
-    if (warps_per_cta < 1) return cudaErrorInvalidConfiguration;
-    int envs_per_cta = warps_per_cta * p.E;
-    int grid = (p.N + envs_per_cta - 1) / envs_per_cta;
-    size_t smem = mqe_substeps_smem_bytes(p.A, p.Pd, p.E, maxpair);
+extern "C" cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, cudaStream_t st) {
+    const SubstepPlan pl = substeps_plan(p.N, p.A, p.Pd, p.E, maxpair);
+    if (pl.warps < 1) return cudaErrorInvalidConfiguration;
     static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (pl.smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured = pl.smem;
     }
-    return launch_heavy(k_substeps, dim3(grid), dim3(warps_per_cta * 32), smem, st, p, nsub, maxpair, pair_table, n_pair_entries);
+    return launch_heavy(k_substeps, dim3(pl.grid), dim3(pl.warps * 32), pl.smem, st, p, nsub, maxpair, pl.spair);
 }

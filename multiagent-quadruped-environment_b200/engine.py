@@ -23,7 +23,7 @@ OBS_FLOATS = 71
 (BUF_ROOT_STATES, BUF_DOF_STATES, BUF_CONTACT_FORCES, BUF_TORQUES, BUF_ACTIONS, BUF_LAST_ACTIONS, BUF_OBS,
  BUF_BASE_LIN_VEL, BUF_BASE_ANG_VEL, BUF_PROJ_GRAVITY, BUF_RESET, BUF_TIMEOUT, BUF_COLLIDE, BUF_ROLL_TERM,
  BUF_PITCH_TERM, BUF_ZLOW_TERM, BUF_ZHIGH_TERM, BUF_EPISODE_LENGTH, BUF_COMMANDS, BUF_LOC_OBS, BUF_LOC_ACTION,
- BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_CLOCK, BUF_COUNT) = range(27)
+ BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_CLOCK, BUF_WARP_TRACE, BUF_COUNT) = range(28)
 
 OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
     "base_pos": (0, 3), "base_quat": (3, 7), "dof_pos": (7, 19), "dof_vel": (19, 31), "lin_vel": (31, 34),
@@ -179,7 +179,7 @@ class _DevArray:
 
 _TYPESTR = {("f", 4): "<f4", ("u", 1): "|u1", ("i", 8): "<i8", ("i", 4): "<i4", ("h", 2): "<u2"}
 _BUF_KIND = {BUF_RESET: "u", BUF_TIMEOUT: "u", BUF_COLLIDE: "u", BUF_ROLL_TERM: "u", BUF_PITCH_TERM: "u",
-             BUF_ZLOW_TERM: "u", BUF_ZHIGH_TERM: "u", BUF_EPISODE_LENGTH: "i", BUF_STATS: "i"}
+             BUF_ZLOW_TERM: "u", BUF_ZHIGH_TERM: "u", BUF_EPISODE_LENGTH: "i", BUF_STATS: "i", BUF_WARP_TRACE: "i"}
 
 
 class Engine:
