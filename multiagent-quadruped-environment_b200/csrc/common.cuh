@@ -15,7 +15,7 @@
 #define MQE_ROBOT_BOUND 0.60f
 #define MQE_HIST_PAD 80          // one 70-float frame padded to 5 x 16 for the tensor-core K loop
 #define MQE_NV 18
-#define MQE_TRACE_COLS 12       // start ns, end ns, pair contacts, widest row count, cycles of P1..P5, integrate, prologue, epilogue
+#define MQE_TRACE_COLS 16       // start ns, end ns, pair contacts, widest row count, cycles of P1..P5, integrate, prologue, epilogue
 
 struct DevParams {
     int N, A, P, D, G;            // envs (local), agents, npcs, npc dofs per env, actors per env (A+P)

@@ -16,7 +16,7 @@
 #include "kernels.cuh"
 
 #define ROWF 24        // floats per local row: Jb6 Jl3 Yb6 Yl3 dinv bias lambda meta + pad
-#define PROWF 40       // floats per pair row: side A (18) side B (18) dinv bias lambda meta
+#define PROWF 44       // floats per pair row: side A at 0 (18 + 2 pad), side B at 20 (18 + 2 pad), then dinv bias lambda meta at 40
 // per-robot shared block (floats)
 #define RS_ORIGIN 0
 #define RS_SINV 3
@@ -153,6 +153,18 @@ __device__ __forceinline__ void sym6_mulv(const float *A, const float *x, float 
         y[i] = s;
     }
 }
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n) {      // position of the n-th (0-based) set bit
+    for (int i = 0; i < n; i++) m &= m - 1u;
+    return __ffs(m) - 1;
+}
+// value selects (never references: a reference to one of several register objects sends all of them to local memory)
+__device__ __forceinline__ float sel1(int k, float a, float b, float c, float d) { return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d)); }
+__device__ __forceinline__ V3 sel3(int k, V3 a, V3 b, V3 c, V3 d) { return mk(sel1(k, a.x, b.x, c.x, d.x), sel1(k, a.y, b.y, c.y, d.y), sel1(k, a.z, b.z, c.z, d.z)); }
+__device__ __forceinline__ M3 selm(int k, const M3 &a, const M3 &b, const M3 &c, const M3 &d) {
+    M3 o;
+    o.c0 = sel3(k, a.c0, b.c0, c.c0, d.c0); o.c1 = sel3(k, a.c1, b.c1, c.c1, d.c1); o.c2 = sel3(k, a.c2, b.c2, c.c2, d.c2);
+    return o;
+}
 // sym 3x3: 00 01 02 11 12 22
 __device__ __forceinline__ void sym3_inverse(const float *H, float *Hi) {
     float c00 = H[3] * H[5] - H[4] * H[4], c01 = H[2] * H[4] - H[1] * H[5], c02 = H[1] * H[4] - H[2] * H[3];
@@ -288,24 +300,26 @@ __device__ __forceinline__ void seg_seg(V3 p1, V3 q1, V3 p2, V3 q2, V3 &c1, V3 &
 
 // Build one side (18 floats: Jb6 Jl3 Yb6 Yl3) of a row for a robot from the operators in shared memory.
 // link: 0 base, 1..12.  Returns the diagonal contribution J.Y.
-__device__ float robot_side_from_smem(const float *rs, int link, V3 r, V3 d, float *out) {
+__device__ __forceinline__ float robot_side_from_smem(const float *rs, int link, V3 r, V3 d, float *out) {
     V3 rxd = cross(r, d);
-    float Jb[6] = {rxd.x, rxd.y, rxd.z, d.x, d.y, d.z}, Jl[3] = {0.f, 0.f, 0.f};
-    int leg = 0, k = 0;
-    if (link > 0) { leg = (link - 1) / 3; k = (link - 1) % 3 + 1; }
-    for (int j = 0; j < k; j++) {
+    float Jb[6] = {rxd.x, rxd.y, rxd.z, d.x, d.y, d.z}, Jl[3], Yb[6], Yl[3];
+    const int leg = link > 0 ? (link - 1) / 3 : 0, k = link > 0 ? (link - 1) % 3 + 1 : 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {      // fixed trip count, joints past the link masked: no dynamically indexed registers
         const float *a = rs + RS_A + (3 * leg + j) * 3, *pj = rs + RS_P + (3 * leg + j) * 3;
         V3 rel = mk(r.x - pj[0], r.y - pj[1], r.z - pj[2]);
-        Jl[j] = dot(mk(a[0], a[1], a[2]), cross(rel, d));
+        const float v = dot(mk(a[0], a[1], a[2]), cross(rel, d));
+        Jl[j] = j < k ? v : 0.f;
     }
     const float *G = rs + RS_G + leg * 18;
-    if (k > 0)
-        for (int i = 0; i < 6; i++) Jb[i] -= G[i * 3] * Jl[0] + G[i * 3 + 1] * Jl[1] + G[i * 3 + 2] * Jl[2];
-    float Yb[6], Yl[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 6; i++) Jb[i] -= G[i * 3] * Jl[0] + G[i * 3 + 1] * Jl[1] + G[i * 3 + 2] * Jl[2];
     sym6_mulv(rs + RS_SINV, Jb, Yb);
-    if (k > 0) sym3_mulv(rs + RS_HINV + leg * 6, Jl, Yl);
+    sym3_mulv(rs + RS_HINV + leg * 6, Jl, Yl);
     float dd = 0.f;
+#pragma unroll
     for (int i = 0; i < 6; i++) { out[i] = Jb[i]; out[9 + i] = Yb[i]; dd += Jb[i] * Yb[i]; }
+#pragma unroll
     for (int i = 0; i < 3; i++) { out[6 + i] = Jl[i]; out[15 + i] = Yl[i]; dd += Jl[i] * Yl[i]; }
     return dd;
 }
@@ -711,10 +725,10 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 float gap = side ? md->q_upper[3 * leg + k] - q[k] : q[k] - md->q_lower[3 * leg + k];
                 float Jb[6], Yb[6];
 #pragma unroll
-                for (int i = 0; i < 6; i++) Jb[i] = -sg * Gm[i * 3 + k];
+                for (int i = 0; i < 6; i++) Jb[i] = -sg * sel1(k, Gm[i * 3], Gm[i * 3 + 1], Gm[i * 3 + 2], 0.f);   // value selects keep Gm / Hinv in registers
                 sym6_mulv(Sinv, Jb, Yb);
-                float hk[3] = {Hinv[k == 0 ? 0 : (k == 1 ? 1 : 2)], Hinv[k == 0 ? 1 : (k == 1 ? 3 : 4)], Hinv[k == 0 ? 2 : (k == 1 ? 4 : 5)]};
-                float dd = hk[k];
+                const float hk[3] = {sel1(k, Hinv[0], Hinv[1], Hinv[2], 0.f), sel1(k, Hinv[1], Hinv[3], Hinv[4], 0.f), sel1(k, Hinv[2], Hinv[4], Hinv[5], 0.f)};
+                float dd = sel1(k, hk[0], hk[1], hk[2], 0.f);
 #pragma unroll
                 for (int i = 0; i < 6; i++) dd += Jb[i] * Yb[i];
                 float *row = lrow(slot);
@@ -725,6 +739,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 row[18] = 1.f / (dd + p.cfm); row[19] = contact_bias(p, gap); row[20] = 0.f;
                 row[21] = __int_as_float(leg | (0 << 4) | (slot << 8));
             }
+            PHASE_MARK(8);
             // ---- world contacts: pass 1 flags ----
             const float sdf_o = active ? sdf_sample(p, pos.x, pos.y).sdf : 0.f;     // same address in all four lanes of the quad
             unsigned long long cm = 0ull;
@@ -735,8 +750,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     const float *pr = md->probes[pi];
                     const int link = (int)pr[0];
                     const int k = link == 0 ? 0 : link - 3 * leg;
-                    const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
-                    V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                    const M3 Rl = selm(k, Rb, R1, R2, R3);
+                    V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                     V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
                     ProbeHit h = probe_world(p, pos + xr, pr[5], seesaw, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
                     cm |= (unsigned long long)h.mask << (2 * pi);
@@ -746,6 +761,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             call |= __shfl_xor_sync(quad_mask, call, 2);
             int ncon = min(__popcll(call), MQE_MAX_LOCAL);
             nrows = nlim + 3 * ncon;
+            PHASE_MARK(9);
             // ---- pass 2: build rows for my contacts ----
             while (cm) {
                 int b = __ffsll((long long)cm) - 1;
@@ -756,8 +772,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 const float *pr = md->probes[pi];
                 int link = (int)pr[0], body = (int)pr[1];
                 int k = link == 0 ? 0 : link - 3 * leg;
-                const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
-                V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                const M3 Rl = selm(k, Rb, R1, R2, R3);
+                V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                 V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));            // probe centre rel. O
                 ProbeHit h = probe_world(p, pos + xr, pr[5], seesaw, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
                 V3 n = kind ? h.nw : mk(0, 0, 1);
@@ -890,8 +906,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         const float *cp = md->caps[ci];
                         const int link = (int)cp[0];
                         const int k = link == 0 ? 0 : link - 3 * leg;
-                        const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
-                        V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                        const M3 Rl = selm(k, Rb, R1, R2, R3);
+                        V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                         V3 l0 = pl + mul(Rl, mk(cp[2], cp[3], cp[4])), l1 = pl + mul(Rl, mk(cp[5], cp[6], cp[7]));
                         V3 w0 = pos + l0, w1 = pos + l1;
                         float *o = rs + RS_CAP + ci * 7;
@@ -964,7 +980,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                                 float cgap = 0.f;
                                 int ci = 0, cj = 0;
                                 if (c < ncombo) {
-                                    ci = __fns(mXY, 0, c / ny + 1); cj = __fns(mYX, 0, c % ny + 1);
+                                    ci = nth_set_bit(mXY, c / ny); cj = nth_set_bit(mYX, c % ny);
                                     const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
                                     V3 c1, c2;
                                     seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
@@ -1011,11 +1027,12 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         const V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
                         float *row = prow(item);
                         float dd = X < A ? robot_side_from_smem(bx_, la, ra, d, row) : npc_side(p, ra, d, row);
-                        dd += Y < A ? robot_side_from_smem(by_, lb, rb_, -d, row + 18) : npc_side(p, rb_, -d, row + 18);
-                        row[36] = 1.f / (dd + p.cfm);
-                        row[37] = dch == 0 ? contact_bias(p, cgap) : 0.f;
-                        row[38] = 0.f;
-                        row[39] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
+                        dd += Y < A ? robot_side_from_smem(by_, lb, rb_, -d, row + 20) : npc_side(p, rb_, -d, row + 20);
+                        row[18] = row[19] = row[38] = row[39] = 0.f;
+                        row[40] = 1.f / (dd + p.cfm);
+                        row[41] = dch == 0 ? contact_bias(p, cgap) : 0.f;
+                        row[42] = 0.f;
+                        row[43] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
                     }
                 }
             }
@@ -1043,8 +1060,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         const float *pr = md->probes[pi];
                         const int link = (int)pr[0];
                         const int k = link == 0 ? 0 : link - 3 * leg;
-                        const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
-                        V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                        const M3 Rl = selm(k, Rb, R1, R2, R3);
+                        V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                         V3 nn, pp;
                         float gg;
                         if (sphere_obb(p, oc, oex, oey, oez, oh, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], nn, gg, pp)) sm |= 1u << pi;
@@ -1065,8 +1082,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     const float *pr = md->probes[b];
                     const int link = (int)pr[0], body = (int)pr[1];
                     const int k = link == 0 ? 0 : link - 3 * leg;
-                    const M3 &Rl = k == 0 ? Rb : (k == 1 ? R1 : (k == 2 ? R2 : R3));
-                    V3 pl = k == 0 ? mk(0, 0, 0) : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                    const M3 Rl = selm(k, Rb, R1, R2, R3);
+                    V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                     V3 cn, cpos, t1, t2;
                     float cgap;
                     sphere_obb(p, oc, oex, oey, oez, oh, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], cn, cgap, cpos);
@@ -1079,11 +1096,12 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
                         float *row = prow(3 * slot + dch);
                         float dd = robot_side_regs(k, ra, d, a1, a2, p1, p2, p3, Gm, Sinv, Hinv, row);
-                        dd += npc_side(p, rb_, -d, row + 18);
-                        row[36] = 1.f / (dd + p.cfm);
-                        row[37] = dch == 0 ? contact_bias(p, cgap) : 0.f;
-                        row[38] = 0.f;
-                        row[39] = __int_as_float(ag | (leg << 4) | (A << 8) | (0 << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
+                        dd += npc_side(p, rb_, -d, row + 20);
+                        row[18] = row[19] = row[38] = row[39] = 0.f;
+                        row[40] = 1.f / (dd + p.cfm);
+                        row[41] = dch == 0 ? contact_bias(p, cgap) : 0.f;
+                        row[42] = 0.f;
+                        row[43] = __int_as_float(ag | (leg << 4) | (A << 8) | (0 << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
                     }
                 }
                 npair = min(npair + total, maxpair);
@@ -1107,6 +1125,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             // row i lives at rowS + i*ROWF (shared memory; generic pointer) or, past SROWS (robots only), at rowG + i*ROWF
             float *const rowS = is_robot ? rs + RS_ROWS : ns + NS_ROWS;
             float *const rowG = grows - SROWS * ROWF;
+            PHASE_MARK(10);
             for (int it = 0; it < p.iters; it++) {
                 float lam_n = 0.f;                                  // multiplier of the last normal row (friction rows follow it)
                 for (int i = 0; i < nrows; i++) {
@@ -1139,39 +1158,42 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 if (npair > 0) {   // uniform over the env's lanes
 #pragma unroll
                     for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));
-                    __syncwarp(env_mask);
+                    // Pair rows.  A lane reads only its own group's side (5 x 16 B) and the 16-byte tail; the lane that owns the row's
+                    // leg on each side forms that side's J.w, two shuffles combine them, every lane of the env applies the same
+                    // clamp, and the multiplier is carried to the next sweep through the row (one __syncwarp per sweep).
+                    float lam_np = 0.f;
                     for (int i = 0; i < 3 * npair; i++) {
                         float *row = prow(i);
-                        int meta = __float_as_int(row[39]);
-                        int ga = meta & 15, la = (meta >> 4) & 15, gb = (meta >> 8) & 15, lb = (meta >> 12) & 15, kind = (meta >> 16) & 1, nrow = meta >> 20;
-                        const float *sa = row, *sb = row + 18;
-                        float pbA = 0.f, plA = 0.f, pbB = 0.f, plB = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 6; k++) { pbA += sa[k] * vb[k]; pbB += sb[k] * vb[k]; }
-#pragma unroll
-                        for (int k = 0; k < 3; k++) { plA += sa[6 + k] * u[k]; plB += sb[6 + k] * u[k]; }
-                        int srcA = ga < A ? e_loc * 4 * A + 4 * ga : nrl + e_loc * P + (ga - A);
-                        int srcB = gb < A ? e_loc * 4 * A + 4 * gb : nrl + e_loc * P + (gb - A);
-                        float urel = row[37] + __shfl_sync(env_mask, pbA, srcA) + __shfl_sync(env_mask, plA, ga < A ? srcA + la : srcA)
-                                             + __shfl_sync(env_mask, pbB, srcB) + __shfl_sync(env_mask, plB, gb < A ? srcB + lb : srcB);
-                        float lam_old = row[38], lam = lam_old - urel * row[36];
-                        if (kind == 0) lam = fmaxf(lam, 0.f);
-                        else { float lim = p.mu * prow(nrow)[38]; lam = fminf(fmaxf(lam, -lim), lim); }
-                        float dl = lam - lam_old;
-                        __syncwarp(env_mask);
-                        row[38] = lam;
-                        if (grp == ga) {
-#pragma unroll
-                            for (int k = 0; k < 6; k++) vb[k] += sa[9 + k] * dl;
-                            if (is_robot && leg == la) { u[0] += sa[15] * dl; u[1] += sa[16] * dl; u[2] += sa[17] * dl; }
+                        const float4 tl = *reinterpret_cast<const float4 *>(row + 40);            // dinv, bias, lambda, meta
+                        const int meta = __float_as_int(tl.w);
+                        const int ga = meta & 15, la = (meta >> 4) & 15, gb = (meta >> 8) & 15, lb = (meta >> 12) & 15, kind = (meta >> 16) & 1;
+                        const bool inA = grp == ga, inB = grp == gb;
+                        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0, s4 = s0;
+                        if (inA || inB) {
+                            const float *sd = row + (inB ? 20 : 0);                                // Jb0..5 Jl0..2 Yb0..5 Yl0..2 (+2 pad)
+                            s0 = *reinterpret_cast<const float4 *>(sd); s1 = *reinterpret_cast<const float4 *>(sd + 4);
+                            s2 = *reinterpret_cast<const float4 *>(sd + 8); s3 = *reinterpret_cast<const float4 *>(sd + 12);
+                            s4 = *reinterpret_cast<const float4 *>(sd + 16);
                         }
-                        if (grp == gb) {
-#pragma unroll
-                            for (int k = 0; k < 6; k++) vb[k] += sb[9 + k] * dl;
-                            if (is_robot && leg == lb) { u[0] += sb[15] * dl; u[1] += sb[16] * dl; u[2] += sb[17] * dl; }
-                        }
-                        __syncwarp(env_mask);
+                        const float jw = ((fmaf(s0.x, vb[0], s0.y * vb[1]) + fmaf(s0.z, vb[2], s0.w * vb[3])) + fmaf(s1.x, vb[4], s1.y * vb[5]))
+                                         + fmaf(s1.z, u[0], fmaf(s1.w, u[1], s2.x * u[2]));
+                        const int srcA = ga < A ? e_loc * 4 * A + 4 * ga + la : nrl + e_loc * P + (ga - A);
+                        const int srcB = gb < A ? e_loc * 4 * A + 4 * gb + lb : nrl + e_loc * P + (gb - A);
+                        const float urel = tl.y + (__shfl_sync(env_mask, jw, srcA) + __shfl_sync(env_mask, jw, srcB));
+                        const float lam_old = tl.z;
+                        float lam = lam_old - urel * tl.x;
+                        const float lo = kind == 0 ? 0.f : -p.mu * lam_np, hi = kind == 0 ? 3.0e38f : p.mu * lam_np;
+                        lam = fminf(fmaxf(lam, lo), hi);
+                        lam_np = kind == 0 ? lam : lam_np;
+                        const float dl = lam - lam_old;
+                        if (rank_in_env == 0) row[42] = lam;
+                        // s* are zero outside the two groups; the leg part only moves the lane that owns the row's leg
+                        vb[0] = fmaf(s2.y, dl, vb[0]); vb[1] = fmaf(s2.z, dl, vb[1]); vb[2] = fmaf(s2.w, dl, vb[2]);
+                        vb[3] = fmaf(s3.x, dl, vb[3]); vb[4] = fmaf(s3.y, dl, vb[4]); vb[5] = fmaf(s3.z, dl, vb[5]);
+                        const float dll = (is_robot && leg == (inB ? lb : la)) ? dl : 0.f;
+                        u[0] = fmaf(s3.w, dll, u[0]); u[1] = fmaf(s4.x, dll, u[1]); u[2] = fmaf(s4.y, dll, u[2]);
                     }
+                    __syncwarp(env_mask);
                     if (is_robot) {
 #pragma unroll
                         for (int L = 0; L < 4; L++)
@@ -1217,7 +1239,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     V3 n = mk(cmeta[0], cmeta[1], cmeta[2]), t1, t2;
                     tangent_basis(n, t1, t2);
                     int rba = __float_as_int(cmeta[3]), rbb = __float_as_int(cmeta[4]);
-                    V3 f = (prow(3 * c)[38] * idt) * n + (prow(3 * c + 1)[38] * idt) * t1 + (prow(3 * c + 2)[38] * idt) * t2;
+                    V3 f = (prow(3 * c)[42] * idt) * n + (prow(3 * c + 1)[42] * idt) * t1 + (prow(3 * c + 2)[42] * idt) * t2;
                     for (int side = 0; side < 2; side++) {
                         int rb = side ? rbb : rba;
                         float sg = side ? -1.f : 1.f;

@@ -18,6 +18,7 @@ eng = base.engine
 acts = torch.as_tensor(B.synth_actions(n, base._ctrl_agents, 64, env_offset=0), device="cuda:0")
 env.reset()
 rows = []
+worst = (0.0, None, None)
 for i in range(steps):
     env.step(acts[i % 64])
     if i >= 50 and i % 25 == 0:
@@ -28,6 +29,8 @@ for i in range(steps):
         late = (tr[:, 0].max() - tr[:, 0].min()) * 1e-3
         k = int(np.argmax(d))
         print(f"step {i:4d} span {span:7.1f} mean {d.mean():7.1f} p99 {np.percentile(d, 99):7.1f} max {d.max():7.1f}  warps rows>=13 {np.mean(tr[:, 3] >= 13):.3f} rows>=19 {np.mean(tr[:, 3] >= 19):.3f} pairs {np.mean(tr[:, 2] > 0):.4f}")
+        if d.max() > worst[0]:
+            worst = (float(d.max()), i, tr[k].copy())
         rows.append((span, d.mean(), np.percentile(d, 50), np.percentile(d, 90), np.percentile(d, 99), d.max(), late, tr[k, 2], tr[k, 3], (tr[:, 2] > 0).mean()))
 r = np.array(rows, dtype=np.float64)
 names = ["span_us", "mean", "p50", "p90", "p99", "max", "last_start", "pairs@slowest", "rows@slowest", "frac_warps_with_pairs"]
@@ -40,8 +43,8 @@ for lo, hi in [(0, 7), (7, 13), (13, 19), (19, 29)]:
     if m.any():
         print(f"  warps with widest row count in [{lo},{hi}) and no pairs: n={int(m.sum()):5d} mean {d[m].mean():8.2f} us")
 if tr[:, 4:].sum() > 0:
-    ph = tr[:, 4:12].astype(np.float64)
-    names_p = ["P1 actuator", "P2 dynamics", "P3 rows", "P3b pairs", "P4 PGS", "P5 integrate", "prologue", "epilogue"]
+    ph = tr[:, 4:16].astype(np.float64)
+    names_p = ["P1 actuator", "P2 dynamics", "P3 pass2 rows", "P3b pairs", "P4 PGS", "P5 integrate", "prologue", "epilogue", "P3 limits", "P3 pass1 probes", "P4 setup", "-"]
     tot = ph.sum(1)
     print("  per-phase share of warp cycles (mean over warps; MQE_TRACE=1), cycles per launch:")
     for i, nm in enumerate(names_p):
@@ -49,3 +52,9 @@ if tr[:, 4:].sum() > 0:
 m = tr[:, 2] > 0
 if m.any():
     print(f"  warps with pair contacts: n={int(m.sum())} mean {d[m].mean():.2f} us, max {d[m].max():.2f}")
+
+if worst[2] is not None and worst[2][4:].sum() > 0:
+    w = worst[2]
+    nm = ["P1 actuator", "P2 dynamics", "P3 pass2 rows", "P3b pairs", "P4 PGS", "P5 integrate", "prologue", "epilogue", "P3 limits", "P3 pass1 probes", "P4 setup", "-"]
+    print(f"slowest warp of the run: step {worst[1]}, {worst[0]:.1f} us, pair contacts {w[2]}, widest rows {w[3]}; cycles per phase:")
+    print("   " + ", ".join(f"{n} {int(c)}" for n, c in zip(nm, w[4:16]) if c))
