@@ -158,7 +158,7 @@ typedef enum {
     MQE_BUF_SHEEP_STATS,        /* f32 [N][3]     sheep_pos_avg xy, sheep_pos_var */
     MQE_BUF_STATS,              /* i32 [8]        contact / row statistics of the last step */
     MQE_BUF_CLOCK,              /* f32 [N*A][4]   gait clock inputs (go1.py:240-279)        */
-    MQE_BUF_WARP_TRACE,         /* i64 [warps][16] substep kernel trace per warp of envs: start ns, end ns, pair contacts, widest row count, then (MQE_TRACE=1) cycles per phase */
+    MQE_BUF_WARP_TRACE,         /* i64 [warps][20] substep kernel trace per warp of envs: start ns, end ns, pair contacts, widest row count, then (MQE_TRACE=1) cycles per phase */
     MQE_BUF_COUNT
 } MqeBuffer;
 

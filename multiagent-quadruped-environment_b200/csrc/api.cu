@@ -227,6 +227,14 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     { const char *e = getenv("MQE_TRACE"); p.trace = (e && e[0] == '1') ? 1 : 0; }
     CK(dalloc(s, &p.row_scratch, mqe_substeps_row_scratch_floats(N, A), false));
     CK(dalloc(s, &p.prow_scratch, mqe_substeps_prow_scratch_floats(N, s->maxpair), false));
+    {
+        const int Gd = A + (d->npc_kind == MQE_NPC_RIGID ? P : 0), nc = d->model.n_caps;    // capsule groups only
+        int total = 0;
+        for (int X = 0; X < Gd; X++)
+            for (int Y = X + 1; Y < Gd; Y++) total += (X < A ? nc : 1) * (Y < A ? nc : 1);
+        p.max_cand = total > 0 ? total : 1;
+        CK(dalloc(s, &p.cand_scratch, (size_t)N * p.max_cand, false));
+    }
     CK(dalloc(s, &p.pdesc_scratch, mqe_substeps_pdesc_scratch_floats(N, s->maxpair), false));
     const size_t ring = (size_t)M * MQE_HIST_FRAMES * MQE_HIST_PAD;
     CK(dalloc(s, &p.hist_f32, ring));

@@ -15,7 +15,7 @@
 #define MQE_ROBOT_BOUND 0.60f
 #define MQE_HIST_PAD 80          // one 70-float frame padded to 5 x 16 for the tensor-core K loop
 #define MQE_NV 18
-#define MQE_TRACE_COLS 16       // start ns, end ns, pair contacts, widest row count, cycles of P1..P5, integrate, prologue, epilogue
+#define MQE_TRACE_COLS 20       // start ns, end ns, pair contacts, widest row count, cycles of P1..P5, integrate, prologue, epilogue
 
 struct DevParams {
     int N, A, P, D, G;            // envs (local), agents, npcs, npc dofs per env, actors per env (A+P)
@@ -51,7 +51,9 @@ struct DevParams {
     unsigned char *reset_buf, *timeout_buf, *collide_buf, *r_term, *p_term, *zl_term, *zh_term;
     unsigned int *episode;
     unsigned char *hist_dirty;    // [N] history must be zeroed before the next frame is appended (go1.py:141-145)
-    float *row_scratch, *prow_scratch, *pdesc_scratch;   // k_substeps: local / pair constraint rows that do not fit in shared memory
+    float *row_scratch, *prow_scratch, *pdesc_scratch;
+    int *cand_scratch; int max_cand;     // k_substeps: capsule-pair candidates per env (upper bound: all capsule pairs of all group pairs)
+      // k_substeps: local / pair constraint rows that do not fit in shared memory
     long long *warp_trace;        // [ceil(N/E)][MQE_TRACE_COLS] k_substeps per-warp trace
     int trace;                    // MQE_TRACE=1: also accumulate per-phase cycles into the trace rows
     int *stats;                   // [8]

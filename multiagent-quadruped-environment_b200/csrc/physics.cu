@@ -364,7 +364,7 @@ __device__ __forceinline__ float robot_side_regs(int k, V3 r, V3 d, V3 a1, V3 a2
     return dd;
 }
 
-__global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int maxpair, int spair) {
+__global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int maxpair, int spair, int max_cand) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -888,6 +888,14 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             }
             if (env >= p.N) close = false;
             bool any_close = __ballot_sync(env_mask, close) != 0u;
+            unsigned t_sub = 0;
+            if (p.trace && rank_in_env == 0) t_sub = (unsigned)clock();
+#define SUB_MARK(k)                                                                                        \
+    if (p.trace && rank_in_env == 0) {                                                                     \
+        const unsigned now_ = (unsigned)clock();                                                           \
+        atomicAdd(reinterpret_cast<unsigned long long *>(tr + 4 + (k)), (unsigned long long)(now_ - t_sub)); \
+        t_sub = now_;                                                                                      \
+    }
             if (any_close) {
                 // publish the operators other lanes need to build pair rows, and the capsule end points (only now:
                 // most substeps have no dynamic pair in range)
@@ -919,6 +927,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     if (leg == 0) rs[RS_BOUND] = bound * 1.0001f + 1e-5f;
                 }
                 __syncwarp(env_mask);
+                SUB_MARK(11);
                 // capsule culling: bit ci of capmask[X][Y] = capsule ci of group X reaches into the true bounding sphere of
                 // group Y (+ contact offset).  A pair (X,ci,Y,cj) can only touch if both bits are set, so the narrow phase
                 // below skips everything else -- exact, it never drops a pair the full enumeration would accept.
@@ -956,12 +965,19 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 }
                 if (env >= p.N) live_any = false;
                 __syncwarp(env_mask);
+                SUB_MARK(12);
                 const bool any_live = __ballot_sync(env_mask, live_any) != 0u;
                 if (any_live) {
                     // ---- narrow phase.  Candidates are enumerated from the masks -- capsule ci of X (bit set in mask[X][Y])
                     // against capsule cj of Y (bit set in mask[Y][X]), groups X < Y, ci then cj ascending: the oracle's loop
                     // order restricted to pairs that can touch, so contact slots come out in the same canonical order.
                     // Hits only record a descriptor; rows are built afterwards by all lanes of the env.
+                    // Stage 1: a bounding-sphere test per capsule pair (centre distance against half lengths + radii + offset; it
+                    // can only pass pairs the exact test might accept) compacts the candidates, still in canonical order, into a
+                    // per-env list.  ci runs over the set bits of mask[X][Y] for all lanes together; lane `rank` owns the set bits
+                    // number rank, rank + L, rank + 2L, ... of mask[Y][X], so every round covers L consecutive cj in order.
+                    int *cand = p.cand_scratch + (size_t)env * max_cand;
+                    int ncand = 0;
                     for (int X = 0; X < Gc - 1; X++)
                         for (int Y = X + 1; Y < Gc; Y++) {
                             const unsigned mXY = (unsigned)capmask[X * G + Y], mYX = (unsigned)capmask[Y * G + X];
@@ -972,42 +988,82 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                             const float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
                             const float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
                             if (!(dx * dx + dy * dy + dz * dz <= lim * lim)) continue;
-                            const int ny = __popc(mYX), ncombo = __popc(mXY) * ny;
-                            for (int t0 = 0; t0 < ncombo; t0 += lanes_per_env) {
-                                const int c = t0 + rank_in_env;
-                                bool hit = false;
-                                V3 cn = mk(0, 0, 0), cpos = mk(0, 0, 0);
-                                float cgap = 0.f;
-                                int ci = 0, cj = 0;
-                                if (c < ncombo) {
-                                    ci = nth_set_bit(mXY, c / ny); cj = nth_set_bit(mYX, c % ny);
-                                    const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
-                                    V3 c1, c2;
-                                    seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
-                                    V3 dv = c1 - c2;
-                                    float dist = sqrtf(dot(dv, dv));
-                                    cgap = dist - ca[6] - cb[6];
-                                    if (cgap < p.coff && dist >= 1e-9f) {
-                                        hit = true;
-                                        cn = (1.f / dist) * dv;
-                                        cpos = c2 + (cb[6] + 0.5f * cgap) * cn;
-                                    }
+                            unsigned mine = 0;
+                            {
+                                unsigned t = mYX;
+                                int idx = 0, next = rank_in_env;
+                                while (t) {
+                                    const unsigned low = t & (0u - t);
+                                    if (idx == next) { mine |= low; next += lanes_per_env; }
+                                    t ^= low; idx++;
                                 }
-                                const unsigned hb = __ballot_sync(env_mask, hit);
-                                const int slot = npair + __popc(hb & ((1u << lane) - 1u));
-                                npair += __popc(hb);
-                                if (hit && slot < maxpair) {
-                                    float *ds = pdesc + slot * PDESCF;
-                                    const int rba = X < A ? X * MQE_NUM_BODIES + (int)md->caps[ci][1] : A * MQE_NUM_BODIES + (X - A);
-                                    const int rbb = Y < A ? Y * MQE_NUM_BODIES + (int)md->caps[cj][1] : A * MQE_NUM_BODIES + (Y - A);
-                                    ds[0] = cn.x; ds[1] = cn.y; ds[2] = cn.z; ds[3] = __int_as_float(rba); ds[4] = __int_as_float(rbb);
-                                    ds[5] = cpos.x; ds[6] = cpos.y; ds[7] = cpos.z; ds[8] = cgap;
-                                    ds[9] = __int_as_float(X | (ci << 8) | (Y << 16) | (cj << 24));
+                            }
+                            const int rounds = (__popc(mYX) + lanes_per_env - 1) / lanes_per_env;
+                            for (unsigned ma = mXY; ma; ma &= ma - 1u) {
+                                const int ci = __ffs(ma) - 1;
+                                const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP);
+                                const V3 a0 = mk(ca[0], ca[1], ca[2]), a1 = mk(ca[3], ca[4], ca[5]);
+                                const V3 cA = 0.5f * (a0 + a1), dA = a1 - a0;
+                                const float reachA = 0.5f * sqrtf(dot(dA, dA)) + ca[6] + p.coff;
+                                unsigned mb = mine;
+                                for (int r = 0; r < rounds; r++) {
+                                    bool ok = false;
+                                    int cj = 0;
+                                    if (mb) {
+                                        cj = __ffs(mb) - 1;
+                                        mb &= mb - 1u;
+                                        const float *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
+                                        const V3 b0 = mk(cb[0], cb[1], cb[2]), b1 = mk(cb[3], cb[4], cb[5]);
+                                        const V3 dc = cA - 0.5f * (b0 + b1), dB = b1 - b0;
+                                        const float reach = (reachA + 0.5f * sqrtf(dot(dB, dB)) + cb[6]) * 1.0001f + 1e-6f;
+                                        ok = dot(dc, dc) <= reach * reach;
+                                    }
+                                    const unsigned ob = __ballot_sync(env_mask, ok);
+                                    if (ok) cand[ncand + __popc(ob & ((1u << lane) - 1u))] = X | (ci << 8) | (Y << 16) | (cj << 24);
+                                    ncand += __popc(ob);
                                 }
                             }
                         }
+                    __syncwarp(env_mask);
+                    // Stage 2: exact segment / segment test on the candidates
+                    for (int t0 = 0; t0 < ncand; t0 += lanes_per_env) {
+                        const int c = t0 + rank_in_env;
+                        bool hit = false;
+                        V3 cn = mk(0, 0, 0), cpos = mk(0, 0, 0);
+                        float cgap = 0.f;
+                        int X = 0, Y = 0, ci = 0, cj = 0;
+                        if (c < ncand) {
+                            const unsigned ent = (unsigned)cand[c];
+                            X = ent & 0xff; ci = (ent >> 8) & 0xff; Y = (ent >> 16) & 0xff; cj = ent >> 24;
+                            const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
+                            const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
+                            const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
+                            V3 c1, c2;
+                            seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
+                            V3 dv = c1 - c2;
+                            float dist = sqrtf(dot(dv, dv));
+                            cgap = dist - ca[6] - cb[6];
+                            if (cgap < p.coff && dist >= 1e-9f) {
+                                hit = true;
+                                cn = (1.f / dist) * dv;
+                                cpos = c2 + (cb[6] + 0.5f * cgap) * cn;
+                            }
+                        }
+                        const unsigned hb = __ballot_sync(env_mask, hit);
+                        const int slot = npair + __popc(hb & ((1u << lane) - 1u));
+                        npair += __popc(hb);
+                        if (hit && slot < maxpair) {
+                            float *ds = pdesc + slot * PDESCF;
+                            const int rba = X < A ? X * MQE_NUM_BODIES + (int)md->caps[ci][1] : A * MQE_NUM_BODIES + (X - A);
+                            const int rbb = Y < A ? Y * MQE_NUM_BODIES + (int)md->caps[cj][1] : A * MQE_NUM_BODIES + (Y - A);
+                            ds[0] = cn.x; ds[1] = cn.y; ds[2] = cn.z; ds[3] = __int_as_float(rba); ds[4] = __int_as_float(rbb);
+                            ds[5] = cpos.x; ds[6] = cpos.y; ds[7] = cpos.z; ds[8] = cgap;
+                            ds[9] = __int_as_float(X | (ci << 8) | (Y << 16) | (cj << 24));
+                        }
+                    }
                     npair = min(npair, maxpair);
                     __syncwarp(env_mask);
+                    SUB_MARK(13);
                     // ---- rows: one (contact, direction) per lane and round instead of all six sides in the lane that found the hit
                     for (int item = rank_in_env; item < 3 * npair; item += lanes_per_env) {
                         const int slot = item / 3, dch = item - 3 * slot;
@@ -1036,6 +1092,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     }
                 }
             }
+            SUB_MARK(14);
             if (obb) {
                 // robot probes on the plank / the push box: canonical order = robot ascending, probe-table order (two-pass compaction)
                 const float *nsS = wbase + E * A * RS_SIZE + (e_loc * P) * NS_SIZE;
@@ -1399,5 +1456,5 @@ extern "C" cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int max
         if (e != cudaSuccess) return e;
         configured = pl.smem;
     }
-    return launch_heavy(k_substeps, dim3(pl.grid), dim3(pl.warps * 32), pl.smem, st, p, nsub, maxpair, pl.spair);
+    return launch_heavy(k_substeps, dim3(pl.grid), dim3(pl.warps * 32), pl.smem, st, p, nsub, maxpair, pl.spair, p.max_cand);
 }
