@@ -43,19 +43,18 @@
 #define NS_ROWS 28
 #define NS_CMETA (NS_ROWS + 12 * ROWF)
 #define NS_SIZE (NS_CMETA + 16)
-// per-env shared block
-#define ES_CNT 0
-#define ES_ROWS 4
-// the first `spair` pair contacts keep their rows in shared memory, the rest (up to maxpair) in a per-env global scratch
-#define ES_MASK(spair) (ES_ROWS + (spair) * 3 * PROWF)      // int capmask[G][G]: capsules of X within reach of group Y
-#define ES_SIZE(spair, G) (ES_MASK(spair) + (((G) * (G) + 3) & ~3))
+// per-warp pair-row pool: E * spair contacts x 3 rows.  Envs claim slots in env order each substep (most substeps only one env
+// of a warp has dynamic contacts, and it then keeps all of them in shared memory); what does not fit goes to a global scratch.
+// per-env: int capmask[G][G] (capsules of X within reach of group Y)
+#define ES_MASKSZ(G) (((G) * (G) + 3) & ~3)
 #define PDESCF 12      // pair-contact descriptor (global scratch): n3, body a, body b, point3, gap, packed (X, ci, Y, cj)
 
 #define ACTW_FLOATS 1316   // 192 + 32 + 1024 + 32 + 32 + 1 = 1313, padded
 #define TBL_INTS 80        // per-leg probe lists [4][10] (count + 9 ids), per-leg capsule lists [4][10]
 
 __host__ __device__ inline int physics_warp_smem_floats(int A, int P, int E, int spair, int maxpair) {
-    return E * A * RS_SIZE + E * P * NS_SIZE + E * ES_SIZE(spair, A + P);
+    (void)maxpair;
+    return E * A * RS_SIZE + E * P * NS_SIZE + E * spair * 3 * PROWF + E * ES_MASKSZ(A + P);
 }
 __host__ __device__ inline int physics_cta_header_floats() { return (int)(sizeof(MqeRobotModel) / 4) + ACTW_FLOATS + TBL_INTS; }
 
@@ -437,13 +436,15 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
     const int grp = is_robot ? ag : A + pn;                              // group index inside the env
     float *rs = wbase + (e_loc * A + ag) * RS_SIZE;                      // my robot block
     float *ns = wbase + E * A * RS_SIZE + (e_loc * P + pn) * NS_SIZE;    // my npc block
-    float *es = wbase + E * A * RS_SIZE + E * P * NS_SIZE + e_loc * ES_SIZE(spair, G);
+    float *const pool = wbase + E * A * RS_SIZE + E * P * NS_SIZE;
+    int *const capmask = reinterpret_cast<int *>(pool + E * spair * 3 * PROWF) + e_loc * ES_MASKSZ(G);
+    int my_start = e_loc * spair, my_smem = spair;                      // this env's slice of the pool (contacts), reassigned per substep
     // row stores: shared memory first, global scratch for the overflow (generic pointers; same layout in both)
     float *const grows = p.row_scratch + (size_t)(env * A + ag) * ((MQE_MAX_ROWS - SROWS) * ROWF);
-    float *const gprows = p.prow_scratch + (size_t)env * ((size_t)(maxpair - spair) * 3 * PROWF);
+    float *const gprows = p.prow_scratch + (size_t)env * ((size_t)maxpair * 3 * PROWF);
     float *const pdesc = p.pdesc_scratch + (size_t)env * ((size_t)maxpair * PDESCF);
     auto lrow = [&](int i) -> float * { return i < SROWS ? rs + RS_ROWS + i * ROWF : grows + (i - SROWS) * ROWF; };
-    auto prow = [&](int i) -> float * { return i < 3 * spair ? es + ES_ROWS + i * PROWF : gprows + (i - 3 * spair) * PROWF; };
+    auto prow = [&](int i) -> float * { return i < 3 * my_smem ? pool + (3 * my_start + i) * PROWF : gprows + (i - 3 * my_smem) * PROWF; };
     const unsigned quad_mask = is_robot ? (0xFu << (lane & ~3)) : (1u << lane);
     unsigned env_mask = 0;
     {
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             }
             ns[NS_FORCE] = ns[NS_FORCE + 1] = ns[NS_FORCE + 2] = 0.f;
         }
-        if (rank_in_env == 0) ((int *)es)[ES_CNT] = 0;
+        my_start = e_loc * spair; my_smem = spair;
         __syncwarp();
 
         PHASE_MARK(1);
@@ -872,6 +873,9 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         PHASE_MARK(2);
         // ================================================================ P3b: dynamic-vs-dynamic pairs (capsule / capsule)
         int npair = 0;
+        bool pairs_pending = false;                      // capsule contacts recorded in pdesc, rows not built yet
+        unsigned t_sub = 0;
+        if (p.trace && rank_in_env == 0) t_sub = (unsigned)clock();
         if (G > 1 && (is_robot || is_npc)) {
             // broadphase over group pairs
             bool close = false;
@@ -888,8 +892,6 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             }
             if (env >= p.N) close = false;
             bool any_close = __ballot_sync(env_mask, close) != 0u;
-            unsigned t_sub = 0;
-            if (p.trace && rank_in_env == 0) t_sub = (unsigned)clock();
 #define SUB_MARK(k)                                                                                        \
     if (p.trace && rank_in_env == 0) {                                                                     \
         const unsigned now_ = (unsigned)clock();                                                           \
@@ -931,7 +933,6 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 // capsule culling: bit ci of capmask[X][Y] = capsule ci of group X reaches into the true bounding sphere of
                 // group Y (+ contact offset).  A pair (X,ci,Y,cj) can only touch if both bits are set, so the narrow phase
                 // below skips everything else -- exact, it never drops a pair the full enumeration would accept.
-                int *capmask = reinterpret_cast<int *>(es + ES_MASK(spair));
                 bool live_any = false;
                 for (int Y = 0; Y < Gc; Y++) {
                     if (Y == grp || grp >= Gc) continue;
@@ -1062,34 +1063,51 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         }
                     }
                     npair = min(npair, maxpair);
-                    __syncwarp(env_mask);
+                    pairs_pending = npair > 0;
                     SUB_MARK(13);
-                    // ---- rows: one (contact, direction) per lane and round instead of all six sides in the lane that found the hit
-                    for (int item = rank_in_env; item < 3 * npair; item += lanes_per_env) {
-                        const int slot = item / 3, dch = item - 3 * slot;
-                        const float *ds = pdesc + slot * PDESCF;
-                        const V3 cn = mk(ds[0], ds[1], ds[2]), cpos = mk(ds[5], ds[6], ds[7]);
-                        const float cgap = ds[8];
-                        const unsigned ent = (unsigned)__float_as_int(ds[9]);
-                        const int X = ent & 0xff, ci = (ent >> 8) & 0xff, Y = (ent >> 16) & 0xff, cj = ent >> 24;
-                        V3 t1, t2;
-                        tangent_basis(cn, t1, t2);
-                        const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
-                        const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
-                        const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
-                        const int la = X < A ? (int)md->caps[ci][0] : 0, lb = Y < A ? (int)md->caps[cj][0] : 0;
-                        const V3 ra = cpos - mk(ox[0], ox[1], ox[2]), rb_ = cpos - mk(oy[0], oy[1], oy[2]);
-                        const int lega = la > 0 ? (la - 1) / 3 : 0, legb = lb > 0 ? (lb - 1) / 3 : 0;
-                        const V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
-                        float *row = prow(item);
-                        float dd = X < A ? robot_side_from_smem(bx_, la, ra, d, row) : npc_side(p, ra, d, row);
-                        dd += Y < A ? robot_side_from_smem(by_, lb, rb_, -d, row + 20) : npc_side(p, rb_, -d, row + 20);
-                        row[18] = row[19] = row[38] = row[39] = 0.f;
-                        row[40] = 1.f / (dd + p.cfm);
-                        row[41] = dch == 0 ? contact_bias(p, cgap) : 0.f;
-                        row[42] = 0.f;
-                        row[43] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
-                    }
+                }
+            }
+        }
+        __syncwarp();
+        // claim pool slots in env order (capsule path; the oriented-box path keeps its static slice)
+        if (!obb && G > 1) {
+            if (__ballot_sync(FULL, npair > 0)) {
+                int start = 0;
+                for (int e2 = 0; e2 < E; e2++) {
+                    const int n = __shfl_sync(FULL, npair, e2 * 4 * A);
+                    if (e2 < e_loc) start += n;
+                }
+                my_start = min(start, E * spair);
+                my_smem = min(npair, E * spair - my_start);
+            }
+        }
+        if (G > 1 && (is_robot || is_npc)) {
+            if (pairs_pending) {
+                // ---- rows: one (contact, direction) per lane and round instead of all six sides in the lane that found the hit
+                for (int item = rank_in_env; item < 3 * npair; item += lanes_per_env) {
+                    const int slot = item / 3, dch = item - 3 * slot;
+                    const float *ds = pdesc + slot * PDESCF;
+                    const V3 cn = mk(ds[0], ds[1], ds[2]), cpos = mk(ds[5], ds[6], ds[7]);
+                    const float cgap = ds[8];
+                    const unsigned ent = (unsigned)__float_as_int(ds[9]);
+                    const int X = ent & 0xff, ci = (ent >> 8) & 0xff, Y = (ent >> 16) & 0xff, cj = ent >> 24;
+                    V3 t1, t2;
+                    tangent_basis(cn, t1, t2);
+                    const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
+                    const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
+                    const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
+                    const int la = X < A ? (int)md->caps[ci][0] : 0, lb = Y < A ? (int)md->caps[cj][0] : 0;
+                    const V3 ra = cpos - mk(ox[0], ox[1], ox[2]), rb_ = cpos - mk(oy[0], oy[1], oy[2]);
+                    const int lega = la > 0 ? (la - 1) / 3 : 0, legb = lb > 0 ? (lb - 1) / 3 : 0;
+                    const V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
+                    float *row = prow(item);
+                    float dd = X < A ? robot_side_from_smem(bx_, la, ra, d, row) : npc_side(p, ra, d, row);
+                    dd += Y < A ? robot_side_from_smem(by_, lb, rb_, -d, row + 20) : npc_side(p, rb_, -d, row + 20);
+                    row[18] = row[19] = row[38] = row[39] = 0.f;
+                    row[40] = 1.f / (dd + p.cfm);
+                    row[41] = dch == 0 ? contact_bias(p, cgap) : 0.f;
+                    row[42] = 0.f;
+                    row[43] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
                 }
             }
             SUB_MARK(14);
