@@ -224,6 +224,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     CK(dalloc(s, &p.episode, (size_t)N)); CK(dalloc(s, &p.hist_dirty, (size_t)N)); CK(dalloc(s, &p.stats, (size_t)8));
     CK(dalloc(s, &p.ctr, (size_t)4));
     CK(dalloc(s, &p.warp_trace, (size_t)((N + p.E - 1) / p.E) * MQE_TRACE_COLS));
+    { const char *e = getenv("MQE_CTA_SYNC"); p.cta_sync = e ? atoi(e) : 1; }
     { const char *e = getenv("MQE_TRACE"); p.trace = (e && e[0] == '1') ? 1 : 0; }
     CK(dalloc(s, &p.row_scratch, mqe_substeps_row_scratch_floats(N, A), false));
     CK(dalloc(s, &p.prow_scratch, mqe_substeps_prow_scratch_floats(N, s->maxpair), false));

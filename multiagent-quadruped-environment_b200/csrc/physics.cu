@@ -489,8 +489,14 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
     int stat_local = 0, stat_lim = 0, stat_pair = 0, stat_rows = 0;
 
     PHASE_MARK(6);
+    // warps of the CTA that own envs (the others returned above); they re-align at phase boundaries so that the seven warps of
+    // an SM walk the 240 KB instruction stream together instead of each missing the instruction cache on its own
+    const int live_threads = 32 * min(nwarps, (p.N + E - 1) / E - (int)blockIdx.x * nwarps);
+#define CTA_ALIGN(level)                                                                 \
+    if (p.cta_sync >= (level)) asm volatile("bar.sync 1, %0;" ::"r"(live_threads) : "memory");
     for (int sub = 0; sub < nsub; sub++) {
         const bool last = (sub == nsub - 1);
+        CTA_ALIGN(1);
         // ================================================================ P1: actuator network (go1.py:315-354, 369-380)
         if (active && is_robot) {
             float x[3][6];
@@ -551,6 +557,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         }
 
         PHASE_MARK(0);
+        CTA_ALIGN(2);
         // ================================================================ P2: kinematics + dynamics (robot lanes), npc prediction
         float vb[6] = {0, 0, 0, 0, 0, 0}, u[3] = {0, 0, 0};   // solve coordinates
         float Gm[18];                                           // my leg's G (6x3 row-major)
@@ -700,6 +707,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         __syncwarp();
 
         PHASE_MARK(1);
+        CTA_ALIGN(2);
         // ================================================================ P3: rows.  joint limits, then world contacts
         int nrows = 0, nlim = 0;
         if (is_robot) {
@@ -785,7 +793,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 float *cmeta = rs + RS_CMETA + slot * 4;
                 cmeta[0] = n.x; cmeta[1] = n.y; cmeta[2] = n.z; cmeta[3] = __int_as_float(body);
                 int r0 = nlim + 3 * slot;
-#pragma unroll
+#pragma unroll 1          // rolled: the body (~850 instructions) then fits the 32 KB L1.5 instruction cache, unrolled it does not
                 for (int dch = 0; dch < 3; dch++) {
                     V3 d = dch == 0 ? n : (dch == 1 ? t1 : t2);
                     V3 rxd = cross(r, d);
@@ -825,6 +833,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 tangent_basis(n, t1, t2);
                 float *cmeta = ns + NS_CMETA + ncon * 4;
                 cmeta[0] = n.x; cmeta[1] = n.y; cmeta[2] = n.z; cmeta[3] = 0.f;
+#pragma unroll 1
                 for (int dch = 0; dch < 3; dch++) {
                     V3 d = dch == 0 ? n : (dch == 1 ? t1 : t2);
                     float *row = ns + NS_ROWS + (3 * ncon + dch) * ROWF;
@@ -853,6 +862,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     tangent_basis(n, t1, t2);
                     float *cmeta = ns + NS_CMETA + ncon * 4;
                     cmeta[0] = n.x; cmeta[1] = n.y; cmeta[2] = n.z; cmeta[3] = 0.f;
+#pragma unroll 1
                     for (int dch = 0; dch < 3; dch++) {
                         V3 d = dch == 0 ? n : (dch == 1 ? t1 : t2);
                         float *row = ns + NS_ROWS + (3 * ncon + dch) * ROWF;
@@ -1167,6 +1177,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     float *cmeta = pdesc + slot * PDESCF;
                     cmeta[0] = cn.x; cmeta[1] = cn.y; cmeta[2] = cn.z;
                     cmeta[3] = __int_as_float(ag * MQE_NUM_BODIES + body); cmeta[4] = __int_as_float(A * MQE_NUM_BODIES);
+#pragma unroll 1
                     for (int dch = 0; dch < 3; dch++) {
                         V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
                         float *row = prow(3 * slot + dch);
@@ -1187,6 +1198,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         if (active && (leg == 0 || is_npc)) stat_rows = max(stat_rows, nrows);
 
         PHASE_MARK(3);
+        CTA_ALIGN(2);
         // ================================================================ P4: projected Gauss-Seidel
         {
             const int quad_base = lane & ~3;
@@ -1282,6 +1294,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         }
 
         PHASE_MARK(4);
+        CTA_ALIGN(3);
         // ================================================================ P5: contact force report (last substep), integrate
         if (last) {
             float idt = 1.f / p.dt;
