@@ -182,6 +182,33 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
         memcpy(aw.data() + 1248, w.act_b1, 32 * 4);
         memcpy(aw.data() + 1280, w.act_w2, 32 * 4); aw[1312] = w.act_b2[0];
         CK(dupload(s, &p.act_w, aw.data(), aw.size()));
+        // CTA header of k_substeps: model, actuator weights, and which lane of a robot's quad owns which probe / capsule (leg
+        // links belong to their leg, base colliders are dealt round-robin (probes) or to leg 0 (capsules); lists keep table order)
+        {
+            const size_t mf = sizeof(MqeRobotModel) / 4;
+            std::vector<float> hdr(mf + 1316 + 80, 0.f);
+            memcpy(hdr.data(), &d->model, sizeof(MqeRobotModel));
+            memcpy(hdr.data() + mf, aw.data(), 1316 * sizeof(float));
+            int *tbl = reinterpret_cast<int *>(hdr.data() + mf + 1316);
+            for (int lg = 0; lg < 4; lg++) {
+                int n = 0, nbase = 0;
+                for (int pi = 0; pi < d->model.n_probes; pi++) {
+                    const int link = (int)d->model.probes[pi][0];
+                    const bool mine = link == 0 ? ((nbase++ & 3) == lg) : ((link - 1) / 3 == lg);
+                    if (mine && n < 9) tbl[lg * 10 + 1 + n++] = pi;
+                }
+                tbl[lg * 10] = n;
+                n = 0;
+                for (int ci = 0; ci < d->model.n_caps; ci++) {
+                    const int link = (int)d->model.caps[ci][0];
+                    const bool mine = link == 0 ? (lg == 0) : ((link - 1) / 3 == lg);
+                    if (mine && n < 9) tbl[40 + lg * 10 + 1 + n++] = ci;
+                }
+                tbl[40 + lg * 10] = n;
+            }
+            CK(dupload(s, &p.substep_hdr, hdr.data(), hdr.size()));
+            CK(cudaStreamSynchronize(s->stream));
+        }
         // layer 0 of both networks, age-blocked and padded: [768][30][80]
         const int RR = MQE_HIST_FRAMES * MQE_HIST_PAD;
         std::vector<float> w0((size_t)768 * RR, 0.f), b0(768), wl(512 * 2);

@@ -41,6 +41,7 @@ struct DevParams {
     // device pointers ------------------------------------------------------------------
     const float *sdf, *env_origins, *agent_origins, *base_init, *npc_init, *npc_dof_default;
     const MqeRobotModel *model;   // global copy (kernels stage it in shared memory)
+    const float *substep_hdr;     // [model | act_w | per-leg probe / capsule lists]: the CTA header of k_substeps, one bulk copy
     const float *act_w;           // packed actuator weights: W0[32][6] b0[32] W1[32][32] b1[32] W2[32] b2
     const float *loc_default;     // [70]
     float *root, *dof, *contact, *torques, *actions, *last_actions;
@@ -98,6 +99,33 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 template <typename... KArgs, typename... Args>      // heavy grids: frame, layer 0, substeps, post
 static inline cudaError_t launch_heavy(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     return launch_pdl_if(mqe_pdl_level() >= 2, kernel, grid, block, smem, st, args...);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------- mbarrier / bulk copy
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), done = 0;
+    for (unsigned long long spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (spin > (1ull << 28)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 #endif
 

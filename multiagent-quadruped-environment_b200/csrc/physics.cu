@@ -368,36 +368,19 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
     pdl_launch_dependents();
-    // ---- CTA header: robot model + actuator weights ----
+    // ---- CTA header: robot model + actuator weights + per-leg probe / capsule lists, one 8 KB bulk copy (api.cu builds it) ----
+    __shared__ uint64_t hdr_bar;
     MqeRobotModel *md = reinterpret_cast<MqeRobotModel *>(smem);
     float *actw = smem + sizeof(MqeRobotModel) / 4;
-    {
-        const float *src = reinterpret_cast<const float *>(p.model);
-        for (int i = threadIdx.x; i < (int)(sizeof(MqeRobotModel) / 4); i += blockDim.x) smem[i] = src[i];
-        for (int i = threadIdx.x; i < 1313; i += blockDim.x) actw[i] = p.act_w[i];
-    }
-    __syncthreads();
-    // which lane of a robot's quad owns which probe / capsule: leg links belong to their leg, base colliders are dealt
-    // round-robin (probes) or to leg 0 (capsules).  Built once per CTA; lists keep the canonical (table) order.
     int *tbl = reinterpret_cast<int *>(actw + ACTW_FLOATS);
-    if (threadIdx.x < 4) {
-        const int lg = threadIdx.x;
-        int n = 0, nbase = 0;
-        for (int pi = 0; pi < md->n_probes; pi++) {
-            int link = (int)md->probes[pi][0];
-            bool mine = link == 0 ? ((nbase++ & 3) == lg) : ((link - 1) / 3 == lg);
-            if (mine && n < 9) tbl[lg * 10 + 1 + n++] = pi;
-        }
-        tbl[lg * 10] = n;
-        n = 0;
-        for (int ci = 0; ci < md->n_caps; ci++) {
-            int link = (int)md->caps[ci][0];
-            bool mine = link == 0 ? (lg == 0) : ((link - 1) / 3 == lg);
-            if (mine && n < 9) tbl[40 + lg * 10 + 1 + n++] = ci;
-        }
-        tbl[40 + lg * 10] = n;
+    if (threadIdx.x == 0) {
+        mbar_init(&hdr_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&hdr_bar, (uint32_t)physics_cta_header_floats() * 4u);
+        bulk_g2s(smem, p.substep_hdr, (uint32_t)physics_cta_header_floats() * 4u, &hdr_bar);
     }
     __syncthreads();
+    mbar_wait(&hdr_bar, 0);
     pdl_wait();                                         // constants above were staged in the predecessor's shadow
     const int A = p.A, P = p.Pd, E = p.E, G = A + P;   // P: NPCs that own a lane
     const int GA = p.G;                                 // actors per env in the root-state tensor
@@ -1249,9 +1232,11 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     // leg on each side forms that side's J.w, two shuffles combine them, every lane of the env applies the same
                     // clamp, and the multiplier is carried to the next sweep through the row (one __syncwarp per sweep).
                     float lam_np = 0.f;
+                    float4 tl_next = *reinterpret_cast<const float4 *>(prow(0) + 40);
                     for (int i = 0; i < 3 * npair; i++) {
                         float *row = prow(i);
-                        const float4 tl = *reinterpret_cast<const float4 *>(row + 40);            // dinv, bias, lambda, meta
+                        const float4 tl = tl_next;                                                 // dinv, bias, lambda, meta
+                        if (i + 1 < 3 * npair) tl_next = *reinterpret_cast<const float4 *>(prow(i + 1) + 40);   // one row ahead: meta picks the side to load
                         const int meta = __float_as_int(tl.w);
                         const int ga = meta & 15, la = (meta >> 4) & 15, gb = (meta >> 8) & 15, lb = (meta >> 12) & 15, kind = (meta >> 16) & 1;
                         const bool inA = grp == ga, inB = grp == gb;
