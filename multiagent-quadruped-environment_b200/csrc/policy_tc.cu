@@ -215,14 +215,25 @@ __host__ __device__ constexpr int lt_stage_bytes(int ncta) { return 2 * LT_A_PLA
 __host__ __device__ constexpr int lt_smem_bytes(int ncta) { return LT_STAGES * lt_stage_bytes(ncta) + 128; }
 
 #define LT_THREADS 320                                       // producer warp, MMA warp, 8 epilogue warps
-template <int NCTA>
+// Fused network heads.  HEAD > 0: the layer that follows (adapt.4: 128 -> 2, body.6: 128 -> 12) is so small that the epilogue
+// evaluates it in fp32 straight from the accumulator row each thread already holds, instead of writing planes for a 16-column
+// tensor-core launch.  LATENT: with the latent in hand the same CTA also finishes body.0 for its 128 rows,
+// planes(ELU(Z_body + W_lat latent)) (go1.py:404-406), which used to be a kernel of its own.
+struct HeadArgs {
+    const float *hw, *hb;          // [HEAD][128] row-major fp32, [HEAD]
+    float *hy;                     // [M][HEAD]
+    const float *Z, *wlat;         // LATENT: layer-0 output [M][768], latent columns of body.0 [512][2]
+    unsigned short *l_hi, *l_lo;   // LATENT: body.0 activation planes (64 k-chunks)
+};
+template <int NCTA, int HEAD = 0, bool LATENT = false>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo, int K,
             const unsigned short *__restrict__ w_hi, const unsigned short *__restrict__ w_lo, const float *__restrict__ bias,
             float *__restrict__ Y, int ldy, int n_valid,                       // fp32 output (heads) when Y != nullptr
             unsigned short *__restrict__ o_hi, unsigned short *__restrict__ o_lo, int out_kchunks,   // plane output otherwise
-            int M, int elu, int passes) {
+            int M, int elu, int passes, HeadArgs ha) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    static_assert(HEAD == 0 || NCTA == 128, "fused heads read a full 128-wide activation row");
     constexpr int STAGE = lt_stage_bytes(NCTA);
     constexpr int W_PLANE = NCTA * LT_BK * 2;
     constexpr uint32_t TCOLS = NCTA < 32 ? 32 : NCTA;
@@ -231,11 +242,14 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
     uint64_t *accum = empty + LT_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
     __shared__ float s_bias[NCTA];
+    __shared__ float s_hw[HEAD > 0 ? HEAD * 128 : 1], s_part[HEAD > 0 ? HEAD * 128 : 1], s_lat[LATENT ? 256 : 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntile = blockIdx.x, mtile = blockIdx.y;
     pdl_launch_dependents();
     const int nk = K / LT_BK;
     for (int i = threadIdx.x; i < NCTA; i += blockDim.x) s_bias[i] = (ntile * NCTA + i < n_valid) ? bias[ntile * NCTA + i] : 0.f;   // constants
+    if (HEAD > 0)
+        for (int i = threadIdx.x; i < HEAD * 128; i += blockDim.x) s_hw[i] = ha.hw[i];
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < LT_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -303,6 +317,9 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
         const int half = (warp - 2) >> 2;                    // the two epilogue warps of a quarter split the columns
         const int orow = mtile * 128 + q * 32 + lane;
         constexpr int NCH = NCTA / 16, CH0 = (NCH + 1) / 2;
+        float hp[HEAD > 0 ? HEAD : 1];
+#pragma unroll
+        for (int j = 0; j < (HEAD > 0 ? HEAD : 1); j++) hp[j] = 0.f;
 #pragma unroll 1
         for (int c = half ? CH0 : 0; c < (half ? NCH : CH0); c++) {
             uint32_t v[16];
@@ -320,7 +337,12 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
                 float t = __uint_as_float(v[i]) + s_bias[c * 16 + i];
                 f[i] = elu ? elu1_tc(t) : t;
             }
-            if (Y) {
+            if (HEAD > 0) {
+#pragma unroll
+                for (int j = 0; j < HEAD; j++)
+#pragma unroll
+                    for (int i = 0; i < 16; i++) hp[j] = fmaf(f[i], s_hw[j * 128 + c * 16 + i], hp[j]);
+            } else if (Y) {
                 if (orow < M)
 #pragma unroll
                     for (int i = 0; i < 16; i++)
@@ -333,6 +355,48 @@ k_linear_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__res
                 split_bf16x8(f + 8, hi, lo);
                 o = plane_index(orow, n0 + 8, out_kchunks);
                 *reinterpret_cast<uint4 *>(o_hi + o) = hi; *reinterpret_cast<uint4 *>(o_lo + o) = lo;
+            }
+        }
+        if (HEAD > 0) {                                      // the two warps of a lane quarter each hold half of the row's dot products
+            const int r = q * 32 + lane;
+            if (half == 1)
+#pragma unroll
+                for (int j = 0; j < HEAD; j++) s_part[r * HEAD + j] = hp[j];
+            asm volatile("bar.sync 2, 256;" ::: "memory");   // the 8 epilogue warps
+            if (half == 0) {
+#pragma unroll
+                for (int j = 0; j < HEAD; j++) {
+                    const float o = (hp[j] + s_part[r * HEAD + j]) + __ldg(ha.hb + j);
+                    if (orow < M) ha.hy[(size_t)orow * HEAD + j] = o;
+                    if (LATENT && j < 2) s_lat[r * 2 + j] = o;
+                }
+            }
+            if (LATENT) {
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                // one (row, 8-column chunk) per thread and trip; consecutive threads take consecutive rows so plane stores coalesce
+                for (int t = (int)threadIdx.x - 64; t < 128 * 64; t += 256) {
+                    const int chunk = t >> 7, m = t & 127, row = mtile * 128 + m;
+                    float v[8];
+                    if (row < M) {
+                        const float *z = ha.Z + (size_t)row * 768 + 256 + chunk * 8;
+                        const float4 a = *reinterpret_cast<const float4 *>(z), b = *reinterpret_cast<const float4 *>(z + 4);
+                        const float l0 = s_lat[m * 2], l1 = s_lat[m * 2 + 1];
+                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int n = chunk * 8 + i;
+                            v[i] = elu1_tc(v[i] + __ldg(ha.wlat + n * 2) * l0 + __ldg(ha.wlat + n * 2 + 1) * l1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[i] = 0.f;
+                    }
+                    uint4 hi, lo;
+                    split_bf16x8(v, hi, lo);
+                    const size_t o = plane_index(row, chunk * 8, 64);
+                    *reinterpret_cast<uint4 *>(ha.l_hi + o) = hi;
+                    *reinterpret_cast<uint4 *>(ha.l_lo + o) = lo;
+                }
             }
         }
     }
@@ -448,6 +512,9 @@ extern "C" int mqe_policy_tc_prepare(const MqeWeights *w, int rows, PolicyTcWeig
     if (cudaFuncSetAttribute(k_policy_l0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_linear_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(128)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_linear_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(16)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_linear_tc<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(128)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_linear_tc<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(128)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_linear_tc<128, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(128)) != cudaSuccess) return -1;
     out->blob = blob;
     out->bytes = total * sizeof(unsigned short);
     out->l0_hi = blob;
@@ -476,13 +543,34 @@ extern "C" cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const
     auto PL = [&](int i) { return (unsigned short *)w.p_lo[i]; };
     float *const nof = nullptr;
     unsigned short *const nou = nullptr;
+    const HeadArgs none = {};
     cudaError_t e;
-    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, PH(1), PL(1), 16, M, 1, passes)) != cudaSuccess) return e;
-    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(16), st, PH(1), PL(1), 128, H(1), L(1), pw.ab2, s.latent, 2, 2, nou, nou, 0, M, 0, passes)) != cudaSuccess) return e;
+    // MQE_TC_FUSED_HEADS: 1 (default) the two small heads ride in the epilogue of the layer before them (4 launches);
+    // 2 additionally folds body.0's latent / ELU / plane stage into the adapt kernel (3 launches; measured slower: that stage
+    // then runs on the 64 CTAs of the row tiles instead of the whole chip); 0 one launch per layer (6).
+    static const int fused = [] { const char *v = getenv("MQE_TC_FUSED_HEADS"); return v ? atoi(v) : 1; }();
+    if (fused >= 1) {
+        const HeadArgs h1 = {pw.aw2, pw.ab2, s.latent, s.Z, pw.wlat, PH(2), PL(2)};
+        const HeadArgs h2 = {pw.bw3, pw.bb3, s.act, nullptr, nullptr, nullptr, nullptr};
+        int n = 3;
+        if (fused >= 2) {
+            if ((e = launch_pdl(k_linear_tc<128, 2, true>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, nou, nou, 0, M, 1, passes, h1)) != cudaSuccess) return e;
+        } else {
+            if ((e = launch_pdl(k_linear_tc<128, 2, false>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, nou, nou, 0, M, 1, passes, h1)) != cudaSuccess) return e;
+            if ((e = launch_pdl(k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
+            n = 4;
+        }
+        if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes, none)) != cudaSuccess) return e;
+        if ((e = launch_pdl(k_linear_tc<128, 12, false>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(3), PL(3), 256, H(3), L(3), pw.bb2, nof, 0, 128, nou, nou, 0, M, 1, passes, h2)) != cudaSuccess) return e;
+        *launches += n;
+        return cudaGetLastError();
+    }
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, PH(1), PL(1), 16, M, 1, passes, none)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(16), st, PH(1), PL(1), 128, H(1), L(1), pw.ab2, s.latent, 2, 2, nou, nou, 0, M, 0, passes, none)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
-    if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes)) != cudaSuccess) return e;
-    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(3), PL(3), 256, H(3), L(3), pw.bb2, nof, 0, 128, PH(4), PL(4), 16, M, 1, passes)) != cudaSuccess) return e;
-    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(16), st, PH(4), PL(4), 128, H(4), L(4), pw.bb3, s.act, 12, 12, nou, nou, 0, M, 0, passes)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes, none)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(3), PL(3), 256, H(3), L(3), pw.bb2, nof, 0, 128, PH(4), PL(4), 16, M, 1, passes, none)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<16>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(16), st, PH(4), PL(4), 128, H(4), L(4), pw.bb3, s.act, 12, 12, nou, nou, 0, M, 0, passes, none)) != cudaSuccess) return e;
     *launches += 6;
     return cudaGetLastError();
 }
