@@ -252,6 +252,8 @@ def run_gpu(args):
     h_obs = np.empty((n_local * A, E.OBS_FLOATS), dtype=np.float32)
     h_reset = np.empty(n_local, dtype=np.uint8)
     Ke = min(K, 100)
+    for buf in (h_actions, h_obs, h_reset):                       # caller-owned buffers, page-locked once: DMA source / target
+        eng.pin_host(buf)
     for i in range(3):
         eng.step_host(h_actions[i % n_act], h_obs, h_reset)
     if world > 1:

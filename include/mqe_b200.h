@@ -17,6 +17,7 @@
 #ifndef MQE_B200_H
 #define MQE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -204,6 +205,12 @@ int mqe_sim_step(MqeSim *sim, const float *d_actions);
 /* Same step through HOST buffers: H2D of actions, step, D2H of obs rows / reset flags; blocks until
  * the results are in host memory.  h_obs: [N*A][71] (may be NULL), h_reset: [N] (may be NULL). */
 int mqe_sim_step_host(MqeSim *sim, const float *h_actions, float *h_obs, uint8_t *h_reset);
+
+/* Optional: register a caller-owned host range (cudaHostRegister) so that mqe_sim_step_host copies straight from / into it
+ * instead of through the handle's staging buffers.  The range must stay mapped until mqe_sim_unpin_host / mqe_sim_destroy.
+ * (The reference has no host path of its own here: openrl_ws/utils.py:55-60 does .cpu().numpy() on pageable memory.) */
+int mqe_sim_pin_host(MqeSim *sim, void *h_ptr, size_t bytes);
+int mqe_sim_unpin_host(MqeSim *sim, void *h_ptr);
 
 /* Finer-grained entry points mirroring the individual gym calls (used by tests and by a host that
  * wants to keep the reference's loop structure). */

@@ -47,6 +47,13 @@ struct MqeSim {
     cudaStream_t cap_stream = nullptr;
     bool use_graph = false;
     long long plain_steps = 0;
+    struct Pinned { char *ptr; size_t bytes; };
+    std::vector<Pinned> pinned;          // host ranges registered with mqe_sim_pin_host: mqe_sim_step_host copies straight to / from them
+    bool is_pinned(const void *ptr, size_t bytes) const {
+        for (const auto &r : pinned)
+            if ((const char *)ptr >= r.ptr && (const char *)ptr + bytes <= r.ptr + r.bytes) return true;
+        return false;
+    }
 };
 
 template <typename T>
@@ -89,6 +96,7 @@ int mqe_sim_destroy(MqeSim *s) {
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);
+    for (auto &r : s->pinned) cudaHostUnregister(r.ptr);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     for (void *ptr : s->allocs) cudaFree(ptr);
     if (s->tcw.blob) cudaFree(s->tcw.blob);
@@ -478,20 +486,44 @@ int mqe_sim_step(MqeSim *s, const float *d_actions) {
     return rc;
 }
 
+int mqe_sim_pin_host(MqeSim *s, void *ptr, size_t bytes) {
+    if (!s || !ptr || !bytes) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    if (s->is_pinned(ptr, bytes)) return MQE_OK;
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    s->pinned.push_back({(char *)ptr, bytes});
+    return MQE_OK;
+}
+int mqe_sim_unpin_host(MqeSim *s, void *ptr) {
+    if (!s || !ptr) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    for (size_t i = 0; i < s->pinned.size(); i++)
+        if (s->pinned[i].ptr == (char *)ptr) {
+            CK(cudaStreamSynchronize(s->stream));
+            CK(cudaHostUnregister(ptr));
+            s->pinned.erase(s->pinned.begin() + i);
+            return MQE_OK;
+        }
+    return fail(MQE_ERR_INVALID, "range was not pinned by this handle");
+}
+
 int mqe_sim_step_host(MqeSim *s, const float *h_actions, float *h_obs, uint8_t *h_reset) {
     if (!s || !h_actions) return fail(MQE_ERR_INVALID, "null argument");
     CK(cudaSetDevice(s->device));
     const size_t na = (size_t)s->p.N * s->actrl * 3 * sizeof(float);
-    memcpy(s->h_actions, h_actions, na);
-    CK(cudaMemcpyAsync(s->d_actions_stage, s->h_actions, na, cudaMemcpyHostToDevice, s->stream));
+    const size_t no = (size_t)s->M * MQE_OBS_FLOATS * sizeof(float);
+    // buffers the caller pinned (mqe_sim_pin_host) are DMA sources / targets themselves; anything else goes through the
+    // handle's own pinned staging buffers with one extra host copy each way
+    const bool pa = s->is_pinned(h_actions, na), po = h_obs && s->is_pinned(h_obs, no), pr = h_reset && s->is_pinned(h_reset, s->p.N);
+    if (!pa) memcpy(s->h_actions, h_actions, na);
+    CK(cudaMemcpyAsync(s->d_actions_stage, pa ? h_actions : s->h_actions, na, cudaMemcpyHostToDevice, s->stream));
     int rc = mqe_sim_step(s, s->d_actions_stage);
     if (rc != MQE_OK) return rc;
-    const size_t no = (size_t)s->M * MQE_OBS_FLOATS * sizeof(float);
-    if (h_obs) CK(cudaMemcpyAsync(s->h_obs, s->p.obs, no, cudaMemcpyDeviceToHost, s->stream));
-    if (h_reset) CK(cudaMemcpyAsync(s->h_reset, s->p.reset_buf, s->p.N, cudaMemcpyDeviceToHost, s->stream));
+    if (h_obs) CK(cudaMemcpyAsync(po ? h_obs : s->h_obs, s->p.obs, no, cudaMemcpyDeviceToHost, s->stream));
+    if (h_reset) CK(cudaMemcpyAsync(pr ? h_reset : s->h_reset, s->p.reset_buf, s->p.N, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    if (h_obs) memcpy(h_obs, s->h_obs, no);
-    if (h_reset) memcpy(h_reset, s->h_reset, s->p.N);
+    if (h_obs && !po) memcpy(h_obs, s->h_obs, no);
+    if (h_reset && !pr) memcpy(h_reset, s->h_reset, s->p.N);
     return MQE_OK;
 }
 

@@ -144,6 +144,8 @@ def load_library(path=None):
     lib.mqe_sim_reset.argtypes = [vp]
     lib.mqe_sim_step.argtypes = [vp, vp]
     lib.mqe_sim_step_host.argtypes = [vp, vp, vp, vp]
+    lib.mqe_sim_pin_host.argtypes = [vp, vp, ctypes.c_size_t]
+    lib.mqe_sim_unpin_host.argtypes = [vp, vp]
     lib.mqe_sim_policy.argtypes = [vp, vp]
     lib.mqe_sim_substeps.argtypes = [vp, i32]
     lib.mqe_sim_post_physics.argtypes = [vp]
@@ -163,7 +165,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = [
     "mqe_last_error", "mqe_abi_version", "mqe_device_count", "mqe_sim_create", "mqe_sim_destroy", "mqe_sim_set_stream", "mqe_sim_set_action_scale",
-    "mqe_sim_get_buffer", "mqe_sim_reset", "mqe_sim_step", "mqe_sim_step_host", "mqe_sim_policy", "mqe_sim_substeps",
+    "mqe_sim_get_buffer", "mqe_sim_reset", "mqe_sim_step", "mqe_sim_step_host", "mqe_sim_pin_host", "mqe_sim_unpin_host", "mqe_sim_policy", "mqe_sim_substeps",
     "mqe_sim_post_physics", "mqe_sim_set_root_indexed", "mqe_sim_set_dof_indexed", "mqe_policy_forward",
     "mqe_actuator_forward", "mqe_sim_history_head", "mqe_sim_synchronize", "mqe_sim_launch_count",
 ]
@@ -237,6 +239,13 @@ class Engine:
 
     def step(self, actions_ptr: int):
         self._check(self.lib.mqe_sim_step(self.h, ctypes.c_void_p(actions_ptr)))
+
+    def pin_host(self, arr: np.ndarray):
+        """Page-lock a caller-owned numpy buffer so step_host DMAs straight from / into it; keep `arr` alive until close()."""
+        assert arr.flags["C_CONTIGUOUS"]
+        self._check(self.lib.mqe_sim_pin_host(self.h, arr.ctypes.data_as(ctypes.c_void_p), arr.nbytes))
+        self._pinned = getattr(self, "_pinned", []) + [arr]
+        return arr
 
     def step_host(self, h_actions: np.ndarray, h_obs: np.ndarray | None, h_reset: np.ndarray | None):
         self._check(self.lib.mqe_sim_step_host(
