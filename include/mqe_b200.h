@@ -41,7 +41,7 @@ typedef enum {
     MQE_ERR_UNSUPPORTED = -4
 } MqeStatus;
 
-typedef enum { MQE_NPC_NONE = 0, MQE_NPC_RIGID = 1, MQE_NPC_SEESAW = 2, MQE_NPC_BOX = 3 } MqeNpcKind;   /* RIGID: capsule / sphere; BOX: free box */
+typedef enum { MQE_NPC_NONE = 0, MQE_NPC_RIGID = 1, MQE_NPC_SEESAW = 2, MQE_NPC_BOX = 3, MQE_NPC_PLATFORM = 4 } MqeNpcKind;   /* RIGID: capsule / sphere; BOX: free box; PLATFORM: fixed raised boxes */
 typedef enum { MQE_NPC_PASSIVE = 0, MQE_NPC_SHEEP = 1 } MqeNpcCtrl;
 typedef enum { MQE_POLICY_FP32 = 0, MQE_POLICY_BF16X3 = 1, MQE_POLICY_BF16 = 2 } MqePolicyMode;
 
@@ -110,7 +110,10 @@ typedef struct {
      * [3] plank box / COM x offset in the plank frame, [4..6] plank half extents, [7..9] platform (base box) half extents,
      * [10] column radius, [11] column length (0: none), [12] joint velocity limit [rad/s], [13] hinge axis (0: y seesaw,
      * 1: z revolving door, rotation_door.urdf), [14], [15] box centre y, z in the hinged frame.
-     * MQE_NPC_BOX (resources/objects/box.urdf): [4..6] box half extents. */
+     * MQE_NPC_BOX (resources/objects/box.urdf): [4..6] box half extents.
+     * MQE_NPC_PLATFORM (fix_npc_base_link assets made of axis-aligned boxes: wrestling_field/urdf/wrestling.urdf,
+     * bridge/urdf/bridge.urdf): [0] number of boxes (<= 3), then per box centre x, y, half extents x, y and top z, all
+     * relative to the NPC root position.  Their tops are ground for the robots' probes; their sides are not modelled. */
     float npc_geom[16];
     uint64_t seed;
     /* static world: 2-D signed distance to the wall footprint on the BarrierTrack pixel grid */

@@ -225,7 +225,14 @@ __device__ __forceinline__ ProbeHit probe_world(const DevParams &p, V3 x, float 
     float gw = s.sdf - r, gn = sqrtf(s.gx * s.gx + s.gy * s.gy);
     bool wall_ok = !above && gn > 1e-6f;
     h.nw = wall_ok ? mk(s.gx / gn, s.gy / gn, 0.f) : mk(0.f, 0.f, 0.f);
-    if (has_fix) {
+    if (has_fix && p.npc_kind == MQE_NPC_PLATFORM) {      // wrestling.urdf / bridge.urdf: tops of fixed boxes are ground inside their footprints
+        const float *g = p.geom;
+        for (int b = 0; b < (int)g[0]; b++) {
+            const float *bx = g + 1 + 5 * b;
+            const float px = x.x - fix.x - bx[0], py = x.y - fix.y - bx[1], top = fix.z + bx[4];
+            if (fabsf(px) <= bx[2] && fabsf(py) <= bx[3] && x.z >= top - 0.15f && top > ground) ground = top;
+        }
+    } else if (has_fix) {
         const float *g = p.geom;
         float px = x.x - fix.x, py = x.y - fix.y;
         if (g[7] > 0.f && fabsf(px) <= g[7] && fabsf(py) <= g[8] && x.z >= fix.z) ground = fmaxf(ground, fix.z + g[9]);
@@ -386,6 +393,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
     const int GA = p.G;                                 // actors per env in the root-state tensor
     const bool seesaw = p.npc_kind == MQE_NPC_SEESAW;   // the NPC lane is a 1-DOF plank on a fixed base (seesaw.urdf)
     const bool box = p.npc_kind == MQE_NPC_BOX;         // the NPC lane is a free box (box.urdf)
+    const bool has_fix = seesaw || p.npc_kind == MQE_NPC_PLATFORM;   // probes see a fixed NPC base (seesaw platform / column, raised boxes)
     const bool obb = seesaw || box;                     // robot probes collide with an oriented box instead of capsules
     const int Gc = obb ? A : G;                         // groups that take part in the capsule / capsule phase
     float *wbase = smem + physics_cta_header_floats() + warp * physics_warp_smem_floats(A, P, E, spair, maxpair);
@@ -464,10 +472,10 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         for (int k = 0; k < 3; k++) { e1[k] = e2[k] = v1[k] = v2[k] = 0.f; }
     }
     V3 fixb = mk(0, 0, 0);                                               // seesaw: position of the fixed base (platform)
-    if (seesaw && env < p.N) {
+    if (has_fix && env < p.N) {
         const float *r = p.root + ((size_t)env * GA + A) * 13;
         fixb = mk(r[0], r[1], r[2]);
-        if (is_npc) { const float *d = p.dof + ((size_t)env * (12 * A + p.D) + 12 * A) * 2; q[0] = d[0]; qd[0] = d[1]; }
+        if (seesaw && is_npc) { const float *d = p.dof + ((size_t)env * (12 * A + p.D) + 12 * A) * 2; q[0] = d[0]; qd[0] = d[1]; }
     }
     int stat_local = 0, stat_lim = 0, stat_pair = 0, stat_rows = 0;
 
@@ -745,7 +753,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     const M3 Rl = selm(k, Rb, R1, R2, R3);
                     V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                     V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
-                    ProbeHit h = probe_world(p, pos + xr, pr[5], seesaw, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
+                    ProbeHit h = probe_world(p, pos + xr, pr[5], has_fix, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
                     cm |= (unsigned long long)h.mask << (2 * pi);
                 }
             unsigned long long call = cm;
@@ -767,7 +775,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 const M3 Rl = selm(k, Rb, R1, R2, R3);
                 V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                 V3 xr = pl + mul(Rl, mk(pr[2], pr[3], pr[4]));            // probe centre rel. O
-                ProbeHit h = probe_world(p, pos + xr, pr[5], seesaw, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
+                ProbeHit h = probe_world(p, pos + xr, pr[5], has_fix, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
                 V3 n = kind ? h.nw : mk(0, 0, 1);
                 float gap = kind ? h.gap_w : h.gap_f;
                 V3 r = xr - (pr[5] + 0.5f * gap) * n;                     // contact point rel. O

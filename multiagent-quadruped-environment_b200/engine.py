@@ -31,7 +31,7 @@ OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
     "clock_inputs": (64, 68), "base_rpy": (68, 71),
 }
 
-NPC_NONE, NPC_RIGID, NPC_SEESAW, NPC_BOX = 0, 1, 2, 3
+NPC_NONE, NPC_RIGID, NPC_SEESAW, NPC_BOX, NPC_PLATFORM = 0, 1, 2, 3, 4
 NPC_PASSIVE, NPC_SHEEP = 0, 1
 POLICY_FP32, POLICY_BF16X3, POLICY_BF16 = 0, 1, 2
 POLICY_MODE_DEFAULT = int(os.environ.get("MQE_POLICY_MODE", POLICY_FP32))

@@ -320,6 +320,52 @@ def Go1RotationCfg() -> Cfg:
     return c
 
 
+def Go1WrestlingCfg() -> Cfg:
+    """go1_wrestling_config.py:5-120: two robots on a fixed 4.37 m square platform 0.5 m high (wrestling.urdf)."""
+    c = go1_base()
+    c.env.update(env_name="go1wrestling", num_envs=1, num_agents=2, num_npcs=1, episode_length_s=15)
+    c.asset.update(terminate_after_contacts_on=[], file_npc="{LEGGED_GYM_ROOT_DIR}/resources/objects/wrestling_field/urdf/wrestling.urdf",
+                   name_npc="wrestling", fix_npc_base_link=True)
+    c.terrain.update(num_rows=1, num_cols=1, BarrierTrack_kwargs=_track(
+        options=["init", "plane"], randomize_obstacle_order=False, track_width=6,
+        init=dict(block_length=0.0, room_size=(0.0, 0.0), border_width=0.0, offset=(0, 0)),
+        wall=dict(block_length=0.1), plane=dict(block_length=7), wall_height=0.001))
+    c.command.cfg.vel = True
+    c.init_state.multi_init_state = True
+    c.init_state.init_states = [InitState(pos=(3.1, 1.0, 0.74), rot=(0.0, 0.0, -1.0, 1.0)), InitState(pos=(3.1, -1.0, 0.74), rot=(0.0, 0.0, 1.0, 1.0))]
+    c.init_state.init_states_npc = [InitState(pos=(3.1, 0.0, 0.0))]
+    c.termination.update(termination_terms=["roll", "pitch", "z_low"], z_low_kwargs=dict(threshold=0.3))
+    c.domain_rand.init_dof_pos_ratio_range = None
+    c.domain_rand.init_base_pos_range = dict(x=[-0.1, 0.1], y=[-0.1, 0.1])
+    c.domain_rand.init_npc_base_pos_range = None
+    c.rewards.scales = Cfg(punishment_scale=1, success_reward_scale=10)
+    c.viewer.update(pos=[0.0, 3.0, 5.0], lookat=[4.0, 3.0, 0.0])
+    return c
+
+
+def Go1BridgeCfg() -> Cfg:
+    """go1_bridge_config.py:5-118: two robots facing each other across a 0.7 m wide deck between two platforms (bridge.urdf)."""
+    c = go1_base()
+    c.env.update(env_name="go1bridge", num_envs=1, num_agents=2, num_npcs=1, episode_length_s=20)
+    c.asset.update(terminate_after_contacts_on=[], file_npc="{LEGGED_GYM_ROOT_DIR}/resources/objects/bridge/urdf/bridge.urdf",
+                   name_npc="bridge", fix_npc_base_link=True)
+    c.terrain.update(num_rows=1, num_cols=1, BarrierTrack_kwargs=_track(
+        options=["init", "wall", "plane", "wall"], randomize_obstacle_order=False, track_width=6,
+        init=dict(block_length=0.5, room_size=(0.0, 0.0), border_width=0.0, offset=(0, 0)),
+        plane=dict(block_length=10.0), wall=dict(block_length=0.1), wall_height=0.01))
+    c.command.cfg.vel = True
+    c.init_state.multi_init_state = True
+    c.init_state.init_states = [InitState(pos=(2.0, 0.0, 1.4)), InitState(pos=(7.5, 0.0, 1.4), rot=(0.0, 0.0, 1.0, 0.0))]
+    c.init_state.init_states_npc = [InitState(pos=(5.0, 0.0, 0.72))]
+    c.termination.update(z_low_kwargs=dict(threshold=0.3))
+    c.domain_rand.init_dof_pos_ratio_range = None
+    c.domain_rand.init_base_pos_range = dict(x=[-0.1, 0.1], y=[-0.1, 0.1])
+    c.domain_rand.init_npc_base_pos_range = None
+    c.rewards.scales = Cfg(target_reward_scale=1, punishment_scale=1, success_reward_scale=10)
+    c.viewer.update(pos=[0.0, 3.0, 5.0], lookat=[4.0, 3.0, 0.0])
+    return c
+
+
 def _football_game(num_agents, init_xy, episode_length_s):
     """go1_football_config.py:133-371 (1 vs 1 and 2 vs 2): free-play football, ball at (7, 0, 0.2)."""
     c = go1_base()

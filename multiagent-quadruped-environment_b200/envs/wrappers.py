@@ -431,3 +431,112 @@ class Go1RotationWrapper(EmptyWrapper):
             self.last_dis = dis
         self._acc("step count", 1)
         return self._obs(obs_buf), reward.reshape(N, A, 1), termination, info
+
+
+def get_euler_xyz(q):
+    """isaacgym.torch_utils.get_euler_xyz (xyzw; every angle returned in [0, 2 pi)) -- SURVEY appendix B."""
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    roll = torch.atan2(2.0 * (w * x + y * z), w * w - x * x - y * y + z * z)
+    sinp = 2.0 * (w * y - z * x)
+    pitch = torch.where(torch.abs(sinp) >= 1, torch.copysign(torch.full_like(sinp, torch.pi / 2.0), sinp), torch.asin(sinp))
+    yaw = torch.atan2(2.0 * (w * z + x * y), w * w + x * x - y * y - z * z)
+    two_pi = 2 * torch.pi
+    return roll % two_pi, pitch % two_pi, yaw % two_pi
+
+
+class Go1WrestlingWrapper(EmptyWrapper):
+    """go1_wrestling_wrapper.py:9-89: obs = (pos, rpy) self / other with agent 1 mirrored in y (12); reward on agent 0 only:
+    success when agent 1 is flipped (|pitch| > 0.9 pi or |roll| >= 0.4 pi), punishment when agent 0 is.  Reward is [N, A, 1]."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(12,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.reward_buffer = {"punishment": 0, "success reward": 0, "step count": 0}
+
+    def _init_extras(self, obs):
+        agent_ids = self.env_agent_indices.reshape(-1)
+        self.target_pos = self.base_init_state[agent_ids][:, 2].reshape(self.env.num_envs * self.env.num_agents, -1) - 0.5
+
+    def _obs(self, obs_buf):
+        base_info = self._base_info(obs_buf)
+        obs = torch.cat([base_info, torch.flip(base_info, [1])], dim=2)
+        obs[:, 1, 1::3] = -obs[:, 1, 1::3]                    # y and pitch of both halves, as seen by the mirrored agent
+        return obs
+
+    def reset(self):
+        obs_buf = self.env.reset()
+        self._init_extras(obs_buf)
+        return self._obs(obs_buf)
+
+    def step(self, action):
+        action[:, 1, 1:] = -action[:, 1, 1:]                  # in place, as the reference does
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        N, A = self.env.num_envs, self.env.num_agents
+        self._acc("step count", 1)
+        reward = torch.zeros([N, A], device=self.env.device, dtype=torch.float)
+        r, p, _ = get_euler_xyz(obs_buf.base_quat)
+        r = torch.where(r > torch.pi, r - 2 * torch.pi, r).reshape(N, A)       # to (-pi, pi]
+        p = torch.where(p > torch.pi, p - 2 * torch.pi, p).reshape(N, A)
+        flipped = (p.abs() > torch.pi * 0.9) | (r.abs() >= torch.pi * 0.4)       # [N, A]
+        if self.success_reward_scale != 0:
+            success = flipped[:, 1] * float(self.success_reward_scale)
+            reward[:, 0] += success
+            self._acc("success reward", torch.sum(success))
+        if self.punishment_scale != 0:
+            punishment = flipped[:, 0] * float(self.punishment_scale)
+            reward[:, 0] -= punishment
+            self._acc("punishment", torch.sum(punishment))
+        return self._obs(obs_buf), reward.reshape(N, A, 1), termination, info
+
+
+class Go1BridgeWrapper(EmptyWrapper):
+    """go1_bridge_wrapper.py:8-80: obs = (pos, rpy) self / other, agent 1 sees x reflected about the midpoint of the two start
+    positions and pitch negated (12); reward on agent 0 only: success when agent 1 is below z = 0.5 (fell off), punishment
+    when agent 0 is, target reward once agent 0 is past agent 1's start x.  Reward is [N, A]."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(12,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.reward_buffer = {"target reward": 0, "success reward": 0, "punishment": 0, "step count": 0}
+
+    def _init_extras(self, obs):
+        base_pos = obs.base_pos.reshape(self.env.num_envs, self.env.num_agents, -1)
+        self.target_pos = torch.flip(base_pos, [1]).clone()
+
+    def _obs(self, obs_buf):
+        base_info = self._base_info(obs_buf)
+        obs = torch.cat([base_info, torch.flip(base_info, [1])], dim=2)
+        span = (self.target_pos[:, 0, 0] + self.target_pos[:, 1, 0]).abs()
+        obs[:, 1, 0] = span - obs[:, 1, 0]
+        obs[:, 1, 4] = -obs[:, 1, 4]
+        obs[:, 1, 6] = span - obs[:, 1, 6]
+        obs[:, 1, 10] = -obs[:, 1, 10]
+        return obs
+
+    def reset(self):
+        obs_buf = self.env.reset()
+        self._init_extras(obs_buf)
+        return self._obs(obs_buf)
+
+    def step(self, action):
+        action[:, 1, 1:] = -action[:, 1, 1:]
+        obs_buf, _, termination, info = self.env.step_from_wrapper(action)
+        N, A = self.env.num_envs, self.env.num_agents
+        self._acc("step count", 1)
+        reward = torch.zeros([N, A], device=self.env.device, dtype=torch.float)
+        base_pos = obs_buf.base_pos.reshape(N, A, -1)
+        if self.success_reward_scale != 0:
+            success = (base_pos[:, 1, 2] < 0.5) * float(self.success_reward_scale)
+            reward[:, 0] += success
+            self._acc("success reward", torch.sum(success))
+        if self.punishment_scale != 0:
+            punishment = (base_pos[:, 0, 2] < 0.5) * float(self.punishment_scale)
+            reward[:, 0] -= punishment
+            self._acc("punishment", torch.sum(punishment))
+        if self.target_reward_scale != 0:
+            target = (base_pos[:, 0, 0] > self.target_pos[:, 0, 0]) * float(self.target_reward_scale)
+            reward[:, 0] += target
+            self._acc("target reward", torch.sum(target))
+        return self._obs(obs_buf), reward, termination, info

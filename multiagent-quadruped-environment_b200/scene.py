@@ -23,7 +23,16 @@ TASK_NPC = {            # npc asset -> (kind, ctrl, radius, half length of the c
     "seesaw": (E.NPC_SEESAW, E.NPC_PASSIVE, 0.0, 0.0, 100.0, 100.0), # resources/objects/seesaw.urdf
     "box": (E.NPC_BOX, E.NPC_PASSIVE, 0.0, 0.0, 6.0, 0.25),          # resources/objects/box.urdf (1 x 1 x 1 m, 6 kg)
     "rotation": (E.NPC_SEESAW, E.NPC_PASSIVE, 0.0, 0.0, 4.0, 1.232),  # resources/objects/rotation_door.urdf (izz of the panel)
+    "wrestling": (E.NPC_PLATFORM, E.NPC_PASSIVE, 0.0, 0.0, 0.0, 0.0),  # resources/objects/wrestling_field/urdf/wrestling.urdf (fixed)
+    "bridge": (E.NPC_PLATFORM, E.NPC_PASSIVE, 0.0, 0.0, 0.0, 0.0),     # resources/objects/bridge/urdf/bridge.urdf (fixed)
 }
+# Fixed assets made of boxes (fix_npc_base_link = True; the STL meshes are 12-triangle boxes, extents read from the files):
+# [n boxes, then per box: centre x, y, half extents x, y, top z] relative to the NPC root.
+# wrestling.urdf: base_link 4.368 x 4.368 x 0.5 m; the eight Empty_Link* parts are 1-4 cm thick floor markings on its top, not modelled.
+WRESTLING_GEOM = [1.0, 0.0, 0.0, 2.184, 2.184, 0.5] + [0.0] * 10
+# bridge.urdf: deck base_link 4 x 0.7 x 0.3 m; Link1 / Link2 (2.5 x 1 x 1.3 m boxes, joint rpy (pi/2, 0, pi/2)) become end platforms
+# x in +-[2.0, 3.3], |y| <= 1.25, z in [-0.7, 0.3]: all three tops at 0.3 above the root.
+BRIDGE_GEOM = [3.0, 0.0, 0.0, 2.0, 0.35, 0.3, 2.65, 0.0, 0.65, 1.25, 0.3, -2.65, 0.0, 0.65, 1.25, 0.3]
 # rotation_door.urdf: joint "rot1" at the base origin, axis z, velocity limit 28; panel box 0.08 x 1.95 x 0.8 centred 0.4 above it
 DOOR_GEOM = [0.0, 0.0, 0.0, 0.0, 0.04, 0.975, 0.4, 0.0, 0.0, 0.0, 0.0, 0.0, 28.0, 1.0, 0.0, 0.4]
 BOX_GEOM = [0.0] * 4 + [0.5, 0.5, 0.5] + [0.0] * 9
@@ -225,7 +234,7 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     d.npc_mass, d.npc_inertia, d.npc_radius, d.npc_halflen = npc_m, npc_I, npc_r, npc_hl
     # pair-contact budget per env and substep: two robots alone rarely touch in more than a few capsule pairs
     d.max_pair_contacts = 8 if (A <= 2 and npc_kind == E.NPC_NONE) else 16
-    geom = {"seesaw": SEESAW_GEOM, "rotation": DOOR_GEOM, "box": BOX_GEOM}.get(cfg.asset.name_npc if P else "", [0.0] * 16)
+    geom = {"seesaw": SEESAW_GEOM, "rotation": DOOR_GEOM, "box": BOX_GEOM, "wrestling": WRESTLING_GEOM, "bridge": BRIDGE_GEOM}.get(cfg.asset.name_npc if P else "", [0.0] * 16)
     d.npc_geom[:] = geom
     d.sheep_scale = float(getattr(cfg.asset, "sheep_movement_scale", 0.0))
     d.sheep_randomness = float(getattr(cfg.asset, "sheep_movement_randomness", 0.0))
@@ -239,10 +248,12 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     eo = np.ascontiguousarray(env_origins[start:stop], dtype=np.float32)
     ao = np.ascontiguousarray(agent_origins[start:stop], dtype=np.float32)
     bi = np.ascontiguousarray(base_init[start * A:stop * A], dtype=np.float32)
+    bi_engine = bi.copy()                                  # PhysX normalises the pose quaternion it is handed (go1_wrestling_config.py
+    bi_engine[:, 3:7] /= np.linalg.norm(bi_engine[:, 3:7], axis=1, keepdims=True)   # gives rot = [0, 0, -1, 1]); `base_init_state` stays raw
     ni = np.ascontiguousarray(npc_init[start * P:stop * P], dtype=np.float32) if P else np.zeros((1, 13), dtype=np.float32)
-    keep += [sdf, eo, ao, bi, ni, npc_dof_default]
+    keep += [sdf, eo, ao, bi, bi_engine, ni, npc_dof_default]
     d.h_sdf, d.h_env_origins, d.h_agent_origins = E.as_fp(sdf), E.as_fp(eo), E.as_fp(ao)
-    d.h_base_init_state, d.h_npc_init_state, d.h_npc_dof_default = E.as_fp(bi), E.as_fp(ni), E.as_fp(npc_dof_default)
+    d.h_base_init_state, d.h_npc_init_state, d.h_npc_dof_default = E.as_fp(bi_engine), E.as_fp(ni), E.as_fp(npc_dof_default)
     d.model = model.to_c()
     if weights is None:
         weights = E.load_weights()

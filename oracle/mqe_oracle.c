@@ -550,7 +550,14 @@ static int probe_world(const Oracle *o, const real *x, real r, const real *fix, 
     real gw = s.sdf - r, gn = sqrt(s.gx * s.gx + s.gy * s.gy), wn[2] = {0, 0};
     int wall_ok = !above_top && gn > (real)1e-6;
     if (wall_ok) { wn[0] = s.gx / gn; wn[1] = s.gy / gn; }
-    if (fix) { /* seesaw.urdf statics: platform top is ground inside its footprint, the column is a vertical cylinder */
+    if (fix && d->npc_kind == MQE_NPC_PLATFORM) {   /* wrestling.urdf / bridge.urdf: tops of fixed boxes are ground inside their footprints */
+        const float *g = d->npc_geom;
+        for (int b = 0; b < (int)g[0]; b++) {
+            const float *bx = g + 1 + 5 * b;
+            real px = x[0] - fix[0] - bx[0], py = x[1] - fix[1] - bx[1], top = fix[2] + bx[4];
+            if (fabs(px) <= bx[2] && fabs(py) <= bx[3] && x[2] >= top - (real)0.15 && top > ground) ground = top;
+        }
+    } else if (fix) { /* seesaw.urdf statics: platform top is ground inside its footprint, the column is a vertical cylinder */
         const float *g = d->npc_geom;
         real px = x[0] - fix[0], py = x[1] - fix[1];
         if (g[7] > 0 && fabs(px) <= g[7] && fabs(py) <= g[8] && x[2] >= fix[2]) { real top = fix[2] + g[9]; if (top > ground) ground = top; }
@@ -801,6 +808,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
     real ss_c = 1, ss_s = 0;
     real h_ex[3] = {1, 0, 0}, h_ey[3] = {0, 1, 0}, h_ez[3] = {0, 0, 1}, h_c[3] = {0, 0, 0};
     const real *ss_fix = NULL;
+    if (P && d->npc_kind == MQE_NPC_PLATFORM) ss_fix = root + A * 13;   /* fixed boxes: only their position matters */
     if (seesaw) {   /* resources/objects/seesaw.urdf, rotation_door.urdf: fixed base, box on a passive revolute joint */
         const float *gm = d->npc_geom;
         const real *rs = root + A * 13;

@@ -147,3 +147,31 @@ def test_timeout_and_reset_bookkeeping():
         if s <= 10:
             assert (ep == s).all() and o.get(E.BUF_TIMEOUT).sum() == 0
     assert o.get(E.BUF_TIMEOUT).all() and o.get(E.BUF_RESET).all() and (o.get(E.BUF_EPISODE_LENGTH) == 0).all()
+
+
+@pytest.mark.parametrize("cfg_fn,top", [(C.Go1WrestlingCfg, 0.5), (C.Go1BridgeCfg, 0.72 + 0.3)])
+def test_robots_stand_on_fixed_platforms(cfg_fn, top):
+    """wrestling.urdf / bridge.urdf (fix_npc_base_link): the box tops carry the robots -- standing height above the top is the
+    same ~0.3 m as on the floor, the feet carry the weight, nobody terminates; a robot moved off the platform falls to the slab."""
+    sc = _scene(cfg_fn, 2)
+    o = oracle.Oracle(sc, "f64")
+    o.reset()
+    act = np.zeros((2, 2, 3), dtype=np.float32)
+    fz = []
+    for s in range(120):
+        o.step(act)
+        assert o.get(E.BUF_RESET).sum() == 0, s
+        if s >= 80:
+            fz.append(o.get(E.BUF_CONTACT_FORCES).reshape(2, -1, 3)[:, :17, 2].sum(axis=1))
+    z = o.root_states()[:, :2, 2]
+    assert np.all(z > top + 0.22) and np.all(z < top + 0.40), z
+    w = sc.model.total_mass * 9.81
+    assert np.all(np.abs(np.mean(fz, axis=0) - w) < 0.06 * w)
+    root = o.root_states().copy()
+    root[0, 0, 1] += 4.0                                          # env 0, agent 0: 4 m to the side, off every box
+    o.set(E.BUF_ROOT_STATES, root)
+    fell = False
+    for s in range(40):
+        o.step(act)
+        fell |= bool(o.get(E.BUF_RESET)[0])                      # z_low termination (0.3 m) once it has dropped to the slab
+    assert fell

@@ -17,6 +17,8 @@ CASES = {
     "go1football-defender": (W.Go1FootballDefenderWrapper, C.Go1FootballDefenderCfg, 3, 1),
     "go1pushbox": (W.Go1PushboxWrapper, C.Go1PushboxCfg, 2, 1),
     "go1revolvingdoor": (W.Go1RotationWrapper, C.Go1RotationCfg, 2, 1),
+    "go1wrestling": (W.Go1WrestlingWrapper, C.Go1WrestlingCfg, 2, 1),
+    "go1bridge": (W.Go1BridgeWrapper, C.Go1BridgeCfg, 2, 1),
 }
 
 
@@ -35,12 +37,16 @@ class FakeEnv:
         self.npc_env_origins = self.env_origins.unsqueeze(1).repeat(1, max(P, 1), 1)
         if "in_gate_pos" in z.files:
             self.gate_pos = torch.as_tensor(z["in_gate_pos"])
+        self.env_agent_indices = torch.arange(self.num_envs * A).view(self.num_envs, A)
+        if "in_base_init_state" in z.files:
+            self.base_init_state = torch.as_tensor(z["in_base_init_state"])
         self._load(0)
 
     def _load(self, t):
         z = self.z
         self.obs_buf = Ns(base_pos=torch.as_tensor(z["in_base_pos"][t]), base_rpy=torch.as_tensor(z["in_base_rpy"][t]),
                           lin_vel=torch.as_tensor(z["in_lin_vel"][t]),
+                          base_quat=torch.as_tensor(z["in_base_quat"][t]) if "in_base_quat" in z.files else None,
                           env_info={"gate_deviation": torch.as_tensor(z["in_gate_deviation"]).clone()})
         self.root_states_npc = torch.as_tensor(z["in_root_states_npc"][t])
         self.collide_buf = torch.as_tensor(z["in_collide"][t])

@@ -44,6 +44,20 @@ def stub_modules():
         sys.modules[name] = types.ModuleType(name)
     sys.modules["isaacgym.torch_utils"].__all__ = []
 
+    def get_euler_xyz(q):      # restated from the public Isaac Gym Preview 4 torch_utils (xyzw, angles in [0, 2 pi)); SURVEY appendix B
+        qx, qy, qz, qw = 0, 1, 2, 3
+        sinr_cosp = 2.0 * (q[:, qw] * q[:, qx] + q[:, qy] * q[:, qz])
+        cosr_cosp = q[:, qw] * q[:, qw] - q[:, qx] * q[:, qx] - q[:, qy] * q[:, qy] + q[:, qz] * q[:, qz]
+        roll = torch.atan2(sinr_cosp, cosr_cosp)
+        sinp = 2.0 * (q[:, qw] * q[:, qy] - q[:, qz] * q[:, qx])
+        pitch = torch.where(torch.abs(sinp) >= 1, torch.sign(sinp) * (np.pi / 2.0), torch.asin(sinp))
+        siny_cosp = 2.0 * (q[:, qw] * q[:, qz] + q[:, qx] * q[:, qy])
+        cosy_cosp = q[:, qw] * q[:, qw] + q[:, qx] * q[:, qx] - q[:, qy] * q[:, qy] - q[:, qz] * q[:, qz]
+        yaw = torch.atan2(siny_cosp, cosy_cosp)
+        return roll % (2 * np.pi), pitch % (2 * np.pi), yaw % (2 * np.pi)
+
+    sys.modules["isaacgym.torch_utils"].get_euler_xyz = get_euler_xyz
+
 
 def load(name):
     path = os.path.join(REF, "mqe", "envs", "wrappers", name + ".py")
@@ -73,12 +87,14 @@ class FakeEnv:
             self.npc_env_origins = self.env_origins.unsqueeze(1).repeat(1, num_npcs, 1)
         if "gate_pos" in rec:
             self.gate_pos = torch.as_tensor(rec["gate_pos"])
+        self.env_agent_indices = torch.arange(self.num_envs * num_agents).view(self.num_envs, num_agents)
+        self.base_init_state = torch.as_tensor(rec["base_init_state"])
         self._load(0)
 
     def _load(self, t):
         r = self.rec
         self.obs_buf = Ns(base_pos=torch.as_tensor(r["base_pos"][t]), base_rpy=torch.as_tensor(r["base_rpy"][t]),
-                          lin_vel=torch.as_tensor(r["lin_vel"][t]),
+                          lin_vel=torch.as_tensor(r["lin_vel"][t]), base_quat=torch.as_tensor(r["base_quat"][t]),
                           env_info={"gate_deviation": torch.as_tensor(r["gate_deviation"]).clone()})
         if self.num_npcs:
             self.root_states_npc = torch.as_tensor(r["root_states_npc"][t])
@@ -117,6 +133,18 @@ def make_record(rng, N, A, P, T, with_gate=False):
         "actions": rng.uniform(-1.5, 1.5, size=(T, N, min(A, 2) if with_gate else A, 3)).astype(np.float32),
     }
     rec["base_pos"][:, :, 2] = rng.uniform(0.2, 1.5, size=(T, M))
+    # drawn last so that the streams of the earlier goldens stay as they were: base orientation (some robots flipped) and
+    # the per-agent initial root states the wrestling wrapper reads
+    rng2 = np.random.default_rng(int(rng.integers(1 << 30)) if False else 12345 + N * 31 + A * 7 + P)
+    rpy = rng2.uniform(-0.5, 0.5, size=(T, M, 3))
+    flip = rng2.random((T, M)) < 0.3
+    rpy[flip, 0] = rng2.uniform(1.3, 3.1, size=int(flip.sum())) * rng2.choice([-1.0, 1.0], size=int(flip.sum()))
+    flip = rng2.random((T, M)) < 0.2
+    rpy[flip, 1] = rng2.uniform(-1.5, 1.5, size=int(flip.sum()))
+    cr, sr, cp, sp, cy, sy = (f(rpy[..., i] * 0.5) for i in range(3) for f in (np.cos, np.sin))
+    rec["base_quat"] = np.stack([cy * sr * cp - sy * cr * sp, cy * cr * sp + sy * sr * cp, sy * cr * cp - cy * sr * sp,
+                                 cy * cr * cp + sy * sr * sp], axis=-1).astype(np.float32)
+    rec["base_init_state"] = rng2.uniform(-1, 3, size=(M, 13)).astype(np.float32)
     if A >= 2:                                   # some envs with the two agents within 0.5 m (agent-distance terms)
         bp = rec["base_pos"].reshape(T, N, A, 3)
         close = rng.random((T, N)) < 0.4
@@ -176,6 +204,8 @@ def main():
     run("go1pushbox", load("go1_pushbox_wrapper").Go1PushboxWrapper, C.Go1PushboxCfg(), 2, 1, 5)
     # the reference's rotation wrapper only broadcasts for num_envs <= 2 (go1_rotation_wrapper.py:77)
     run("go1revolvingdoor", load("go1_rotation_wrapper").Go1RotationWrapper, C.Go1RotationCfg(), 2, 1, 6, N=2, T=12)
+    run("go1wrestling", load("go1_wrestling_wrapper").Go1WrestlingWrapper, C.Go1WrestlingCfg(), 2, 1, 7)
+    run("go1bridge", load("go1_bridge_wrapper").Go1BridgeWrapper, C.Go1BridgeCfg(), 2, 1, 8)
 
 
 if __name__ == "__main__":
