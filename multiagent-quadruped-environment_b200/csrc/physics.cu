@@ -282,6 +282,28 @@ __device__ __forceinline__ bool sphere_obb(const DevParams &p, V3 c, V3 ex, V3 e
     return true;
 }
 
+// sphere (centre x, radius r) vs a solid vertical cylinder (centre c, radius R, half height hh); normal cylinder -> sphere.
+// The tug-of-war disc (resources/objects/cylinder.urdf); same arithmetic as the oracle's sphere_vcyl.
+__device__ __forceinline__ bool sphere_vcyl(const DevParams &p, V3 c, float R, float hh, V3 x, float r, V3 &nrm, float &gap, V3 &pos) {
+    const V3 dx = x - c;
+    const float dr = sqrtf(dx.x * dx.x + dx.y * dx.y);
+    const float ux = dr > 1e-9f ? dx.x / dr : 1.f, uy = dr > 1e-9f ? dx.y / dr : 0.f;
+    const float dfr = dr - fminf(dr, R), dfz = dx.z - fminf(fmaxf(dx.z, -hh), hh);
+    const float d2 = dfr * dfr + dfz * dfz;
+    if (d2 > 1e-12f) {
+        const float dist = sqrtf(d2);
+        nrm = mk(ux * dfr / dist, uy * dfr / dist, dfz / dist);
+        gap = dist - r;
+    } else {
+        const float penr = R - dr, penz = hh - fabsf(dx.z);
+        if (penr < penz) { nrm = mk(ux, uy, 0.f); gap = -penr - r; }
+        else { nrm = mk(0.f, 0.f, dx.z >= 0.f ? 1.f : -1.f); gap = -penz - r; }
+    }
+    if (gap >= p.coff) return false;
+    pos = x - (r + 0.5f * gap) * nrm;
+    return true;
+}
+
 // closest points of two segments (Ericson 5.1.9); same branch structure as the oracle
 __device__ __forceinline__ void seg_seg(V3 p1, V3 q1, V3 p2, V3 q2, V3 &c1, V3 &c2) {
     V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
@@ -344,7 +366,9 @@ __device__ float npc_side(const DevParams &p, V3 r, V3 d, float *out) {
         const float iIp = 1.f / (p.npc_inertia + p.npc_mass * r2);
 #pragma unroll
         for (int i = 9; i < 15; i++) out[i] = 0.f;
-        if (hz) out[11] = rxd.z * iIp; else out[10] = rxd.y * iIp;
+        if (p.geom[13] > 1.5f) out[13] = d.y * im;      // prismatic y (tug disc): only v_y responds
+        else if (hz) out[11] = rxd.z * iIp;
+        else out[10] = rxd.y * iIp;
     }
     float dd = 0.f;
     for (int i = 0; i < 6; i++) dd += out[i] * out[9 + i];
@@ -673,8 +697,10 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             const float r2 = hz ? p.geom[3] * p.geom[3] + p.geom[14] * p.geom[14] : p.geom[3] * p.geom[3] + p.geom[15] * p.geom[15];
             const float Ip = p.npc_inertia + p.npc_mass * r2;
             const float tau_g = hz ? 0.f : p.geom[3] * cs * p.npc_mass * (-p.gz);
-            vb[hz ? 2 : 1] = qd[0] + p.dt * tau_g / Ip;
-            ns[NS_ORIGIN] = pos.x + p.geom[0]; ns[NS_ORIGIN + 1] = pos.y + p.geom[1]; ns[NS_ORIGIN + 2] = pos.z + p.geom[2];
+            const bool pz = p.geom[13] > 1.5f;                              // prismatic y joint (tug disc): q is a displacement
+            if (pz) vb[4] = qd[0];
+            else vb[hz ? 2 : 1] = qd[0] + p.dt * tau_g / Ip;
+            ns[NS_ORIGIN] = pos.x + p.geom[0]; ns[NS_ORIGIN + 1] = pos.y + p.geom[1] + (pz ? q[0] : 0.f); ns[NS_ORIGIN + 2] = pos.z + p.geom[2];
             ns[NS_CAP] = cs; ns[NS_CAP + 1] = sn;
             ((int *)ns)[NS_CNT] = 0;
             ns[NS_BOUND] = 0.f;
@@ -1118,7 +1144,11 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 const V3 pivot = mk(nsS[NS_ORIGIN], nsS[NS_ORIGIN + 1], nsS[NS_ORIGIN + 2]);   // group origin: seesaw pivot / box COM
                 V3 oex, oey, oez, oc;
                 const float oh[3] = {p.geom[4], p.geom[5], p.geom[6]};
-                if (seesaw) {
+                const bool vcyl = seesaw && p.geom[13] > 1.5f;                    // tug disc: vertical cylinder, radius geom[4], half height geom[5]
+                if (vcyl) {
+                    oex = mk(1.f, 0.f, 0.f); oey = mk(0.f, 1.f, 0.f); oez = mk(0.f, 0.f, 1.f);
+                    oc = pivot + mk(0.f, 0.f, p.geom[15]);
+                } else if (seesaw) {
                     const float cs = nsS[NS_CAP], sn = nsS[NS_CAP + 1];
                     if (p.geom[13] > 0.5f) { oex = mk(cs, sn, 0.f); oey = mk(-sn, cs, 0.f); oez = mk(0.f, 0.f, 1.f); }
                     else { oex = mk(cs, 0.f, -sn); oey = mk(0.f, 1.f, 0.f); oez = mk(sn, 0.f, cs); }
@@ -1140,7 +1170,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                         V3 nn, pp;
                         float gg;
-                        if (sphere_obb(p, oc, oex, oey, oez, oh, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], nn, gg, pp)) sm |= 1u << pi;
+                        const V3 xs = pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
+                        if (vcyl ? sphere_vcyl(p, oc, oh[0], oh[1], xs, pr[5], nn, gg, pp) : sphere_obb(p, oc, oex, oey, oez, oh, xs, pr[5], nn, gg, pp)) sm |= 1u << pi;
                     }
                 unsigned sall = sm;
                 if (is_robot) { sall |= __shfl_xor_sync(quad_mask, sall, 1); sall |= __shfl_xor_sync(quad_mask, sall, 2); }
@@ -1162,7 +1193,9 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     V3 pl = sel3(k, mk(0, 0, 0), p1, p2, p3);
                     V3 cn, cpos, t1, t2;
                     float cgap;
-                    sphere_obb(p, oc, oex, oey, oez, oh, pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4])), pr[5], cn, cgap, cpos);
+                    const V3 xs = pos + pl + mul(Rl, mk(pr[2], pr[3], pr[4]));
+                    if (vcyl) sphere_vcyl(p, oc, oh[0], oh[1], xs, pr[5], cn, cgap, cpos);
+                    else sphere_obb(p, oc, oex, oey, oez, oh, xs, pr[5], cn, cgap, cpos);
                     tangent_basis(cn, t1, t2);
                     const V3 ra = cpos - pos, rb_ = cpos - pivot;
                     float *cmeta = pdesc + slot * PDESCF;
@@ -1352,7 +1385,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         }
         if (is_npc && seesaw) {
             const float lim = p.geom[12];                                    // URDF joint velocity limit
-            qd[0] = fminf(fmaxf(p.geom[13] > 0.5f ? vb[2] : vb[1], -lim), lim);
+            qd[0] = fminf(fmaxf(p.geom[13] > 1.5f ? vb[4] : (p.geom[13] > 0.5f ? vb[2] : vb[1]), -lim), lim);
             q[0] += p.dt * qd[0];
         } else if (is_robot || is_npc) {
             wang = mk(vb[0], vb[1], vb[2]); vlin = mk(vb[3], vb[4], vb[5]);

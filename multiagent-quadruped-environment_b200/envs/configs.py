@@ -320,6 +320,29 @@ def Go1RotationCfg() -> Cfg:
     return c
 
 
+def Go1TugCfg() -> Cfg:
+    """go1_tug_config.py:5-124: two robots push a 1.2 m disc that slides along y between them (cylinder.urdf, prismatic joint)."""
+    c = go1_base()
+    c.env.update(env_name="go1tug", num_envs=1, num_agents=2, num_npcs=1, num_actions_npc=1, episode_length_s=15)
+    c.asset.update(terminate_after_contacts_on=[], file_npc="{LEGGED_GYM_ROOT_DIR}/resources/objects/cylinder.urdf",
+                   name_npc="circular", fix_npc_base_link=True)
+    c.terrain.update(num_rows=1, num_cols=1, BarrierTrack_kwargs=_track(
+        options=["init", "wall", "plane", "wall"], randomize_obstacle_order=False, track_width=6.0,
+        init=dict(block_length=0.0, room_size=(0.0, 0.0), border_width=0.0, offset=(0, 0)),
+        plane=dict(block_length=3.0), wall=dict(block_length=0.1), wall_height=1.0))
+    c.command.cfg.vel = True
+    c.init_state.multi_init_state = True
+    c.init_state.init_states = [InitState(pos=(1.6, 2.5, 0.34), rot=(0.0, 0.0, -1.0, 1.0)), InitState(pos=(1.6, -2.5, 0.34), rot=(0.0, 0.0, 1.0, 1.0))]
+    c.init_state.init_states_npc = [InitState(pos=(1.6, 0.0, 0.0))]
+    c.termination.update(termination_terms=["roll", "pitch", "z_low", "z_high"])
+    c.domain_rand.init_dof_pos_ratio_range = None
+    c.domain_rand.init_base_pos_range = dict(x=[-1.0, 1.0], y=[-0.0, 0.0])
+    c.domain_rand.init_npc_base_pos_range = None
+    c.rewards.scales = Cfg(success_reward_scale=10, punishment_reward_scale=10, pos_reward_scale=2, pos_punishment_scale=2)
+    c.viewer.update(pos=[0.0, 11.0, 5.0], lookat=[4.0, 11.0, 0.0])
+    return c
+
+
 def Go1WrestlingCfg() -> Cfg:
     """go1_wrestling_config.py:5-120: two robots on a fixed 4.37 m square platform 0.5 m high (wrestling.urdf)."""
     c = go1_base()

@@ -10,7 +10,7 @@ import numpy as np
 from . import configs as C
 from .go1 import Go1, Go1FootballDefender, Go1Object, Go1Sheep
 from .wrappers import (EmptyWrapper, Go1FootballDefenderWrapper, Go1FootballGameWrapper, Go1GateWrapper, Go1PushboxWrapper, Go1RotationWrapper,
-                       Go1SeesawWrapper, Go1SheepWrapper, Go1WrestlingWrapper, Go1BridgeWrapper)
+                       Go1SeesawWrapper, Go1SheepWrapper, Go1WrestlingWrapper, Go1BridgeWrapper, Go1TugWrapper)
 
 ENV_DICT = {
     "go1plane": {"class": Go1, "config": C.Go1PlaneCfg, "wrapper": EmptyWrapper},
@@ -23,11 +23,12 @@ ENV_DICT = {
     "go1seesaw": {"class": Go1Object, "config": C.Go1SeesawCfg, "wrapper": Go1SeesawWrapper},
     "go1pushbox": {"class": Go1Object, "config": C.Go1PushboxCfg, "wrapper": Go1PushboxWrapper},
     "go1revolvingdoor": {"class": Go1Object, "config": C.Go1RotationCfg, "wrapper": Go1RotationWrapper},
+    "go1tug": {"class": Go1Object, "config": C.Go1TugCfg, "wrapper": Go1TugWrapper},
     "go1wrestling": {"class": Go1Object, "config": C.Go1WrestlingCfg, "wrapper": Go1WrestlingWrapper},
     "go1bridge": {"class": Go1Object, "config": C.Go1BridgeCfg, "wrapper": Go1BridgeWrapper},
 }
-# tasks of the reference registry that are outside the hot-path scope of this round
-NOT_YET = ("go1tug",)
+# every task of the reference registry (mqe/envs/utils.py:38-109) is built; kept for callers that probe it
+NOT_YET = ()
 
 
 def set_seed(seed):

@@ -540,3 +540,101 @@ class Go1BridgeWrapper(EmptyWrapper):
             reward[:, 0] += target
             self._acc("target reward", torch.sum(target))
         return self._obs(obs_buf), reward, termination, info
+
+
+class Go1TugWrapper(EmptyWrapper):
+    """go1_tug_wrapper.py:9-136 (tug of war over a sliding disc): obs = (pos, rpy) self, disc (pos, vel), distance to the disc,
+    disc pos again (10), agent 1 mirrored in y; reward on agent 0 only: success ~ how far the disc is on the opponent's side
+    (y < 0), punishment for the own side, +/- for closing in on the disc.  Reward is [N, A, 1].
+
+    Kept from the reference: no clip before the [2, .5, .5] scale (the env clips afterwards, go1.py:38); for three steps after
+    an env reset the disc is pinned back to zero through `env.gym.set_dof_state_tensor_indexed` (:61-69, with the mask taken
+    after the decrement); the last obs column is the disc position of THIS step (`last_npc_pos` is refreshed before the obs is
+    built, :113); "total reward" leaves the position punishment out (:116).  The reference's `reward[:, 0] += x[:, 0]` on a
+    [N, A, 1] tensor only broadcasts for num_envs = 1 (its config's value); here it is the same arithmetic for any N."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Box(low=-float("inf"), high=float("inf"), shape=(10,), dtype=float)
+        self.action_space = spaces.Box(low=-1, high=1, shape=(3,), dtype=float)
+        self.action_scale = torch.tensor([[[2, 0.5, 0.5]]], device=self.env.device).repeat(self.num_envs, self.num_agents, 1)
+        self.reward_buffer = {"success reward": 0, "pos reward": 0, "pos punishment": 0, "step count": 0, "npc pos": 0, "punishment": 0,
+                              "total reward": 0, "pos": 0, "pos_y": 0, "opponet pos": 0, "opponet pos_y": 0}
+        self.reset_dic = torch.zeros([self.env.num_envs], dtype=torch.float, device=self.env.device)
+
+    def _init_extras(self, obs):
+        self.last_dis = torch.clone(obs.base_pos.reshape([self.env.num_envs, self.env.num_agents, -1]))
+        self.last_npc_pos = torch.clone(self.env.dof_state_npc[:, :, :1])
+        self.env_step = torch.zeros(self.env.num_envs, dtype=torch.float, device=self.env.device)
+
+    def _obs(self, obs_buf):
+        N, A = self.env.num_envs, self.env.num_agents
+        base_info = self._base_info(obs_buf)
+        npc = self.env.dof_state_npc
+        dis = base_info[:, :, :2].clone()
+        dis[:, :, 0] -= 1.6
+        dis[:, :, 1] -= npc[:, :, 0].repeat(1, A)
+        dis = torch.norm(dis, p=2, dim=-1, keepdim=True)
+        obs = torch.cat([base_info, npc.repeat(1, A, 1), dis, self.last_npc_pos.repeat(1, A, 1)], dim=2)
+        obs[:, 1, 1] = -obs[:, 1, 1]
+        obs[:, 1, 4] = -obs[:, 1, 4]
+        obs[:, 1, 6] = -obs[:, 1, 6]
+        obs[:, 1, -1] = -obs[:, 1, -1]
+        return obs
+
+    def reset(self):
+        obs_buf = self.env.reset()
+        self._init_extras(obs_buf)
+        obs = self._obs(obs_buf)
+        self.env_step[:] += 1
+        return obs
+
+    def step(self, action):
+        action[:, 1, 1:] = -action[:, 1, 1:]
+        if bool((self.reset_dic > 0).any()):
+            self.reset_dic[self.reset_dic > 0] -= 1
+            pin = self.reset_dic > 0
+            self.env.dof_state_npc[pin, 0, 0] = 0.0
+            self.env.dof_state_npc[pin, 0, 1] = 0.0
+            npc_indices = self.npc_indices.reshape(-1)
+            self.env.gym.set_dof_state_tensor_indexed(self.env.sim, self.env.all_dof_states, npc_indices, len(npc_indices))
+        obs_buf, _, termination, info = self.env.step((action * self.action_scale).reshape(-1, self.action_space.shape[0]))
+        self.reset_dic[self.env.reset_ids] = 3
+        self._acc("step count", 1)
+        N, A = self.env.num_envs, self.env.num_agents
+        base_pos = obs_buf.base_pos.reshape([N, A, -1])
+        npc_y = self.env.dof_state_npc[:, 0, 0]
+        last_dis = self.last_dis[:, 0, :2].clone()
+        last_dis[:, 0] -= 1.6
+        last_dis[:, 1] -= npc_y
+        last_dis = torch.norm(last_dis, p=2, dim=-1)
+        dis = base_pos[:, 0, :2].clone()
+        dis[:, 0] -= 1.6
+        dis[:, 1] -= npc_y
+        dis = torch.norm(dis, p=2, dim=-1)
+        reward = torch.zeros([N, A, 1], device=self.env.device, dtype=torch.float)
+        last_y = self.last_npc_pos[:, 0, 0]
+        zero = torch.zeros_like(npc_y)
+        success = torch.where(npc_y < 0, float(self.success_reward_scale) * -npc_y, zero)
+        success = torch.where(last_y <= npc_y, success / 2, success)
+        punishment = torch.where(npc_y > 0, float(self.punishment_reward_scale) * npc_y, zero)
+        punishment = torch.where(last_y > npc_y, punishment / 2, punishment)
+        pos_reward = torch.where(dis < last_dis, (last_dis - dis) * float(self.pos_reward_scale), zero)
+        pos_punishment = torch.where(dis >= last_dis, torch.pow(2.0, dis) * float(self.pos_punishment_scale), zero)
+        reward[:, 0, 0] += success - punishment + pos_reward - pos_punishment
+        self._acc("success reward", torch.sum(success))
+        self._acc("punishment", torch.sum(punishment))
+        self._acc("pos reward", torch.sum(pos_reward))
+        self._acc("pos punishment", torch.sum(pos_punishment))
+        self.last_dis = torch.clone(base_pos)
+        self.last_npc_pos = torch.clone(self.env.dof_state_npc[:, :, :1])
+        self._acc("npc pos", torch.sum(npc_y))
+        self._acc("total reward", torch.sum(pos_reward) + torch.sum(success) - torch.sum(punishment))
+        self._acc("pos", torch.sum(base_pos[:, 0, 0]))
+        self._acc("pos_y", torch.sum(base_pos[:, 0, 1]))
+        self._acc("opponet pos", torch.sum(base_pos[:, 1, 0]))
+        self._acc("opponet pos_y", torch.sum(base_pos[:, 1, 1]))
+        obs = self._obs(obs_buf)
+        self.env_step[:] += 1
+        self.env_step[self.env.reset_ids] = 1
+        return obs, reward, termination, info

@@ -23,9 +23,13 @@ TASK_NPC = {            # npc asset -> (kind, ctrl, radius, half length of the c
     "seesaw": (E.NPC_SEESAW, E.NPC_PASSIVE, 0.0, 0.0, 100.0, 100.0), # resources/objects/seesaw.urdf
     "box": (E.NPC_BOX, E.NPC_PASSIVE, 0.0, 0.0, 6.0, 0.25),          # resources/objects/box.urdf (1 x 1 x 1 m, 6 kg)
     "rotation": (E.NPC_SEESAW, E.NPC_PASSIVE, 0.0, 0.0, 4.0, 1.232),  # resources/objects/rotation_door.urdf (izz of the panel)
+    "circular": (E.NPC_SEESAW, E.NPC_PASSIVE, 0.0, 0.0, 3.0, 0.54),    # resources/objects/cylinder.urdf: 3 kg disc on a prismatic y joint
     "wrestling": (E.NPC_PLATFORM, E.NPC_PASSIVE, 0.0, 0.0, 0.0, 0.0),  # resources/objects/wrestling_field/urdf/wrestling.urdf (fixed)
     "bridge": (E.NPC_PLATFORM, E.NPC_PASSIVE, 0.0, 0.0, 0.0, 0.0),     # resources/objects/bridge/urdf/bridge.urdf (fixed)
 }
+# cylinder.urdf: joint "rot1" prismatic along y at (0, 0, 0.25), velocity limit 1.0 (limits +-10 never reached inside the track);
+# collision cylinder r 1.2, length 0.5 centred 0.05 above the joint.  [13] = 2: prismatic y, [4] radius, [5] half height, [15] centre z.
+TUG_GEOM = [0.0, 0.0, 0.25, 0.0, 1.2, 0.25, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 2.0, 0.0, 0.05]
 # Fixed assets made of boxes (fix_npc_base_link = True; the STL meshes are 12-triangle boxes, extents read from the files):
 # [n boxes, then per box: centre x, y, half extents x, y, top z] relative to the NPC root.
 # wrestling.urdf: base_link 4.368 x 4.368 x 0.5 m; the eight Empty_Link* parts are 1-4 cm thick floor markings on its top, not modelled.
@@ -234,7 +238,7 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     d.npc_mass, d.npc_inertia, d.npc_radius, d.npc_halflen = npc_m, npc_I, npc_r, npc_hl
     # pair-contact budget per env and substep: two robots alone rarely touch in more than a few capsule pairs
     d.max_pair_contacts = 8 if (A <= 2 and npc_kind == E.NPC_NONE) else 16
-    geom = {"seesaw": SEESAW_GEOM, "rotation": DOOR_GEOM, "box": BOX_GEOM, "wrestling": WRESTLING_GEOM, "bridge": BRIDGE_GEOM}.get(cfg.asset.name_npc if P else "", [0.0] * 16)
+    geom = {"seesaw": SEESAW_GEOM, "rotation": DOOR_GEOM, "box": BOX_GEOM, "wrestling": WRESTLING_GEOM, "bridge": BRIDGE_GEOM, "circular": TUG_GEOM}.get(cfg.asset.name_npc if P else "", [0.0] * 16)
     d.npc_geom[:] = geom
     d.sheep_scale = float(getattr(cfg.asset, "sheep_movement_scale", 0.0))
     d.sheep_randomness = float(getattr(cfg.asset, "sheep_movement_randomness", 0.0))

@@ -608,6 +608,30 @@ static int sphere_obb(const MqeSimDesc *d, const real *c, const real *ex, const 
     return 1;
 }
 
+/* sphere (centre x, radius r) vs a solid vertical cylinder (centre c, radius R, half height hh); normal cylinder -> sphere.
+ * The tug-of-war disc: resources/objects/cylinder.urdf (collision cylinder r 1.2, length 0.5). */
+static int sphere_vcyl(const MqeSimDesc *d, const real *c, real R, real hh, const real *x, real r, real *nrm, real *gap_out, real *pos) {
+    real dx[3] = {x[0] - c[0], x[1] - c[1], x[2] - c[2]};
+    real dr = sqrt(dx[0] * dx[0] + dx[1] * dx[1]);
+    real ux = dr > (real)1e-9 ? dx[0] / dr : 1, uy = dr > (real)1e-9 ? dx[1] / dr : 0;
+    real qz = dx[2] < -hh ? -hh : (dx[2] > hh ? hh : dx[2]);
+    real dfr = dr - (dr < R ? dr : R), dfz = dx[2] - qz, gap;
+    real d2 = dfr * dfr + dfz * dfz;
+    if (d2 > (real)1e-12) {
+        real dist = sqrt(d2);
+        nrm[0] = ux * dfr / dist; nrm[1] = uy * dfr / dist; nrm[2] = dfz / dist;
+        gap = dist - r;
+    } else {
+        real penr = R - dr, penz = hh - fabs(dx[2]);
+        if (penr < penz) { nrm[0] = ux; nrm[1] = uy; nrm[2] = 0; gap = -penr - r; }
+        else { nrm[0] = 0; nrm[1] = 0; nrm[2] = dx[2] >= 0 ? 1 : -1; gap = -penz - r; }
+    }
+    if (gap >= d->contact_offset) return 0;
+    for (int i = 0; i < 3; i++) pos[i] = x[i] - nrm[i] * (r + gap * (real)0.5);
+    *gap_out = gap;
+    return 1;
+}
+
 /* closest points of two segments (Ericson, Real-Time Collision Detection 5.1.9) */
 static void seg_seg(const real *p1, const real *q1, const real *p2, const real *q2, real *c1, real *c2) {
     real d1[3], d2[3], r[3];
@@ -678,7 +702,8 @@ static void group_jacobian(const Oracle *o, const EnvScratch *es, int g, int lin
         if (o->d.npc_kind == MQE_NPC_SEESAW) {   /* one revolute DOF about the pivot (= group origin): only w_axis responds */
             int ax = o->d.npc_geom[13] > 0.5f ? 2 : 1;   /* seesaw: y, revolving door: z */
             memset(Y, 0, NV * sizeof(real));
-            Y[ax] = rxd[ax] * es->npc_minv[0];
+            if (o->d.npc_geom[13] > 1.5f) Y[4] = dir[1] * es->npc_minv[1];   /* prismatic y (tug disc): only v_y responds */
+            else Y[ax] = rxd[ax] * es->npc_minv[0];
         }
     }
 }
@@ -732,7 +757,8 @@ static void solve_row(Row *r, Row *rows, EnvScratch *es, real mu) {
     if (r->gb >= 0) for (int i = 0; i < NV; i++) es->vel[r->gb][i] += r->Yb[i] * dl;
 }
 
-/* contacts of every robot probe (robot X ascending, probe-table order) with the oriented box of NPC group A */
+/* contacts of every robot probe (robot X ascending, probe-table order) with the oriented box of NPC group A
+ * (ex == NULL: a vertical cylinder of radius h[0] and half height h[1] instead) */
 static int obb_probe_contacts(const Oracle *o, const EnvScratch *es, const MqeRobotModel *md, const real *c, const real *ex, const real *ey,
                               const real *ez, const real *h, Contact *contacts, int *nc_io, Row *rows, int *nr_io, int npair, int max_pair) {
     const MqeSimDesc *d = &o->d;
@@ -745,7 +771,8 @@ static int obb_probe_contacts(const Oracle *o, const EnvScratch *es, const MqeRo
             m3mulv(x, es->rd[X].R[link], loc);
             v3add(x, x, es->rd[X].p[link]);
             v3add(x, x, es->origin[X]);
-            if (npair >= max_pair || !sphere_obb(d, c, ex, ey, ez, h, x, pr[5], nrm, &gap, pos)) continue;
+            if (npair >= max_pair) continue;
+            if (ex ? !sphere_obb(d, c, ex, ey, ez, h, x, pr[5], nrm, &gap, pos) : !sphere_vcyl(d, c, h[0], h[1], x, pr[5], nrm, &gap, pos)) continue;
             Contact *ct = &contacts[nc];
             ct->ga = X; ct->la = link; ct->rba = X * MQE_NUM_BODIES + body; ct->gb = A; ct->lb = 0; ct->rbb = A * MQE_NUM_BODIES;
             v3cpy(ct->n, nrm); v3cpy(ct->pos, pos); ct->gap = gap;
@@ -804,7 +831,8 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
     }
 
     const int seesaw = P && d->npc_kind == MQE_NPC_SEESAW;      /* hinged box on a fixed base: seesaw plank (y) or revolving door (z) */
-    const int hz = seesaw && d->npc_geom[13] > 0.5f;            /* hinge axis z */
+    const int hz = seesaw && d->npc_geom[13] > 0.5f;            /* hinge axis z (also set for the prismatic disc: no floor-end rows) */
+    const int pz = seesaw && d->npc_geom[13] > 1.5f;            /* prismatic y joint: the tug disc (resources/objects/cylinder.urdf) */
     real ss_c = 1, ss_s = 0;
     real h_ex[3] = {1, 0, 0}, h_ey[3] = {0, 1, 0}, h_ez[3] = {0, 0, 1}, h_c[3] = {0, 0, 0};
     const real *ss_fix = NULL;
@@ -819,12 +847,14 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         ss_fix = rs;
         ss_c = cos(th); ss_s = sin(th);
         for (int i = 0; i < 3; i++) es.origin[A][i] = rs[i] + gm[i];
+        if (pz) es.origin[A][1] += th;                           /* th is the displacement along y */
         if (hz) { v3set(h_ex, ss_c, ss_s, 0); v3set(h_ey, -ss_s, ss_c, 0); v3set(h_ez, 0, 0, 1); }
         else    { v3set(h_ex, ss_c, 0, -ss_s); v3set(h_ey, 0, 1, 0); v3set(h_ez, ss_s, 0, ss_c); }
         for (int i = 0; i < 3; i++) h_c[i] = es.origin[A][i] + cx * h_ex[i] + cy * h_ey[i] + cz * h_ez[i];
-        es.npc_minv[0] = 1 / Ip; es.npc_minv[1] = 0;
+        es.npc_minv[0] = 1 / Ip; es.npc_minv[1] = pz ? 1 / d->npc_mass : 0;
         real tau_g = hz ? 0 : gm[3] * ss_c * d->npc_mass * (-d->gravity_z);       /* r_x m g about +y; none about a vertical axis */
-        es.vel[A][hz ? 2 : 1] = thd + dt * tau_g / Ip;
+        if (pz) { es.vel[A][4] = thd; v3set(h_c, es.origin[A][0], es.origin[A][1], es.origin[A][2] + gm[15]); }
+        else es.vel[A][hz ? 2 : 1] = thd + dt * tau_g / Ip;
         es.ndof[A] = 6;
     }
 
@@ -969,7 +999,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         /* robot probes on the plank: robot X ascending, probe table order */
         {
             real h[3] = {gm[4], gm[5], gm[6]};
-            npair = obb_probe_contacts(o, &es, md, h_c, h_ex, h_ey, h_ez, h, contacts, &nc, rows, &nr, npair, max_pair);
+            npair = obb_probe_contacts(o, &es, md, h_c, pz ? NULL : h_ex, h_ey, h_ez, h, contacts, &nc, rows, &nr, npair, max_pair);
         }
     }
     if (P && d->npc_kind == MQE_NPC_BOX) {   /* robot probes on the push box (resources/objects/box.urdf) */
@@ -999,7 +1029,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
     }
 
     if (seesaw) {
-        real lim = d->npc_geom[12], thd = es.vel[A][hz ? 2 : 1];
+        real lim = d->npc_geom[12], thd = es.vel[A][pz ? 4 : (hz ? 2 : 1)];
         thd = thd > lim ? lim : (thd < -lim ? -lim : thd);         /* URDF joint velocity limit */
         dof[(12 * A) * 2] += dt * thd;
         dof[(12 * A) * 2 + 1] = thd;

@@ -24,7 +24,7 @@ from mqe_b200.envs import configs as C  # noqa: E402
 
 TASKS = {"go1pushbox": C.Go1PushboxCfg, "go1gate": C.Go1GateCfg, "go1sheep-hard": C.NineSheepCfg, "go1sheep-easy": C.SingleSheepCfg,
          "go1revolvingdoor": C.Go1RotationCfg, "go1seesaw": C.Go1SeesawCfg, "go1football-defender": C.Go1FootballDefenderCfg, "go1plane": C.Go1PlaneCfg,
-         "go1wrestling": C.Go1WrestlingCfg, "go1bridge": C.Go1BridgeCfg}
+         "go1wrestling": C.Go1WrestlingCfg, "go1bridge": C.Go1BridgeCfg, "go1tug": C.Go1TugCfg}
 
 
 def make_pair(task, n, mode=E.POLICY_FP32, seed=0, precision="f32"):
@@ -89,7 +89,7 @@ def test_actuator_golden(golden_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1plane", "go1wrestling", "go1bridge"])
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1plane", "go1wrestling", "go1bridge", "go1tug"])
 def test_reset_matches_oracle(task):
     """reset_idx + compute_observations: same counter RNG, same arithmetic."""
     sc, eng, orc = make_pair(task, 64)
@@ -115,7 +115,7 @@ def _state_err(a_root, a_dof, b_root, b_dof):
             np.abs(a_dof[:, 0] - b_dof[:, 0]), np.abs(a_dof[:, 1] - b_dof[:, 1]))
 
 
-@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1pushbox", "go1revolvingdoor", "go1wrestling", "go1bridge"])
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1pushbox", "go1revolvingdoor", "go1wrestling", "go1bridge", "go1tug"])
 def test_single_substep_parity(task):
     """Single physics substeps from IDENTICAL states, robots dropped onto the floor so foot / knee / pair contacts,
     joint limits and the actuator net are all active.  Truth = the fp64 oracle; the fp32 oracle (dense Cholesky) run
@@ -200,7 +200,7 @@ def test_single_substep_parity(task):
 
 
 @pytest.mark.parametrize("mode", [E.POLICY_FP32, E.POLICY_BF16X3], ids=["fp32", "tcgen05-bf16x3"])
-@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1pushbox", "go1revolvingdoor", "go1wrestling", "go1bridge"])
+@pytest.mark.parametrize("task", ["go1gate", "go1sheep-hard", "go1football-defender", "go1seesaw", "go1pushbox", "go1revolvingdoor", "go1wrestling", "go1bridge", "go1tug"])
 def test_short_trajectory_parity(task, mode):
     """Full Go1.step() x 5 from reset on identical seeds and actions (tensor-core mode: steps 3.. are CUDA-graph replays)."""
     sc, eng, orc = make_pair(task, 32, mode)
@@ -328,7 +328,7 @@ def test_env_surface_go1gate():
 
 
 @pytest.mark.parametrize("task,D,A", [("go1sheep-hard", 34, 2), ("go1sheep-easy", 18, 2), ("go1seesaw", 14, 2), ("go1football-defender", 20, 2),
-                                      ("go1pushbox", 22, 2), ("go1revolvingdoor", 12, 2), ("go1wrestling", 12, 2), ("go1bridge", 12, 2)])
+                                      ("go1pushbox", 22, 2), ("go1revolvingdoor", 12, 2), ("go1wrestling", 12, 2), ("go1bridge", 12, 2), ("go1tug", 10, 2)])
 def test_env_surface_wrappers(task, D, A):
     from types import SimpleNamespace
     from mqe_b200.envs import make_mqe_env, custom_cfg

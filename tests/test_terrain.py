@@ -11,7 +11,7 @@ from mqe_b200.terrain.barrier_track import BarrierTrack
 
 TASKS = {
     "go1gate": C.Go1GateCfg, "go1sheep-easy": C.SingleSheepCfg, "go1sheep-hard": C.NineSheepCfg,
-    "go1seesaw": C.Go1SeesawCfg, "go1football-defender": C.Go1FootballDefenderCfg, "go1revolvingdoor": C.Go1RotationCfg, "go1wrestling": C.Go1WrestlingCfg, "go1bridge": C.Go1BridgeCfg,
+    "go1seesaw": C.Go1SeesawCfg, "go1football-defender": C.Go1FootballDefenderCfg, "go1revolvingdoor": C.Go1RotationCfg, "go1wrestling": C.Go1WrestlingCfg, "go1tug": C.Go1TugCfg, "go1bridge": C.Go1BridgeCfg,
     "go1pushbox": C.Go1PushboxCfg, "go1football-2vs2": C.Go1Football2vs2Cfg,
 }
 

@@ -19,6 +19,7 @@ CASES = {
     "go1revolvingdoor": (W.Go1RotationWrapper, C.Go1RotationCfg, 2, 1),
     "go1wrestling": (W.Go1WrestlingWrapper, C.Go1WrestlingCfg, 2, 1),
     "go1bridge": (W.Go1BridgeWrapper, C.Go1BridgeCfg, 2, 1),
+    "go1tug": (W.Go1TugWrapper, C.Go1TugCfg, 2, 1),
 }
 
 
@@ -40,6 +41,9 @@ class FakeEnv:
         self.env_agent_indices = torch.arange(self.num_envs * A).view(self.num_envs, A)
         if "in_base_init_state" in z.files:
             self.base_init_state = torch.as_tensor(z["in_base_init_state"])
+        self.npc_indices = torch.arange(self.num_envs * max(P, 1), dtype=torch.int32)
+        self.all_dof_states, self.sim = None, None
+        self.gym = Ns(set_dof_state_tensor_indexed=lambda *a: None)
         self._load(0)
 
     def _load(self, t):
@@ -49,6 +53,8 @@ class FakeEnv:
                           base_quat=torch.as_tensor(z["in_base_quat"][t]) if "in_base_quat" in z.files else None,
                           env_info={"gate_deviation": torch.as_tensor(z["in_gate_deviation"]).clone()})
         self.root_states_npc = torch.as_tensor(z["in_root_states_npc"][t])
+        if "in_dof_state_npc" in z.files:
+            self.dof_state_npc = torch.as_tensor(z["in_dof_state_npc"][t]).clone()
         self.collide_buf = torch.as_tensor(z["in_collide"][t])
         self.r_term_buff = torch.as_tensor(z["in_r_term"][t])
         self.p_term_buff = torch.as_tensor(z["in_p_term"][t])
@@ -60,6 +66,13 @@ class FakeEnv:
     def reset(self):
         self._load(0)
         return self.obs_buf
+
+    def step(self, action):
+        """Go1.step(): the wrapper has scaled the action itself (go1_tug_wrapper.py:70); the env clips it afterwards."""
+        self.last_action = action
+        self.t += 1
+        self._load(self.t)
+        return self.obs_buf, None, self.reset_buf, {}
 
     def step_from_wrapper(self, action):
         """The engine applies clip(+-1) * [2, .5, .5] inside the frame kernel; record what it would receive."""

@@ -57,6 +57,7 @@ def stub_modules():
         return roll % (2 * np.pi), pitch % (2 * np.pi), yaw % (2 * np.pi)
 
     sys.modules["isaacgym.torch_utils"].get_euler_xyz = get_euler_xyz
+    sys.modules["isaacgym"].gymtorch = types.SimpleNamespace(unwrap_tensor=lambda t: t)      # go1_tug_wrapper.py:1, :67-69
 
 
 def load(name):
@@ -89,6 +90,9 @@ class FakeEnv:
             self.gate_pos = torch.as_tensor(rec["gate_pos"])
         self.env_agent_indices = torch.arange(self.num_envs * num_agents).view(self.num_envs, num_agents)
         self.base_init_state = torch.as_tensor(rec["base_init_state"])
+        self.npc_indices = torch.arange(self.num_envs * max(num_npcs, 1), dtype=torch.int32)
+        self.all_dof_states, self.sim = None, None
+        self.gym = types.SimpleNamespace(set_dof_state_tensor_indexed=lambda *a: None)
         self._load(0)
 
     def _load(self, t):
@@ -98,6 +102,7 @@ class FakeEnv:
                           env_info={"gate_deviation": torch.as_tensor(r["gate_deviation"]).clone()})
         if self.num_npcs:
             self.root_states_npc = torch.as_tensor(r["root_states_npc"][t])
+            self.dof_state_npc = torch.as_tensor(r["dof_state_npc"][t]).clone()
         self.collide_buf = torch.as_tensor(r["collide"][t])
         self.r_term_buff = torch.as_tensor(r["r_term"][t])
         self.p_term_buff = torch.as_tensor(r["p_term"][t])
@@ -145,6 +150,7 @@ def make_record(rng, N, A, P, T, with_gate=False):
     rec["base_quat"] = np.stack([cy * sr * cp - sy * cr * sp, cy * cr * sp + sy * sr * cp, sy * cr * cp - cy * sr * sp,
                                  cy * cr * cp + sy * sr * sp], axis=-1).astype(np.float32)
     rec["base_init_state"] = rng2.uniform(-1, 3, size=(M, 13)).astype(np.float32)
+    rec["dof_state_npc"] = rng2.uniform(-1.5, 1.5, size=(T, N, 1, 2)).astype(np.float32)
     if A >= 2:                                   # some envs with the two agents within 0.5 m (agent-distance terms)
         bp = rec["base_pos"].reshape(T, N, A, 3)
         close = rng.random((T, N)) < 0.4
@@ -206,6 +212,8 @@ def main():
     run("go1revolvingdoor", load("go1_rotation_wrapper").Go1RotationWrapper, C.Go1RotationCfg(), 2, 1, 6, N=2, T=12)
     run("go1wrestling", load("go1_wrestling_wrapper").Go1WrestlingWrapper, C.Go1WrestlingCfg(), 2, 1, 7)
     run("go1bridge", load("go1_bridge_wrapper").Go1BridgeWrapper, C.Go1BridgeCfg(), 2, 1, 8)
+    # the reference's tug wrapper only broadcasts for num_envs = 1 (go1_tug_wrapper.py:88: [N, 1] += [N])
+    run("go1tug", load("go1_tug_wrapper").Go1TugWrapper, C.Go1TugCfg(), 2, 1, 9, N=1, T=16)
 
 
 if __name__ == "__main__":
