@@ -6,7 +6,8 @@ from mqe_b200 import engine as E, scene as S
 from mqe_b200.envs import configs as C
 
 for task, fn, n in (("go1gate", C.Go1GateCfg, 8), ("go1sheep-hard", C.NineSheepCfg, 3), ("go1football-defender", C.Go1FootballDefenderCfg, 5),
-                    ("go1seesaw", C.Go1SeesawCfg, 7), ("go1football-2vs2", C.Go1Football2vs2Cfg, 3)):
+                    ("go1seesaw", C.Go1SeesawCfg, 7), ("go1football-2vs2", C.Go1Football2vs2Cfg, 3), ("go1pushbox", C.Go1PushboxCfg, 5),
+                    ("go1tug", C.Go1TugCfg, 6), ("go1wrestling", C.Go1WrestlingCfg, 5), ("go1bridge", C.Go1BridgeCfg, 4)):
     for mode in (E.POLICY_FP32, E.POLICY_BF16X3):
         cfg = fn(); cfg.env.num_envs = n; cfg.env.episode_length_s = 0.1
         np.random.seed(0)
