@@ -130,6 +130,22 @@ typedef struct {
     MqeWeights weights;
 } MqeSimDesc;
 
+/* Task-wrapper gather fused into the step: observation vector, per-agent reward and the running sums behind the
+ * wrappers' `reward_buffer`, for the wrappers of the BASELINE tasks.  Scales are `cfg.rewards.scales.*` in the order given. */
+typedef enum {
+    MQE_WRAP_NONE = 0,
+    MQE_WRAP_SHEEP = 1,              /* go1_sheep_wrapper.py:54-118   scale: success, contact_punishment, sheep_movement, mixed_sheep,
+                                        sheep_pos_var_lin_punishment, sheep_pos_var_exp_punishment; D = 14 + 2 P + A */
+    MQE_WRAP_SEESAW = 2,             /* go1_seesaw_wrapper.py:48-120  scale: x_movement, height, y_punishment, contact_punishment,
+                                        agent_distance_punishment, success, fall_punishment; D = 12 + A */
+    MQE_WRAP_FOOTBALL_DEFENDER = 3   /* go1_football_wrapper.py:57-91 scale: goal, ball_gate_distance; D = 20, two reported agents */
+} MqeWrapperKind;
+typedef struct {
+    int32_t kind;
+    float scale[8];
+    const float *h_gate;             /* HOST: sheep [N][2] gate position (env-relative), football defender [N][3] gate position (world) */
+} MqeWrapperDesc;
+
 typedef struct MqeSim MqeSim;
 
 /* Buffers owned by the engine; mqe_sim_get_buffer returns the device pointer and shape so a host
@@ -162,6 +178,9 @@ typedef enum {
     MQE_BUF_SHEEP_STATS,        /* f32 [N][3]     sheep_pos_avg xy, sheep_pos_var */
     MQE_BUF_STATS,              /* i32 [8]        contact / row statistics of the last step */
     MQE_BUF_CLOCK,              /* f32 [N*A][4]   gait clock inputs (go1.py:240-279)        */
+    MQE_BUF_WRAP_OBS,           /* f32 [N][Aw][D]  task-wrapper observation (after mqe_sim_set_wrapper)            */
+    MQE_BUF_WRAP_REWARD,        /* f32 [N][Aw]     task-wrapper reward                                              */
+    MQE_BUF_WRAP_SUMS,          /* f64 [16]        running sums of the reward terms (scale order), [8] = steps      */
     MQE_BUF_WARP_TRACE,         /* i64 [warps][20] substep kernel trace per warp of envs: start ns, end ns, pair contacts, widest row count, then (MQE_TRACE=1) cycles per phase */
     MQE_BUF_COUNT
 } MqeBuffer;
@@ -192,6 +211,13 @@ int mqe_sim_set_stream(MqeSim *sim, void *stream);
  * is a task wrapper handing over raw policy actions (wrappers/go1_*_wrapper.py step()), [1,1,1] when the caller is
  * Go1.step() itself and the wrapper has already scaled (go1.py:38). */
 int mqe_sim_set_action_scale(MqeSim *sim, const float scale[3]);
+
+/* Enable the fused task-wrapper gather: every following mqe_sim_step also fills MQE_BUF_WRAP_OBS / _REWARD / _SUMS, and
+ * mqe_sim_reset fills the observation (the wrappers' reset()).  kind = MQE_WRAP_NONE switches it off again. */
+int mqe_sim_set_wrapper(MqeSim *sim, const MqeWrapperDesc *desc);
+/* the wrappers' reset() without an env reset: observation only, per-episode wrapper state cleared (used once, right after
+ * mqe_sim_set_wrapper, when the env has already been reset) */
+int mqe_sim_wrapper_reset(MqeSim *sim);
 
 /* gym.acquire_*_tensor (legged_robot.py:554-557).  shape[4] is zero padded; elem_size in bytes. */
 int mqe_sim_get_buffer(MqeSim *sim, int which, void **d_ptr, int64_t shape[4], int32_t *elem_size);

@@ -47,6 +47,7 @@ struct MqeSim {
     cudaStream_t cap_stream = nullptr;
     bool use_graph = false;
     long long plain_steps = 0;
+    WrapParams wrap = {};                // fused task-wrapper gather (mqe_sim_set_wrapper); kind 0 = off
     struct Pinned { char *ptr; size_t bytes; };
     std::vector<Pinned> pinned;          // host ranges registered with mqe_sim_pin_host: mqe_sim_step_host copies straight to / from them
     bool is_pinned(const void *ptr, size_t bytes) const {
@@ -360,8 +361,55 @@ int mqe_sim_set_action_scale(MqeSim *s, const float scale[3]) {
     return MQE_OK;
 }
 
+int mqe_sim_set_wrapper(MqeSim *s, const MqeWrapperDesc *d) {
+    if (!s || !d) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);      // the step graph changes shape
+    s->graphs.clear();
+    const DevParams &p = s->p;
+    WrapParams w = {};
+    w.kind = d->kind;
+    if (d->kind == MQE_WRAP_NONE) { s->wrap = w; return MQE_OK; }
+    int gate_cols = 0;
+    if (d->kind == MQE_WRAP_SHEEP) {
+        if (p.npc_ctrl != MQE_NPC_SHEEP || p.P < 1 || p.P > 12) return fail(MQE_ERR_INVALID, "sheep wrapper needs 1..12 sheep");
+        w.Aw = p.A; w.D = 14 + 2 * p.P + p.A; gate_cols = 2;
+    } else if (d->kind == MQE_WRAP_SEESAW) {
+        w.Aw = p.A; w.D = 12 + p.A;
+    } else if (d->kind == MQE_WRAP_FOOTBALL_DEFENDER) {
+        if (p.A < 2 || p.P < 1) return fail(MQE_ERR_INVALID, "football wrapper needs two agents and the ball");
+        w.Aw = 2; w.D = 20; gate_cols = 3;
+    } else return fail(MQE_ERR_INVALID, "unknown wrapper kind");
+    if (w.Aw > 4) return fail(MQE_ERR_INVALID, "wrapper: at most 4 agents");
+    for (int i = 0; i < 8; i++) w.scale[i] = d->scale[i];
+    if (gate_cols) {
+        if (!d->h_gate) return fail(MQE_ERR_INVALID, "h_gate missing");
+        CK(dupload(s, &w.gate, d->h_gate, (size_t)p.N * gate_cols));
+        CK(cudaStreamSynchronize(s->stream));
+    }
+    CK(dalloc(s, &w.obs, (size_t)p.N * w.Aw * w.D)); CK(dalloc(s, &w.reward, (size_t)p.N * w.Aw));
+    CK(dalloc(s, &w.sums, (size_t)16)); CK(dalloc(s, &w.last, (size_t)p.N * 4));
+    CK(dalloc(s, &w.delayed_reset, (size_t)p.N)); CK(dalloc(s, &w.has_last, (size_t)p.N));
+    s->wrap = w;
+    set_buf(s, MQE_BUF_WRAP_OBS, w.obs, 4, p.N, w.Aw, w.D);
+    set_buf(s, MQE_BUF_WRAP_REWARD, w.reward, 4, p.N, w.Aw);
+    set_buf(s, MQE_BUF_WRAP_SUMS, w.sums, 8, 16);
+    return MQE_OK;
+}
+
+int mqe_sim_wrapper_reset(MqeSim *s) {
+    if (!s) return fail(MQE_ERR_INVALID, "null handle");
+    if (s->wrap.kind == MQE_WRAP_NONE) return fail(MQE_ERR_INVALID, "no task wrapper set");
+    CK(cudaSetDevice(s->device));
+    CK(mqe_launch_task_gather(s->p, s->wrap, 1, s->stream));
+    s->launches += 1;
+    return MQE_OK;
+}
+
 int mqe_sim_get_buffer(MqeSim *s, int which, void **d_ptr, int64_t shape[4], int32_t *elem_size) {
     if (!s || which < 0 || which >= MQE_BUF_COUNT) return fail(MQE_ERR_INVALID, "bad buffer id");
+    if (!s->bufs[which].ptr) return fail(MQE_ERR_INVALID, "buffer not allocated (task-wrapper buffers exist after mqe_sim_set_wrapper)");
     if (d_ptr) *d_ptr = s->bufs[which].ptr;
     if (shape) for (int i = 0; i < 4; i++) shape[i] = s->bufs[which].shape[i];
     if (elem_size) *elem_size = s->bufs[which].elem;
@@ -375,6 +423,7 @@ int mqe_sim_reset(MqeSim *s) {
     CK(cudaSetDevice(s->device));
     CK(mqe_launch_reset_all(s->p, s->stream));
     s->launches += 1;
+    if (s->wrap.kind != MQE_WRAP_NONE) { CK(mqe_launch_task_gather(s->p, s->wrap, 1, s->stream)); s->launches += 1; }
     return MQE_OK;
 }
 
@@ -440,7 +489,11 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     if (rc != MQE_OK) return rc;
     rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: k_policy_finish zeroed the statistics
     if (rc != MQE_OK) return rc;
-    return post_impl(s, device_ctr);
+    rc = post_impl(s, device_ctr);
+    if (rc != MQE_OK || s->wrap.kind == MQE_WRAP_NONE) return rc;
+    CK(mqe_launch_task_gather(s->p, s->wrap, 0, s->stream));
+    s->launches += 1;
+    return MQE_OK;
 }
 
 int mqe_sim_step(MqeSim *s, const float *d_actions) {

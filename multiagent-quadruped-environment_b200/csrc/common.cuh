@@ -67,6 +67,18 @@ struct DevParams {
     unsigned short *hist_hi, *hist_lo;  // bf16 split ring, blocked layout (tensor-core modes)
 };
 
+// task-wrapper gather (wrapper.cu): what mqe/envs/wrappers/go1_{sheep,seesaw,football}_wrapper.py compute after every env step
+struct WrapParams {
+    int kind, D, Aw;              // MqeWrapperKind, observation floats per agent, agents the wrapper reports (football defender: 2 of 3)
+    float scale[8];               // reward scales in the order of MqeWrapperDesc
+    const float *gate;            // sheep: [N][2] gate position (env-relative); football defender: [N][3] gate position (world)
+    float *obs, *reward;          // [N][Aw][D], [N][Aw]
+    double *sums;                 // [16]: running sums of the reward terms, [8] = steps
+    float *last;                  // sheep: [N][2] last flock centre; seesaw: [N][Aw] last x
+    unsigned char *delayed_reset; // sheep: reset_buf of the previous step (go1_sheep_wrapper.py:116)
+    int *has_last;                // [N]
+};
+
 // ---------------------------------------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the step is launched with programmatic stream serialization: it may be scheduled while its predecessor
 // is still running and does its own set-up (barrier init, TMEM allocation, constant staging) in that shadow; pdl_wait()

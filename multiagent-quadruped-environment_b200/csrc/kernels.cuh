@@ -35,6 +35,7 @@ cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat
                                     int head, int rows, int passes, float *Z, int planes_out, const int *ctr, cudaStream_t st);
 cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, int M, int passes,
                                       cudaStream_t st, int *launches);
+cudaError_t mqe_launch_task_gather(const DevParams &p, const WrapParams &w, int mode, cudaStream_t st);
 size_t mqe_substeps_smem_bytes(int N, int A, int Pd, int E, int maxpair);
 size_t mqe_substeps_row_scratch_floats(int N, int A);
 size_t mqe_substeps_prow_scratch_floats(int N, int maxpair);

@@ -23,7 +23,7 @@ OBS_FLOATS = 71
 (BUF_ROOT_STATES, BUF_DOF_STATES, BUF_CONTACT_FORCES, BUF_TORQUES, BUF_ACTIONS, BUF_LAST_ACTIONS, BUF_OBS,
  BUF_BASE_LIN_VEL, BUF_BASE_ANG_VEL, BUF_PROJ_GRAVITY, BUF_RESET, BUF_TIMEOUT, BUF_COLLIDE, BUF_ROLL_TERM,
  BUF_PITCH_TERM, BUF_ZLOW_TERM, BUF_ZHIGH_TERM, BUF_EPISODE_LENGTH, BUF_COMMANDS, BUF_LOC_OBS, BUF_LOC_ACTION,
- BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_CLOCK, BUF_WARP_TRACE, BUF_COUNT) = range(28)
+ BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_CLOCK, BUF_WRAP_OBS, BUF_WRAP_REWARD, BUF_WRAP_SUMS, BUF_WARP_TRACE, BUF_COUNT) = range(31)
 
 OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
     "base_pos": (0, 3), "base_quat": (3, 7), "dof_pos": (7, 19), "dof_vel": (19, 31), "lin_vel": (31, 34),
@@ -32,6 +32,12 @@ OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
 }
 
 NPC_NONE, NPC_RIGID, NPC_SEESAW, NPC_BOX, NPC_PLATFORM = 0, 1, 2, 3, 4
+WRAP_NONE, WRAP_SHEEP, WRAP_SEESAW, WRAP_FOOTBALL_DEFENDER = 0, 1, 2, 3
+
+
+class WrapperDescC(ctypes.Structure):
+    """MqeWrapperDesc (include/mqe_b200.h)"""
+    _fields_ = [("kind", ctypes.c_int32), ("scale", ctypes.c_float * 8), ("h_gate", ctypes.POINTER(ctypes.c_float))]
 NPC_PASSIVE, NPC_SHEEP = 0, 1
 POLICY_FP32, POLICY_BF16X3, POLICY_BF16 = 0, 1, 2
 POLICY_MODE_DEFAULT = int(os.environ.get("MQE_POLICY_MODE", POLICY_FP32))
@@ -144,6 +150,8 @@ def load_library(path=None):
     lib.mqe_sim_reset.argtypes = [vp]
     lib.mqe_sim_step.argtypes = [vp, vp]
     lib.mqe_sim_step_host.argtypes = [vp, vp, vp, vp]
+    lib.mqe_sim_set_wrapper.argtypes = [vp, vp]
+    lib.mqe_sim_wrapper_reset.argtypes = [vp]
     lib.mqe_sim_pin_host.argtypes = [vp, vp, ctypes.c_size_t]
     lib.mqe_sim_unpin_host.argtypes = [vp, vp]
     lib.mqe_sim_policy.argtypes = [vp, vp]
@@ -165,7 +173,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = [
     "mqe_last_error", "mqe_abi_version", "mqe_device_count", "mqe_sim_create", "mqe_sim_destroy", "mqe_sim_set_stream", "mqe_sim_set_action_scale",
-    "mqe_sim_get_buffer", "mqe_sim_reset", "mqe_sim_step", "mqe_sim_step_host", "mqe_sim_pin_host", "mqe_sim_unpin_host", "mqe_sim_policy", "mqe_sim_substeps",
+    "mqe_sim_set_wrapper", "mqe_sim_wrapper_reset", "mqe_sim_get_buffer", "mqe_sim_reset", "mqe_sim_step", "mqe_sim_step_host", "mqe_sim_pin_host", "mqe_sim_unpin_host", "mqe_sim_policy", "mqe_sim_substeps",
     "mqe_sim_post_physics", "mqe_sim_set_root_indexed", "mqe_sim_set_dof_indexed", "mqe_policy_forward",
     "mqe_actuator_forward", "mqe_sim_history_head", "mqe_sim_synchronize", "mqe_sim_launch_count",
 ]
@@ -179,7 +187,7 @@ class _DevArray:
         self._owner = owner
 
 
-_TYPESTR = {("f", 4): "<f4", ("u", 1): "|u1", ("i", 8): "<i8", ("i", 4): "<i4", ("h", 2): "<u2"}
+_TYPESTR = {("f", 4): "<f4", ("f", 8): "<f8", ("u", 1): "|u1", ("i", 8): "<i8", ("i", 4): "<i4", ("h", 2): "<u2"}
 _BUF_KIND = {BUF_RESET: "u", BUF_TIMEOUT: "u", BUF_COLLIDE: "u", BUF_ROLL_TERM: "u", BUF_PITCH_TERM: "u",
              BUF_ZLOW_TERM: "u", BUF_ZHIGH_TERM: "u", BUF_EPISODE_LENGTH: "i", BUF_STATS: "i", BUF_WARP_TRACE: "i"}
 
@@ -239,6 +247,22 @@ class Engine:
 
     def step(self, actions_ptr: int):
         self._check(self.lib.mqe_sim_step(self.h, ctypes.c_void_p(actions_ptr)))
+
+    def set_wrapper(self, kind: int, scales, gate: np.ndarray | None = None):
+        """Fuse a task wrapper's obs / reward gather into the step (mqe_sim_set_wrapper)."""
+        d = WrapperDescC()
+        d.kind = int(kind)
+        for i, v in enumerate(scales):
+            d.scale[i] = float(v)
+        if gate is not None:
+            gate = np.ascontiguousarray(gate, dtype=np.float32)
+            d.h_gate = gate.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        self._check(self.lib.mqe_sim_set_wrapper(self.h, ctypes.byref(d)))
+        for b in (BUF_WRAP_OBS, BUF_WRAP_REWARD, BUF_WRAP_SUMS):
+            self._views.pop(b, None)
+
+    def wrapper_reset(self):
+        self._check(self.lib.mqe_sim_wrapper_reset(self.h))
 
     def pin_host(self, arr: np.ndarray):
         """Page-lock a caller-owned numpy buffer so step_host DMAs straight from / into it; keep `arr` alive until close()."""

@@ -8,6 +8,8 @@ Differences from the reference that do not change any returned value:
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .gym_shim import Wrapper, spaces
@@ -25,6 +27,7 @@ class EmptyWrapper(Wrapper):
         for key in dir(self.env.cfg.rewards.scales):
             if key[0] != "_" and "scale" in key:
                 setattr(self, key, getattr(self.env.cfg.rewards.scales, key))
+        self._fuse_allowed = os.environ.get("MQE_FUSED_WRAPPERS", "1") != "0"
         dev = self.env.device
         self.obs_ids = torch.eye(self.num_agents, dtype=torch.float32, device=dev).repeat(self.num_envs, 1).reshape(
             self.num_envs, self.num_agents, -1)
@@ -34,6 +37,51 @@ class EmptyWrapper(Wrapper):
 
     def _base_info(self, obs_buf):
         return torch.cat([obs_buf.base_pos, obs_buf.base_rpy], dim=1).reshape(self.env.num_envs, self.env.num_agents, -1)
+
+    # -- fused gather (csrc/wrapper.cu): obs / reward / reward_buffer sums computed by one kernel inside the step graph ----------
+    def _fuse(self, kind, scales, keys, gate=None):
+        """Switch this wrapper to the engine's fused gather.  Only on a real env (an `engine` behind it); the torch code below
+        stays the definition (pinned against the reference on the CPU, compared with the kernel on the GPU)."""
+        eng = getattr(self.env, "engine", None)
+        if eng is None or not self._fuse_allowed:
+            return False
+        from .. import engine as E
+        eng.set_wrapper(kind, scales, None if gate is None else gate.detach().cpu().numpy())
+        self._wobs, self._wrew = eng.tensor(E.BUF_WRAP_OBS), eng.tensor(E.BUF_WRAP_REWARD)
+        self.reward_buffer = _FusedRewardBuffer(keys, eng.tensor(E.BUF_WRAP_SUMS))
+        eng.wrapper_reset()
+        return True
+
+    def _fused_step(self, action):
+        _, _, termination, info = self.env.step_from_wrapper(action)
+        return self._wobs.clone(), self._wrew.clone(), termination, info
+
+
+class _FusedRewardBuffer(dict):
+    """`reward_buffer` backed by the kernel's running sums: reads are lazy 0-dim tensors (`float(v)` / `v.cpu()` work as on the
+    reference's values), assigning a key (loggers zero them) re-bases it."""
+
+    def __init__(self, key_to_index, sums):
+        super().__init__({k: 0 for k in key_to_index})
+        self._idx, self._sums = dict(key_to_index), sums
+        self._off = {k: 0.0 for k in key_to_index}
+
+    def __getitem__(self, k):
+        return self._sums[self._idx[k]] + self._off[k]
+
+    def __setitem__(self, k, v):
+        if k not in self._idx:
+            raise KeyError(k)
+        self._off[k] = float(v) - float(self._sums[self._idx[k]])
+
+    def get(self, k, default=None):
+        return self[k] if k in self._idx else default
+
+    def items(self):
+        return [(k, self[k]) for k in self._idx]
+
+    def values(self):
+        return [self[k] for k in self._idx]
 
 
 class Go1GateWrapper(EmptyWrapper):
@@ -143,11 +191,20 @@ class Go1SheepWrapper(EmptyWrapper):
         obs_buf = self.env.reset()
         if self.gate_pos is None:
             self._init_extras(obs_buf)
+            s = self
+            self._fused = self._fuse(1, [s.success_reward_scale, s.contact_punishment_scale, s.sheep_movement_reward_scale, s.mixed_sheep_reward_scale,
+                                         s.sheep_pos_var_lin_punishment_scale, s.sheep_pos_var_exp_punishment_scale],
+                                     {"success reward": 0, "contact punishment": 1, "sheep movement reward": 2, "mixed sheep reward": 3,
+                                      "sheep pos var punishment": 4, "step count": 8}, gate=self.gate_pos[:, 0, :])
+        if getattr(self, "_fused", False):
+            return self._wobs.clone()
         obs, _ = self._obs(obs_buf)
         self.last_sheep_pos_avg = None
         return obs
 
     def step(self, action):
+        if getattr(self, "_fused", False):
+            return self._fused_step(action)
         obs_buf, _, termination, info = self.env.step_from_wrapper(action)
         if self.gate_pos is None:
             self._init_extras(obs_buf)
@@ -201,9 +258,18 @@ class Go1SeesawWrapper(EmptyWrapper):
         return torch.cat([self.obs_ids, base_info, torch.flip(base_info, [1])], dim=2)
 
     def reset(self):
-        return self._obs(self.env.reset())
+        obs_buf = self.env.reset()
+        if not hasattr(self, "_fused"):
+            s = self
+            self._fused = self._fuse(2, [s.x_movement_reward_scale, s.height_reward_scale, s.y_punishment_scale, s.contact_punishment_scale,
+                                         s.agent_distance_punishment_scale, s.success_reward_scale, s.fall_punishment_scale],
+                                     {"x movement reward": 0, "height reward": 1, "y punishment": 2, "contact punishment": 3,
+                                      "agent distance punishment": 4, "success reward": 5, "fall punishment": 6, "step count": 8})
+        return self._wobs.clone() if self._fused else self._obs(obs_buf)
 
     def step(self, action):
+        if getattr(self, "_fused", False):
+            return self._fused_step(action)
         obs_buf, _, termination, info = self.env.step_from_wrapper(action)
         obs = self._obs(obs_buf)
         base_pos = obs_buf.base_pos
@@ -269,9 +335,15 @@ class Go1FootballDefenderWrapper(EmptyWrapper):
         return torch.cat([self.obs_ids, base_info, torch.flip(base_info, [1]), ball_pos, ball_vel], dim=2), ball_pos
 
     def reset(self):
-        return self._obs(self.env.reset())[0]
+        obs_buf = self.env.reset()
+        if not hasattr(self, "_fused"):
+            self._fused = self._fuse(3, [self.goal_reward_scale, self.ball_gate_distance_reward_scale],
+                                     {"goal reward": 0, "ball gate distance reward": 1, "step count": 8}, gate=self.gate_pos)
+        return self._wobs.clone() if self._fused else self._obs(obs_buf)[0]
 
     def step(self, action):
+        if getattr(self, "_fused", False):
+            return self._fused_step(action)
         obs_buf, _, termination, info = self.env.step_from_wrapper(action)
         obs, ball_pos = self._obs(obs_buf)
         self._acc("step count", 1)

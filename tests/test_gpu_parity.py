@@ -391,3 +391,43 @@ def test_football_game_tasks(task, A):
     assert (dx[:, 0] > 0).all() and dx[:, 0].median() > 0.1 and (dx[:, A - 1] < 0).all() and dx[:, A - 1].median() < -0.1
     assert env.ball_pos.shape == (32, 2, 3)
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["go1sheep-hard", "go1sheep-easy", "go1seesaw", "go1football-defender"])
+def test_fused_wrapper_gather_matches_torch_wrapper(task, monkeypatch):
+    """csrc/wrapper.cu (one kernel inside the step graph) against the torch wrappers (pinned to the reference's own code by
+    tests/test_wrappers_golden.py): two envs built from the same seed, same actions, resets included (short episodes)."""
+    from types import SimpleNamespace
+    from mqe_b200.envs import make_mqe_env
+
+    def build(fused):
+        monkeypatch.setenv("MQE_FUSED_WRAPPERS", "1" if fused else "0")
+        args = SimpleNamespace(num_envs=33, seed=3, headless=True, record_video=False, sim_device="cuda:0")
+
+        def cc(cfg):
+            cfg.env.num_envs = 33
+            cfg.env.episode_length_s = 0.3                        # 15 policy steps: time-outs exercise the reset-dependent terms
+            return cfg
+        return make_mqe_env(task, args, cc)[0]
+
+    ef, et = build(True), build(False)
+    of, ot = ef.reset(), et.reset()
+    assert getattr(ef, "_fused", False) and not getattr(et, "_fused", False)
+    assert torch.allclose(of, ot, rtol=1e-6, atol=1e-6)
+    A = of.shape[1]
+    rng = np.random.default_rng(0)
+    for s in range(40):
+        a = torch.as_tensor(rng.uniform(-1.2, 1.2, size=(33, A, 3)).astype(np.float32), device="cuda:0")
+        of, rf, df, _ = ef.step(a.clone())
+        ot, rt, dt_, _ = et.step(a.clone())
+        assert torch.equal(df, dt_), s
+        assert torch.allclose(of, ot, rtol=1e-6, atol=1e-6), (s, (of - ot).abs().max())
+        assert rf.shape == rt.shape and torch.allclose(rf, rt, rtol=1e-5, atol=1e-5), (s, (rf - rt).abs().max())
+    for k in et.reward_buffer:
+        vt, vf = float(et.reward_buffer[k]), float(ef.reward_buffer[k])
+        assert abs(vt - vf) <= 1e-4 * max(1.0, abs(vt)), (k, vt, vf)
+    ef.reward_buffer["step count"] = 0                            # loggers zero the buffer: assignment re-bases the running sum
+    ef.step(a.clone())
+    assert float(ef.reward_buffer["step count"]) == 1
+    ef.close(); et.close()
