@@ -915,7 +915,9 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 const float *oy = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE + RS_ORIGIN : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE + NS_ORIGIN;
                 float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
                 float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
-                if (dx * dx + dy * dy + dz * dz <= lim * lim) close = true;
+                const bool c = dx * dx + dy * dy + dz * dz <= lim * lim;
+                capmask[X * G + Y] = capmask[Y * G + X] = c ? 1 : 0;       // pre-flag: only pairs in range get their capsule masks computed
+                close |= c;
             }
             if (env >= p.N) close = false;
             bool any_close = __ballot_sync(env_mask, close) != 0u;
@@ -963,6 +965,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 bool live_any = false;
                 for (int Y = 0; Y < Gc; Y++) {
                     if (Y == grp || grp >= Gc) continue;
+                    if (!capmask[grp * G + Y]) continue;                     // out of broadphase range: the mask stays 0 (same for the whole quad)
                     const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
                     const float *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
                     const float reach = by_[Y < A ? RS_BOUND : NS_BOUND] + p.coff;
