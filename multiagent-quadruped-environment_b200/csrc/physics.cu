@@ -1009,7 +1009,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     // number rank, rank + L, rank + 2L, ... of mask[Y][X], so every round covers L consecutive cj in order.
                     int *cand = p.cand_scratch + (size_t)env * max_cand;
                     int ncand = 0;
-                    for (int X = 0; X < Gc - 1; X++)
+                    for (int X = 0; X < min(A, Gc - 1); X++)                        // pairs with a robot on the X side (robot-robot, robot-NPC)
                         for (int Y = X + 1; Y < Gc; Y++) {
                             const unsigned mXY = (unsigned)capmask[X * G + Y], mYX = (unsigned)capmask[Y * G + X];
                             if (!mXY || !mYX) continue;                                  // uniform over the env's lanes
@@ -1055,6 +1055,25 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                                 }
                             }
                         }
+                    // NPC-NPC pairs have one capsule each: a pair whose two masks are set IS the candidate, so they are appended L pairs per
+                    // round (lexicographic (X, Y) order, after every pair with a robot on the X side: still the canonical order)
+                    {
+                        const int Pn = Gc - A, npp = Pn * (Pn - 1) / 2;
+                        for (int t0 = 0; t0 < npp; t0 += lanes_per_env) {
+                            const int t = t0 + rank_in_env;
+                            bool ok = false;
+                            int X = 0, Y = 0;
+                            if (t < npp) {
+                                int i = 0, rem = t;
+                                while (rem >= Pn - 1 - i) { rem -= Pn - 1 - i; i++; }
+                                X = A + i; Y = X + 1 + rem;
+                                ok = capmask[X * G + Y] && capmask[Y * G + X];
+                            }
+                            const unsigned ob = __ballot_sync(env_mask, ok);
+                            if (ok) cand[ncand + __popc(ob & ((1u << lane) - 1u))] = X | (Y << 16);
+                            ncand += __popc(ob);
+                        }
+                    }
                     __syncwarp(env_mask);
                     // Stage 2: exact segment / segment test on the candidates
                     for (int t0 = 0; t0 < ncand; t0 += lanes_per_env) {
