@@ -247,6 +247,20 @@ def run_gpu(args):
                 "note": "scalar-fp32 / latency-bound articulated dynamics + PGS: algorithmic bytes per launch are tiny against the time"}
     policy_flops = 2.0 * 1_812_224 * n_local * A
     roofline["policy_tflops"] = policy_flops / (float(np.mean(pol_ms)) * 1e-3) / 1e12
+    # the one genuinely dense contraction of the path: the walk policy on the tensor pipe.  bf16x3 issues three bf16
+    # MMAs per fp32-equivalent product; the time is the whole policy phase (frame + layer 0 + tail + finish kernels).
+    passes = {"fp32": 0, "bf16x3": 3, "bf16": 1}[args.policy]
+    tpeak = None
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        with open(ppath) as f:
+            tpeak = float(json.load(f).get("bf16_tflops_sustained", 0.0)) or None
+    if passes:
+        ach = passes * policy_flops / (float(np.mean(pol_ms)) * 1e-3) / 1e12
+        roofline["policy"] = {"bound": "tensor", "kernels": "k_policy_frame + k_policy_l0_tc + k_linear_tc x3 + k_body_latent_planes + k_policy_finish",
+                              "achieved": ach, "peak": tpeak or 1368.9, "unit": "TFLOP/s", "frac": ach / (tpeak or 1368.9),
+                              "peak_source": "measured (bf16 sustained)" if tpeak else "fallback",
+                              "note": f"{passes} bf16 MMA passes per fp32-equivalent product; fp32-equivalent rate is policy_tflops"}
 
     # ---- e2e: through the C-ABI with HOST buffers ----
     h_obs = np.empty((n_local * A, E.OBS_FLOATS), dtype=np.float32)

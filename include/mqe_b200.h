@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MQE_ABI_VERSION 1
+#define MQE_ABI_VERSION 2
 #define MQE_MAX_PROBES 32
 #define MQE_MAX_CAPS 20
 #define MQE_NUM_DOF 12
@@ -105,7 +105,7 @@ typedef struct {
     float npc_mass, npc_inertia, npc_radius, npc_halflen;
     float sheep_scale, sheep_randomness;        /* go1_sheep_config.py asset.sheep_movement_*              */
     float gate_x;                               /* defender: init+plane block length                       */
-    float reserved2;
+    float max_push_vel_xy;                      /* domain_rand.max_push_vel_xy (legged_robot.py:472-477)   */
     /* MQE_NPC_SEESAW geometry (resources/objects/seesaw.urdf): [0..2] revolute-y joint origin rel. the fixed base,
      * [3] plank box / COM x offset in the plank frame, [4..6] plank half extents, [7..9] platform (base box) half extents,
      * [10] column radius, [11] column length (0: none), [12] joint velocity limit [rad/s], [13] hinge axis (0: y seesaw,
@@ -118,7 +118,9 @@ typedef struct {
     uint64_t seed;
     /* static world: 2-D signed distance to the wall footprint on the BarrierTrack pixel grid */
     int32_t sdf_nx, sdf_ny;
-    float sdf_cell, reserved3;
+    float sdf_cell;
+    int32_t push_interval;                      /* domain_rand.push_robots: every push_interval policy steps (ceil(push_interval_s / dt),
+                                                   legged_robot.py:1024) every robot's base velocity x, y is redrawn in +-max_push_vel_xy; 0 = off */
     const float *h_sdf;                         /* [nx][ny] host, copied                                   */
     /* per-env constants, host, copied */
     const float *h_env_origins;                 /* [N][3]                                                  */
@@ -126,6 +128,8 @@ typedef struct {
     const float *h_base_init_state;             /* [N*A][13]                                               */
     const float *h_npc_init_state;              /* [N*P][13] or NULL                                       */
     const float *h_npc_dof_default;             /* [D] or NULL                                             */
+    const float *h_env_friction;                /* [N] contact friction per env (domain_rand.randomize_friction, legged_robot.py:283-294,
+                                                   already combined with the terrain's) or NULL: `friction` everywhere */
     MqeRobotModel model;
     MqeWeights weights;
 } MqeSimDesc;

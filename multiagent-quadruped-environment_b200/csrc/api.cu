@@ -160,6 +160,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     p.npc_mass = d->npc_mass; p.npc_inertia = d->npc_inertia; p.npc_radius = d->npc_radius; p.npc_halflen = d->npc_halflen;
     p.sheep_scale = d->sheep_scale; p.sheep_rand = d->sheep_randomness; p.gate_x = d->gate_x;
     p.seed = d->seed;
+    p.push_interval = d->push_interval > 0 ? d->push_interval : 0; p.max_push_vel = d->max_push_vel_xy;
     p.sdf_nx = d->sdf_nx; p.sdf_ny = d->sdf_ny; p.sdf_cell = d->sdf_cell;
     if (!d->h_sdf || !d->h_env_origins || !d->h_agent_origins || !d->h_base_init_state) return fail(MQE_ERR_INVALID, "descriptor host arrays missing");
     if (P && !d->h_npc_init_state) return fail(MQE_ERR_INVALID, "h_npc_init_state missing");
@@ -172,6 +173,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     CK(dupload(s, &p.agent_origins, d->h_agent_origins, (size_t)M * 3));
     CK(dupload(s, &p.base_init, d->h_base_init_state, (size_t)M * 13));
     if (P) CK(dupload(s, &p.npc_init, d->h_npc_init_state, (size_t)N * P * 13));
+    if (d->h_env_friction) CK(dupload(s, &p.mu_env, d->h_env_friction, (size_t)N));
     {
         std::vector<float> nd(D > 0 ? D : 1, 0.f);
         if (D && d->h_npc_dof_default) memcpy(nd.data(), d->h_npc_dof_default, D * sizeof(float));

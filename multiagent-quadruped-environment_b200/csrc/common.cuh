@@ -34,6 +34,8 @@ struct DevParams {
     float bpos_x[2], bpos_y[2], npos_x[2], npos_y[2], nrpy_r[2], nrpy_p[2], nrpy_y[2];
     float npc_mass, npc_inertia, npc_radius, npc_halflen;
     float sheep_scale, sheep_rand, gate_x;
+    int push_interval; float max_push_vel;     // domain_rand.push_robots
+    const float *mu_env;                       // [N] per-env friction (domain_rand.randomize_friction) or nullptr
     float geom[16];               // MQE_NPC_SEESAW geometry (MqeSimDesc.npc_geom)
     unsigned long long seed;
     int sdf_nx, sdf_ny;
@@ -215,7 +217,7 @@ __device__ __forceinline__ float rng_normal(unsigned long long seed, uint32_t en
     float u2 = rng_uniform(seed, env, counter, stream, 2 * idx + 1);
     return sqrtf(-2.f * logf(u1)) * cosf(6.28318530717958647692f * u2);
 }
-enum { RNG_DOF = 0, RNG_BASE_POS = 1, RNG_BASE_VEL = 2, RNG_NPC_POS = 3, RNG_NPC_RPY = 4, RNG_SHEEP = 5 };
+enum { RNG_DOF = 0, RNG_BASE_POS = 1, RNG_BASE_VEL = 2, RNG_NPC_POS = 3, RNG_NPC_RPY = 4, RNG_SHEEP = 5, RNG_PUSH = 6 };
 
 // ---------------------------------------------------------------------------------------------- static world
 struct SdfSample { float sdf, gx, gy; };

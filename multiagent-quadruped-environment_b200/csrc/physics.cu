@@ -501,6 +501,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         fixb = mk(r[0], r[1], r[2]);
         if (seesaw && is_npc) { const float *d = p.dof + ((size_t)env * (12 * A + p.D) + 12 * A) * 2; q[0] = d[0]; qd[0] = d[1]; }
     }
+    const float mu_e = (p.mu_env && env < p.N) ? p.mu_env[env] : p.mu;    // domain_rand.randomize_friction: one coefficient per env
     int stat_local = 0, stat_lim = 0, stat_pair = 0, stat_rows = 0;
 
     PHASE_MARK(6);
@@ -1276,7 +1277,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     }
                     float urel = (r4.w + pl) + pb;            // bias + J w
                     float lam_old = r5.x, lam = lam_old - urel * r4.z;
-                    const float lo = kind == 0 ? 0.f : -p.mu * lam_n, hi = kind == 0 ? 3.0e38f : p.mu * lam_n;
+                    const float lo = kind == 0 ? 0.f : -mu_e * lam_n, hi = kind == 0 ? 3.0e38f : mu_e * lam_n;
                     lam = fminf(fmaxf(lam, lo), hi);
                     lam_n = kind == 0 ? lam : lam_n;
                     float dl = lam - lam_old;
@@ -1317,7 +1318,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         const float urel = tl.y + (__shfl_sync(env_mask, jw, srcA) + __shfl_sync(env_mask, jw, srcB));
                         const float lam_old = tl.z;
                         float lam = lam_old - urel * tl.x;
-                        const float lo = kind == 0 ? 0.f : -p.mu * lam_np, hi = kind == 0 ? 3.0e38f : p.mu * lam_np;
+                        const float lo = kind == 0 ? 0.f : -mu_e * lam_np, hi = kind == 0 ? 3.0e38f : mu_e * lam_np;
                         lam = fminf(fmaxf(lam, lo), hi);
                         lam_np = kind == 0 ? lam : lam_np;
                         const float dl = lam - lam_old;

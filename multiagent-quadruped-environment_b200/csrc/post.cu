@@ -166,6 +166,13 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
         p.base_ang_vel[m * 3] = av.x; p.base_ang_vel[m * 3 + 1] = av.y; p.base_ang_vel[m * 3 + 2] = av.z;
         p.proj_grav[m * 3] = pg.x; p.proj_grav[m * 3 + 1] = pg.y; p.proj_grav[m * 3 + 2] = pg.z;
         dev_gait_clock(p, m, dt_policy);
+        // _push_robots (go1.py:237-238, legged_robot.py:472-477): common_step_counter % push_interval == 0 -> every robot's base
+        // velocity x, y is redrawn; it takes effect in the next physics step (the derived base quantities above are pre-push)
+        if (p.push_interval > 0 && ((step_count + 1u) % (unsigned)p.push_interval) == 0u) {
+            float *rw = p.root + ((size_t)e * G + a) * 13;
+            rw[7] = (2.f * rng_uniform(p.seed, (uint32_t)(p.env_off + e), step_count, RNG_PUSH, 2 * a) - 1.f) * p.max_push_vel;
+            rw[8] = (2.f * rng_uniform(p.seed, (uint32_t)(p.env_off + e), step_count, RNG_PUSH, 2 * a + 1) - 1.f) * p.max_push_vel;
+        }
         int f = 0;
         const float *cf = p.contact + ((size_t)e * p.NB + a * MQE_NUM_BODIES) * 3;          // body 0 = base
         if (sqrtf(cf[0] * cf[0] + cf[1] * cf[1] + cf[2] * cf[2]) > 1.f) f |= 16;

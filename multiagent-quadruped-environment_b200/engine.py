@@ -16,7 +16,7 @@ from .model import MAX_CAPS, MAX_PROBES, RobotModelC  # noqa: F401
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libmqe_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 LOC_OBS = 70
 OBS_FLOATS = 71
 
@@ -91,12 +91,12 @@ class SimDescC(ctypes.Structure):
         ("npc_mass", ctypes.c_float), ("npc_inertia", ctypes.c_float), ("npc_radius", ctypes.c_float),
         ("npc_halflen", ctypes.c_float),
         ("sheep_scale", ctypes.c_float), ("sheep_randomness", ctypes.c_float),
-        ("gate_x", ctypes.c_float), ("reserved2", ctypes.c_float),
+        ("gate_x", ctypes.c_float), ("max_push_vel_xy", ctypes.c_float),
         ("npc_geom", ctypes.c_float * 16),
         ("seed", ctypes.c_uint64),
-        ("sdf_nx", ctypes.c_int32), ("sdf_ny", ctypes.c_int32), ("sdf_cell", ctypes.c_float), ("reserved3", ctypes.c_float),
+        ("sdf_nx", ctypes.c_int32), ("sdf_ny", ctypes.c_int32), ("sdf_cell", ctypes.c_float), ("push_interval", ctypes.c_int32),
         ("h_sdf", _fp), ("h_env_origins", _fp), ("h_agent_origins", _fp), ("h_base_init_state", _fp),
-        ("h_npc_init_state", _fp), ("h_npc_dof_default", _fp),
+        ("h_npc_init_state", _fp), ("h_npc_dof_default", _fp), ("h_env_friction", _fp),
         ("model", RobotModelC),
         ("weights", WeightsC),
     ]

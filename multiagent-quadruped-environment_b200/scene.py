@@ -246,6 +246,16 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
         kw = cfg.terrain.BarrierTrack_kwargs
         d.gate_x = float(kw["init"]["block_length"] + kw["plane"]["block_length"])   # go1_football_defender.py:61-63
     d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    # domain randomisation switches of the reference that are off in its task configs
+    if getattr(dr, "push_robots", False):                                      # legged_robot.py:1024, go1.py:237-238
+        d.push_interval = int(np.ceil(dr.push_interval_s / dt))
+        d.max_push_vel_xy = float(dr.max_push_vel_xy)
+    env_friction = None
+    if getattr(dr, "randomize_friction", False):                               # legged_robot.py:283-294: 64 buckets over friction_range,
+        frng = np.random.Generator(np.random.Philox(key=(int(seed) & 0xFFFFFFFF) * 7919 + 13))   # one bucket per env (own generator: shards agree)
+        buckets = frng.uniform(dr.friction_range[0], dr.friction_range[1], size=64)
+        coeff = buckets[frng.integers(0, 64, size=N_global)]
+        env_friction = np.ascontiguousarray(0.5 * (coeff + float(cfg.terrain.static_friction)), dtype=np.float32)[start:stop].copy()
 
     sdf = np.ascontiguousarray(sdf, dtype=np.float32)
     d.sdf_nx, d.sdf_ny, d.sdf_cell = sdf.shape[0], sdf.shape[1], cell
@@ -256,6 +266,9 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     bi_engine[:, 3:7] /= np.linalg.norm(bi_engine[:, 3:7], axis=1, keepdims=True)   # gives rot = [0, 0, -1, 1]); `base_init_state` stays raw
     ni = np.ascontiguousarray(npc_init[start * P:stop * P], dtype=np.float32) if P else np.zeros((1, 13), dtype=np.float32)
     keep += [sdf, eo, ao, bi, bi_engine, ni, npc_dof_default]
+    if env_friction is not None:
+        keep.append(env_friction)
+        d.h_env_friction = E.as_fp(env_friction)
     d.h_sdf, d.h_env_origins, d.h_agent_origins = E.as_fp(sdf), E.as_fp(eo), E.as_fp(ao)
     d.h_base_init_state, d.h_npc_init_state, d.h_npc_dof_default = E.as_fp(bi_engine), E.as_fp(ni), E.as_fp(npc_dof_default)
     d.model = model.to_c()

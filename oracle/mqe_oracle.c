@@ -126,7 +126,7 @@ static inline real rng_normal(uint64_t seed, uint32_t env, uint32_t counter, uin
     real u2 = rng_uniform(seed, env, counter, stream, 2 * idx + 1);
     return sqrt(-2 * log(u1)) * cos(2 * PI_R * u2);
 }
-enum { RNG_DOF = 0, RNG_BASE_POS = 1, RNG_BASE_VEL = 2, RNG_NPC_POS = 3, RNG_NPC_RPY = 4, RNG_SHEEP = 5 };
+enum { RNG_DOF = 0, RNG_BASE_POS = 1, RNG_BASE_VEL = 2, RNG_NPC_POS = 3, RNG_NPC_RPY = 4, RNG_SHEEP = 5, RNG_PUSH = 6 };
 
 /* ------------------------------------------------------------------------------------------------ spatial algebra
  * Everything of one robot is expressed in ONE frame: world axes, origin O = current base origin taken as an
@@ -396,6 +396,7 @@ typedef struct {
     real *commands;                         /* [M][3]                           */
     real *last_dof_vel, *last_root_vel;
     real *sheep_stats;                      /* [N][3]                           */
+    float *mu_env;                          /* [N] per-env friction or NULL (domain_rand.randomize_friction) */
     int64_t *ep_len;
     uint8_t *reset_buf, *timeout_buf, *collide_buf, *r_term, *p_term, *zl_term, *zh_term;
     uint32_t *episode;                      /* reset counter per env (RNG key)  */
@@ -430,6 +431,7 @@ Oracle *orc_create(const MqeSimDesc *desc) {
     o->base_init = dupr(desc->h_base_init_state, (size_t)M * 13);
     o->npc_init = dupr(desc->h_npc_init_state, (size_t)N * P * 13);
     o->npc_dof_default = dupr(desc->h_npc_dof_default, (size_t)(o->D ? o->D : 1));
+    o->mu_env = desc->h_env_friction ? dupf(desc->h_env_friction, (size_t)N) : NULL;
     /* private copies of the weights */
     const float **src = (const float **)&desc->weights;
     const size_t sz[20] = {256 * 2100, 256, 128 * 256, 128, 2 * 128, 2, 512 * 2102, 512, 256 * 512, 256,
@@ -476,7 +478,7 @@ Oracle *orc_create(const MqeSimDesc *desc) {
 
 void orc_destroy(Oracle *o) {
     if (!o) return;
-    free(o->sdf); free(o->env_origins); free(o->agent_origins); free(o->base_init); free(o->npc_init); free(o->npc_dof_default);
+    free(o->sdf); free(o->env_origins); free(o->agent_origins); free(o->base_init); free(o->npc_init); free(o->npc_dof_default); free(o->mu_env);
     for (int i = 0; i < 20; i++) free(o->wbuf[i]);
     free(o->root); free(o->dof); free(o->contact); free(o->torques); free(o->actions); free(o->last_actions);
     free(o->loc_last); free(o->loc_last2); free(o->loc_obs); free(o->hist); free(o->err1); free(o->err2); free(o->vel1); free(o->vel2);
@@ -1013,7 +1015,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
 
     /* 3. projected Gauss-Seidel sweeps */
     for (int it = 0; it < d->solver_iters; it++)
-        for (int i = 0; i < nr; i++) solve_row(&rows[i], rows, &es, d->friction);
+        for (int i = 0; i < nr; i++) solve_row(&rows[i], rows, &es, o->mu_env ? (real)o->mu_env[e] : (real)d->friction);
 
     /* 4. contact force report (impulse / dt, world frame) */
     real *cf = o->contact + (size_t)e * o->NB * 3;
@@ -1325,6 +1327,12 @@ void orc_post_physics(Oracle *o) {
             quat_rotate_inverse(o->base_ang_vel + m * 3, rs + 3, rs + 10);
             quat_rotate_inverse(o->proj_grav + m * 3, rs + 3, grav);
             gait_clock(o, m, dt_policy);
+            /* _push_robots (go1.py:237-238, legged_robot.py:472-477) */
+            if (d->push_interval > 0 && ((o->step_count + 1u) % (uint32_t)d->push_interval) == 0u) {
+                real *rw = o->root + ((size_t)e * G + a) * 13;
+                for (int k = 0; k < 2; k++)
+                    rw[7 + k] = (2 * (real)rng_uniform(d->seed, (uint32_t)(d->env_id_offset + e), o->step_count, RNG_PUSH, 2 * a + k) - 1) * d->max_push_vel_xy;
+            }
             /* check_termination: legged_robot.py:159-169 + legged_robot_field.py:121-146 */
             const real *cf = o->contact + ((size_t)e * o->NB + a * MQE_NUM_BODIES) * 3; /* base = body 0 */
             if (sqrt(v3dot(cf, cf)) > 1) collide = 1;

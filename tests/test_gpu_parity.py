@@ -431,3 +431,24 @@ def test_fused_wrapper_gather_matches_torch_wrapper(task, monkeypatch):
     ef.step(a.clone())
     assert float(ef.reward_buffer["step count"]) == 1
     ef.close(); et.close()
+
+
+@pytest.mark.gpu
+def test_domain_rand_push_and_friction_parity():
+    """push_robots + randomize_friction switched on: kernels against the oracle over the first pushes."""
+    cfg = C.Go1GateCfg(); cfg.env.num_envs = 16
+    cfg.domain_rand.push_robots = True; cfg.domain_rand.push_interval_s = 0.06; cfg.domain_rand.max_push_vel_xy = 0.8
+    cfg.domain_rand.randomize_friction = True; cfg.domain_rand.friction_range = [0.05, 1.5]
+    np.random.seed(0)
+    sc = S.build_scene(cfg, seed=0, policy_mode=E.POLICY_FP32, wrapper_action_scale=(2.0, 0.5, 0.5))
+    eng, orc = E.Engine(sc.desc, device=0, keepalive=sc), oracle.Oracle(sc, "f32")
+    eng.reset(); orc.reset()
+    for s in range(7):
+        a = actions_for(sc, s)
+        eng.step(dev(a).data_ptr()); orc.step(a)
+        g, r = get(eng, E.BUF_ROOT_STATES).reshape(16, 2, 13), orc.root_states()
+        if (s + 1) % 3 == 0:                                     # push step: the redrawn velocities are the same draws on both sides
+            assert np.allclose(g[..., 7:9], r[..., 7:9], atol=1e-6) and np.all(np.abs(g[..., 7:9]) <= 0.8 + 1e-6)
+        assert np.allclose(g[..., :7], r[..., :7], atol=2e-4), (s, np.abs(g[..., :7] - r[..., :7]).max())
+        assert np.allclose(g[..., 7:], r[..., 7:], atol=5e-3), (s, np.abs(g[..., 7:] - r[..., 7:]).max())
+    eng.close(); orc.close()

@@ -199,3 +199,37 @@ def test_tug_disc_slides_along_y_only_when_pushed():
     assert np.all(y[-1] < -0.2), y[-1]                            # pushed towards -y
     assert vmax <= 1.0 + 1e-9
     assert np.allclose(o.root_states()[:, 2], npc0)               # fixed base link
+
+
+def test_push_robots_and_randomised_friction():
+    """domain_rand.push_robots / randomize_friction (off in the reference's task configs; legged_robot.py:283-294, 472-477, go1.py:237-238):
+    the base velocity x, y of every robot is redrawn within +-max_push_vel_xy exactly when common_step_counter % push_interval == 0, and
+    tangential contact forces stay inside the per-env friction cone |f_t| <= mu_env f_n."""
+    cfg = C.Go1GateCfg(); cfg.env.num_envs = 6
+    cfg.domain_rand.push_robots = True
+    cfg.domain_rand.push_interval_s = 0.2                        # every 10 policy steps
+    cfg.domain_rand.max_push_vel_xy = 0.7
+    cfg.domain_rand.randomize_friction = True
+    cfg.domain_rand.friction_range = [0.1, 0.4]
+    np.random.seed(0)
+    sc = S.build_scene(cfg, seed=0)
+    assert sc.desc.push_interval == 10 and bool(sc.desc.h_env_friction)
+    mu = np.ctypeslib.as_array(sc.desc.h_env_friction, shape=(6,)).copy()
+    assert np.all(mu >= 0.5 * (0.1 + 1.0) - 1e-6) and np.all(mu <= 0.5 * (0.4 + 1.0) + 1e-6) and len(np.unique(mu)) > 1
+    o = oracle.Oracle(sc, "f64")
+    o.reset()
+    act = np.zeros((6, 2, 3), dtype=np.float32)
+    act[..., 1] = 1.0                                             # sideways command: feet push tangentially
+    prev = o.root_states()[:, :2, 7:9].copy()
+    for s in range(1, 31):
+        o.step(act)
+        v = o.root_states()[:, :2, 7:9]
+        if s % 10 == 0:
+            assert np.all(np.abs(v) <= 0.7 + 1e-9) and np.abs(v - prev).max() > 0.05, s    # a fresh draw, not the integrated velocity
+        prev = v.copy()
+        if s > 12:                                                # later the pushed robots reach walls / each other: normals are no longer +z
+            continue
+        cf = o.get(E.BUF_CONTACT_FORCES).reshape(6, -1, 3)[:, :34]
+        ft, fn = np.linalg.norm(cf[..., :2], axis=-1), cf[..., 2]
+        # two-direction pyramid: |f_t| <= sqrt(2) mu f_n per contact, summed over the probes of a body
+        assert np.all(ft <= np.sqrt(2.0) * mu[:, None] * np.maximum(fn, 0) * (1 + 1e-4) + 1e-4), s
