@@ -6,7 +6,9 @@ from mqe_b200 import engine as E, scene as S
 from mqe_b200.envs import configs as C
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 for task, fn, n in (("go1gate", C.Go1GateCfg, 4096), ("go1sheep-hard", C.NineSheepCfg, 2048), ("go1football-defender", C.Go1FootballDefenderCfg, 2048),
-                    ("go1seesaw", C.Go1SeesawCfg, 2048), ("go1football-2vs2", C.Go1Football2vs2Cfg, 1024)):
+                    ("go1seesaw", C.Go1SeesawCfg, 2048), ("go1football-2vs2", C.Go1Football2vs2Cfg, 1024), ("go1pushbox", C.Go1PushboxCfg, 1024),
+                    ("go1revolvingdoor", C.Go1RotationCfg, 1024), ("go1tug", C.Go1TugCfg, 1024), ("go1wrestling", C.Go1WrestlingCfg, 1024),
+                    ("go1bridge", C.Go1BridgeCfg, 1024)):
     cfg = fn(); cfg.env.num_envs = n
     np.random.seed(0)
     sc = S.build_scene(cfg, seed=0, policy_mode=E.POLICY_BF16X3, wrapper_action_scale=(2.0, 0.5, 0.5))
