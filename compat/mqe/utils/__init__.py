@@ -1,0 +1,3 @@
+"""mqe/utils/__init__.py:31 (the names callers use)"""
+from mqe_b200.envs.configs import class_to_dict  # noqa: F401
+from mqe_b200.envs.utils import get_args, make_env, set_seed  # noqa: F401
