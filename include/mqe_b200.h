@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MQE_ABI_VERSION 2
+#define MQE_ABI_VERSION 3
 #define MQE_MAX_PROBES 32
 #define MQE_MAX_CAPS 20
 #define MQE_NUM_DOF 12
@@ -128,6 +128,8 @@ typedef struct {
     const float *h_base_init_state;             /* [N*A][13]                                               */
     const float *h_npc_init_state;              /* [N*P][13] or NULL                                       */
     const float *h_npc_dof_default;             /* [D] or NULL                                             */
+    const float *h_base_added_mass;             /* [N*A] mass added to each robot's base link (domain_rand.randomize_base_mass,
+                                                   legged_robot.py:332-335: props[0].mass += U(added_mass_range)) or NULL */
     const float *h_env_friction;                /* [N] contact friction per env (domain_rand.randomize_friction, legged_robot.py:283-294,
                                                    already combined with the terrain's) or NULL: `friction` everywhere */
     MqeRobotModel model;

@@ -174,6 +174,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     CK(dupload(s, &p.base_init, d->h_base_init_state, (size_t)M * 13));
     if (P) CK(dupload(s, &p.npc_init, d->h_npc_init_state, (size_t)N * P * 13));
     if (d->h_env_friction) CK(dupload(s, &p.mu_env, d->h_env_friction, (size_t)N));
+    if (d->h_base_added_mass) CK(dupload(s, &p.base_mass_add, d->h_base_added_mass, (size_t)M));
     {
         std::vector<float> nd(D > 0 ? D : 1, 0.f);
         if (D && d->h_npc_dof_default) memcpy(nd.data(), d->h_npc_dof_default, D * sizeof(float));

@@ -35,6 +35,7 @@ struct DevParams {
     float npc_mass, npc_inertia, npc_radius, npc_halflen;
     float sheep_scale, sheep_rand, gate_x;
     int push_interval; float max_push_vel;     // domain_rand.push_robots
+    const float *base_mass_add;                // [N*A] mass added to the base link (domain_rand.randomize_base_mass) or nullptr
     const float *mu_env;                       // [N] per-env friction (domain_rand.randomize_friction) or nullptr
     float geom[16];               // MQE_NPC_SEESAW geometry (MqeSimDesc.npc_geom)
     unsigned long long seed;

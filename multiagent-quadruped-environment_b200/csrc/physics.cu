@@ -61,9 +61,9 @@ __host__ __device__ inline int physics_cta_header_floats() { return (int)(sizeof
 struct SV { V3 w, v; };
 struct RBI { float m; V3 h; float I[6]; };   // xx xy xz yy yz zz about O
 
-__device__ __forceinline__ RBI rbi_from_link(const float *in, const M3 &R, V3 p) {
+__device__ __forceinline__ RBI rbi_from_link(const float *in, const M3 &R, V3 p, float added_mass = 0.f) {
     RBI o;
-    float m = in[0];
+    float m = in[0] + added_mass;      // extra mass sits at the link's COM (PhysX changes the mass, not the inertia tensor)
     V3 c = mul(R, mk(in[1], in[2], in[3])) + p;
     V3 t0 = in[4] * R.c0 + in[5] * R.c1 + in[6] * R.c2;
     V3 t1 = in[5] * R.c0 + in[7] * R.c1 + in[8] * R.c2;
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             S1.w = a1; S1.v = cross(p1, a1);
             S2.w = a2; S2.v = cross(p2, a2);
             S3.w = a2; S3.v = cross(p3, a2);
-            RBI I0 = rbi_from_link(md->base_inertial, Rb, mk(0, 0, 0));
+            RBI I0 = rbi_from_link(md->base_inertial, Rb, mk(0, 0, 0), (p.base_mass_add && active) ? p.base_mass_add[m_idx] : 0.f);
             RBI I1 = rbi_from_link(md->leg_inertial[leg][0], R1, p1);
             RBI I2 = rbi_from_link(md->leg_inertial[leg][1], R2, p2);
             RBI I3 = rbi_from_link(md->leg_inertial[leg][2], R3, p3);

@@ -250,6 +250,11 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     if getattr(dr, "push_robots", False):                                      # legged_robot.py:1024, go1.py:237-238
         d.push_interval = int(np.ceil(dr.push_interval_s / dt))
         d.max_push_vel_xy = float(dr.max_push_vel_xy)
+    base_added_mass = None
+    if getattr(dr, "randomize_base_mass", False):                              # legged_robot.py:332-335: props[0].mass += U(added_mass_range)
+        mrng = np.random.Generator(np.random.Philox(key=(int(seed) & 0xFFFFFFFF) * 7919 + 29))
+        base_added_mass = np.ascontiguousarray(mrng.uniform(dr.added_mass_range[0], dr.added_mass_range[1], size=(N_global, A)),
+                                               dtype=np.float32)[start:stop].reshape(-1).copy()
     env_friction = None
     if getattr(dr, "randomize_friction", False):                               # legged_robot.py:283-294: 64 buckets over friction_range,
         frng = np.random.Generator(np.random.Philox(key=(int(seed) & 0xFFFFFFFF) * 7919 + 13))   # one bucket per env (own generator: shards agree)
@@ -266,6 +271,9 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     bi_engine[:, 3:7] /= np.linalg.norm(bi_engine[:, 3:7], axis=1, keepdims=True)   # gives rot = [0, 0, -1, 1]); `base_init_state` stays raw
     ni = np.ascontiguousarray(npc_init[start * P:stop * P], dtype=np.float32) if P else np.zeros((1, 13), dtype=np.float32)
     keep += [sdf, eo, ao, bi, bi_engine, ni, npc_dof_default]
+    if base_added_mass is not None:
+        keep.append(base_added_mass)
+        d.h_base_added_mass = E.as_fp(base_added_mass)
     if env_friction is not None:
         keep.append(env_friction)
         d.h_env_friction = E.as_fp(env_friction)

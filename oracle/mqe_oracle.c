@@ -134,9 +134,11 @@ enum { RNG_DOF = 0, RNG_BASE_POS = 1, RNG_BASE_VEL = 2, RNG_NPC_POS = 3, RNG_NPC
 typedef struct { real w[3], v[3]; } sv;
 typedef struct { real m, h[3], I[6]; } rbi; /* mass, first moment m*c, rotational inertia about O: xx xy xz yy yz zz */
 
-static void rbi_from_link(rbi *o, const float *in10, const real *R, const real *p) {
-    /* in10: mass, com, I about com in link frame; R link->world, p link origin rel. O */
-    real m = in10[0], cl[3] = {in10[1], in10[2], in10[3]}, c[3];
+static void rbi_from_link_m(rbi *o, const float *in10, const real *R, const real *p, real added_mass);
+static void rbi_from_link(rbi *o, const float *in10, const real *R, const real *p) { rbi_from_link_m(o, in10, R, p, 0); }
+static void rbi_from_link_m(rbi *o, const float *in10, const real *R, const real *p, real added_mass) {
+    /* in10: mass, com, I about com in link frame; R link->world, p link origin rel. O; added_mass sits at the COM */
+    real m = in10[0] + added_mass, cl[3] = {in10[1], in10[2], in10[3]}, c[3];
     m3mulv(c, R, cl);
     v3add(c, c, p);
     real Il[9] = {in10[4], in10[5], in10[6], in10[5], in10[7], in10[8], in10[6], in10[8], in10[9]}, T[9], Iw[9], Rt[9];
@@ -199,11 +201,13 @@ typedef struct {
     real Minv[NV][NV];
 } RobotDyn;
 
-static void robot_kinematics(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q) {
+static void robot_kinematics_m(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q, real base_added_mass);
+static void robot_kinematics(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q) { robot_kinematics_m(d, md, quat, q, 0); }
+static void robot_kinematics_m(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q, real base_added_mass) {
     quat_to_mat(d->Rb, quat);
     memcpy(d->R[0], d->Rb, sizeof d->Rb);
     v3set(d->p[0], 0, 0, 0);
-    rbi_from_link(&d->Il[0], md->base_inertial, d->Rb, d->p[0]);
+    rbi_from_link_m(&d->Il[0], md->base_inertial, d->Rb, d->p[0], base_added_mass);
     for (int l = 0; l < 4; l++) {
         const real *Rp = d->Rb;
         const real *pp = d->p[0];
@@ -397,6 +401,7 @@ typedef struct {
     real *last_dof_vel, *last_root_vel;
     real *sheep_stats;                      /* [N][3]                           */
     float *mu_env;                          /* [N] per-env friction or NULL (domain_rand.randomize_friction) */
+    float *base_mass_add;                   /* [M] mass added to the base link or NULL (domain_rand.randomize_base_mass) */
     int64_t *ep_len;
     uint8_t *reset_buf, *timeout_buf, *collide_buf, *r_term, *p_term, *zl_term, *zh_term;
     uint32_t *episode;                      /* reset counter per env (RNG key)  */
@@ -432,6 +437,7 @@ Oracle *orc_create(const MqeSimDesc *desc) {
     o->npc_init = dupr(desc->h_npc_init_state, (size_t)N * P * 13);
     o->npc_dof_default = dupr(desc->h_npc_dof_default, (size_t)(o->D ? o->D : 1));
     o->mu_env = desc->h_env_friction ? dupf(desc->h_env_friction, (size_t)N) : NULL;
+    o->base_mass_add = desc->h_base_added_mass ? dupf(desc->h_base_added_mass, (size_t)M) : NULL;
     /* private copies of the weights */
     const float **src = (const float **)&desc->weights;
     const size_t sz[20] = {256 * 2100, 256, 128 * 256, 128, 2 * 128, 2, 512 * 2102, 512, 256 * 512, 256,
@@ -478,7 +484,7 @@ Oracle *orc_create(const MqeSimDesc *desc) {
 
 void orc_destroy(Oracle *o) {
     if (!o) return;
-    free(o->sdf); free(o->env_origins); free(o->agent_origins); free(o->base_init); free(o->npc_init); free(o->npc_dof_default); free(o->mu_env);
+    free(o->sdf); free(o->env_origins); free(o->agent_origins); free(o->base_init); free(o->npc_init); free(o->npc_dof_default); free(o->mu_env); free(o->base_mass_add);
     for (int i = 0; i < 20; i++) free(o->wbuf[i]);
     free(o->root); free(o->dof); free(o->contact); free(o->torques); free(o->actions); free(o->last_actions);
     free(o->loc_last); free(o->loc_last2); free(o->loc_obs); free(o->hist); free(o->err1); free(o->err2); free(o->vel1); free(o->vel2);
@@ -808,7 +814,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         real v[NV], rhs[NV], acc[NV];
         for (int j = 0; j < 12; j++) { q[a][j] = dof[(12 * a + j) * 2]; v[6 + j] = dof[(12 * a + j) * 2 + 1]; }
         for (int i = 0; i < 3; i++) { v[i] = rs[10 + i]; v[3 + i] = rs[7 + i]; es.origin[a][i] = rs[i]; }
-        robot_kinematics(rd, md, rs + 3, q[a]);
+        robot_kinematics_m(rd, md, rs + 3, q[a], o->base_mass_add ? (real)o->base_mass_add[e * A + a] : 0);
         robot_dynamics(rd, v, d->gravity_z);
         if (spd_inverse(NV, &rd->M[0][0], &rd->Minv[0][0]) != 0) { fprintf(stderr, "oracle: mass matrix not SPD (env %d)\n", e); abort(); }
         for (int i = 0; i < NV; i++) rhs[i] = -rd->c[i];

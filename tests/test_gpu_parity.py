@@ -435,10 +435,11 @@ def test_fused_wrapper_gather_matches_torch_wrapper(task, monkeypatch):
 
 @pytest.mark.gpu
 def test_domain_rand_push_and_friction_parity():
-    """push_robots + randomize_friction switched on: kernels against the oracle over the first pushes."""
+    """push_robots + randomize_friction + randomize_base_mass switched on: kernels against the oracle over the first pushes."""
     cfg = C.Go1GateCfg(); cfg.env.num_envs = 16
     cfg.domain_rand.push_robots = True; cfg.domain_rand.push_interval_s = 0.06; cfg.domain_rand.max_push_vel_xy = 0.8
     cfg.domain_rand.randomize_friction = True; cfg.domain_rand.friction_range = [0.05, 1.5]
+    cfg.domain_rand.randomize_base_mass = True; cfg.domain_rand.added_mass_range = [-1.0, 3.0]
     np.random.seed(0)
     sc = S.build_scene(cfg, seed=0, policy_mode=E.POLICY_FP32, wrapper_action_scale=(2.0, 0.5, 0.5))
     eng, orc = E.Engine(sc.desc, device=0, keepalive=sc), oracle.Oracle(sc, "f32")

@@ -233,3 +233,25 @@ def test_push_robots_and_randomised_friction():
         ft, fn = np.linalg.norm(cf[..., :2], axis=-1), cf[..., 2]
         # two-direction pyramid: |f_t| <= sqrt(2) mu f_n per contact, summed over the probes of a body
         assert np.all(ft <= np.sqrt(2.0) * mu[:, None] * np.maximum(fn, 0) * (1 + 1e-4) + 1e-4), s
+
+
+def test_randomised_base_mass_carried_by_the_feet():
+    """domain_rand.randomize_base_mass (legged_robot.py:332-335): each robot's trunk gets U(added_mass_range) kg; standing, the feet
+    carry (m + added) g."""
+    cfg = C.Go1GateCfg(); cfg.env.num_envs = 3
+    cfg.domain_rand.randomize_base_mass = True
+    cfg.domain_rand.added_mass_range = [1.0, 3.0]
+    np.random.seed(0)
+    sc = S.build_scene(cfg, seed=0)
+    add = np.ctypeslib.as_array(sc.desc.h_base_added_mass, shape=(6,)).copy().reshape(3, 2)
+    assert np.all(add >= 1.0) and np.all(add <= 3.0) and len(np.unique(add)) == 6
+    o = oracle.Oracle(sc, "f64")
+    o.reset()
+    act = np.zeros((3, 2, 3), dtype=np.float32)
+    fz = []
+    for s in range(150):
+        o.step(act)
+        if s >= 100:
+            fz.append(o.get(E.BUF_CONTACT_FORCES).reshape(3, -1, 3)[:, :34, 2].reshape(3, 2, 17).sum(axis=2))
+    w = (sc.model.total_mass + add) * 9.81
+    assert np.all(np.abs(np.mean(fz, axis=0) - w) < 0.05 * w), (np.mean(fz, axis=0), w)
