@@ -453,3 +453,52 @@ def test_domain_rand_push_and_friction_parity():
         assert np.allclose(g[..., :7], r[..., :7], atol=2e-4), (s, np.abs(g[..., :7] - r[..., :7]).max())
         assert np.allclose(g[..., 7:], r[..., 7:], atol=5e-3), (s, np.abs(g[..., 7:] - r[..., 7:]).max())
     eng.close(); orc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 5, 131])
+def test_ragged_env_counts_match_oracle(n):
+    """Env counts that do not fill a warp of 4 envs, a CTA of 7 warps or a wave of 148 CTAs: the last warp / CTA is partly empty."""
+    sc, eng, orc = make_pair("go1gate", n)
+    eng.reset(); orc.reset()
+    for s in range(3):
+        a = actions_for(sc, s)
+        eng.step(dev(a).data_ptr()); orc.step(a)
+    g, r = get(eng, E.BUF_ROOT_STATES).reshape(n, 2, 13), orc.root_states()
+    assert np.allclose(g[..., :7], r[..., :7], atol=1e-4) and np.allclose(g[..., 7:], r[..., 7:], atol=2e-3)
+    assert np.array_equal(get(eng, E.BUF_RESET), orc.get(E.BUF_RESET)) and np.array_equal(get(eng, E.BUF_EPISODE_LENGTH), orc.get(E.BUF_EPISODE_LENGTH))
+    eng.close(); orc.close()
+
+
+@pytest.mark.gpu
+def test_error_paths_return_codes_not_crashes():
+    """The C ABI reports bad descriptors / arguments through MqeStatus + mqe_last_error (include/mqe_b200.h), it never throws."""
+    cfg = C.Go1GateCfg(); cfg.env.num_envs = 4
+    np.random.seed(0)
+    sc = S.build_scene(cfg, seed=0)
+    for field, bad, msg in (("num_agents", 5, "out of range"), ("num_envs", 0, "out of range"), ("abi_version", 99, "abi_version"), ("defender", 1, "defender")):
+        keep = getattr(sc.desc, field)
+        setattr(sc.desc, field, bad)
+        with pytest.raises(E.EngineError) as ei:
+            E.Engine(sc.desc, device=0, keepalive=sc)
+        assert msg in str(ei.value), (field, str(ei.value))
+        setattr(sc.desc, field, keep)
+    with pytest.raises(E.EngineError):
+        E.Engine(sc.desc, device=99, keepalive=sc)
+    eng = E.Engine(sc.desc, device=0, keepalive=sc)
+    lib = eng.lib
+    assert lib.mqe_sim_step(eng.h, None) < 0 and b"null" in lib.mqe_last_error()
+    assert lib.mqe_sim_substeps(eng.h, 0) < 0
+    assert lib.mqe_sim_get_buffer(eng.h, 999, None, None, None) < 0
+    assert lib.mqe_sim_get_buffer(eng.h, E.BUF_WRAP_OBS, None, None, None) < 0        # no task wrapper set yet
+    assert lib.mqe_sim_wrapper_reset(eng.h) < 0
+    with pytest.raises(E.EngineError):
+        eng.set_wrapper(E.WRAP_SHEEP, [1, 0, 0, 0, 0, 0])                              # no sheep in go1gate
+    with pytest.raises(E.EngineError):
+        eng.set_wrapper(77, [0])
+    buf = np.zeros(16, dtype=np.float32)
+    assert lib.mqe_sim_unpin_host(eng.h, buf.ctypes.data_as(__import__("ctypes").c_void_p)) < 0   # never pinned
+    eng.pin_host(buf); eng.pin_host(buf)                                               # idempotent
+    eng.reset(); eng.step(dev(actions_for(sc, 0)).data_ptr()); eng.synchronize()       # the handle is still healthy
+    assert np.isfinite(get(eng, E.BUF_ROOT_STATES)).all()
+    eng.close()
