@@ -47,6 +47,9 @@ struct MqeSim {
     cudaStream_t cap_stream = nullptr;
     bool use_graph = false;
     long long plain_steps = 0;
+    cudaStream_t aux_stream = nullptr;   // forked policy: adaptation branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fork_policy = false;
     WrapParams wrap = {};                // fused task-wrapper gather (mqe_sim_set_wrapper); kind 0 = off
     struct Pinned { char *ptr; size_t bytes; };
     std::vector<Pinned> pinned;          // host ranges registered with mqe_sim_pin_host: mqe_sim_step_host copies straight to / from them
@@ -99,6 +102,9 @@ int mqe_sim_destroy(MqeSim *s) {
     for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);
     for (auto &r : s->pinned) cudaHostUnregister(r.ptr);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+    if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     for (void *ptr : s->allocs) cudaFree(ptr);
     if (s->tcw.blob) cudaFree(s->tcw.blob);
     if (s->h_actions) cudaFreeHost(s->h_actions);
@@ -242,6 +248,12 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
         CK(cudaStreamSynchronize(s->stream));     // host staging vectors go out of scope
     }
     { const char *e = getenv("MQE_TC_TAIL"); s->tail_fp32 = e && e[0] == '0'; }
+    { const char *e = getenv("MQE_POLICY_FORK"); s->fork_policy = (p.policy_mode != MQE_POLICY_FP32) && !s->tail_fp32 && !(e && e[0] == '0'); }
+    if (s->fork_policy) {
+        CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    }
     { const char *e = getenv("MQE_GRAPH"); s->use_graph = (p.policy_mode != MQE_POLICY_FP32) && !(e && e[0] == '0'); }
     if (p.policy_mode != MQE_POLICY_FP32) {
         int rc = mqe_policy_tc_prepare(&w, M, &s->tcw, s->stream);
@@ -433,6 +445,13 @@ int mqe_sim_reset(MqeSim *s) {
 static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, const unsigned short *lo, int head, int rows, float *latent, float *act) {
     PolicyScratch ps = s->ps;
     ps.latent = latent; ps.act = act;
+    if (s->fork_policy) {
+        int nf = 0;
+        CK(mqe_launch_policy_tc_forked(s->tcw, s->pw, ps, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->p.ctr, s->stream, s->aux_stream,
+                                       s->ev_fork, s->ev_join, &nf));
+        s->launches += nf;
+        return MQE_OK;
+    }
     if (s->p.policy_mode == MQE_POLICY_FP32)
         CK(mqe_launch_policy_l0_fp32(s->pw, ps, ring, head, rows, s->stream));
     else

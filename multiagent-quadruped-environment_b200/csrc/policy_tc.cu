@@ -74,14 +74,14 @@ __global__ void __launch_bounds__(320, 1)
 k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo,
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
                const float *__restrict__ b0cat, float *__restrict__ Z, unsigned short *__restrict__ a0_hi,
-               unsigned short *__restrict__ a0_lo, int M, int head, int passes, const int *__restrict__ ctr) {
+               unsigned short *__restrict__ a0_lo, int M, int head, int passes, const int *__restrict__ ctr, int ntile0) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t *empty = full + TC_STAGES;
     uint64_t *accum = empty + TC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntile = blockIdx.x, mtile = blockIdx.y;
+    const int ntile = blockIdx.x + ntile0, mtile = blockIdx.y;     // ntile0: first 128-column tile of this launch (forked policy)
     pdl_launch_dependents();
 
     if (threadIdx.x == 0) {
@@ -530,7 +530,40 @@ extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const f
     dim3 grid(6, (rows + 127) / 128);
     return launch_heavy(k_policy_l0_tc, grid, dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                       (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
-                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr);
+                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0);
+}
+
+// Forked policy: the adaptation branch (layer-0 columns 0..255 -> adapt.2 -> adapt.4 = latent) runs on a second stream next to the body's
+// layer-0 columns (256..767) and joins before body.0's latent / ELU / plane stage.  Same kernels, same arithmetic; the 64-CTA adapt
+// layer then fills SMs that the 2.6-wave layer-0 grid leaves idle in its last wave instead of running after it.
+extern "C" cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const unsigned short *hist_hi,
+                                                   const unsigned short *hist_lo, int head, int M, int passes, const int *ctr, cudaStream_t st, cudaStream_t aux,
+                                                   cudaEvent_t ev_fork, cudaEvent_t ev_join, int *launches) {
+    const int mt = (M + 127) / 128, mpad = mt * 128;
+    auto H = [&](int i) { return (const unsigned short *)w.t_hi[i]; };
+    auto L = [&](int i) { return (const unsigned short *)w.t_lo[i]; };
+    auto PH = [&](int i) { return (unsigned short *)w.p_hi[i]; };
+    auto PL = [&](int i) { return (unsigned short *)w.p_lo[i]; };
+    float *const nof = nullptr;
+    unsigned short *const nou = nullptr;
+    const HeadArgs none = {};
+    const HeadArgs h1 = {pw.aw2, pw.ab2, s.latent, s.Z, pw.wlat, PH(2), PL(2)};
+    const HeadArgs h2 = {pw.bw3, pw.bb3, s.act, nullptr, nullptr, nullptr, nullptr};
+    cudaError_t e;
+    if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(aux, ev_fork, 0)) != cudaSuccess) return e;
+    if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(2, mt), dim3(320), TC_SMEM_BYTES, aux, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128, 2, false>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), aux, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, nou, nou, 0, M, 1, passes, h1)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(ev_join, aux)) != cudaSuccess) return e;
+    if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(4, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
+    if ((e = launch_pdl_if(false, k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes, none)) != cudaSuccess) return e;
+    if ((e = launch_pdl(k_linear_tc<128, 12, false>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(3), PL(3), 256, H(3), L(3), pw.bb2, nof, 0, 128, nou, nou, 0, M, 1, passes, h2)) != cudaSuccess) return e;
+    *launches += 6;
+    return cudaGetLastError();
 }
 
 // layers 1.. on the tensor cores: operands are bf16 hi/lo planes end to end (needs layer 0 launched with planes_out = 1)
