@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MQE_ABI_VERSION 3
+#define MQE_ABI_VERSION 4
 #define MQE_MAX_PROBES 32
 #define MQE_MAX_CAPS 20
 #define MQE_NUM_DOF 12
@@ -121,6 +121,9 @@ typedef struct {
     float sdf_cell;
     int32_t push_interval;                      /* domain_rand.push_robots: every push_interval policy steps (ceil(push_interval_s / dt),
                                                    legged_robot.py:1024) every robot's base velocity x, y is redrawn in +-max_push_vel_xy; 0 = off */
+    int32_t control_type;                       /* cfg.control.control_type: 0 'C' actuator network (go1.py:335-352, every shipped task),
+                                                   1 'P' PD position targets, 2 'T' scaled torques (legged_robot.py:384-392; no hip scale there) */
+    float stiffness, damping;                   /* cfg.control.stiffness / damping ['joint'] for control_type 'P'                  */
     const float *h_sdf;                         /* [nx][ny] host, copied                                   */
     /* per-env constants, host, copied */
     const float *h_env_origins;                 /* [N][3]                                                  */

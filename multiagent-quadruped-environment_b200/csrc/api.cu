@@ -166,6 +166,8 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     p.npc_mass = d->npc_mass; p.npc_inertia = d->npc_inertia; p.npc_radius = d->npc_radius; p.npc_halflen = d->npc_halflen;
     p.sheep_scale = d->sheep_scale; p.sheep_rand = d->sheep_randomness; p.gate_x = d->gate_x;
     p.seed = d->seed;
+    if (d->control_type < 0 || d->control_type > 2) return fail(MQE_ERR_UNSUPPORTED, "control_type must be 0 (C), 1 (P) or 2 (T)");
+    p.control_type = d->control_type; p.kp = d->stiffness; p.kd = d->damping;
     p.push_interval = d->push_interval > 0 ? d->push_interval : 0; p.max_push_vel = d->max_push_vel_xy;
     p.sdf_nx = d->sdf_nx; p.sdf_ny = d->sdf_ny; p.sdf_cell = d->sdf_cell;
     if (!d->h_sdf || !d->h_env_origins || !d->h_agent_origins || !d->h_base_init_state) return fail(MQE_ERR_INVALID, "descriptor host arrays missing");

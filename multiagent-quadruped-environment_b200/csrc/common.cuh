@@ -34,6 +34,7 @@ struct DevParams {
     float bpos_x[2], bpos_y[2], npos_x[2], npos_y[2], nrpy_r[2], nrpy_p[2], nrpy_y[2];
     float npc_mass, npc_inertia, npc_radius, npc_halflen;
     float sheep_scale, sheep_rand, gate_x;
+    int control_type; float kp, kd;            // cfg.control: 0 actuator net, 1 PD position, 2 torque
     int push_interval; float max_push_vel;     // domain_rand.push_robots
     const float *base_mass_add;                // [N*A] mass added to the base link (domain_rand.randomize_base_mass) or nullptr
     const float *mu_env;                       // [N] per-env friction (domain_rand.randomize_friction) or nullptr

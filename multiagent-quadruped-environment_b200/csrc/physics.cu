@@ -514,7 +514,17 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         const bool last = (sub == nsub - 1);
         CTA_ALIGN(1);
         // ================================================================ P1: actuator network (go1.py:315-354, 369-380)
-        if (active && is_robot) {
+        if (active && is_robot && p.control_type != 0) {
+            // LeggedRobot._compute_torques (legged_robot.py:384-392): 'P' PD towards action * scale + default pose, 'T' scaled torques
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int j = 3 * leg + k;
+                const float a = act[k] * p.action_scale;
+                const float t = p.control_type == 1 ? p.kp * (a + md->q_default[j] - q[k]) - p.kd * qd[k] : a;
+                const float lim = md->tau_limit[j];
+                tau[k] = fminf(fmaxf(t, -lim), lim);
+            }
+        } else if (active && is_robot) {
             float x[3][6];
 #pragma unroll
             for (int k = 0; k < 3; k++) {

@@ -16,7 +16,7 @@ from .model import MAX_CAPS, MAX_PROBES, RobotModelC  # noqa: F401
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libmqe_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LOC_OBS = 70
 OBS_FLOATS = 71
 
@@ -95,6 +95,7 @@ class SimDescC(ctypes.Structure):
         ("npc_geom", ctypes.c_float * 16),
         ("seed", ctypes.c_uint64),
         ("sdf_nx", ctypes.c_int32), ("sdf_ny", ctypes.c_int32), ("sdf_cell", ctypes.c_float), ("push_interval", ctypes.c_int32),
+        ("control_type", ctypes.c_int32), ("stiffness", ctypes.c_float), ("damping", ctypes.c_float),
         ("h_sdf", _fp), ("h_env_origins", _fp), ("h_agent_origins", _fp), ("h_base_init_state", _fp),
         ("h_npc_init_state", _fp), ("h_npc_dof_default", _fp), ("h_base_added_mass", _fp), ("h_env_friction", _fp),
         ("model", RobotModelC),

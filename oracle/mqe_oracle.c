@@ -1078,6 +1078,14 @@ static void env_torques(Oracle *o, int e, real *tau) {
         int m = e * A + a;
         for (int j = 0; j < 12; j++) {
             real act = o->actions[m * 12 + j] * d->action_scale;
+            if (d->control_type != 0) {   /* LeggedRobot._compute_torques (legged_robot.py:384-392): 'P' / 'T', no hip scale, no histories */
+                real t = d->control_type == 1 ? d->stiffness * (act + d->model.q_default[j] - dof[(12 * a + j) * 2]) - d->damping * dof[(12 * a + j) * 2 + 1] : act;
+                real lim = d->model.tau_limit[j];
+                t = t > lim ? lim : (t < -lim ? -lim : t);
+                tau[12 * a + j] = t;
+                o->torques[m * 12 + j] = t;
+                continue;
+            }
             if (j % 3 == 0) act *= d->hip_scale;
             real target = act + d->model.q_default[j];
             real err = dof[(12 * a + j) * 2] - target, vel = dof[(12 * a + j) * 2 + 1];

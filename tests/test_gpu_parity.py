@@ -502,3 +502,23 @@ def test_error_paths_return_codes_not_crashes():
     eng.reset(); eng.step(dev(actions_for(sc, 0)).data_ptr()); eng.synchronize()       # the handle is still healthy
     assert np.isfinite(get(eng, E.BUF_ROOT_STATES)).all()
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ct", ["P", "T"])
+def test_pd_and_torque_control_parity(ct):
+    """cfg.control.control_type 'P' / 'T' (legged_robot.py:384-392) instead of the actuator network: kernels against the oracle."""
+    cfg = C.Go1GateCfg(); cfg.env.num_envs = 8
+    cfg.control.control_type = ct
+    cfg.control.stiffness = {"joint": 40.0}; cfg.control.damping = {"joint": 1.0}
+    np.random.seed(0)
+    sc = S.build_scene(cfg, seed=0, policy_mode=E.POLICY_FP32, wrapper_action_scale=(2.0, 0.5, 0.5))
+    eng, orc = E.Engine(sc.desc, device=0, keepalive=sc), oracle.Oracle(sc, "f32")
+    eng.reset(); orc.reset()
+    for s in range(4):
+        a = actions_for(sc, s)
+        eng.step(dev(a).data_ptr()); orc.step(a)
+        g, r = get(eng, E.BUF_ROOT_STATES).reshape(8, 2, 13), orc.root_states()
+        assert np.allclose(g[..., :7], r[..., :7], atol=2e-4), (s, np.abs(g[..., :7] - r[..., :7]).max())
+        assert np.allclose(get(eng, E.BUF_TORQUES).ravel(), orc.get(E.BUF_TORQUES).ravel(), atol=2e-2), s
+    eng.close(); orc.close()

@@ -255,3 +255,23 @@ def test_randomised_base_mass_carried_by_the_feet():
             fz.append(o.get(E.BUF_CONTACT_FORCES).reshape(3, -1, 3)[:, :34, 2].reshape(3, 2, 17).sum(axis=2))
     w = (sc.model.total_mass + add) * 9.81
     assert np.all(np.abs(np.mean(fz, axis=0) - w) < 0.05 * w), (np.mean(fz, axis=0), w)
+
+
+def test_pd_position_control_holds_the_default_pose():
+    """cfg.control.control_type = 'P' (legged_robot.py:384-392): zero actions = PD towards the default pose; the robot keeps standing."""
+    cfg = C.Go1GateCfg(); cfg.env.num_envs = 2
+    cfg.control.control_type = "P"
+    cfg.control.stiffness = {"joint": 40.0}; cfg.control.damping = {"joint": 1.0}
+    np.random.seed(0)
+    sc = S.build_scene(cfg, seed=0)
+    assert sc.desc.control_type == 1
+    o = oracle.Oracle(sc, "f64")
+    o.reset()
+    # the walk policy's outputs drive the PD targets; hold them at zero by zeroing the action buffer every step
+    act = np.zeros((2, 2, 3), dtype=np.float32)
+    for s in range(60):
+        o.step(act)
+    z = o.root_states()[:, :2, 2]
+    assert np.all(z > 0.2) and o.get(E.BUF_RESET).sum() == 0, z
+    tq = o.get(E.BUF_TORQUES)
+    assert np.all(np.abs(tq) <= 25.0 + 1e-6)
