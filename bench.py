@@ -170,6 +170,8 @@ def run_gpu(args):
     K, W = args.steps, max(args.warmup, 3)
     n_act = min(K + W, 64)                                        # distinct action tensors, cycled
     h_actions = synth_actions(n_local, a_ctrl, n_act, env_offset=start)
+    if args.actions == "forward":
+        h_actions[:] = np.asarray([0.5, 0.0, 0.0], dtype=np.float32)
     d_actions = torch.as_tensor(h_actions, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     obs_rows = eng.tensor(E.BUF_OBS)
@@ -288,7 +290,7 @@ def run_gpu(args):
         "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.task}, {A} Go1 agents, num_envs={args.num_envs} per GPU ({n_global} global), decimation {base.decimation}, "
-                               f"dt {cfg.sim.dt}, PGS sweeps {eng.desc.solver_iters}", "policy_arithmetic": args.policy,
+                               f"dt {cfg.sim.dt}, PGS sweeps {eng.desc.solver_iters}", "policy_arithmetic": args.policy, "actions": "U(-1,1) per step" if args.actions == "uniform" else "fixed (0.5, 0, 0)",
                    "l2": "flushed between timed steps (256 MiB memset, untimed; per-step CUDA events summed)",
                    "sharding": "contiguous env blocks per rank; NCCL all_gather of obs rows + done per step" if world > 1 else "single GPU",
                    "env_steps_per_s": value / A, "physics_substeps_per_s": value / A * base.decimation},
@@ -316,6 +318,8 @@ def main():
     ap.add_argument("--num-envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--policy", type=str, default=os.environ.get("MQE_BENCH_POLICY", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--actions", type=str, default="uniform", choices=["uniform", "forward"],
+                    help="SURVEY 8(d): U(-1,1) per step (default), or the fixed pattern a = (0.5, 0, 0): every robot walks straight into the gate (contact-heavy)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
