@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MQE_ABI_VERSION 4
+#define MQE_ABI_VERSION 5
 #define MQE_MAX_PROBES 32
 #define MQE_MAX_CAPS 20
 #define MQE_NUM_DOF 12
@@ -124,6 +124,9 @@ typedef struct {
     int32_t control_type;                       /* cfg.control.control_type: 0 'C' actuator network (go1.py:335-352, every shipped task),
                                                    1 'P' PD position targets, 2 'T' scaled torques (legged_robot.py:384-392; no hip scale there) */
     float stiffness, damping;                   /* cfg.control.stiffness / damping ['joint'] for control_type 'P'                  */
+    int32_t lag_enabled;                        /* domain_rand.randomize_lag_timesteps (go1.py:337-339, 363): the actuator network's position
+                                                   target is the scaled action of `lag_timesteps` _compute_torques calls (substeps) ago */
+    int32_t lag_timesteps;
     const float *h_sdf;                         /* [nx][ny] host, copied                                   */
     /* per-env constants, host, copied */
     const float *h_env_origins;                 /* [N][3]                                                  */

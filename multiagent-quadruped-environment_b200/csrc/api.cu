@@ -275,10 +275,15 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     CK(dalloc(s, &p.reset_buf, (size_t)N)); CK(dalloc(s, &p.timeout_buf, (size_t)N)); CK(dalloc(s, &p.collide_buf, (size_t)N));
     CK(dalloc(s, &p.r_term, (size_t)N)); CK(dalloc(s, &p.p_term, (size_t)N)); CK(dalloc(s, &p.zl_term, (size_t)N)); CK(dalloc(s, &p.zh_term, (size_t)N));
     CK(dalloc(s, &p.episode, (size_t)N)); CK(dalloc(s, &p.hist_dirty, (size_t)N)); CK(dalloc(s, &p.stats, (size_t)8));
-    CK(dalloc(s, &p.ctr, (size_t)4));
+    CK(dalloc(s, &p.ctr, (size_t)8));
     CK(dalloc(s, &p.warp_trace, (size_t)((N + p.E - 1) / p.E) * MQE_TRACE_COLS));
     { const char *e = getenv("MQE_CTA_SYNC"); p.cta_sync = e ? atoi(e) : 1; }
     { const char *e = getenv("MQE_TRACE"); p.trace = (e && e[0] == '1') ? 1 : 0; }
+    if (d->lag_enabled) {
+        if (d->lag_timesteps < 0 || d->lag_timesteps > 63) return fail(MQE_ERR_INVALID, "lag_timesteps out of range (0..63)");
+        p.lag_n = d->lag_timesteps + 1;
+        CK(dalloc(s, &p.lag_ring, (size_t)M * p.lag_n * 12));
+    }
     CK(dalloc(s, &p.row_scratch, mqe_substeps_row_scratch_floats(N, A), false));
     CK(dalloc(s, &p.prow_scratch, mqe_substeps_prow_scratch_floats(N, s->maxpair), false));
     {

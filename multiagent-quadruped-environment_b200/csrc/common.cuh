@@ -34,6 +34,7 @@ struct DevParams {
     float bpos_x[2], bpos_y[2], npos_x[2], npos_y[2], nrpy_r[2], nrpy_p[2], nrpy_y[2];
     float npc_mass, npc_inertia, npc_radius, npc_halflen;
     float sheep_scale, sheep_rand, gate_x;
+    float *lag_ring; int lag_n;                // action lag (go1.py:337-339): [N*A][lag_n][12] scaled actions, lag_n = lag_timesteps + 1; nullptr = off
     int control_type; float kp, kd;            // cfg.control: 0 actuator net, 1 PD position, 2 torque
     int push_interval; float max_push_vel;     // domain_rand.push_robots
     const float *base_mass_add;                // [N*A] mass added to the base link (domain_rand.randomize_base_mass) or nullptr
@@ -63,7 +64,8 @@ struct DevParams {
     int cta_sync;                 // MQE_CTA_SYNC: 0 none, 1 per substep, 2 also per phase
     int trace;                    // MQE_TRACE=1: also accumulate per-phase cycles into the trace rows
     int *stats;                   // [8]
-    int *ctr;                     // device-side step counters: [0] ring slot that receives the next frame, [1] policy steps done
+    int *ctr;                     // device-side step counters ([3] _compute_torques calls so far, [4] CTAs of k_substeps finished: action lag);
+                                  // [0] ring slot that receives the next frame, [1] policy steps done
                                   // (sheep RNG key), [2] scratch (blocks of k_post_physics finished); let a captured CUDA graph of
                                   // the whole step be replayed with constant kernel arguments
     // history ring for the policy (policy.cu)

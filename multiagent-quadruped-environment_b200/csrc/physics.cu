@@ -502,6 +502,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         if (seesaw && is_npc) { const float *d = p.dof + ((size_t)env * (12 * A + p.D) + 12 * A) * 2; q[0] = d[0]; qd[0] = d[1]; }
     }
     const float mu_e = (p.mu_env && env < p.N) ? p.mu_env[env] : p.mu;    // domain_rand.randomize_friction: one coefficient per env
+    const int lag_c0 = p.lag_ring ? p.ctr[3] : 0;                          // _compute_torques calls before this launch
     int stat_local = 0, stat_lim = 0, stat_pair = 0, stat_rows = 0;
 
     PHASE_MARK(6);
@@ -531,6 +532,12 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 int j = 3 * leg + k;
                 float a = act[k] * p.action_scale;
                 if (k == 0) a *= p.hip_scale;
+                if (p.lag_ring) {      // lag_buffer = lag_buffer[1:] + [actions_scaled]; target = lag_buffer[0] (go1.py:337-339), as a ring
+                    float *ring = p.lag_ring + (size_t)m_idx * p.lag_n * 12 + j;
+                    const int c = lag_c0 + sub;
+                    ring[(c % p.lag_n) * 12] = a;
+                    a = ring[((c + 1) % p.lag_n) * 12];
+                }
                 float err = q[k] - (a + md->q_default[j]);
                 x[k][0] = err; x[k][1] = e1[k]; x[k][2] = e2[k]; x[k][3] = qd[k]; x[k][4] = v1[k]; x[k][5] = v2[k];
                 e2[k] = e1[k]; e1[k] = err; v2[k] = v1[k]; v1[k] = qd[k];
@@ -1462,6 +1469,10 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             atomicMax(p.stats + 3, stat_rows);
         }
         if (rank_in_env == 0) atomicAdd(p.stats + 2, stat_pair);
+    }
+    if (p.lag_ring && threadIdx.x == 0) {                                  // the last CTA to finish advances the call counter
+        __threadfence();
+        if (atomicAdd(&p.ctr[4], 1) == (int)gridDim.x - 1) { p.ctr[4] = 0; p.ctr[3] += nsub; }
     }
     // per-warp trace (MQE_BUF_WARP_TRACE): start / end on the global timer [ns], pair contacts and widest row count of the warp
     {

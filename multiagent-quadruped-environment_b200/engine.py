@@ -16,7 +16,7 @@ from .model import MAX_CAPS, MAX_PROBES, RobotModelC  # noqa: F401
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libmqe_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LOC_OBS = 70
 OBS_FLOATS = 71
 
@@ -96,6 +96,7 @@ class SimDescC(ctypes.Structure):
         ("seed", ctypes.c_uint64),
         ("sdf_nx", ctypes.c_int32), ("sdf_ny", ctypes.c_int32), ("sdf_cell", ctypes.c_float), ("push_interval", ctypes.c_int32),
         ("control_type", ctypes.c_int32), ("stiffness", ctypes.c_float), ("damping", ctypes.c_float),
+        ("lag_enabled", ctypes.c_int32), ("lag_timesteps", ctypes.c_int32),
         ("h_sdf", _fp), ("h_env_origins", _fp), ("h_agent_origins", _fp), ("h_base_init_state", _fp),
         ("h_npc_init_state", _fp), ("h_npc_dof_default", _fp), ("h_base_added_mass", _fp), ("h_env_friction", _fp),
         ("model", RobotModelC),

@@ -250,6 +250,8 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     assert ct in ("C", "control_net", "P", "T"), f"control_type {ct!r}: 'V' is not built"
     d.control_type = {"C": 0, "control_net": 0, "P": 1, "T": 2}[ct]
     d.stiffness, d.damping = float(cfg.control.stiffness.get("joint", 0.0)), float(cfg.control.damping.get("joint", 0.0))
+    if getattr(dr, "randomize_lag_timesteps", False):                          # go1.py:337-339, 363
+        d.lag_enabled, d.lag_timesteps = 1, int(dr.lag_timesteps)
     # domain randomisation switches of the reference that are off in its task configs
     if getattr(dr, "push_robots", False):                                      # legged_robot.py:1024, go1.py:237-238
         d.push_interval = int(np.ceil(dr.push_interval_s / dt))

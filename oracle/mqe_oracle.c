@@ -401,6 +401,7 @@ typedef struct {
     real *last_dof_vel, *last_root_vel;
     real *sheep_stats;                      /* [N][3]                           */
     float *mu_env;                          /* [N] per-env friction or NULL (domain_rand.randomize_friction) */
+    real *lag_ring; int lag_n; uint32_t lag_calls;   /* action lag (go1.py:337-339, 363): [M][lag_n][12] scaled actions; calls so far */
     float *base_mass_add;                   /* [M] mass added to the base link or NULL (domain_rand.randomize_base_mass) */
     int64_t *ep_len;
     uint8_t *reset_buf, *timeout_buf, *collide_buf, *r_term, *p_term, *zl_term, *zh_term;
@@ -437,6 +438,7 @@ Oracle *orc_create(const MqeSimDesc *desc) {
     o->npc_init = dupr(desc->h_npc_init_state, (size_t)N * P * 13);
     o->npc_dof_default = dupr(desc->h_npc_dof_default, (size_t)(o->D ? o->D : 1));
     o->mu_env = desc->h_env_friction ? dupf(desc->h_env_friction, (size_t)N) : NULL;
+    if (desc->lag_enabled) { o->lag_n = desc->lag_timesteps + 1; o->lag_ring = (real *)xcalloc((size_t)M * o->lag_n * 12, sizeof(real)); }
     o->base_mass_add = desc->h_base_added_mass ? dupf(desc->h_base_added_mass, (size_t)M) : NULL;
     /* private copies of the weights */
     const float **src = (const float **)&desc->weights;
@@ -484,7 +486,7 @@ Oracle *orc_create(const MqeSimDesc *desc) {
 
 void orc_destroy(Oracle *o) {
     if (!o) return;
-    free(o->sdf); free(o->env_origins); free(o->agent_origins); free(o->base_init); free(o->npc_init); free(o->npc_dof_default); free(o->mu_env); free(o->base_mass_add);
+    free(o->sdf); free(o->env_origins); free(o->agent_origins); free(o->base_init); free(o->npc_init); free(o->npc_dof_default); free(o->mu_env); free(o->base_mass_add); free(o->lag_ring);
     for (int i = 0; i < 20; i++) free(o->wbuf[i]);
     free(o->root); free(o->dof); free(o->contact); free(o->torques); free(o->actions); free(o->last_actions);
     free(o->loc_last); free(o->loc_last2); free(o->loc_obs); free(o->hist); free(o->err1); free(o->err2); free(o->vel1); free(o->vel2);
@@ -1070,7 +1072,7 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
 }
 
 /* ------------------------------------------------------------------------------------------------ _compute_torques (go1.py:315-354) */
-static void env_torques(Oracle *o, int e, real *tau) {
+static void env_torques(Oracle *o, int e, real *tau, uint32_t call) {
     const MqeSimDesc *d = &o->d;
     int A = o->A;
     real *dof = o->dof + (size_t)e * (12 * A + o->D) * 2;
@@ -1087,6 +1089,11 @@ static void env_torques(Oracle *o, int e, real *tau) {
                 continue;
             }
             if (j % 3 == 0) act *= d->hip_scale;
+            if (o->lag_ring) {   /* lag_buffer = lag_buffer[1:] + [actions_scaled]; target = lag_buffer[0] (go1.py:337-339), as a ring */
+                real *ring = o->lag_ring + (size_t)m * o->lag_n * 12 + j;
+                ring[(call % o->lag_n) * 12] = act;
+                act = ring[((call + 1) % o->lag_n) * 12];
+            }
             real target = act + d->model.q_default[j];
             real err = dof[(12 * a + j) * 2] - target, vel = dof[(12 * a + j) * 2 + 1];
             real x[6] = {err, o->err1[m * 12 + j], o->err2[m * 12 + j], vel, o->vel1[m * 12 + j], o->vel2[m * 12 + j]};
@@ -1263,13 +1270,14 @@ void orc_substeps(Oracle *o, int count) {
         int32_t st[8] = {0};
         real tau[48];
         for (int s = 0; s < count; s++) {
-            env_torques(o, e, tau);
+            env_torques(o, e, tau, o->lag_calls + (uint32_t)s);
             env_substep(o, e, tau, st);
         }
 #pragma omp critical
         { tot[0] += st[0]; tot[1] += st[1]; tot[2] += st[2]; if (st[3] > tot[3]) tot[3] = st[3]; }
     }
     memcpy(o->stats, tot, sizeof tot);
+    o->lag_calls += (uint32_t)count;
 }
 
 /* _step_contact_targets (go1.py:240-279) */
@@ -1453,7 +1461,8 @@ int orc_real_size(void) { return (int)sizeof(real); }
 void orc_set_reset_state(Oracle *o, int on) { o->reset_state = on; }
 /* _compute_torques for every env, no physics (go1.py:315-354) */
 void orc_torques(Oracle *o) {
-    for (int e = 0; e < o->N; e++) { real tau[48]; env_torques(o, e, tau); }
+    for (int e = 0; e < o->N; e++) { real tau[48]; env_torques(o, e, tau, o->lag_calls); }
+    o->lag_calls += 1;
 }
 /* base_quat <- root quaternion, then compute_observations: the state Go1.reset() leaves behind */
 void orc_observe(Oracle *o) {

@@ -522,3 +522,23 @@ def test_pd_and_torque_control_parity(ct):
         assert np.allclose(g[..., :7], r[..., :7], atol=2e-4), (s, np.abs(g[..., :7] - r[..., :7]).max())
         assert np.allclose(get(eng, E.BUF_TORQUES).ravel(), orc.get(E.BUF_TORQUES).ravel(), atol=2e-2), s
     eng.close(); orc.close()
+
+
+@pytest.mark.gpu
+def test_action_lag_parity():
+    """domain_rand.randomize_lag_timesteps (go1.py:337-339): the lag ring in k_substeps against the oracle, across policy steps (the ring
+    position is a device-side counter of torque evaluations, so CUDA-graph replays keep advancing it)."""
+    for mode in (E.POLICY_FP32, E.POLICY_BF16X3):
+        cfg = C.Go1GateCfg(); cfg.env.num_envs = 8
+        cfg.domain_rand.randomize_lag_timesteps = True; cfg.domain_rand.lag_timesteps = 6
+        np.random.seed(0)
+        sc = S.build_scene(cfg, seed=0, policy_mode=mode, wrapper_action_scale=(2.0, 0.5, 0.5))
+        eng, orc = E.Engine(sc.desc, device=0, keepalive=sc), oracle.Oracle(sc, "f32")
+        eng.reset(); orc.reset()
+        for s in range(6):
+            a = actions_for(sc, s)
+            eng.step(dev(a).data_ptr()); orc.step(a)
+            g, r = get(eng, E.BUF_ROOT_STATES).reshape(8, 2, 13), orc.root_states()
+            assert np.allclose(g[..., :7], r[..., :7], atol=3e-4), (mode, s, np.abs(g[..., :7] - r[..., :7]).max())
+            assert np.allclose(get(eng, E.BUF_TORQUES).ravel(), orc.get(E.BUF_TORQUES).ravel(), atol=5e-2), (mode, s)
+        eng.close(); orc.close()

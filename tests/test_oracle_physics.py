@@ -275,3 +275,28 @@ def test_pd_position_control_holds_the_default_pose():
     assert np.all(z > 0.2) and o.get(E.BUF_RESET).sum() == 0, z
     tq = o.get(E.BUF_TORQUES)
     assert np.all(np.abs(tq) <= 25.0 + 1e-6)
+
+
+def test_action_lag_buffer():
+    """domain_rand.randomize_lag_timesteps (go1.py:337-339, 363): the position target is the scaled action of `lag_timesteps` torque
+    evaluations (substeps) ago.  lag_timesteps = 0 is no lag at all; with 6 the first 6 substeps act on the all-zero initial buffer."""
+    def run(lag_on, lag):
+        cfg = C.Go1GateCfg(); cfg.env.num_envs = 2
+        cfg.domain_rand.randomize_lag_timesteps = lag_on
+        cfg.domain_rand.lag_timesteps = lag
+        cfg.domain_rand.init_dof_pos_ratio_range = None
+        np.random.seed(0)
+        sc = S.build_scene(cfg, seed=0)
+        o = oracle.Oracle(sc, "f64")
+        o.reset()
+        act = np.zeros((2, 2, 3), dtype=np.float32); act[..., 0] = 0.5
+        out = []
+        for s in range(4):
+            o.step(act)
+            out.append((o.get(E.BUF_DOF_STATES).copy(), o.get(E.BUF_TORQUES).copy()))
+        return out
+    off, lag0, lag6 = run(False, 6), run(True, 0), run(True, 6)
+    for (d0, t0), (d1, t1) in zip(off, lag0):
+        assert np.array_equal(d0, d1) and np.array_equal(t0, t1)
+    assert not np.allclose(off[1][0], lag6[1][0], atol=1e-4)          # the delayed targets change the joint trajectory
+    assert np.isfinite(lag6[-1][0]).all()
