@@ -60,3 +60,28 @@ def test_no_cpu_fallback():
     src = "".join(open(os.path.join(ROOT, "multiagent-quadruped-environment_b200", f)).read()
                   for f in ("engine.py", "scene.py", os.path.join("envs", "go1.py"), os.path.join("envs", "wrappers.py")))
     assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_substep_launch_plan_residency():
+    """Host-side launch plan of k_substeps (physics.cu `substeps_plan`): shared memory per CTA must fit the 227 KB opt-in limit for every
+    task shape, and C2 (4096 envs x 2 robots) must come out as 7 resident warps of 4 envs -- the one-wave design point of DESIGN.md 3.1."""
+    import __graft_entry__ as g
+    if not os.path.exists(E.LIB_PATH):
+        g.build()
+    lib = E.load_library()
+    fn = lib.mqe_substeps_smem_bytes
+    fn.restype = ctypes.c_size_t
+    fn.argtypes = [ctypes.c_int] * 5
+    LIMIT = 227 * 1024
+    shapes = {  # task: (A, NPCs that own a lane, pair budget)
+        "go1gate": (2, 0, 8), "go1sheep-hard": (2, 9, 16), "go1sheep-easy": (2, 1, 16), "go1seesaw": (2, 1, 16),
+        "go1football-defender": (3, 1, 16), "go1football-2vs2": (4, 1, 16), "go1plane": (1, 0, 8), "go1wrestling": (2, 0, 16),
+    }
+    for task, (A, Pd, maxpair) in shapes.items():
+        lanes = 4 * A + Pd
+        Eenv = 32 // lanes
+        for N in (1, 7, 4096, 32768):
+            b = fn(N, A, Pd, Eenv, maxpair)
+            assert 0 < b <= LIMIT, (task, N, b)
+    assert fn(4096, 2, 0, 4, 8) == 230688          # 8 KB header + 7 warps x 4 envs x 7.9 KB
+    assert fn(4, 2, 0, 4, 8) < 48 * 1024           # a single warp of envs needs no opt-in at all
