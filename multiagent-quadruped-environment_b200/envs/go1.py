@@ -160,7 +160,15 @@ class Go1:
         """go1.py:147-151: reset_idx(all) + compute_observations; no physics step."""
         self.engine.reset()
         self._reset_ids = torch.arange(self.num_envs, device=self.device)
+        self._fill_extras()
         return self.obs_buf
+
+    def _fill_extras(self):
+        """legged_robot.py:1063-1076 as it comes out for Go1: no reward terms are registered (go1.py:198-219), so `extras["episode"]`
+        is empty; `extras["time_outs"]` aliases the time-out flags (cfg.env.send_timeouts), which the engine rewrites in place."""
+        self.extras["episode"] = {}
+        if getattr(self.cfg.env, "send_timeouts", False):
+            self.extras["time_outs"] = self.time_out_buf
 
     def step(self, action):
         """go1.py:35-62.  action: [N*A_ctrl, 3] already scaled by the task wrapper."""
