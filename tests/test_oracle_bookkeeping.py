@@ -14,7 +14,7 @@ from mqe_b200 import scene as S
 from mqe_b200.envs import configs as C
 
 TASKS = {"go1gate": C.Go1GateCfg, "go1sheep-easy": C.SingleSheepCfg, "go1football-defender": C.Go1FootballDefenderCfg,
-         "go1seesaw": C.Go1SeesawCfg}
+         "go1seesaw": C.Go1SeesawCfg, "go1tug": C.Go1TugCfg, "go1wrestling": C.Go1WrestlingCfg, "go1bridge": C.Go1BridgeCfg}
 O = E.OBS_SLICES
 
 

@@ -254,6 +254,9 @@ def main():
     run("go1sheep-easy", "mqe.envs.configs.go1_sheep_config", "SingleSheepCfg", "mqe.envs.npc.go1_sheep", "Go1Sheep", 12, 12)
     run("go1football-defender", "mqe.envs.configs.go1_football_config", "Go1FootballDefenderCfg", "mqe.envs.npc.go1_football_defender", "Go1FootballDefender", 12, 13)
     run("go1seesaw", "mqe.envs.configs.go1_seesaw_config", "Go1SeesawCfg", "mqe.envs.npc.go1_object", "Go1Object", 12, 14)
+    run("go1tug", "mqe.envs.configs.go1_tug_config", "Go1TugCfg", "mqe.envs.npc.go1_object", "Go1Object", 12, 15)
+    run("go1wrestling", "mqe.envs.configs.go1_wrestling_config", "Go1WrestlingCfg", "mqe.envs.npc.go1_object", "Go1Object", 12, 16)
+    run("go1bridge", "mqe.envs.configs.go1_bridge_config", "Go1BridgeCfg", "mqe.envs.npc.go1_object", "Go1Object", 12, 17)
 
 
 if __name__ == "__main__":
