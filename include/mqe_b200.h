@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MQE_ABI_VERSION 5
+#define MQE_ABI_VERSION 6
 #define MQE_MAX_PROBES 32
 #define MQE_MAX_CAPS 20
 #define MQE_NUM_DOF 12
@@ -121,12 +121,15 @@ typedef struct {
     float sdf_cell;
     int32_t push_interval;                      /* domain_rand.push_robots: every push_interval policy steps (ceil(push_interval_s / dt),
                                                    legged_robot.py:1024) every robot's base velocity x, y is redrawn in +-max_push_vel_xy; 0 = off */
-    int32_t control_type;                       /* cfg.control.control_type: 0 'C' actuator network (go1.py:335-352, every shipped task),
-                                                   1 'P' PD position targets, 2 'T' scaled torques (legged_robot.py:384-392; no hip scale there) */
+    int32_t control_type;                       /* cfg.control.control_type: 0 'C' actuator network behind the walk policy (go1.py:335-352, every
+                                                   shipped task; mqe_sim_step takes 3-D commands), 1 'P' PD position targets, 2 'T' scaled torques,
+                                                   3 'V' PD velocity targets (legged_robot.py:384-392; no hip scale there).  1..3 bypass the walk
+                                                   policy as Go1.step does (go1.py:43-45): the caller hands [N][12A] joint actions to mqe_sim_step_joint */
     float stiffness, damping;                   /* cfg.control.stiffness / damping ['joint'] for control_type 'P'                  */
     int32_t lag_enabled;                        /* domain_rand.randomize_lag_timesteps (go1.py:337-339, 363): the actuator network's position
                                                    target is the scaled action of `lag_timesteps` _compute_torques calls (substeps) ago */
     int32_t lag_timesteps;
+    float soft_dof_pos_limit;                   /* cfg.rewards.soft_dof_pos_limit (legged_robot.py:318-321): the limits substep_exceed_dof_pos_limits tests */
     const float *h_sdf;                         /* [nx][ny] host, copied                                   */
     /* per-env constants, host, copied */
     const float *h_env_origins;                 /* [N][3]                                                  */
@@ -190,10 +193,19 @@ typedef enum {
     MQE_BUF_SHEEP_STATS,        /* f32 [N][3]     sheep_pos_avg xy, sheep_pos_var */
     MQE_BUF_STATS,              /* i32 [8]        contact / row statistics of the last step */
     MQE_BUF_CLOCK,              /* f32 [N*A][4]   gait clock inputs (go1.py:240-279)        */
-    MQE_BUF_WRAP_OBS,           /* f32 [N][Aw][D]  task-wrapper observation (after mqe_sim_set_wrapper)            */
-    MQE_BUF_WRAP_REWARD,        /* f32 [N][Aw]     task-wrapper reward                                              */
     MQE_BUF_WRAP_SUMS,          /* f64 [16]        running sums of the reward terms (scale order), [8] = steps      */
     MQE_BUF_WARP_TRACE,         /* i64 [warps][20] substep kernel trace per warp of envs: start ns, end ns, pair contacts, widest row count, then (MQE_TRACE=1) cycles per phase */
+    /* post_decimation_step logs (legged_robot.py:112-115).  Nothing on the Go1 path reads them, so they are produced LAZILY: the first
+     * mqe_sim_get_buffer on any of the three allocates them and switches the per-substep stores on for every following step. */
+    MQE_BUF_SUBSTEP_TORQUES,    /* f32 [N][decimation][12A]                 */
+    MQE_BUF_SUBSTEP_DOF_VEL,    /* f32 [N][decimation][12A]                 */
+    MQE_BUF_SUBSTEP_EXCEED,     /* u8  [N][decimation][12A]  dof_pos outside the soft limits */
+    MQE_BUF_HISTORY_HI,         /* u16 [ceil(N*A/128)][30][10][128][8] bf16 high plane of the frame ring (tensor-core policy modes) */
+    MQE_BUF_HISTORY_LO,         /* u16 same layout, bf16 residual plane: frame = float(hi) + float(lo) to 2^-16 relative */
+    MQE_BUF_STEP_RESULT,        /* u8  [2][total_bytes] what the learner reads after a step, packed for ONE copy / ONE exchange: wrapper obs
+                                   f32 [N][Aw][D], reward f32 [N][Aw], done u8 [N]; see mqe_sim_step_result_layout.  Double buffered: step t
+                                   writes half (t + 1) & 1 (mqe_sim_result_parity), so the previous step's result stays readable for one more
+                                   step -- the reference returns fresh tensors every step, a learner may hold obs_t across env.step() */
     MQE_BUF_COUNT
 } MqeBuffer;
 
@@ -224,7 +236,7 @@ int mqe_sim_set_stream(MqeSim *sim, void *stream);
  * Go1.step() itself and the wrapper has already scaled (go1.py:38). */
 int mqe_sim_set_action_scale(MqeSim *sim, const float scale[3]);
 
-/* Enable the fused task-wrapper gather: every following mqe_sim_step also fills MQE_BUF_WRAP_OBS / _REWARD / _SUMS, and
+/* Enable the fused task-wrapper gather: every following mqe_sim_step also fills the obs / reward fields of MQE_BUF_STEP_RESULT and MQE_BUF_WRAP_SUMS, and
  * mqe_sim_reset fills the observation (the wrappers' reset()).  kind = MQE_WRAP_NONE switches it off again. */
 int mqe_sim_set_wrapper(MqeSim *sim, const MqeWrapperDesc *desc);
 /* the wrappers' reset() without an env reset: observation only, per-episode wrapper state cleared (used once, right after
@@ -243,9 +255,47 @@ int mqe_sim_reset(MqeSim *sim);
  * (A_ctrl = A, or A-1 when desc.defender).  Asynchronous on the stream. */
 int mqe_sim_step(MqeSim *sim, const float *d_actions);
 
+/* Go1.step() for control_type 'P' / 'V' / 'T' (go1.py:43-45 -> legged_robot.py:108-110 pre_physics_step): d_joint_actions f32 [N][12A]
+ * are clipped to +-clip_actions and become `actions`; no walk policy, no gait clock.  MQE_ERR_UNSUPPORTED for control_type 'C'
+ * (and mqe_sim_step returns MQE_ERR_UNSUPPORTED for the other control types). */
+int mqe_sim_step_joint(MqeSim *sim, const float *d_joint_actions);
+
 /* Same step through HOST buffers: H2D of actions, step, D2H of obs rows / reset flags; blocks until
  * the results are in host memory.  h_obs: [N*A][71] (may be NULL), h_reset: [N] (may be NULL). */
 int mqe_sim_step_host(MqeSim *sim, const float *h_actions, float *h_obs, uint8_t *h_reset);
+
+/* What the learner reads after a step, packed so that ONE device->host copy (mqe_sim_step_host_result) or ONE peer exchange
+ * (mqe_sim_gather_*) moves it: the fused task-wrapper observation and reward (empty when no wrapper is set, e.g. go1gate whose shipped
+ * wrapper returns 0, go1_gate_wrapper.py:155) and the done flags.  Offsets in bytes into MQE_BUF_STEP_RESULT. */
+typedef struct {
+    int64_t obs_off, obs_bytes;          /* f32 [N][Aw][D]  */
+    int64_t reward_off, reward_bytes;    /* f32 [N][Aw]     */
+    int64_t done_off, done_bytes;        /* u8  [N]         */
+    int64_t total_bytes;                 /* multiple of 16  */
+    int32_t num_envs, Aw, D, reserved;
+} MqeStepResultLayout;
+int mqe_sim_step_result_layout(MqeSim *sim, MqeStepResultLayout *out);
+/* half of MQE_BUF_STEP_RESULT that holds the latest result (policy steps done so far & 1; reset rewrites the current half) */
+int mqe_sim_result_parity(MqeSim *sim);
+/* mqe_sim_step through HOST buffers with the packed result: H2D of actions, step, ONE D2H of MQE_BUF_STEP_RESULT into h_result
+ * (total_bytes); blocks until it has landed.  This is the call behind openrl_ws/utils.py:53-67 (`mqe_openrl_wrapper.step`). */
+int mqe_sim_step_host_result(MqeSim *sim, const float *h_actions, void *h_result);
+
+/* Per-step exchange between the ranks of one node over NVLink peer memory (replaces an NCCL all-gather after the step).
+ * Every rank owns a receive buffer [2 parities][obs | reward | done regions, each world x local bytes]; the last kernel of the step
+ * (inside the step graph) stores this rank's MQE_BUF_STEP_RESULT fields into EVERY peer's buffer, publishes a per-rank step flag
+ * with system-scope release, and waits until all peers' flags for this step have arrived locally.  Equal shard sizes only.
+ *   1. every rank: mqe_sim_gather_init (after mqe_sim_set_wrapper) -> 64-byte cudaIpcMemHandle;
+ *   2. hosts exchange the handles (torch.distributed all_gather_object in mqe_b200/dist.py);
+ *   3. every rank: mqe_sim_gather_connect(handles of all ranks, rank order).
+ * After step t (t = 0, 1, ...) the global result is in the parity (t + 1) & 1 half; mqe_sim_gather_view returns its device pointer and
+ * the GLOBAL layout (num_envs = world x N).  A peer that never arrives makes the wait give up after ~2 s and raises MQE_STAT_GATHER_TIMEOUT
+ * in MQE_BUF_STATS[5] instead of hanging the device. */
+int mqe_sim_gather_init(MqeSim *sim, int rank, int world, void *ipc_handle_out /* 64 bytes */);
+int mqe_sim_gather_connect(MqeSim *sim, const void *ipc_handles /* [world][64] */);
+int mqe_sim_gather_view(MqeSim *sim, int parity, void **d_ptr, MqeStepResultLayout *global_layout);
+/* half of the receive buffer that holds the latest exchange (every mqe_sim_reset and every step performs one) */
+int mqe_sim_gather_parity(MqeSim *sim);
 
 /* Optional: register a caller-owned host range (cudaHostRegister) so that mqe_sim_step_host copies straight from / into it
  * instead of through the handle's staging buffers.  The range must stay mapped until mqe_sim_unpin_host / mqe_sim_destroy.

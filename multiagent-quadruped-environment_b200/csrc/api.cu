@@ -51,8 +51,18 @@ struct MqeSim {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool fork_policy = false;
     WrapParams wrap = {};                // fused task-wrapper gather (mqe_sim_set_wrapper); kind 0 = off
+    // what the learner reads after a step, packed (MQE_BUF_STEP_RESULT): wrapper obs | reward | done
+    unsigned char *d_result = nullptr, *h_result = nullptr;
+    MqeStepResultLayout rl = {};
+    GatherParams gather = {};            // peer exchange of the step result (mqe_sim_gather_*); world 0 = off
+    void *gather_peers[MQE_MAX_RANKS] = {};
+    int gather_pending_world = 0;
+    unsigned long long gather_seq = 0;   // exchanges enqueued so far (host mirror of ctr[5])
     struct Pinned { char *ptr; size_t bytes; };
     std::vector<Pinned> pinned;          // host ranges registered with mqe_sim_pin_host: mqe_sim_step_host copies straight to / from them
+    size_t action_bytes() const {        // [N][A_ctrl][3] commands ('C') or [N][12A] joint actions ('P' / 'V' / 'T')
+        return (p.control_type == 0 ? (size_t)p.N * actrl * 3 : (size_t)p.N * p.A * 12) * sizeof(float);
+    }
     bool is_pinned(const void *ptr, size_t bytes) const {
         for (const auto &r : pinned)
             if ((const char *)ptr >= r.ptr && (const char *)ptr + bytes <= r.ptr + r.bytes) return true;
@@ -85,8 +95,35 @@ static void set_buf(MqeSim *s, int which, void *ptr, int elem, int64_t a, int64_
     s->bufs[which].shape[0] = a; s->bufs[which].shape[1] = b; s->bufs[which].shape[2] = c; s->bufs[which].shape[3] = d;
 }
 
+// (Re)allocate MQE_BUF_STEP_RESULT for the current wrapper shape: [obs f32 N*Aw*D | reward f32 N*Aw | done u8 N], every region 16-byte aligned
+static cudaError_t alloc_step_result(MqeSim *s, int Aw, int D) {
+    const int N = s->p.N;
+    auto up16 = [](int64_t v) { return (v + 15) & ~(int64_t)15; };
+    MqeStepResultLayout &L = s->rl;
+    L.num_envs = N; L.Aw = Aw; L.D = D; L.reserved = 0;
+    L.obs_off = 0; L.obs_bytes = (int64_t)N * Aw * D * 4;
+    L.reward_off = up16(L.obs_off + L.obs_bytes); L.reward_bytes = (int64_t)N * Aw * 4;
+    L.done_off = up16(L.reward_off + L.reward_bytes); L.done_bytes = N;
+    L.total_bytes = up16(L.done_off + L.done_bytes);
+    cudaError_t e = dalloc(s, &s->d_result, (size_t)(2 * L.total_bytes));      // double buffered: half = policy steps done & 1
+    if (e != cudaSuccess) return e;
+    s->p.result_half = L.total_bytes;
+    if (s->h_result) { cudaFreeHost(s->h_result); s->h_result = nullptr; }
+    if ((e = cudaMallocHost(&s->h_result, (size_t)L.total_bytes)) != cudaSuccess) return e;
+    s->p.result_done = s->d_result + L.done_off;
+    e = cudaMemsetAsync(s->p.result_done, 1, N, s->stream);            // reset_buf starts as ones (base_task.py:77)
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->p.result_done + L.total_bytes, 1, N, s->stream);
+    set_buf(s, MQE_BUF_STEP_RESULT, s->d_result, 1, 2, L.total_bytes);
+    return e;
+}
+static void drop_graphs(MqeSim *s) {
+    for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);
+    s->graphs.clear();
+}
+
 extern "C" {
 
+static int exchange_impl(MqeSim *s);
 const char *mqe_last_error(void) { return g_err.c_str(); }
 int mqe_abi_version(void) { return MQE_ABI_VERSION; }
 int mqe_device_count(void) {
@@ -110,6 +147,9 @@ int mqe_sim_destroy(MqeSim *s) {
     if (s->h_actions) cudaFreeHost(s->h_actions);
     if (s->h_obs) cudaFreeHost(s->h_obs);
     if (s->h_reset) cudaFreeHost(s->h_reset);
+    if (s->h_result) cudaFreeHost(s->h_result);
+    for (int r = 0; r < s->gather.world; r++)
+        if (r != s->gather.rank && s->gather_peers[r]) cudaIpcCloseMemHandle(s->gather_peers[r]);
     if (s->tmp_ring) cudaFree(s->tmp_ring);
     if (s->tmp_hi) cudaFree(s->tmp_hi);
     if (s->tmp_lo) cudaFree(s->tmp_lo);
@@ -166,8 +206,9 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     p.npc_mass = d->npc_mass; p.npc_inertia = d->npc_inertia; p.npc_radius = d->npc_radius; p.npc_halflen = d->npc_halflen;
     p.sheep_scale = d->sheep_scale; p.sheep_rand = d->sheep_randomness; p.gate_x = d->gate_x;
     p.seed = d->seed;
-    if (d->control_type < 0 || d->control_type > 2) return fail(MQE_ERR_UNSUPPORTED, "control_type must be 0 (C), 1 (P) or 2 (T)");
+    if (d->control_type < 0 || d->control_type > 3) return fail(MQE_ERR_UNSUPPORTED, "control_type must be 0 (C), 1 (P), 2 (T) or 3 (V)");
     p.control_type = d->control_type; p.kp = d->stiffness; p.kd = d->damping;
+    p.soft_limit = d->soft_dof_pos_limit > 0.f ? d->soft_dof_pos_limit : 1.f;
     p.push_interval = d->push_interval > 0 ? d->push_interval : 0; p.max_push_vel = d->max_push_vel_xy;
     p.sdf_nx = d->sdf_nx; p.sdf_ny = d->sdf_ny; p.sdf_cell = d->sdf_cell;
     if (!d->h_sdf || !d->h_env_origins || !d->h_agent_origins || !d->h_base_init_state) return fail(MQE_ERR_INVALID, "descriptor host arrays missing");
@@ -296,12 +337,12 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     }
     CK(dalloc(s, &p.pdesc_scratch, mqe_substeps_pdesc_scratch_floats(N, s->maxpair), false));
     const size_t ring = (size_t)M * MQE_HIST_FRAMES * MQE_HIST_PAD;
-    CK(dalloc(s, &p.hist_f32, ring));
+    if (p.policy_mode == MQE_POLICY_FP32) CK(dalloc(s, &p.hist_f32, ring));      // tensor-core modes: the bf16 hi / lo planes ARE the ring
     const size_t ring_tc = (size_t)((M + 127) / 128) * 128 * MQE_HIST_FRAMES * MQE_HIST_PAD;     // pre-tiled planes, rows padded to 128
     if (p.policy_mode != MQE_POLICY_FP32) { CK(dalloc(s, &p.hist_hi, ring_tc)); CK(dalloc(s, &p.hist_lo, ring_tc)); }
     CK(dalloc(s, &s->ps.Z, (size_t)M * 768)); CK(dalloc(s, &s->ps.T1, (size_t)M * 128)); CK(dalloc(s, &s->ps.T2, (size_t)M * 256));
     CK(dalloc(s, &s->ps.T3, (size_t)M * 128)); CK(dalloc(s, &s->ps.latent, (size_t)M * 2)); CK(dalloc(s, &s->ps.act, (size_t)M * 12));
-    CK(dalloc(s, &s->d_actions_stage, (size_t)N * s->actrl * 3));
+    CK(dalloc(s, &s->d_actions_stage, s->action_bytes() / sizeof(float)));
     CK(cudaMemsetAsync(p.reset_buf, 1, N, s->stream));                      // base_task.py:77: reset_buf starts as ones
     // _prepare_locomotion_policy: locomotion_obs = default command frame (go1.py:393-394); actors at their start poses
     {
@@ -320,14 +361,35 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
                 for (int i = 0; i < 3; i++) r[i] += d->h_env_origins[e * 3 + i];
             }
         }
+        // _init_buffers (legged_robot.py:570, 620-622): base_quat is the spawn quaternion, base_lin_vel / base_ang_vel / projected_gravity
+        // are derived from the spawn state, so the observation of the very first reset() already carries gravity (0, 0, -1) in the base
+        // frame (reset_idx does not recompute them; post_physics_step does, after the first physics step)
+        std::vector<float> bq((size_t)M * 4), blv((size_t)M * 3), bav((size_t)M * 3), pg((size_t)M * 3);
+        for (int m = 0; m < M; m++) {
+            const float *r = d->h_base_init_state + (size_t)m * 13, *q = r + 3;
+            auto rot_inv = [&](const float *v, float *o) {       // isaacgym.torch_utils.quat_rotate_inverse
+                const float w = q[3], k = 2.f * w * w - 1.f, dq = q[0] * v[0] + q[1] * v[1] + q[2] * v[2];
+                const float c[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+                for (int i = 0; i < 3; i++) o[i] = k * v[i] - 2.f * w * c[i] + 2.f * dq * q[i];
+            };
+            const float g[3] = {0.f, 0.f, -1.f};
+            for (int i = 0; i < 4; i++) bq[(size_t)m * 4 + i] = q[i];
+            rot_inv(r + 7, &blv[(size_t)m * 3]); rot_inv(r + 10, &bav[(size_t)m * 3]); rot_inv(g, &pg[(size_t)m * 3]);
+        }
+        CK(cudaMemcpyAsync(p.base_quat, bq.data(), bq.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(p.base_lin_vel, blv.data(), blv.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(p.base_ang_vel, bav.data(), bav.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        CK(cudaMemcpyAsync(p.proj_grav, pg.data(), pg.size() * 4, cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(p.loc_obs, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(p.root, root.data(), root.size() * 4, cudaMemcpyHostToDevice, s->stream));
         CK(cudaMemcpyAsync(p.dof, dof.data(), dof.size() * 4, cudaMemcpyHostToDevice, s->stream));
         CK(cudaStreamSynchronize(s->stream));
     }
-    CK(cudaMallocHost(&s->h_actions, (size_t)N * s->actrl * 3 * sizeof(float)));
+    CK(cudaMallocHost(&s->h_actions, s->action_bytes()));
     CK(cudaMallocHost(&s->h_obs, (size_t)M * MQE_OBS_FLOATS * sizeof(float)));
     CK(cudaMallocHost(&s->h_reset, (size_t)N));
+    CK(alloc_step_result(s, 0, 0));
+    CK(mqe_substeps_configure(p, s->maxpair));               // per-device function attribute of k_substeps
 
     set_buf(s, MQE_BUF_ROOT_STATES, p.root, 4, N, G, 13);
     set_buf(s, MQE_BUF_DOF_STATES, p.dof, 4, N, 12 * A + D, 2);
@@ -351,7 +413,9 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     set_buf(s, MQE_BUF_LOC_OBS, p.loc_obs, 4, M, MQE_LOC_OBS);
     set_buf(s, MQE_BUF_LOC_ACTION, p.loc_last, 4, M, 12);
     set_buf(s, MQE_BUF_GAIT, p.gait, 4, M);
-    set_buf(s, MQE_BUF_HISTORY, p.hist_f32, 4, M, MQE_HIST_FRAMES, MQE_HIST_PAD);
+    set_buf(s, MQE_BUF_HISTORY, p.hist_f32, 4, M, MQE_HIST_FRAMES, MQE_HIST_PAD);      // null outside MQE_POLICY_FP32
+    set_buf(s, MQE_BUF_HISTORY_HI, p.hist_hi, 2, (M + 127) / 128, MQE_HIST_FRAMES, MQE_HIST_PAD / 8, 128 * 8);
+    set_buf(s, MQE_BUF_HISTORY_LO, p.hist_lo, 2, (M + 127) / 128, MQE_HIST_FRAMES, MQE_HIST_PAD / 8, 128 * 8);
     set_buf(s, MQE_BUF_SHEEP_STATS, p.sheep_stats, 4, N, 3);
     set_buf(s, MQE_BUF_STATS, p.stats, 4, 8);
     set_buf(s, MQE_BUF_CLOCK, p.clock, 4, M, 4);
@@ -387,12 +451,12 @@ int mqe_sim_set_wrapper(MqeSim *s, const MqeWrapperDesc *d) {
     if (!s || !d) return fail(MQE_ERR_INVALID, "null argument");
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->stream));
-    for (auto &g : s->graphs) cudaGraphExecDestroy(g.exec);      // the step graph changes shape
-    s->graphs.clear();
+    drop_graphs(s);                                              // the step graph changes shape
+    if (s->gather.world) return fail(MQE_ERR_INVALID, "mqe_sim_set_wrapper must precede mqe_sim_gather_init");
     const DevParams &p = s->p;
     WrapParams w = {};
     w.kind = d->kind;
-    if (d->kind == MQE_WRAP_NONE) { s->wrap = w; return MQE_OK; }
+    if (d->kind == MQE_WRAP_NONE) { s->wrap = w; CK(alloc_step_result(s, 0, 0)); return MQE_OK; }
     int gate_cols = 0;
     if (d->kind == MQE_WRAP_SHEEP) {
         if (p.npc_ctrl != MQE_NPC_SHEEP || p.P < 1 || p.P > 12) return fail(MQE_ERR_INVALID, "sheep wrapper needs 1..12 sheep");
@@ -410,12 +474,11 @@ int mqe_sim_set_wrapper(MqeSim *s, const MqeWrapperDesc *d) {
         CK(dupload(s, &w.gate, d->h_gate, (size_t)p.N * gate_cols));
         CK(cudaStreamSynchronize(s->stream));
     }
-    CK(dalloc(s, &w.obs, (size_t)p.N * w.Aw * w.D)); CK(dalloc(s, &w.reward, (size_t)p.N * w.Aw));
+    CK(alloc_step_result(s, w.Aw, w.D));                         // obs and reward live inside the packed step result
+    w.obs = reinterpret_cast<float *>(s->d_result + s->rl.obs_off); w.reward = reinterpret_cast<float *>(s->d_result + s->rl.reward_off);
     CK(dalloc(s, &w.sums, (size_t)16)); CK(dalloc(s, &w.last, (size_t)p.N * 4));
     CK(dalloc(s, &w.delayed_reset, (size_t)p.N)); CK(dalloc(s, &w.has_last, (size_t)p.N));
     s->wrap = w;
-    set_buf(s, MQE_BUF_WRAP_OBS, w.obs, 4, p.N, w.Aw, w.D);
-    set_buf(s, MQE_BUF_WRAP_REWARD, w.reward, 4, p.N, w.Aw);
     set_buf(s, MQE_BUF_WRAP_SUMS, w.sums, 8, 16);
     return MQE_OK;
 }
@@ -431,7 +494,19 @@ int mqe_sim_wrapper_reset(MqeSim *s) {
 
 int mqe_sim_get_buffer(MqeSim *s, int which, void **d_ptr, int64_t shape[4], int32_t *elem_size) {
     if (!s || which < 0 || which >= MQE_BUF_COUNT) return fail(MQE_ERR_INVALID, "bad buffer id");
-    if (!s->bufs[which].ptr) return fail(MQE_ERR_INVALID, "buffer not allocated (task-wrapper buffers exist after mqe_sim_set_wrapper)");
+    if (!s->bufs[which].ptr && which >= MQE_BUF_SUBSTEP_TORQUES && which <= MQE_BUF_SUBSTEP_EXCEED) {
+        // post_decimation_step logs (legged_robot.py:112-115): first request switches them on for every following step
+        CK(cudaSetDevice(s->device));
+        CK(cudaStreamSynchronize(s->stream));
+        DevParams &p = s->p;
+        const size_t n = (size_t)p.N * p.decimation * 12 * p.A;
+        CK(dalloc(s, &p.sub_tau, n)); CK(dalloc(s, &p.sub_qd, n)); CK(dalloc(s, &p.sub_exceed, n));
+        set_buf(s, MQE_BUF_SUBSTEP_TORQUES, p.sub_tau, 4, p.N, p.decimation, 12 * p.A);
+        set_buf(s, MQE_BUF_SUBSTEP_DOF_VEL, p.sub_qd, 4, p.N, p.decimation, 12 * p.A);
+        set_buf(s, MQE_BUF_SUBSTEP_EXCEED, p.sub_exceed, 1, p.N, p.decimation, 12 * p.A);
+        drop_graphs(s);                                            // kernel arguments changed
+    }
+    if (!s->bufs[which].ptr) return fail(MQE_ERR_INVALID, "buffer not allocated (task-wrapper buffers exist after mqe_sim_set_wrapper; MQE_BUF_HISTORY only with MQE_POLICY_FP32, the bf16 planes otherwise)");
     if (d_ptr) *d_ptr = s->bufs[which].ptr;
     if (shape) for (int i = 0; i < 4; i++) shape[i] = s->bufs[which].shape[i];
     if (elem_size) *elem_size = s->bufs[which].elem;
@@ -446,7 +521,8 @@ int mqe_sim_reset(MqeSim *s) {
     CK(mqe_launch_reset_all(s->p, s->stream));
     s->launches += 1;
     if (s->wrap.kind != MQE_WRAP_NONE) { CK(mqe_launch_task_gather(s->p, s->wrap, 1, s->stream)); s->launches += 1; }
-    return MQE_OK;
+    if (s->gather.world) s->gather_seq++;
+    return exchange_impl(s);                                      // ranks reset together: the global observation is exchanged as after a step
 }
 
 static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, const unsigned short *lo, int head, int rows, float *latent, float *act) {
@@ -493,7 +569,7 @@ int mqe_sim_policy(MqeSim *s, const float *d_actions) {
 static int substeps_impl(MqeSim *s, int count, bool zero_stats) {
     if (!s || count <= 0) return fail(MQE_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(s->device));
-    if (zero_stats) CK(cudaMemsetAsync(s->p.stats, 0, 8 * sizeof(int), s->stream));   // inside mqe_sim_step k_policy_finish did it
+    if (zero_stats) CK(cudaMemsetAsync(s->p.stats, 0, 5 * sizeof(int), s->stream));   // inside mqe_sim_step k_policy_finish did it
     CK(mqe_launch_substeps(s->p, count, s->maxpair, s->stream));
     s->launches += 1;
     return MQE_OK;
@@ -513,27 +589,51 @@ int mqe_sim_post_physics(MqeSim *s) {
     return rc;
 }
 
-static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
-    int rc = policy_impl(s, d_actions, device_ctr);
-    if (rc != MQE_OK) return rc;
-    rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: k_policy_finish zeroed the statistics
-    if (rc != MQE_OK) return rc;
-    rc = post_impl(s, device_ctr);
-    if (rc != MQE_OK || s->wrap.kind == MQE_WRAP_NONE) return rc;
-    CK(mqe_launch_task_gather(s->p, s->wrap, 0, s->stream));
+static int exchange_impl(MqeSim *s) {                    // peer exchange of the step result: last kernel of a step / reset
+    if (!s->gather.world) return MQE_OK;
+    CK(mqe_launch_gather_exchange(s->p, s->gather, s->stream));
     s->launches += 1;
     return MQE_OK;
 }
+static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
+    int rc;
+    if (s->p.control_type == 0) rc = policy_impl(s, d_actions, device_ctr);
+    else {                                               // 'P' / 'V' / 'T': the caller's joint actions are the actions (go1.py:43-45)
+        CK(mqe_launch_joint_actions(s->p, d_actions, s->stream));
+        s->launches += 1;
+        rc = MQE_OK;
+    }
+    if (rc != MQE_OK) return rc;
+    rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: k_policy_finish / k_joint_actions zeroed the statistics
+    if (rc != MQE_OK) return rc;
+    rc = post_impl(s, device_ctr);
+    if (rc != MQE_OK) return rc;
+    if (s->wrap.kind != MQE_WRAP_NONE) {
+        CK(mqe_launch_task_gather(s->p, s->wrap, 0, s->stream));
+        s->launches += 1;
+    }
+    return exchange_impl(s);
+}
 
+static int step_any(MqeSim *s, const float *d_actions);
 int mqe_sim_step(MqeSim *s, const float *d_actions) {
     if (!s || !d_actions) return fail(MQE_ERR_INVALID, "null argument");
+    if (s->p.control_type != 0) return fail(MQE_ERR_UNSUPPORTED, "control_type P / V / T takes [N][12A] joint actions: call mqe_sim_step_joint (go1.py:43-45)");
+    return step_any(s, d_actions);
+}
+int mqe_sim_step_joint(MqeSim *s, const float *d_joint_actions) {
+    if (!s || !d_joint_actions) return fail(MQE_ERR_INVALID, "null argument");
+    if (s->p.control_type == 0) return fail(MQE_ERR_UNSUPPORTED, "control_type C takes [N][A][3] commands for the walk policy: call mqe_sim_step");
+    return step_any(s, d_joint_actions);
+}
+static int step_any(MqeSim *s, const float *d_actions) {
     CK(cudaSetDevice(s->device));
     int rc;
     if (!s->use_graph || s->plain_steps < 2) {           // first steps run plainly (lazy function attributes, module load)
         rc = step_plain(s, d_actions, false);
         s->plain_steps++;
     } else {
-        const size_t na = (size_t)s->p.N * s->actrl * 3 * sizeof(float);
+        const size_t na = s->action_bytes();
         if (d_actions != s->d_actions_stage) CK(cudaMemcpyAsync(s->d_actions_stage, d_actions, na, cudaMemcpyDeviceToDevice, s->stream));
         MqeSim::StepGraph *g = nullptr;
         for (auto &c : s->graphs)
@@ -564,7 +664,7 @@ int mqe_sim_step(MqeSim *s, const float *d_actions) {
         s->launches += g->launches;
         rc = MQE_OK;
     }
-    if (rc == MQE_OK) { s->head = (s->head + 1) % MQE_HIST_FRAMES; s->step_count++; }
+    if (rc == MQE_OK) { s->head = (s->head + 1) % MQE_HIST_FRAMES; s->step_count++; if (s->gather.world) s->gather_seq++; }
     return rc;
 }
 
@@ -589,23 +689,114 @@ int mqe_sim_unpin_host(MqeSim *s, void *ptr) {
     return fail(MQE_ERR_INVALID, "range was not pinned by this handle");
 }
 
+int mqe_sim_step_result_layout(MqeSim *s, MqeStepResultLayout *out) {
+    if (!s || !out) return fail(MQE_ERR_INVALID, "null argument");
+    *out = s->rl;
+    return MQE_OK;
+}
+
+int mqe_sim_result_parity(MqeSim *s) { return s ? (int)(s->step_count & 1u) : -1; }
+
+int mqe_sim_step_host_result(MqeSim *s, const float *h_actions, void *h_result) {
+    if (!s || !h_actions || !h_result) return fail(MQE_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(s->device));
+    const size_t na = s->action_bytes(), nr = (size_t)s->rl.total_bytes;
+    const bool pa = s->is_pinned(h_actions, na), pr = s->is_pinned(h_result, nr);
+    if (!pa) memcpy(s->h_actions, h_actions, na);
+    CK(cudaMemcpyAsync(s->d_actions_stage, pa ? h_actions : s->h_actions, na, cudaMemcpyHostToDevice, s->stream));
+    int rc = step_any(s, s->d_actions_stage);
+    if (rc != MQE_OK) return rc;
+    CK(cudaMemcpyAsync(pr ? h_result : (void *)s->h_result, s->d_result + (size_t)(s->step_count & 1u) * nr, nr, cudaMemcpyDeviceToHost, s->stream));     // ONE copy: obs | reward | done
+    CK(cudaStreamSynchronize(s->stream));
+    if (!pr) memcpy(h_result, s->h_result, nr);
+    return MQE_OK;
+}
+
 int mqe_sim_step_host(MqeSim *s, const float *h_actions, float *h_obs, uint8_t *h_reset) {
     if (!s || !h_actions) return fail(MQE_ERR_INVALID, "null argument");
     CK(cudaSetDevice(s->device));
-    const size_t na = (size_t)s->p.N * s->actrl * 3 * sizeof(float);
+    const size_t na = s->action_bytes();
     const size_t no = (size_t)s->M * MQE_OBS_FLOATS * sizeof(float);
     // buffers the caller pinned (mqe_sim_pin_host) are DMA sources / targets themselves; anything else goes through the
     // handle's own pinned staging buffers with one extra host copy each way
     const bool pa = s->is_pinned(h_actions, na), po = h_obs && s->is_pinned(h_obs, no), pr = h_reset && s->is_pinned(h_reset, s->p.N);
     if (!pa) memcpy(s->h_actions, h_actions, na);
     CK(cudaMemcpyAsync(s->d_actions_stage, pa ? h_actions : s->h_actions, na, cudaMemcpyHostToDevice, s->stream));
-    int rc = mqe_sim_step(s, s->d_actions_stage);
+    int rc = step_any(s, s->d_actions_stage);
     if (rc != MQE_OK) return rc;
     if (h_obs) CK(cudaMemcpyAsync(po ? h_obs : s->h_obs, s->p.obs, no, cudaMemcpyDeviceToHost, s->stream));
     if (h_reset) CK(cudaMemcpyAsync(pr ? h_reset : s->h_reset, s->p.reset_buf, s->p.N, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     if (h_obs && !po) memcpy(h_obs, s->h_obs, no);
     if (h_reset && !pr) memcpy(h_reset, s->h_reset, s->p.N);
+    return MQE_OK;
+}
+
+// ---- peer exchange of the step result (gather.cu) ----
+int mqe_sim_gather_init(MqeSim *s, int rank, int world, void *ipc_handle_out) {
+    if (!s || !ipc_handle_out) return fail(MQE_ERR_INVALID, "null argument");
+    if (world < 1 || world > MQE_MAX_RANKS || rank < 0 || rank >= world) return fail(MQE_ERR_INVALID, "rank / world out of range (world <= 16)");
+    if (s->gather.world) return fail(MQE_ERR_INVALID, "gather already initialised");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    const MqeStepResultLayout &L = s->rl;
+    if ((L.obs_bytes | L.reward_bytes | L.done_bytes) & 15) return fail(MQE_ERR_UNSUPPORTED, "peer exchange needs 16-byte multiples per field (num_envs per rank % 16 == 0): use an NCCL gather");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    drop_graphs(s);
+    GatherParams g = {};
+    g.rank = rank; g.world = world;
+    g.seg_src[0] = L.obs_off; g.seg_bytes[0] = L.obs_bytes; g.seg_dst[0] = 0;
+    g.seg_src[1] = L.reward_off; g.seg_bytes[1] = L.reward_bytes; g.seg_dst[1] = (long long)world * L.obs_bytes;
+    g.seg_src[2] = L.done_off; g.seg_bytes[2] = L.done_bytes; g.seg_dst[2] = (long long)world * (L.obs_bytes + L.reward_bytes);
+    g.parity_bytes = (long long)world * (L.obs_bytes + L.reward_bytes + L.done_bytes);
+    g.flags_off = 2 * g.parity_bytes;
+    g.src = s->d_result;
+    const size_t total = (size_t)g.flags_off + 2 * MQE_MAX_RANKS * sizeof(unsigned int);
+    unsigned char *buf = nullptr;
+    CK(dalloc(s, &buf, total));                                   // a cudaMalloc allocation of its own: exportable
+    CK(dalloc(s, &g.blocks_done, (size_t)1));
+    CK(cudaStreamSynchronize(s->stream));
+    g.peer[rank] = buf;
+    s->gather_peers[rank] = buf;
+    CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(ipc_handle_out), buf));
+    s->gather = g;
+    s->gather.world = 0;                                          // armed by mqe_sim_gather_connect
+    s->gather.rank = rank;
+    s->gather_pending_world = world;
+    return MQE_OK;
+}
+int mqe_sim_gather_connect(MqeSim *s, const void *ipc_handles) {
+    if (!s || !ipc_handles) return fail(MQE_ERR_INVALID, "null argument");
+    if (!s->gather_pending_world) return fail(MQE_ERR_INVALID, "mqe_sim_gather_init first");
+    CK(cudaSetDevice(s->device));
+    const int world = s->gather_pending_world, rank = s->gather.rank;
+    const cudaIpcMemHandle_t *h = reinterpret_cast<const cudaIpcMemHandle_t *>(ipc_handles);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        void *ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h[r], cudaIpcMemLazyEnablePeerAccess));
+        s->gather_peers[r] = ptr;
+        s->gather.peer[r] = (unsigned char *)ptr;
+    }
+    s->gather.world = world;
+    s->gather_pending_world = 0;
+    drop_graphs(s);
+    return MQE_OK;
+}
+int mqe_sim_gather_parity(MqeSim *s) { return (s && s->gather.world) ? (int)(s->gather_seq & 1ull) : -1; }
+int mqe_sim_gather_view(MqeSim *s, int parity, void **d_ptr, MqeStepResultLayout *gl) {
+    if (!s || !s->gather.world) return fail(MQE_ERR_INVALID, "peer exchange not connected");
+    if (parity < 0 || parity > 1) return fail(MQE_ERR_INVALID, "parity must be 0 or 1");
+    const GatherParams &g = s->gather;
+    if (d_ptr) *d_ptr = g.peer[g.rank] + (long long)parity * g.parity_bytes;
+    if (gl) {
+        const MqeStepResultLayout &L = s->rl;
+        gl->num_envs = L.num_envs * g.world; gl->Aw = L.Aw; gl->D = L.D; gl->reserved = 0;
+        gl->obs_off = g.seg_dst[0]; gl->obs_bytes = L.obs_bytes * g.world;
+        gl->reward_off = g.seg_dst[1]; gl->reward_bytes = L.reward_bytes * g.world;
+        gl->done_off = g.seg_dst[2]; gl->done_bytes = L.done_bytes * g.world;
+        gl->total_bytes = g.parity_bytes;
+    }
     return MQE_OK;
 }
 
@@ -637,7 +828,7 @@ int mqe_policy_forward(MqeSim *s, const float *d_history, int rows, float *d_lat
         if (s->tmp_hi) cudaFree(s->tmp_hi);
         if (s->tmp_lo) cudaFree(s->tmp_lo);
         s->tmp_ring = nullptr; s->tmp_hi = s->tmp_lo = nullptr; s->tmp_rows = 0;
-        CK(cudaMalloc(&s->tmp_ring, ring * sizeof(float)));
+        if (s->p.policy_mode == MQE_POLICY_FP32) CK(cudaMalloc(&s->tmp_ring, ring * sizeof(float)));
         if (s->p.policy_mode != MQE_POLICY_FP32) {
             const size_t rtc = (size_t)((rows + 127) / 128) * 128 * MQE_HIST_FRAMES * MQE_HIST_PAD * 2;
             CK(cudaMalloc(&s->tmp_hi, rtc)); CK(cudaMalloc(&s->tmp_lo, rtc));

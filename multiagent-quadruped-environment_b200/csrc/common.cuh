@@ -35,7 +35,11 @@ struct DevParams {
     float npc_mass, npc_inertia, npc_radius, npc_halflen;
     float sheep_scale, sheep_rand, gate_x;
     float *lag_ring; int lag_n;                // action lag (go1.py:337-339): [N*A][lag_n][12] scaled actions, lag_n = lag_timesteps + 1; nullptr = off
-    int control_type; float kp, kd;            // cfg.control: 0 actuator net, 1 PD position, 2 torque
+    int control_type; float kp, kd;            // cfg.control: 0 actuator net, 1 PD position, 2 torque, 3 PD velocity
+    float *sub_tau, *sub_qd;                   // post_decimation_step logs [N][decimation][12A] (legged_robot.py:112-115); nullptr until asked for
+    unsigned char *sub_exceed; float soft_limit;
+    unsigned char *result_done;                // done flags inside half 0 of MQE_BUF_STEP_RESULT (written by k_post_physics / k_reset_all)
+    long long result_half;                     // bytes between the two halves of MQE_BUF_STEP_RESULT; half in use = policy steps done & 1
     int push_interval; float max_push_vel;     // domain_rand.push_robots
     const float *base_mass_add;                // [N*A] mass added to the base link (domain_rand.randomize_base_mass) or nullptr
     const float *mu_env;                       // [N] per-env friction (domain_rand.randomize_friction) or nullptr
@@ -64,7 +68,7 @@ struct DevParams {
     int cta_sync;                 // MQE_CTA_SYNC: 0 none, 1 per substep, 2 also per phase
     int trace;                    // MQE_TRACE=1: also accumulate per-phase cycles into the trace rows
     int *stats;                   // [8]
-    int *ctr;                     // device-side step counters ([3] _compute_torques calls so far, [4] CTAs of k_substeps finished: action lag);
+    int *ctr;                     // device-side step counters ([3] _compute_torques calls so far, [4] CTAs of k_substeps finished: action lag; [5] peer exchanges done);
                                   // [0] ring slot that receives the next frame, [1] policy steps done
                                   // (sheep RNG key), [2] scratch (blocks of k_post_physics finished); let a captured CUDA graph of
                                   // the whole step be replayed with constant kernel arguments
@@ -78,11 +82,24 @@ struct WrapParams {
     int kind, D, Aw;              // MqeWrapperKind, observation floats per agent, agents the wrapper reports (football defender: 2 of 3)
     float scale[8];               // reward scales in the order of MqeWrapperDesc
     const float *gate;            // sheep: [N][2] gate position (env-relative); football defender: [N][3] gate position (world)
-    float *obs, *reward;          // [N][Aw][D], [N][Aw]
+    float *obs, *reward;          // [N][Aw][D], [N][Aw] inside half 0 of MQE_BUF_STEP_RESULT (+ DevParams.result_half for half 1)
     double *sums;                 // [16]: running sums of the reward terms, [8] = steps
     float *last;                  // sheep: [N][2] last flock centre; seesaw: [N][Aw] last x
     unsigned char *delayed_reset; // sheep: reset_buf of the previous step (go1_sheep_wrapper.py:116)
     int *has_last;                // [N]
+};
+
+// per-step exchange of the packed step result between the ranks of one node over NVLink peer memory (gather.cu)
+#define MQE_MAX_RANKS 16
+#define MQE_STAT_GATHER_TIMEOUT 5           // index into MQE_BUF_STATS: a peer's flag did not arrive within the bounded wait
+struct GatherParams {
+    int rank, world;                        // world 0: exchange off
+    unsigned char *peer[MQE_MAX_RANKS];     // receive buffer of every rank (peer[rank] is this rank's own allocation)
+    long long parity_bytes;                 // one parity half: [obs region | reward region | done region], each world x local bytes
+    long long flags_off;                    // u32 flags[2][MQE_MAX_RANKS] behind the two halves
+    long long seg_src[3], seg_bytes[3], seg_dst[3];   // local field offset in MQE_BUF_STEP_RESULT, its bytes (x16), region offset in a half
+    const unsigned char *src;               // this rank's MQE_BUF_STEP_RESULT (half 0)
+    int *blocks_done;                       // device scratch
 };
 
 // ---------------------------------------------------------------------------------------------- programmatic dependent launch

@@ -39,6 +39,9 @@ cudaError_t mqe_launch_task_gather(const DevParams &p, const WrapParams &w, int 
 cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const unsigned short *hist_hi,
                                         const unsigned short *hist_lo, int head, int M, int passes, const int *ctr, cudaStream_t st, cudaStream_t aux,
                                         cudaEvent_t ev_fork, cudaEvent_t ev_join, int *launches);
+cudaError_t mqe_launch_joint_actions(const DevParams &p, const float *joint_actions, cudaStream_t st);
+cudaError_t mqe_launch_gather_exchange(const DevParams &p, const GatherParams &g, cudaStream_t st);
+cudaError_t mqe_substeps_configure(const DevParams &p, int maxpair);
 size_t mqe_substeps_smem_bytes(int N, int A, int Pd, int E, int maxpair);
 size_t mqe_substeps_row_scratch_floats(int N, int A);
 size_t mqe_substeps_prow_scratch_floats(int N, int maxpair);

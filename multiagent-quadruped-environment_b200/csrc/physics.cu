@@ -516,12 +516,15 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         CTA_ALIGN(1);
         // ================================================================ P1: actuator network (go1.py:315-354, 369-380)
         if (active && is_robot && p.control_type != 0) {
-            // LeggedRobot._compute_torques (legged_robot.py:384-392): 'P' PD towards action * scale + default pose, 'T' scaled torques
+            // LeggedRobot._compute_torques (legged_robot.py:384-392): 'P' PD towards action * scale + default pose, 'T' scaled torques,
+            // 'V' PD on the joint velocity with the velocity of the previous POLICY step as the derivative reference (last_dof_vel)
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const int j = 3 * leg + k;
                 const float a = act[k] * p.action_scale;
-                const float t = p.control_type == 1 ? p.kp * (a + md->q_default[j] - q[k]) - p.kd * qd[k] : a;
+                float t = a;
+                if (p.control_type == 1) t = p.kp * (a + md->q_default[j] - q[k]) - p.kd * qd[k];
+                else if (p.control_type == 3) t = p.kp * (a - qd[k]) - p.kd * (qd[k] - p.last_dof_vel[m_idx * 12 + j]) / p.dt;
                 const float lim = md->tau_limit[j];
                 tau[k] = fminf(fmaxf(t, -lim), lim);
             }
@@ -1425,6 +1428,16 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 qd[k] = v;
                 q[k] += p.dt * v;
             }
+            if (p.sub_tau && active) {      // post_decimation_step (legged_robot.py:112-115): torques applied, then the refreshed dof state
+                const size_t o = ((size_t)env * nsub + sub) * (12 * A) + 12 * ag + 3 * leg;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int j = 3 * leg + k;
+                    const float mid = 0.5f * (md->q_lower[j] + md->q_upper[j]), half = 0.5f * (md->q_upper[j] - md->q_lower[j]) * p.soft_limit;
+                    p.sub_tau[o + k] = tau[k]; p.sub_qd[o + k] = qd[k];
+                    p.sub_exceed[o + k] = (unsigned char)((q[k] < mid - half) | (q[k] > mid + half));
+                }
+            }
         }
         if (is_npc && seesaw) {
             const float lim = p.geom[12];                                    // URDF joint velocity limit
@@ -1475,7 +1488,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
     }
     if (p.lag_ring && threadIdx.x == 0) {                                  // the last CTA to finish advances the call counter
         __threadfence();
-        if (atomicAdd(&p.ctr[4], 1) == (int)gridDim.x - 1) { p.ctr[4] = 0; p.ctr[3] += nsub; }
+        if (atomicAdd(&p.ctr[4], 1) == (int)gridDim.x - 1) { p.ctr[4] = 0; p.ctr[3] = (p.ctr[3] + nsub) % p.lag_n; }   // kept reduced: never overflows
     }
     // per-warp trace (MQE_BUF_WARP_TRACE): start / end on the global timer [ns], pair contacts and widest row count of the warp
     {
@@ -1521,11 +1534,16 @@ __global__ void k_actuator(const float *__restrict__ aw, const float *__restrict
 // = 147 CTAs x 7 warps = one wave on 148 SMs).
 struct SubstepPlan { int warps, spair, grid; size_t smem; };
 static SubstepPlan substeps_plan(int N, int A, int Pd, int E, int maxpair) {
-    static const int sms = [] {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
-        return n;
-    }();
+    static int sm_count[64] = {0};                    // per device ordinal (one process may own engines on several devices)
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+        if (sm_count[dev] == 0) {
+            int n = 0;
+            if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+            sm_count[dev] = n;
+        }
+        sms = sm_count[dev];
+    }
     const size_t budget = 227 * 1024, hdr = (size_t)physics_cta_header_floats() * 4;
     auto fit = [&](int sp) { int w = (int)((budget - hdr) / ((size_t)physics_warp_smem_floats(A, Pd, E, sp, maxpair) * 4)); return w > 8 ? 8 : w; };
     SubstepPlan pl;
@@ -1551,14 +1569,23 @@ extern "C" cudaError_t mqe_launch_actuator(const float *act_w, const float *x, i
     k_actuator<<<(rows + 127) / 128, 128, 0, st>>>(act_w, x, rows, out);
     return cudaGetLastError();
 }
+// cudaFuncSetAttribute applies to the CURRENT device: called once per engine at creation (api.cu), for that engine's device
+extern "C" cudaError_t mqe_substeps_configure(const DevParams &p, int maxpair) {
+    const SubstepPlan pl = substeps_plan(p.N, p.A, p.Pd, p.E, maxpair);
+    if (pl.warps < 1) return cudaErrorInvalidConfiguration;
+    static size_t configured[64] = {0};                // largest size asked for so far, per device ordinal
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || pl.smem > configured[dev]) {
+        e = cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = pl.smem;
+    }
+    return cudaSuccess;
+}
 extern "C" cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, cudaStream_t st) {
     const SubstepPlan pl = substeps_plan(p.N, p.A, p.Pd, p.E, maxpair);
     if (pl.warps < 1) return cudaErrorInvalidConfiguration;
-    static size_t configured = 0;
-    if (pl.smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-        if (e != cudaSuccess) return e;
-        configured = pl.smem;
-    }
     return launch_heavy(k_substeps, dim3(pl.grid), dim3(pl.warps * 32), pl.smem, st, p, nsub, maxpair, pl.spair, p.max_cand);
 }

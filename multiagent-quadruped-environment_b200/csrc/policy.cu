@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(256) k_policy_frame(DevParams p, const float *
     if (lane < 3) p.commands[m * 3 + lane] = cmd[lane];
     const float *ob = p.obs + (size_t)m * MQE_OBS_FLOATS;
     float *lo = p.loc_obs + (size_t)m * MQE_LOC_OBS;
-    float *ring = p.hist_f32 + (size_t)m * RING_ROW;
+    float *ring = p.hist_f32 ? p.hist_f32 + (size_t)m * RING_ROW : nullptr;     // fp32 ring: MQE_POLICY_FP32 only (the planes are the ring otherwise)
     if (p.hist_dirty[e]) {                                   // _reset_buffers zeroed this row's history
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = lane; i < RING_ROW / 4; i += 32)
-            if (i / (FRAME_PAD / 4) != head) reinterpret_cast<float4 *>(ring)[i] = z;
+        if (ring)
+            for (int i = lane; i < RING_ROW / 4; i += 32)
+                if (i / (FRAME_PAD / 4) != head) reinterpret_cast<float4 *>(ring)[i] = z;
         if (p.hist_hi) {                                     // pre-tiled planes: one 16-byte chunk per (slot, k-chunk)
             uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
             for (int i = lane; i < MQE_HIST_FRAMES * (FRAME_PAD / 8); i += 32) {
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) k_policy_frame(DevParams p, const float *
         else if (i < 66) v = p.loc_last2[m * 12 + i - 54];
         else if (i < 70) v = ob[MQE_OBS_CLOCK + i - 66];
         if (i < MQE_LOC_OBS) lo[i] = v;
-        ring[head * FRAME_PAD + i] = v;
+        if (ring) ring[head * FRAME_PAD + i] = v;
         if (p.hist_hi) {
             unsigned int b = __float_as_uint(v);
             unsigned int hi = (b + 0x7fffu + ((b >> 16) & 1u)) & 0xffff0000u;       // round-to-nearest-even bf16
@@ -119,8 +120,23 @@ __global__ void k_policy_finish(DevParams p, const float *__restrict__ act) {
         p.actions[t] = fminf(fmaxf(a, -p.clip_actions), p.clip_actions);
     }
     if (t < p.N) p.hist_dirty[t] = 0;
-    if (t < 8) p.stats[t] = 0;
+    if (t < 5) p.stats[t] = 0;                           // [5..7] are sticky (MQE_STAT_GATHER_TIMEOUT)
     if (t == 0) p.ctr[0] = (p.ctr[0] + 1) % MQE_HIST_FRAMES;  // nobody reads the slot counter after this point of the step                               // contact statistics of the step that follows (k_substeps accumulates)
+}
+
+// Go1.step() for control_type 'P' / 'V' / 'T' (go1.py:43-45 -> pre_physics_step, legged_robot.py:108-110): the caller's joint actions,
+// clipped to +-clip_actions, ARE `actions`; the walk policy is never evaluated
+__global__ void k_joint_actions(DevParams p, const float *__restrict__ joint_actions) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.N * p.A * 12) p.actions[t] = fminf(fmaxf(joint_actions[t], -p.clip_actions), p.clip_actions);
+    if (t < p.N) p.hist_dirty[t] = 0;
+    if (t < 5) p.stats[t] = 0;                           // [5..7] are sticky (MQE_STAT_GATHER_TIMEOUT)
+}
+extern "C" cudaError_t mqe_launch_joint_actions(const DevParams &p, const float *joint_actions, cudaStream_t st) {
+    const int n = p.N * p.A * 12;
+    return launch_pdl(k_joint_actions, dim3((n + 255) / 256), dim3(256), 0, st, p, joint_actions);
 }
 
 // ---------------------------------------------------------------------------------------------- fp32 SGEMM chain
@@ -197,7 +213,7 @@ __global__ void k_history_to_ring(const float *__restrict__ hist, float *__restr
     if (t >= (size_t)rows * RING_ROW) return;
     const int r = (int)(t / RING_ROW), k = (int)(t % RING_ROW), s = k / FRAME_PAD, i = k % FRAME_PAD;
     float v = i < MQE_LOC_OBS ? hist[(size_t)r * 2100 + s * MQE_LOC_OBS + i] : 0.f;
-    ring[t] = v;
+    if (ring) ring[t] = v;
     if (hi) {
         unsigned int b = __float_as_uint(v);
         unsigned int h = (b + 0x7fffu + ((b >> 16) & 1u)) & 0xffff0000u;

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
         p.base_lin_vel[m * 3] = lv.x; p.base_lin_vel[m * 3 + 1] = lv.y; p.base_lin_vel[m * 3 + 2] = lv.z;
         p.base_ang_vel[m * 3] = av.x; p.base_ang_vel[m * 3 + 1] = av.y; p.base_ang_vel[m * 3 + 2] = av.z;
         p.proj_grav[m * 3] = pg.x; p.proj_grav[m * 3 + 1] = pg.y; p.proj_grav[m * 3 + 2] = pg.z;
-        dev_gait_clock(p, m, dt_policy);
+        if (p.control_type == 0) dev_gait_clock(p, m, dt_policy);     // _step_contact_targets runs for control_type 'C' only (go1.py:241)
         // _push_robots (go1.py:237-238, legged_robot.py:472-477): common_step_counter % push_interval == 0 -> every robot's base
         // velocity x, y is redrawn; it takes effect in the next physics step (the derived base quantities above are pre-push)
         if (p.push_interval > 0 && ((step_count + 1u) % (unsigned)p.push_interval) == 0u) {
@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
             for (int i = e * A * 12; i < (e + 1) * A * 12; i++) { p.err1[i] = p.err2[i] = p.vel1[i] = p.vel2[i] = 0.f; p.loc_last[i] = p.loc_last2[i] = 0.f; p.actions[i] = 0.f; }
         }
         p.reset_buf[e] = (unsigned char)reset;
+        if (p.result_done) p.result_done[(long long)((step_count + 1u) & 1u) * p.result_half + e] = (unsigned char)reset;     // the learner's copy
         // legged_robot.py:164-169 binds reset_buf and collide_buf to ONE tensor and ORs every later cause in place, so the
         // reference's collide_buf equals the full reset mask whenever base contacts terminate
         if (p.term_mask & 16) p.collide_buf[e] = (unsigned char)reset;
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(128) k_reset_all(DevParams p) {
     if (e >= p.N) return;
     dev_env_reset(p, e);
     dev_env_observations(p, e);
+    if (p.result_done) p.result_done[(long long)(p.ctr[1] & 1) * p.result_half + e] = 1;
 }
 
 // gym.set_actor_root_state_tensor_indexed / set_dof_state_tensor_indexed for hosts that stage state elsewhere

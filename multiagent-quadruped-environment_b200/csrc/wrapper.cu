@@ -17,8 +17,13 @@ __device__ __forceinline__ void base_info(const DevParams &p, int m, float *o) {
 
 // mode 0: step (obs + reward + running sums); mode 1: wrapper reset() (obs only; sheep forgets its last flock centre)
 __global__ void __launch_bounds__(WRAP_THREADS) k_task_gather(DevParams p, WrapParams w, int mode) {
+    pdl_launch_dependents();
+    pdl_wait();                                         // launched with the PDL attribute at MQE_PDL=2: k_post_physics must have finished
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int A = p.A, P = p.P, Aw = w.Aw, D = w.D;
+    // half of the double-buffered step result this step writes: k_post_physics has already advanced ctr[1] (reset: the current half)
+    const long long half_f = (long long)(p.ctr[1] & 1) * (p.result_half >> 2);
+    w.obs += half_f; w.reward += half_f;
     float term[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (e < p.N) {
         float bi[4][6];

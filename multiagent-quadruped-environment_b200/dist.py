@@ -67,3 +67,40 @@ class StepGather:
             for r, (a, b) in enumerate(self.ranges):
                 out[a:b].copy_(allbuf[r * big:r * big + (b - a)])
         return out
+
+
+class PeerStepExchange:
+    """The per-step exchange as part of the engine's step graph (csrc/gather.cu): every rank stores its packed step result (task-wrapper
+    observation | reward | done) straight into every peer's receive buffer over NVLink peer memory; no NCCL call, no extra launch from
+    the host.  `torch.distributed` is used once, to hand the 64-byte IPC handles around.  Equal shards with num_envs % 16 == 0.
+
+        ex = PeerStepExchange(env.engine)          # after the task wrapper has been set up (first env.reset())
+        env.step(actions)                          # exchange happens inside the step
+        obs, reward, done = ex.latest()            # GLOBAL tensors [N_global, A, D], [N_global, A], [N_global] (zero-copy views)
+    """
+
+    def __init__(self, engine, group=None):
+        self.engine = engine
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        handle = engine.gather_init(self.rank, self.world)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, handle, group=group)
+        else:
+            handles[0] = handle
+        engine.gather_connect(handles)
+        from . import engine as E
+        self._views = []
+        for parity in (0, 1):
+            buf, L = engine.gather_view(parity)
+            self._views.append(E.Engine.split_result(buf, L))
+        self.layout = L
+
+    def latest(self):
+        return self._views[self.engine.gather_parity()]
+
+    def timed_out(self) -> bool:
+        """True if a peer's flag ever failed to arrive within the kernel's bounded wait (sticky; MQE_BUF_STATS[5])."""
+        from . import engine as E
+        return int(self.engine.tensor(E.BUF_STATS)[E.STAT_GATHER_TIMEOUT].item()) != 0

@@ -16,14 +16,17 @@ from .model import MAX_CAPS, MAX_PROBES, RobotModelC  # noqa: F401
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libmqe_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 LOC_OBS = 70
 OBS_FLOATS = 71
 
 (BUF_ROOT_STATES, BUF_DOF_STATES, BUF_CONTACT_FORCES, BUF_TORQUES, BUF_ACTIONS, BUF_LAST_ACTIONS, BUF_OBS,
  BUF_BASE_LIN_VEL, BUF_BASE_ANG_VEL, BUF_PROJ_GRAVITY, BUF_RESET, BUF_TIMEOUT, BUF_COLLIDE, BUF_ROLL_TERM,
  BUF_PITCH_TERM, BUF_ZLOW_TERM, BUF_ZHIGH_TERM, BUF_EPISODE_LENGTH, BUF_COMMANDS, BUF_LOC_OBS, BUF_LOC_ACTION,
- BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_CLOCK, BUF_WRAP_OBS, BUF_WRAP_REWARD, BUF_WRAP_SUMS, BUF_WARP_TRACE, BUF_COUNT) = range(31)
+ BUF_GAIT, BUF_HISTORY, BUF_SHEEP_STATS, BUF_STATS, BUF_CLOCK, BUF_WRAP_SUMS, BUF_WARP_TRACE,
+ BUF_SUBSTEP_TORQUES, BUF_SUBSTEP_DOF_VEL, BUF_SUBSTEP_EXCEED, BUF_HISTORY_HI, BUF_HISTORY_LO, BUF_STEP_RESULT, BUF_COUNT) = range(35)
+STAT_GATHER_TIMEOUT = 5
+CONTROL_TYPES = {"C": 0, "control_net": 0, "P": 1, "T": 2, "V": 3}
 
 OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
     "base_pos": (0, 3), "base_quat": (3, 7), "dof_pos": (7, 19), "dof_vel": (19, 31), "lin_vel": (31, 34),
@@ -33,6 +36,13 @@ OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
 
 NPC_NONE, NPC_RIGID, NPC_SEESAW, NPC_BOX, NPC_PLATFORM = 0, 1, 2, 3, 4
 WRAP_NONE, WRAP_SHEEP, WRAP_SEESAW, WRAP_FOOTBALL_DEFENDER = 0, 1, 2, 3
+
+
+class StepResultLayoutC(ctypes.Structure):
+    """MqeStepResultLayout (include/mqe_b200.h): byte offsets of obs | reward | done inside the packed step result."""
+    _fields_ = [("obs_off", ctypes.c_int64), ("obs_bytes", ctypes.c_int64), ("reward_off", ctypes.c_int64), ("reward_bytes", ctypes.c_int64),
+                ("done_off", ctypes.c_int64), ("done_bytes", ctypes.c_int64), ("total_bytes", ctypes.c_int64),
+                ("num_envs", ctypes.c_int32), ("Aw", ctypes.c_int32), ("D", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class WrapperDescC(ctypes.Structure):
@@ -96,7 +106,7 @@ class SimDescC(ctypes.Structure):
         ("seed", ctypes.c_uint64),
         ("sdf_nx", ctypes.c_int32), ("sdf_ny", ctypes.c_int32), ("sdf_cell", ctypes.c_float), ("push_interval", ctypes.c_int32),
         ("control_type", ctypes.c_int32), ("stiffness", ctypes.c_float), ("damping", ctypes.c_float),
-        ("lag_enabled", ctypes.c_int32), ("lag_timesteps", ctypes.c_int32),
+        ("lag_enabled", ctypes.c_int32), ("lag_timesteps", ctypes.c_int32), ("soft_dof_pos_limit", ctypes.c_float),
         ("h_sdf", _fp), ("h_env_origins", _fp), ("h_agent_origins", _fp), ("h_base_init_state", _fp),
         ("h_npc_init_state", _fp), ("h_npc_dof_default", _fp), ("h_base_added_mass", _fp), ("h_env_friction", _fp),
         ("model", RobotModelC),
@@ -152,6 +162,14 @@ def load_library(path=None):
     lib.mqe_sim_reset.argtypes = [vp]
     lib.mqe_sim_step.argtypes = [vp, vp]
     lib.mqe_sim_step_host.argtypes = [vp, vp, vp, vp]
+    lib.mqe_sim_step_joint.argtypes = [vp, vp]
+    lib.mqe_sim_step_result_layout.argtypes = [vp, ctypes.POINTER(StepResultLayoutC)]
+    lib.mqe_sim_step_host_result.argtypes = [vp, vp, vp]
+    lib.mqe_sim_result_parity.argtypes = [vp]
+    lib.mqe_sim_gather_init.argtypes = [vp, i32, i32, vp]
+    lib.mqe_sim_gather_connect.argtypes = [vp, vp]
+    lib.mqe_sim_gather_parity.argtypes = [vp]
+    lib.mqe_sim_gather_view.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(StepResultLayoutC)]
     lib.mqe_sim_set_wrapper.argtypes = [vp, vp]
     lib.mqe_sim_wrapper_reset.argtypes = [vp]
     lib.mqe_sim_pin_host.argtypes = [vp, vp, ctypes.c_size_t]
@@ -178,6 +196,7 @@ EXPORTED_SYMBOLS = [
     "mqe_sim_set_wrapper", "mqe_sim_wrapper_reset", "mqe_sim_get_buffer", "mqe_sim_reset", "mqe_sim_step", "mqe_sim_step_host", "mqe_sim_pin_host", "mqe_sim_unpin_host", "mqe_sim_policy", "mqe_sim_substeps",
     "mqe_sim_post_physics", "mqe_sim_set_root_indexed", "mqe_sim_set_dof_indexed", "mqe_policy_forward",
     "mqe_actuator_forward", "mqe_sim_history_head", "mqe_sim_synchronize", "mqe_sim_launch_count",
+    "mqe_sim_step_joint", "mqe_sim_step_result_layout", "mqe_sim_step_host_result", "mqe_sim_result_parity", "mqe_sim_gather_init", "mqe_sim_gather_connect", "mqe_sim_gather_view", "mqe_sim_gather_parity",
 ]
 
 
@@ -189,8 +208,8 @@ class _DevArray:
         self._owner = owner
 
 
-_TYPESTR = {("f", 4): "<f4", ("f", 8): "<f8", ("u", 1): "|u1", ("i", 8): "<i8", ("i", 4): "<i4", ("h", 2): "<u2"}
-_BUF_KIND = {BUF_RESET: "u", BUF_TIMEOUT: "u", BUF_COLLIDE: "u", BUF_ROLL_TERM: "u", BUF_PITCH_TERM: "u",
+_TYPESTR = {("f", 4): "<f4", ("f", 8): "<f8", ("u", 1): "|u1", ("i", 8): "<i8", ("i", 4): "<i4", ("h", 2): "<i2"}
+_BUF_KIND = {BUF_SUBSTEP_EXCEED: "u", BUF_HISTORY_HI: "h", BUF_HISTORY_LO: "h", BUF_STEP_RESULT: "u", BUF_RESET: "u", BUF_TIMEOUT: "u", BUF_COLLIDE: "u", BUF_ROLL_TERM: "u", BUF_PITCH_TERM: "u",
              BUF_ZLOW_TERM: "u", BUF_ZHIGH_TERM: "u", BUF_EPISODE_LENGTH: "i", BUF_STATS: "i", BUF_WARP_TRACE: "i"}
 
 
@@ -250,6 +269,66 @@ class Engine:
     def step(self, actions_ptr: int):
         self._check(self.lib.mqe_sim_step(self.h, ctypes.c_void_p(actions_ptr)))
 
+    def step_joint(self, joint_actions_ptr: int):
+        """control_type 'P' / 'V' / 'T': [N][12A] joint actions (go1.py:43-45)."""
+        self._check(self.lib.mqe_sim_step_joint(self.h, ctypes.c_void_p(joint_actions_ptr)))
+
+    # -- packed step result (what the learner reads: wrapper obs | reward | done) ---------------------
+    def result_layout(self) -> StepResultLayoutC:
+        L = StepResultLayoutC()
+        self._check(self.lib.mqe_sim_step_result_layout(self.h, ctypes.byref(L)))
+        return L
+
+    def result_parity(self) -> int:
+        """Half of BUF_STEP_RESULT ([2, total_bytes]) holding the latest step's result."""
+        return int(self.lib.mqe_sim_result_parity(self.h))
+
+    def result_views(self):
+        """[(obs, reward, done) torch views of half 0, ... of half 1] -- zero-copy; the engine alternates halves every step."""
+        buf, L = self.tensor(BUF_STEP_RESULT), self.result_layout()
+        return [self.split_result(buf[h], L) for h in (0, 1)]
+
+    @staticmethod
+    def split_result(buf, L):
+        """Views (obs [N, Aw, D] f32, reward [N, Aw] f32, done [N] bool) into a packed result held in a numpy u8 array or a torch u8 tensor."""
+        N, Aw, D = L.num_envs, L.Aw, L.D
+        if isinstance(buf, np.ndarray):
+            obs = buf[L.obs_off:L.obs_off + L.obs_bytes].view(np.float32).reshape(N, Aw, D)
+            rew = buf[L.reward_off:L.reward_off + L.reward_bytes].view(np.float32).reshape(N, Aw)
+            done = buf[L.done_off:L.done_off + L.done_bytes].view(np.bool_)
+        else:
+            import torch
+            obs = buf[L.obs_off:L.obs_off + L.obs_bytes].view(torch.float32).view(N, Aw, D)
+            rew = buf[L.reward_off:L.reward_off + L.reward_bytes].view(torch.float32).view(N, Aw)
+            done = buf[L.done_off:L.done_off + L.done_bytes].view(torch.bool)
+        return obs, rew, done
+
+    def step_host_result(self, h_actions: np.ndarray, h_result: np.ndarray):
+        """H2D of the actions, one step, ONE D2H of the packed result (mqe_sim_step_host_result); blocks until it has landed."""
+        self._check(self.lib.mqe_sim_step_host_result(self.h, h_actions.ctypes.data_as(ctypes.c_void_p), h_result.ctypes.data_as(ctypes.c_void_p)))
+
+    # -- peer exchange of the step result over NVLink (mqe_sim_gather_*) ------------------------------
+    def gather_init(self, rank: int, world: int) -> bytes:
+        h = (ctypes.c_ubyte * 64)()
+        self._check(self.lib.mqe_sim_gather_init(self.h, rank, world, ctypes.cast(h, ctypes.c_void_p)))
+        return bytes(h)
+
+    def gather_connect(self, handles):
+        blob = b"".join(handles)
+        self._check(self.lib.mqe_sim_gather_connect(self.h, ctypes.cast(ctypes.c_char_p(blob), ctypes.c_void_p)))
+
+    def gather_parity(self) -> int:
+        return int(self.lib.mqe_sim_gather_parity(self.h))
+
+    def gather_view(self, parity: int):
+        """(torch u8 view of the global result half `parity`, its layout)."""
+        import torch
+        ptr = ctypes.c_void_p()
+        L = StepResultLayoutC()
+        self._check(self.lib.mqe_sim_gather_view(self.h, parity, ctypes.byref(ptr), ctypes.byref(L)))
+        arr = _DevArray(ptr.value, [int(L.total_bytes)], "|u1", self)
+        return torch.as_tensor(arr, device=f"cuda:{self.device}"), L
+
     def set_wrapper(self, kind: int, scales, gate: np.ndarray | None = None):
         """Fuse a task wrapper's obs / reward gather into the step (mqe_sim_set_wrapper)."""
         d = WrapperDescC()
@@ -260,7 +339,7 @@ class Engine:
             gate = np.ascontiguousarray(gate, dtype=np.float32)
             d.h_gate = gate.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
         self._check(self.lib.mqe_sim_set_wrapper(self.h, ctypes.byref(d)))
-        for b in (BUF_WRAP_OBS, BUF_WRAP_REWARD, BUF_WRAP_SUMS):
+        for b in (BUF_STEP_RESULT, BUF_WRAP_SUMS):
             self._views.pop(b, None)
 
     def wrapper_reset(self):
@@ -304,8 +383,16 @@ class Engine:
     def history(self):
         """history_locomotion_obs in the reference layout [M, 2100], oldest frame first (go1.py:102)."""
         import torch
-        ring = self.tensor(BUF_HISTORY)                                    # [M, 30, 80]
         order = [(self.history_head() + 1 + b) % 30 for b in range(30)]
+        if int(self.desc.policy_mode) == POLICY_FP32:
+            ring = self.tensor(BUF_HISTORY)                                # [M, 30, 80]
+        else:                                                              # tensor-core modes: the bf16 hi / lo planes are the ring
+            M = int(self.desc.num_envs) * int(self.desc.num_agents)
+            planes = []
+            for which in (BUF_HISTORY_HI, BUF_HISTORY_LO):                 # [tiles, 30, 10, 128, 8] -> [tiles*128, 30, 80]
+                t = self.tensor(which).view(-1, 30, 10, 128, 8).view(torch.bfloat16).float()
+                planes.append(t.permute(0, 3, 1, 2, 4).reshape(-1, 30, 80)[:M])
+            ring = planes[0] + planes[1]
         return ring[:, order, :LOC_OBS].reshape(ring.shape[0], -1)
 
     def policy_forward(self, history, want_latent=True):

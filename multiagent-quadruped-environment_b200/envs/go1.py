@@ -41,7 +41,13 @@ class Go1:
         self.cfg = cfg
         self.env_name = cfg.env.env_name
         self.sim_params, self.physics_engine, self.headless = sim_params, physics_engine, headless
-        dev = torch.device(sim_device if "cuda" in str(sim_device) else "cuda:0")
+        if "cuda" not in str(sim_device):
+            # BASELINE config C1 (`--sim_device cpu`, PhysX CPU pipeline) has no counterpart here: refusing is better than silently
+            # running the CUDA engine under a "cpu" label.  The CPU restatement lives in oracle/ and is test infrastructure only.
+            raise E.EngineError(f"sim_device={sim_device!r}: mqe_b200 has no CPU pipeline (sm_100a kernels only); pass sim_device='cuda:<i>'")
+        if "FLEX" in str(physics_engine).upper():                           # gymapi.SIM_FLEX: the reference only ever configures PhysX
+            raise E.EngineError(f"physics_engine={physics_engine!r}: only the PhysX-style rigid-body path is restated (cfg.sim.physx parameters)")
+        dev = torch.device(sim_device)
         if not torch.cuda.is_available():
             raise E.EngineError("mqe_b200 needs a CUDA device (sm_100a); there is no CPU pipeline")
         self.device = dev
@@ -68,6 +74,12 @@ class Go1:
         self.record_now = False
         self._ctrl_agents = self.num_agents - 1 if sc.desc.defender else self.num_agents
         self._scale_mode = None
+        self.control_type = str(cfg.control.control_type)
+        self._joint_control = int(sc.desc.control_type) != 0                # 'P' / 'V' / 'T': Go1.step takes [N, 12A] joint actions (go1.py:43-45)
+        if sim_params is not None:                                          # gymapi.SimParams the reference hands over: must agree with cfg.sim
+            dt = getattr(sim_params, "dt", None)
+            if dt is not None and abs(float(dt) - float(cfg.sim.dt)) > 1e-9:
+                raise E.EngineError(f"sim_params.dt = {dt} disagrees with cfg.sim.dt = {cfg.sim.dt}")
 
     # -- zero-copy views over the engine buffers (legged_robot.py:554-595) ------------------------------------
     def _bind_views(self):
@@ -171,7 +183,17 @@ class Go1:
             self.extras["time_outs"] = self.time_out_buf
 
     def step(self, action):
-        """go1.py:35-62.  action: [N*A_ctrl, 3] already scaled by the task wrapper."""
+        """go1.py:35-62.  control_type 'C': action [N*A_ctrl, 3] already scaled by the task wrapper.  'P' / 'V' / 'T' (go1.py:43-45):
+        action reshapes to [N, 12A] joint actions, clipped to +-clip_actions by pre_physics_step; the walk policy is not used."""
+        if self._joint_control:
+            a = action.reshape(self.num_envs, -1)
+            if a.dtype != torch.float32 or not a.is_contiguous() or a.device != self.device:
+                a = a.to(device=self.device, dtype=torch.float32).contiguous()
+            assert a.shape[1] == self.num_actions, f"expected [{self.num_envs}, {self.num_actions}] joint actions, got {tuple(action.shape)}"
+            self.engine.step_joint(a.data_ptr())
+            self._last_action_ref = a
+            self._reset_ids = None
+            return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
         self._set_scale("env")
         return self._step(action)
 
@@ -190,6 +212,20 @@ class Go1:
         self._last_action_ref = a                                          # keep alive until the kernels have read it
         self._reset_ids = None
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # post_decimation_step logs (legged_robot.py:112-115).  Nothing on the Go1 path reads them, so the engine only starts writing them
+    # once somebody asks: the first access allocates them (zeros, as in _init_buffers :623-625) and every following step fills them.
+    @property
+    def substep_torques(self):
+        return self.engine.tensor(E.BUF_SUBSTEP_TORQUES)
+
+    @property
+    def substep_dof_vel(self):
+        return self.engine.tensor(E.BUF_SUBSTEP_DOF_VEL)
+
+    @property
+    def substep_exceed_dof_pos_limits(self):
+        return self.engine.tensor(E.BUF_SUBSTEP_EXCEED).view(torch.bool)
 
     def get_observations(self):
         return self.obs_buf

@@ -47,14 +47,30 @@ class EmptyWrapper(Wrapper):
             return False
         from .. import engine as E
         eng.set_wrapper(kind, scales, None if gate is None else gate.detach().cpu().numpy())
-        self._wobs, self._wrew = eng.tensor(E.BUF_WRAP_OBS), eng.tensor(E.BUF_WRAP_REWARD)
+        self._halves = eng.result_views()                  # (obs, reward, done) views of the two halves of the packed step result
         self.reward_buffer = _FusedRewardBuffer(keys, eng.tensor(E.BUF_WRAP_SUMS))
         eng.wrapper_reset()
         return True
 
+    @property
+    def _wobs(self):
+        """Observation of the latest step / reset: a zero-copy view.  The engine alternates between two result buffers, so a returned
+        observation stays intact across the NEXT step() (the reference returns fresh tensors; a rollout loop may hold obs_t while
+        stepping) and is overwritten by the one after."""
+        return self._halves[self.env.engine.result_parity()][0]
+
     def _fused_step(self, action):
         _, _, termination, info = self.env.step_from_wrapper(action)
-        return self._wobs.clone(), self._wrew.clone(), termination, info
+        obs, reward, _ = self._halves[self.env.engine.result_parity()]
+        return obs, reward, termination, info
+
+    def step_host(self, h_actions, h_result):
+        """Host-buffer step for the numpy adapter (openrl_ws/utils.py:53-67): pinned H2D of the raw [N, A, 3] actions, one step, ONE D2H of
+        the packed (obs | reward | done) result.  Fused wrappers only."""
+        base = self.env
+        base._set_scale("wrapper")
+        base.engine.step_host_result(h_actions, h_result)
+        base._reset_ids = None
 
 
 class _FusedRewardBuffer(dict):
@@ -197,7 +213,7 @@ class Go1SheepWrapper(EmptyWrapper):
                                      {"success reward": 0, "contact punishment": 1, "sheep movement reward": 2, "mixed sheep reward": 3,
                                       "sheep pos var punishment": 4, "step count": 8}, gate=self.gate_pos[:, 0, :])
         if getattr(self, "_fused", False):
-            return self._wobs.clone()
+            return self._wobs
         obs, _ = self._obs(obs_buf)
         self.last_sheep_pos_avg = None
         return obs
@@ -265,7 +281,7 @@ class Go1SeesawWrapper(EmptyWrapper):
                                          s.agent_distance_punishment_scale, s.success_reward_scale, s.fall_punishment_scale],
                                      {"x movement reward": 0, "height reward": 1, "y punishment": 2, "contact punishment": 3,
                                       "agent distance punishment": 4, "success reward": 5, "fall punishment": 6, "step count": 8})
-        return self._wobs.clone() if self._fused else self._obs(obs_buf)
+        return self._wobs if self._fused else self._obs(obs_buf)
 
     def step(self, action):
         if getattr(self, "_fused", False):
@@ -339,7 +355,7 @@ class Go1FootballDefenderWrapper(EmptyWrapper):
         if not hasattr(self, "_fused"):
             self._fused = self._fuse(3, [self.goal_reward_scale, self.ball_gate_distance_reward_scale],
                                      {"goal reward": 0, "ball gate distance reward": 1, "step count": 8}, gate=self.gate_pos)
-        return self._wobs.clone() if self._fused else self._obs(obs_buf)[0]
+        return self._wobs if self._fused else self._obs(obs_buf)[0]
 
     def step(self, action):
         if getattr(self, "_fused", False):

@@ -1,58 +1,122 @@
 """numpy <-> device adapter the OpenRL scripts put around the env (`openrl_ws/utils.py:31-155`), SURVEY 8(f).2.
 
-Same class names and semantics (`mqe_openrl_wrapper`, `SingleAgentWrapper`, `make_env`), without importing
-`openrl` / `isaacgym`.  Differences that do not change returned values: the host copies go through ONE pinned staging
-buffer per direction (the reference calls `.cpu().numpy()` three times per step, `utils.py:59-61`), and
-`batch_rewards` reduces device scalars once per logging interval instead of once per term per step.
+Same class names and semantics (`make_env`, `mqe_openrl_wrapper`, `MATWrapper`, `SingleAgentWrapper`), without importing
+`openrl` / `isaacgym`.  What differs from the reference, none of it in the returned values:
+
+* **Host path.**  The reference does `torch.from_numpy(0.5 * actions).cuda()` and three `.cpu().numpy()` calls on pageable memory per
+  step (`utils.py:55-61`).  For the tasks whose wrapper gather is fused into the step graph (sheep, seesaw, football-defender) `step()`
+  goes through ONE C-ABI call, `mqe_sim_step_host_result`: the scaled actions are written into a page-locked buffer (H2D by DMA), and the
+  observation, reward and done flags come back as ONE packed device->host copy into a page-locked buffer.  The arrays handed back are
+  views into that buffer; two buffers alternate, so what step t returned stays intact until step t + 2 (the rollout loop of
+  `openrl_ws/train.py` copies them into its own storage right away).  Other wrappers take the torch path with pinned staging.
+* **Device-resident path** (`device_resident=True`, SURVEY 8(f).2 "keep obs/reward on device"): `step()` takes and returns CUDA tensors
+  (DLPack-exportable views of the engine's double-buffered step result); nothing crosses PCIe.
+* `batch_rewards` reads the device-side running sums once per logging interval instead of one `.cpu()` per reward term per step.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 
+from . import engine as E
 from .envs import make_mqe_env
 from .envs.gym_shim import Wrapper
 
 
-def make_env(args, custom_cfg=None, single_agent=False):
+def make_env(args, custom_cfg=None, single_agent=False, device_resident=False):
     """openrl_ws/utils.py:31-38"""
     env, env_cfg = make_mqe_env(args.task, args, custom_cfg=custom_cfg)
     if single_agent:
         env = SingleAgentWrapper(env)
-    return mqe_openrl_wrapper(env), env_cfg
+    return mqe_openrl_wrapper(env, device_resident=device_resident), env_cfg
 
 
 class mqe_openrl_wrapper(Wrapper):
     """openrl_ws/utils.py:40-90"""
 
-    def __init__(self, env):
+    def __init__(self, env, device_resident=False):
         super().__init__(env)
         self.agent_num = self.env.num_agents
         self.parallel_env_num = self.env.num_envs
         self.action_space = self.env.action_space
         self.observation_space = self.env.observation_space
+        self.device_resident = bool(device_resident)
+        self._task = env.env if isinstance(env, SingleAgentWrapper) else env       # the task wrapper (mqe.envs.wrappers.*)
+        self._host = None                                                           # pinned buffers of the fused host path
         self._h_act = None
+
+    # -- fused host path --------------------------------------------------------------------------------------------
+    def _host_ready(self):
+        """Page-locked action / result buffers, allocated once the task wrapper has switched to the fused gather (first reset())."""
+        if self._host is None and getattr(self._task, "_fused", False) and not self.device_resident:
+            eng = self._task.env.engine
+            L = eng.result_layout()
+            n, a = self._task.env.num_envs, self._task.env._ctrl_agents
+            bufs = {"act": eng.pin_host(np.zeros((n, a, 3), dtype=np.float32)),
+                    "res": [eng.pin_host(np.zeros(int(L.total_bytes), dtype=np.uint8)) for _ in range(2)], "L": L, "k": 0}
+            bufs["views"] = [E.Engine.split_result(r, L) for r in bufs["res"]]
+            self._host = bufs
+        return self._host is not None
 
     def reset(self, **kwargs):
         obs = self.env.reset()
-        return obs.cpu().numpy() if torch.is_tensor(obs) else obs
+        if self.device_resident or not torch.is_tensor(obs):
+            return obs
+        return obs.cpu().numpy()
 
     def step(self, actions, extra_data=None):
+        if self.device_resident:
+            return self._step_device(actions)
+        if self._host_ready():
+            return self._step_host(actions)
         dev = self.env.device
         a = np.ascontiguousarray(0.5 * np.asarray(actions, dtype=np.float32))
         if self._h_act is None or self._h_act.shape != a.shape:
             self._h_act = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
+            self._h_out = {}
         self._h_act.copy_(torch.from_numpy(a))
         d_act = self._h_act.to(dev, non_blocking=True).clip(-1, 1)
         obs, reward, termination, info = self.env.step(d_act)
         if torch.is_tensor(obs):
-            obs = obs.cpu().numpy()
-            rewards = reward.cpu().unsqueeze(-1).numpy()
+            obs = self._to_host("obs", obs)
+            rewards = self._to_host("rew", reward)[..., None]
         else:                                         # the shipped go1gate wrapper returns 0, 0 (go1_gate_wrapper.py:155)
             rewards = reward
-        dones = termination.cpu().unsqueeze(-1).repeat(1, self.agent_num).numpy().astype(bool)
-        infos = [{} for _ in range(dones.shape[0])]
-        return obs, rewards, dones, infos
+        done = self._to_host("done", termination)
+        torch.cuda.current_stream(dev).synchronize()
+        dones = np.repeat(done[:, None], self.agent_num, axis=1).astype(bool)
+        return (obs.copy() if isinstance(obs, np.ndarray) else obs), (rewards.copy() if isinstance(rewards, np.ndarray) else rewards), dones, [{} for _ in range(dones.shape[0])]
+
+    def _to_host(self, key, t):
+        """device tensor -> numpy through a pinned staging tensor (asynchronous copy; the caller synchronises once)"""
+        buf = self._h_out.get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = self._h_out[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
+        return buf.numpy()
+
+    def _step_host(self, actions):
+        h = self._host
+        np.multiply(np.asarray(actions, dtype=np.float32).reshape(h["act"].shape), 0.5, out=h["act"])    # utils.py:55; the +-1 clip is the frame kernel's
+        h["k"] ^= 1
+        k = h["k"]
+        self._task.step_host(h["act"], h["res"][k])
+        obs, rew, done = h["views"][k]
+        if isinstance(self.env, SingleAgentWrapper):                                 # utils.py:150-155
+            n = self.env.num_envs
+            obs, rew = obs.reshape(n, 1, -1), rew.reshape(n, 1)
+            done = np.repeat(done, self._task.num_agents)
+        rewards = rew[..., None]
+        dones = np.repeat(done[:, None], self.agent_num, axis=1)
+        return obs, rewards, dones, [{} for _ in range(dones.shape[0])]
+
+    def _step_device(self, actions):
+        """CUDA tensors in, CUDA tensors out (zero-copy views of the engine's step result; valid until the step after next)."""
+        a = torch.as_tensor(actions, device=self.env.device, dtype=torch.float32) * 0.5
+        obs, reward, termination, info = self.env.step(a.clip(-1, 1))
+        rewards = reward.unsqueeze(-1) if torch.is_tensor(reward) else reward
+        dones = termination.unsqueeze(-1).expand(-1, self.agent_num)
+        return obs, rewards, dones, info
 
     def close(self, **kwargs):
         return self.env.close()
@@ -77,6 +141,39 @@ class mqe_openrl_wrapper(Wrapper):
             rb[k] = 0
         rb["step count"] = 0
         return out
+
+
+class MATWrapper(Wrapper):
+    """openrl_ws/utils.py:92-129: for dict observation spaces with "policy" / "critic" entries the multi-agent transformer sees the
+    "policy" part; everything else passes through."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self._observation_space = None
+
+    @staticmethod
+    def _policy_part(space):
+        sub = getattr(space, "spaces", None)
+        return sub is not None and "critic" in sub.keys() and "policy" in sub.keys()
+
+    @property
+    def observation_space(self):
+        space = self.env.observation_space if self._observation_space is None else self._observation_space
+        return space["policy"] if self._policy_part(space) else space
+
+    @observation_space.setter
+    def observation_space(self, value):
+        self._observation_space = value
+
+    def observation(self, observation):
+        space = self.env.observation_space if self._observation_space is None else self._observation_space
+        return observation["policy"] if self._policy_part(space) else observation
+
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
+
+    def step(self, actions, extra_data=None):
+        return self.env.step(actions, extra_data)
 
 
 class SingleAgentWrapper(Wrapper):

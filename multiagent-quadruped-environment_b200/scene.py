@@ -247,8 +247,9 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
         d.gate_x = float(kw["init"]["block_length"] + kw["plane"]["block_length"])   # go1_football_defender.py:61-63
     d.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     ct = str(cfg.control.control_type)
-    assert ct in ("C", "control_net", "P", "T"), f"control_type {ct!r}: 'V' is not built"
-    d.control_type = {"C": 0, "control_net": 0, "P": 1, "T": 2}[ct]
+    assert ct in E.CONTROL_TYPES, f"unknown control_type {ct!r} (legged_robot.py:384-392)"
+    d.control_type = E.CONTROL_TYPES[ct]
+    d.soft_dof_pos_limit = float(getattr(cfg.rewards, "soft_dof_pos_limit", 1.0))          # legged_robot.py:318-321
     d.stiffness, d.damping = float(cfg.control.stiffness.get("joint", 0.0)), float(cfg.control.damping.get("joint", 0.0))
     if getattr(dr, "randomize_lag_timesteps", False):                          # go1.py:337-339, 363
         d.lag_enabled, d.lag_timesteps = 1, int(dr.lag_timesteps)

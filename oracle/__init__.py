@@ -41,6 +41,7 @@ def load(precision="f64"):
         lib.orc_destroy.argtypes = [vp]
         lib.orc_reset.argtypes = [vp]
         lib.orc_step.argtypes = [vp, vp]
+        lib.orc_step_joint.argtypes = [vp, vp]
         lib.orc_policy.argtypes = [vp, vp]
         lib.orc_substeps.argtypes = [vp, ctypes.c_int]
         lib.orc_post_physics.argtypes = [vp]
@@ -93,6 +94,10 @@ class Oracle:
         a = np.ascontiguousarray(actions, dtype=np.float32)
         self.lib.orc_step(self.h, a.ctypes.data_as(ctypes.c_void_p))
 
+    def step_joint(self, joint_actions):
+        a = np.ascontiguousarray(joint_actions, dtype=np.float32)
+        self.lib.orc_step_joint(self.h, a.ctypes.data_as(ctypes.c_void_p))
+
     def policy(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.float32)
         self.lib.orc_policy(self.h, a.ctypes.data_as(ctypes.c_void_p))
@@ -118,7 +123,7 @@ class Oracle:
         n = self.lib.orc_get(self.h, which, None)
         if n < 0:
             raise KeyError(which)
-        if which in (E.BUF_RESET, E.BUF_TIMEOUT, E.BUF_COLLIDE, E.BUF_ROLL_TERM, E.BUF_PITCH_TERM, E.BUF_ZLOW_TERM, E.BUF_ZHIGH_TERM):
+        if which in (E.BUF_RESET, E.BUF_TIMEOUT, E.BUF_COLLIDE, E.BUF_ROLL_TERM, E.BUF_PITCH_TERM, E.BUF_ZLOW_TERM, E.BUF_ZHIGH_TERM, E.BUF_SUBSTEP_EXCEED):
             out = np.zeros(n, dtype=np.uint8)
         elif which == E.BUF_EPISODE_LENGTH:
             out = np.zeros(n, dtype=np.int64)

@@ -399,6 +399,7 @@ typedef struct {
     real *obs;                              /* [M][71]                          */
     real *commands;                         /* [M][3]                           */
     real *last_dof_vel, *last_root_vel;
+    real *sub_tau, *sub_qd; uint8_t *sub_exceed;   /* post_decimation_step logs [N][decimation][12A] (legged_robot.py:112-115) */
     real *sheep_stats;                      /* [N][3]                           */
     float *mu_env;                          /* [N] per-env friction or NULL (domain_rand.randomize_friction) */
     real *lag_ring; int lag_n; uint32_t lag_calls;   /* action lag (go1.py:337-339, 363): [M][lag_n][12] scaled actions; calls so far */
@@ -456,6 +457,8 @@ Oracle *orc_create(const MqeSimDesc *desc) {
     o->base_quat = RA(M * 4); o->base_lin_vel = RA(M * 3); o->base_ang_vel = RA(M * 3); o->proj_grav = RA(M * 3);
     o->obs = RA(M * MQE_OBS_FLOATS); o->commands = RA(M * 3);
     o->last_dof_vel = RA(M * 12); o->last_root_vel = RA(M * 6); o->sheep_stats = RA(N * 3);
+    o->sub_tau = RA((size_t)M * 12 * desc->decimation); o->sub_qd = RA((size_t)M * 12 * desc->decimation);
+    o->sub_exceed = (uint8_t *)xcalloc((size_t)M * 12 * desc->decimation, 1);
 #undef RA
     o->ep_len = (int64_t *)xcalloc(N, sizeof(int64_t));
     o->reset_buf = (uint8_t *)xcalloc(N, 1); o->timeout_buf = (uint8_t *)xcalloc(N, 1);
@@ -474,6 +477,14 @@ Oracle *orc_create(const MqeSimDesc *desc) {
             for (int i = 0; i < 13; i++) r[i] = o->base_init[(e * A + a) * 13 + i];
             for (int i = 0; i < 3; i++) r[i] += o->agent_origins[(e * A + a) * 3 + i];
             for (int j = 0; j < 12; j++) o->dof[((size_t)e * (12 * A + o->D) + 12 * a + j) * 2] = desc->model.q_default[j];
+            /* _init_buffers (legged_robot.py:570, 620-622): base_quat = spawn quaternion; base_lin_vel / base_ang_vel / projected_gravity
+             * derived from the spawn state.  reset_idx does not recompute them, so the first reset()'s observation carries these. */
+            int m = e * A + a;
+            const real g[3] = {0, 0, -1};
+            for (int i = 0; i < 4; i++) o->base_quat[m * 4 + i] = r[3 + i];
+            quat_rotate_inverse(o->base_lin_vel + m * 3, r + 3, r + 7);
+            quat_rotate_inverse(o->base_ang_vel + m * 3, r + 3, r + 10);
+            quat_rotate_inverse(o->proj_grav + m * 3, r + 3, g);
         }
         for (int p = 0; p < P; p++) {
             real *r = o->root + ((size_t)e * (A + P) + A + p) * 13;
@@ -492,6 +503,7 @@ void orc_destroy(Oracle *o) {
     free(o->loc_last); free(o->loc_last2); free(o->loc_obs); free(o->hist); free(o->err1); free(o->err2); free(o->vel1); free(o->vel2);
     free(o->gait); free(o->clock); free(o->base_quat); free(o->base_lin_vel); free(o->base_ang_vel); free(o->proj_grav);
     free(o->obs); free(o->commands); free(o->last_dof_vel); free(o->last_root_vel); free(o->sheep_stats);
+    free(o->sub_tau); free(o->sub_qd); free(o->sub_exceed);
     free(o->ep_len); free(o->reset_buf); free(o->timeout_buf); free(o->collide_buf); free(o->r_term); free(o->p_term);
     free(o->zl_term); free(o->zh_term); free(o->episode);
     free(o);
@@ -1080,8 +1092,11 @@ static void env_torques(Oracle *o, int e, real *tau, uint32_t call) {
         int m = e * A + a;
         for (int j = 0; j < 12; j++) {
             real act = o->actions[m * 12 + j] * d->action_scale;
-            if (d->control_type != 0) {   /* LeggedRobot._compute_torques (legged_robot.py:384-392): 'P' / 'T', no hip scale, no histories */
-                real t = d->control_type == 1 ? d->stiffness * (act + d->model.q_default[j] - dof[(12 * a + j) * 2]) - d->damping * dof[(12 * a + j) * 2 + 1] : act;
+            if (d->control_type != 0) {   /* LeggedRobot._compute_torques (legged_robot.py:384-392): 'P' / 'V' / 'T', no hip scale, no histories */
+                real qj = dof[(12 * a + j) * 2], qdj = dof[(12 * a + j) * 2 + 1];
+                real t = act;
+                if (d->control_type == 1) t = d->stiffness * (act + d->model.q_default[j] - qj) - d->damping * qdj;
+                else if (d->control_type == 3) t = d->stiffness * (act - qdj) - d->damping * (qdj - o->last_dof_vel[m * 12 + j]) / d->sim_dt;
                 real lim = d->model.tau_limit[j];
                 t = t > lim ? lim : (t < -lim ? -lim : t);
                 tau[12 * a + j] = t;
@@ -1272,6 +1287,18 @@ void orc_substeps(Oracle *o, int count) {
         for (int s = 0; s < count; s++) {
             env_torques(o, e, tau, o->lag_calls + (uint32_t)s);
             env_substep(o, e, tau, st);
+            if (s < o->d.decimation) {   /* post_decimation_step (legged_robot.py:112-115) */
+                const real soft = o->d.soft_dof_pos_limit > 0 ? o->d.soft_dof_pos_limit : 1;
+                const real *dof = o->dof + (size_t)e * (12 * o->A + o->D) * 2;
+                for (int k = 0; k < 12 * o->A; k++) {
+                    size_t ix = ((size_t)e * o->d.decimation + s) * (12 * o->A) + k;
+                    int j = k % 12;
+                    real mid = (real)0.5 * ((real)o->d.model.q_lower[j] + (real)o->d.model.q_upper[j]);
+                    real half = (real)0.5 * ((real)o->d.model.q_upper[j] - (real)o->d.model.q_lower[j]) * soft;
+                    o->sub_tau[ix] = tau[k]; o->sub_qd[ix] = dof[k * 2 + 1];
+                    o->sub_exceed[ix] = (uint8_t)((dof[k * 2] < mid - half) | (dof[k * 2] > mid + half));
+                }
+            }
         }
 #pragma omp critical
         { tot[0] += st[0]; tot[1] += st[1]; tot[2] += st[2]; if (st[3] > tot[3]) tot[3] = st[3]; }
@@ -1348,7 +1375,7 @@ void orc_post_physics(Oracle *o) {
             quat_rotate_inverse(o->base_lin_vel + m * 3, rs + 3, rs + 7);
             quat_rotate_inverse(o->base_ang_vel + m * 3, rs + 3, rs + 10);
             quat_rotate_inverse(o->proj_grav + m * 3, rs + 3, grav);
-            gait_clock(o, m, dt_policy);
+            if (d->control_type == 0) gait_clock(o, m, dt_policy);   /* _step_contact_targets: control_type 'C' only (go1.py:241) */
             /* _push_robots (go1.py:237-238, legged_robot.py:472-477) */
             if (d->push_interval > 0 && ((o->step_count + 1u) % (uint32_t)d->push_interval) == 0u) {
                 real *rw = o->root + ((size_t)e * G + a) * 13;
@@ -1399,6 +1426,13 @@ void orc_step(Oracle *o, const float *actions) {
     orc_substeps(o, o->d.decimation);
     orc_post_physics(o);
 }
+/* Go1.step() for control_type 'P' / 'V' / 'T' (go1.py:43-45 -> pre_physics_step, legged_robot.py:108-110): [N][12A] joint actions */
+void orc_step_joint(Oracle *o, const float *joint_actions) {
+    const real c = o->d.clip_actions;
+    for (int i = 0; i < o->M * 12; i++) { real a = joint_actions[i]; o->actions[i] = a > c ? c : (a < -c ? -c : a); }
+    orc_substeps(o, o->d.decimation);
+    orc_post_physics(o);
+}
 
 /* ------------------------------------------------------------------------------------------------ accessors */
 static void to_f32(float *dst, const real *src, size_t n) { for (size_t i = 0; i < n; i++) dst[i] = (float)src[i]; }
@@ -1435,6 +1469,9 @@ int64_t orc_get(Oracle *o, int which, void *out) {
     case MQE_BUF_ZHIGH_TERM: if (out) memcpy(out, o->zh_term, N); return N;
     case MQE_BUF_EPISODE_LENGTH: if (out) memcpy(out, o->ep_len, N * sizeof(int64_t)); return N;
     case MQE_BUF_STATS: if (out) memcpy(out, o->stats, sizeof o->stats); return 8;
+    case MQE_BUF_SUBSTEP_TORQUES: src = o->sub_tau; n = (size_t)M * 12 * o->d.decimation; break;
+    case MQE_BUF_SUBSTEP_DOF_VEL: src = o->sub_qd; n = (size_t)M * 12 * o->d.decimation; break;
+    case MQE_BUF_SUBSTEP_EXCEED: if (out) memcpy(out, o->sub_exceed, (size_t)M * 12 * o->d.decimation); return (int64_t)M * 12 * o->d.decimation;
     default: return -1;
     }
     if (out) to_f32((float *)out, src, n);

@@ -31,7 +31,19 @@ def test_bookkeeping_matches_reference_methods(task, golden_dir):
     sc.agent_origins[:] = z["agent_origins"]
     assert sc.desc.max_episode_length == int(z["max_episode_length"])
     o = oracle.Oracle(sc, "f64")
+    # LeggedRobot._init_buffers (legged_robot.py:567-570, 620-622), the reference's own lines run on the spawn state: base_quat = spawn
+    # quaternion, projected_gravity = R^T (0, 0, -1), base velocities from the spawn velocities.  reset_idx does not recompute them, so
+    # the observation of the very first reset() must carry them (they used to start as zeros).
+    M0 = N * sc.num_agents
+    assert np.allclose(o.get(E.BUF_PROJ_GRAVITY).reshape(M0, 3), z["init_proj_grav"], atol=1e-6)
+    assert np.allclose(o.get(E.BUF_BASE_LIN_VEL).reshape(M0, 3), z["init_base_lin_vel"], atol=1e-6)
+    assert np.allclose(o.get(E.BUF_BASE_ANG_VEL).reshape(M0, 3), z["init_base_ang_vel"], atol=1e-6)
     o.reset()
+    first = o.obs()
+    assert np.allclose(first[:, O["projected_gravity"][0]:O["projected_gravity"][1]], z["init_proj_grav"], atol=1e-6), "first reset(): gravity"
+    assert np.allclose(first[:, O["lin_vel"][0]:O["lin_vel"][1]], 2.0 * z["init_base_lin_vel"], atol=1e-6)      # pre-reset values, not the redrawn root velocity
+    if sc.num_npcs:                                      # P > 0: base_quat is a stale copy of the spawn quaternion until the first physics step
+        assert np.allclose(first[:, O["base_quat"][0]:O["base_quat"][1]], z["init_base_quat"], atol=1e-6)
     o.set_reset_state(False)                             # reset_idx without its RNG part, as in the golden run
     o.set(E.BUF_HISTORY, np.zeros((N * A, 2100), dtype=np.float32))
     o.set(E.BUF_ROOT_STATES, z["root0"]); o.set(E.BUF_DOF_STATES, z["dof0"])

@@ -131,8 +131,26 @@ def run(task, cfg_mod, cfg_name, cls_mod, cls_name, N, seed):
     s.gait_indices = torch.zeros(M); s.clock_inputs = torch.zeros(M, 4)
     s.doubletime_clock_inputs = torch.zeros(M, 4); s.halftime_clock_inputs = torch.zeros(M, 4)
     s.gravity_vec = T(np.tile(np.array([[0, 0, -1.0]], dtype=np.float32), (M, 1)))
-    s.base_quat = torch.zeros(M, 4); s.base_lin_vel = torch.zeros(M, 3); s.base_ang_vel = torch.zeros(M, 3)
-    s.projected_gravity = torch.zeros(M, 3)
+    # ---- derived base quantities exactly as LeggedRobot._init_buffers leaves them (legged_robot.py:567-570, 620-622): the reference's OWN
+    # assignment lines, executed on the spawn root state (cfg.init_state, quaternion normalised as PhysX does when the actor is created).
+    # reset_idx does not recompute them, so the first reset()'s observation carries projected_gravity = R(spawn)^T (0, 0, -1).
+    ist = cfg.init_state
+    if getattr(ist, "multi_init_state", False):
+        spawn = np.asarray([st.pos + st.rot + st.lin_vel + st.ang_vel for st in ist.init_states], dtype=np.float32)
+    else:
+        spawn = np.asarray([ist.pos + ist.rot + ist.lin_vel + ist.ang_vel] * A, dtype=np.float32)
+    spawn[:, 3:7] /= np.linalg.norm(spawn[:, 3:7], axis=1, keepdims=True)
+    s.root_states = T(np.tile(spawn, (N, 1)))
+    LeggedRobot = importlib.import_module("mqe.envs.base.legged_robot").LeggedRobot
+    init_src = inspect.getsource(LeggedRobot._init_buffers).splitlines()
+    wanted = ("self.base_quat = ", "self.base_lin_vel = ", "self.base_ang_vel = ", "self.projected_gravity = ")
+    picked = [ln.strip() for ln in init_src if ln.strip().startswith(wanted)]
+    assert len(picked) == 4, picked
+    tu0 = sys.modules["isaacgym.torch_utils"]
+    exec("\n".join(picked), {"quat_rotate_inverse": tu0.quat_rotate_inverse, "self": s})
+    s.base_quat = s.base_quat.clone()
+    init_rec = {"init_spawn": spawn.copy(), "init_base_quat": s.base_quat.numpy().copy(), "init_base_lin_vel": s.base_lin_vel.numpy().copy(),
+                "init_base_ang_vel": s.base_ang_vel.numpy().copy(), "init_proj_grav": s.projected_gravity.numpy().copy()}
     s.actions = torch.zeros(N, 12 * A); s.last_actions = torch.zeros(N, 12 * A)
     s.env_origins = T(rng.uniform(0, 30, size=(N, 3)).astype(np.float32)); s.env_origins[:, 2] = 0
     s.agent_origins = s.env_origins.unsqueeze(1).repeat(1, A, 1) + T(rng.uniform(-1, 1, size=(N, A, 3)).astype(np.float32))
@@ -142,7 +160,7 @@ def run(task, cfg_mod, cfg_name, cls_mod, cls_name, N, seed):
     s.episode_length_buf = T(rng.integers(0, s.max_episode_length + 2, size=N).astype(np.int64))
 
     steps = 4
-    rec = {"env_origins": s.env_origins.numpy().copy(), "agent_origins": s.agent_origins.numpy().copy(),
+    rec = {**init_rec, "env_origins": s.env_origins.numpy().copy(), "agent_origins": s.agent_origins.numpy().copy(),
            "episode_length0": s.episode_length_buf.numpy().copy(), "max_episode_length": np.int64(s.max_episode_length)}
     out = {k: [] for k in ("in_actions", "in_root", "in_dof", "in_contact", "loc_obs", "history", "actions", "torques1", "torques2",
                            "base_lin_vel", "base_ang_vel", "proj_grav", "gait", "clock", "collide", "timeout", "r_term", "p_term", "reset",
