@@ -104,3 +104,12 @@ class PeerStepExchange:
         """True if a peer's flag ever failed to arrive within the kernel's bounded wait (sticky; MQE_BUF_STATS[5])."""
         from . import engine as E
         return int(self.engine.tensor(E.BUF_STATS)[E.STAT_GATHER_TIMEOUT].item()) != 0
+
+
+def split_gathered_result(buf: torch.Tensor, layout, world: int):
+    """NCCL / gloo fallback of the peer exchange: `buf` is the all-gathered packed step result, [world x total_bytes] u8 (every rank's
+    MQE_BUF_STEP_RESULT half back to back); returns GLOBAL (obs [N_global, Aw, D], reward [N_global, Aw], done [N_global])."""
+    from .engine import Engine
+    total = int(layout.total_bytes)
+    parts = [Engine.split_result(buf[r * total:(r + 1) * total], layout) for r in range(world)]
+    return tuple(torch.cat([p[i] for p in parts], dim=0) for i in range(3))

@@ -31,7 +31,7 @@ def test_struct_mirrors_match_header_sizes():
     """ctypes mirrors vs the C compiler's view of the structs (compiled with gcc from the header)."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "mqe_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(MqeRobotModel), sizeof(MqeWeights), sizeof(MqeSimDesc));return 0;}\n'
+    src = '#include <stdio.h>\n#include "mqe_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(MqeRobotModel), sizeof(MqeWeights), sizeof(MqeSimDesc), sizeof(MqeStepResultLayout), sizeof(MqeWrapperDesc));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -39,7 +39,8 @@ def test_struct_mirrors_match_header_sizes():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         out = subprocess.check_output([exe]).decode().split()
     from mqe_b200.model import RobotModelC
-    assert [int(x) for x in out] == [ctypes.sizeof(RobotModelC), ctypes.sizeof(E.WeightsC), ctypes.sizeof(E.SimDescC)]
+    assert [int(x) for x in out] == [ctypes.sizeof(RobotModelC), ctypes.sizeof(E.WeightsC), ctypes.sizeof(E.SimDescC),
+                                     ctypes.sizeof(E.StepResultLayoutC), ctypes.sizeof(E.WrapperDescC)]
 
 
 def test_no_cpu_fallback():

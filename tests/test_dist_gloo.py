@@ -67,3 +67,50 @@ def test_step_gather_gloo(world, n_global):
     for p in procs:
         p.join(timeout=60)
     assert all(ok is True for _, ok in res), res
+
+
+def _pack_worker(rank, world, port, q):
+    """The NCCL / gloo fallback of the per-step exchange: ONE all_gather of the packed step result (obs | reward | done), then split."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mqe_b200 import engine as E
+        from mqe_b200.dist import split_gathered_result
+        n, Aw, D = 16, 2, 5
+        L = E.StepResultLayoutC()
+        up16 = lambda v: (v + 15) & ~15
+        L.num_envs, L.Aw, L.D = n, Aw, D
+        L.obs_off, L.obs_bytes = 0, n * Aw * D * 4
+        L.reward_off, L.reward_bytes = up16(L.obs_bytes), n * Aw * 4
+        L.done_off, L.done_bytes = up16(L.reward_off + L.reward_bytes), n
+        L.total_bytes = up16(L.done_off + L.done_bytes)
+        local = torch.zeros(int(L.total_bytes), dtype=torch.uint8)
+        obs, rew, done = E.Engine.split_result(local, L)
+        obs.copy_(torch.arange(n * Aw * D, dtype=torch.float32).view(n, Aw, D) + 1000 * rank)
+        rew.copy_(torch.full((n, Aw), float(rank)))
+        done.copy_(torch.arange(n) % (rank + 2) == 0)
+        g = StepGather(world)                                # one packed row per rank
+        G = g.gather("result", local.view(1, -1)).view(-1)
+        go, gr, gd = split_gathered_result(G, L, world)
+        ok = go.shape == (n * world, Aw, D) and gr.shape == (n * world, Aw) and gd.dtype == torch.bool
+        for r in range(world):
+            ok &= bool(torch.equal(go[r * n:(r + 1) * n], torch.arange(n * Aw * D, dtype=torch.float32).view(n, Aw, D) + 1000 * r))
+            ok &= bool((gr[r * n:(r + 1) * n] == r).all()) and bool(torch.equal(gd[r * n:(r + 1) * n], torch.arange(n) % (r + 2) == 0))
+        q.put((rank, ok))
+    except Exception as exc:  # noqa: BLE001
+        q.put((rank, f"{type(exc).__name__}: {exc}"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_step_result_gather_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pack_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=60) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok is True for _, ok in res), res

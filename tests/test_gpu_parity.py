@@ -490,7 +490,10 @@ def test_error_paths_return_codes_not_crashes():
     assert lib.mqe_sim_step(eng.h, None) < 0 and b"null" in lib.mqe_last_error()
     assert lib.mqe_sim_substeps(eng.h, 0) < 0
     assert lib.mqe_sim_get_buffer(eng.h, 999, None, None, None) < 0
-    assert lib.mqe_sim_get_buffer(eng.h, E.BUF_WRAP_OBS, None, None, None) < 0        # no task wrapper set yet
+    assert lib.mqe_sim_get_buffer(eng.h, E.BUF_WRAP_SUMS, None, None, None) < 0       # no task wrapper set yet
+    assert lib.mqe_sim_get_buffer(eng.h, E.BUF_HISTORY_HI, None, None, None) < 0      # fp32 policy mode: no bf16 planes
+    assert lib.mqe_sim_step_joint(eng.h, dev(actions_for(sc, 0)).data_ptr()) == -4 and b"control_type" in lib.mqe_last_error()   # 'C' takes commands
+    assert lib.mqe_sim_gather_view(eng.h, 0, None, None) < 0 and lib.mqe_sim_gather_parity(eng.h) == -1   # no peer exchange connected
     assert lib.mqe_sim_wrapper_reset(eng.h) < 0
     with pytest.raises(E.EngineError):
         eng.set_wrapper(E.WRAP_SHEEP, [1, 0, 0, 0, 0, 0])                              # no sheep in go1gate
@@ -505,23 +508,40 @@ def test_error_paths_return_codes_not_crashes():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ct", ["P", "T"])
-def test_pd_and_torque_control_parity(ct):
-    """cfg.control.control_type 'P' / 'T' (legged_robot.py:384-392) instead of the actuator network: kernels against the oracle."""
+@pytest.mark.parametrize("ct", ["P", "T", "V"])
+def test_joint_action_control_types_parity(ct):
+    """cfg.control.control_type 'P' / 'T' / 'V' (legged_robot.py:384-392): Go1.step bypasses the walk policy (go1.py:43-45) and takes
+    [N, 12A] joint actions, clipped to +-clip_actions by pre_physics_step.  Kernels (mqe_sim_step_joint) against the oracle, and the
+    reference-facing Go1.step() on top of it; a 3-D command caller is refused instead of silently getting another controller."""
     cfg = C.Go1GateCfg(); cfg.env.num_envs = 8
     cfg.control.control_type = ct
-    cfg.control.stiffness = {"joint": 40.0}; cfg.control.damping = {"joint": 1.0}
+    cfg.control.stiffness = {"joint": 40.0 if ct == "P" else 2.0}; cfg.control.damping = {"joint": 1.0 if ct == "P" else 0.002}
+    cfg.normalization.clip_actions = 1.5
     np.random.seed(0)
     sc = S.build_scene(cfg, seed=0, policy_mode=E.POLICY_FP32, wrapper_action_scale=(2.0, 0.5, 0.5))
     eng, orc = E.Engine(sc.desc, device=0, keepalive=sc), oracle.Oracle(sc, "f32")
     eng.reset(); orc.reset()
+    assert eng.lib.mqe_sim_step(eng.h, dev(actions_for(sc, 0)).data_ptr()) == -4           # MQE_ERR_UNSUPPORTED: commands need control_type 'C'
+    rng = np.random.default_rng(5)
     for s in range(4):
-        a = actions_for(sc, s)
-        eng.step(dev(a).data_ptr()); orc.step(a)
+        a = rng.uniform(-2.0, 2.0, size=(8, 24)).astype(np.float32)                       # beyond the clip on purpose
+        eng.step_joint(dev(a).data_ptr()); orc.step_joint(a)
+        torch.cuda.synchronize()
+        assert np.allclose(get(eng, E.BUF_ACTIONS).ravel(), np.clip(a, -1.5, 1.5).ravel())
         g, r = get(eng, E.BUF_ROOT_STATES).reshape(8, 2, 13), orc.root_states()
         assert np.allclose(g[..., :7], r[..., :7], atol=2e-4), (s, np.abs(g[..., :7] - r[..., :7]).max())
         assert np.allclose(get(eng, E.BUF_TORQUES).ravel(), orc.get(E.BUF_TORQUES).ravel(), atol=2e-2), s
+        assert np.array_equal(get(eng, E.BUF_RESET), orc.get(E.BUF_RESET))
+        assert np.abs(get(eng, E.BUF_CLOCK)).max() == 0.0                                   # no gait clock outside control_type 'C' (go1.py:241)
     eng.close(); orc.close()
+    from mqe_b200.envs.go1 import Go1
+    env = Go1(cfg, sim_device="cuda:0", seed=0, policy_mode=E.POLICY_FP32)
+    env.reset()
+    obs, rew, done, _ = env.step(torch.zeros(8 * 2, 12, device="cuda:0"))                 # the reference reshapes to [N, -1] (go1.py:44)
+    assert done.shape == (8,) and obs.dof_pos.shape == (16, 12) and torch.isfinite(env.root_states).all()
+    with pytest.raises(AssertionError):
+        env.step(torch.zeros(8, 2, 3, device="cuda:0"))
+    env.close()
 
 
 @pytest.mark.gpu
