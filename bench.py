@@ -212,7 +212,7 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
             gather.gather("result", result_all[eng.result_parity()].view(1, -1))
 
     # ---- steady state: random episode phases, then one full episode of pre-roll (untimed) ----
-    pre = 0 if args.no_preroll else int(base.max_episode_length) + 1
+    pre = 0 if args.no_preroll else (args.preroll_episodes if headline else 1) * int(base.max_episode_length) + 1
     if pre:
         desynchronise(base, torch, seed=0)
     for i in range(pre):
@@ -223,13 +223,14 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
 
     # ---- timed region: K steps, L2 flushed (untimed) between steps, per-step CUDA events on the launching stream ----
     sampler = ClockSampler(ctx["local_rank"]) if (headline and rank == 0) else None
+    if sampler:                                                   # spun up before the region so that even a 7 ms region is sampled
+        sampler.start()
+        time.sleep(0.02)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
     launches0 = eng.launch_count()
     wall0 = time.perf_counter()
     for i in range(K):
@@ -244,7 +245,11 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
     if world > 1:
         dist.barrier()
     launches = eng.launch_count() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    per_step = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    dev_ms = sum(per_step)
+    q = max(1, K // 4)
+    drift = {"first_quarter_ms": float(np.mean(per_step[:q])), "last_quarter_ms": float(np.mean(per_step[-q:])),
+             "p50_ms": float(np.median(per_step)), "p95_ms": float(np.quantile(per_step, 0.95)), "max_ms": float(np.max(per_step))}
     t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -344,7 +349,7 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
 
     out = {
         "value": value, "ms_per_step": dev_ms / K, "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches / K,
-        "wall_s_timed_region": wall, "roofline": roofline, "clocks": clocks,
+        "wall_s_timed_region": wall, "roofline": roofline, "clocks": clocks, "per_step_ms": drift,
         "config": {"workload": f"{task}, {A} Go1 agents" + (f" + {base.num_npcs} NPC" if base.num_npcs else "") +
                                f", num_envs={n_per_gpu} per GPU ({n_global} global), decimation {base.decimation}, dt {cfg.sim.dt}, PGS sweeps {eng.desc.solver_iters}",
                    "policy_arithmetic": args.policy, "actions": "U(-1,1) per step" if args.actions == "uniform" else "fixed (0.5, 0, 0)",
@@ -380,7 +385,8 @@ def run_gpu(args):
         "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.policy == "fp32" else f"f32 physics / {args.policy} policy (bf16 hi+lo operands, fp32 accumulate)" if args.policy == "bf16x3" else "f32 physics / bf16 policy",
         "data": "synthetic", "config": main["config"], "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
-        "launches_per_step": main["launches_per_step"], "wall_s_timed_region": main["wall_s_timed_region"], "roofline": main["roofline"],
+        "launches_per_step": main["launches_per_step"], "wall_s_timed_region": main["wall_s_timed_region"], "per_step_ms": main["per_step_ms"],
+        "roofline": main["roofline"],
     }
     if "exchange_timeout" in main:
         line["exchange_timeout"] = True
@@ -418,6 +424,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sublines", action="store_true", help="skip the C3 / C4 / C5 sub-lines")
     ap.add_argument("--no-preroll", action="store_true", help="time from a synchronised reset instead of the steady state (round-1 behaviour)")
+    ap.add_argument("--preroll-episodes", type=int, default=3, help="episodes rolled forward (untimed) after the phase randomisation, headline workload")
     ap.add_argument("--c5", action="store_true", help="under torchrun with fewer than 8 ranks: still add the sharded football-defender sub-line")
     ap.add_argument("--exchange", type=str, default=os.environ.get("MQE_EXCHANGE", "p2p"), choices=["p2p", "nccl"],
                     help="multi-GPU per-step exchange: peer-memory stores inside the step graph (default) or one NCCL all_gather")

@@ -17,6 +17,10 @@ base = env.env
 eng = base.engine
 acts = torch.as_tensor(B.synth_actions(n, base._ctrl_agents, 64, env_offset=0), device="cuda:0")
 env.reset()
+if os.environ.get("MQE_SYNC_EPISODES", "0") != "1":       # steady state as in bench.py: random episode phases + one episode of pre-roll
+    B.desynchronise(base, torch, seed=0)
+    for i in range(int(base.max_episode_length) + 1):
+        env.step(acts[i % 64])
 rows = []
 worst = (0.0, None, None)
 for i in range(steps):
