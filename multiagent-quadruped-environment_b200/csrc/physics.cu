@@ -394,6 +394,28 @@ __device__ __forceinline__ float robot_side_regs(int k, V3 r, V3 d, V3 a1, V3 a2
     return dd;
 }
 
+// Contact blocks.  The three rows of a contact (normal, two friction directions) are solved as ONE block per Gauss-Seidel sweep: the
+// three J.w are formed together from the velocity at the start of the block, and the effect of the block's own earlier updates is added
+// through the coupling terms K_ij = J_i . (M^-1 J_j^T) = J_i . Y_j (i > j), stored in the pad floats of rows 1 and 2.  Algebraically
+// this IS the row-by-row sweep of the oracle (same order, same clamps); it shortens the dependency chain of the sweep from three
+// dot -> clamp -> update rounds to one, and for pair contacts needs one exchange between the two groups instead of three.
+__device__ __forceinline__ float side_dot(const float *ji, const float *yj) {      // J_i . Y_j for one side: Jb6 Jl3 at [0..8], Yb6 Yl3 at [9..17]
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; k++) s = fmaf(ji[k], yj[9 + k], s);
+    return s;
+}
+__device__ __forceinline__ void local_block_coupling(float *r0, float *r1, float *r2) {
+    r1[22] = side_dot(r1, r0);
+    r2[22] = side_dot(r2, r0);
+    r2[23] = side_dot(r2, r1);
+}
+__device__ __forceinline__ void pair_block_coupling(float *r0, float *r1, float *r2) {   // both sides: A at [0..17], B at [20..37]
+    r1[18] = side_dot(r1, r0) + side_dot(r1 + 20, r0 + 20);
+    r2[18] = side_dot(r2, r0) + side_dot(r2 + 20, r0 + 20);
+    r2[19] = side_dot(r2, r1) + side_dot(r2 + 20, r1 + 20);
+}
+
 __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int maxpair, int spair, int max_cand) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -856,6 +878,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     row[20] = 0.f;
                     row[21] = __int_as_float(leg | ((dch ? 1 : 0) << 4) | (r0 << 8));
                 }
+                local_block_coupling(lrow(r0), lrow(r0 + 1), lrow(r0 + 2));
             }
             if (leg == 0 && active) { stat_local += ncon; stat_lim += nlim; }
         } else if (is_npc && active && seesaw) {
@@ -881,6 +904,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     row[20] = 0.f;
                     row[21] = __int_as_float(0 | ((dch ? 1 : 0) << 4) | ((3 * ncon) << 8));
                 }
+                local_block_coupling(ns + NS_ROWS + 3 * ncon * ROWF, ns + NS_ROWS + (3 * ncon + 1) * ROWF, ns + NS_ROWS + (3 * ncon + 2) * ROWF);
                 ncon++;
             }
             nrows = 3 * ncon;
@@ -910,6 +934,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         row[20] = 0.f;
                         row[21] = __int_as_float(0 | ((dch ? 1 : 0) << 4) | ((3 * ncon) << 8));
                     }
+                    local_block_coupling(ns + NS_ROWS + 3 * ncon * ROWF, ns + NS_ROWS + (3 * ncon + 1) * ROWF, ns + NS_ROWS + (3 * ncon + 2) * ROWF);
                     ncon++;
                 }
             }
@@ -1259,6 +1284,10 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 }
                 npair = min(npair + total, maxpair);
             }
+            if (npair > 0) {                                   // uniform over the env's lanes
+                __syncwarp(env_mask);                              // rows of a contact were written by up to three lanes
+                for (int c = rank_in_env; c < npair; c += lanes_per_env) pair_block_coupling(prow(3 * c), prow(3 * c + 1), prow(3 * c + 2));
+            }
             if (rank_in_env == 0 && env < p.N) stat_pair += npair;
         }
         __syncwarp();
@@ -1284,26 +1313,21 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             float *const rowG = grows - SROWS * ROWF;
             PHASE_MARK(10);
             for (int it = 0; it < p.iters; it++) {
-                float lam_n = 0.f;                                  // multiplier of the last normal row (friction rows follow it)
-                for (int i = 0; i < nrows; i++) {
+                // ---- joint-limit rows: single rows, kind 0 (lambda >= 0) ----
+                for (int i = 0; i < nlim; i++) {
                     float *row = (i < SROWS ? rowS : rowG) + i * ROWF;
-                    float4 r0 = *reinterpret_cast<const float4 *>(row), r1 = *reinterpret_cast<const float4 *>(row + 4), r2 = *reinterpret_cast<const float4 *>(row + 8);
-                    float4 r3 = *reinterpret_cast<const float4 *>(row + 12), r4 = *reinterpret_cast<const float4 *>(row + 16), r5 = *reinterpret_cast<const float4 *>(row + 20);
-                    const int meta = __float_as_int(r5.y), rleg = meta & 15, kind = (meta >> 4) & 1;
-                    // J.w as a balanced tree: the sweep is one long dependency chain through vb / ua, so depth is what counts
+                    const float4 r0 = *reinterpret_cast<const float4 *>(row), r1 = *reinterpret_cast<const float4 *>(row + 4), r2 = *reinterpret_cast<const float4 *>(row + 8);
+                    const float4 r3 = *reinterpret_cast<const float4 *>(row + 12), r4 = *reinterpret_cast<const float4 *>(row + 16), r5 = *reinterpret_cast<const float4 *>(row + 20);
+                    const int rleg = __float_as_int(r5.y) & 15;
                     const float pb = (fmaf(r0.x, vb[0], r0.y * vb[1]) + fmaf(r0.z, vb[2], r0.w * vb[3])) + fmaf(r1.x, vb[4], r1.y * vb[5]);
                     float pl = 0.f;
 #pragma unroll
                     for (int L = 0; L < 4; L++) {
-                        float t = fmaf(r1.z, ua[L][0], fmaf(r1.w, ua[L][1], r2.x * ua[L][2]));
+                        const float t = fmaf(r1.z, ua[L][0], fmaf(r1.w, ua[L][1], r2.x * ua[L][2]));
                         pl = rleg == L ? t : pl;
                     }
-                    float urel = (r4.w + pl) + pb;            // bias + J w
-                    float lam_old = r5.x, lam = lam_old - urel * r4.z;
-                    const float lo = kind == 0 ? 0.f : -mu_e * lam_n, hi = kind == 0 ? 3.0e38f : mu_e * lam_n;
-                    lam = fminf(fmaxf(lam, lo), hi);
-                    lam_n = kind == 0 ? lam : lam_n;
-                    float dl = lam - lam_old;
+                    const float urel = (r4.w + pl) + pb;            // bias + J w
+                    const float lam_old = r5.x, lam = fmaxf(lam_old - urel * r4.z, 0.f), dl = lam - lam_old;
                     row[20] = lam;                               // all four lanes of the quad store the SAME value (benign same-value race)
                     vb[0] += r2.y * dl; vb[1] += r2.z * dl; vb[2] += r2.w * dl; vb[3] += r3.x * dl; vb[4] += r3.y * dl; vb[5] += r3.z * dl;
 #pragma unroll
@@ -1312,45 +1336,99 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         ua[L][0] = fmaf(r3.w, dlL, ua[L][0]); ua[L][1] = fmaf(r4.x, dlL, ua[L][1]); ua[L][2] = fmaf(r4.y, dlL, ua[L][2]);
                     }
                 }
+                // ---- contact blocks: normal + two friction rows solved together (see local_block_coupling) ----
+                for (int c0 = nlim; c0 < nrows; c0 += 3) {
+                    float *ra = (c0 < SROWS ? rowS : rowG) + c0 * ROWF;
+                    float *rb = (c0 + 1 < SROWS ? rowS : rowG) + (c0 + 1) * ROWF;
+                    float *rc = (c0 + 2 < SROWS ? rowS : rowG) + (c0 + 2) * ROWF;
+                    // J parts of the three rows: Jb0..5 Jl0..2
+                    const float4 a0 = *reinterpret_cast<const float4 *>(ra), a1 = *reinterpret_cast<const float4 *>(ra + 4), a2 = *reinterpret_cast<const float4 *>(ra + 8);
+                    const float4 b0 = *reinterpret_cast<const float4 *>(rb), b1 = *reinterpret_cast<const float4 *>(rb + 4), b2 = *reinterpret_cast<const float4 *>(rb + 8);
+                    const float4 c0v = *reinterpret_cast<const float4 *>(rc), c1 = *reinterpret_cast<const float4 *>(rc + 4), c2 = *reinterpret_cast<const float4 *>(rc + 8);
+                    const float4 a4 = *reinterpret_cast<const float4 *>(ra + 16), a5 = *reinterpret_cast<const float4 *>(ra + 20);   // Yl1 Yl2 dinv bias | lam meta - -
+                    const float4 b4 = *reinterpret_cast<const float4 *>(rb + 16), b5 = *reinterpret_cast<const float4 *>(rb + 20);   //                 | lam meta K10 -
+                    const float4 c4 = *reinterpret_cast<const float4 *>(rc + 16), c5 = *reinterpret_cast<const float4 *>(rc + 20);   //                 | lam meta K20 K21
+                    const int rleg = __float_as_int(a5.y) & 15;
+                    // the block's leg velocity, selected once
+                    const float ul0 = sel1(rleg, ua[0][0], ua[1][0], ua[2][0], ua[3][0]), ul1 = sel1(rleg, ua[0][1], ua[1][1], ua[2][1], ua[3][1]),
+                                ul2 = sel1(rleg, ua[0][2], ua[1][2], ua[2][2], ua[3][2]);
+#define BLOCK_DOT(q0, q1, q2)                                                                                              \
+    (((fmaf(q0.x, vb[0], q0.y * vb[1]) + fmaf(q0.z, vb[2], q0.w * vb[3])) + fmaf(q1.x, vb[4], q1.y * vb[5])) +            \
+     fmaf(q1.z, ul0, fmaf(q1.w, ul1, q2.x * ul2)))
+                    const float j0 = BLOCK_DOT(a0, a1, a2), j1 = BLOCK_DOT(b0, b1, b2), j2 = BLOCK_DOT(c0v, c1, c2);
+                    // sequential solve inside the block (row order n, t1, t2 as in the oracle)
+                    const float l0o = a5.x, l1o = b5.x, l2o = c5.x;
+                    const float l0 = fmaxf(l0o - (a4.w + j0) * a4.z, 0.f), d0 = l0 - l0o;
+                    const float lim = mu_e * l0;
+                    const float l1 = fminf(fmaxf(l1o - (b4.w + fmaf(b5.z, d0, j1)) * b4.z, -lim), lim), d1 = l1 - l1o;
+                    const float l2 = fminf(fmaxf(l2o - (c4.w + fmaf(c5.w, d1, fmaf(c5.z, d0, j2))) * c4.z, -lim), lim), d2 = l2 - l2o;
+                    ra[20] = l0; rb[20] = l1; rc[20] = l2;         // all four lanes of the quad store the SAME values
+                    // velocity update: w += Y0 d0 + Y1 d1 + Y2 d2
+                    const float4 a3 = *reinterpret_cast<const float4 *>(ra + 12), b3 = *reinterpret_cast<const float4 *>(rb + 12), c3 = *reinterpret_cast<const float4 *>(rc + 12);
+                    vb[0] = fmaf(c2.y, d2, fmaf(b2.y, d1, fmaf(a2.y, d0, vb[0]))); vb[1] = fmaf(c2.z, d2, fmaf(b2.z, d1, fmaf(a2.z, d0, vb[1])));
+                    vb[2] = fmaf(c2.w, d2, fmaf(b2.w, d1, fmaf(a2.w, d0, vb[2]))); vb[3] = fmaf(c3.x, d2, fmaf(b3.x, d1, fmaf(a3.x, d0, vb[3])));
+                    vb[4] = fmaf(c3.y, d2, fmaf(b3.y, d1, fmaf(a3.y, d0, vb[4]))); vb[5] = fmaf(c3.z, d2, fmaf(b3.z, d1, fmaf(a3.z, d0, vb[5])));
+                    const float du0 = fmaf(c3.w, d2, fmaf(b3.w, d1, a3.w * d0)), du1 = fmaf(c4.x, d2, fmaf(b4.x, d1, a4.x * d0)),
+                                du2 = fmaf(c4.y, d2, fmaf(b4.y, d1, a4.y * d0));
+#pragma unroll
+                    for (int L = 0; L < 4; L++) {                       // branch-free: only the block's leg moves
+                        const bool mine = rleg == L;
+                        ua[L][0] += mine ? du0 : 0.f; ua[L][1] += mine ? du1 : 0.f; ua[L][2] += mine ? du2 : 0.f;
+                    }
+                }
                 if (npair > 0) {   // uniform over the env's lanes
 #pragma unroll
                     for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));
-                    // Pair rows.  A lane reads only its own group's side (5 x 16 B) and the 16-byte tail; the lane that owns the row's
-                    // leg on each side forms that side's J.w, two shuffles combine them, every lane of the env applies the same
-                    // clamp, and the multiplier is carried to the next sweep through the row (one __syncwarp per sweep).
-                    float lam_np = 0.f;
-                    float4 tl_next = *reinterpret_cast<const float4 *>(prow(0) + 40);
-                    for (int i = 0; i < 3 * npair; i++) {
-                        float *row = prow(i);
-                        const float4 tl = tl_next;                                                 // dinv, bias, lambda, meta
-                        if (i + 1 < 3 * npair) tl_next = *reinterpret_cast<const float4 *>(prow(i + 1) + 40);   // one row ahead: meta picks the side to load
-                        const int meta = __float_as_int(tl.w);
-                        const int ga = meta & 15, la = (meta >> 4) & 15, gb = (meta >> 8) & 15, lb = (meta >> 12) & 15, kind = (meta >> 16) & 1;
-                        const bool inA = grp == ga, inB = grp == gb;
-                        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0, s4 = s0;
-                        if (inA || inB) {
-                            const float *sd = row + (inB ? 20 : 0);                                // Jb0..5 Jl0..2 Yb0..5 Yl0..2 (+2 pad)
-                            s0 = *reinterpret_cast<const float4 *>(sd); s1 = *reinterpret_cast<const float4 *>(sd + 4);
-                            s2 = *reinterpret_cast<const float4 *>(sd + 8); s3 = *reinterpret_cast<const float4 *>(sd + 12);
-                            s4 = *reinterpret_cast<const float4 *>(sd + 16);
+                    // Pair contacts, one block per contact.  A lane reads only its own group's side of the three rows; the lane that
+                    // owns the contact's leg on each side forms that side's three J.w, ONE round of shuffles combines the sides, every
+                    // lane of the env runs the same 3-row solve, and the multipliers are carried to the next sweep through the rows.
+                    for (int c = 0; c < npair; c++) {
+                        float *R0 = prow(3 * c), *R1 = prow(3 * c + 1), *R2 = prow(3 * c + 2);
+                        const float4 t0 = *reinterpret_cast<const float4 *>(R0 + 40), t1 = *reinterpret_cast<const float4 *>(R1 + 40),
+                                     t2 = *reinterpret_cast<const float4 *>(R2 + 40);                    // dinv, bias, lambda, meta
+                        const float k10 = R1[18], k20 = R2[18], k21 = R2[19];
+                        const int meta = __float_as_int(t0.w);
+                        const int ga = meta & 15, la = (meta >> 4) & 15, gb = (meta >> 8) & 15, lb = (meta >> 12) & 15;
+                        const bool inA = grp == ga, inB = grp == gb, in = inA || inB;
+                        const int so = inB ? 20 : 0;
+                        float jw0 = 0.f, jw1 = 0.f, jw2 = 0.f;
+                        if (in) {
+#define SIDE_DOT(R)                                                                                                         \
+    {                                                                                                                       \
+        const float4 q0 = *reinterpret_cast<const float4 *>((R) + so), q1 = *reinterpret_cast<const float4 *>((R) + so + 4); \
+        const float q2x = (R)[so + 8];                                                                                      \
+        jw_ = ((fmaf(q0.x, vb[0], q0.y * vb[1]) + fmaf(q0.z, vb[2], q0.w * vb[3])) + fmaf(q1.x, vb[4], q1.y * vb[5])) +     \
+              fmaf(q1.z, u[0], fmaf(q1.w, u[1], q2x * u[2]));                                                               \
+    }
+                            float jw_;
+                            SIDE_DOT(R0) jw0 = jw_;
+                            SIDE_DOT(R1) jw1 = jw_;
+                            SIDE_DOT(R2) jw2 = jw_;
                         }
-                        const float jw = ((fmaf(s0.x, vb[0], s0.y * vb[1]) + fmaf(s0.z, vb[2], s0.w * vb[3])) + fmaf(s1.x, vb[4], s1.y * vb[5]))
-                                         + fmaf(s1.z, u[0], fmaf(s1.w, u[1], s2.x * u[2]));
                         const int srcA = ga < A ? e_loc * 4 * A + 4 * ga + la : nrl + e_loc * P + (ga - A);
                         const int srcB = gb < A ? e_loc * 4 * A + 4 * gb + lb : nrl + e_loc * P + (gb - A);
-                        const float urel = tl.y + (__shfl_sync(env_mask, jw, srcA) + __shfl_sync(env_mask, jw, srcB));
-                        const float lam_old = tl.z;
-                        float lam = lam_old - urel * tl.x;
-                        const float lo = kind == 0 ? 0.f : -mu_e * lam_np, hi = kind == 0 ? 3.0e38f : mu_e * lam_np;
-                        lam = fminf(fmaxf(lam, lo), hi);
-                        lam_np = kind == 0 ? lam : lam_np;
-                        const float dl = lam - lam_old;
-                        if (rank_in_env == 0) row[42] = lam;
-                        // s* are zero outside the two groups; the leg part only moves the lane that owns the row's leg
-                        vb[0] = fmaf(s2.y, dl, vb[0]); vb[1] = fmaf(s2.z, dl, vb[1]); vb[2] = fmaf(s2.w, dl, vb[2]);
-                        vb[3] = fmaf(s3.x, dl, vb[3]); vb[4] = fmaf(s3.y, dl, vb[4]); vb[5] = fmaf(s3.z, dl, vb[5]);
-                        const float dll = (is_robot && leg == (inB ? lb : la)) ? dl : 0.f;
-                        u[0] = fmaf(s3.w, dll, u[0]); u[1] = fmaf(s4.x, dll, u[1]); u[2] = fmaf(s4.y, dll, u[2]);
+                        const float s0 = __shfl_sync(env_mask, jw0, srcA) + __shfl_sync(env_mask, jw0, srcB);
+                        const float s1 = __shfl_sync(env_mask, jw1, srcA) + __shfl_sync(env_mask, jw1, srcB);
+                        const float s2 = __shfl_sync(env_mask, jw2, srcA) + __shfl_sync(env_mask, jw2, srcB);
+                        const float l0 = fmaxf(t0.z - (t0.y + s0) * t0.x, 0.f), d0 = l0 - t0.z;
+                        const float lim = mu_e * l0;
+                        const float l1 = fminf(fmaxf(t1.z - (t1.y + fmaf(k10, d0, s1)) * t1.x, -lim), lim), d1 = l1 - t1.z;
+                        const float l2 = fminf(fmaxf(t2.z - (t2.y + fmaf(k21, d1, fmaf(k20, d0, s2))) * t2.x, -lim), lim), d2 = l2 - t2.z;
+                        if (rank_in_env == 0) { R0[42] = l0; R1[42] = l1; R2[42] = l2; }
+                        if (in) {
+                            // Y parts: Yb0..5 at [9..14], Yl0..2 at [15..17] of this lane's side
+                            const float dll0 = (is_robot && leg == (inB ? lb : la)) ? 1.f : 0.f;
+#define SIDE_UPD(R, d)                                                                                                      \
+    {                                                                                                                       \
+        const float4 y2 = *reinterpret_cast<const float4 *>((R) + so + 8), y3 = *reinterpret_cast<const float4 *>((R) + so + 12); \
+        const float4 y4 = *reinterpret_cast<const float4 *>((R) + so + 16);                                                 \
+        vb[0] = fmaf(y2.y, d, vb[0]); vb[1] = fmaf(y2.z, d, vb[1]); vb[2] = fmaf(y2.w, d, vb[2]);                           \
+        vb[3] = fmaf(y3.x, d, vb[3]); vb[4] = fmaf(y3.y, d, vb[4]); vb[5] = fmaf(y3.z, d, vb[5]);                           \
+        const float dl_ = dll0 * (d);                                                                                       \
+        u[0] = fmaf(y3.w, dl_, u[0]); u[1] = fmaf(y4.x, dl_, u[1]); u[2] = fmaf(y4.y, dl_, u[2]);                           \
+    }
+                            SIDE_UPD(R0, d0) SIDE_UPD(R1, d1) SIDE_UPD(R2, d2)
+                        }
                     }
                     __syncwarp(env_mask);
                     if (is_robot) {
