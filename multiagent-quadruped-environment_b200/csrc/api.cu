@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 static thread_local std::string g_err;
@@ -247,10 +249,43 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
         // links belong to their leg, base colliders are dealt round-robin (probes) or to leg 0 (capsules); lists keep table order)
         {
             const size_t mf = sizeof(MqeRobotModel) / 4;
-            std::vector<float> hdr(mf + 1316 + 80, 0.f);
+            const size_t ACTW = 1380;                                    // physics.cu ACTW_FLOATS
+            std::vector<float> hdr(mf + ACTW + 80, 0.f);
             memcpy(hdr.data(), &d->model, sizeof(MqeRobotModel));
-            memcpy(hdr.data() + mf, aw.data(), 1316 * sizeof(float));
-            int *tbl = reinterpret_cast<int *>(hdr.data() + mf + 1316);
+            { const char *e = getenv("MQE_ACT_MMA"); p.act_mma = (e && e[0] == '0') ? 0 : 1; }
+            if (!p.act_mma) memcpy(hdr.data() + mf, aw.data(), 1316 * sizeof(float));
+            else {
+                // fp16 hi / lo fragment table of the actuator net for mma.sync (k_substeps P1): B operands in the per-lane register
+                // order of m16n8k8 (layer 0, K = 6 padded to 8) and m16n8k16 (layer 1), then b0, b1, W2, b2 as floats
+                auto h16 = [](float v) { return (uint32_t)__half_as_ushort(__float2half_rn(v)); };
+                auto hi_lo = [&](float e0, float e1, uint32_t &hi, uint32_t &lo) {
+                    const uint32_t h0 = h16(e0), h1 = h16(e1);
+                    hi = h0 | (h1 << 16);
+                    const float r0 = e0 - __half2float(__ushort_as_half((unsigned short)h0)), r1 = e1 - __half2float(__ushort_as_half((unsigned short)h1));
+                    lo = h16(r0) | (h16(r1) << 16);
+                };
+                uint32_t *fr = reinterpret_cast<uint32_t *>(hdr.data() + mf);
+                auto W0 = [&](int n, int k) { return k < 6 ? w.act_w0[n * 6 + k] : 0.f; };
+                auto W1 = [&](int n, int k) { return w.act_w1[n * 32 + k]; };
+                for (int lane = 0; lane < 32; lane++) {
+                    const int g = lane >> 2, t = lane & 3;
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t hi, lo;
+                        hi_lo(W0(8 * j + g, 2 * t), W0(8 * j + g, 2 * t + 1), hi, lo);
+                        fr[(0 * 32 + lane) * 4 + j] = hi; fr[(1 * 32 + lane) * 4 + j] = lo;
+                        for (int s2 = 0; s2 < 2; s2++) {
+                            uint32_t h0, l0, h1, l1;
+                            hi_lo(W1(8 * j + g, 16 * s2 + 2 * t), W1(8 * j + g, 16 * s2 + 2 * t + 1), h0, l0);
+                            hi_lo(W1(8 * j + g, 16 * s2 + 2 * t + 8), W1(8 * j + g, 16 * s2 + 2 * t + 9), h1, l1);
+                            uint32_t *q = fr + ((2 + j * 2 + s2) * 32 + lane) * 4;
+                            q[0] = h0; q[1] = h1; q[2] = l0; q[3] = l1;
+                        }
+                    }
+                }
+                float *ft = hdr.data() + mf + 1280;
+                memcpy(ft, w.act_b0, 32 * 4); memcpy(ft + 32, w.act_b1, 32 * 4); memcpy(ft + 64, w.act_w2, 32 * 4); ft[96] = w.act_b2[0];
+            }
+            int *tbl = reinterpret_cast<int *>(hdr.data() + mf + ACTW);
             for (int lg = 0; lg < 4; lg++) {
                 int n = 0, nbase = 0;
                 for (int pi = 0; pi < d->model.n_probes; pi++) {

@@ -49,7 +49,10 @@
 #define ES_MASKSZ(G) (((G) * (G) + 3) & ~3)
 #define PDESCF 12      // pair-contact descriptor (global scratch): n3, body a, body b, point3, gap, packed (X, ci, Y, cj)
 
-#define ACTW_FLOATS 1316   // 192 + 32 + 1024 + 32 + 32 + 1 = 1313, padded
+#define ACTW_PLAIN 1316    // W0[32][6] b0[32] W1T[32][32] b1[32] W2[32] b2 = 1313 floats, padded (FFMA path, k_actuator)
+#define ACTW_FLOATS 1380   // actuator-net region of the CTA header: the plain table, or (MMA path) the fp16 hi / lo fragment table:
+                           // uint4 frag[10][32 lanes] (W0 hi, W0 lo, then {hi.b0, hi.b1, lo.b0, lo.b1} per (n-tile, k-step) of W1),
+                           // then b0[32] b1[32] W2[32] b2 as floats at 1280
 #define TBL_INTS 80        // per-leg probe lists [4][10] (count + 9 ids), per-leg capsule lists [4][10]
 
 __host__ __device__ inline int physics_warp_smem_floats(int A, int P, int E, int spair, int maxpair) {
@@ -394,6 +397,36 @@ __device__ __forceinline__ float robot_side_regs(int k, V3 r, V3 d, V3 a1, V3 a2
     return dd;
 }
 
+// ---- actuator network on the tensor cores (mma.sync, fp16 hi / lo split, fp32 accumulate) -------------------------------------------
+// 12 joints x E x A robots = up to 96 rows per warp and substep through 6 -> 32 -> 32 -> 1 (unitree_go1.pt, go1.py:369-380): a batched MLP
+// that cost 3.6 k warp instructions per substep as FFMA2 chains.  Every operand is split into fp16 hi + lo and three MMAs
+// (hi*hi + hi*lo + lo*hi) accumulate in fp32 -- the dropped lo*lo term is < 2^-22 relative, i.e. fp32-level results.
+__device__ __forceinline__ uint32_t pack_h2(float e0, float e1) {        // low half = e0 (lower column / k index), high half = e1
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+__device__ __forceinline__ void split_h2(float e0, float e1, uint32_t &hi, uint32_t &lo) {
+    hi = pack_h2(e0, e1);
+    float h0, h1;
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+    lo = pack_h2(e0 - h0, e1 - h1);
+}
+__device__ __forceinline__ void mma_k8(float *c, uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void mma_k16(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// x / (1 + |x|) with MUFU.RCP alone (<= 1 ulp of the quotient; the Newton step of softsign() buys nothing at the tolerances in use)
+__device__ __forceinline__ float softsign_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + fabsf(x)));
+    return x * r;
+}
+
 // Contact blocks.  The three rows of a contact (normal, two friction directions) are solved as ONE block per Gauss-Seidel sweep: the
 // three J.w are formed together from the velocity at the start of the block, and the effect of the block's own earlier updates is added
 // through the coupling terms K_ij = J_i . (M^-1 J_j^T) = J_i . Y_j (i > j), stored in the pad floats of rows 1 and 2.  Algebraically
@@ -550,6 +583,100 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 const float lim = md->tau_limit[j];
                 tau[k] = fminf(fmaxf(t, -lim), lim);
             }
+        } else if (p.act_mma) {
+            // ---- tensor-core path.  Rows of the batched MLP: (joint k, lane L) -> m-tile (k, L / 16), row L % 16.
+            float x[3][6];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int i = 0; i < 6; i++) x[k][i] = 0.f;
+            if (active && is_robot) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    int j = 3 * leg + k;
+                    float a = act[k] * p.action_scale;
+                    if (k == 0) a *= p.hip_scale;
+                    if (p.lag_ring) {      // lag_buffer = lag_buffer[1:] + [actions_scaled]; target = lag_buffer[0] (go1.py:337-339), as a ring
+                        float *ring = p.lag_ring + (size_t)m_idx * p.lag_n * 12 + j;
+                        const int c = lag_c0 + sub;
+                        ring[(c % p.lag_n) * 12] = a;
+                        a = ring[((c + 1) % p.lag_n) * 12];
+                    }
+                    float err = q[k] - (a + md->q_default[j]);
+                    x[k][0] = err; x[k][1] = e1[k]; x[k][2] = e2[k]; x[k][3] = qd[k]; x[k][4] = v1[k]; x[k][5] = v2[k];
+                    e2[k] = e1[k]; e1[k] = err; v2[k] = v1[k]; v1[k] = qd[k];
+                }
+            }
+            // stage the inputs as fp16 hi / lo rows [96][8] in row storage that is dead until P3 (robots 0 and 1 of the warp)
+            uint32_t *xh = reinterpret_cast<uint32_t *>(wbase + RS_ROWS);
+            uint32_t *xl = reinterpret_cast<uint32_t *>(wbase + RS_SIZE + RS_ROWS);
+            float *outs = wbase + RS_SIZE + RS_ROWS + 384;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                uint4 h4, l4;
+                split_h2(x[k][0], x[k][1], h4.x, l4.x); split_h2(x[k][2], x[k][3], h4.y, l4.y); split_h2(x[k][4], x[k][5], h4.z, l4.z);
+                h4.w = 0u; l4.w = 0u;
+                reinterpret_cast<uint4 *>(xh)[k * 32 + lane] = h4;
+                reinterpret_cast<uint4 *>(xl)[k * 32 + lane] = l4;
+            }
+            __syncwarp();
+            const int fg = lane >> 2, ft = lane & 3;
+            const uint4 *frag = reinterpret_cast<const uint4 *>(actw);
+            const float *fb0 = actw + 1280, *fb1 = actw + 1312, *fw2 = actw + 1344;
+            const uint4 w0h = frag[lane], w0l = frag[32 + lane];
+            const int mtiles = 2 * 3;
+#pragma unroll 1
+            for (int mt = 0; mt < mtiles; mt++) {
+                const int k = mt >> 1, hf = mt & 1;
+                if (16 * hf >= nrl) continue;                        // no robot lane in this half of the warp
+                const int r0 = (k * 32 + 16 * hf + fg) * 4 + ft;
+                const uint32_t ah0 = xh[r0], ah1 = xh[r0 + 32], al0 = xl[r0], al1 = xl[r0 + 32];
+                float c[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 b = *reinterpret_cast<const float2 *>(fb0 + 8 * j + 2 * ft);
+                    c[j][0] = c[j][2] = b.x; c[j][1] = c[j][3] = b.y;
+                }
+                const uint32_t w0hj[4] = {w0h.x, w0h.y, w0h.z, w0h.w}, w0lj[4] = {w0l.x, w0l.y, w0l.z, w0l.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) { mma_k8(c[j], ah0, ah1, w0hj[j]); mma_k8(c[j], ah0, ah1, w0lj[j]); mma_k8(c[j], al0, al1, w0hj[j]); }
+                uint32_t a2h[2][4], a2l[2][4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) c[j][i] = softsign_fast(c[j][i]);
+#pragma unroll
+                for (int s2 = 0; s2 < 2; s2++) {                     // C fragments of n-tiles 2s, 2s+1 ARE the A fragment of k-step s
+                    split_h2(c[2 * s2][0], c[2 * s2][1], a2h[s2][0], a2l[s2][0]); split_h2(c[2 * s2][2], c[2 * s2][3], a2h[s2][1], a2l[s2][1]);
+                    split_h2(c[2 * s2 + 1][0], c[2 * s2 + 1][1], a2h[s2][2], a2l[s2][2]); split_h2(c[2 * s2 + 1][2], c[2 * s2 + 1][3], a2h[s2][3], a2l[s2][3]);
+                }
+                float vlo = 0.f, vhi = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 b = *reinterpret_cast<const float2 *>(fb1 + 8 * j + 2 * ft);
+                    float d[4] = {b.x, b.y, b.x, b.y};
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; s2++) {
+                        const uint4 w = frag[(2 + j * 2 + s2) * 32 + lane];      // hi.b0 hi.b1 lo.b0 lo.b1
+                        mma_k16(d, a2h[s2], w.x, w.y); mma_k16(d, a2h[s2], w.z, w.w); mma_k16(d, a2l[s2], w.x, w.y);
+                    }
+                    const float2 w2 = *reinterpret_cast<const float2 *>(fw2 + 8 * j + 2 * ft);
+                    vlo = fmaf(w2.y, softsign_fast(d[1]), fmaf(w2.x, softsign_fast(d[0]), vlo));
+                    vhi = fmaf(w2.y, softsign_fast(d[3]), fmaf(w2.x, softsign_fast(d[2]), vhi));
+                }
+                vlo += __shfl_xor_sync(FULL, vlo, 1); vhi += __shfl_xor_sync(FULL, vhi, 1);
+                vlo += __shfl_xor_sync(FULL, vlo, 2); vhi += __shfl_xor_sync(FULL, vhi, 2);
+                if (ft == 0) { outs[k * 32 + 16 * hf + fg] = vlo + actw[1376]; outs[k * 32 + 16 * hf + fg + 8] = vhi + actw[1376]; }
+            }
+            __syncwarp();
+            if (active && is_robot) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float lim = md->tau_limit[3 * leg + k];
+                    tau[k] = fminf(fmaxf(outs[k * 32 + lane], -lim), lim);
+                }
+            }
+            __syncwarp();                                            // the staging area becomes row storage again in P3
         } else if (active && is_robot) {
             float x[3][6];
 #pragma unroll
@@ -1176,35 +1303,64 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 my_smem = min(npair, E * spair - my_start);
             }
         }
-        if (G > 1 && (is_robot || is_npc)) {
-            if (pairs_pending) {
-                // ---- rows: one (contact, direction) per lane and round instead of all six sides in the lane that found the hit
-                for (int item = rank_in_env; item < 3 * npair; item += lanes_per_env) {
-                    const int slot = item / 3, dch = item - 3 * slot;
-                    const float *ds = pdesc + slot * PDESCF;
-                    const V3 cn = mk(ds[0], ds[1], ds[2]), cpos = mk(ds[5], ds[6], ds[7]);
-                    const float cgap = ds[8];
-                    const unsigned ent = (unsigned)__float_as_int(ds[9]);
-                    const int X = ent & 0xff, ci = (ent >> 8) & 0xff, Y = (ent >> 16) & 0xff, cj = ent >> 24;
-                    V3 t1, t2;
-                    tangent_basis(cn, t1, t2);
-                    const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
-                    const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
-                    const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
-                    const int la = X < A ? (int)md->caps[ci][0] : 0, lb = Y < A ? (int)md->caps[cj][0] : 0;
-                    const V3 ra = cpos - mk(ox[0], ox[1], ox[2]), rb_ = cpos - mk(oy[0], oy[1], oy[2]);
-                    const int lega = la > 0 ? (la - 1) / 3 : 0, legb = lb > 0 ? (lb - 1) / 3 : 0;
-                    const V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
-                    float *row = prow(item);
-                    float dd = X < A ? robot_side_from_smem(bx_, la, ra, d, row) : npc_side(p, ra, d, row);
-                    dd += Y < A ? robot_side_from_smem(by_, lb, rb_, -d, row + 20) : npc_side(p, rb_, -d, row + 20);
-                    row[18] = row[19] = row[38] = row[39] = 0.f;
-                    row[40] = 1.f / (dd + p.cfm);
-                    row[41] = dch == 0 ? contact_bias(p, cgap) : 0.f;
-                    row[42] = 0.f;
-                    row[43] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
+        if (G > 1) {
+            // ---- capsule-pair rows, WARP-wide: the env that found dynamic contacts borrows the lanes of the other envs of its warp (most substeps
+            // at most one env of a warp has any), one (contact, direction, side) per lane and round; the two sides of a row sit in
+            // neighbouring lanes and exchange their diagonal terms with one shuffle.  The operators it reads were published to shared
+            // memory above; the descriptors live in the env's global scratch.
+            unsigned pend = __ballot_sync(FULL, pairs_pending && is_robot && rank_in_env == 0);
+            while (pend) {
+                const int src = __ffs(pend) - 1;
+                pend &= pend - 1u;
+                const int h_eloc = __shfl_sync(FULL, e_loc, src), h_np = __shfl_sync(FULL, npair, src), h_env = __shfl_sync(FULL, env, src);
+                const int h_start = __shfl_sync(FULL, my_start, src), h_smem = __shfl_sync(FULL, my_smem, src);
+                const float *h_pdesc = p.pdesc_scratch + (size_t)h_env * ((size_t)maxpair * PDESCF);
+                float *const h_gp = p.prow_scratch + (size_t)h_env * ((size_t)maxpair * 3 * PROWF);
+                auto hrow = [&](int i) -> float * { return i < 3 * h_smem ? pool + (3 * h_start + i) * PROWF : h_gp + (i - 3 * h_smem) * PROWF; };
+                const int total = 6 * h_np;
+                for (int t0 = 0; t0 < total; t0 += 32) {
+                    const int t = t0 + lane;
+                    const bool on = t < total;
+                    const int slot = t / 6, rem = t - 6 * slot, dch = rem >> 1, side = rem & 1;
+                    float dd = 0.f, cgap = 0.f;
+                    float *row = nullptr;
+                    int X = 0, Y = 0, lega = 0, legb = 0;
+                    if (on) {
+                        const float *ds = h_pdesc + slot * PDESCF;
+                        const V3 cn = mk(ds[0], ds[1], ds[2]), cpos = mk(ds[5], ds[6], ds[7]);
+                        cgap = ds[8];
+                        const unsigned ent = (unsigned)__float_as_int(ds[9]);
+                        X = ent & 0xff; Y = (ent >> 16) & 0xff;
+                        const int ci = (ent >> 8) & 0xff, cj = ent >> 24;
+                        V3 t1, t2;
+                        tangent_basis(cn, t1, t2);
+                        const int la = X < A ? (int)md->caps[ci][0] : 0, lb = Y < A ? (int)md->caps[cj][0] : 0;
+                        lega = la > 0 ? (la - 1) / 3 : 0; legb = lb > 0 ? (lb - 1) / 3 : 0;
+                        const int Z = side ? Y : X, lz = side ? lb : la;                      // this lane's side of the row
+                        const float *bz = Z < A ? wbase + (h_eloc * A + Z) * RS_SIZE : wbase + E * A * RS_SIZE + (h_eloc * P + Z - A) * NS_SIZE;
+                        const float *oz = bz + (Z < A ? RS_ORIGIN : NS_ORIGIN);
+                        const V3 rz = cpos - mk(oz[0], oz[1], oz[2]);
+                        V3 d = dch == 0 ? cn : (dch == 1 ? t1 : t2);
+                        if (side) d = -d;
+                        row = hrow(3 * slot + dch);
+                        dd = Z < A ? robot_side_from_smem(bz, lz, rz, d, row + 20 * side) : npc_side(p, rz, d, row + 20 * side);
+                    }
+                    const float dd_other = __shfl_xor_sync(FULL, dd, 1);
+                    if (on && side == 0) {
+                        row[18] = row[19] = 0.f;
+                        row[40] = 1.f / ((dd + dd_other) + p.cfm);
+                        row[41] = dch == 0 ? contact_bias(p, cgap) : 0.f;
+                        row[42] = 0.f;
+                        row[43] = __int_as_float(X | (lega << 4) | (Y << 8) | (legb << 12) | ((dch ? 1 : 0) << 16) | ((3 * slot) << 20));
+                    } else if (on) {
+                        row[38] = row[39] = 0.f;
+                    }
                 }
+                __syncwarp();                                  // both sides of every row are in place
+                for (int c = lane; c < h_np; c += 32) pair_block_coupling(hrow(3 * c), hrow(3 * c + 1), hrow(3 * c + 2));
             }
+        }
+        if (G > 1 && (is_robot || is_npc)) {
             SUB_MARK(14);
             if (obb) {
                 // robot probes on the plank / the push box: canonical order = robot ascending, probe-table order (two-pass compaction)
@@ -1284,8 +1440,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 }
                 npair = min(npair + total, maxpair);
             }
-            if (npair > 0) {                                   // uniform over the env's lanes
-                __syncwarp(env_mask);                              // rows of a contact were written by up to three lanes
+            if (obb && npair > 0) {                            // uniform over the env's lanes (capsule contacts were done in the warp-wide pass; recomputing them is idempotent)
+                __syncwarp(env_mask);                              // rows of a contact were written by the lane that owns the probe
                 for (int c = rank_in_env; c < npair; c += lanes_per_env) pair_block_coupling(prow(3 * c), prow(3 * c + 1), prow(3 * c + 2));
             }
             if (rank_in_env == 0 && env < p.N) stat_pair += npair;
@@ -1584,7 +1740,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
 
 // stand-alone actuator network (parity tests against unitree_go1.pt): x [rows][6] -> torque [rows], unclipped
 __global__ void k_actuator(const float *__restrict__ aw, const float *__restrict__ x, int rows, float *__restrict__ out) {
-    __shared__ float w[ACTW_FLOATS];
+    __shared__ float w[ACTW_PLAIN];
     for (int i = threadIdx.x; i < 1313; i += blockDim.x) w[i] = aw[i];
     __syncthreads();
     int r = blockIdx.x * blockDim.x + threadIdx.x;

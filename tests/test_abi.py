@@ -84,5 +84,5 @@ def test_substep_launch_plan_residency():
         for N in (1, 7, 4096, 32768):
             b = fn(N, A, Pd, Eenv, maxpair)
             assert 0 < b <= LIMIT, (task, N, b)
-    assert fn(4096, 2, 0, 4, 8) == 230688          # 8 KB header + 7 warps x 4 envs x 7.9 KB
+    assert fn(4096, 2, 0, 4, 8) == 230944          # 8.3 KB header + 7 warps x 4 envs x 7.9 KB
     assert fn(4, 2, 0, 4, 8) < 48 * 1024           # a single warp of envs needs no opt-in at all
