@@ -1074,6 +1074,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         // ================================================================ P3b: dynamic-vs-dynamic pairs (capsule / capsule)
         int npair = 0;
         bool pairs_pending = false;                      // capsule contacts recorded in pdesc, rows not built yet
+        bool need_narrow = false;                        // this env's capsule masks are live: run the narrow phase for it
         unsigned t_sub = 0;
         if (p.trace && rank_in_env == 0) t_sub = (unsigned)clock();
         if (G > 1 && (is_robot || is_npc)) {
@@ -1170,124 +1171,114 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 if (env >= p.N) live_any = false;
                 __syncwarp(env_mask);
                 SUB_MARK(12);
-                const bool any_live = __ballot_sync(env_mask, live_any) != 0u;
-                if (any_live) {
-                    // ---- narrow phase.  Candidates are enumerated from the masks -- capsule ci of X (bit set in mask[X][Y])
-                    // against capsule cj of Y (bit set in mask[Y][X]), groups X < Y, ci then cj ascending: the oracle's loop
-                    // order restricted to pairs that can touch, so contact slots come out in the same canonical order.
-                    // Hits only record a descriptor; rows are built afterwards by all lanes of the env.
-                    // Stage 1: a bounding-sphere test per capsule pair (centre distance against half lengths + radii + offset; it
-                    // can only pass pairs the exact test might accept) compacts the candidates, still in canonical order, into a
-                    // per-env list.  ci runs over the set bits of mask[X][Y] for all lanes together; lane `rank` owns the set bits
-                    // number rank, rank + L, rank + 2L, ... of mask[Y][X], so every round covers L consecutive cj in order.
-                    int *cand = p.cand_scratch + (size_t)env * max_cand;
-                    int ncand = 0;
-                    for (int X = 0; X < min(A, Gc - 1); X++)                        // pairs with a robot on the X side (robot-robot, robot-NPC)
-                        for (int Y = X + 1; Y < Gc; Y++) {
-                            const unsigned mXY = (unsigned)capmask[X * G + Y], mYX = (unsigned)capmask[Y * G + X];
-                            if (!mXY || !mYX) continue;                                  // uniform over the env's lanes
-                            const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
-                            const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
-                            const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
-                            const float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
-                            const float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
-                            if (!(dx * dx + dy * dy + dz * dz <= lim * lim)) continue;
-                            unsigned mine = 0;
-                            {
-                                unsigned t = mYX;
-                                int idx = 0, next = rank_in_env;
-                                while (t) {
-                                    const unsigned low = t & (0u - t);
-                                    if (idx == next) { mine |= low; next += lanes_per_env; }
-                                    t ^= low; idx++;
-                                }
-                            }
-                            const int rounds = (__popc(mYX) + lanes_per_env - 1) / lanes_per_env;
-                            for (unsigned ma = mXY; ma; ma &= ma - 1u) {
-                                const int ci = __ffs(ma) - 1;
-                                const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP);
-                                const V3 a0 = mk(ca[0], ca[1], ca[2]), a1 = mk(ca[3], ca[4], ca[5]);
-                                const V3 cA = 0.5f * (a0 + a1), dA = a1 - a0;
-                                const float reachA = 0.5f * sqrtf(dot(dA, dA)) + ca[6] + p.coff;
-                                unsigned mb = mine;
-                                for (int r = 0; r < rounds; r++) {
-                                    bool ok = false;
-                                    int cj = 0;
-                                    if (mb) {
-                                        cj = __ffs(mb) - 1;
-                                        mb &= mb - 1u;
-                                        const float *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
-                                        const V3 b0 = mk(cb[0], cb[1], cb[2]), b1 = mk(cb[3], cb[4], cb[5]);
-                                        const V3 dc = cA - 0.5f * (b0 + b1), dB = b1 - b0;
-                                        const float reach = (reachA + 0.5f * sqrtf(dot(dB, dB)) + cb[6]) * 1.0001f + 1e-6f;
-                                        ok = dot(dc, dc) <= reach * reach;
-                                    }
-                                    const unsigned ob = __ballot_sync(env_mask, ok);
-                                    if (ok) cand[ncand + __popc(ob & ((1u << lane) - 1u))] = X | (ci << 8) | (Y << 16) | (cj << 24);
-                                    ncand += __popc(ob);
-                                }
-                            }
-                        }
-                    // NPC-NPC pairs have one capsule each: a pair whose two masks are set IS the candidate, so they are appended L pairs per
-                    // round (lexicographic (X, Y) order, after every pair with a robot on the X side: still the canonical order)
-                    {
-                        const int Pn = Gc - A, npp = Pn * (Pn - 1) / 2;
-                        for (int t0 = 0; t0 < npp; t0 += lanes_per_env) {
-                            const int t = t0 + rank_in_env;
+                need_narrow = __ballot_sync(env_mask, live_any) != 0u;
+            }
+        }
+        __syncwarp();
+        if (G > 1) {
+            // ---- narrow phase, WARP-wide.  An env whose capsule masks are live borrows all 32 lanes of its warp (most substeps at most one
+            // env of a warp has robots within reach of each other).  Candidates are enumerated from the masks -- capsule ci of X (bit set in
+            // mask[X][Y]) against capsule cj of Y (bit set in mask[Y][X]), groups X < Y, ci then cj ascending: the oracle's loop order
+            // restricted to pairs that can touch, so contact slots come out in the same canonical order (ballot compaction keeps lane =
+            // item order).  Stage 1: a bounding-sphere test per capsule pair (it can only pass pairs the exact test might accept) compacts
+            // the candidates into a per-env list; stage 2: the exact segment / segment test.  Hits only record a descriptor; rows are built
+            // afterwards, also warp-wide.
+            unsigned pendn = __ballot_sync(FULL, need_narrow && is_robot && rank_in_env == 0);
+            while (pendn) {
+                const int src = __ffs(pendn) - 1;
+                pendn &= pendn - 1u;
+                const int h_eloc = __shfl_sync(FULL, e_loc, src), h_env = __shfl_sync(FULL, env, src);
+                const int *cm = reinterpret_cast<const int *>(pool + E * spair * 3 * PROWF) + h_eloc * ES_MASKSZ(G);
+                int *cand = p.cand_scratch + (size_t)h_env * max_cand;
+                float *h_pdesc = p.pdesc_scratch + (size_t)h_env * ((size_t)maxpair * PDESCF);
+                auto gblock = [&](int Z) -> const float * { return Z < A ? wbase + (h_eloc * A + Z) * RS_SIZE : wbase + E * A * RS_SIZE + (h_eloc * P + Z - A) * NS_SIZE; };
+                int ncand = 0;
+                for (int X = 0; X < min(A, Gc - 1); X++)                        // pairs with a robot on the X side (robot-robot, robot-NPC)
+                    for (int Y = X + 1; Y < Gc; Y++) {
+                        const unsigned mXY = (unsigned)cm[X * G + Y], mYX = (unsigned)cm[Y * G + X];
+                        if (!mXY || !mYX) continue;                                  // uniform over the warp
+                        const float *bx_ = gblock(X), *by_ = gblock(Y);
+                        const float *ox = bx_ + (X < A ? RS_ORIGIN : NS_ORIGIN), *oy = by_ + (Y < A ? RS_ORIGIN : NS_ORIGIN);
+                        const float bx = X < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen, by = Y < A ? MQE_ROBOT_BOUND : p.npc_radius + p.npc_halflen;
+                        const float lim = bx + by + p.coff, dx = ox[0] - oy[0], dy = ox[1] - oy[1], dz = ox[2] - oy[2];
+                        if (!(dx * dx + dy * dy + dz * dz <= lim * lim)) continue;
+                        const int nY = __popc(mYX), total = __popc(mXY) * nY;
+                        for (int t0 = 0; t0 < total; t0 += 32) {
+                            const int t = t0 + lane;
                             bool ok = false;
-                            int X = 0, Y = 0;
-                            if (t < npp) {
-                                int i = 0, rem = t;
-                                while (rem >= Pn - 1 - i) { rem -= Pn - 1 - i; i++; }
-                                X = A + i; Y = X + 1 + rem;
-                                ok = capmask[X * G + Y] && capmask[Y * G + X];
+                            int ci = 0, cj = 0;
+                            if (t < total) {
+                                ci = __fns(mXY, 0, t / nY + 1); cj = __fns(mYX, 0, t % nY + 1);     // the (t / nY)-th capsule of X against the (t % nY)-th of Y
+                                const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
+                                const V3 a0 = mk(ca[0], ca[1], ca[2]), a1 = mk(ca[3], ca[4], ca[5]), b0 = mk(cb[0], cb[1], cb[2]), b1 = mk(cb[3], cb[4], cb[5]);
+                                const V3 dA = a1 - a0, dB = b1 - b0, dc = 0.5f * (a0 + a1) - 0.5f * (b0 + b1);
+                                const float reachA = 0.5f * sqrtf(dot(dA, dA)) + ca[6] + p.coff;
+                                const float reach = (reachA + 0.5f * sqrtf(dot(dB, dB)) + cb[6]) * 1.0001f + 1e-6f;
+                                ok = dot(dc, dc) <= reach * reach;
                             }
-                            const unsigned ob = __ballot_sync(env_mask, ok);
-                            if (ok) cand[ncand + __popc(ob & ((1u << lane) - 1u))] = X | (Y << 16);
+                            const unsigned ob = __ballot_sync(FULL, ok);
+                            if (ok) cand[ncand + __popc(ob & ((1u << lane) - 1u))] = X | (ci << 8) | (Y << 16) | (cj << 24);
                             ncand += __popc(ob);
                         }
                     }
-                    __syncwarp(env_mask);
-                    // Stage 2: exact segment / segment test on the candidates
-                    for (int t0 = 0; t0 < ncand; t0 += lanes_per_env) {
-                        const int c = t0 + rank_in_env;
-                        bool hit = false;
-                        V3 cn = mk(0, 0, 0), cpos = mk(0, 0, 0);
-                        float cgap = 0.f;
-                        int X = 0, Y = 0, ci = 0, cj = 0;
-                        if (c < ncand) {
-                            const unsigned ent = (unsigned)cand[c];
-                            X = ent & 0xff; ci = (ent >> 8) & 0xff; Y = (ent >> 16) & 0xff; cj = ent >> 24;
-                            const float *bx_ = X < A ? wbase + (e_loc * A + X) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + X - A) * NS_SIZE;
-                            const float *by_ = Y < A ? wbase + (e_loc * A + Y) * RS_SIZE : wbase + E * A * RS_SIZE + (e_loc * P + Y - A) * NS_SIZE;
-                            const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
-                            V3 c1, c2;
-                            seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
-                            V3 dv = c1 - c2;
-                            float dist = sqrtf(dot(dv, dv));
-                            cgap = dist - ca[6] - cb[6];
-                            if (cgap < p.coff && dist >= 1e-9f) {
-                                hit = true;
-                                cn = (1.f / dist) * dv;
-                                cpos = c2 + (cb[6] + 0.5f * cgap) * cn;
-                            }
+                // NPC-NPC pairs have one capsule each: a pair whose two masks are set IS the candidate (lexicographic (X, Y) order, after
+                // every pair with a robot on the X side: still the canonical order)
+                {
+                    const int Pn = Gc - A, npp = Pn * (Pn - 1) / 2;
+                    for (int t0 = 0; t0 < npp; t0 += 32) {
+                        const int t = t0 + lane;
+                        bool ok = false;
+                        int X = 0, Y = 0;
+                        if (t < npp) {
+                            int i = 0, rem = t;
+                            while (rem >= Pn - 1 - i) { rem -= Pn - 1 - i; i++; }
+                            X = A + i; Y = X + 1 + rem;
+                            ok = cm[X * G + Y] && cm[Y * G + X];
                         }
-                        const unsigned hb = __ballot_sync(env_mask, hit);
-                        const int slot = npair + __popc(hb & ((1u << lane) - 1u));
-                        npair += __popc(hb);
-                        if (hit && slot < maxpair) {
-                            float *ds = pdesc + slot * PDESCF;
-                            const int rba = X < A ? X * MQE_NUM_BODIES + (int)md->caps[ci][1] : A * MQE_NUM_BODIES + (X - A);
-                            const int rbb = Y < A ? Y * MQE_NUM_BODIES + (int)md->caps[cj][1] : A * MQE_NUM_BODIES + (Y - A);
-                            ds[0] = cn.x; ds[1] = cn.y; ds[2] = cn.z; ds[3] = __int_as_float(rba); ds[4] = __int_as_float(rbb);
-                            ds[5] = cpos.x; ds[6] = cpos.y; ds[7] = cpos.z; ds[8] = cgap;
-                            ds[9] = __int_as_float(X | (ci << 8) | (Y << 16) | (cj << 24));
+                        const unsigned ob = __ballot_sync(FULL, ok);
+                        if (ok) cand[ncand + __popc(ob & ((1u << lane) - 1u))] = X | (Y << 16);
+                        ncand += __popc(ob);
+                    }
+                }
+                __syncwarp();
+                // Stage 2: exact segment / segment test on the candidates
+                int np = 0;
+                for (int t0 = 0; t0 < ncand; t0 += 32) {
+                    const int c = t0 + lane;
+                    bool hit = false;
+                    V3 cn = mk(0, 0, 0), cpos = mk(0, 0, 0);
+                    float cgap = 0.f;
+                    int X = 0, Y = 0, ci = 0, cj = 0;
+                    if (c < ncand) {
+                        const unsigned ent = (unsigned)cand[c];
+                        X = ent & 0xff; ci = (ent >> 8) & 0xff; Y = (ent >> 16) & 0xff; cj = ent >> 24;
+                        const float *bx_ = gblock(X), *by_ = gblock(Y);
+                        const float *ca = bx_ + (X < A ? RS_CAP + ci * 7 : NS_CAP), *cb = by_ + (Y < A ? RS_CAP + cj * 7 : NS_CAP);
+                        V3 c1, c2;
+                        seg_seg(mk(ca[0], ca[1], ca[2]), mk(ca[3], ca[4], ca[5]), mk(cb[0], cb[1], cb[2]), mk(cb[3], cb[4], cb[5]), c1, c2);
+                        V3 dv = c1 - c2;
+                        float dist = sqrtf(dot(dv, dv));
+                        cgap = dist - ca[6] - cb[6];
+                        if (cgap < p.coff && dist >= 1e-9f) {
+                            hit = true;
+                            cn = (1.f / dist) * dv;
+                            cpos = c2 + (cb[6] + 0.5f * cgap) * cn;
                         }
                     }
-                    npair = min(npair, maxpair);
-                    pairs_pending = npair > 0;
-                    SUB_MARK(13);
+                    const unsigned hb = __ballot_sync(FULL, hit);
+                    const int slot = np + __popc(hb & ((1u << lane) - 1u));
+                    np += __popc(hb);
+                    if (hit && slot < maxpair) {
+                        float *ds = h_pdesc + slot * PDESCF;
+                        const int rba = X < A ? X * MQE_NUM_BODIES + (int)md->caps[ci][1] : A * MQE_NUM_BODIES + (X - A);
+                        const int rbb = Y < A ? Y * MQE_NUM_BODIES + (int)md->caps[cj][1] : A * MQE_NUM_BODIES + (Y - A);
+                        ds[0] = cn.x; ds[1] = cn.y; ds[2] = cn.z; ds[3] = __int_as_float(rba); ds[4] = __int_as_float(rbb);
+                        ds[5] = cpos.x; ds[6] = cpos.y; ds[7] = cpos.z; ds[8] = cgap;
+                        ds[9] = __int_as_float(X | (ci << 8) | (Y << 16) | (cj << 24));
+                    }
                 }
+                np = min(np, maxpair);
+                if ((is_robot || is_npc) && e_loc == h_eloc) { npair = np; pairs_pending = np > 0; }
             }
         }
         __syncwarp();
