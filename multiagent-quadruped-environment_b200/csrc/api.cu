@@ -52,6 +52,7 @@ struct MqeSim {
     cudaStream_t aux_stream = nullptr;   // forked policy: adaptation branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool fork_policy = false;
+    bool fused_policy = false;           // one layer-0 launch + one fused tail kernel (default in the tensor-core modes)
     WrapParams wrap = {};                // fused task-wrapper gather (mqe_sim_set_wrapper); kind 0 = off
     // what the learner reads after a step, packed (MQE_BUF_STEP_RESULT): wrapper obs | reward | done
     unsigned char *d_result = nullptr, *h_result = nullptr;
@@ -327,6 +328,8 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     }
     { const char *e = getenv("MQE_TC_TAIL"); s->tail_fp32 = e && e[0] == '0'; }
     { const char *e = getenv("MQE_POLICY_FORK"); s->fork_policy = (p.policy_mode != MQE_POLICY_FP32) && !s->tail_fp32 && !(e && e[0] == '0'); }
+    { const char *e = getenv("MQE_POLICY_FUSED"); s->fused_policy = (p.policy_mode != MQE_POLICY_FP32) && !s->tail_fp32 && !(e && e[0] == '0'); }
+    if (s->fused_policy) s->fork_policy = false;
     if (s->fork_policy) {
         CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
@@ -560,9 +563,19 @@ int mqe_sim_reset(MqeSim *s) {
     return exchange_impl(s);                                      // ranks reset together: the global observation is exchanged as after a step
 }
 
-static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, const unsigned short *lo, int head, int rows, float *latent, float *act) {
+// finish: the simulation step (policy_impl) lets the fused tail kernel do k_policy_finish's work; returns 1 in *finished if it did
+static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, const unsigned short *lo, int head, int rows, float *latent, float *act,
+                       int finish = 0, int *finished = nullptr) {
     PolicyScratch ps = s->ps;
     ps.latent = latent; ps.act = act;
+    if (finished) *finished = 0;
+    if (s->fused_policy) {
+        int nf = 0;
+        CK(mqe_launch_policy_tc_fused(s->tcw, s->pw, ps, s->p, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->p.ctr, finish, s->stream, &nf));
+        s->launches += nf;
+        if (finished) *finished = finish;
+        return MQE_OK;
+    }
     if (s->fork_policy) {
         int nf = 0;
         CK(mqe_launch_policy_tc_forked(s->tcw, s->pw, ps, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->p.ctr, s->stream, s->aux_stream,
@@ -589,10 +602,11 @@ static int policy_impl(MqeSim *s, const float *d_actions, bool device_ctr) {
     CK(cudaSetDevice(s->device));
     const int slot = (s->head + 1) % MQE_HIST_FRAMES;
     CK(mqe_launch_policy_frame(s->p, d_actions, device_ctr ? -1 : slot, s->stream));
-    int rc = run_network(s, s->p.hist_f32, s->p.hist_hi, s->p.hist_lo, device_ctr ? -1 : slot, s->M, s->ps.latent, s->ps.act);
+    int finished = 0;
+    int rc = run_network(s, s->p.hist_f32, s->p.hist_hi, s->p.hist_lo, device_ctr ? -1 : slot, s->M, s->ps.latent, s->ps.act, 1, &finished);
     if (rc != MQE_OK) return rc;
-    CK(mqe_launch_policy_finish(s->p, s->ps.act, s->stream));
-    s->launches += 2;
+    if (!finished) { CK(mqe_launch_policy_finish(s->p, s->ps.act, s->stream)); s->launches += 1; }
+    s->launches += 1;                                    // k_policy_frame
     return MQE_OK;
 }
 int mqe_sim_policy(MqeSim *s, const float *d_actions) {

@@ -35,6 +35,9 @@ cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const float *b0cat
                                     int head, int rows, int passes, float *Z, int planes_out, const int *ctr, cudaStream_t st);
 cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, int M, int passes,
                                       cudaStream_t st, int *launches);
+cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
+                                       const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes, const int *ctr,
+                                       int finish, cudaStream_t st, int *launches);
 cudaError_t mqe_launch_task_gather(const DevParams &p, const WrapParams &w, int mode, cudaStream_t st);
 cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const unsigned short *hist_hi,
                                         const unsigned short *hist_lo, int head, int M, int passes, const int *ctr, cudaStream_t st, cudaStream_t aux,

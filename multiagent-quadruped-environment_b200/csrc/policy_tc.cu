@@ -439,6 +439,277 @@ __global__ void k_body_latent_planes(const float *__restrict__ Z, const float *_
     *reinterpret_cast<uint4 *>(o_lo + o) = lo;
 }
 
+// ---------------------------------------------------------------------------------------------- fused policy tail
+// Everything behind layer 0 for one 128-row tile in ONE kernel (SURVEY 7 hard part 4):
+//     adapt.2 (256 -> 128, ELU) -> adapt.4 (128 -> 2) = latent                                  (go1.py:400-403)
+//     body.0 finish: ELU(Z_body + W_lat latent) -> body.2 (512 -> 256, ELU) -> body.4 (256 -> 128, ELU) -> body.6 (128 -> 12)   (go1.py:404-407)
+//     last_locomotion_action(s) shift + clip to +-clip_actions                                  (go1.py:40-41, 104-106)
+// Activations never leave the SM: the A operand of body.2 is produced chunk by chunk (64 columns) by the epilogue warps straight into the
+// pipeline stage from Z and the latent, the A operand of body.4 from body.2's TMEM accumulator; only the weights stream in by bulk copy.
+// TMEM: adapt.2 accumulator cols [0,128), body.2 [128,384), body.4 [384,512).  Sixteen stage fills through a 2-stage ring:
+//     fills 0..3   adapt.2  : A planes (hi, lo) + W planes by bulk copy                         64 KB
+//     fills 4..11  body.2   : W planes of both 128-column tiles by bulk copy (64 KB), A chunk written by the epilogue warps (32 KB)
+//     fills 12..15 body.4   : W planes by bulk copy (32 KB), A chunk written by the epilogue warps from TMEM (32 KB)
+// Barriers per stage: full_w (weights landed, tx count), full_a (8 epilogue warps wrote the A chunk), empty (MMAs that read it retired).
+#define FT_STAGE_BYTES (96 * 1024)
+#define FT_THREADS 320
+struct TailArgs {
+    const unsigned short *a0_hi, *a0_lo;                 // adapt.0 activation planes (K = 256), from layer 0's epilogue
+    const float *Z;                                      // layer-0 output [M][768]; columns 256.. = body.0 pre-activation without the latent
+    const unsigned short *wa_hi, *wa_lo, *wb1_hi, *wb1_lo, *wb2_hi, *wb2_lo;   // tail weights, pre-tiled (tile_layer, 128-row tiles)
+    const float *ba1, *bb1, *bb2;                        // biases of adapt.2, body.2, body.4
+    const float *aw2, *ab2, *bw3, *bb3, *wlat;           // heads (fp32): adapt.4 [2][128], body.6 [12][128]; latent columns of body.0 [512][2]
+    float *latent, *act;                                 // [M][2], [M][12]
+    int M, passes, finish;                               // finish: also do k_policy_finish's work (simulation step; not for mqe_policy_forward)
+};
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full_w = reinterpret_cast<uint64_t *>(smem + 2 * FT_STAGE_BYTES);
+    uint64_t *full_a = full_w + 2, *empty = full_a + 2, *acc_done = empty + 2;     // acc_done[3]: adapt.2, body.2, body.4
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 3);
+    float *sf = reinterpret_cast<float *>(smem + 2 * FT_STAGE_BYTES + 128);
+    float *s_ba1 = sf, *s_bb1 = sf + 128, *s_bb2 = sf + 384, *s_hwA = sf + 512, *s_hwB = sf + 768, *s_lat = sf + 2304, *s_part = sf + 2560;   // .. + 1536
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mtile = blockIdx.x, M = a.M;
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < 128; i += FT_THREADS) { s_ba1[i] = a.ba1[i]; s_bb2[i] = a.bb2[i]; }
+    for (int i = threadIdx.x; i < 256; i += FT_THREADS) { s_bb1[i] = a.bb1[i]; s_hwA[i] = a.aw2[i]; }
+    for (int i = threadIdx.x; i < 1536; i += FT_THREADS) s_hwB[i] = a.bw3[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(&full_w[i], 1); mbar_init(&full_a[i], 8); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 3; i++) mbar_init(&acc_done[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                              // set-up above ran in the predecessor's shadow
+    const int passes = a.passes;
+    const uint32_t PL = 128 * LT_BK * 2;                     // one 128-row x 64-k plane: 16 KB
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int f = 0; f < 16; f++) {
+                const int st = f & 1;
+                mbar_wait(&empty[st], ((f >> 1) & 1) ^ 1);
+                unsigned char *sb = smem + st * FT_STAGE_BYTES;
+                if (f < 4) {                                 // adapt.2: A chunk f of the adapt.0 planes + W chunk f
+                    mbar_expect_tx(&full_w[st], passes == 3 ? 4 * PL : 2 * PL);
+                    const size_t ao = ((size_t)mtile * 4 + f) * (128 * LT_BK), wo = (size_t)f * (128 * LT_BK);
+                    bulk_g2s(sb, a.a0_hi + ao, PL, &full_w[st]);
+                    bulk_g2s(sb + 2 * PL, a.wa_hi + wo, PL, &full_w[st]);
+                    if (passes == 3) { bulk_g2s(sb + PL, a.a0_lo + ao, PL, &full_w[st]); bulk_g2s(sb + 3 * PL, a.wa_lo + wo, PL, &full_w[st]); }
+                } else if (f < 12) {                         // body.2: W chunk j of both 128-column tiles (tile_layer: [n-tile][k-chunk][..])
+                    const int j = f - 4;
+                    mbar_expect_tx(&full_w[st], passes == 3 ? 4 * PL : 2 * PL);
+                    for (int nt = 0; nt < 2; nt++) {
+                        const size_t wo = ((size_t)nt * 8 + j) * (128 * LT_BK);
+                        bulk_g2s(sb + (2 + 2 * nt) * PL, a.wb1_hi + wo, PL, &full_w[st]);
+                        if (passes == 3) bulk_g2s(sb + (3 + 2 * nt) * PL, a.wb1_lo + wo, PL, &full_w[st]);
+                    }
+                } else {                                     // body.4: W chunk j
+                    const int j = f - 12;
+                    mbar_expect_tx(&full_w[st], passes == 3 ? 2 * PL : PL);
+                    const size_t wo = (size_t)j * (128 * LT_BK);
+                    bulk_g2s(sb + 2 * PL, a.wb2_hi + wo, PL, &full_w[st]);
+                    if (passes == 3) bulk_g2s(sb + 3 * PL, a.wb2_lo + wo, PL, &full_w[st]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);     // D fp32, A/B bf16 K-major, N = 128, M = 128
+            const uint64_t hiD = ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);      // 128-row planes: LBO 2 KB, SBO 128 B
+            constexpr uint32_t kStep = (2 * 2048) >> 4;      // two 8-wide k-chunks per MMA
+            for (int f = 0; f < 16; f++) {
+                const int st = f & 1;
+                mbar_wait(&full_w[st], (f >> 1) & 1);
+                if (f >= 4) mbar_wait(&full_a[st], ((f - 4) >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sb = smem_u32(smem + st * FT_STAGE_BYTES);
+                auto D = [&](uint32_t off) { return hiD | (uint64_t)(((sb + off) & 0x3FFFFu) >> 4); };
+                const uint64_t dAh = D(0), dAl = D(PL);
+                const int ntiles = (f >= 4 && f < 12) ? 2 : 1;
+                const int first = (f == 0 || f == 4 || f == 12);
+                for (int nt = 0; nt < ntiles; nt++) {
+                    const uint64_t dBh = D((2 + 2 * nt) * PL), dBl = D((3 + 2 * nt) * PL);
+                    const uint32_t d_tmem = tmem + (f < 4 ? 0u : (f < 12 ? 128u + 128u * nt : 384u));
+#pragma unroll
+                    for (int j = 0; j < LT_BK / 16; j++) umma_f16(d_tmem, dAh + j * kStep, dBh + j * kStep, idesc, (first && j == 0) ? 0u : 1u);
+                    if (passes == 3) {
+#pragma unroll
+                        for (int j = 0; j < LT_BK / 16; j++) umma_f16(d_tmem, dAh + j * kStep, dBl + j * kStep, idesc, 1u);
+#pragma unroll
+                        for (int j = 0; j < LT_BK / 16; j++) umma_f16(d_tmem, dAl + j * kStep, dBh + j * kStep, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty[st]);
+                if (f == 3) umma_commit(&acc_done[0]);
+                if (f == 11) umma_commit(&acc_done[1]);
+                if (f == 15) umma_commit(&acc_done[2]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;       // TMEM lane quarter this warp may read; the two warps of a quarter split the columns
+        const int r = q * 32 + lane, row = mtile * 128 + r;    // this thread's row of the tile
+        const int et = (int)threadIdx.x - 64;                 // 0..255 among the epilogue threads
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        // ---- adapt.2 epilogue: bias + ELU, head adapt.4 in fp32 from the accumulator row -> latent ----
+        mbar_wait(&acc_done[0], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            float h0 = 0.f, h1 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                uint32_t v[16];
+                const int col = half * 64 + c * 16;
+                tmem_ld16(trow + (uint32_t)col, v);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float t = elu1_tc(__uint_as_float(v[i]) + s_ba1[col + i]);
+                    h0 = fmaf(t, s_hwA[col + i], h0); h1 = fmaf(t, s_hwA[128 + col + i], h1);
+                }
+            }
+            if (half == 1) { s_part[r * 2] = h0; s_part[r * 2 + 1] = h1; }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (half == 0) {
+                const float l0 = (h0 + s_part[r * 2]) + __ldg(a.ab2), l1 = (h1 + s_part[r * 2 + 1]) + __ldg(a.ab2 + 1);
+                s_lat[r * 2] = l0; s_lat[r * 2 + 1] = l1;
+                if (row < M) { a.latent[(size_t)row * 2] = l0; a.latent[(size_t)row * 2 + 1] = l1; }
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+        // ---- body.2 A operand: ELU(Z_body + W_lat latent), one 64-column chunk per fill, written in the canonical K-major layout ----
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            const int f = 4 + j, st = f & 1;
+            mbar_wait(&empty[st], ((f >> 1) & 1) ^ 1);
+            unsigned char *sb = smem + st * FT_STAGE_BYTES;
+            const int m = et & 127, grow = mtile * 128 + m;
+            const float l0 = s_lat[m * 2], l1 = s_lat[m * 2 + 1];
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const int kc = (et >> 7) * 4 + cc;            // 8-wide k-chunk inside the 64-column chunk
+                float v[8];
+                if (grow < M) {
+                    const float *z = a.Z + (size_t)grow * 768 + 256 + j * 64 + kc * 8;
+                    const float4 z0 = *reinterpret_cast<const float4 *>(z), z1 = *reinterpret_cast<const float4 *>(z + 4);
+                    v[0] = z0.x; v[1] = z0.y; v[2] = z0.z; v[3] = z0.w; v[4] = z1.x; v[5] = z1.y; v[6] = z1.z; v[7] = z1.w;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int n = j * 64 + kc * 8 + i;
+                        v[i] = elu1_tc(v[i] + __ldg(a.wlat + n * 2) * l0 + __ldg(a.wlat + n * 2 + 1) * l1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = 0.f;
+                }
+                uint4 hi, lo;
+                split_bf16x8(v, hi, lo);
+                *reinterpret_cast<uint4 *>(sb + ((size_t)kc * 128 + m) * 16) = hi;
+                *reinterpret_cast<uint4 *>(sb + PL + ((size_t)kc * 128 + m) * 16) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_a[st])) : "memory");
+        }
+        // ---- body.4 A operand: ELU(body.2 accumulator + bias) from TMEM, 64 columns per fill ----
+        mbar_wait(&acc_done[1], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+            const int f = 12 + j, st = f & 1;
+            mbar_wait(&empty[st], ((f >> 1) & 1) ^ 1);
+            unsigned char *sb = smem + st * FT_STAGE_BYTES;
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                uint32_t v[16];
+                const int col = j * 64 + half * 32 + c * 16;  // column of body.2's output = k index of body.4
+                tmem_ld16(trow + 128u + (uint32_t)col, v);
+                float fv[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) fv[i] = elu1_tc(__uint_as_float(v[i]) + s_bb1[col + i]);
+                uint4 hi, lo;
+                const int kc = half * 4 + c * 2;
+                split_bf16x8(fv, hi, lo);
+                *reinterpret_cast<uint4 *>(sb + ((size_t)kc * 128 + r) * 16) = hi;
+                *reinterpret_cast<uint4 *>(sb + PL + ((size_t)kc * 128 + r) * 16) = lo;
+                split_bf16x8(fv + 8, hi, lo);
+                *reinterpret_cast<uint4 *>(sb + ((size_t)(kc + 1) * 128 + r) * 16) = hi;
+                *reinterpret_cast<uint4 *>(sb + PL + ((size_t)(kc + 1) * 128 + r) * 16) = lo;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_a[st])) : "memory");
+        }
+        // ---- body.4 epilogue: bias + ELU, head body.6 in fp32 -> action; then the shift / clip of k_policy_finish ----
+        mbar_wait(&acc_done[2], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            float hp[12];
+#pragma unroll
+            for (int o = 0; o < 12; o++) hp[o] = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; c++) {
+                uint32_t v[16];
+                const int col = half * 64 + c * 16;
+                tmem_ld16(trow + 384u + (uint32_t)col, v);
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float t = elu1_tc(__uint_as_float(v[i]) + s_bb2[col + i]);
+#pragma unroll
+                    for (int o = 0; o < 12; o++) hp[o] = fmaf(t, s_hwB[o * 128 + col + i], hp[o]);
+                }
+            }
+            if (half == 1)
+#pragma unroll
+                for (int o = 0; o < 12; o++) s_part[r * 12 + o] = hp[o];
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (half == 0 && row < M) {
+#pragma unroll
+                for (int o = 0; o < 12; o++) {
+                    const float act = (hp[o] + s_part[r * 12 + o]) + __ldg(a.bb3 + o);
+                    a.act[(size_t)row * 12 + o] = act;
+                    if (a.finish) {                          // go1.py:104-106 + :40-41
+                        const size_t t = (size_t)row * 12 + o;
+                        p.loc_last2[t] = p.loc_last[t];
+                        p.loc_last[t] = act;
+                        p.actions[t] = fminf(fmaxf(act, -p.clip_actions), p.clip_actions);
+                    }
+                }
+            }
+        }
+        if (a.finish && blockIdx.x == 0) {                    // the rest of k_policy_finish: nothing reads these before the next kernel
+            for (int t = et; t < p.N; t += 256) p.hist_dirty[t] = 0;
+            if (et < 5) p.stats[et] = 0;
+            if (et == 0) p.ctr[0] = (p.ctr[0] + 1) % MQE_HIST_FRAMES;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+#define FT_SMEM_BYTES (2 * FT_STAGE_BYTES + 128 + (2560 + 1536) * 4)
+
 // ---------------------------------------------------------------------------------------------- host side
 static inline unsigned short f2bf_rne(float v) {
     uint32_t b;
@@ -515,6 +786,7 @@ extern "C" int mqe_policy_tc_prepare(const MqeWeights *w, int rows, PolicyTcWeig
     if (cudaFuncSetAttribute(k_linear_tc<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(128)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_linear_tc<128, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(128)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(k_linear_tc<128, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes(128)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(k_policy_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES) != cudaSuccess) return -1;
     out->blob = blob;
     out->bytes = total * sizeof(unsigned short);
     out->l0_hi = blob;
@@ -531,6 +803,32 @@ extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const f
     return launch_heavy(k_policy_l0_tc, grid, dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                       (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
                       planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0);
+}
+
+// Fused policy (default): ONE layer-0 launch over all 768 columns (the six column tiles of a row tile are neighbours in launch order, so the
+// history planes are fetched from HBM once and shared through L2), then ONE kernel for everything behind it (k_policy_tail).  With
+// k_policy_frame in front that is three launches for preprocess_action (go1.py:64-108).
+extern "C" cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
+                                                  const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes, const int *ctr,
+                                                  int finish, cudaStream_t st, int *launches) {
+    const int mt = (M + 127) / 128;
+    cudaError_t e;
+    if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0)) != cudaSuccess) return e;
+    TailArgs a;
+    a.a0_hi = (const unsigned short *)w.p_hi[0]; a.a0_lo = (const unsigned short *)w.p_lo[0];
+    a.Z = s.Z;
+    a.wa_hi = (const unsigned short *)w.t_hi[0]; a.wa_lo = (const unsigned short *)w.t_lo[0];
+    a.wb1_hi = (const unsigned short *)w.t_hi[2]; a.wb1_lo = (const unsigned short *)w.t_lo[2];
+    a.wb2_hi = (const unsigned short *)w.t_hi[3]; a.wb2_lo = (const unsigned short *)w.t_lo[3];
+    a.ba1 = pw.ab1; a.bb1 = pw.bb1; a.bb2 = pw.bb2;
+    a.aw2 = pw.aw2; a.ab2 = pw.ab2; a.bw3 = pw.bw3; a.bb3 = pw.bb3; a.wlat = pw.wlat;
+    a.latent = s.latent; a.act = s.act;
+    a.M = M; a.passes = passes; a.finish = finish;
+    // plain stream order (not PDL): a 213 KB-per-CTA grid that becomes resident early would take SMs from layer 0's last wave
+    if ((e = launch_heavy(k_policy_tail, dim3(mt), dim3(FT_THREADS), FT_SMEM_BYTES, st, a, p)) != cudaSuccess) return e;
+    *launches += 2;
+    return cudaGetLastError();
 }
 
 // Forked policy: the adaptation branch (layer-0 columns 0..255 -> adapt.2 -> adapt.4 = latent) runs on a second stream next to the body's
