@@ -53,6 +53,8 @@ struct MqeSim {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool fork_policy = false;
     bool fused_policy = false;           // one layer-0 launch + one fused tail kernel (default in the tensor-core modes)
+    bool incremental = false;            // incremental layer 0: the 29 known frames of the next step are contracted behind this step's physics
+    int zold_head = -1;                  // ring slot (of the NEXT frame) the partial sums in ps.Zold were computed for; -1: none
     WrapParams wrap = {};                // fused task-wrapper gather (mqe_sim_set_wrapper); kind 0 = off
     // what the learner reads after a step, packed (MQE_BUF_STEP_RESULT): wrapper obs | reward | done
     unsigned char *d_result = nullptr, *h_result = nullptr;
@@ -330,7 +332,8 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     { const char *e = getenv("MQE_POLICY_FORK"); s->fork_policy = (p.policy_mode != MQE_POLICY_FP32) && !s->tail_fp32 && !(e && e[0] == '0'); }
     { const char *e = getenv("MQE_POLICY_FUSED"); s->fused_policy = (p.policy_mode != MQE_POLICY_FP32) && !s->tail_fp32 && !(e && e[0] == '0'); }
     if (s->fused_policy) s->fork_policy = false;
-    if (s->fork_policy) {
+    { const char *e = getenv("MQE_POLICY_INCR"); s->incremental = s->fused_policy && !(e && e[0] == '0'); }
+    if (s->fork_policy || s->incremental) {
         CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
@@ -380,6 +383,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     if (p.policy_mode != MQE_POLICY_FP32) { CK(dalloc(s, &p.hist_hi, ring_tc)); CK(dalloc(s, &p.hist_lo, ring_tc)); }
     CK(dalloc(s, &s->ps.Z, (size_t)M * 768)); CK(dalloc(s, &s->ps.T1, (size_t)M * 128)); CK(dalloc(s, &s->ps.T2, (size_t)M * 256));
     CK(dalloc(s, &s->ps.T3, (size_t)M * 128)); CK(dalloc(s, &s->ps.latent, (size_t)M * 2)); CK(dalloc(s, &s->ps.act, (size_t)M * 12));
+    if (s->incremental) CK(dalloc(s, &s->ps.Zold, (size_t)M * 768));
     CK(dalloc(s, &s->d_actions_stage, s->action_bytes() / sizeof(float)));
     CK(cudaMemsetAsync(p.reset_buf, 1, N, s->stream));                      // base_task.py:77: reset_buf starts as ones
     // _prepare_locomotion_policy: locomotion_obs = default command frame (go1.py:393-394); actors at their start poses
@@ -565,10 +569,17 @@ int mqe_sim_reset(MqeSim *s) {
 
 // finish: the simulation step (policy_impl) lets the fused tail kernel do k_policy_finish's work; returns 1 in *finished if it did
 static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, const unsigned short *lo, int head, int rows, float *latent, float *act,
-                       int finish = 0, int *finished = nullptr) {
+                       int finish = 0, int *finished = nullptr, bool incr = false) {
     PolicyScratch ps = s->ps;
     ps.latent = latent; ps.act = act;
     if (finished) *finished = 0;
+    if (s->incremental && incr) {                        // the 29 older frames are already in ps.Zold: only the new frame's K = 80 GEMM, then the tail
+        int nf = 0;
+        CK(mqe_launch_policy_tc_incremental(s->tcw, s->pw, ps, s->p, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->p.ctr, finish, s->stream, &nf));
+        s->launches += nf;
+        if (finished) *finished = finish;
+        return MQE_OK;
+    }
     if (s->fused_policy) {
         int nf = 0;
         CK(mqe_launch_policy_tc_fused(s->tcw, s->pw, ps, s->p, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->p.ctr, finish, s->stream, &nf));
@@ -603,13 +614,26 @@ static int policy_impl(MqeSim *s, const float *d_actions, bool device_ctr) {
     const int slot = (s->head + 1) % MQE_HIST_FRAMES;
     CK(mqe_launch_policy_frame(s->p, d_actions, device_ctr ? -1 : slot, s->stream));
     int finished = 0;
-    int rc = run_network(s, s->p.hist_f32, s->p.hist_hi, s->p.hist_lo, device_ctr ? -1 : slot, s->M, s->ps.latent, s->ps.act, 1, &finished);
+    if (s->incremental && !device_ctr && s->zold_head != slot) {     // no partial sums for this slot yet (first step, or after an explicit call): prime them now
+        CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->ps.Zold, s->p.ctr, s->stream));
+        s->launches += 1;
+    }
+    int rc = run_network(s, s->p.hist_f32, s->p.hist_hi, s->p.hist_lo, device_ctr ? -1 : slot, s->M, s->ps.latent, s->ps.act, 1, &finished, true);
     if (rc != MQE_OK) return rc;
     if (!finished) { CK(mqe_launch_policy_finish(s->p, s->ps.act, s->stream)); s->launches += 1; }
     s->launches += 1;                                    // k_policy_frame
     return MQE_OK;
 }
-int mqe_sim_policy(MqeSim *s, const float *d_actions) {
+// incremental layer 0: contract the 29 frames the NEXT step already knows (every slot but the one its frame will go to)
+static int l0_old_impl(MqeSim *s, bool device_ctr, cudaStream_t st) {
+    const int next_slot = (s->head + 2) % MQE_HIST_FRAMES;            // s->head still names the previous step's slot here
+    CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, device_ctr ? -1 : next_slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1,
+                                s->ps.Zold, s->p.ctr, st));
+    s->launches += 1;
+    s->zold_head = next_slot;
+    return MQE_OK;
+}
+int mqe_sim_policy(MqeSim *s, const float *d_actions) {      // stand-alone call: the 29-frame pass runs in line (policy_impl primes it)
     int rc = policy_impl(s, d_actions, false);
     if (rc == MQE_OK) s->head = (s->head + 1) % MQE_HIST_FRAMES;
     return rc;
@@ -653,6 +677,14 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
         rc = MQE_OK;
     }
     if (rc != MQE_OK) return rc;
+    const bool bg = s->incremental && s->p.control_type == 0;
+    if (bg) {                                            // fork: next step's 29-frame layer-0 pass, low priority, behind this step's physics
+        CK(cudaEventRecord(s->ev_fork, s->stream));
+        CK(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+        rc = l0_old_impl(s, device_ctr, s->aux_stream);
+        if (rc != MQE_OK) return rc;
+        CK(cudaEventRecord(s->ev_join, s->aux_stream));
+    }
     rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: k_policy_finish / k_joint_actions zeroed the statistics
     if (rc != MQE_OK) return rc;
     rc = post_impl(s, device_ctr);
@@ -661,7 +693,9 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
         CK(mqe_launch_task_gather(s->p, s->wrap, 0, s->stream));
         s->launches += 1;
     }
-    return exchange_impl(s);
+    rc = exchange_impl(s);
+    if (bg) CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));     // join: the ring must not move under the background pass
+    return rc;
 }
 
 static int step_any(MqeSim *s, const float *d_actions);
@@ -693,7 +727,9 @@ static int step_any(MqeSim *s, const float *d_actions) {
             const long long l0 = s->launches;
             CK(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
             s->stream = s->cap_stream;
+            const int keep_zold = s->zold_head;                   // capturing executes nothing: host mirrors must not move
             rc = step_plain(s, s->d_actions_stage, true);
+            s->zold_head = keep_zold;
             s->stream = user;
             cudaGraph_t graph = nullptr;
             cudaError_t ce = cudaStreamEndCapture(s->cap_stream, &graph);
@@ -709,11 +745,21 @@ static int step_any(MqeSim *s, const float *d_actions) {
             s->graphs.push_back(ng);
             g = &s->graphs.back();
         }
+        if (s->incremental && s->p.control_type == 0 && s->zold_head != (s->head + 1) % MQE_HIST_FRAMES) {
+            // the previous call was not a full step (e.g. mqe_sim_policy): the partial sums the graph expects do not exist yet
+            const int slot = (s->head + 1) % MQE_HIST_FRAMES;
+            CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->ps.Zold, s->p.ctr, s->stream));
+            s->launches += 1;
+        }
         CK(cudaGraphLaunch(g->exec, s->stream));
         s->launches += g->launches;
         rc = MQE_OK;
     }
-    if (rc == MQE_OK) { s->head = (s->head + 1) % MQE_HIST_FRAMES; s->step_count++; if (s->gather.world) s->gather_seq++; }
+    if (rc == MQE_OK) {
+        s->head = (s->head + 1) % MQE_HIST_FRAMES; s->step_count++;
+        if (s->gather.world) s->gather_seq++;
+        if (s->incremental && s->p.control_type == 0) s->zold_head = (s->head + 1) % MQE_HIST_FRAMES;     // every step leaves the next step's partial sums behind
+    }
     return rc;
 }
 

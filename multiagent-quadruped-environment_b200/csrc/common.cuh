@@ -118,14 +118,38 @@ static inline int mqe_pdl_level() {
     static const int level = [] { const char *e = getenv("MQE_PDL"); return e ? atoi(e) : 1; }();
     return level;
 }
+// Launch priorities (captured into the step graph as kernel-node attributes): the kernels on the critical path of a step get the
+// device's greatest priority, the incremental layer-0 pass for the NEXT step (launch_background) the least, so the block scheduler
+// places its CTAs only on SMs the step's own grids do not want -- the idle tail of k_substeps.
+static inline void mqe_priority_range(int *least, int *greatest) {
+    static int lo = 0, hi = 0, init = 0;
+    if (!init) { if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { cudaGetLastError(); lo = hi = 0; } init = 1; }
+    *least = lo; *greatest = hi;
+}
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl_if(bool allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    int least, greatest;
+    mqe_priority_range(&least, &greatest);
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = greatest;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = allow ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>      // work for the next step that may only use what the current step leaves idle
+static inline cudaError_t launch_background(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    int least, greatest;
+    mqe_priority_range(&least, &greatest);
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = allow ? 1 : 0;
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = least;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 template <typename... KArgs, typename... Args>      // short kernels of the policy tail

@@ -15,7 +15,7 @@ struct PolicyTcWeights {            // bf16 hi/lo planes, pre-tiled (policy_tc.c
     const void *t_hi[5], *t_lo[5];   // tail layer weights
     void *p_hi[5], *p_lo[5];         // activation planes between layers (sized for `rows`)
 };
-struct PolicyScratch { float *Z, *T1, *T2, *T3, *latent, *act; };
+struct PolicyScratch { float *Z, *T1, *T2, *T3, *latent, *act, *Zold; };   // Zold: layer-0 partial sums of the 29 known frames (incremental layer 0)
 
 extern "C" {
 cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, cudaStream_t st);
@@ -38,6 +38,11 @@ cudaError_t mqe_launch_policy_tail_tc(const PolicyTcWeights &w, const PolicyWeig
 cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
                                        const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes, const int *ctr,
                                        int finish, cudaStream_t st, int *launches);
+cudaError_t mqe_launch_policy_l0_old(const PolicyTcWeights &w, const unsigned short *hist_hi, const unsigned short *hist_lo, int head_next,
+                                     int M, int passes, float *Zold, const int *ctr, cudaStream_t st);
+cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
+                                             const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes,
+                                             const int *ctr, int finish, cudaStream_t st, int *launches);
 cudaError_t mqe_launch_task_gather(const DevParams &p, const WrapParams &w, int mode, cudaStream_t st);
 cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const unsigned short *hist_hi,
                                         const unsigned short *hist_lo, int head, int M, int passes, const int *ctr, cudaStream_t st, cudaStream_t aux,

@@ -19,6 +19,9 @@
 
 #include "kernels.cuh"
 
+extern "C" cudaError_t mqe_launch_policy_tail_only(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p, int M,
+                                                   int passes, int finish, cudaStream_t st);
+
 #define TC_TILE_ELEMS (10 * 128 * 8)
 #define TC_TILE_BYTES (TC_TILE_ELEMS * 2)
 #define TC_STAGES 2
@@ -74,7 +77,12 @@ __global__ void __launch_bounds__(320, 1)
 k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo,
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
                const float *__restrict__ b0cat, float *__restrict__ Z, unsigned short *__restrict__ a0_hi,
-               unsigned short *__restrict__ a0_lo, int M, int head, int passes, const int *__restrict__ ctr, int ntile0) {
+               unsigned short *__restrict__ a0_lo, int M, int head, int passes, const int *__restrict__ ctr, int ntile0,
+               int mode, float *__restrict__ Zold, const unsigned char *__restrict__ dirty, int agents) {
+    // mode 0: all 30 slots.  Incremental layer 0 (29 of the 30 history frames of the NEXT step are known as soon as this step's frame is in
+    // the ring): mode 1 = the 29 slots other than `head` (the slot the next frame will go to), raw accumulators -> Zold, launched at low
+    // priority behind the physics of the step so that it fills the idle tail of k_substeps; mode 2 = slot `head` alone (K = 80), plus
+    // Zold (dropped for rows whose history was just reset: `dirty`), then the normal epilogue.
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t *empty = full + TC_STAGES;
@@ -98,13 +106,15 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     pdl_wait();                                              // set-up above ran in the predecessor's shadow
-    if (head < 0) head = ctr[0];                             // graph replay: newest slot = the one k_policy_frame just wrote
+    if (head < 0) head = ctr[0];                             // graph replay: newest slot = the one k_policy_frame just wrote (mode 1: will write next)
     const uint32_t stage_tx = passes == 3 ? TC_STAGE_BYTES : 2 * TC_TILE_BYTES;
+    const int n_iter = mode == 0 ? MQE_HIST_FRAMES : (mode == 1 ? MQE_HIST_FRAMES - 1 : 1);
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int it = 0; it < MQE_HIST_FRAMES; it++) {
-                const int st = it & 1, ph = (it >> 1) & 1;
+            for (int i = 0; i < n_iter; i++) {
+                const int it = mode == 0 ? i : (mode == 1 ? (i < head ? i : i + 1) : head);     // ring slot of this k-iteration
+                const int st = i & 1, ph = (i >> 1) & 1;
                 mbar_wait(&empty[st], ph ^ 1);
                 mbar_expect_tx(&full[st], stage_tx);
                 int blk = it - head - 1;
@@ -125,7 +135,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B bf16 K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-            for (int it = 0; it < MQE_HIST_FRAMES; it++) {
+            for (int it = 0; it < n_iter; it++) {
                 const int st = it & 1, ph = (it >> 1) & 1;
                 mbar_wait(&full[st], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -166,6 +176,23 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int n0 = ntile * 128 + c * 32;
+            if (mode == 1) {                                // raw partial sums of the 29 known frames
+                if (row < M) {
+                    float *dst = Zold + (size_t)row * 768 + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<uint4 *>(dst + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+                continue;
+            }
+            if (mode == 2 && row < M && !dirty[row / agents]) {      // + the 29 older frames (a row whose history was reset keeps only the new frame)
+                const float *src = Zold + (size_t)row * 768 + n0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 z = *reinterpret_cast<const float4 *>(src + i);
+                    v[i] = __float_as_uint(__uint_as_float(v[i]) + z.x); v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + z.y);
+                    v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + z.z); v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + z.w);
+                }
+            }
             if (n0 < 256 && a0_hi) {                        // adapt.0: bias + ELU, emitted as bf16 hi/lo planes for adapt.2
                 float f[32];
 #pragma unroll
@@ -452,7 +479,8 @@ __global__ void k_body_latent_planes(const float *__restrict__ Z, const float *_
 //     fills 12..15 body.4   : W planes by bulk copy (32 KB), A chunk written by the epilogue warps from TMEM (32 KB)
 // Barriers per stage: full_w (weights landed, tx count), full_a (8 epilogue warps wrote the A chunk), empty (MMAs that read it retired).
 #define FT_STAGE_BYTES (96 * 1024)
-#define FT_THREADS 320
+#define FT_EPI_WARPS 16                                   // epilogue / A-operand producer warps: four per TMEM lane quarter
+#define FT_THREADS (64 + 32 * FT_EPI_WARPS)
 struct TailArgs {
     const unsigned short *a0_hi, *a0_lo;                 // adapt.0 activation planes (K = 256), from layer 0's epilogue
     const float *Z;                                      // layer-0 output [M][768]; columns 256.. = body.0 pre-activation without the latent
@@ -476,7 +504,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
     uint64_t *full_a = full_w + 2, *empty = full_a + 2, *acc_done = empty + 2;     // acc_done[3]: adapt.2, body.2, body.4
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 3);
     float *sf = reinterpret_cast<float *>(smem + 2 * FT_STAGE_BYTES + 128);
-    float *s_ba1 = sf, *s_bb1 = sf + 128, *s_bb2 = sf + 384, *s_hwA = sf + 512, *s_hwB = sf + 768, *s_lat = sf + 2304, *s_part = sf + 2560;   // .. + 1536
+    float *s_ba1 = sf, *s_bb1 = sf + 128, *s_bb2 = sf + 384, *s_hwA = sf + 512, *s_hwB = sf + 768, *s_lat = sf + 2304, *s_part = sf + 2560;   // .. + 4608: [128 rows][3 parts][12]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mtile = blockIdx.x, M = a.M;
     pdl_launch_dependents();
@@ -484,7 +512,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
     for (int i = threadIdx.x; i < 256; i += FT_THREADS) { s_bb1[i] = a.bb1[i]; s_hwA[i] = a.aw2[i]; }
     for (int i = threadIdx.x; i < 1536; i += FT_THREADS) s_hwB[i] = a.bw3[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) { mbar_init(&full_w[i], 1); mbar_init(&full_a[i], 8); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&full_w[i], 1); mbar_init(&full_a[i], FT_EPI_WARPS); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 3; i++) mbar_init(&acc_done[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -565,9 +593,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
         }
         __syncwarp();
     } else {
-        const int q = warp & 3, half = (warp - 2) >> 2;       // TMEM lane quarter this warp may read; the two warps of a quarter split the columns
+        const int q = warp & 3, part = (warp - 2) >> 2;       // TMEM lane quarter this warp may read; the four warps of a quarter split the columns
         const int r = q * 32 + lane, row = mtile * 128 + r;    // this thread's row of the tile
-        const int et = (int)threadIdx.x - 64;                 // 0..255 among the epilogue threads
+        const int et = (int)threadIdx.x - 64;                 // 0..511 among the epilogue threads
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         // ---- adapt.2 epilogue: bias + ELU, head adapt.4 in fp32 from the accumulator row -> latent ----
         mbar_wait(&acc_done[0], 0);
@@ -575,9 +603,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
         {
             float h0 = 0.f, h1 = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < 2; c++) {
                 uint32_t v[16];
-                const int col = half * 64 + c * 16;
+                const int col = part * 32 + c * 16;
                 tmem_ld16(trow + (uint32_t)col, v);
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
@@ -585,14 +613,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
                     h0 = fmaf(t, s_hwA[col + i], h0); h1 = fmaf(t, s_hwA[128 + col + i], h1);
                 }
             }
-            if (half == 1) { s_part[r * 2] = h0; s_part[r * 2 + 1] = h1; }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (half == 0) {
-                const float l0 = (h0 + s_part[r * 2]) + __ldg(a.ab2), l1 = (h1 + s_part[r * 2 + 1]) + __ldg(a.ab2 + 1);
+            if (part) { s_part[(r * 3 + part - 1) * 2] = h0; s_part[(r * 3 + part - 1) * 2 + 1] = h1; }
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * FT_EPI_WARPS) : "memory");
+            if (part == 0) {
+                const float l0 = (((h0 + s_part[(r * 3) * 2]) + s_part[(r * 3 + 1) * 2]) + s_part[(r * 3 + 2) * 2]) + __ldg(a.ab2);
+                const float l1 = (((h1 + s_part[(r * 3) * 2 + 1]) + s_part[(r * 3 + 1) * 2 + 1]) + s_part[(r * 3 + 2) * 2 + 1]) + __ldg(a.ab2 + 1);
                 s_lat[r * 2] = l0; s_lat[r * 2 + 1] = l1;
                 if (row < M) { a.latent[(size_t)row * 2] = l0; a.latent[(size_t)row * 2 + 1] = l1; }
             }
-            asm volatile("bar.sync 2, 256;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * FT_EPI_WARPS) : "memory");
         }
         // ---- body.2 A operand: ELU(Z_body + W_lat latent), one 64-column chunk per fill, written in the canonical K-major layout ----
 #pragma unroll 1
@@ -603,8 +632,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
             const int m = et & 127, grow = mtile * 128 + m;
             const float l0 = s_lat[m * 2], l1 = s_lat[m * 2 + 1];
 #pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
-                const int kc = (et >> 7) * 4 + cc;            // 8-wide k-chunk inside the 64-column chunk
+            for (int cc = 0; cc < 2; cc++) {
+                const int kc = (et >> 7) * 2 + cc;            // 8-wide k-chunk inside the 64-column chunk
                 float v[8];
                 if (grow < M) {
                     const float *z = a.Z + (size_t)grow * 768 + 256 + j * 64 + kc * 8;
@@ -636,16 +665,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
             const int f = 12 + j, st = f & 1;
             mbar_wait(&empty[st], ((f >> 1) & 1) ^ 1);
             unsigned char *sb = smem + st * FT_STAGE_BYTES;
-#pragma unroll 1
-            for (int c = 0; c < 2; c++) {
+            {
                 uint32_t v[16];
-                const int col = j * 64 + half * 32 + c * 16;  // column of body.2's output = k index of body.4
+                const int col = j * 64 + part * 16;           // column of body.2's output = k index of body.4
                 tmem_ld16(trow + 128u + (uint32_t)col, v);
                 float fv[16];
 #pragma unroll
                 for (int i = 0; i < 16; i++) fv[i] = elu1_tc(__uint_as_float(v[i]) + s_bb1[col + i]);
                 uint4 hi, lo;
-                const int kc = half * 4 + c * 2;
+                const int kc = part * 2;
                 split_bf16x8(fv, hi, lo);
                 *reinterpret_cast<uint4 *>(sb + ((size_t)kc * 128 + r) * 16) = hi;
                 *reinterpret_cast<uint4 *>(sb + PL + ((size_t)kc * 128 + r) * 16) = lo;
@@ -666,9 +694,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
 #pragma unroll
             for (int o = 0; o < 12; o++) hp[o] = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < 4; c++) {
+            for (int c = 0; c < 2; c++) {
                 uint32_t v[16];
-                const int col = half * 64 + c * 16;
+                const int col = part * 32 + c * 16;
                 tmem_ld16(trow + 384u + (uint32_t)col, v);
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
@@ -677,14 +705,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
                     for (int o = 0; o < 12; o++) hp[o] = fmaf(t, s_hwB[o * 128 + col + i], hp[o]);
                 }
             }
-            if (half == 1)
+            if (part)
 #pragma unroll
-                for (int o = 0; o < 12; o++) s_part[r * 12 + o] = hp[o];
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (half == 0 && row < M) {
+                for (int o = 0; o < 12; o++) s_part[(r * 3 + part - 1) * 12 + o] = hp[o];
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * FT_EPI_WARPS) : "memory");
+            if (part == 0 && row < M) {
 #pragma unroll
                 for (int o = 0; o < 12; o++) {
-                    const float act = (hp[o] + s_part[r * 12 + o]) + __ldg(a.bb3 + o);
+                    const float act = (((hp[o] + s_part[(r * 3) * 12 + o]) + s_part[(r * 3 + 1) * 12 + o]) + s_part[(r * 3 + 2) * 12 + o]) + __ldg(a.bb3 + o);
                     a.act[(size_t)row * 12 + o] = act;
                     if (a.finish) {                          // go1.py:104-106 + :40-41
                         const size_t t = (size_t)row * 12 + o;
@@ -696,7 +724,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
             }
         }
         if (a.finish && blockIdx.x == 0) {                    // the rest of k_policy_finish: nothing reads these before the next kernel
-            for (int t = et; t < p.N; t += 256) p.hist_dirty[t] = 0;
+            for (int t = et; t < p.N; t += 32 * FT_EPI_WARPS) p.hist_dirty[t] = 0;
             if (et < 5) p.stats[et] = 0;
             if (et == 0) p.ctr[0] = (p.ctr[0] + 1) % MQE_HIST_FRAMES;
         }
@@ -708,7 +736,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
-#define FT_SMEM_BYTES (2 * FT_STAGE_BYTES + 128 + (2560 + 1536) * 4)
+#define FT_SMEM_BYTES (2 * FT_STAGE_BYTES + 128 + (2560 + 4608) * 4)
 
 // ---------------------------------------------------------------------------------------------- host side
 static inline unsigned short f2bf_rne(float v) {
@@ -802,7 +830,7 @@ extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const f
     dim3 grid(6, (rows + 127) / 128);
     return launch_heavy(k_policy_l0_tc, grid, dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                       (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
-                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0);
+                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1);
 }
 
 // Fused policy (default): ONE layer-0 launch over all 768 columns (the six column tiles of a row tile are neighbours in launch order, so the
@@ -814,7 +842,15 @@ extern "C" cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, cons
     const int mt = (M + 127) / 128;
     cudaError_t e;
     if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0)) != cudaSuccess) return e;
+                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1)) != cudaSuccess) return e;
+    if ((e = mqe_launch_policy_tail_only(w, pw, s, p, M, passes, finish, st)) != cudaSuccess) return e;
+    *launches += 2;
+    return cudaGetLastError();
+}
+extern "C" cudaError_t mqe_launch_policy_tail_only(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p, int M,
+                                                   int passes, int finish, cudaStream_t st) {
+    const int mt = (M + 127) / 128;
+    cudaError_t e;
     TailArgs a;
     a.a0_hi = (const unsigned short *)w.p_hi[0]; a.a0_lo = (const unsigned short *)w.p_lo[0];
     a.Z = s.Z;
@@ -827,6 +863,30 @@ extern "C" cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, cons
     a.M = M; a.passes = passes; a.finish = finish;
     // plain stream order (not PDL): a 213 KB-per-CTA grid that becomes resident early would take SMs from layer 0's last wave
     if ((e = launch_heavy(k_policy_tail, dim3(mt), dim3(FT_THREADS), FT_SMEM_BYTES, st, a, p)) != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+// Incremental layer 0.  The first layer contracts the 30-frame history; 29 of the 30 frames of step t+1 are already in the ring when step t's
+// frame has been written.  mqe_launch_policy_l0_old (mode 1) contracts those 29 frames into Zold at LOW launch priority on a side stream
+// behind the policy of step t, i.e. concurrently with k_substeps / k_post_physics of step t, whose one-wave grid leaves ~30 % of the SM time
+// idle in its tail; step t+1 then only needs the K = 80 GEMM of its new frame (mode 2) in front of the fused tail.  preprocess_action's
+// critical path drops from frame + 96 us + tail to frame + ~6 us + tail.
+extern "C" cudaError_t mqe_launch_policy_l0_old(const PolicyTcWeights &w, const unsigned short *hist_hi, const unsigned short *hist_lo, int head_next,
+                                                int M, int passes, float *Zold, const int *ctr, cudaStream_t st) {
+    const int mt = (M + 127) / 128;
+    return launch_background(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+                             (const unsigned short *)w.l0_lo, (const float *)nullptr, (float *)nullptr, (unsigned short *)nullptr, (unsigned short *)nullptr,
+                             M, head_next, passes, ctr, 0, 1, Zold, (const unsigned char *)nullptr, 1);
+}
+extern "C" cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
+                                                        const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes,
+                                                        const int *ctr, int finish, cudaStream_t st, int *launches) {
+    const int mt = (M + 127) / 128;
+    cudaError_t e;
+    if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0,
+                          2, s.Zold, (const unsigned char *)p.hist_dirty, p.A)) != cudaSuccess) return e;
+    if ((e = mqe_launch_policy_tail_only(w, pw, s, p, M, passes, finish, st)) != cudaSuccess) return e;
     *launches += 2;
     return cudaGetLastError();
 }
@@ -851,11 +911,11 @@ extern "C" cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, con
     if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(aux, ev_fork, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(2, mt), dim3(320), TC_SMEM_BYTES, aux, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0)) != cudaSuccess) return e;
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_linear_tc<128, 2, false>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), aux, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, nou, nou, 0, M, 1, passes, h1)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ev_join, aux)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(4, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2)) != cudaSuccess) return e;
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2, 0, (float *)nullptr, (const unsigned char *)nullptr, 1)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes, none)) != cudaSuccess) return e;
