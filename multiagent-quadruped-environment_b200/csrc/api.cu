@@ -678,15 +678,17 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     }
     if (rc != MQE_OK) return rc;
     const bool bg = s->incremental && s->p.control_type == 0;
-    if (bg) {                                            // fork: next step's 29-frame layer-0 pass, low priority, behind this step's physics
-        CK(cudaEventRecord(s->ev_fork, s->stream));
+    if (bg) CK(cudaEventRecord(s->ev_fork, s->stream));   // fork point: the policy of this step is done, the ring holds its frame
+    rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: k_policy_finish / k_joint_actions zeroed the statistics
+    if (rc != MQE_OK) return rc;
+    if (bg) {
+        // next step's 29-frame layer-0 pass on the side stream, low priority, dependent on the fork point only.  It is enqueued AFTER
+        // k_substeps on purpose: the one-wave physics grid must get its SMs first, the background pass takes what that grid leaves idle.
         CK(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
         rc = l0_old_impl(s, device_ctr, s->aux_stream);
         if (rc != MQE_OK) return rc;
         CK(cudaEventRecord(s->ev_join, s->aux_stream));
     }
-    rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: k_policy_finish / k_joint_actions zeroed the statistics
-    if (rc != MQE_OK) return rc;
     rc = post_impl(s, device_ctr);
     if (rc != MQE_OK) return rc;
     if (s->wrap.kind != MQE_WRAP_NONE) {
