@@ -505,12 +505,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 3);
     float *sf = reinterpret_cast<float *>(smem + 2 * FT_STAGE_BYTES + 128);
     float *s_ba1 = sf, *s_bb1 = sf + 128, *s_bb2 = sf + 384, *s_hwA = sf + 512, *s_hwB = sf + 768, *s_lat = sf + 2304, *s_part = sf + 2560;   // .. + 4608: [128 rows][3 parts][12]
+    float *s_wlat = sf + 7168;                              // [512][2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mtile = blockIdx.x, M = a.M;
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < 128; i += FT_THREADS) { s_ba1[i] = a.ba1[i]; s_bb2[i] = a.bb2[i]; }
     for (int i = threadIdx.x; i < 256; i += FT_THREADS) { s_bb1[i] = a.bb1[i]; s_hwA[i] = a.aw2[i]; }
     for (int i = threadIdx.x; i < 1536; i += FT_THREADS) s_hwB[i] = a.bw3[i];
+    for (int i = threadIdx.x; i < 1024; i += FT_THREADS) s_wlat[i] = a.wlat[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) { mbar_init(&full_w[i], 1); mbar_init(&full_a[i], FT_EPI_WARPS); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 3; i++) mbar_init(&acc_done[i], 1);
@@ -624,25 +626,35 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
             asm volatile("bar.sync 2, %0;" ::"n"(32 * FT_EPI_WARPS) : "memory");
         }
         // ---- body.2 A operand: ELU(Z_body + W_lat latent), one 64-column chunk per fill, written in the canonical K-major layout ----
+        // this thread's part of Z (row m, 16 columns of every 64-column chunk) is fetched one chunk ahead of its use
+        const int m = et & 127, grow = mtile * 128 + m, kc0 = (et >> 7) * 2;
+        const float *zrow = a.Z + (size_t)(grow < M ? grow : 0) * 768 + 256 + kc0 * 8;
+        float4 zq[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) zq[i] = *reinterpret_cast<const float4 *>(zrow + 4 * i);
+        const float l0 = s_lat[m * 2], l1 = s_lat[m * 2 + 1];
 #pragma unroll 1
         for (int j = 0; j < 8; j++) {
             const int f = 4 + j, st = f & 1;
+            float4 zc[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) zc[i] = zq[i];
+            if (j + 1 < 8)
+#pragma unroll
+                for (int i = 0; i < 4; i++) zq[i] = *reinterpret_cast<const float4 *>(zrow + (j + 1) * 64 + 4 * i);
             mbar_wait(&empty[st], ((f >> 1) & 1) ^ 1);
             unsigned char *sb = smem + st * FT_STAGE_BYTES;
-            const int m = et & 127, grow = mtile * 128 + m;
-            const float l0 = s_lat[m * 2], l1 = s_lat[m * 2 + 1];
 #pragma unroll
             for (int cc = 0; cc < 2; cc++) {
-                const int kc = (et >> 7) * 2 + cc;            // 8-wide k-chunk inside the 64-column chunk
+                const int kc = kc0 + cc;                      // 8-wide k-chunk inside the 64-column chunk
                 float v[8];
                 if (grow < M) {
-                    const float *z = a.Z + (size_t)grow * 768 + 256 + j * 64 + kc * 8;
-                    const float4 z0 = *reinterpret_cast<const float4 *>(z), z1 = *reinterpret_cast<const float4 *>(z + 4);
+                    const float4 z0 = zc[2 * cc], z1 = zc[2 * cc + 1];
                     v[0] = z0.x; v[1] = z0.y; v[2] = z0.z; v[3] = z0.w; v[4] = z1.x; v[5] = z1.y; v[6] = z1.z; v[7] = z1.w;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int n = j * 64 + kc * 8 + i;
-                        v[i] = elu1_tc(v[i] + __ldg(a.wlat + n * 2) * l0 + __ldg(a.wlat + n * 2 + 1) * l1);
+                        v[i] = elu1_tc(v[i] + s_wlat[n * 2] * l0 + s_wlat[n * 2 + 1] * l1);
                     }
                 } else {
 #pragma unroll
@@ -736,7 +748,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 }
-#define FT_SMEM_BYTES (2 * FT_STAGE_BYTES + 128 + (2560 + 4608) * 4)
+#define FT_SMEM_BYTES (2 * FT_STAGE_BYTES + 128 + (2560 + 4608 + 1024) * 4)
 
 // ---------------------------------------------------------------------------------------------- host side
 static inline unsigned short f2bf_rne(float v) {
