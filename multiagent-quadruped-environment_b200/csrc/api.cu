@@ -55,6 +55,9 @@ struct MqeSim {
     bool fused_policy = false;           // one layer-0 launch + one fused tail kernel (default in the tensor-core modes)
     bool incremental = false;            // incremental layer 0: the 29 known frames of the next step are contracted behind this step's physics
     int zold_head = -1;                  // ring slot (of the NEXT frame) the partial sums in ps.Zold were computed for; -1: none
+    int early_tiles = 0;                 // row tiles of the background pass that start beside the fused tail (MQE_L0_EARLY_TILES)
+    int bg_early = 0;                    // set by step_plain around policy_impl: this call may fork the early part
+    cudaEvent_t ev_early = nullptr;
     WrapParams wrap = {};                // fused task-wrapper gather (mqe_sim_set_wrapper); kind 0 = off
     // what the learner reads after a step, packed (MQE_BUF_STEP_RESULT): wrapper obs | reward | done
     unsigned char *d_result = nullptr, *h_result = nullptr;
@@ -147,6 +150,7 @@ int mqe_sim_destroy(MqeSim *s) {
     if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->ev_early) cudaEventDestroy(s->ev_early);
     for (void *ptr : s->allocs) cudaFree(ptr);
     if (s->tcw.blob) cudaFree(s->tcw.blob);
     if (s->h_actions) cudaFreeHost(s->h_actions);
@@ -333,6 +337,8 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     { const char *e = getenv("MQE_POLICY_FUSED"); s->fused_policy = (p.policy_mode != MQE_POLICY_FP32) && !s->tail_fp32 && !(e && e[0] == '0'); }
     if (s->fused_policy) s->fork_policy = false;
     { const char *e = getenv("MQE_POLICY_INCR"); s->incremental = s->fused_policy && !(e && e[0] == '0'); }
+    { const char *e = getenv("MQE_L0_EARLY_TILES"); s->early_tiles = s->incremental ? (e ? atoi(e) : 14) : 0; }
+    if (s->incremental) CK(cudaEventCreateWithFlags(&s->ev_early, cudaEventDisableTiming));
     if (s->fork_policy || s->incremental) {
         CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
@@ -575,7 +581,10 @@ static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, c
     if (finished) *finished = 0;
     if (s->incremental && incr) {                        // the 29 older frames are already in ps.Zold: only the new frame's K = 80 GEMM, then the tail
         int nf = 0;
-        CK(mqe_launch_policy_tc_incremental(s->tcw, s->pw, ps, s->p, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->p.ctr, finish, s->stream, &nf));
+        const int early = s->bg_early ? s->early_tiles : 0;
+        const int head_next = head < 0 ? -2 : (head + 1) % MQE_HIST_FRAMES;
+        CK(mqe_launch_policy_tc_incremental(s->tcw, s->pw, ps, s->p, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->p.ctr, finish, s->stream, &nf,
+                                            early, head_next, s->aux_stream, s->ev_early));
         s->launches += nf;
         if (finished) *finished = finish;
         return MQE_OK;
@@ -615,7 +624,7 @@ static int policy_impl(MqeSim *s, const float *d_actions, bool device_ctr) {
     CK(mqe_launch_policy_frame(s->p, d_actions, device_ctr ? -1 : slot, s->stream));
     int finished = 0;
     if (s->incremental && !device_ctr && s->zold_head != slot) {     // no partial sums for this slot yet (first step, or after an explicit call): prime them now
-        CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->ps.Zold, s->p.ctr, s->stream));
+        CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->ps.Zold, s->p.ctr, 0, -1, s->stream));
         s->launches += 1;
     }
     int rc = run_network(s, s->p.hist_f32, s->p.hist_hi, s->p.hist_lo, device_ctr ? -1 : slot, s->M, s->ps.latent, s->ps.act, 1, &finished, true);
@@ -627,13 +636,15 @@ static int policy_impl(MqeSim *s, const float *d_actions, bool device_ctr) {
 // incremental layer 0: contract the 29 frames the NEXT step already knows (every slot but the one its frame will go to)
 static int l0_old_impl(MqeSim *s, bool device_ctr, cudaStream_t st) {
     const int next_slot = (s->head + 2) % MQE_HIST_FRAMES;            // s->head still names the previous step's slot here
-    CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, device_ctr ? -1 : next_slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1,
-                                s->ps.Zold, s->p.ctr, st));
+    const int first = s->bg_early ? s->early_tiles : 0;                // those row tiles were started beside the tail
+    CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, device_ctr ? -2 : next_slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1,
+                                s->ps.Zold, s->p.ctr, first, -1, st));
     s->launches += 1;
     s->zold_head = next_slot;
     return MQE_OK;
 }
 int mqe_sim_policy(MqeSim *s, const float *d_actions) {      // stand-alone call: the 29-frame pass runs in line (policy_impl primes it)
+    if (s) s->bg_early = 0;
     int rc = policy_impl(s, d_actions, false);
     if (rc == MQE_OK) s->head = (s->head + 1) % MQE_HIST_FRAMES;
     return rc;
@@ -670,6 +681,7 @@ static int exchange_impl(MqeSim *s) {                    // peer exchange of the
 }
 static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     int rc;
+    s->bg_early = (s->incremental && s->p.control_type == 0 && s->early_tiles > 0) ? 1 : 0;
     if (s->p.control_type == 0) rc = policy_impl(s, d_actions, device_ctr);
     else {                                               // 'P' / 'V' / 'T': the caller's joint actions are the actions (go1.py:43-45)
         CK(mqe_launch_joint_actions(s->p, d_actions, s->stream));
@@ -697,6 +709,7 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     }
     rc = exchange_impl(s);
     if (bg) CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));     // join: the ring must not move under the background pass
+    s->bg_early = 0;
     return rc;
 }
 
@@ -750,7 +763,7 @@ static int step_any(MqeSim *s, const float *d_actions) {
         if (s->incremental && s->p.control_type == 0 && s->zold_head != (s->head + 1) % MQE_HIST_FRAMES) {
             // the previous call was not a full step (e.g. mqe_sim_policy): the partial sums the graph expects do not exist yet
             const int slot = (s->head + 1) % MQE_HIST_FRAMES;
-            CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->ps.Zold, s->p.ctr, s->stream));
+            CK(mqe_launch_policy_l0_old(s->tcw, s->p.hist_hi, s->p.hist_lo, slot, s->M, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->ps.Zold, s->p.ctr, 0, -1, s->stream));
             s->launches += 1;
         }
         CK(cudaGraphLaunch(g->exec, s->stream));

@@ -69,7 +69,8 @@ struct DevParams {
     int cta_sync;                 // MQE_CTA_SYNC: 0 none, 1 per substep, 2 also per phase
     int trace;                    // MQE_TRACE=1: also accumulate per-phase cycles into the trace rows
     int *stats;                   // [8]
-    int *ctr;                     // device-side step counters ([3] _compute_torques calls so far, [4] CTAs of k_substeps finished: action lag; [5] peer exchanges done);
+    int *ctr;                     // device-side step counters ([3] _compute_torques calls so far, [4] CTAs of k_substeps finished: action lag; [5] peer exchanges done;
+                                  // [7] ring slot of the current step's frame);
                                   // [0] ring slot that receives the next frame, [1] policy steps done
                                   // (sheep RNG key), [2] scratch (blocks of k_post_physics finished); let a captured CUDA graph of
                                   // the whole step be replayed with constant kernel arguments

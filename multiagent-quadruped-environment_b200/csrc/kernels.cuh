@@ -39,10 +39,11 @@ cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, const PolicyWei
                                        const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes, const int *ctr,
                                        int finish, cudaStream_t st, int *launches);
 cudaError_t mqe_launch_policy_l0_old(const PolicyTcWeights &w, const unsigned short *hist_hi, const unsigned short *hist_lo, int head_next,
-                                     int M, int passes, float *Zold, const int *ctr, cudaStream_t st);
+                                     int M, int passes, float *Zold, const int *ctr, int mtile0, int mtiles, cudaStream_t st);
 cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
                                              const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes,
-                                             const int *ctr, int finish, cudaStream_t st, int *launches);
+                                             const int *ctr, int finish, cudaStream_t st, int *launches,
+                                             int early_tiles, int head_next, cudaStream_t aux, cudaEvent_t ev);
 cudaError_t mqe_launch_task_gather(const DevParams &p, const WrapParams &w, int mode, cudaStream_t st);
 cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const unsigned short *hist_hi,
                                         const unsigned short *hist_lo, int head, int M, int passes, const int *ctr, cudaStream_t st, cudaStream_t aux,

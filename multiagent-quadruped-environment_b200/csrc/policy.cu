@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) k_policy_frame(DevParams p, const float *
     pdl_launch_dependents();
     pdl_wait();
     if (head < 0) head = p.ctr[0];                           // graph replay: the slot comes from the device counter
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.ctr[7] = head;   // slot of THIS step's frame: what the background layer-0 passes key on (ctr[0] moves mid-step)
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int M = p.N * p.A;
     if (m >= M) return;

@@ -78,7 +78,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
                const float *__restrict__ b0cat, float *__restrict__ Z, unsigned short *__restrict__ a0_hi,
                unsigned short *__restrict__ a0_lo, int M, int head, int passes, const int *__restrict__ ctr, int ntile0,
-               int mode, float *__restrict__ Zold, const unsigned char *__restrict__ dirty, int agents) {
+               int mode, float *__restrict__ Zold, const unsigned char *__restrict__ dirty, int agents, int mtile0) {
     // mode 0: all 30 slots.  Incremental layer 0 (29 of the 30 history frames of the NEXT step are known as soon as this step's frame is in
     // the ring): mode 1 = the 29 slots other than `head` (the slot the next frame will go to), raw accumulators -> Zold, launched at low
     // priority behind the physics of the step so that it fills the idle tail of k_substeps; mode 2 = slot `head` alone (K = 80), plus
@@ -89,7 +89,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     uint64_t *accum = empty + TC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntile = blockIdx.x + ntile0, mtile = blockIdx.y;     // ntile0: first 128-column tile of this launch (forked policy)
+    const int ntile = blockIdx.x + ntile0, mtile = blockIdx.y + mtile0;     // ntile0 / mtile0: first column / row tile of this launch
     pdl_launch_dependents();
 
     if (threadIdx.x == 0) {
@@ -106,7 +106,8 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     pdl_wait();                                              // set-up above ran in the predecessor's shadow
-    if (head < 0) head = ctr[0];                             // graph replay: newest slot = the one k_policy_frame just wrote (mode 1: will write next)
+    if (head == -2) head = (ctr[7] + 1) % MQE_HIST_FRAMES;  // graph replay, background pass: the slot after the one k_policy_frame wrote this step
+    else if (head < 0) head = ctr[0];                        // graph replay: newest slot = the one k_policy_frame just wrote (mode 1: will write next)
     const uint32_t stage_tx = passes == 3 ? TC_STAGE_BYTES : 2 * TC_TILE_BYTES;
     const int n_iter = mode == 0 ? MQE_HIST_FRAMES : (mode == 1 ? MQE_HIST_FRAMES - 1 : 1);
 
@@ -842,7 +843,7 @@ extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const f
     dim3 grid(6, (rows + 127) / 128);
     return launch_heavy(k_policy_l0_tc, grid, dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                       (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
-                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1);
+                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0);
 }
 
 // Fused policy (default): ONE layer-0 launch over all 768 columns (the six column tiles of a row tile are neighbours in launch order, so the
@@ -854,7 +855,7 @@ extern "C" cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, cons
     const int mt = (M + 127) / 128;
     cudaError_t e;
     if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1)) != cudaSuccess) return e;
+                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0)) != cudaSuccess) return e;
     if ((e = mqe_launch_policy_tail_only(w, pw, s, p, M, passes, finish, st)) != cudaSuccess) return e;
     *launches += 2;
     return cudaGetLastError();
@@ -883,23 +884,37 @@ extern "C" cudaError_t mqe_launch_policy_tail_only(const PolicyTcWeights &w, con
 // behind the policy of step t, i.e. concurrently with k_substeps / k_post_physics of step t, whose one-wave grid leaves ~30 % of the SM time
 // idle in its tail; step t+1 then only needs the K = 80 GEMM of its new frame (mode 2) in front of the fused tail.  preprocess_action's
 // critical path drops from frame + 96 us + tail to frame + ~6 us + tail.
+// row tiles [mtile0, mtile0 + mtiles) (mtiles < 0: to the end)
 extern "C" cudaError_t mqe_launch_policy_l0_old(const PolicyTcWeights &w, const unsigned short *hist_hi, const unsigned short *hist_lo, int head_next,
-                                                int M, int passes, float *Zold, const int *ctr, cudaStream_t st) {
+                                                int M, int passes, float *Zold, const int *ctr, int mtile0, int mtiles, cudaStream_t st) {
     const int mt = (M + 127) / 128;
-    return launch_background(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+    if (mtiles < 0) mtiles = mt - mtile0;
+    if (mtiles <= 0) return cudaSuccess;
+    return launch_background(k_policy_l0_tc, dim3(6, mtiles), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                              (const unsigned short *)w.l0_lo, (const float *)nullptr, (float *)nullptr, (unsigned short *)nullptr, (unsigned short *)nullptr,
-                             M, head_next, passes, ctr, 0, 1, Zold, (const unsigned char *)nullptr, 1);
+                             M, head_next, passes, ctr, 0, 1, Zold, (const unsigned char *)nullptr, 1, mtile0);
 }
 extern "C" cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
                                                         const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes,
-                                                        const int *ctr, int finish, cudaStream_t st, int *launches) {
+                                                        const int *ctr, int finish, cudaStream_t st, int *launches,
+                                                        int early_tiles, int head_next, cudaStream_t aux, cudaEvent_t ev) {
     const int mt = (M + 127) / 128;
     cudaError_t e;
     if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0,
-                          2, s.Zold, (const unsigned char *)p.hist_dirty, p.A)) != cudaSuccess) return e;
-    if ((e = mqe_launch_policy_tail_only(w, pw, s, p, M, passes, finish, st)) != cudaSuccess) return e;
+                          2, s.Zold, (const unsigned char *)p.hist_dirty, p.A, 0)) != cudaSuccess) return e;
     *launches += 2;
+    if (early_tiles > 0 && aux) {
+        // the first row tiles of the NEXT step's 29-frame pass start right here, beside the fused tail, which keeps only 64 of the 148
+        // SMs busy: as many CTAs as finish before the tail does (so k_substeps still finds every SM free).  It may only start once the
+        // new-frame pass above has read Zold.  NOTE: the tail advances ctr[0] at its end, so this launch takes the next slot explicitly
+        // (head_next >= 0) or, in graph replay, derives it from the not-yet-advanced counter (head_next == -2).
+        if ((e = cudaEventRecord(ev, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(aux, ev, 0)) != cudaSuccess) return e;
+        if ((e = mqe_launch_policy_l0_old(w, hist_hi, hist_lo, head_next, M, passes, s.Zold, ctr, 0, early_tiles < mt ? early_tiles : mt, aux)) != cudaSuccess) return e;
+        *launches += 1;
+    }
+    if ((e = mqe_launch_policy_tail_only(w, pw, s, p, M, passes, finish, st)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
@@ -923,11 +938,11 @@ extern "C" cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, con
     if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(aux, ev_fork, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(2, mt), dim3(320), TC_SMEM_BYTES, aux, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1)) != cudaSuccess) return e;
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_linear_tc<128, 2, false>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), aux, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, nou, nou, 0, M, 1, passes, h1)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ev_join, aux)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(4, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2, 0, (float *)nullptr, (const unsigned char *)nullptr, 1)) != cudaSuccess) return e;
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes, none)) != cudaSuccess) return e;
