@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
     if (p.cta_sync >= (level)) asm volatile("bar.sync 1, %0;" ::"r"(live_threads) : "memory");
     for (int sub = 0; sub < nsub; sub++) {
         const bool last = (sub == nsub - 1);
-        CTA_ALIGN(1);
+        if (p.cta_sync != 3 || (sub & 1) == 0) { CTA_ALIGN(1); }      // MQE_CTA_SYNC=3: re-align every other substep only (experiment)
         // ================================================================ P1: actuator network (go1.py:315-354, 369-380)
         if (active && is_robot && p.control_type != 0) {
             // LeggedRobot._compute_torques (legged_robot.py:384-392): 'P' PD towards action * scale + default pose, 'T' scaled torques,
@@ -1075,8 +1075,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
         int npair = 0;
         bool pairs_pending = false;                      // capsule contacts recorded in pdesc, rows not built yet
         bool need_narrow = false;                        // this env's capsule masks are live: run the narrow phase for it
-        unsigned t_sub = 0;
-        if (p.trace && rank_in_env == 0) t_sub = (unsigned)clock();
+        unsigned t_sub = 0;                              // sub-phase marks of P3b (MQE_TRACE=1): lane 0's clock at warp-uniform points
+        if (p.trace && lane == 0) t_sub = (unsigned)clock();
         if (G > 1 && (is_robot || is_npc)) {
             // broadphase over group pairs
             bool close = false;
@@ -1096,9 +1096,9 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             if (env >= p.N) close = false;
             bool any_close = __ballot_sync(env_mask, close) != 0u;
 #define SUB_MARK(k)                                                                                        \
-    if (p.trace && rank_in_env == 0) {                                                                     \
+    if (p.trace && lane == 0) {                                                                            \
         const unsigned now_ = (unsigned)clock();                                                           \
-        atomicAdd(reinterpret_cast<unsigned long long *>(tr + 4 + (k)), (unsigned long long)(now_ - t_sub)); \
+        tr[4 + (k)] += (long long)(now_ - t_sub);                                                          \
         t_sub = now_;                                                                                      \
     }
             if (any_close) {
@@ -1132,7 +1132,6 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                     if (leg == 0) rs[RS_BOUND] = bound * 1.0001f + 1e-5f;
                 }
                 __syncwarp(env_mask);
-                SUB_MARK(11);
                 // capsule culling: bit ci of capmask[X][Y] = capsule ci of group X reaches into the true bounding sphere of
                 // group Y (+ contact offset).  A pair (X,ci,Y,cj) can only touch if both bits are set, so the narrow phase
                 // below skips everything else -- exact, it never drops a pair the full enumeration would accept.
@@ -1170,11 +1169,11 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 }
                 if (env >= p.N) live_any = false;
                 __syncwarp(env_mask);
-                SUB_MARK(12);
                 need_narrow = __ballot_sync(env_mask, live_any) != 0u;
             }
         }
         __syncwarp();
+        SUB_MARK(11);                                    // broadphase + publish + capsule masks
         if (G > 1) {
             // ---- narrow phase, WARP-wide.  An env whose capsule masks are live borrows all 32 lanes of its warp (most substeps at most one
             // env of a warp has robots within reach of each other).  Candidates are enumerated from the masks -- capsule ci of X (bit set in
@@ -1282,6 +1281,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             }
         }
         __syncwarp();
+        SUB_MARK(12);                                    // narrow phase
         // claim pool slots in env order (capsule path; the oriented-box path keeps its static slice)
         if (!obb && G > 1) {
             if (__ballot_sync(FULL, npair > 0)) {
@@ -1351,8 +1351,8 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                 for (int c = lane; c < h_np; c += 32) pair_block_coupling(hrow(3 * c), hrow(3 * c + 1), hrow(3 * c + 2));
             }
         }
+        SUB_MARK(13);                                    // capsule-pair rows
         if (G > 1 && (is_robot || is_npc)) {
-            SUB_MARK(14);
             if (obb) {
                 // robot probes on the plank / the push box: canonical order = robot ascending, probe-table order (two-pass compaction)
                 const float *nsS = wbase + E * A * RS_SIZE + (e_loc * P) * NS_SIZE;
@@ -1523,6 +1523,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                         ua[L][0] += mine ? du0 : 0.f; ua[L][1] += mine ? du1 : 0.f; ua[L][2] += mine ? du2 : 0.f;
                     }
                 }
+                if (p.trace && lane == 0) t_sub = (unsigned)clock();
                 if (npair > 0) {   // uniform over the env's lanes
 #pragma unroll
                     for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));
@@ -1585,6 +1586,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
                             for (int k = 0; k < 3; k++) ua[L][k] = __shfl_sync(quad_mask, u[k], quad_base + L);
                     }
                 }
+                if (p.trace) { __syncwarp(); SUB_MARK(14); }     // pair sweeps (lane 0 waits here for the envs of its warp that have pairs)
             }
 #pragma unroll
             for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));

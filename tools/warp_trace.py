@@ -48,7 +48,7 @@ for lo, hi in [(0, 7), (7, 13), (13, 19), (19, 29)]:
         print(f"  warps with widest row count in [{lo},{hi}) and no pairs: n={int(m.sum()):5d} mean {d[m].mean():8.2f} us")
 if tr[:, 4:].sum() > 0:
     ph = tr[:, 4:20].astype(np.float64)
-    names_p = ["P1 actuator", "P2 dynamics", "P3 pass2 rows", "P3b pairs", "P4 PGS", "P5 integrate", "prologue", "epilogue", "P3 limits", "P3 pass1 probes", "P4 setup", "P3b broadphase+publish", "P3b capmask", "P3b narrow", "P3b pair rows", "-"]
+    names_p = ["P1 actuator", "P2 dynamics", "P3 pass2 rows", "P3b pairs", "P4 PGS", "P5 integrate", "prologue", "epilogue", "P3 limits", "P3 pass1 probes", "P4 setup", "P3b broadphase+publish+capmask", "P3b narrow", "P3b pair rows", "P4 pair sweeps", "-"]
     tot = ph.sum(1)
     print("  per-phase share of warp cycles (mean over warps; MQE_TRACE=1), cycles per launch:")
     for i, nm in enumerate(names_p):
@@ -59,6 +59,6 @@ if m.any():
 
 if worst[2] is not None and worst[2][4:].sum() > 0:
     w = worst[2]
-    nm = ["P1 actuator", "P2 dynamics", "P3 pass2 rows", "P3b pairs", "P4 PGS", "P5 integrate", "prologue", "epilogue", "P3 limits", "P3 pass1 probes", "P4 setup", "P3b broadphase+publish", "P3b capmask", "P3b narrow", "P3b pair rows", "-"]
+    nm = ["P1 actuator", "P2 dynamics", "P3 pass2 rows", "P3b pairs", "P4 PGS", "P5 integrate", "prologue", "epilogue", "P3 limits", "P3 pass1 probes", "P4 setup", "P3b broadphase+publish+capmask", "P3b narrow", "P3b pair rows", "P4 pair sweeps", "-"]
     print(f"slowest warp of the run: step {worst[1]}, {worst[0]:.1f} us, pair contacts {w[2]}, widest rows {w[3]}; cycles per phase:")
     print("   " + ", ".join(f"{n} {int(c)}" for n, c in zip(nm, w[4:20]) if c))
