@@ -141,6 +141,10 @@ typedef struct {
                                                    legged_robot.py:332-335: props[0].mass += U(added_mass_range)) or NULL */
     const float *h_env_friction;                /* [N] contact friction per env (domain_rand.randomize_friction, legged_robot.py:283-294,
                                                    already combined with the terrain's) or NULL: `friction` everywhere */
+    const float *h_base_com_shift;              /* [N*A][3] shift of each robot's base-link centre of mass, base frame (domain_rand.randomize_com,
+                                                   legged_robot_field.py:321-332: props[0].com += U(com_range)) or NULL */
+    const float *h_motor_strength;              /* [N][12A] factor on the joint actions of control types P / V / T (domain_rand.randomize_motor,
+                                                   legged_robot_field.py:283-291, 180-183; Go1's 'C' path never applies it, go1.py:315-354) or NULL */
     MqeRobotModel model;
     MqeWeights weights;
 } MqeSimDesc;

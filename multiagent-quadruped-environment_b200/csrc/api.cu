@@ -233,6 +233,8 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     if (P) CK(dupload(s, &p.npc_init, d->h_npc_init_state, (size_t)N * P * 13));
     if (d->h_env_friction) CK(dupload(s, &p.mu_env, d->h_env_friction, (size_t)N));
     if (d->h_base_added_mass) CK(dupload(s, &p.base_mass_add, d->h_base_added_mass, (size_t)M));
+    if (d->h_base_com_shift) CK(dupload(s, &p.base_com_shift, d->h_base_com_shift, (size_t)M * 3));
+    if (d->h_motor_strength) CK(dupload(s, &p.motor_strength, d->h_motor_strength, (size_t)M * 12));
     {
         std::vector<float> nd(D > 0 ? D : 1, 0.f);
         if (D && d->h_npc_dof_default) memcpy(nd.data(), d->h_npc_dof_default, D * sizeof(float));

@@ -43,6 +43,8 @@ struct DevParams {
     int push_interval; float max_push_vel;     // domain_rand.push_robots
     const float *base_mass_add;                // [N*A] mass added to the base link (domain_rand.randomize_base_mass) or nullptr
     const float *mu_env;                       // [N] per-env friction (domain_rand.randomize_friction) or nullptr
+    const float *base_com_shift;               // [N*A][3] base-link COM shift (domain_rand.randomize_com) or nullptr
+    const float *motor_strength;               // [N][12A] action factor of control types P / V / T (domain_rand.randomize_motor) or nullptr
     float geom[16];               // MQE_NPC_SEESAW geometry (MqeSimDesc.npc_geom)
     unsigned long long seed;
     int sdf_nx, sdf_ny;

@@ -64,10 +64,10 @@ __host__ __device__ inline int physics_cta_header_floats() { return (int)(sizeof
 struct SV { V3 w, v; };
 struct RBI { float m; V3 h; float I[6]; };   // xx xy xz yy yz zz about O
 
-__device__ __forceinline__ RBI rbi_from_link(const float *in, const M3 &R, V3 p, float added_mass = 0.f) {
+__device__ __forceinline__ RBI rbi_from_link(const float *in, const M3 &R, V3 p, float added_mass = 0.f, V3 com_shift = V3{0.f, 0.f, 0.f}) {
     RBI o;
     float m = in[0] + added_mass;      // extra mass sits at the link's COM (PhysX changes the mass, not the inertia tensor)
-    V3 c = mul(R, mk(in[1], in[2], in[3])) + p;
+    V3 c = mul(R, mk(in[1] + com_shift.x, in[2] + com_shift.y, in[3] + com_shift.z)) + p;      // randomize_com moves the COM, the tensor about it stays
     V3 t0 = in[4] * R.c0 + in[5] * R.c1 + in[6] * R.c2;
     V3 t1 = in[5] * R.c0 + in[7] * R.c1 + in[8] * R.c2;
     V3 t2 = in[6] * R.c0 + in[8] * R.c1 + in[9] * R.c2;
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 const int j = 3 * leg + k;
-                const float a = act[k] * p.action_scale;
+                const float a = (p.motor_strength ? p.motor_strength[m_idx * 12 + j] : 1.f) * act[k] * p.action_scale;     // legged_robot_field.py:180-183
                 float t = a;
                 if (p.control_type == 1) t = p.kp * (a + md->q_default[j] - q[k]) - p.kd * qd[k];
                 else if (p.control_type == 3) t = p.kp * (a - qd[k]) - p.kd * (qd[k] - p.last_dof_vel[m_idx * 12 + j]) / p.dt;
@@ -766,7 +766,9 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             S1.w = a1; S1.v = cross(p1, a1);
             S2.w = a2; S2.v = cross(p2, a2);
             S3.w = a2; S3.v = cross(p3, a2);
-            RBI I0 = rbi_from_link(md->base_inertial, Rb, mk(0, 0, 0), (p.base_mass_add && active) ? p.base_mass_add[m_idx] : 0.f);
+            V3 com_sh = mk(0.f, 0.f, 0.f);
+            if (p.base_com_shift && active) com_sh = mk(p.base_com_shift[m_idx * 3], p.base_com_shift[m_idx * 3 + 1], p.base_com_shift[m_idx * 3 + 2]);
+            RBI I0 = rbi_from_link(md->base_inertial, Rb, mk(0, 0, 0), (p.base_mass_add && active) ? p.base_mass_add[m_idx] : 0.f, com_sh);
             RBI I1 = rbi_from_link(md->leg_inertial[leg][0], R1, p1);
             RBI I2 = rbi_from_link(md->leg_inertial[leg][1], R2, p2);
             RBI I3 = rbi_from_link(md->leg_inertial[leg][2], R3, p3);

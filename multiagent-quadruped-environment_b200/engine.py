@@ -109,6 +109,7 @@ class SimDescC(ctypes.Structure):
         ("lag_enabled", ctypes.c_int32), ("lag_timesteps", ctypes.c_int32), ("soft_dof_pos_limit", ctypes.c_float),
         ("h_sdf", _fp), ("h_env_origins", _fp), ("h_agent_origins", _fp), ("h_base_init_state", _fp),
         ("h_npc_init_state", _fp), ("h_npc_dof_default", _fp), ("h_base_added_mass", _fp), ("h_env_friction", _fp),
+        ("h_base_com_shift", _fp), ("h_motor_strength", _fp),
         ("model", RobotModelC),
         ("weights", WeightsC),
     ]

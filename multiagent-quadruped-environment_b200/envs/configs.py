@@ -120,6 +120,7 @@ def go1_base() -> Cfg:
     c.domain_rand = Cfg(                                  # legged_robot_config.py:135-144 + go1_config.py:216-247
         randomize_friction=False, friction_range=[0.05, 4.5], randomize_base_mass=False, added_mass_range=[-1.0, 3.0],
         push_robots=False, push_interval_s=15, max_push_vel_xy=1.0, max_push_vel_ang=0.0, randomize_com=False,
+        com_range=Cfg(x=[-0.05, 0.15], y=[-0.1, 0.1], z=[-0.05, 0.05]),
         randomize_motor=False, leg_motor_strength_range=[0.9, 1.1], randomize_lag_timesteps=False, lag_timesteps=6,
         init_base_pos_range=dict(x=[0.1, 0.1], y=[-0.1, 0.1]), init_dof_pos_ratio_range=[0.7, 1.3],
         init_npc_base_pos_range=dict(x=[-0.2, 0.2], y=[-0.2, 0.2]))

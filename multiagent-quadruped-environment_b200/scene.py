@@ -262,6 +262,17 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
         mrng = np.random.Generator(np.random.Philox(key=(int(seed) & 0xFFFFFFFF) * 7919 + 29))
         base_added_mass = np.ascontiguousarray(mrng.uniform(dr.added_mass_range[0], dr.added_mass_range[1], size=(N_global, A)),
                                                dtype=np.float32)[start:stop].reshape(-1).copy()
+    base_com_shift = None
+    if getattr(dr, "randomize_com", False):                                    # legged_robot_field.py:321-332: props[0].com += U(com_range), per robot
+        crng = np.random.Generator(np.random.Philox(key=(int(seed) & 0xFFFFFFFF) * 7919 + 31))
+        cr = dr.com_range
+        lo, hi = np.array([cr.x[0], cr.y[0], cr.z[0]]), np.array([cr.x[1], cr.y[1], cr.z[1]])
+        base_com_shift = np.ascontiguousarray(crng.uniform(lo, hi, size=(N_global, A, 3)), dtype=np.float32)[start:stop].reshape(-1, 3).copy()
+    motor_strength = None
+    if getattr(dr, "randomize_motor", False):                                  # legged_robot_field.py:283-291: U(leg_motor_strength_range) per env and joint
+        srng = np.random.Generator(np.random.Philox(key=(int(seed) & 0xFFFFFFFF) * 7919 + 37))
+        motor_strength = np.ascontiguousarray(srng.uniform(dr.leg_motor_strength_range[0], dr.leg_motor_strength_range[1], size=(N_global, 12 * A)),
+                                              dtype=np.float32)[start:stop].copy()
     env_friction = None
     if getattr(dr, "randomize_friction", False):                               # legged_robot.py:283-294: 64 buckets over friction_range,
         frng = np.random.Generator(np.random.Philox(key=(int(seed) & 0xFFFFFFFF) * 7919 + 13))   # one bucket per env (own generator: shards agree)
@@ -284,6 +295,12 @@ def build_scene(cfg, seed=0, env_slice=None, policy_mode=E.POLICY_BF16X3, solver
     if env_friction is not None:
         keep.append(env_friction)
         d.h_env_friction = E.as_fp(env_friction)
+    if base_com_shift is not None:
+        keep.append(base_com_shift)
+        d.h_base_com_shift = E.as_fp(base_com_shift)
+    if motor_strength is not None:
+        keep.append(motor_strength)
+        d.h_motor_strength = E.as_fp(motor_strength)
     d.h_sdf, d.h_env_origins, d.h_agent_origins = E.as_fp(sdf), E.as_fp(eo), E.as_fp(ao)
     d.h_base_init_state, d.h_npc_init_state, d.h_npc_dof_default = E.as_fp(bi_engine), E.as_fp(ni), E.as_fp(npc_dof_default)
     d.model = model.to_c()

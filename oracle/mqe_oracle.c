@@ -134,11 +134,14 @@ enum { RNG_DOF = 0, RNG_BASE_POS = 1, RNG_BASE_VEL = 2, RNG_NPC_POS = 3, RNG_NPC
 typedef struct { real w[3], v[3]; } sv;
 typedef struct { real m, h[3], I[6]; } rbi; /* mass, first moment m*c, rotational inertia about O: xx xy xz yy yz zz */
 
-static void rbi_from_link_m(rbi *o, const float *in10, const real *R, const real *p, real added_mass);
-static void rbi_from_link(rbi *o, const float *in10, const real *R, const real *p) { rbi_from_link_m(o, in10, R, p, 0); }
-static void rbi_from_link_m(rbi *o, const float *in10, const real *R, const real *p, real added_mass) {
-    /* in10: mass, com, I about com in link frame; R link->world, p link origin rel. O; added_mass sits at the COM */
+static void rbi_from_link_mc(rbi *o, const float *in10, const real *R, const real *p, real added_mass, const real *com_shift);
+static void rbi_from_link_m(rbi *o, const float *in10, const real *R, const real *p, real added_mass) { rbi_from_link_mc(o, in10, R, p, added_mass, NULL); }
+static void rbi_from_link(rbi *o, const float *in10, const real *R, const real *p) { rbi_from_link_mc(o, in10, R, p, 0, NULL); }
+static void rbi_from_link_mc(rbi *o, const float *in10, const real *R, const real *p, real added_mass, const real *com_shift) {
+    /* in10: mass, com, I about com in link frame; R link->world, p link origin rel. O; added_mass sits at the COM;
+     * com_shift (domain_rand.randomize_com, legged_robot_field.py:321-332) moves the COM, the tensor about it stays */
     real m = in10[0] + added_mass, cl[3] = {in10[1], in10[2], in10[3]}, c[3];
+    if (com_shift) { cl[0] += com_shift[0]; cl[1] += com_shift[1]; cl[2] += com_shift[2]; }
     m3mulv(c, R, cl);
     v3add(c, c, p);
     real Il[9] = {in10[4], in10[5], in10[6], in10[5], in10[7], in10[8], in10[6], in10[8], in10[9]}, T[9], Iw[9], Rt[9];
@@ -201,13 +204,14 @@ typedef struct {
     real Minv[NV][NV];
 } RobotDyn;
 
-static void robot_kinematics_m(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q, real base_added_mass);
-static void robot_kinematics(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q) { robot_kinematics_m(d, md, quat, q, 0); }
-static void robot_kinematics_m(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q, real base_added_mass) {
+static void robot_kinematics_mc(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q, real base_added_mass, const real *com_shift);
+static void robot_kinematics_m(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q, real base_added_mass) { robot_kinematics_mc(d, md, quat, q, base_added_mass, NULL); }
+static void robot_kinematics(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q) { robot_kinematics_mc(d, md, quat, q, 0, NULL); }
+static void robot_kinematics_mc(RobotDyn *d, const MqeRobotModel *md, const real *quat, const real *q, real base_added_mass, const real *com_shift) {
     quat_to_mat(d->Rb, quat);
     memcpy(d->R[0], d->Rb, sizeof d->Rb);
     v3set(d->p[0], 0, 0, 0);
-    rbi_from_link_m(&d->Il[0], md->base_inertial, d->Rb, d->p[0], base_added_mass);
+    rbi_from_link_mc(&d->Il[0], md->base_inertial, d->Rb, d->p[0], base_added_mass, com_shift);
     for (int l = 0; l < 4; l++) {
         const real *Rp = d->Rb;
         const real *pp = d->p[0];
@@ -404,6 +408,8 @@ typedef struct {
     float *mu_env;                          /* [N] per-env friction or NULL (domain_rand.randomize_friction) */
     real *lag_ring; int lag_n; uint32_t lag_calls;   /* action lag (go1.py:337-339, 363): [M][lag_n][12] scaled actions; calls so far */
     float *base_mass_add;                   /* [M] mass added to the base link or NULL (domain_rand.randomize_base_mass) */
+    float *base_com_shift;                  /* [M][3] base-link COM shift or NULL (domain_rand.randomize_com) */
+    float *motor_strength;                  /* [M][12] action factor for control types P / V / T or NULL (domain_rand.randomize_motor) */
     int64_t *ep_len;
     uint8_t *reset_buf, *timeout_buf, *collide_buf, *r_term, *p_term, *zl_term, *zh_term;
     uint32_t *episode;                      /* reset counter per env (RNG key)  */
@@ -441,6 +447,8 @@ Oracle *orc_create(const MqeSimDesc *desc) {
     o->mu_env = desc->h_env_friction ? dupf(desc->h_env_friction, (size_t)N) : NULL;
     if (desc->lag_enabled) { o->lag_n = desc->lag_timesteps + 1; o->lag_ring = (real *)xcalloc((size_t)M * o->lag_n * 12, sizeof(real)); }
     o->base_mass_add = desc->h_base_added_mass ? dupf(desc->h_base_added_mass, (size_t)M) : NULL;
+    o->base_com_shift = desc->h_base_com_shift ? dupf(desc->h_base_com_shift, (size_t)M * 3) : NULL;
+    o->motor_strength = desc->h_motor_strength ? dupf(desc->h_motor_strength, (size_t)M * 12) : NULL;
     /* private copies of the weights */
     const float **src = (const float **)&desc->weights;
     const size_t sz[20] = {256 * 2100, 256, 128 * 256, 128, 2 * 128, 2, 512 * 2102, 512, 256 * 512, 256,
@@ -497,7 +505,7 @@ Oracle *orc_create(const MqeSimDesc *desc) {
 
 void orc_destroy(Oracle *o) {
     if (!o) return;
-    free(o->sdf); free(o->env_origins); free(o->agent_origins); free(o->base_init); free(o->npc_init); free(o->npc_dof_default); free(o->mu_env); free(o->base_mass_add); free(o->lag_ring);
+    free(o->sdf); free(o->env_origins); free(o->agent_origins); free(o->base_init); free(o->npc_init); free(o->npc_dof_default); free(o->mu_env); free(o->base_mass_add); free(o->base_com_shift); free(o->motor_strength); free(o->lag_ring);
     for (int i = 0; i < 20; i++) free(o->wbuf[i]);
     free(o->root); free(o->dof); free(o->contact); free(o->torques); free(o->actions); free(o->last_actions);
     free(o->loc_last); free(o->loc_last2); free(o->loc_obs); free(o->hist); free(o->err1); free(o->err2); free(o->vel1); free(o->vel2);
@@ -828,7 +836,9 @@ static void env_substep(Oracle *o, int e, const real *tau /* [12A] */, int32_t *
         real v[NV], rhs[NV], acc[NV];
         for (int j = 0; j < 12; j++) { q[a][j] = dof[(12 * a + j) * 2]; v[6 + j] = dof[(12 * a + j) * 2 + 1]; }
         for (int i = 0; i < 3; i++) { v[i] = rs[10 + i]; v[3 + i] = rs[7 + i]; es.origin[a][i] = rs[i]; }
-        robot_kinematics_m(rd, md, rs + 3, q[a], o->base_mass_add ? (real)o->base_mass_add[e * A + a] : 0);
+        real csh[3] = {0, 0, 0};
+        if (o->base_com_shift) for (int i = 0; i < 3; i++) csh[i] = o->base_com_shift[(e * A + a) * 3 + i];
+        robot_kinematics_mc(rd, md, rs + 3, q[a], o->base_mass_add ? (real)o->base_mass_add[e * A + a] : 0, o->base_com_shift ? csh : NULL);
         robot_dynamics(rd, v, d->gravity_z);
         if (spd_inverse(NV, &rd->M[0][0], &rd->Minv[0][0]) != 0) { fprintf(stderr, "oracle: mass matrix not SPD (env %d)\n", e); abort(); }
         for (int i = 0; i < NV; i++) rhs[i] = -rd->c[i];
@@ -1092,6 +1102,7 @@ static void env_torques(Oracle *o, int e, real *tau, uint32_t call) {
         int m = e * A + a;
         for (int j = 0; j < 12; j++) {
             real act = o->actions[m * 12 + j] * d->action_scale;
+            if (d->control_type != 0 && o->motor_strength) act *= o->motor_strength[m * 12 + j];     /* legged_robot_field.py:180-183 */
             if (d->control_type != 0) {   /* LeggedRobot._compute_torques (legged_robot.py:384-392): 'P' / 'V' / 'T', no hip scale, no histories */
                 real qj = dof[(12 * a + j) * 2], qdj = dof[(12 * a + j) * 2 + 1];
                 real t = act;

@@ -440,8 +440,10 @@ def test_domain_rand_push_and_friction_parity():
     cfg.domain_rand.push_robots = True; cfg.domain_rand.push_interval_s = 0.06; cfg.domain_rand.max_push_vel_xy = 0.8
     cfg.domain_rand.randomize_friction = True; cfg.domain_rand.friction_range = [0.05, 1.5]
     cfg.domain_rand.randomize_base_mass = True; cfg.domain_rand.added_mass_range = [-1.0, 3.0]
+    cfg.domain_rand.randomize_com = True                                  # legged_robot_field.py:321-332 (com_range of go1_config.py:218-221)
     np.random.seed(0)
     sc = S.build_scene(cfg, seed=0, policy_mode=E.POLICY_FP32, wrapper_action_scale=(2.0, 0.5, 0.5))
+    assert sc.desc.h_base_com_shift and sc.desc.h_base_added_mass and sc.desc.h_env_friction
     eng, orc = E.Engine(sc.desc, device=0, keepalive=sc), oracle.Oracle(sc, "f32")
     eng.reset(); orc.reset()
     for s in range(7):
@@ -518,8 +520,10 @@ def test_joint_action_control_types_parity(ct):
     cfg.control.control_type = ct
     cfg.control.stiffness = {"joint": 40.0 if ct == "P" else 2.0}; cfg.control.damping = {"joint": 1.0 if ct == "P" else 0.002}
     cfg.normalization.clip_actions = 1.5
+    cfg.domain_rand.randomize_motor = True; cfg.domain_rand.leg_motor_strength_range = [0.7, 1.3]     # legged_robot_field.py:283-291, 180-183
     np.random.seed(0)
     sc = S.build_scene(cfg, seed=0, policy_mode=E.POLICY_FP32, wrapper_action_scale=(2.0, 0.5, 0.5))
+    assert sc.desc.h_motor_strength
     eng, orc = E.Engine(sc.desc, device=0, keepalive=sc), oracle.Oracle(sc, "f32")
     eng.reset(); orc.reset()
     assert eng.lib.mqe_sim_step(eng.h, dev(actions_for(sc, 0)).data_ptr()) == -4           # MQE_ERR_UNSUPPORTED: commands need control_type 'C'
