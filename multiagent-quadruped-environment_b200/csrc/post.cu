@@ -29,18 +29,18 @@ __device__ void dev_gait_clock(const DevParams &p, int m, float dt_policy) {
 
 // ---- warp-cooperative helpers (one warp per agent / per env) ----
 // reset_idx for one env by one warp: _reset_dofs, _reset_root_states, _reset_buffers (go1.py:110-145, legged_robot.py:394-470)
-__device__ void dev_env_reset_warp(const DevParams &p, int e, int lane) {
+__device__ void dev_env_reset_warp(const DevParams &p, int e, int lane, int GS) {
     const int A = p.A, P = p.P, G = p.G;
     const uint32_t ge = (uint32_t)(e + p.env_off), ep = p.episode[e];
     float *dof = p.dof + (size_t)e * (12 * A + p.D) * 2;
-    for (int t = lane; t < A * 12; t += 32) {
+    for (int t = lane; t < A * 12; t += GS) {
         const int a = t / 12, j = t % 12, m = e * A + a;
         const float u = rng_uniform(p.seed, ge, ep, RNG_DOF, a * 12 + j);
         dof[(12 * a + j) * 2] = p.model->q_default[j] * (p.dof_lo + (p.dof_hi - p.dof_lo) * u);
         dof[(12 * a + j) * 2 + 1] = 0.f;
         p.last_actions[m * 12 + j] = 0.f; p.last_dof_vel[m * 12 + j] = 0.f;
     }
-    for (int t = lane; t < A * 13; t += 32) {
+    for (int t = lane; t < A * 13; t += GS) {
         const int a = t / 13, i = t % 13, m = e * A + a;
         float v = p.base_init[m * 13 + i];
         if (i < 3) v += p.agent_origins[m * 3 + i];
@@ -48,9 +48,9 @@ __device__ void dev_env_reset_warp(const DevParams &p, int e, int lane) {
         if (i >= 7) v = p.bvel_lo + (p.bvel_hi - p.bvel_lo) * rng_uniform(p.seed, ge, ep, RNG_BASE_VEL, a * 6 + (i - 7));
         p.root[((size_t)e * G + a) * 13 + i] = v;
     }
-    if (lane < A) p.gait[e * A + lane] = 0.f;
-    for (int k = lane; k < p.D; k += 32) { dof[(12 * A + k) * 2] = p.npc_dof_default[k]; dof[(12 * A + k) * 2 + 1] = 0.f; }
-    for (int n = lane; n < P; n += 32) {               // one lane per NPC (quaternion needs all three angles)
+    for (int a = lane; a < A; a += GS) p.gait[e * A + a] = 0.f;
+    for (int k = lane; k < p.D; k += GS) { dof[(12 * A + k) * 2] = p.npc_dof_default[k]; dof[(12 * A + k) * 2 + 1] = 0.f; }
+    for (int n = lane; n < P; n += GS) {               // one lane per NPC (quaternion needs all three angles)
         float *rs = p.root + ((size_t)e * G + A + n) * 13;
         for (int i = 0; i < 13; i++) rs[i] = p.npc_init[(e * P + n) * 13 + i];
         for (int i = 0; i < 3; i++) rs[i] += p.env_origins[e * 3 + i];
@@ -74,7 +74,7 @@ __device__ void dev_env_reset_warp(const DevParams &p, int e, int lane) {
 }
 
 // compute_observations for one agent by one warp (go1.py:153-196): one obs entry per lane and trip
-__device__ void dev_agent_observations_warp(const DevParams &p, int e, int a, int lane) {
+__device__ void dev_agent_observations_warp(const DevParams &p, int e, int a, int lane, int GS) {
     const int A = p.A, G = p.G;
     const int m = e * A + a;
     float *ob = p.obs + (size_t)m * MQE_OBS_FLOATS;
@@ -84,7 +84,7 @@ __device__ void dev_agent_observations_warp(const DevParams &p, int e, int a, in
     const float q4[4] = {bq[0], bq[1], bq[2], bq[3]};
     float rpy[3];
     get_euler_xyz(q4, rpy);
-    for (int i = lane; i < MQE_OBS_FLOATS; i += 32) {
+    for (int i = lane; i < MQE_OBS_FLOATS; i += GS) {
         float v;
         if (i < MQE_OBS_BASE_QUAT) v = rs[i] - p.env_origins[e * 3 + i];
         else if (i < MQE_OBS_DOF_POS) { const int k = i - MQE_OBS_BASE_QUAT; v = k == 0 ? q4[0] : (k == 1 ? q4[1] : (k == 2 ? q4[2] : q4[3])); }
@@ -102,16 +102,16 @@ __device__ void dev_agent_observations_warp(const DevParams &p, int e, int a, in
 }
 
 // Go1Sheep._step_npc by one warp: every lane forms the flock statistics in the scalar code's order, lane n then moves sheep n
-__device__ void dev_sheep_step_warp(const DevParams &p, int e, uint32_t step_count, int lane) {
+__device__ void dev_sheep_step_warp(const DevParams &p, int e, uint32_t step_count, int lane, int GS, unsigned gmask) {
     const int A = p.A, P = p.P, G = p.G;
     float *root = p.root + (size_t)e * G * 13;
     float avg[3] = {0.f, 0.f, 0.f}, var[2] = {0.f, 0.f};
     for (int n = 0; n < P; n++) for (int i = 0; i < 3; i++) avg[i] += root[(A + n) * 13 + i] / (float)P;
     for (int n = 0; n < P; n++) for (int i = 0; i < 2; i++) { float t = root[(A + n) * 13 + i] - avg[i]; var[i] += t * t / (float)P; }
-    __syncwarp();                                          // every lane has read the pre-step positions
+    __syncwarp(gmask);                                     // every lane of the group has read the pre-step positions
     if (lane == 0) { p.sheep_stats[e * 3] = avg[0]; p.sheep_stats[e * 3 + 1] = avg[1]; p.sheep_stats[e * 3 + 2] = var[0] + var[1]; }
     const uint32_t ge = (uint32_t)(e + p.env_off);
-    for (int n = lane; n < P; n += 32) {                   // a sheep only writes its own row; agents' rows are read-only here
+    for (int n = lane; n < P; n += GS) {                   // a sheep only writes its own row; agents' rows are read-only here
         float *rs = root + (A + n) * 13, dv[3];
         for (int i = 0; i < 3; i++) dv[i] = p.sheep_rand * rng_normal(p.seed, ge, step_count, RNG_SHEEP, n * 3 + i) * 2.f;
         if (P != 1) {
@@ -135,41 +135,44 @@ __device__ void dev_sheep_step_warp(const DevParams &p, int e, uint32_t step_cou
     }
 }
 
-// One WARP per (env, agent); a block handles POST_WARPS / A whole envs.  Per-agent work (base-frame velocities, gait clock,
-// termination tests, observation row, last_* copies) is spread over the lanes, the env-level decisions (time-out, reset, NPC step)
-// run on the env's first agent warp between two block barriers.  (Round 1 used one THREAD per agent: 8192 threads for C2, i.e.
-// 55 threads per SM of serial scattered loads / stores -- pure latency.)
-#define POST_WARPS 8
-#define POST_THREADS (32 * POST_WARPS)
+// A group of POST_GS lanes per (env, agent); a block handles POST_GROUPS / A whole envs.  The scalar part of an agent's work (base-frame
+// velocities, Euler angles, gait clock: a few hundred dependent instructions full of atan2f / sinf / fmodf) is executed once per WARP
+// instruction whatever the lane count, so a whole warp per agent pays it 8192 times (measured 29 us) and a thread per agent leaves the
+// machine empty (r1: 25 us); four lanes per agent issue it 1024 times and still spread the 71-float observation row, the reset and the
+// sheep step over lanes.  Env-level decisions (time-out, reset, NPC step) run on the env's first agent group between two block barriers.
+#define POST_GS 4
+#define POST_THREADS 256
+#define POST_GROUPS (POST_THREADS / POST_GS)
 __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsigned int step_count) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ int s_flags[POST_WARPS];
+    __shared__ int s_flags[POST_GROUPS], s_reset[POST_GROUPS];
     if (step_count == 0xffffffffu) step_count = (unsigned int)p.ctr[1];     // graph replay: device counter
     const int A = p.A, P = p.P, G = p.G;
-    const int envs_per_block = POST_WARPS / A;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int el = warp / A, a = warp % A;
+    const int envs_per_block = POST_GROUPS / A;
+    const int grp = threadIdx.x / POST_GS, gl = threadIdx.x % POST_GS;       // agent slot of the block, lane inside the group
+    const unsigned gmask = ((1u << POST_GS) - 1u) << ((threadIdx.x & 31) & ~(POST_GS - 1));
+    const int el = grp / A, a = grp % A;
     const int e = blockIdx.x * envs_per_block + el;
     const bool live = el < envs_per_block && e < p.N;
     const float PI = 3.14159265358979323846f;
     const float dt_policy = p.dt * (float)p.decimation;
-    if (threadIdx.x < POST_WARPS) s_flags[threadIdx.x] = 0;
+    if (threadIdx.x < POST_GROUPS) { s_flags[threadIdx.x] = 0; s_reset[threadIdx.x] = 0; }
     __syncthreads();
     if (live) {
         const int m = e * A + a;
         const float *rs = p.root + ((size_t)e * G + a) * 13;
-        const float q4[4] = {rs[3], rs[4], rs[5], rs[6]};                    // same addresses in every lane: one broadcast load each
+        const float q4[4] = {rs[3], rs[4], rs[5], rs[6]};                    // same addresses in the lanes of a group: broadcast loads
         const V3 lv = quat_rotate_inverse(q4, mk(rs[7], rs[8], rs[9]));
         const V3 av = quat_rotate_inverse(q4, mk(rs[10], rs[11], rs[12]));
         const V3 pg = quat_rotate_inverse(q4, mk(0.f, 0.f, -1.f));
-        if (lane < 4) p.base_quat[m * 4 + lane] = lane == 0 ? q4[0] : (lane == 1 ? q4[1] : (lane == 2 ? q4[2] : q4[3]));   // value select: no local array
-        if (lane < 3) {
-            p.base_lin_vel[m * 3 + lane] = comp(lv, lane);
-            p.base_ang_vel[m * 3 + lane] = comp(av, lane);
-            p.proj_grav[m * 3 + lane] = comp(pg, lane);
+        p.base_quat[m * 4 + gl] = gl == 0 ? q4[0] : (gl == 1 ? q4[1] : (gl == 2 ? q4[2] : q4[3]));   // value select: no local array
+        if (gl < 3) {
+            p.base_lin_vel[m * 3 + gl] = comp(lv, gl);
+            p.base_ang_vel[m * 3 + gl] = comp(av, gl);
+            p.proj_grav[m * 3 + gl] = comp(pg, gl);
         }
-        if (p.control_type == 0 && lane == 0) dev_gait_clock(p, m, dt_policy);     // _step_contact_targets runs for control_type 'C' only (go1.py:241)
+        if (p.control_type == 0 && gl == 0) dev_gait_clock(p, m, dt_policy);     // _step_contact_targets runs for control_type 'C' only (go1.py:241)
         // _push_robots (go1.py:237-238, legged_robot.py:472-477): common_step_counter % push_interval == 0 -> every robot's base
         // velocity x, y is redrawn; it takes effect in the next physics step (the derived base quantities above are pre-push)
         const bool push = p.push_interval > 0 && ((step_count + 1u) % (unsigned)p.push_interval) == 0u;
@@ -189,50 +192,51 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
         // comparison with NaN is false), so it is reset here.  Never taken in the parity tests or in 3000-step soak runs.
         const float chk = rs[0] + rs[1] + rs[2] + q4[0] + q4[1] + q4[2] + q4[3] + lv.x + lv.y + lv.z + av.x + av.y + av.z;
         if (!(fabsf(chk) < 1e6f)) f |= 32;
-        __syncwarp();                                                        // all lanes have read the pre-push velocity
-        if (push && lane < 2)
-            p.root[((size_t)e * G + a) * 13 + 7 + lane] = (2.f * rng_uniform(p.seed, (uint32_t)(p.env_off + e), step_count, RNG_PUSH, 2 * a + lane) - 1.f) * p.max_push_vel;
-        if (f && lane == 0) atomicOr(&s_flags[el], f);
+        __syncwarp(gmask);                                                   // all lanes of the group have read the pre-push velocity
+        if (push && gl < 2)
+            p.root[((size_t)e * G + a) * 13 + 7 + gl] = (2.f * rng_uniform(p.seed, (uint32_t)(p.env_off + e), step_count, RNG_PUSH, 2 * a + gl) - 1.f) * p.max_push_vel;
+        if (f && gl == 0) atomicOr(&s_flags[el], f);
     }
     __syncthreads();
-    if (live && a == 0) {
+    if (live && a == 0 && gl == 0) {
+        const int f = s_flags[el];
         int reset = 0;
-        if (lane == 0) {
-            const int f = s_flags[el];
-            long long ep = p.ep_len[e] + 1;
-            p.ep_len[e] = ep;
-            if (p.term_mask & 16) { p.collide_buf[e] = (unsigned char)((f >> 4) & 1); reset |= (f >> 4) & 1; }
-            int to = ep > (long long)p.max_ep_len;
-            p.timeout_buf[e] = (unsigned char)to;
-            reset |= to;
-            if (p.term_mask & 1) { p.r_term[e] = (unsigned char)(f & 1); reset |= f & 1; }
-            if (p.term_mask & 2) { p.p_term[e] = (unsigned char)((f >> 1) & 1); reset |= (f >> 1) & 1; }
-            if (p.term_mask & 4) { p.zl_term[e] = (unsigned char)((f >> 2) & 1); reset |= (f >> 2) & 1; }
-            if (p.term_mask & 8) { p.zh_term[e] = (unsigned char)((f >> 3) & 1); reset |= (f >> 3) & 1; }
-            if (f & 32) {                                    // blown-up env: also clear what a normal reset keeps (actuator / action histories)
-                reset = 1;
-                atomicAdd(p.stats + 4, 1);
-                for (int i = e * A * 12; i < (e + 1) * A * 12; i++) { p.err1[i] = p.err2[i] = p.vel1[i] = p.vel2[i] = 0.f; p.loc_last[i] = p.loc_last2[i] = 0.f; p.actions[i] = 0.f; }
-            }
-            p.reset_buf[e] = (unsigned char)reset;
-            if (p.result_done) p.result_done[(long long)((step_count + 1u) & 1u) * p.result_half + e] = (unsigned char)reset;     // the learner's copy
-            // legged_robot.py:164-169 binds reset_buf and collide_buf to ONE tensor and ORs every later cause in place, so the
-            // reference's collide_buf equals the full reset mask whenever base contacts terminate
-            if (p.term_mask & 16) p.collide_buf[e] = (unsigned char)reset;
+        long long ep = p.ep_len[e] + 1;
+        p.ep_len[e] = ep;
+        if (p.term_mask & 16) { p.collide_buf[e] = (unsigned char)((f >> 4) & 1); reset |= (f >> 4) & 1; }
+        int to = ep > (long long)p.max_ep_len;
+        p.timeout_buf[e] = (unsigned char)to;
+        reset |= to;
+        if (p.term_mask & 1) { p.r_term[e] = (unsigned char)(f & 1); reset |= f & 1; }
+        if (p.term_mask & 2) { p.p_term[e] = (unsigned char)((f >> 1) & 1); reset |= (f >> 1) & 1; }
+        if (p.term_mask & 4) { p.zl_term[e] = (unsigned char)((f >> 2) & 1); reset |= (f >> 2) & 1; }
+        if (p.term_mask & 8) { p.zh_term[e] = (unsigned char)((f >> 3) & 1); reset |= (f >> 3) & 1; }
+        if (f & 32) {                                    // blown-up env: also clear what a normal reset keeps (actuator / action histories)
+            reset = 1;
+            atomicAdd(p.stats + 4, 1);
+            for (int i = e * A * 12; i < (e + 1) * A * 12; i++) { p.err1[i] = p.err2[i] = p.vel1[i] = p.vel2[i] = 0.f; p.loc_last[i] = p.loc_last2[i] = 0.f; p.actions[i] = 0.f; }
         }
-        reset = __shfl_sync(0xffffffffu, reset, 0);
-        if (P && p.npc_ctrl == MQE_NPC_SHEEP) { dev_sheep_step_warp(p, e, step_count, lane); __syncwarp(); }
-        if (reset) dev_env_reset_warp(p, e, lane);
+        p.reset_buf[e] = (unsigned char)reset;
+        if (p.result_done) p.result_done[(long long)((step_count + 1u) & 1u) * p.result_half + e] = (unsigned char)reset;     // the learner's copy
+        // legged_robot.py:164-169 binds reset_buf and collide_buf to ONE tensor and ORs every later cause in place, so the
+        // reference's collide_buf equals the full reset mask whenever base contacts terminate
+        if (p.term_mask & 16) p.collide_buf[e] = (unsigned char)reset;
+        s_reset[el] = reset;
+    }
+    __syncthreads();
+    if (live && a == 0) {                                // the env's first agent group: NPC step, then the indexed reset
+        if (P && p.npc_ctrl == MQE_NPC_SHEEP) { dev_sheep_step_warp(p, e, step_count, gl, POST_GS, gmask); __syncwarp(gmask); }
+        if (s_reset[el]) dev_env_reset_warp(p, e, gl, POST_GS);
     }
     __syncthreads();                                     // reset wrote state / last_actions of every agent of the env
     if (live) {
         const int m = e * A + a;
-        dev_agent_observations_warp(p, e, a, lane);
-        __syncwarp();                                    // the row read last_actions before they are overwritten below
+        dev_agent_observations_warp(p, e, a, gl, POST_GS);
+        __syncwarp(gmask);                               // the row read last_actions before they are overwritten below
         const float *rs = p.root + ((size_t)e * G + a) * 13;
         const float *dof = p.dof + ((size_t)e * (12 * A + p.D) + 12 * a) * 2;
-        if (lane < 12) { p.last_actions[m * 12 + lane] = p.actions[m * 12 + lane]; p.last_dof_vel[m * 12 + lane] = dof[lane * 2 + 1]; }
-        else if (lane < 18) p.last_root_vel[m * 6 + lane - 12] = rs[7 + lane - 12];
+        for (int j = gl; j < 12; j += POST_GS) { p.last_actions[m * 12 + j] = p.actions[m * 12 + j]; p.last_dof_vel[m * 12 + j] = dof[j * 2 + 1]; }
+        for (int i = gl; i < 6; i += POST_GS) p.last_root_vel[m * 6 + i] = rs[7 + i];
     }
     // the last block to finish advances the step counter (every block read it at its start, so nobody still needs it)
     __syncthreads();
@@ -246,9 +250,9 @@ __global__ void __launch_bounds__(POST_THREADS) k_post_physics(DevParams p, unsi
 __global__ void __launch_bounds__(128) k_reset_all(DevParams p) {
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= p.N) return;
-    dev_env_reset_warp(p, e, lane);
+    dev_env_reset_warp(p, e, lane, 32);
     __syncwarp();
-    for (int a = 0; a < p.A; a++) dev_agent_observations_warp(p, e, a, lane);
+    for (int a = 0; a < p.A; a++) dev_agent_observations_warp(p, e, a, lane, 32);
     if (p.result_done && lane == 0) p.result_done[(long long)(p.ctr[1] & 1) * p.result_half + e] = 1;
 }
 
@@ -275,7 +279,7 @@ __global__ void k_set_dof_indexed(DevParams p, const float *__restrict__ src, co
 }
 
 extern "C" cudaError_t mqe_launch_post(const DevParams &p, unsigned int step_count, cudaStream_t st) {
-    const int envs_per_block = POST_WARPS / p.A;
+    const int envs_per_block = POST_GROUPS / p.A;
     return launch_heavy(k_post_physics, dim3((p.N + envs_per_block - 1) / envs_per_block), dim3(POST_THREADS), 0, st, p, step_count);
 }
 extern "C" cudaError_t mqe_launch_reset_all(const DevParams &p, cudaStream_t st) {
