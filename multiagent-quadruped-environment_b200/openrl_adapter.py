@@ -85,7 +85,7 @@ class mqe_openrl_wrapper(Wrapper):
         done = self._to_host("done", termination)
         torch.cuda.current_stream(dev).synchronize()
         dones = np.repeat(done[:, None], self.agent_num, axis=1).astype(bool)
-        return (obs.copy() if isinstance(obs, np.ndarray) else obs), (rewards.copy() if isinstance(rewards, np.ndarray) else rewards), dones, [{} for _ in range(dones.shape[0])]
+        return (obs.copy() if isinstance(obs, np.ndarray) else obs), (rewards.copy() if isinstance(rewards, np.ndarray) else rewards), dones, self._empty_infos(dones.shape[0])
 
     def _to_host(self, key, t):
         """device tensor -> numpy through a pinned staging tensor (asynchronous copy; the caller synchronises once)"""
@@ -108,7 +108,18 @@ class mqe_openrl_wrapper(Wrapper):
             done = np.repeat(done, self._task.num_agents)
         rewards = rew[..., None]
         dones = np.repeat(done[:, None], self.agent_num, axis=1)
-        return obs, rewards, dones, [{} for _ in range(dones.shape[0])]
+        return obs, rewards, dones, self._empty_infos(dones.shape[0])
+
+    def _empty_infos(self, n):
+        """`infos = [{} ...]` of utils.py:63-65 without allocating num_envs dicts per step (0.2 ms for 4096 envs): one list of distinct
+        dicts is kept and handed out again; whatever a caller put into them is cleared first."""
+        infos = getattr(self, "_infos", None)
+        if infos is None or len(infos) != n:
+            infos = self._infos = [{} for _ in range(n)]
+        elif any(infos):
+            for d in infos:
+                d.clear()
+        return infos
 
     def _step_device(self, actions):
         """CUDA tensors in, CUDA tensors out (zero-copy views of the engine's step result; valid until the step after next)."""

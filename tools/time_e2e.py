@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Where does the host path spend its time?  Breaks mqe_openrl_wrapper.step (fused host path) into its pieces on one task."""
 import os, sys, time
+os.environ.setdefault("MQE_POLICY_MODE", "1")          # tensor-core policy (bf16x3), as bench.py; must be set before mqe_b200.engine is imported
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
@@ -12,7 +13,6 @@ from mqe_b200.openrl_adapter import make_env
 task = sys.argv[1] if len(sys.argv) > 1 else "go1sheep-hard"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 args = SimpleNamespace(task=task, num_envs=n, seed=0, headless=True, record_video=False, sim_device="cuda:0")
-os.environ.setdefault("MQE_POLICY_MODE", "1")
 ad, cfg = make_env(args)
 ad.reset()
 A = ad._task.env._ctrl_agents
@@ -31,6 +31,11 @@ print(task, n, "engine.step_host_result %.3f ms" % T(lambda i: eng.step_host_res
 print(task, n, "engine.step (device)    %.3f ms" % T(lambda i: eng.step(d_act[i % 16].data_ptr())))
 print(task, n, "engine.step + sync each %.3f ms" % T(lambda i: (eng.step(d_act[i % 16].data_ptr()), eng.synchronize())))
 print(task, n, "np.multiply only        %.3f ms" % T(lambda i: np.multiply(acts[i % 16].reshape(h["act"].shape), 0.5, out=h["act"])))
+print(task, n, "infos list of dicts     %.3f ms" % T(lambda i: [{} for _ in range(n)]))
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for i in range(50): ad.step(acts[i % 16])
+pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(12)
 res = torch.empty(int(h["L"].total_bytes), dtype=torch.uint8, pin_memory=True)
 src = eng.tensor(E.BUF_STEP_RESULT)[0]
 print(task, n, "D2H result (torch pinned) %.3f ms" % T(lambda i: (res.copy_(src, non_blocking=True), torch.cuda.synchronize())))
