@@ -198,7 +198,7 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
             sharding = "contiguous env blocks per rank; ONE NCCL all_gather of the packed step result per step"
         env.reset()                                               # first exchange: global reset observation
 
-    n_act = min(K + W, 64)                                        # distinct action tensors, cycled
+    n_act = 64                                                    # distinct action tensors, cycled (independent of K and W: the pre-rolled state must not depend on --steps)
     h_actions = synth_actions(n_local, a_ctrl, n_act, env_offset=start)
     if args.actions == "forward":
         h_actions[:] = np.asarray([0.5, 0.0, 0.0], dtype=np.float32)
@@ -212,20 +212,24 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
             gather.gather("result", result_all[eng.result_parity()].view(1, -1))
 
     # ---- steady state: random episode phases, then one full episode of pre-roll (untimed) ----
-    pre = 0 if args.no_preroll else (args.preroll_episodes if headline else 1) * int(base.max_episode_length) + 1
+    pre = 0 if (args.no_preroll or ctx.get("no_preroll")) else (args.preroll_episodes if headline else 1) * int(base.max_episode_length) + 1
     if pre:
         desynchronise(base, torch, seed=0)
     for i in range(pre):
+        if i >= pre - 40:                                          # the last pre-roll steps already run in the timed region's regime (L2 flushed every step)
+            flush.zero_()
         one_step(i)
+    # the clock sampler thread is spun up BEFORE the warm-up steps: it is then polling when even a 7 ms timed region starts, and the GPU
+    # never sits idle between warm-up and the timed region (a 20 ms pause here cost the first ~15 timed steps 10 % in an earlier version)
+    sampler = ClockSampler(ctx["local_rank"]) if (headline and rank == 0) else None
+    if sampler:
+        sampler.start()
     for i in range(W):
+        flush.zero_()
         one_step(pre + i)
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, L2 flushed (untimed) between steps, per-step CUDA events on the launching stream ----
-    sampler = ClockSampler(ctx["local_rank"]) if (headline and rank == 0) else None
-    if sampler:                                                   # spun up before the region so that even a 7 ms region is sampled
-        sampler.start()
-        time.sleep(0.02)
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     if world > 1:
@@ -249,7 +253,8 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
     dev_ms = sum(per_step)
     q = max(1, K // 4)
     drift = {"first_quarter_ms": float(np.mean(per_step[:q])), "last_quarter_ms": float(np.mean(per_step[-q:])),
-             "p50_ms": float(np.median(per_step)), "p95_ms": float(np.quantile(per_step, 0.95)), "max_ms": float(np.max(per_step))}
+             "p50_ms": float(np.median(per_step)), "p95_ms": float(np.quantile(per_step, 0.95)), "max_ms": float(np.max(per_step)),
+             "first_32_ms": [round(float(x), 4) for x in per_step[:32]]}
     t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -272,6 +277,21 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
         torch.cuda.synchronize()
         pol_ms.append(e[0].elapsed_time(e[1])); sub_ms.append(e[1].elapsed_time(e[2])); post_ms.append(e[2].elapsed_time(e[3]))
         contacts += float(eng.tensor(E.BUF_STATS)[0].item())
+    # the same stages INSIDE the step graph (event marks between them; the marks cost the launch overlap between stages, ~0.01-0.02 ms)
+    eng.stage_timing(True)
+    for i in range(3):
+        one_step(i)
+    st_rows = []
+    for i in range(R):
+        flush.zero_()
+        one_step(3 + i)
+        st_rows.append(list(eng.stage_ms().values()))
+    eng.stage_timing(False)
+    st_mean = np.mean(np.asarray(st_rows), axis=0)
+    in_step = {"policy_ms": float(st_mean[0]), "physics_and_bookkeeping_ms": float(st_mean[1]), "separate_bookkeeping_gather_exchange_ms": float(st_mean[2]),
+               "background_join_ms": float(st_mean[3]),
+               "note": "mqe_sim_stage_ms: event marks recorded as nodes of the step graph; post-physics bookkeeping runs in the epilogue of k_substeps "
+                       "(fused), the 29-frame layer-0 pass of the next step runs behind the physics and is joined at the end"}
     sub_t = float(np.mean(sub_ms)) * 1e-3
     algo_bytes = n_local * (A * BYTES_PER_AGENT_SUBSTEPS + base.num_npcs * BYTES_PER_NPC)
     peaks, peak_src = measured_peaks()
@@ -287,10 +307,10 @@ def measure(args, task, n_per_gpu, K, W, ctx, headline):
     roofline = {"bound": "hbm", "kernel": "k_substeps", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "kernel_ms": sub_t * 1e3, "policy_ms": float(np.mean(pol_ms)), "post_ms": float(np.mean(post_ms)),
-                "policy_ms_on_critical_path": max(0.0, dev_ms / K - sub_t * 1e3 - float(np.mean(post_ms))),
-                "policy_note": "policy_ms = stand-alone preprocess_action (frame + full 30-frame layer 0 + fused tail); inside a step 29 of the 30 frames "
-                               "were contracted behind the previous step's physics (incremental layer 0), so the step only pays policy_ms_on_critical_path "
-                               "(= ms_per_step - kernel_ms - post_ms)",
+                "policy_ms_on_critical_path": in_step["policy_ms"], "in_step": in_step,
+                "policy_note": "kernel_ms / policy_ms / post_ms are the three stand-alone C-ABI calls (mqe_sim_substeps, mqe_sim_policy = frame + full 30-frame "
+                               "layer 0 + fused tail, mqe_sim_post_physics); inside mqe_sim_step 29 of the 30 frames were contracted behind the previous step's "
+                               "physics and the bookkeeping is fused into k_substeps, so the step pays `in_step` instead",
                 "contacts_per_env_substep": contacts / max(1, R * n_local * base.decimation),
                 "regime": f"steady state (random episode phases, {pre} pre-roll steps), {R} launches after the timed region",
                 "note": "scalar-fp32 articulated dynamics + PGS: bound by instruction issue / latency, not by HBM -- see `issue`"}
@@ -406,6 +426,13 @@ def run_gpu(args):
                          "roofline_frac_hbm": r["roofline"]["frac"], "contacts_per_env_substep": r["roofline"]["contacts_per_env_substep"],
                          "pre_roll_steps": r["config"]["pre_roll_steps"], "launches_per_step": r["launches_per_step"]})
         line["configs"] = subs
+    if world == 1 and not args.no_sublines and not args.no_preroll and args.task == TASK:
+        # round 1 timed steps 5..25 after a synchronised reset (every robot still settling, few contacts); kept as a side number so that
+        # BENCH_r01 and this round can be compared like for like -- the headline above is the steady state
+        r = measure(args, args.task, args.num_envs, 20, 5, dict(ctx, no_preroll=True), headline=False)
+        line["early_episode"] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "kernel_ms": r["roofline"]["kernel_ms"],
+                                 "contacts_per_env_substep": r["roofline"]["contacts_per_env_substep"],
+                                 "note": "round-1 regime (all envs at episode steps 5..25); comparison only, not the headline"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, threads = time_oracle(256, 20, 2)
         line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MQE_ABI_VERSION 6
+#define MQE_ABI_VERSION 7
 #define MQE_MAX_PROBES 32
 #define MQE_MAX_CAPS 20
 #define MQE_NUM_DOF 12
@@ -330,6 +330,12 @@ int mqe_sim_history_head(MqeSim *sim);
 int mqe_sim_synchronize(MqeSim *sim);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t mqe_sim_launch_count(MqeSim *sim);
+/* diagnostics: device time of the four stages of mqe_sim_step, from event marks that become nodes of the step graph (so they cost the
+ * programmatic launch overlap between the stages: a few us; off by default).  ms4 = policy (frame, new-frame layer 0, fused tail) |
+ * physics (k_substeps incl. the fused bookkeeping) | separate bookkeeping launches, task gather, peer exchange | wait for the
+ * background layer-0 pass of the NEXT step.  Values are those of the last step on this handle. */
+int mqe_sim_stage_timing(MqeSim *sim, int enable);
+int mqe_sim_stage_ms(MqeSim *sim, float *ms4);
 
 #ifdef __cplusplus
 }

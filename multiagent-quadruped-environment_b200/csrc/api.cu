@@ -51,11 +51,14 @@ struct MqeSim {
     long long plain_steps = 0;
     cudaStream_t aux_stream = nullptr;   // forked policy: adaptation branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_stage[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // mqe_sim_stage_timing: step start, policy done, physics done, bookkeeping done, join done
+    int stage_timing = 0;
     bool fork_policy = false;
     bool fused_policy = false;           // one layer-0 launch + one fused tail kernel (default in the tensor-core modes)
     bool incremental = false;            // incremental layer 0: the 29 known frames of the next step are contracted behind this step's physics
     int zold_head = -1;                  // ring slot (of the NEXT frame) the partial sums in ps.Zold were computed for; -1: none
     int early_tiles = 0;                 // row tiles of the background pass that start beside the fused tail (MQE_L0_EARLY_TILES)
+    int fuse_post = 1;                   // mqe_sim_step: post-physics stages run in the epilogue of k_substeps (MQE_FUSE_POST=0: separate launch)
     int bg_early = 0;                    // set by step_plain around policy_impl: this call may fork the early part
     cudaEvent_t ev_early = nullptr;
     WrapParams wrap = {};                // fused task-wrapper gather (mqe_sim_set_wrapper); kind 0 = off
@@ -148,6 +151,7 @@ int mqe_sim_destroy(MqeSim *s) {
     for (auto &r : s->pinned) cudaHostUnregister(r.ptr);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
+    for (auto &e : s->ev_stage) if (e) cudaEventDestroy(e);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_early) cudaEventDestroy(s->ev_early);
@@ -338,6 +342,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     { const char *e = getenv("MQE_POLICY_FORK"); s->fork_policy = (p.policy_mode != MQE_POLICY_FP32) && !s->tail_fp32 && !(e && e[0] == '0'); }
     { const char *e = getenv("MQE_POLICY_FUSED"); s->fused_policy = (p.policy_mode != MQE_POLICY_FP32) && !s->tail_fp32 && !(e && e[0] == '0'); }
     if (s->fused_policy) s->fork_policy = false;
+    { const char *e = getenv("MQE_FUSE_POST"); s->fuse_post = !(e && e[0] == '0'); }
     { const char *e = getenv("MQE_POLICY_INCR"); s->incremental = s->fused_policy && !(e && e[0] == '0'); }
     { const char *e = getenv("MQE_L0_EARLY_TILES"); s->early_tiles = s->incremental ? (e ? atoi(e) : 0) : 0; }     // measured: 0.400 ms/step with 0, 0.406 with 8 or 14, 0.431 with 28 (the early CTAs slow the tail they run beside)
     if (s->incremental) CK(cudaEventCreateWithFlags(&s->ev_early, cudaEventDisableTiming));
@@ -683,6 +688,9 @@ static int exchange_impl(MqeSim *s) {                    // peer exchange of the
 }
 static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     int rc;
+    // inside a capture (device_ctr) the mark has to become an event-record NODE that the host can query after the replay
+#define STAGE_MARK(i) if (s->stage_timing) CK(device_ctr ? cudaEventRecordWithFlags(s->ev_stage[i], s->stream, cudaEventRecordExternal) : cudaEventRecord(s->ev_stage[i], s->stream))
+    STAGE_MARK(0);
     s->bg_early = (s->incremental && s->p.control_type == 0 && s->early_tiles > 0) ? 1 : 0;
     if (s->p.control_type == 0) rc = policy_impl(s, d_actions, device_ctr);
     else {                                               // 'P' / 'V' / 'T': the caller's joint actions are the actions (go1.py:43-45)
@@ -691,10 +699,21 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
         rc = MQE_OK;
     }
     if (rc != MQE_OK) return rc;
-    const bool bg = s->incremental && s->p.control_type == 0;
+    static const bool debug_no_bg = getenv("MQE_DEBUG_NO_BG") != nullptr;     // TIMING EXPERIMENT ONLY (results are wrong): how much of the step the background pass still costs
+    const bool bg = s->incremental && s->p.control_type == 0 && !debug_no_bg;
+    STAGE_MARK(1);
     if (bg) CK(cudaEventRecord(s->ev_fork, s->stream));   // fork point: the policy of this step is done, the ring holds its frame
-    rc = substeps_impl(s, s->p.decimation, false);      // no memset between kernels: k_policy_finish / k_joint_actions zeroed the statistics
+    // no memset between kernels: k_policy_finish / k_joint_actions zeroed the statistics.  With fuse_post the physics kernel also
+    // finishes the step (post_dev.cuh stages in its epilogue) and no k_post_physics launch follows.
+    if (s->fuse_post) {                                  // the device step counter ctr[1] always equals s->step_count (every post pass bumps it)
+        DevParams q = s->p;
+        q.fuse_post = 1;
+        CK(mqe_launch_substeps(q, s->p.decimation, s->maxpair, s->stream));
+        s->launches += 1;
+        rc = MQE_OK;
+    } else rc = substeps_impl(s, s->p.decimation, false);
     if (rc != MQE_OK) return rc;
+    STAGE_MARK(2);
     if (bg) {
         // next step's 29-frame layer-0 pass on the side stream, low priority, dependent on the fork point only.  It is enqueued AFTER
         // k_substeps on purpose: the one-wave physics grid must get its SMs first, the background pass takes what that grid leaves idle.
@@ -703,14 +722,19 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
         if (rc != MQE_OK) return rc;
         CK(cudaEventRecord(s->ev_join, s->aux_stream));
     }
-    rc = post_impl(s, device_ctr);
-    if (rc != MQE_OK) return rc;
+    if (!s->fuse_post) {
+        rc = post_impl(s, device_ctr);
+        if (rc != MQE_OK) return rc;
+    }
     if (s->wrap.kind != MQE_WRAP_NONE) {
         CK(mqe_launch_task_gather(s->p, s->wrap, 0, s->stream));
         s->launches += 1;
     }
     rc = exchange_impl(s);
+    STAGE_MARK(3);
     if (bg) CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));     // join: the ring must not move under the background pass
+    STAGE_MARK(4);
+#undef STAGE_MARK
     s->bg_early = 0;
     return rc;
 }
@@ -969,5 +993,21 @@ int mqe_sim_synchronize(MqeSim *s) {
     return MQE_OK;
 }
 int64_t mqe_sim_launch_count(MqeSim *s) { return s ? s->launches : 0; }
+int mqe_sim_stage_timing(MqeSim *s, int enable) {
+    if (!s) return fail(MQE_ERR_INVALID, "null handle");
+    CK(cudaSetDevice(s->device));
+    if (enable && !s->ev_stage[0]) for (auto &e : s->ev_stage) CK(cudaEventCreate(&e));
+    if ((enable != 0) != (s->stage_timing != 0)) { CK(cudaStreamSynchronize(s->stream)); drop_graphs(s); }      // the marks are nodes of the step graph
+    s->stage_timing = enable ? 1 : 0;
+    return MQE_OK;
+}
+int mqe_sim_stage_ms(MqeSim *s, float *ms4) {
+    if (!s || !ms4) return fail(MQE_ERR_INVALID, "null argument");
+    if (!s->stage_timing) return fail(MQE_ERR_UNSUPPORTED, "mqe_sim_stage_timing(sim, 1) first");
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->ev_stage[4]));
+    for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(ms4 + i, s->ev_stage[i], s->ev_stage[i + 1]));
+    return MQE_OK;
+}
 
 }  // extern "C"

@@ -12,7 +12,7 @@
 //     M^-1 = blockdiag(S^-1, H_l^-1) (S = Schur complement of the base), so a contact row is 9+9 floats and one
 //     Gauss-Seidel update costs 18 FMAs;
 //   * all per-robot operators of one substep live in shared memory (4 KB / robot), the persistent state in registers.
-#include "common.cuh"
+#include "post_dev.cuh"
 #include "kernels.cuh"
 
 #define ROWF 24        // floats per local row: Jb6 Jl3 Yb6 Yl3 dinv bias lambda meta + pad
@@ -449,7 +449,131 @@ __device__ __forceinline__ void pair_block_coupling(float *r0, float *r1, float 
     r2[19] = side_dot(r2, r1) + side_dot(r2 + 20, r1 + 20);
 }
 
-__global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int maxpair, int spair, int max_cand) {
+// ---- fused post-physics step (mqe_sim_step): the warp that integrated an env also does its bookkeeping, so the fast warps finish the
+// step while the slowest ones are still solving contacts and no separate launch waits for the whole grid (post_dev.cuh; same stages,
+// same four lanes per agent as k_post_physics).  Env-level decisions travel by shuffle: an env never spans two warps.  Kept out of line
+// (DevParams is a __grid_constant__ parameter, so the reference costs nothing): inlined, its live ranges cost the substep loop registers.
+struct PostLaneState { V3 pos, vlin, wang; float qx, qy, qz, qw, q[3], qd[3], act[3]; };
+static __device__ __noinline__ void substeps_fused_post(const DevParams &p, const MqeRobotModel *md, const float *rs, const PostLaneState &st,
+                                                        int env, int ag, int leg, int e_loc, int lane, bool active, bool is_robot, unsigned quad_mask) {
+    const unsigned FULL = 0xffffffffu;
+    const int A = p.A, E = p.E, GA = p.G;
+    const int m_idx = env * A + ag;
+    const V3 pos = st.pos, vlin = st.vlin, wang = st.wang;
+    const float qx = st.qx, qy = st.qy, qz = st.qz, qw = st.qw;
+    const float q[3] = {st.q[0], st.q[1], st.q[2]}, qd[3] = {st.qd[0], st.qd[1], st.qd[2]}, act[3] = {st.act[0], st.act[1], st.act[2]};
+    __syncwarp();                                                      // root / dof / contact rows of the env are visible to its lanes
+    const unsigned step_count = (unsigned)p.ctr[1];                    // read before this warp's arrival below: the increment comes last
+    const bool robot_live = active && is_robot;
+    const int lead = min(31, e_loc * 4 * A);                           // first lane of my env
+    // Stage 1 and stage 4 of a live robot work from the registers this lane integrated (quaternion, velocities, its leg's q / qd /
+    // actions) instead of re-reading the state through global memory: the stand-alone kernel's ~20 us are one chain of dependent
+    // L2 round trips per agent, which the slowest warp would otherwise pay in full.  Same expressions, same rounding as post_dev.cuh.
+    float la[3] = {0.f, 0.f, 0.f}, org[3] = {0.f, 0.f, 0.f}, gp[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, gait0 = 0.f, oz = 0.f;
+    if (robot_live) {                                                  // every load the fast path needs, issued together
+#pragma unroll
+        for (int k = 0; k < 3; k++) { la[k] = p.last_actions[m_idx * 12 + 3 * leg + k]; org[k] = p.env_origins[env * 3 + k]; }
+        oz = p.agent_origins[m_idx * 3 + 2];
+        if (p.control_type == 0) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) gp[k] = p.loc_obs[(size_t)m_idx * MQE_LOC_OBS + 7 + k];
+            gait0 = p.gait[m_idx];
+        }
+    }
+    const float q4[4] = {qx, qy, qz, qw};
+    V3 lv = mk(0, 0, 0), av = mk(0, 0, 0), pg = mk(0, 0, 0);
+    float rpy[3] = {0.f, 0.f, 0.f}, clk = 0.f, pushed = 0.f;
+    bool push = false;
+    int f = 0;
+    if (robot_live) {
+        const float PI = 3.14159265358979323846f;
+        lv = quat_rotate_inverse(q4, vlin); av = quat_rotate_inverse(q4, wang); pg = quat_rotate_inverse(q4, mk(0.f, 0.f, -1.f));
+        p.base_quat[m_idx * 4 + leg] = leg == 0 ? qx : (leg == 1 ? qy : (leg == 2 ? qz : qw));
+        if (leg < 3) {
+            p.base_lin_vel[m_idx * 3 + leg] = comp(lv, leg);
+            p.base_ang_vel[m_idx * 3 + leg] = comp(av, leg);
+            p.proj_grav[m_idx * 3 + leg] = comp(pg, leg);
+        }
+        if (p.control_type == 0) {                                     // dev_gait_clock, foot `leg` on lane `leg`
+            const float dt_policy = p.dt * (float)p.decimation;
+            float g = fmodf(gait0 + dt_policy * gp[0], 1.0f);
+            if (g < 0.f) g += 1.f;
+            if (leg == 0) p.gait[m_idx] = g;
+            const float fi = leg == 0 ? g + gp[1] + gp[2] + gp[3] : (leg == 1 ? g + gp[2] : (leg == 2 ? g + gp[3] : g + gp[1]));
+            const float dur = gp[4];
+            float r = fmodf(fi, 1.0f);
+            if (r < 0.f) r += 1.f;
+            float x = fi;
+            if (r < dur) x = r * (0.5f / dur);
+            else if (r > dur) x = 0.5f + (r - dur) * (0.5f / (1.f - dur));
+            clk = sinf(6.28318530717958647692f * x);
+            p.clock[m_idx * 4 + leg] = clk;
+        } else clk = p.clock[m_idx * 4 + leg];
+        push = p.push_interval > 0 && ((step_count + 1u) % (unsigned)p.push_interval) == 0u;
+        const float *cfb = rs + RS_FORCE;                              // base body: what the last substep stored to p.contact
+        if (sqrtf(cfb[0] * cfb[0] + cfb[1] * cfb[1] + cfb[2] * cfb[2]) > 1.f) f |= 16;
+        get_euler_xyz(q4, rpy);
+        float r0 = rpy[0], r1 = rpy[1];
+        if (r0 > PI) r0 -= 2.f * PI;
+        if (r1 > PI) r1 -= 2.f * PI;
+        const float z = pos.z - oz;
+        if (fabsf(r0) > p.term_roll) f |= 1;
+        if (fabsf(r1) > p.term_pitch) f |= 2;
+        if (z < p.term_zlow) f |= 4;
+        if (z > p.term_zhigh) f |= 8;
+        const float chk = pos.x + pos.y + pos.z + q4[0] + q4[1] + q4[2] + q4[3] + lv.x + lv.y + lv.z + av.x + av.y + av.z;
+        if (!(fabsf(chk) < 1e6f)) f |= 32;
+        if (push && leg < 2) {
+            pushed = (2.f * rng_uniform(p.seed, (uint32_t)(p.env_off + env), step_count, RNG_PUSH, 2 * ag + leg) - 1.f) * p.max_push_vel;
+            p.root[((size_t)env * GA + ag) * 13 + 7 + leg] = pushed;
+        }
+    }
+    int fe = 0;
+    for (int a2 = 0; a2 < A; a2++) fe |= __shfl_sync(FULL, f, min(31, lead + 4 * a2));
+    int reset = 0;
+    if (robot_live && ag == 0 && leg == 0) reset = dev_post_env_decide(p, env, fe, step_count);
+    reset = __shfl_sync(FULL, reset, lead);
+    if (robot_live && ag == 0) dev_post_env_npc_reset(p, env, reset, leg, quad_mask, step_count);
+    __syncwarp();                                                      // the reset wrote state / last_actions of every agent of the env
+    if (robot_live && reset) dev_post_agent_finish(p, env, ag, leg, quad_mask);       // rare: the row of a freshly reset env, from memory
+    else if (robot_live) {
+        float *ob = p.obs + (size_t)m_idx * MQE_OBS_FLOATS;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int j = 3 * leg + k;
+            ob[MQE_OBS_DOF_POS + j] = q[k] - md->q_default[j];
+            ob[MQE_OBS_DOF_VEL + j] = qd[k] * 0.05f;
+            ob[MQE_OBS_LAST_ACTION + j] = act[k];
+            ob[MQE_OBS_LAST_LAST_ACTION + j] = la[k];
+            p.last_actions[m_idx * 12 + j] = act[k];
+            p.last_dof_vel[m_idx * 12 + j] = qd[k];
+        }
+        ob[MQE_OBS_CLOCK + leg] = clk;
+        if (leg == 0) {
+            ob[MQE_OBS_BASE_POS] = pos.x - org[0]; ob[MQE_OBS_BASE_POS + 1] = pos.y - org[1]; ob[MQE_OBS_BASE_POS + 2] = pos.z - org[2];
+            ob[MQE_OBS_BASE_QUAT] = qx; ob[MQE_OBS_BASE_QUAT + 1] = qy; ob[MQE_OBS_BASE_QUAT + 2] = qz; ob[MQE_OBS_BASE_QUAT + 3] = qw;
+        } else if (leg == 1) {
+            ob[MQE_OBS_LIN_VEL] = lv.x * 2.0f; ob[MQE_OBS_LIN_VEL + 1] = lv.y * 2.0f; ob[MQE_OBS_LIN_VEL + 2] = lv.z * 2.0f;
+            ob[MQE_OBS_ANG_VEL] = av.x * 0.25f; ob[MQE_OBS_ANG_VEL + 1] = av.y * 0.25f; ob[MQE_OBS_ANG_VEL + 2] = av.z * 0.25f;
+        } else if (leg == 2) {
+            ob[MQE_OBS_PROJ_GRAVITY] = pg.x; ob[MQE_OBS_PROJ_GRAVITY + 1] = pg.y; ob[MQE_OBS_PROJ_GRAVITY + 2] = pg.z;
+        } else {
+            ob[MQE_OBS_BASE_RPY] = rpy[0]; ob[MQE_OBS_BASE_RPY + 1] = rpy[1]; ob[MQE_OBS_BASE_RPY + 2] = rpy[2];
+        }
+        // last_root_vel: the root velocity AFTER a push (legged_robot.py:146 reads root_states once _push_robots has run)
+        float *lr = p.last_root_vel + m_idx * 6;
+        if (leg == 0) { lr[0] = push ? pushed : vlin.x; lr[4] = wang.y; }
+        else if (leg == 1) { lr[1] = push ? pushed : vlin.y; lr[5] = wang.z; }
+        else if (leg == 2) lr[2] = vlin.z;
+        else lr[3] = wang.x;
+    }
+    if (lane == 0) {                                                   // the last warp to arrive advances the step counter
+        __threadfence();
+        if (atomicAdd(&p.ctr[2], 1) == (p.N + E - 1) / E - 1) { p.ctr[2] = 0; p.ctr[1] += 1; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevParams p, int nsub, int maxpair, int spair, int max_cand) {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const unsigned FULL = 0xffffffffu;
@@ -1716,6 +1840,14 @@ __global__ void __launch_bounds__(256) k_substeps(DevParams p, int nsub, int max
             atomicMax(p.stats + 3, stat_rows);
         }
         if (rank_in_env == 0) atomicAdd(p.stats + 2, stat_pair);
+    }
+    if (p.fuse_post) {                                                     // the env's post-physics step, by the warp that integrated it
+        PostLaneState st;
+        st.pos = pos; st.vlin = vlin; st.wang = wang; st.qx = qx; st.qy = qy; st.qz = qz; st.qw = qw;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { st.q[k] = q[k]; st.qd[k] = qd[k]; st.act[k] = act[k]; }
+        substeps_fused_post(p, md, rs, st, env, ag, leg, e_loc, lane, active, is_robot, quad_mask);
+        PHASE_MARK(15);
     }
     if (p.lag_ring && threadIdx.x == 0) {                                  // the last CTA to finish advances the call counter
         __threadfence();

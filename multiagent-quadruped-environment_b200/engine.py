@@ -14,9 +14,9 @@ import numpy as np
 from .model import MAX_CAPS, MAX_PROBES, RobotModelC  # noqa: F401
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "csrc", "libmqe_b200.so")
+LIB_PATH = os.environ.get("MQE_B200_LIB") or os.path.join(PKG_DIR, "csrc", "libmqe_b200.so")     # override: A/B runs of two builds on one box
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 LOC_OBS = 70
 OBS_FLOATS = 71
 
@@ -167,6 +167,8 @@ def load_library(path=None):
     lib.mqe_sim_step_result_layout.argtypes = [vp, ctypes.POINTER(StepResultLayoutC)]
     lib.mqe_sim_step_host_result.argtypes = [vp, vp, vp]
     lib.mqe_sim_result_parity.argtypes = [vp]
+    lib.mqe_sim_stage_timing.argtypes = [vp, i32]
+    lib.mqe_sim_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.mqe_sim_gather_init.argtypes = [vp, i32, i32, vp]
     lib.mqe_sim_gather_connect.argtypes = [vp, vp]
     lib.mqe_sim_gather_parity.argtypes = [vp]
@@ -198,6 +200,7 @@ EXPORTED_SYMBOLS = [
     "mqe_sim_post_physics", "mqe_sim_set_root_indexed", "mqe_sim_set_dof_indexed", "mqe_policy_forward",
     "mqe_actuator_forward", "mqe_sim_history_head", "mqe_sim_synchronize", "mqe_sim_launch_count",
     "mqe_sim_step_joint", "mqe_sim_step_result_layout", "mqe_sim_step_host_result", "mqe_sim_result_parity", "mqe_sim_gather_init", "mqe_sim_gather_connect", "mqe_sim_gather_view", "mqe_sim_gather_parity",
+    "mqe_sim_stage_timing", "mqe_sim_stage_ms",
 ]
 
 
@@ -373,6 +376,16 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.mqe_sim_launch_count(self.h))
+
+    def stage_timing(self, enable=True):
+        """Diagnostics: event marks between the stages of step() (they become nodes of the step graph); see stage_ms()."""
+        self._check(self.lib.mqe_sim_stage_timing(self.h, 1 if enable else 0))
+
+    def stage_ms(self):
+        """Device time [ms] of the last step's stages: policy | physics (+ fused bookkeeping) | bookkeeping / gather / exchange launches | background join."""
+        out = (ctypes.c_float * 4)()
+        self._check(self.lib.mqe_sim_stage_ms(self.h, out))
+        return {"policy": out[0], "physics": out[1], "bookkeeping": out[2], "background_join": out[3]}
 
     def set_action_scale(self, scale):
         arr = (ctypes.c_float * 3)(*[float(x) for x in scale])
