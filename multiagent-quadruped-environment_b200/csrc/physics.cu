@@ -1559,7 +1559,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
             }
             if (obb && npair > 0) {                            // uniform over the env's lanes (capsule contacts were done in the warp-wide pass; recomputing them is idempotent)
                 __syncwarp(env_mask);                              // rows of a contact were written by the lane that owns the probe
-                for (int c = rank_in_env; c < npair; c += lanes_per_env) pair_block_coupling(prow(3 * c), prow(3 * c + 1), prow(3 * c + 2));
+                for (int c = rank_in_env; c < npair; c += lanes_per_env) { float *R = prow(3 * c); pair_block_coupling(R, R + PROWF, R + 2 * PROWF); }   // a contact's rows are contiguous in either store
             }
             if (rank_in_env == 0 && env < p.N) stat_pair += npair;
         }
@@ -1657,7 +1657,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                     // owns the contact's leg on each side forms that side's three J.w, ONE round of shuffles combines the sides, every
                     // lane of the env runs the same 3-row solve, and the multipliers are carried to the next sweep through the rows.
                     for (int c = 0; c < npair; c++) {
-                        float *R0 = prow(3 * c), *R1 = prow(3 * c + 1), *R2 = prow(3 * c + 2);
+                        float *R0 = prow(3 * c), *R1 = R0 + PROWF, *R2 = R0 + 2 * PROWF;      // contiguous in either store (the shared / global boundary is contact-aligned)
                         const float4 t0 = *reinterpret_cast<const float4 *>(R0 + 40), t1 = *reinterpret_cast<const float4 *>(R1 + 40),
                                      t2 = *reinterpret_cast<const float4 *>(R2 + 40);                    // dinv, bias, lambda, meta
                         const float k10 = R1[18], k20 = R2[18], k21 = R2[19];
@@ -1754,7 +1754,8 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                     V3 n = mk(cmeta[0], cmeta[1], cmeta[2]), t1, t2;
                     tangent_basis(n, t1, t2);
                     int rba = __float_as_int(cmeta[3]), rbb = __float_as_int(cmeta[4]);
-                    V3 f = (prow(3 * c)[42] * idt) * n + (prow(3 * c + 1)[42] * idt) * t1 + (prow(3 * c + 2)[42] * idt) * t2;
+                    const float *Rf = prow(3 * c);
+                    V3 f = (Rf[42] * idt) * n + (Rf[PROWF + 42] * idt) * t1 + (Rf[2 * PROWF + 42] * idt) * t2;
                     for (int side = 0; side < 2; side++) {
                         int rb = side ? rbb : rba;
                         float sg = side ? -1.f : 1.f;
@@ -1919,6 +1920,7 @@ static SubstepPlan substeps_plan(int N, int A, int Pd, int E, int maxpair) {
         const int tasks = (N + E - 1) / E, waves = (tasks + sms * wmax - 1) / (sms * wmax);
         int w = (tasks + sms * waves - 1) / (sms * waves);
         pl.warps = w < 1 ? 1 : (w > wmax ? wmax : w);
+        { static const char *e = getenv("MQE_SUBSTEP_WARPS"); if (e && atoi(e) >= 1 && atoi(e) <= wmax) pl.warps = atoi(e); }   // experiment: CTA granularity
         pl.grid = (tasks + pl.warps - 1) / pl.warps;
     } else pl.grid = 0;
     pl.smem = (size_t)(physics_cta_header_floats() + (pl.warps < 1 ? 1 : pl.warps) * physics_warp_smem_floats(A, Pd, E, pl.spair, maxpair)) * sizeof(float);
