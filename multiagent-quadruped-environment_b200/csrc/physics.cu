@@ -1611,9 +1611,13 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                 }
                 // ---- contact blocks: normal + two friction rows solved together (see local_block_coupling) ----
                 for (int c0 = nlim; c0 < nrows; c0 += 3) {
-                    float *ra = (c0 < SROWS ? rowS : rowG) + c0 * ROWF;
-                    float *rb = (c0 + 1 < SROWS ? rowS : rowG) + (c0 + 1) * ROWF;
-                    float *rc = (c0 + 2 < SROWS ? rowS : rowG) + (c0 + 2) * ROWF;
+                    // the three rows are contiguous unless the block straddles or lies past the shared-memory rows (a robot lying on the ground)
+                    float *ra = rowS + c0 * ROWF, *rb = ra + ROWF, *rc = ra + 2 * ROWF;
+                    if (c0 + 2 >= SROWS) {
+                        ra = (c0 < SROWS ? rowS : rowG) + c0 * ROWF;
+                        rb = (c0 + 1 < SROWS ? rowS : rowG) + (c0 + 1) * ROWF;
+                        rc = rowG + (c0 + 2) * ROWF;
+                    }
                     // J parts of the three rows: Jb0..5 Jl0..2
                     const float4 a0 = *reinterpret_cast<const float4 *>(ra), a1 = *reinterpret_cast<const float4 *>(ra + 4), a2 = *reinterpret_cast<const float4 *>(ra + 8);
                     const float4 b0 = *reinterpret_cast<const float4 *>(rb), b1 = *reinterpret_cast<const float4 *>(rb + 4), b2 = *reinterpret_cast<const float4 *>(rb + 8);
@@ -1644,9 +1648,9 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                     const float du0 = fmaf(c3.w, d2, fmaf(b3.w, d1, a3.w * d0)), du1 = fmaf(c4.x, d2, fmaf(b4.x, d1, a4.x * d0)),
                                 du2 = fmaf(c4.y, d2, fmaf(b4.y, d1, a4.y * d0));
 #pragma unroll
-                    for (int L = 0; L < 4; L++) {                       // branch-free: only the block's leg moves
-                        const bool mine = rleg == L;
-                        ua[L][0] += mine ? du0 : 0.f; ua[L][1] += mine ? du1 : 0.f; ua[L][2] += mine ? du2 : 0.f;
+                    for (int L = 0; L < 4; L++) {                       // branch-free: only the block's leg moves (1 * du + ua is exact)
+                        const float mine = rleg == L ? 1.f : 0.f;
+                        ua[L][0] = fmaf(mine, du0, ua[L][0]); ua[L][1] = fmaf(mine, du1, ua[L][1]); ua[L][2] = fmaf(mine, du2, ua[L][2]);
                     }
                 }
                 if (p.trace && lane == 0) t_sub = (unsigned)clock();
