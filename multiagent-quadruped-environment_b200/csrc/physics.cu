@@ -30,6 +30,7 @@
 #define RS_ROWS 320
 #define SROWS 19       // local rows of a robot kept in shared memory; rows past that (a robot lying on the ground) go to a
                        // per-robot global scratch with the same arithmetic -- shared memory per env sets the residency
+static_assert((SROWS - MQE_MAX_LIMIT) % 3 == 0, "contact blocks start at row MQE_MAX_LIMIT and must not straddle the shared-memory rows");
 #define RS_CMETA (RS_ROWS + SROWS * ROWF)
 #define RS_FORCE (RS_CMETA + MQE_MAX_LOCAL * 4)
 #define RS_SIZE (RS_FORCE + 52)
@@ -1022,7 +1023,10 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
         PHASE_MARK(1);
         CTA_ALIGN(2);
         // ================================================================ P3: rows.  joint limits, then world contacts
+        // Row slots: a robot's joint-limit rows sit at [0, nlim), its contact blocks ALWAYS start at row CROW0 = MQE_MAX_LIMIT, so a block never
+        // straddles the shared / global boundary (SROWS = CROW0 + 3 * 5) and one pointer select addresses all three of its rows; NPC rows start at 0.
         int nrows = 0, nlim = 0;
+        const int crow0 = is_robot ? MQE_MAX_LIMIT : 0;
         if (is_robot) {
             // ---- joint limits: canonical order (dof, lower/upper), cap MQE_MAX_LIMIT ----
             unsigned lm = 0;
@@ -1082,7 +1086,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
             call |= __shfl_xor_sync(quad_mask, call, 1);
             call |= __shfl_xor_sync(quad_mask, call, 2);
             int ncon = min(__popcll(call), MQE_MAX_LOCAL);
-            nrows = nlim + 3 * ncon;
+            nrows = crow0 + 3 * ncon;
             PHASE_MARK(9);
             // ---- pass 2: build rows for my contacts ----
             while (cm) {
@@ -1105,7 +1109,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                 tangent_basis(n, t1, t2);
                 float *cmeta = rs + RS_CMETA + slot * 4;
                 cmeta[0] = n.x; cmeta[1] = n.y; cmeta[2] = n.z; cmeta[3] = __int_as_float(body);
-                int r0 = nlim + 3 * slot;
+                int r0 = crow0 + 3 * slot;
 #pragma unroll 1          // rolled: the body (~850 instructions) then fits the 32 KB L1.5 instruction cache, unrolled it does not
                 for (int dch = 0; dch < 3; dch++) {
                     V3 d = dch == 0 ? n : (dch == 1 ? t1 : t2);
@@ -1131,7 +1135,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                     row[20] = 0.f;
                     row[21] = __int_as_float(leg | ((dch ? 1 : 0) << 4) | (r0 << 8));
                 }
-                local_block_coupling(lrow(r0), lrow(r0 + 1), lrow(r0 + 2));
+                { float *R = lrow(r0); local_block_coupling(R, R + ROWF, R + 2 * ROWF); }
             }
             if (leg == 0 && active) { stat_local += ncon; stat_lim += nlim; }
         } else if (is_npc && active && seesaw) {
@@ -1564,7 +1568,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
             if (rank_in_env == 0 && env < p.N) stat_pair += npair;
         }
         __syncwarp();
-        if (active && (leg == 0 || is_npc)) stat_rows = max(stat_rows, nrows);
+        if (active && (leg == 0 || is_npc)) stat_rows = max(stat_rows, nlim + nrows - crow0);
 
         PHASE_MARK(3);
         CTA_ALIGN(2);
@@ -1588,7 +1592,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
             for (int it = 0; it < p.iters; it++) {
                 // ---- joint-limit rows: single rows, kind 0 (lambda >= 0) ----
                 for (int i = 0; i < nlim; i++) {
-                    float *row = (i < SROWS ? rowS : rowG) + i * ROWF;
+                    float *row = rowS + i * ROWF;
                     const float4 r0 = *reinterpret_cast<const float4 *>(row), r1 = *reinterpret_cast<const float4 *>(row + 4), r2 = *reinterpret_cast<const float4 *>(row + 8);
                     const float4 r3 = *reinterpret_cast<const float4 *>(row + 12), r4 = *reinterpret_cast<const float4 *>(row + 16), r5 = *reinterpret_cast<const float4 *>(row + 20);
                     const int rleg = __float_as_int(r5.y) & 15;
@@ -1610,14 +1614,8 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                     }
                 }
                 // ---- contact blocks: normal + two friction rows solved together (see local_block_coupling) ----
-                for (int c0 = nlim; c0 < nrows; c0 += 3) {
-                    // the three rows are contiguous unless the block straddles or lies past the shared-memory rows (a robot lying on the ground)
-                    float *ra = rowS + c0 * ROWF, *rb = ra + ROWF, *rc = ra + 2 * ROWF;
-                    if (c0 + 2 >= SROWS) {
-                        ra = (c0 < SROWS ? rowS : rowG) + c0 * ROWF;
-                        rb = (c0 + 1 < SROWS ? rowS : rowG) + (c0 + 1) * ROWF;
-                        rc = rowG + (c0 + 2) * ROWF;
-                    }
+                for (int c0 = crow0; c0 < nrows; c0 += 3) {
+                    float *ra = (c0 < SROWS ? rowS : rowG) + c0 * ROWF, *rb = ra + ROWF, *rc = ra + 2 * ROWF;     // block-aligned boundary: see crow0
                     // J parts of the three rows: Jb0..5 Jl0..2
                     const float4 a0 = *reinterpret_cast<const float4 *>(ra), a1 = *reinterpret_cast<const float4 *>(ra + 4), a2 = *reinterpret_cast<const float4 *>(ra + 8);
                     const float4 b0 = *reinterpret_cast<const float4 *>(rb), b1 = *reinterpret_cast<const float4 *>(rb + 4), b2 = *reinterpret_cast<const float4 *>(rb + 8);
@@ -1731,14 +1729,14 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
             float idt = 1.f / p.dt;
             __syncwarp();                                        // multipliers written by other lanes of the quad are read below
             if (is_robot && active) {
-                int ncon = (nrows - nlim) / 3;
+                int ncon = (nrows - crow0) / 3;
                 for (int c = leg; c < ncon; c += 4) {
                     const float *cmeta = rs + RS_CMETA + c * 4;
                     V3 n = mk(cmeta[0], cmeta[1], cmeta[2]), t1, t2;
                     tangent_basis(n, t1, t2);
                     int body = __float_as_int(cmeta[3]);
-                    const int r0 = nlim + 3 * c;
-                    V3 f = (lrow(r0)[20] * idt) * n + (lrow(r0 + 1)[20] * idt) * t1 + (lrow(r0 + 2)[20] * idt) * t2;
+                    const float *Rf = lrow(crow0 + 3 * c);
+                    V3 f = (Rf[20] * idt) * n + (Rf[ROWF + 20] * idt) * t1 + (Rf[2 * ROWF + 20] * idt) * t2;
                     atomicAdd(rs + RS_FORCE + body * 3, f.x); atomicAdd(rs + RS_FORCE + body * 3 + 1, f.y); atomicAdd(rs + RS_FORCE + body * 3 + 2, f.z);
                 }
             } else if (is_npc && active) {

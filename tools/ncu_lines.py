@@ -65,7 +65,9 @@ def main():
         print(f"  {name:28s} time {100 * s / tot:5.1f}%   instructions {100 * i / toti:5.1f}%")
     src = open(srcfile).read().split("\n")
     print("hottest lines:")
-    for l, v in samples.most_common(22):
+    by_instr = os.environ.get("SORT", "time") == "instr"
+    for l, v in (instr if by_instr else samples).most_common(int(os.environ.get("NLINES", "22"))):
+        v = samples[l]
         text = src[l - 1].strip()[:100] if l and l > 0 else "<inlined helper / other file>"
         print(f"  line {l}: time {100 * v / tot:4.1f}%  instr {100 * instr[l] / toti:4.1f}%  {text}")
 
