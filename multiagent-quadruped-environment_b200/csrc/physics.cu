@@ -1070,8 +1070,10 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
             const float sdf_o = active ? sdf_sample(p, pos.x, pos.y).sdf : 0.f;     // same address in all four lanes of the quad
             unsigned long long cm = 0ull;
             const int *pl_ = tbl + leg * 10;
-            if (active)
-                for (int t = 0; t < pl_[0]; t++) {
+            if (active) {
+                const int np_ = pl_[0];
+#pragma unroll 1          // measured: two probes in flight (unroll 2) cost more in instruction fetch than the overlap gives (+0.6 % step)
+                for (int t = 0; t < np_; t++) {
                     const int pi = pl_[1 + t];
                     const float *pr = md->probes[pi];
                     const int link = (int)pr[0];
@@ -1082,6 +1084,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                     ProbeHit h = probe_world(p, pos + xr, pr[5], has_fix, fixb, wall_is_far(p, sdf_o, xr, pr[5]));
                     cm |= (unsigned long long)h.mask << (2 * pi);
                 }
+            }
             unsigned long long call = cm;
             call |= __shfl_xor_sync(quad_mask, call, 1);
             call |= __shfl_xor_sync(quad_mask, call, 2);
@@ -1589,6 +1592,9 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
             float *const rowS = is_robot ? rs + RS_ROWS : ns + NS_ROWS;
             float *const rowG = grows - SROWS * ROWF;
             PHASE_MARK(10);
+            // warp-uniform: almost no warp holds a pair contact, and a uniform branch keeps the compiler from hoisting the pair sweep's
+            // leg-velocity selects (36 instructions) into every sweep of every warp
+            const bool warp_pairs = __any_sync(FULL, npair > 0);
             for (int it = 0; it < p.iters; it++) {
                 // ---- joint-limit rows: single rows, kind 0 (lambda >= 0) ----
                 for (int i = 0; i < nlim; i++) {
@@ -1652,7 +1658,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
                     }
                 }
                 if (p.trace && lane == 0) t_sub = (unsigned)clock();
-                if (npair > 0) {   // uniform over the env's lanes
+                if (warp_pairs && npair > 0) {   // npair is uniform over the env's lanes
 #pragma unroll
                     for (int k = 0; k < 3; k++) u[k] = leg == 0 ? ua[0][k] : (leg == 1 ? ua[1][k] : (leg == 2 ? ua[2][k] : ua[3][k]));
                     // Pair contacts, one block per contact.  A lane reads only its own group's side of the three rows; the lane that

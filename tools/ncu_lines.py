@@ -17,7 +17,11 @@ def main():
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, capture_output=True)
     cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    sass = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+    # OUTER=1: attribute inlined helpers to their call site in the kernel body (nvdisasm prints the inline chain innermost first;
+    # the last annotation before an instruction is the outermost frame)
+    outer = os.environ.get("OUTER", "0") == "1"
+    sass = subprocess.run(["nvdisasm", "--print-line-info-inline" if outer else "--print-line-info", os.path.join(tmp, cubin)],
+                          capture_output=True, text=True).stdout.split("\n")
     addr2line, cur, inside = {}, None, False
     base_name = os.path.basename(srcfile)
     for ln in sass:
@@ -26,7 +30,7 @@ def main():
             continue
         if not inside:
             continue
-        m = re.search(r'//## File "(.*)", line (\d+)', ln)
+        m = re.search(r'//## File "([^"]*)", line (\d+)', ln)
         if m:
             cur = int(m.group(2)) if m.group(1).endswith(base_name) else -1
             continue
