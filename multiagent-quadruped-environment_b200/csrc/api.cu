@@ -682,6 +682,8 @@ int mqe_sim_post_physics(MqeSim *s) {
 
 static int exchange_impl(MqeSim *s) {                    // peer exchange of the step result: last kernel of a step / reset
     if (!s->gather.world) return MQE_OK;
+    static const bool debug_skip = getenv("MQE_DEBUG_NO_EXCHANGE") != nullptr;      // TIMING EXPERIMENT ONLY: what the exchange costs a sharded step
+    if (debug_skip) return MQE_OK;
     CK(mqe_launch_gather_exchange(s->p, s->gather, s->stream));
     s->launches += 1;
     return MQE_OK;
