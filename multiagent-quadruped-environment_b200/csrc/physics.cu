@@ -471,6 +471,8 @@ static __device__ __noinline__ void substeps_fused_post(const DevParams &p, cons
     // actions) instead of re-reading the state through global memory: the stand-alone kernel's ~20 us are one chain of dependent
     // L2 round trips per agent, which the slowest warp would otherwise pay in full.  Same expressions, same rounding as post_dev.cuh.
     float la[3] = {0.f, 0.f, 0.f}, org[3] = {0.f, 0.f, 0.f}, gp[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, gait0 = 0.f, oz = 0.f;
+    long long ep_pre = -1;
+    if (robot_live && ag == 0 && leg == 0) ep_pre = p.ep_len[env];     // the env's decision lane: issued with the loads below, used three stages later
     if (robot_live) {                                                  // every load the fast path needs, issued together
 #pragma unroll
         for (int k = 0; k < 3; k++) { la[k] = p.last_actions[m_idx * 12 + 3 * leg + k]; org[k] = p.env_origins[env * 3 + k]; }
@@ -532,7 +534,7 @@ static __device__ __noinline__ void substeps_fused_post(const DevParams &p, cons
     int fe = 0;
     for (int a2 = 0; a2 < A; a2++) fe |= __shfl_sync(FULL, f, min(31, lead + 4 * a2));
     int reset = 0;
-    if (robot_live && ag == 0 && leg == 0) reset = dev_post_env_decide(p, env, fe, step_count);
+    if (robot_live && ag == 0 && leg == 0) reset = dev_post_env_decide(p, env, fe, step_count, ep_pre);
     reset = __shfl_sync(FULL, reset, lead);
     if (robot_live && ag == 0) dev_post_env_npc_reset(p, env, reset, leg, quad_mask, step_count);
     __syncwarp();                                                      // the reset wrote state / last_actions of every agent of the env
@@ -568,8 +570,9 @@ static __device__ __noinline__ void substeps_fused_post(const DevParams &p, cons
         else if (leg == 2) lr[2] = vlin.z;
         else lr[3] = wang.x;
     }
-    if (lane == 0) {                                                   // the last warp to arrive advances the step counter
-        __threadfence();
+    if (lane == 0) {
+        // The last warp to arrive advances the step counter.  No fence: every warp's read of ctr[1] has returned before it gets here (its
+        // value addressed the stores above), and nothing else in this kernel is ordered against the counter.
         if (atomicAdd(&p.ctr[2], 1) == (p.N + E - 1) / E - 1) { p.ctr[2] = 0; p.ctr[1] += 1; }
     }
 }

@@ -182,10 +182,10 @@ static __device__ int dev_post_agent_derive(const DevParams &p, int e, int a, in
 }
 
 // stage 2, ONE lane per env: episode length, time-out, the termination causes the task enabled; f = OR of the agents' flags.  Returns reset.
-static __device__ int dev_post_env_decide(const DevParams &p, int e, int f, unsigned step_count) {
+static __device__ int dev_post_env_decide(const DevParams &p, int e, int f, unsigned step_count, long long ep_loaded = -1) {
     const int A = p.A;
     int reset = 0;
-    long long ep = p.ep_len[e] + 1;
+    long long ep = (ep_loaded >= 0 ? ep_loaded : p.ep_len[e]) + 1;      // ep_loaded: the caller issued the load earlier, with its other loads
     p.ep_len[e] = ep;
     if (p.term_mask & 16) { p.collide_buf[e] = (unsigned char)((f >> 4) & 1); reset |= (f >> 4) & 1; }
     int to = ep > (long long)p.max_ep_len;
