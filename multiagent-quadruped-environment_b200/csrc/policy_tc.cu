@@ -47,25 +47,31 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 // ELU(alpha = 1) without the ~30-instruction expm1f: degree-7 Taylor for -0.25 < x <= 0 (|err| < 2e-8 relative),
 // ex2.approx-based exp(x) - 1 below that (result magnitude >= 0.22, so the absolute 1e-7 is <= 5e-7 relative).
 __device__ __forceinline__ float elu1_tc(float x) {
+    // ELU on the tensor-core path: exp through ex2.approx.  exp(t) - 1 loses RELATIVE accuracy for |t| << 1 but stays within 2.5e-7
+    // ABSOLUTE (the value is about to be split into bf16 hi + lo and summed 128..512 wide against a 2e-4 parity bound), and costs 6
+    // instructions where the expm1-grade polynomial + select used before cost 15 -- the A-operand producers of the fused tail are
+    // bound by exactly this arithmetic (tools/tail_trace.py: 18.6 of 43 us).  The fp32 cross-check path (policy.cu) keeps expm1f.
     const float t = fminf(x, 0.f);
-    float pz = fmaf(t, 1.f / 5040.f, 1.f / 720.f);
-    pz = fmaf(pz, t, 1.f / 120.f); pz = fmaf(pz, t, 1.f / 24.f); pz = fmaf(pz, t, 1.f / 6.f); pz = fmaf(pz, t, 0.5f); pz = fmaf(pz, t, 1.f);
-    const float small = pz * t, big = __expf(t) - 1.f;
-    const float neg = t > -0.25f ? small : big;
+    const float neg = __expf(t) - 1.f;
     return x > 0.f ? x : neg;
 }
+// v = float(hi) + float(lo) + O(2^-17 |v|), both halves rounded to nearest even: two packed conversions per PAIR of values
+// (cvt.rn.bf16x2.f32; same bits as the integer round-to-nearest-even k_policy_frame uses, for every finite value)
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo_half, float hi_half) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+    return r;
+}
 __device__ __forceinline__ void split_bf16x8(const float *v, uint4 &hi, uint4 &lo) {
-    uint32_t h[8], l[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        uint32_t b = __float_as_uint(v[i]);
-        uint32_t hb = (b + 0x7fffu + ((b >> 16) & 1u)) & 0xffff0000u;
-        uint32_t rb = __float_as_uint(v[i] - __uint_as_float(hb));
-        h[i] = hb >> 16;
-        l[i] = (rb + 0x7fffu + ((rb >> 16) & 1u)) >> 16;
+    for (int i = 0; i < 4; i++) {
+        h[i] = bf16x2_rn(v[2 * i], v[2 * i + 1]);
+        const float r0 = v[2 * i] - __uint_as_float(h[i] << 16), r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+        l[i] = bf16x2_rn(r0, r1);
     }
-    hi = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
-    lo = make_uint4(l[0] | (l[1] << 16), l[2] | (l[3] << 16), l[4] | (l[5] << 16), l[6] | (l[7] << 16));
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 // element offset of (row m, column k) in an activation plane with `kchunks` = K/8 chunks per row tile
 __device__ __forceinline__ size_t plane_index(int m, int k, int kchunks) {
@@ -509,6 +515,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
     float *s_wlat = sf + 7168;                              // [512][2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mtile = blockIdx.x, M = a.M;
+    // MQE_TRACE=1: the first epilogue thread stamps the global timer at the phase boundaries into row `mtile` of the warp trace
+    // (read it after a stand-alone mqe_sim_policy call: k_substeps reuses the buffer); tools/tail_trace.py
+    long long *const ttr = (p.trace && p.warp_trace && threadIdx.x == 64) ? p.warp_trace + (size_t)mtile * MQE_TRACE_COLS : nullptr;
+#define TAIL_MARK(k) if (ttr) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ttr[k] = t_; }
+    TAIL_MARK(0);
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < 128; i += FT_THREADS) { s_ba1[i] = a.ba1[i]; s_bb2[i] = a.bb2[i]; }
     for (int i = threadIdx.x; i < 256; i += FT_THREADS) { s_bb1[i] = a.bb1[i]; s_hwA[i] = a.aw2[i]; }
@@ -601,8 +612,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
         const int et = (int)threadIdx.x - 64;                 // 0..511 among the epilogue threads
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         // ---- adapt.2 epilogue: bias + ELU, head adapt.4 in fp32 from the accumulator row -> latent ----
+        TAIL_MARK(1);
         mbar_wait(&acc_done[0], 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TAIL_MARK(2);
         {
             float h0 = 0.f, h1 = 0.f;
 #pragma unroll 1
@@ -626,6 +639,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
             }
             asm volatile("bar.sync 2, %0;" ::"n"(32 * FT_EPI_WARPS) : "memory");
         }
+        TAIL_MARK(3);
         // ---- body.2 A operand: ELU(Z_body + W_lat latent), one 64-column chunk per fill, written in the canonical K-major layout ----
         // this thread's part of Z (row m, 16 columns of every 64-column chunk) is fetched one chunk ahead of its use
         const int m = et & 127, grow = mtile * 128 + m, kc0 = (et >> 7) * 2;
@@ -671,8 +685,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_a[st])) : "memory");
         }
         // ---- body.4 A operand: ELU(body.2 accumulator + bias) from TMEM, 64 columns per fill ----
+        TAIL_MARK(4);
         mbar_wait(&acc_done[1], 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TAIL_MARK(5);
 #pragma unroll 1
         for (int j = 0; j < 4; j++) {
             const int f = 12 + j, st = f & 1;
@@ -700,8 +716,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_a[st])) : "memory");
         }
         // ---- body.4 epilogue: bias + ELU, head body.6 in fp32 -> action; then the shift / clip of k_policy_finish ----
+        TAIL_MARK(6);
         mbar_wait(&acc_done[2], 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TAIL_MARK(7);
         {
             float hp[12];
 #pragma unroll
@@ -711,11 +729,18 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
                 uint32_t v[16];
                 const int col = part * 32 + c * 16;
                 tmem_ld16(trow + 384u + (uint32_t)col, v);
+                float t[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float t = elu1_tc(__uint_as_float(v[i]) + s_bb2[col + i]);
+                for (int i = 0; i < 16; i++) t[i] = elu1_tc(__uint_as_float(v[i]) + s_bb2[col + i]);
 #pragma unroll
-                    for (int o = 0; o < 12; o++) hp[o] = fmaf(t, s_hwB[o * 128 + col + i], hp[o]);
+                for (int o = 0; o < 12; o++) {                // weights four at a time (same per-output summation order as one at a time)
+                    const float4 *w4 = reinterpret_cast<const float4 *>(s_hwB + o * 128 + col);
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; i4++) {
+                        const float4 w = w4[i4];
+                        hp[o] = fmaf(t[4 * i4], w.x, hp[o]); hp[o] = fmaf(t[4 * i4 + 1], w.y, hp[o]);
+                        hp[o] = fmaf(t[4 * i4 + 2], w.z, hp[o]); hp[o] = fmaf(t[4 * i4 + 3], w.w, hp[o]);
+                    }
                 }
             }
             if (part)
@@ -736,6 +761,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
                 }
             }
         }
+        TAIL_MARK(8);
         if (a.finish && blockIdx.x == 0) {                    // the rest of k_policy_finish: nothing reads these before the next kernel
             for (int t = et; t < p.N; t += 32 * FT_EPI_WARPS) p.hist_dirty[t] = 0;
             if (et < 5) p.stats[et] = 0;
