@@ -521,10 +521,6 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
 #define TAIL_MARK(k) if (ttr) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ttr[k] = t_; }
     TAIL_MARK(0);
     pdl_launch_dependents();
-    for (int i = threadIdx.x; i < 128; i += FT_THREADS) { s_ba1[i] = a.ba1[i]; s_bb2[i] = a.bb2[i]; }
-    for (int i = threadIdx.x; i < 256; i += FT_THREADS) { s_bb1[i] = a.bb1[i]; s_hwA[i] = a.aw2[i]; }
-    for (int i = threadIdx.x; i < 1536; i += FT_THREADS) s_hwB[i] = a.bw3[i];
-    for (int i = threadIdx.x; i < 1024; i += FT_THREADS) s_wlat[i] = a.wlat[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) { mbar_init(&full_w[i], 1); mbar_init(&full_a[i], FT_EPI_WARPS); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 3; i++) mbar_init(&acc_done[i], 1);
@@ -611,6 +607,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
         const int r = q * 32 + lane, row = mtile * 128 + r;    // this thread's row of the tile
         const int et = (int)threadIdx.x - 64;                 // 0..511 among the epilogue threads
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        // biases, head weights and the latent columns of body.0 into shared memory -- by the epilogue warps only, while the producer and the
+        // MMA warp already stream adapt.2 (these constants used to sit in front of the first bulk copy: 2 us of the kernel)
+        for (int i = et; i < 128; i += 32 * FT_EPI_WARPS) { s_ba1[i] = a.ba1[i]; s_bb2[i] = a.bb2[i]; }
+        for (int i = et; i < 256; i += 32 * FT_EPI_WARPS) { s_bb1[i] = a.bb1[i]; s_hwA[i] = a.aw2[i]; }
+        for (int i = et; i < 1536; i += 32 * FT_EPI_WARPS) s_hwB[i] = a.bw3[i];
+        for (int i = et; i < 1024; i += 32 * FT_EPI_WARPS) s_wlat[i] = a.wlat[i];
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * FT_EPI_WARPS) : "memory");
         // ---- adapt.2 epilogue: bias + ELU, head adapt.4 in fp32 from the accumulator row -> latent ----
         TAIL_MARK(1);
         mbar_wait(&acc_done[0], 0);

@@ -9,7 +9,7 @@ from mqe_b200 import engine as E
 from mqe_b200.envs.utils import make_mqe_env, custom_cfg
 n = 4096
 eargs = SimpleNamespace(num_envs=n, seed=0, headless=True, record_video=False, sim_device="cuda:0")
-env, cfg = make_mqe_env("go1gate", eargs, custom_cfg(eargs), policy_mode=E.POLICY_BF16X3)
+env, cfg = make_mqe_env("go1gate", eargs, custom_cfg(eargs), policy_mode={"bf16x3": E.POLICY_BF16X3, "bf16": E.POLICY_BF16}[os.environ.get("TAIL_MODE", "bf16x3")])
 base, eng = env.env, env.env.engine
 acts = torch.as_tensor(B.synth_actions(n, base._ctrl_agents, 64, env_offset=0), device="cuda:0")
 env.reset()
