@@ -669,10 +669,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
                 if (grow < M) {
                     const float4 z0 = zc[2 * cc], z1 = zc[2 * cc + 1];
                     v[0] = z0.x; v[1] = z0.y; v[2] = z0.z; v[3] = z0.w; v[4] = z1.x; v[5] = z1.y; v[6] = z1.z; v[7] = z1.w;
+                    // latent columns of body.0 for these 8 outputs: four 16-byte broadcast loads instead of sixteen scalar ones (the
+                    // producers stalled on the short scoreboard here: ncu warm-cache source view)
+                    const float4 *w4 = reinterpret_cast<const float4 *>(s_wlat + (j * 64 + kc * 8) * 2);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int n = j * 64 + kc * 8 + i;
-                        v[i] = elu1_tc(v[i] + s_wlat[n * 2] * l0 + s_wlat[n * 2 + 1] * l1);
+                    for (int i2 = 0; i2 < 4; i2++) {
+                        const float4 w = w4[i2];              // (w0, w1) of output 2 i2, (w0, w1) of output 2 i2 + 1
+                        v[2 * i2] = elu1_tc(v[2 * i2] + w.x * l0 + w.y * l1);
+                        v[2 * i2 + 1] = elu1_tc(v[2 * i2 + 1] + w.z * l0 + w.w * l1);
                     }
                 } else {
 #pragma unroll
@@ -703,7 +707,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
                 tmem_ld16(trow + 128u + (uint32_t)col, v);
                 float fv[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) fv[i] = elu1_tc(__uint_as_float(v[i]) + s_bb1[col + i]);
+                for (int i4 = 0; i4 < 4; i4++) {
+                    const float4 b = *reinterpret_cast<const float4 *>(s_bb1 + col + 4 * i4);
+                    fv[4 * i4] = elu1_tc(__uint_as_float(v[4 * i4]) + b.x); fv[4 * i4 + 1] = elu1_tc(__uint_as_float(v[4 * i4 + 1]) + b.y);
+                    fv[4 * i4 + 2] = elu1_tc(__uint_as_float(v[4 * i4 + 2]) + b.z); fv[4 * i4 + 3] = elu1_tc(__uint_as_float(v[4 * i4 + 3]) + b.w);
+                }
                 uint4 hi, lo;
                 const int kc = part * 2;
                 split_bf16x8(fv, hi, lo);
@@ -734,7 +742,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
                 tmem_ld16(trow + 384u + (uint32_t)col, v);
                 float t[16];
 #pragma unroll
-                for (int i = 0; i < 16; i++) t[i] = elu1_tc(__uint_as_float(v[i]) + s_bb2[col + i]);
+                for (int i4 = 0; i4 < 4; i4++) {
+                    const float4 b = *reinterpret_cast<const float4 *>(s_bb2 + col + 4 * i4);
+                    t[4 * i4] = elu1_tc(__uint_as_float(v[4 * i4]) + b.x); t[4 * i4 + 1] = elu1_tc(__uint_as_float(v[4 * i4 + 1]) + b.y);
+                    t[4 * i4 + 2] = elu1_tc(__uint_as_float(v[4 * i4 + 2]) + b.z); t[4 * i4 + 3] = elu1_tc(__uint_as_float(v[4 * i4 + 3]) + b.w);
+                }
 #pragma unroll
                 for (int o = 0; o < 12; o++) {                // weights four at a time (same per-output summation order as one at a time)
                     const float4 *w4 = reinterpret_cast<const float4 *>(s_hwB + o * 128 + col);

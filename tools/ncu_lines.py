@@ -43,6 +43,7 @@ def main():
     ai, si, ii = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     samples, instr, stalls, base = collections.Counter(), collections.Counter(), collections.Counter(), None
+    line_stalls = collections.defaultdict(collections.Counter)
     for r in rows[2:]:
         if r and r[0] == "Kernel Name":
             break
@@ -59,6 +60,7 @@ def main():
         for c in stall_cols:
             if r[c] and r[c] != "0":
                 stalls[hdr[c]] += int(r[c])
+                line_stalls[l][hdr[c][6:]] += int(r[c])
     tot, toti = sum(samples.values()), sum(instr.values())
     print(f"samples {tot}  warp-instructions {toti}")
     print("stall mix:", ", ".join(f"{k[6:]} {100 * v / sum(stalls.values()):.1f}%" for k, v in stalls.most_common(8)))
@@ -73,7 +75,8 @@ def main():
     for l, v in (instr if by_instr else samples).most_common(int(os.environ.get("NLINES", "22"))):
         v = samples[l]
         text = src[l - 1].strip()[:100] if l and l > 0 else "<inlined helper / other file>"
-        print(f"  line {l}: time {100 * v / tot:4.1f}%  instr {100 * instr[l] / toti:4.1f}%  {text}")
+        why = ", ".join(f"{k} {100 * c / max(1, sum(line_stalls[l].values())):.0f}%" for k, c in line_stalls[l].most_common(3)) if os.environ.get("WHY") else ""
+        print(f"  line {l}: time {100 * v / tot:4.1f}%  instr {100 * instr[l] / toti:4.1f}%  {text}" + (f"   [{why}]" if why else ""))
 
 
 if __name__ == "__main__":
