@@ -396,7 +396,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     if (p.policy_mode != MQE_POLICY_FP32) { CK(dalloc(s, &p.hist_hi, ring_tc)); CK(dalloc(s, &p.hist_lo, ring_tc)); }
     CK(dalloc(s, &s->ps.Z, (size_t)M * 768)); CK(dalloc(s, &s->ps.T1, (size_t)M * 128)); CK(dalloc(s, &s->ps.T2, (size_t)M * 256));
     CK(dalloc(s, &s->ps.T3, (size_t)M * 128)); CK(dalloc(s, &s->ps.latent, (size_t)M * 2)); CK(dalloc(s, &s->ps.act, (size_t)M * 12));
-    if (s->incremental) CK(dalloc(s, &s->ps.Zold, (size_t)M * 768));
+    if (s->incremental) CK(dalloc(s, &s->ps.Zold, (size_t)((M + 127) / 128) * 128 * 768));      // whole 128-row tiles (tile-major layout, policy_tc.cu zold_index)
     CK(dalloc(s, &s->d_actions_stage, s->action_bytes() / sizeof(float)));
     CK(cudaMemsetAsync(p.reset_buf, 1, N, s->stream));                      // base_task.py:77: reset_buf starts as ones
     // _prepare_locomotion_policy: locomotion_obs = default command frame (go1.py:393-394); actors at their start poses

@@ -79,6 +79,10 @@ __device__ __forceinline__ size_t plane_index(int m, int k, int kchunks) {
 }
 
 
+// float offset of (row r of row tile mt, 4-column group g4 of column tile nt) in Zold: [mt][6 column tiles][32 groups][128 rows][4]
+__device__ __forceinline__ size_t zold_index(int mt, int nt, int g4, int r) {
+    return ((((size_t)mt * 6 + nt) * 32 + g4) * 128 + r) * 4;
+}
 __global__ void __launch_bounds__(320, 1)
 k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__restrict__ a_lo,
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
@@ -184,18 +188,21 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int n0 = ntile * 128 + c * 32;
             if (mode == 1) {                                // raw partial sums of the 29 known frames
-                if (row < M) {
-                    float *dst = Zold + (size_t)row * 768 + n0;
+                // Zold is private to these two passes, so it is stored the way its threads touch it: [row tile][column tile][4-column group]
+                // [128 rows][4] -- the 32 lanes of a warp (32 consecutive rows) then write / read 512 contiguous bytes per instruction
+                // instead of one half-used 32-byte sector per lane (row-major [M][768])
+                {
+                    float *dst = Zold + zold_index(mtile, ntile, c * 8, q * 32 + lane);
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<uint4 *>(dst + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<uint4 *>(dst + (size_t)(i / 4) * 512) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 }
                 continue;
             }
             if (mode == 2 && row < M && !dirty[row / agents]) {      // + the 29 older frames (a row whose history was reset keeps only the new frame)
-                const float *src = Zold + (size_t)row * 768 + n0;
+                const float *src = Zold + zold_index(mtile, ntile, c * 8, q * 32 + lane);
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 z = *reinterpret_cast<const float4 *>(src + i);
+                    const float4 z = *reinterpret_cast<const float4 *>(src + (size_t)(i / 4) * 512);
                     v[i] = __float_as_uint(__uint_as_float(v[i]) + z.x); v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + z.y);
                     v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + z.z); v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + z.w);
                 }
