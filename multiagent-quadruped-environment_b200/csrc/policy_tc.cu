@@ -88,7 +88,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
                const float *__restrict__ b0cat, float *__restrict__ Z, unsigned short *__restrict__ a0_hi,
                unsigned short *__restrict__ a0_lo, int M, int head, int passes, const int *__restrict__ ctr, int ntile0,
-               int mode, float *__restrict__ Zold, const unsigned char *__restrict__ dirty, int agents, int mtile0) {
+               int mode, float *__restrict__ Zold, const unsigned char *__restrict__ dirty, int agents, int mtile0, int ztiled) {
     // mode 0: all 30 slots.  Incremental layer 0 (29 of the 30 history frames of the NEXT step are known as soon as this step's frame is in
     // the ring): mode 1 = the 29 slots other than `head` (the slot the next frame will go to), raw accumulators -> Zold, launched at low
     // priority behind the physics of the step so that it fills the idle tail of k_substeps; mode 2 = slot `head` alone (K = 80), plus
@@ -219,8 +219,10 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
                     *reinterpret_cast<uint4 *>(a0_hi + o) = hi;
                     *reinterpret_cast<uint4 *>(a0_lo + o) = lo;
                 }
-            } else if (row < M) {
-                float *dst = Z + (size_t)row * 768 + n0;
+            } else if (row < M || ztiled) {
+                // ztiled (the fused tail follows): Z in the tile-major layout of Zold, so that this store and the tail's loads are coalesced
+                float *dst = ztiled ? Z + zold_index(mtile, ntile, c * 8, q * 32 + lane) : Z + (size_t)row * 768 + n0;
+                const size_t gstride = ztiled ? 512 : 4;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     float4 o;
@@ -228,7 +230,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
                     float t2 = __uint_as_float(v[i + 2]) + __ldg(b0cat + n0 + i + 2), t3 = __uint_as_float(v[i + 3]) + __ldg(b0cat + n0 + i + 3);
                     if (n0 < 256) { t0 = elu1_tc(t0); t1 = elu1_tc(t1); t2 = elu1_tc(t2); t3 = elu1_tc(t3); }
                     o.x = t0; o.y = t1; o.z = t2; o.w = t3;
-                    *reinterpret_cast<float4 *>(dst + i) = o;
+                    *reinterpret_cast<float4 *>(dst + (size_t)(i / 4) * gstride) = o;
                 }
             }
         }
@@ -497,7 +499,7 @@ __global__ void k_body_latent_planes(const float *__restrict__ Z, const float *_
 #define FT_THREADS (64 + 32 * FT_EPI_WARPS)
 struct TailArgs {
     const unsigned short *a0_hi, *a0_lo;                 // adapt.0 activation planes (K = 256), from layer 0's epilogue
-    const float *Z;                                      // layer-0 output [M][768]; columns 256.. = body.0 pre-activation without the latent
+    const float *Z;                                      // layer-0 output, TILE-MAJOR (zold_index; k_policy_l0_tc with ztiled = 1); columns 256.. = body.0 pre-activation without the latent
     const unsigned short *wa_hi, *wa_lo, *wb1_hi, *wb1_lo, *wb2_hi, *wb2_lo;   // tail weights, pre-tiled (tile_layer, 128-row tiles)
     const float *ba1, *bb1, *bb2;                        // biases of adapt.2, body.2, body.4
     const float *aw2, *ab2, *bw3, *bb3, *wlat;           // heads (fp32): adapt.4 [2][128], body.6 [12][128]; latent columns of body.0 [512][2]
@@ -653,10 +655,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
         // ---- body.2 A operand: ELU(Z_body + W_lat latent), one 64-column chunk per fill, written in the canonical K-major layout ----
         // this thread's part of Z (row m, 16 columns of every 64-column chunk) is fetched one chunk ahead of its use
         const int m = et & 127, grow = mtile * 128 + m, kc0 = (et >> 7) * 2;
-        const float *zrow = a.Z + (size_t)(grow < M ? grow : 0) * 768 + 256 + kc0 * 8;
+        // Z arrives tile-major (k_policy_l0_tc, ztiled): body column n = 256 + j * 64 + kc0 * 8 + 4 i sits in column tile n / 128, group (n % 128) / 4
+        auto zptr = [&](int j_, int i_) {
+            const int n = 256 + j_ * 64 + kc0 * 8 + 4 * i_;
+            return reinterpret_cast<const float4 *>(a.Z + zold_index(mtile, n >> 7, (n & 127) >> 2, m));
+        };
         float4 zq[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) zq[i] = *reinterpret_cast<const float4 *>(zrow + 4 * i);
+        for (int i = 0; i < 4; i++) zq[i] = *zptr(0, i);
         const float l0 = s_lat[m * 2], l1 = s_lat[m * 2 + 1];
 #pragma unroll 1
         for (int j = 0; j < 8; j++) {
@@ -666,7 +672,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) k_policy_tail(TailArgs a, DevPa
             for (int i = 0; i < 4; i++) zc[i] = zq[i];
             if (j + 1 < 8)
 #pragma unroll
-                for (int i = 0; i < 4; i++) zq[i] = *reinterpret_cast<const float4 *>(zrow + (j + 1) * 64 + 4 * i);
+                for (int i = 0; i < 4; i++) zq[i] = *zptr(j + 1, i);
             mbar_wait(&empty[st], ((f >> 1) & 1) ^ 1);
             unsigned char *sb = smem + st * FT_STAGE_BYTES;
 #pragma unroll
@@ -891,7 +897,7 @@ extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const f
     dim3 grid(6, (rows + 127) / 128);
     return launch_heavy(k_policy_l0_tc, grid, dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                       (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
-                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0);
+                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0);
 }
 
 // Fused policy (default): ONE layer-0 launch over all 768 columns (the six column tiles of a row tile are neighbours in launch order, so the
@@ -903,7 +909,7 @@ extern "C" cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, cons
     const int mt = (M + 127) / 128;
     cudaError_t e;
     if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0)) != cudaSuccess) return e;
+                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 1)) != cudaSuccess) return e;
     if ((e = mqe_launch_policy_tail_only(w, pw, s, p, M, passes, finish, st)) != cudaSuccess) return e;
     *launches += 2;
     return cudaGetLastError();
@@ -940,7 +946,7 @@ extern "C" cudaError_t mqe_launch_policy_l0_old(const PolicyTcWeights &w, const 
     if (mtiles <= 0) return cudaSuccess;
     return launch_background(k_policy_l0_tc, dim3(6, mtiles), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                              (const unsigned short *)w.l0_lo, (const float *)nullptr, (float *)nullptr, (unsigned short *)nullptr, (unsigned short *)nullptr,
-                             M, head_next, passes, ctr, 0, 1, Zold, (const unsigned char *)nullptr, 1, mtile0);
+                             M, head_next, passes, ctr, 0, 1, Zold, (const unsigned char *)nullptr, 1, mtile0, 0);
 }
 extern "C" cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
                                                         const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes,
@@ -950,7 +956,7 @@ extern "C" cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w
     cudaError_t e;
     if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0,
-                          2, s.Zold, (const unsigned char *)p.hist_dirty, p.A, 0)) != cudaSuccess) return e;
+                          2, s.Zold, (const unsigned char *)p.hist_dirty, p.A, 0, 1)) != cudaSuccess) return e;
     *launches += 2;
     if (early_tiles > 0 && aux) {
         // the first row tiles of the NEXT step's 29-frame pass start right here, beside the fused tail, which keeps only 64 of the 148
@@ -986,11 +992,11 @@ extern "C" cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, con
     if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(aux, ev_fork, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(2, mt), dim3(320), TC_SMEM_BYTES, aux, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0)) != cudaSuccess) return e;
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_linear_tc<128, 2, false>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), aux, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, nou, nou, 0, M, 1, passes, h1)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ev_join, aux)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(4, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0)) != cudaSuccess) return e;
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes, none)) != cudaSuccess) return e;
