@@ -88,7 +88,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
                const unsigned short *__restrict__ b_hi, const unsigned short *__restrict__ b_lo,
                const float *__restrict__ b0cat, float *__restrict__ Z, unsigned short *__restrict__ a0_hi,
                unsigned short *__restrict__ a0_lo, int M, int head, int passes, const int *__restrict__ ctr, int ntile0,
-               int mode, float *__restrict__ Zold, const unsigned char *__restrict__ dirty, int agents, int mtile0, int ztiled) {
+               int mode, float *__restrict__ Zold, const unsigned char *__restrict__ dirty, int agents, int mtile0, int ztiled, int ntpc) {
     // mode 0: all 30 slots.  Incremental layer 0 (29 of the 30 history frames of the NEXT step are known as soon as this step's frame is in
     // the ring): mode 1 = the 29 slots other than `head` (the slot the next frame will go to), raw accumulators -> Zold, launched at low
     // priority behind the physics of the step so that it fills the idle tail of k_substeps; mode 2 = slot `head` alone (K = 80), plus
@@ -99,7 +99,11 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     uint64_t *accum = empty + TC_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntile = blockIdx.x + ntile0, mtile = blockIdx.y + mtile0;     // ntile0 / mtile0: first column / row tile of this launch
+    // ntpc > 1 (mode 2 only): this CTA does `ntpc` neighbouring column tiles of its row tile one after the other -- the new frame's A tile is
+    // loaded once, every tile has its own 128 TMEM columns, and TMEM allocation / barrier set-up are paid once instead of per 128 x 128 tile
+    if (mode != 2) ntpc = 1;
+    const int ntile_first = blockIdx.x * ntpc + ntile0, mtile = blockIdx.y + mtile0;     // ntile0 / mtile0: first column / row tile of this launch
+    const uint32_t tmem_cols = ntpc == 1 ? (uint32_t)TC_TMEM_COLS : 512u;
     pdl_launch_dependents();
 
     if (threadIdx.x == 0) {
@@ -108,7 +112,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -119,24 +123,26 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     if (head == -2) head = (ctr[7] + 1) % MQE_HIST_FRAMES;  // graph replay, background pass: the slot after the one k_policy_frame wrote this step
     else if (head < 0) head = ctr[0];                        // graph replay: newest slot = the one k_policy_frame just wrote (mode 1: will write next)
     const uint32_t stage_tx = passes == 3 ? TC_STAGE_BYTES : 2 * TC_TILE_BYTES;
-    const int n_iter = mode == 0 ? MQE_HIST_FRAMES : (mode == 1 ? MQE_HIST_FRAMES - 1 : 1);
+    const int n_iter = mode == 0 ? MQE_HIST_FRAMES : (mode == 1 ? MQE_HIST_FRAMES - 1 : ntpc);     // mode 2: one iteration per column tile
 
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < n_iter; i++) {
                 const int it = mode == 0 ? i : (mode == 1 ? (i < head ? i : i + 1) : head);     // ring slot of this k-iteration
                 const int st = i & 1, ph = (i >> 1) & 1;
+                const bool load_a = mode != 2 || i == 0;             // mode 2: the A tile (the new frame) stays in stage 0 for every column tile
+                const int ntile = mode == 2 ? ntile_first + i : ntile_first;
                 mbar_wait(&empty[st], ph ^ 1);
-                mbar_expect_tx(&full[st], stage_tx);
+                mbar_expect_tx(&full[st], load_a ? stage_tx : stage_tx / 2);
                 int blk = it - head - 1;
                 if (blk < 0) blk += MQE_HIST_FRAMES;
                 unsigned char *sb = smem + st * TC_STAGE_BYTES;
                 const size_t ao = ((size_t)mtile * MQE_HIST_FRAMES + it) * TC_TILE_ELEMS;
                 const size_t bo = ((size_t)ntile * MQE_HIST_FRAMES + blk) * TC_TILE_ELEMS;
-                bulk_g2s(sb, a_hi + ao, TC_TILE_BYTES, &full[st]);
+                if (load_a) bulk_g2s(sb, a_hi + ao, TC_TILE_BYTES, &full[st]);
                 bulk_g2s(sb + 2 * TC_TILE_BYTES, b_hi + bo, TC_TILE_BYTES, &full[st]);
                 if (passes == 3) {
-                    bulk_g2s(sb + TC_TILE_BYTES, a_lo + ao, TC_TILE_BYTES, &full[st]);
+                    if (load_a) bulk_g2s(sb + TC_TILE_BYTES, a_lo + ao, TC_TILE_BYTES, &full[st]);
                     bulk_g2s(sb + 3 * TC_TILE_BYTES, b_lo + bo, TC_TILE_BYTES, &full[st]);
                 }
             }
@@ -151,15 +157,17 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
                 mbar_wait(&full[st], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sb = smem_u32(smem + st * TC_STAGE_BYTES);
-                const uint64_t dAh = umma_desc(sb), dAl = umma_desc(sb + TC_TILE_BYTES);
+                const uint32_t sa = mode == 2 ? smem_u32(smem) : sb;                 // mode 2: A lives in stage 0
+                const uint32_t d_tmem = mode == 2 ? tmem + 128u * (uint32_t)it : tmem;  // mode 2: one accumulator per column tile
+                const uint64_t dAh = umma_desc(sa), dAl = umma_desc(sa + TC_TILE_BYTES);
                 const uint64_t dBh = umma_desc(sb + 2 * TC_TILE_BYTES), dBl = umma_desc(sb + 3 * TC_TILE_BYTES);
 #pragma unroll
-                for (int j = 0; j < 5; j++) umma_f16(tmem, dAh + j * 256, dBh + j * 256, idesc, (it | j) ? 1u : 0u);
+                for (int j = 0; j < 5; j++) umma_f16(d_tmem, dAh + j * 256, dBh + j * 256, idesc, ((mode == 2 ? 0 : it) | j) ? 1u : 0u);
                 if (passes == 3) {
 #pragma unroll
-                    for (int j = 0; j < 5; j++) umma_f16(tmem, dAh + j * 256, dBl + j * 256, idesc, 1u);
+                    for (int j = 0; j < 5; j++) umma_f16(d_tmem, dAh + j * 256, dBl + j * 256, idesc, 1u);
 #pragma unroll
-                    for (int j = 0; j < 5; j++) umma_f16(tmem, dAl + j * 256, dBh + j * 256, idesc, 1u);
+                    for (int j = 0; j < 5; j++) umma_f16(d_tmem, dAl + j * 256, dBh + j * 256, idesc, 1u);
                 }
                 umma_commit(&empty[st]);             // implies tcgen05.fence::before_thread_sync
             }
@@ -173,9 +181,11 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
         const int half = (warp - 2) >> 2;             // two epilogue warps per quarter, two 32-column chunks each
         const int row = mtile * 128 + q * 32 + lane;
 #pragma unroll 1
-        for (int c = 2 * half; c < 2 * half + 2; c++) {
+        for (int tt = 0; tt < 2 * ntpc; tt++) {
+            const int t = tt >> 1, c = 2 * half + (tt & 1);     // column tile of this CTA, 32-column chunk inside it
+            const int ntile = ntile_first + t;
             uint32_t v[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 128 + c * 32);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -239,7 +249,7 @@ k_policy_l0_tc(const unsigned short *__restrict__ a_hi, const unsigned short *__
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -897,7 +907,7 @@ extern "C" cudaError_t mqe_launch_policy_l0_tc(const PolicyTcWeights &w, const f
     dim3 grid(6, (rows + 127) / 128);
     return launch_heavy(k_policy_l0_tc, grid, dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                       (const unsigned short *)w.l0_lo, b0cat, Z, planes_out ? (unsigned short *)w.p_hi[0] : (unsigned short *)nullptr,
-                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0);
+                      planes_out ? (unsigned short *)w.p_lo[0] : (unsigned short *)nullptr, rows, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0, 1);
 }
 
 // Fused policy (default): ONE layer-0 launch over all 768 columns (the six column tiles of a row tile are neighbours in launch order, so the
@@ -909,7 +919,7 @@ extern "C" cudaError_t mqe_launch_policy_tc_fused(const PolicyTcWeights &w, cons
     const int mt = (M + 127) / 128;
     cudaError_t e;
     if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 1)) != cudaSuccess) return e;
+                          (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 1, 1)) != cudaSuccess) return e;
     if ((e = mqe_launch_policy_tail_only(w, pw, s, p, M, passes, finish, st)) != cudaSuccess) return e;
     *launches += 2;
     return cudaGetLastError();
@@ -946,7 +956,7 @@ extern "C" cudaError_t mqe_launch_policy_l0_old(const PolicyTcWeights &w, const 
     if (mtiles <= 0) return cudaSuccess;
     return launch_background(k_policy_l0_tc, dim3(6, mtiles), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                              (const unsigned short *)w.l0_lo, (const float *)nullptr, (float *)nullptr, (unsigned short *)nullptr, (unsigned short *)nullptr,
-                             M, head_next, passes, ctr, 0, 1, Zold, (const unsigned char *)nullptr, 1, mtile0, 0);
+                             M, head_next, passes, ctr, 0, 1, Zold, (const unsigned char *)nullptr, 1, mtile0, 0, 1);
 }
 extern "C" cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
                                                         const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes,
@@ -954,9 +964,10 @@ extern "C" cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w
                                                         int early_tiles, int head_next, cudaStream_t aux, cudaEvent_t ev) {
     const int mt = (M + 127) / 128;
     cudaError_t e;
-    if ((e = launch_heavy(k_policy_l0_tc, dim3(6, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
+    static const int ntpc = [] { const char *e = getenv("MQE_L0_NTPC"); const int v = e ? atoi(e) : 3; return (v == 1 || v == 2 || v == 3) ? v : 3; }();     // 512 TMEM columns = at most 3 accumulators of 128
+    if ((e = launch_heavy(k_policy_l0_tc, dim3(6 / ntpc, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, (unsigned short *)w.p_hi[0], (unsigned short *)w.p_lo[0], M, head, passes, ctr, 0,
-                          2, s.Zold, (const unsigned char *)p.hist_dirty, p.A, 0, 1)) != cudaSuccess) return e;
+                          2, s.Zold, (const unsigned char *)p.hist_dirty, p.A, 0, 1, ntpc)) != cudaSuccess) return e;
     *launches += 2;
     if (early_tiles > 0 && aux) {
         // the first row tiles of the NEXT step's 29-frame pass start right here, beside the fused tail, which keeps only 64 of the 148
@@ -992,11 +1003,11 @@ extern "C" cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, con
     if ((e = cudaEventRecord(ev_fork, st)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(aux, ev_fork, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(2, mt), dim3(320), TC_SMEM_BYTES, aux, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0)) != cudaSuccess) return e;
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 0, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0, 1)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_linear_tc<128, 2, false>, dim3(1, mt), dim3(LT_THREADS), lt_smem_bytes(128), aux, PH(0), PL(0), 256, H(0), L(0), pw.ab1, nof, 0, 128, nou, nou, 0, M, 1, passes, h1)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(ev_join, aux)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_policy_l0_tc, dim3(4, mt), dim3(320), TC_SMEM_BYTES, st, hist_hi, hist_lo, (const unsigned short *)w.l0_hi,
-                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0)) != cudaSuccess) return e;
+                           (const unsigned short *)w.l0_lo, pw.b0cat, s.Z, PH(0), PL(0), M, head, passes, ctr, 2, 0, (float *)nullptr, (const unsigned char *)nullptr, 1, 0, 0, 1)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(st, ev_join, 0)) != cudaSuccess) return e;
     if ((e = launch_pdl_if(false, k_body_latent_planes, dim3((mpad * 64 + 255) / 256), dim3(256), 0, st, s.Z, s.latent, pw.wlat, PH(2), PL(2), M, mpad)) != cudaSuccess) return e;
     if ((e = launch_pdl(k_linear_tc<128>, dim3(2, mt), dim3(LT_THREADS), lt_smem_bytes(128), st, PH(2), PL(2), 512, H(2), L(2), pw.bb1, nof, 0, 256, PH(3), PL(3), 32, M, 1, passes, none)) != cudaSuccess) return e;
