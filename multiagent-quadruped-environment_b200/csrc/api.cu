@@ -394,7 +394,8 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     if (p.policy_mode == MQE_POLICY_FP32) CK(dalloc(s, &p.hist_f32, ring));      // tensor-core modes: the bf16 hi / lo planes ARE the ring
     const size_t ring_tc = (size_t)((M + 127) / 128) * 128 * MQE_HIST_FRAMES * MQE_HIST_PAD;     // pre-tiled planes, rows padded to 128
     if (p.policy_mode != MQE_POLICY_FP32) { CK(dalloc(s, &p.hist_hi, ring_tc)); CK(dalloc(s, &p.hist_lo, ring_tc)); }
-    CK(dalloc(s, &s->ps.Z, (size_t)((M + 127) / 128) * 128 * 768));      // whole row tiles: the fused tail reads it tile-major CK(dalloc(s, &s->ps.T1, (size_t)M * 128)); CK(dalloc(s, &s->ps.T2, (size_t)M * 256));
+    // Z: whole row tiles (the fused tail reads it tile-major)
+    CK(dalloc(s, &s->ps.Z, (size_t)((M + 127) / 128) * 128 * 768)); CK(dalloc(s, &s->ps.T1, (size_t)M * 128)); CK(dalloc(s, &s->ps.T2, (size_t)M * 256));
     CK(dalloc(s, &s->ps.T3, (size_t)M * 128)); CK(dalloc(s, &s->ps.latent, (size_t)M * 2)); CK(dalloc(s, &s->ps.act, (size_t)M * 12));
     if (s->incremental) CK(dalloc(s, &s->ps.Zold, (size_t)((M + 127) / 128) * 128 * 768));      // whole 128-row tiles (tile-major layout, policy_tc.cu zold_index)
     CK(dalloc(s, &s->d_actions_stage, s->action_bytes() / sizeof(float)));
