@@ -58,6 +58,9 @@ struct MqeSim {
     bool incremental = false;            // incremental layer 0: the 29 known frames of the next step are contracted behind this step's physics
     int zold_head = -1;                  // ring slot (of the NEXT frame) the partial sums in ps.Zold were computed for; -1: none
     int early_tiles = 0;                 // row tiles of the background pass that start beside the fused tail (MQE_L0_EARLY_TILES)
+    int balance = 0;                     // k_balance_tasks before every k_substeps of a step (MQE_BALANCE; default: grids of more than one round)
+    int *d_task_order = nullptr;
+    cudaEvent_t ev_bal0 = nullptr, ev_bal1 = nullptr;
     int fuse_post = 1;                   // mqe_sim_step: post-physics stages run in the epilogue of k_substeps (MQE_FUSE_POST=0: separate launch)
     int bg_early = 0;                    // set by step_plain around policy_impl: this call may fork the early part
     cudaEvent_t ev_early = nullptr;
@@ -152,6 +155,8 @@ int mqe_sim_destroy(MqeSim *s) {
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     if (s->aux_stream) cudaStreamDestroy(s->aux_stream);
     for (auto &e : s->ev_stage) if (e) cudaEventDestroy(e);
+    if (s->ev_bal0) cudaEventDestroy(s->ev_bal0);
+    if (s->ev_bal1) cudaEventDestroy(s->ev_bal1);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_early) cudaEventDestroy(s->ev_early);
@@ -372,6 +377,28 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
     CK(dalloc(s, &p.episode, (size_t)N)); CK(dalloc(s, &p.hist_dirty, (size_t)N)); CK(dalloc(s, &p.stats, (size_t)8));
     CK(dalloc(s, &p.ctr, (size_t)8));
     CK(dalloc(s, &p.warp_trace, (size_t)((N + p.E - 1) / p.E) * MQE_TRACE_COLS));
+    {
+        const int ntasks = (N + p.E - 1) / p.E;
+        CK(dalloc(s, &p.task_cost, (size_t)2 * ntasks));
+        CK(dalloc(s, &s->d_task_order, (size_t)ntasks, false));
+        std::vector<int> ident(ntasks);
+        for (int i = 0; i < ntasks; i++) ident[i] = i;
+        CK(cudaMemcpy(s->d_task_order, ident.data(), sizeof(int) * ntasks, cudaMemcpyHostToDevice));
+        // MQE_BALANCE: 0 off, 1 on; default: on when the substep grid needs more than one round of CTAs (then the order also decides which
+        // CTAs start first).  Needs the side stream.
+        const char *e = getenv("MQE_BALANCE");
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        const bool multi_round = ntasks > sms * 8;                 // at most 8 warps per SM are resident (255 registers per thread)
+        s->balance = e ? (e[0] != '0') : (multi_round ? 1 : 0);
+        if (ntasks > 8192 || p.control_type != 0) s->balance = 0;
+        if (s->balance) {
+            if (!s->aux_stream) CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&s->ev_bal0, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&s->ev_bal1, cudaEventDisableTiming));
+            p.task_order = s->d_task_order;
+        }
+    }
     { const char *e = getenv("MQE_CTA_SYNC"); p.cta_sync = e ? atoi(e) : 1; }
     { const char *e = getenv("MQE_TRACE"); p.trace = (e && e[0] == '1') ? 1 : 0; }
     if (d->lag_enabled) {
@@ -694,6 +721,13 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     // inside a capture (device_ctr) the mark has to become an event-record NODE that the host can query after the replay
 #define STAGE_MARK(i) if (s->stage_timing) CK(device_ctr ? cudaEventRecordWithFlags(s->ev_stage[i], s->stream, cudaEventRecordExternal) : cudaEventRecord(s->ev_stage[i], s->stream))
     STAGE_MARK(0);
+    if (s->balance) {                                    // next launch's task order, on the side stream beside the policy kernels
+        CK(cudaEventRecord(s->ev_bal0, s->stream));
+        CK(cudaStreamWaitEvent(s->aux_stream, s->ev_bal0, 0));
+        CK(mqe_launch_balance_tasks(s->p, s->d_task_order, s->aux_stream));
+        s->launches += 1;
+        CK(cudaEventRecord(s->ev_bal1, s->aux_stream));
+    }
     s->bg_early = (s->incremental && s->p.control_type == 0 && s->early_tiles > 0) ? 1 : 0;
     if (s->p.control_type == 0) rc = policy_impl(s, d_actions, device_ctr);
     else {                                               // 'P' / 'V' / 'T': the caller's joint actions are the actions (go1.py:43-45)
@@ -708,6 +742,7 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     if (bg) CK(cudaEventRecord(s->ev_fork, s->stream));   // fork point: the policy of this step is done, the ring holds its frame
     // no memset between kernels: k_policy_finish / k_joint_actions zeroed the statistics.  With fuse_post the physics kernel also
     // finishes the step (post_dev.cuh stages in its epilogue) and no k_post_physics launch follows.
+    if (s->balance) CK(cudaStreamWaitEvent(s->stream, s->ev_bal1, 0));
     if (s->fuse_post) {                                  // the device step counter ctr[1] always equals s->step_count (every post pass bumps it)
         DevParams q = s->p;
         q.fuse_post = 1;

@@ -67,6 +67,8 @@ struct DevParams {
     int *cand_scratch; int max_cand;     // k_substeps: capsule-pair candidates per env (upper bound: all capsule pairs of all group pairs)
       // k_substeps: local / pair constraint rows that do not fit in shared memory
     long long *warp_trace;        // [ceil(N/E)][MQE_TRACE_COLS] k_substeps per-warp trace
+    const int *task_order;        // [ceil(N/E)] which env group the i-th warp of the k_substeps grid integrates (null: identity); k_balance_tasks
+    int *task_cost;               // [2][ceil(N/E)] duration [ns] of every env group's warp in the last two launches (half = step parity)
     int fuse_post;                // k_substeps finishes the step itself (post_dev.cuh stages in its epilogue); set by mqe_sim_step only
     int act_mma;                  // actuator network of k_substeps on mma.sync (fp16 hi / lo split; default) or as FFMA2 chains (MQE_ACT_MMA=0)
     int cta_sync;                 // MQE_CTA_SYNC: 0 none, 1 per substep, 2 also per phase

@@ -19,6 +19,7 @@ struct PolicyScratch { float *Z, *T1, *T2, *T3, *latent, *act, *Zold; };   // Zo
 
 extern "C" {
 cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, cudaStream_t st);
+cudaError_t mqe_launch_balance_tasks(const DevParams &p, int *order, cudaStream_t st);
 cudaError_t mqe_launch_post(const DevParams &p, unsigned int step_count, cudaStream_t st);
 cudaError_t mqe_launch_reset_all(const DevParams &p, cudaStream_t st);
 cudaError_t mqe_launch_set_root_indexed(const DevParams &p, const float *src, const int *ids, int n, cudaStream_t st);

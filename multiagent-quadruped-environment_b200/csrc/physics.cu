@@ -604,8 +604,12 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
     const bool obb = seesaw || box;                     // robot probes collide with an oriented box instead of capsules
     const int Gc = obb ? A : G;                         // groups that take part in the capsule / capsule phase
     float *wbase = smem + physics_cta_header_floats() + warp * physics_warp_smem_floats(A, P, E, spair, maxpair);
-    const int first_env = (blockIdx.x * nwarps + warp) * E;
-    if (first_env >= p.N) return;
+    // Which env group this warp integrates.  With a task order (k_balance_tasks: groups sorted by the time their warp took in the last
+    // launch, longest first) the warps of a CTA carry similar loads -- they wait less for each other at the alignment barrier -- and
+    // the longest CTAs of a multi-round grid start first.  Results do not depend on the order: an env never looks at another one.
+    const int task = blockIdx.x * nwarps + warp, ntasks = (p.N + E - 1) / E;
+    if (task >= ntasks) return;
+    const int first_env = (p.task_order ? p.task_order[task] : task) * E;
     long long t_start;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     // optional per-phase cycle trace (MQE_TRACE=1): lane 0 accumulates clock deltas straight into the warp's trace row
@@ -1875,6 +1879,7 @@ __global__ void __launch_bounds__(256) k_substeps(const __grid_constant__ DevPar
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
             PHASE_MARK(7);
             tr[0] = t_start; tr[1] = t_end; tr[2] = wp; tr[3] = wr;
+            if (p.task_cost) p.task_cost[(p.ctr[1] & 1) * ntasks + first_env / E] = (int)min(t_end - t_start, (long long)0x7fffffff);
         }
     }
 }
@@ -1959,6 +1964,43 @@ extern "C" cudaError_t mqe_substeps_configure(const DevParams &p, int maxpair) {
         if (dev >= 0 && dev < 64) configured[dev] = pl.smem;
     }
     return cudaSuccess;
+}
+// Task order for the next k_substeps launch: env groups sorted by the duration of their warp in the previous launch, longest first
+// (bitonic sort of (cost, group) pairs in shared memory, one CTA; ntasks <= 8192).  Runs on the side stream beside the policy kernels.
+__global__ void __launch_bounds__(1024) k_balance_tasks(const int *__restrict__ cost2, const int *__restrict__ ctr, int ntasks, int npow2, int *__restrict__ order) {
+    extern __shared__ unsigned long long keys[];          // (cost << 32) | group, padded with zeros (sort descending: padding ends up last)
+    const int *cost = cost2 + ((ctr[1] + 1) & 1) * ntasks;     // the half the PREVIOUS step's launch wrote (its bookkeeping has advanced ctr[1] since)
+    for (int i = threadIdx.x; i < npow2; i += blockDim.x)
+        keys[i] = i < ntasks ? (((unsigned long long)(unsigned)max(cost[i], 0) + 1ull) << 32) | (unsigned)i : 0ull;
+    __syncthreads();
+    for (int k = 2; k <= npow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = keys[i], b = keys[l];
+                    const bool desc = (i & k) == 0;           // descending overall
+                    if (desc ? a < b : a > b) { keys[i] = b; keys[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < ntasks; i += blockDim.x) order[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
+}
+extern "C" cudaError_t mqe_launch_balance_tasks(const DevParams &p, int *order, cudaStream_t st) {
+    const int ntasks = (p.N + p.E - 1) / p.E;
+    int npow2 = 1;
+    while (npow2 < ntasks) npow2 <<= 1;
+    if (npow2 > 8192) return cudaErrorInvalidConfiguration;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_balance_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    return launch_background(k_balance_tasks, dim3(1), dim3(1024), (size_t)npow2 * 8, st, (const int *)p.task_cost, (const int *)p.ctr, ntasks, npow2, order);
 }
 extern "C" cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, cudaStream_t st) {
     const SubstepPlan pl = substeps_plan(p.N, p.A, p.Pd, p.E, maxpair);
