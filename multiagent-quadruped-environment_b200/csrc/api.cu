@@ -61,6 +61,9 @@ struct MqeSim {
     int balance = 0;                     // k_balance_tasks before every k_substeps of a step (MQE_BALANCE; default: grids of more than one round)
     int *d_task_order = nullptr;
     cudaEvent_t ev_bal0 = nullptr, ev_bal1 = nullptr;
+    int bal_pending = 0;                 // this step's k_balance_tasks has been forked and not joined yet
+    cudaStream_t bal_stream = nullptr;   // its own side stream: on aux_stream the background layer-0 node would inherit an edge from it and the
+                                         // instantiated graph then launches that pass BEFORE k_substeps (+57 us on go1gate)
     int fuse_post = 1;                   // mqe_sim_step: post-physics stages run in the epilogue of k_substeps (MQE_FUSE_POST=0: separate launch)
     int bg_early = 0;                    // set by step_plain around policy_impl: this call may fork the early part
     cudaEvent_t ev_early = nullptr;
@@ -157,6 +160,7 @@ int mqe_sim_destroy(MqeSim *s) {
     for (auto &e : s->ev_stage) if (e) cudaEventDestroy(e);
     if (s->ev_bal0) cudaEventDestroy(s->ev_bal0);
     if (s->ev_bal1) cudaEventDestroy(s->ev_bal1);
+    if (s->bal_stream) cudaStreamDestroy(s->bal_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_early) cudaEventDestroy(s->ev_early);
@@ -390,13 +394,13 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
         const bool multi_round = ntasks > sms * 8;                 // at most 8 warps per SM are resident (255 registers per thread)
-        s->balance = e ? (e[0] != '0') : (multi_round ? 1 : 0);
-        if (ntasks > 8192 || p.control_type != 0) s->balance = 0;
+        s->balance = e ? atoi(e) : (multi_round ? 1 : 0);          // 1: grouped (multi-round grids), 2: spread (experiment for one-wave grids)
+        if (p.control_type != 0) s->balance = 0;
         if (s->balance) {
-            if (!s->aux_stream) CK(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&s->bal_stream, cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&s->ev_bal0, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s->ev_bal1, cudaEventDisableTiming));
-            p.task_order = s->d_task_order;
+            if (s->balance != 3) p.task_order = s->d_task_order;     // 3: experiment -- sort and join, but keep the identity order
         }
     }
     { const char *e = getenv("MQE_CTA_SYNC"); p.cta_sync = e ? atoi(e) : 1; }
@@ -619,7 +623,8 @@ static int run_network(MqeSim *s, const float *ring, const unsigned short *hi, c
         const int early = s->bg_early ? s->early_tiles : 0;
         const int head_next = head < 0 ? -2 : (head + 1) % MQE_HIST_FRAMES;
         CK(mqe_launch_policy_tc_incremental(s->tcw, s->pw, ps, s->p, hi, lo, head, rows, s->p.policy_mode == MQE_POLICY_BF16X3 ? 3 : 1, s->p.ctr, finish, s->stream, &nf,
-                                            early, head_next, s->aux_stream, s->ev_early));
+                                            early, head_next, s->aux_stream, s->ev_early, s->bal_pending ? s->ev_bal1 : (cudaEvent_t) nullptr));
+        s->bal_pending = 0;
         s->launches += nf;
         if (finished) *finished = finish;
         return MQE_OK;
@@ -723,10 +728,11 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     STAGE_MARK(0);
     if (s->balance) {                                    // next launch's task order, on the side stream beside the policy kernels
         CK(cudaEventRecord(s->ev_bal0, s->stream));
-        CK(cudaStreamWaitEvent(s->aux_stream, s->ev_bal0, 0));
-        CK(mqe_launch_balance_tasks(s->p, s->d_task_order, s->aux_stream));
+        CK(cudaStreamWaitEvent(s->bal_stream, s->ev_bal0, 0));
+        CK(mqe_launch_balance_tasks(s->p, s->d_task_order, s->balance == 2, s->maxpair, s->bal_stream));
         s->launches += 1;
-        CK(cudaEventRecord(s->ev_bal1, s->aux_stream));
+        CK(cudaEventRecord(s->ev_bal1, s->bal_stream));
+        s->bal_pending = 1;
     }
     s->bg_early = (s->incremental && s->p.control_type == 0 && s->early_tiles > 0) ? 1 : 0;
     if (s->p.control_type == 0) rc = policy_impl(s, d_actions, device_ctr);
@@ -742,7 +748,7 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     if (bg) CK(cudaEventRecord(s->ev_fork, s->stream));   // fork point: the policy of this step is done, the ring holds its frame
     // no memset between kernels: k_policy_finish / k_joint_actions zeroed the statistics.  With fuse_post the physics kernel also
     // finishes the step (post_dev.cuh stages in its epilogue) and no k_post_physics launch follows.
-    if (s->balance) CK(cudaStreamWaitEvent(s->stream, s->ev_bal1, 0));
+    if (s->bal_pending) { CK(cudaStreamWaitEvent(s->stream, s->ev_bal1, 0)); s->bal_pending = 0; }     // policy path without the incremental launcher
     if (s->fuse_post) {                                  // the device step counter ctr[1] always equals s->step_count (every post pass bumps it)
         DevParams q = s->p;
         q.fuse_post = 1;

@@ -19,7 +19,7 @@ struct PolicyScratch { float *Z, *T1, *T2, *T3, *latent, *act, *Zold; };   // Zo
 
 extern "C" {
 cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, cudaStream_t st);
-cudaError_t mqe_launch_balance_tasks(const DevParams &p, int *order, cudaStream_t st);
+cudaError_t mqe_launch_balance_tasks(const DevParams &p, int *order, int spread, int maxpair, cudaStream_t st);
 cudaError_t mqe_launch_post(const DevParams &p, unsigned int step_count, cudaStream_t st);
 cudaError_t mqe_launch_reset_all(const DevParams &p, cudaStream_t st);
 cudaError_t mqe_launch_set_root_indexed(const DevParams &p, const float *src, const int *ids, int n, cudaStream_t st);
@@ -44,7 +44,7 @@ cudaError_t mqe_launch_policy_l0_old(const PolicyTcWeights &w, const unsigned sh
 cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
                                              const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes,
                                              const int *ctr, int finish, cudaStream_t st, int *launches,
-                                             int early_tiles, int head_next, cudaStream_t aux, cudaEvent_t ev);
+                                             int early_tiles, int head_next, cudaStream_t aux, cudaEvent_t ev, cudaEvent_t join_before_tail);
 cudaError_t mqe_launch_task_gather(const DevParams &p, const WrapParams &w, int mode, cudaStream_t st);
 cudaError_t mqe_launch_policy_tc_forked(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const unsigned short *hist_hi,
                                         const unsigned short *hist_lo, int head, int M, int passes, const int *ctr, cudaStream_t st, cudaStream_t aux,

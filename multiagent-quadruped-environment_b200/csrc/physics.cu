@@ -1965,42 +1965,57 @@ extern "C" cudaError_t mqe_substeps_configure(const DevParams &p, int maxpair) {
     }
     return cudaSuccess;
 }
-// Task order for the next k_substeps launch: env groups sorted by the duration of their warp in the previous launch, longest first
-// (bitonic sort of (cost, group) pairs in shared memory, one CTA; ntasks <= 8192).  Runs on the side stream beside the policy kernels.
-__global__ void __launch_bounds__(1024) k_balance_tasks(const int *__restrict__ cost2, const int *__restrict__ ctr, int ntasks, int npow2, int *__restrict__ order) {
-    extern __shared__ unsigned long long keys[];          // (cost << 32) | group, padded with zeros (sort descending: padding ends up last)
+// Task order for the next k_substeps launch: env groups ordered by the duration of their warp in the previous launch, longest first.
+// One CTA, counting sort over 1024 duration buckets in shared memory (a few microseconds for 8192 groups; a bitonic sort of the same keys took
+// 15 us for 1024 groups and 45 us for 4096, which showed in front of the policy tail).  Groups of one bucket come out in arbitrary order: the
+// order never changes results, only which warp works on which env group.  Runs on a side stream beside the policy kernels.
+__global__ void __launch_bounds__(1024) k_balance_tasks(const int *__restrict__ cost2, const int *__restrict__ ctr, int ntasks, int *__restrict__ order, int spread_warps) {
+    __shared__ int hist[1024], offs[1024], s_max;
     const int *cost = cost2 + ((ctr[1] + 1) & 1) * ntasks;     // the half the PREVIOUS step's launch wrote (its bookkeeping has advanced ctr[1] since)
-    for (int i = threadIdx.x; i < npow2; i += blockDim.x)
-        keys[i] = i < ntasks ? (((unsigned long long)(unsigned)max(cost[i], 0) + 1ull) << 32) | (unsigned)i : 0ull;
+    const int t = threadIdx.x;
+    hist[t] = 0;
+    if (t == 0) s_max = 1;
     __syncthreads();
-    for (int k = 2; k <= npow2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const unsigned long long a = keys[i], b = keys[l];
-                    const bool desc = (i & k) == 0;           // descending overall
-                    if (desc ? a < b : a > b) { keys[i] = b; keys[l] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    for (int i = threadIdx.x; i < ntasks; i += blockDim.x) order[i] = (int)(unsigned)(keys[i] & 0xffffffffull);
-}
-extern "C" cudaError_t mqe_launch_balance_tasks(const DevParams &p, int *order, cudaStream_t st) {
-    const int ntasks = (p.N + p.E - 1) / p.E;
-    int npow2 = 1;
-    while (npow2 < ntasks) npow2 <<= 1;
-    if (npow2 > 8192) return cudaErrorInvalidConfiguration;
-    static bool configured[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_balance_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
+    int m = 1;
+    for (int i = t; i < ntasks; i += 1024) m = max(m, cost[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((t & 31) == 0) atomicMax(&s_max, m);
+    __syncthreads();
+    const float scale = 1023.f / (float)s_max;
+    for (int i = t; i < ntasks; i += 1024) atomicAdd(&hist[1023 - min(1023, (int)((float)max(cost[i], 0) * scale))], 1);     // bucket 0 = longest
+    __syncthreads();
+    int v = hist[t];                                          // exclusive scan of the 1024 buckets (Hillis-Steele, inclusive, then shifted)
+    offs[t] = v;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const int add = t >= d ? offs[t - d] : 0;
+        __syncthreads();
+        offs[t] += add;
+        __syncthreads();
     }
-    return launch_background(k_balance_tasks, dim3(1), dim3(1024), (size_t)npow2 * 8, st, (const int *)p.task_cost, (const int *)p.ctr, ntasks, npow2, order);
+    const int excl = offs[t] - v;
+    __syncthreads();
+    offs[t] = excl;
+    __syncthreads();
+    const int W = spread_warps, C = W > 0 ? ntasks / W : 0;   // spread: C full CTAs of W warps
+    for (int i = t; i < ntasks; i += 1024) {
+        const int b = 1023 - min(1023, (int)((float)max(cost[i], 0) * scale));
+        const int r = atomicAdd(&offs[b], 1);                 // rank of group i, longest first
+        if (W <= 0 || r >= C * W) order[r] = i;               // grouped: CTA c takes ranks [c * warps, ..): similar loads together, longest CTAs first
+        else {
+            // spread (one-wave grids): every full CTA takes ONE group of each tier of the ranking (tier k = ranks [k * C, (k + 1) * C)), tiers dealt
+            // in alternating direction, so the slowest warps sit on different SMs, each beside the fastest ones
+            const int k = r / C, pos = r % C, c = (k & 1) ? C - 1 - pos : pos;
+            order[c * W + k] = i;
+        }
+    }
+}
+extern "C" cudaError_t mqe_launch_balance_tasks(const DevParams &p, int *order, int spread, int maxpair, cudaStream_t st) {
+    const int ntasks = (p.N + p.E - 1) / p.E;
+    const int spread_warps = spread ? substeps_plan(p.N, p.A, p.Pd, p.E, maxpair).warps : 0;
+    // greatest priority, like every kernel the step waits for
+    return launch_pdl_if(false, k_balance_tasks, dim3(1), dim3(1024), 0, st, (const int *)p.task_cost, (const int *)p.ctr, ntasks, order, spread_warps);
 }
 extern "C" cudaError_t mqe_launch_substeps(const DevParams &p, int nsub, int maxpair, cudaStream_t st) {
     const SubstepPlan pl = substeps_plan(p.N, p.A, p.Pd, p.E, maxpair);

@@ -961,7 +961,7 @@ extern "C" cudaError_t mqe_launch_policy_l0_old(const PolicyTcWeights &w, const 
 extern "C" cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w, const PolicyWeightsDev &pw, const PolicyScratch &s, const DevParams &p,
                                                         const unsigned short *hist_hi, const unsigned short *hist_lo, int head, int M, int passes,
                                                         const int *ctr, int finish, cudaStream_t st, int *launches,
-                                                        int early_tiles, int head_next, cudaStream_t aux, cudaEvent_t ev) {
+                                                        int early_tiles, int head_next, cudaStream_t aux, cudaEvent_t ev, cudaEvent_t join_before_tail) {
     const int mt = (M + 127) / 128;
     cudaError_t e;
     static const int ntpc = [] { const char *e = getenv("MQE_L0_NTPC"); const int v = e ? atoi(e) : 3; return (v == 1 || v == 2 || v == 3) ? v : 3; }();     // 512 TMEM columns = at most 3 accumulators of 128
@@ -979,6 +979,9 @@ extern "C" cudaError_t mqe_launch_policy_tc_incremental(const PolicyTcWeights &w
         if ((e = mqe_launch_policy_l0_old(w, hist_hi, hist_lo, head_next, M, passes, s.Zold, ctr, 0, early_tiles < mt ? early_tiles : mt, aux)) != cudaSuccess) return e;
         *launches += 1;
     }
+    // a side-stream kernel of this step (k_balance_tasks) is joined HERE, in front of the tail, not in front of k_substeps: an extra edge
+    // into the k_substeps node makes the instantiated graph launch the background layer-0 pass first, which then takes the SMs
+    if (join_before_tail && (e = cudaStreamWaitEvent(st, join_before_tail, 0)) != cudaSuccess) return e;
     if ((e = mqe_launch_policy_tail_only(w, pw, s, p, M, passes, finish, st)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
