@@ -350,3 +350,55 @@ def test_incremental_policy_across_ring_wrap_and_resets():
     assert n_reset >= 64 and np.isfinite(e).all()
     assert np.median(e) <= 2e-4 and np.quantile(e, 0.99) <= 2e-2, (np.median(e), np.quantile(e, 0.99))
     eng.close(); orc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task,n,mode", [("go1sheep-hard", 96, "1"), ("go1gate", 160, "1"), ("go1gate", 160, "2"), ("go1football-defender", 64, "1")])
+def test_task_order_does_not_change_results(task, n, mode, monkeypatch):
+    """k_balance_tasks re-orders which warp of the k_substeps grid integrates which env group (by the duration of each group's warp in the
+    previous launch; MQE_BALANCE=1 grouped, 2 spread).  An env never looks at another one, so state, flags and observation rows must be
+    BIT-identical to the identity order, step after step, through resets."""
+    def run(balance):
+        monkeypatch.setenv("MQE_BALANCE", balance)
+        cfg, sc = build(task, n, mode=E.POLICY_BF16X3, episode_s=0.5)
+        eng = E.Engine(sc.desc, device=0, keepalive=sc)
+        eng.reset()
+        a_ctrl = sc.num_agents - 1 if sc.desc.defender else sc.num_agents
+        out = []
+        for s in range(40):
+            eng.step(dev(actions_for(n, a_ctrl, s)).data_ptr())
+            torch.cuda.synchronize()
+            out.append((get(eng, E.BUF_ROOT_STATES).copy(), get(eng, E.BUF_DOF_STATES).copy(), get(eng, E.BUF_OBS).copy(), get(eng, E.BUF_RESET).copy()))
+        eng.close()
+        return out
+    ref, got = run("0"), run(mode)
+    for s, (r, g) in enumerate(zip(ref, got)):
+        for x, y in zip(r, g):
+            assert np.array_equal(x, y), (task, mode, s)
+    assert sum(int(r[3].sum()) for r in ref) > 0                     # resets happened
+
+
+@pytest.mark.gpu
+def test_stage_timing_marks():
+    """mqe_sim_stage_timing / mqe_sim_stage_ms (ABI 7): event marks between the stages of a step, recorded as nodes of the step graph.  The four
+    stage times are positive, add up to less than the step, and switching the marks on and off does not change results."""
+    cfg, sc = build("go1gate", 256, mode=E.POLICY_BF16X3)
+    eng = E.Engine(sc.desc, device=0, keepalive=sc)
+    eng.reset()
+    with pytest.raises(E.EngineError):
+        eng.stage_ms()                                               # not enabled yet
+    states = []
+    for timing in (False, True, False):
+        eng.stage_timing(timing)
+        for s in range(4):                                           # plain steps, capture, replay
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); eng.step(dev(actions_for(256, 2, s)).data_ptr()); e1.record()
+            torch.cuda.synchronize()
+            if timing:
+                st = eng.stage_ms()
+                assert set(st) == {"policy", "physics", "bookkeeping", "background_join"}
+                assert all(v >= 0.0 for v in st.values()) and st["policy"] > 0.0 and st["physics"] > 0.0
+                assert sum(st.values()) <= e0.elapsed_time(e1) + 1e-3
+        states.append(get(eng, E.BUF_ROOT_STATES).copy())
+    assert np.isfinite(states[-1]).all()
+    eng.close()
