@@ -61,6 +61,7 @@ struct MqeSim {
     int balance = 0;                     // k_balance_tasks before every k_substeps of a step (MQE_BALANCE; default: grids of more than one round)
     int *d_task_order = nullptr;
     cudaEvent_t ev_bal0 = nullptr, ev_bal1 = nullptr;
+    int balance_at_end = 1;              // k_balance_tasks at the end of the step (default) or at the start of the next one, beside the policy (MQE_BALANCE_WHEN=start)
     int bal_pending = 0;                 // this step's k_balance_tasks has been forked and not joined yet
     cudaStream_t bal_stream = nullptr;   // its own side stream: on aux_stream the background layer-0 node would inherit an edge from it and the
                                          // instantiated graph then launches that pass BEFORE k_substeps (+57 us on go1gate)
@@ -396,6 +397,7 @@ static int create_impl(const MqeSimDesc *d, int device, void *stream, MqeSim *s)
         const bool multi_round = ntasks > sms * 8;                 // at most 8 warps per SM are resident (255 registers per thread)
         s->balance = e ? atoi(e) : (multi_round ? 1 : 0);          // 1: grouped (multi-round grids), 2: spread (experiment for one-wave grids)
         if (p.control_type != 0) s->balance = 0;
+        { const char *w = getenv("MQE_BALANCE_WHEN"); s->balance_at_end = !(w && w[0] == 's'); }
         if (s->balance) {
             CK(cudaStreamCreateWithFlags(&s->bal_stream, cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&s->ev_bal0, cudaEventDisableTiming));
@@ -726,7 +728,7 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     // inside a capture (device_ctr) the mark has to become an event-record NODE that the host can query after the replay
 #define STAGE_MARK(i) if (s->stage_timing) CK(device_ctr ? cudaEventRecordWithFlags(s->ev_stage[i], s->stream, cudaEventRecordExternal) : cudaEventRecord(s->ev_stage[i], s->stream))
     STAGE_MARK(0);
-    if (s->balance) {                                    // next launch's task order, on the side stream beside the policy kernels
+    if (s->balance && !s->balance_at_end) {              // next launch's task order, on the side stream beside the policy kernels
         CK(cudaEventRecord(s->ev_bal0, s->stream));
         CK(cudaStreamWaitEvent(s->bal_stream, s->ev_bal0, 0));
         CK(mqe_launch_balance_tasks(s->p, s->d_task_order, s->balance == 2, s->maxpair, s->bal_stream));
@@ -770,6 +772,17 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
         rc = post_impl(s, device_ctr);
         if (rc != MQE_OK) return rc;
     }
+    if (s->balance && s->balance_at_end) {
+        // The NEXT step's task order, from the durations this step's k_substeps just wrote (its bookkeeping has advanced ctr[1]), on its own
+        // side stream: it runs beside the task gather / the tail of the background layer-0 pass and is joined with that pass at the end
+        // of the step, so that no kernel of the next step waits for it.
+        CK(cudaEventRecord(s->ev_bal0, s->stream));
+        CK(cudaStreamWaitEvent(s->bal_stream, s->ev_bal0, 0));
+        CK(mqe_launch_balance_tasks(s->p, s->d_task_order, s->balance == 2, s->maxpair, s->bal_stream));
+        s->launches += 1;
+        CK(cudaEventRecord(s->ev_bal1, s->bal_stream));
+        s->bal_pending = 1;
+    }
     if (s->wrap.kind != MQE_WRAP_NONE) {
         CK(mqe_launch_task_gather(s->p, s->wrap, 0, s->stream));
         s->launches += 1;
@@ -777,6 +790,7 @@ static int step_plain(MqeSim *s, const float *d_actions, bool device_ctr) {
     rc = exchange_impl(s);
     STAGE_MARK(3);
     if (bg) CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));     // join: the ring must not move under the background pass
+    if (s->bal_pending) { CK(cudaStreamWaitEvent(s->stream, s->ev_bal1, 0)); s->bal_pending = 0; }
     STAGE_MARK(4);
 #undef STAGE_MARK
     s->bg_early = 0;
