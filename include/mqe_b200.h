@@ -157,12 +157,14 @@ typedef enum {
                                         sheep_pos_var_lin_punishment, sheep_pos_var_exp_punishment; D = 14 + 2 P + A */
     MQE_WRAP_SEESAW = 2,             /* go1_seesaw_wrapper.py:48-120  scale: x_movement, height, y_punishment, contact_punishment,
                                         agent_distance_punishment, success, fall_punishment; D = 12 + A */
-    MQE_WRAP_FOOTBALL_DEFENDER = 3   /* go1_football_wrapper.py:57-91 scale: goal, ball_gate_distance; D = 20, two reported agents */
+    MQE_WRAP_FOOTBALL_DEFENDER = 3,  /* go1_football_wrapper.py:57-91 scale: goal, ball_gate_distance; D = 20, two reported agents */
+    MQE_WRAP_PUSHBOX = 4             /* go1_pushbox_wrapper.py        scale: box_x_movement; D = 20 + A (ids, pos/rpy self and other, gate xy,
+                                        box xy, box quaternion); h_gate [N][2] */
 } MqeWrapperKind;
 typedef struct {
     int32_t kind;
     float scale[8];
-    const float *h_gate;             /* HOST: sheep [N][2] gate position (env-relative), football defender [N][3] gate position (world) */
+    const float *h_gate;             /* HOST: sheep / pushbox [N][2] gate position (env-relative), football defender [N][3] gate position (world) */
 } MqeWrapperDesc;
 
 typedef struct MqeSim MqeSim;

@@ -14,7 +14,8 @@
 // One warp per env.  The lanes gather what the observation is made of into a per-warp staging row (coalesced loads, one round trip instead
 // of a thread walking ~60 dependent accesses: as one thread per env this kernel took 14 us alone and 30-60 us beside the background
 // layer-0 pass), every lane then writes its share of the observation rows, and lane 0 evaluates the reward terms from the staging row
-// with the arithmetic of the torch wrappers (go1_sheep_wrapper.py:54-118, go1_seesaw_wrapper.py:48-120, go1_football_wrapper.py:57-91).
+// with the arithmetic of the torch wrappers (go1_sheep_wrapper.py:54-118, go1_seesaw_wrapper.py:48-120, go1_football_wrapper.py:57-91,
+// go1_pushbox_wrapper.py).
 __global__ void __launch_bounds__(WRAP_THREADS) k_task_gather(DevParams p, WrapParams w, int mode) {
     pdl_launch_dependents();
     pdl_wait();                                         // launched with the PDL attribute at MQE_PDL=2: the producer of the state must have finished
@@ -50,6 +51,12 @@ __global__ void __launch_bounds__(WRAP_THREADS) k_task_gather(DevParams p, WrapP
                 const float *r = p.root + ((size_t)e * p.G + A) * 13;
                 sg[24 + lane] = lane < 3 ? r[lane] - eo[lane] : r[7 + lane - 3];
             }
+        } else if (w.kind == MQE_WRAP_PUSHBOX) {           // gate xy | box xy (env-relative) | box quaternion (go1_pushbox_wrapper.py)
+            ncol = 8;
+            if (lane < 8) {
+                const float *r = p.root + ((size_t)e * p.G + A) * 13;
+                sg[24 + lane] = lane < 2 ? w.gate[e * 2 + lane] : (lane < 4 ? r[lane - 2] - eo[lane - 2] : r[3 + lane - 4]);
+            }
         }
         // every scalar the reward terms read, fetched in the SAME round trip by the upper lanes (sg[72..]); lane 0 then works from shared memory
         if (mode == 0) {
@@ -69,6 +76,10 @@ __global__ void __launch_bounds__(WRAP_THREADS) k_task_gather(DevParams p, WrapP
                 else if (lane >= 20 && lane < 20 + Aw) ax[4 + lane - 20] = w.last[e * Aw + lane - 20];
             } else if (w.kind == MQE_WRAP_FOOTBALL_DEFENDER) {
                 if (lane == 16 || lane == 17) ax[lane - 16] = w.gate[e * 3 + lane - 16];
+            } else if (w.kind == MQE_WRAP_PUSHBOX) {
+                if (lane == 16) ax[0] = (float)w.has_last[e];
+                else if (lane == 17) ax[1] = w.last[e];
+                else if (lane == 18) ax[2] = (float)p.reset_buf[e];
             }
         }
         __syncwarp();
@@ -167,6 +178,21 @@ __global__ void __launch_bounds__(WRAP_THREADS) k_task_gather(DevParams p, WrapP
                     const float rr = s_dist * expf(-sqrtf(dx * dx + dy * dy) / 3.f);
                     reward += rr; term[1] = rr;
                 }
+            }
+            else if (w.kind == MQE_WRAP_PUSHBOX) {
+                // reward = scale * (box x - box x of the previous step), zero on the step of a reset; the wrapper's reset() forgets the last
+                // position (`last_box_pos = None`), every step stores it whatever the scale
+                if (mode == 0) {
+                    const float *aux = sg + 72;
+                    const float bx = sg[26], s_move = w.scale[0];
+                    if (s_move != 0.f && aux[0] != 0.f) {
+                        float xm = bx - aux[1];
+                        if (aux[2] != 0.f) xm = 0.f;
+                        const float r = s_move * xm;
+                        reward += r; term[0] = r;
+                    }
+                    w.last[e] = bx; w.has_last[e] = 1;
+                } else w.has_last[e] = 0;
             }
 #undef BI
             if (mode == 0)
