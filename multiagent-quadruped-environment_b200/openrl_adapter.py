@@ -84,7 +84,7 @@ class mqe_openrl_wrapper(Wrapper):
             rewards = reward
         done = self._to_host("done", termination)
         torch.cuda.current_stream(dev).synchronize()
-        dones = np.repeat(done[:, None], self.agent_num, axis=1).astype(bool)
+        dones = self._dones(done)
         return (obs.copy() if isinstance(obs, np.ndarray) else obs), (rewards.copy() if isinstance(rewards, np.ndarray) else rewards), dones, self._empty_infos(dones.shape[0])
 
     def _to_host(self, key, t):
@@ -107,19 +107,37 @@ class mqe_openrl_wrapper(Wrapper):
             obs, rew = obs.reshape(n, 1, -1), rew.reshape(n, 1)
             done = np.repeat(done, self._task.num_agents)
         rewards = rew[..., None]
-        dones = np.repeat(done[:, None], self.agent_num, axis=1)
+        dones = self._dones(done)
         return obs, rewards, dones, self._empty_infos(dones.shape[0])
 
     def _empty_infos(self, n):
-        """`infos = [{} ...]` of utils.py:63-65 without allocating num_envs dicts per step (0.2 ms for 4096 envs): one list of distinct
-        dicts is kept and handed out again; whatever a caller put into them is cleared first."""
+        """`infos = [{} ...]` of utils.py:63-65 without allocating num_envs dicts per step (0.2 ms for 4096 envs) and without looking at
+        every one of them either (`any(infos)` alone is 50 us for 4096 envs): one list of distinct dicts is kept and handed out again; the
+        dicts note on a shared flag when a caller writes into one, and only then are they cleared before the next hand-out."""
         infos = getattr(self, "_infos", None)
         if infos is None or len(infos) != n:
-            infos = self._infos = [{} for _ in range(n)]
-        elif any(infos):
+            self._infos_flag = [False]
+            infos = self._infos = [_InfoDict(self._infos_flag) for _ in range(n)]
+        elif self._infos_flag[0]:
             for d in infos:
-                d.clear()
+                dict.clear(d)
+            self._infos_flag[0] = False
         return infos
+
+    def _dones(self, done):
+        """`dones` [N, agent_num] (utils.py:61): the per-env flag repeated per agent into one of two alternating preallocated arrays
+        (np.repeat allocates: 20-35 us per step at 4096-8192 envs); like the fused result views, an array stays intact across the NEXT step."""
+        n = done.shape[0]
+        bufs = getattr(self, "_done_bufs", None)
+        if bufs is None or bufs[0].shape != (n, self.agent_num):
+            bufs = self._done_bufs = [np.empty((n, self.agent_num), dtype=bool) for _ in range(2)]
+            self._done_k = 0
+        self._done_k ^= 1
+        out = bufs[self._done_k]
+        d = np.asarray(done, dtype=bool)
+        for a in range(self.agent_num):                   # column stores: 6 us at 4096 envs (a broadcast copy takes 34, np.repeat 16)
+            out[:, a] = d
+        return out
 
     def _step_device(self, actions):
         """CUDA tensors in, CUDA tensors out (zero-copy views of the engine's step result; valid until the step after next)."""
@@ -152,6 +170,34 @@ class mqe_openrl_wrapper(Wrapper):
             rb[k] = 0
         rb["step count"] = 0
         return out
+
+
+class _InfoDict(dict):
+    """An `info` dict that raises a shared flag when somebody writes into it (see mqe_openrl_wrapper._empty_infos)."""
+    __slots__ = ("_flag",)
+
+    def __init__(self, flag):
+        super().__init__()
+        self._flag = flag
+
+    def _touch(name):                                   # noqa: N805 -- class-body helper
+        base = getattr(dict, name)
+
+        def method(self, *a, **k):
+            self._flag[0] = True
+            return base(self, *a, **k)
+        method.__name__ = name
+        return method
+
+    __setitem__ = _touch("__setitem__")
+    __delitem__ = _touch("__delitem__")
+    __ior__ = _touch("__ior__")
+    update = _touch("update")
+    setdefault = _touch("setdefault")
+    pop = _touch("pop")
+    popitem = _touch("popitem")
+    clear = _touch("clear")
+    del _touch
 
 
 class MATWrapper(Wrapper):
