@@ -158,8 +158,12 @@ typedef enum {
     MQE_WRAP_SEESAW = 2,             /* go1_seesaw_wrapper.py:48-120  scale: x_movement, height, y_punishment, contact_punishment,
                                         agent_distance_punishment, success, fall_punishment; D = 12 + A */
     MQE_WRAP_FOOTBALL_DEFENDER = 3,  /* go1_football_wrapper.py:57-91 scale: goal, ball_gate_distance; D = 20, two reported agents */
-    MQE_WRAP_PUSHBOX = 4             /* go1_pushbox_wrapper.py        scale: box_x_movement; D = 20 + A (ids, pos/rpy self and other, gate xy,
+    MQE_WRAP_PUSHBOX = 4,            /* go1_pushbox_wrapper.py        scale: box_x_movement; D = 20 + A (ids, pos/rpy self and other, gate xy,
                                         box xy, box quaternion); h_gate [N][2] */
+    /* two-agent duel wrappers: D = 12 = (pos, rpy) self | other, agent 1 sees a mirrored world, the reward goes to agent 0 only */
+    MQE_WRAP_WRESTLING = 5,          /* go1_wrestling_wrapper.py:9-89  scale: success, punishment */
+    MQE_WRAP_BRIDGE = 6,             /* go1_bridge_wrapper.py:8-80     scale: success, punishment, target */
+    MQE_WRAP_ROTATION = 7            /* go1_rotation_wrapper.py:8-103  scale: success, punishment, distance, then scale[3] = target x */
 } MqeWrapperKind;
 typedef struct {
     int32_t kind;

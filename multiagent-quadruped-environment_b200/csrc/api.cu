@@ -558,6 +558,9 @@ int mqe_sim_set_wrapper(MqeSim *s, const MqeWrapperDesc *d) {
     } else if (d->kind == MQE_WRAP_PUSHBOX) {
         if (p.P < 1) return fail(MQE_ERR_INVALID, "pushbox wrapper needs the box");
         w.Aw = p.A; w.D = 20 + p.A; gate_cols = 2;
+    } else if (d->kind == MQE_WRAP_WRESTLING || d->kind == MQE_WRAP_BRIDGE || d->kind == MQE_WRAP_ROTATION) {
+        if (p.A != 2) return fail(MQE_ERR_INVALID, "duel wrappers need exactly two agents");
+        w.Aw = 2; w.D = 12;
     } else return fail(MQE_ERR_INVALID, "unknown wrapper kind");
     if (w.Aw > 4) return fail(MQE_ERR_INVALID, "wrapper: at most 4 agents");
     for (int i = 0; i < 8; i++) w.scale[i] = d->scale[i];

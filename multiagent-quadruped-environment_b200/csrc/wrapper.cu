@@ -15,7 +15,7 @@
 // of a thread walking ~60 dependent accesses: as one thread per env this kernel took 14 us alone and 30-60 us beside the background
 // layer-0 pass), every lane then writes its share of the observation rows, and lane 0 evaluates the reward terms from the staging row
 // with the arithmetic of the torch wrappers (go1_sheep_wrapper.py:54-118, go1_seesaw_wrapper.py:48-120, go1_football_wrapper.py:57-91,
-// go1_pushbox_wrapper.py).
+// go1_pushbox_wrapper.py, go1_wrestling_wrapper.py, go1_bridge_wrapper.py, go1_rotation_wrapper.py).
 __global__ void __launch_bounds__(WRAP_THREADS) k_task_gather(DevParams p, WrapParams w, int mode) {
     pdl_launch_dependents();
     pdl_wait();                                         // launched with the PDL attribute at MQE_PDL=2: the producer of the state must have finished
@@ -80,11 +80,28 @@ __global__ void __launch_bounds__(WRAP_THREADS) k_task_gather(DevParams p, WrapP
                 if (lane == 16) ax[0] = (float)w.has_last[e];
                 else if (lane == 17) ax[1] = w.last[e];
                 else if (lane == 18) ax[2] = (float)p.reset_buf[e];
+            } else if (w.kind == MQE_WRAP_BRIDGE || w.kind == MQE_WRAP_ROTATION) {
+                if (lane >= 16 && lane < 20) ax[lane - 16] = w.last[e * 4 + lane - 16];     // what the wrapper's reset() stored (see mode 1 below)
             }
         }
         __syncwarp();
+        const bool duel = w.kind == MQE_WRAP_WRESTLING || w.kind == MQE_WRAP_BRIDGE || w.kind == MQE_WRAP_ROTATION;
+        if (duel) {
+            // (pos, rpy) self | other, no ids; agent 1 lives in a mirrored world: y and pitch negated (wrestling :32-36, rotation :45-49), or x
+            // reflected about the midpoint of the two start positions and pitch negated (bridge :33-41; span = |x0 + x1| at the wrapper's reset())
+            const float span = w.kind == MQE_WRAP_BRIDGE ? (mode == 0 ? sg[72 + 3] : fabsf(sg[6] + sg[0])) : 0.f;
+            for (int idx = lane; idx < 24; idx += 32) {
+                const int a = idx / 12, col = idx % 12;
+                float v = col < 6 ? sg[a * 6 + col] : sg[(1 - a) * 6 + col - 6];
+                if (a == 1) {
+                    if (w.kind == MQE_WRAP_BRIDGE) { if (col == 0 || col == 6) v = span - v; else if (col == 4 || col == 10) v = -v; }
+                    else if (col % 3 == 1) v = -v;
+                }
+                w.obs[((size_t)e * 2 + a) * 12 + col] = v;
+            }
+        }
         // ---- observation rows: one-hot id, (pos, rpy) self, (pos, rpy) of the agent at the mirrored index, then the task columns ----
-        for (int idx = lane; idx < Aw * D; idx += 32) {
+        for (int idx = lane; !duel && idx < Aw * D; idx += 32) {
             const int a = idx / D, col = idx % D;
             float v;
             if (col < Aw) v = col == a ? 1.f : 0.f;
@@ -194,9 +211,42 @@ __global__ void __launch_bounds__(WRAP_THREADS) k_task_gather(DevParams p, WrapP
                     w.last[e] = bx; w.has_last[e] = 1;
                 } else w.has_last[e] = 0;
             }
+            else if (w.kind == MQE_WRAP_WRESTLING && mode == 0) {
+                // flipped: |pitch| > 0.9 pi or |roll| >= 0.4 pi with both angles wrapped to (-pi, pi] (go1_wrestling_wrapper.py:66-72)
+                const float PI = 3.14159265358979323846f;
+                bool fl[2];
+                for (int a = 0; a < 2; a++) {
+                    float r = BI(a, 3), pt = BI(a, 4);
+                    if (r > PI) r -= 2.f * PI;
+                    if (pt > PI) pt -= 2.f * PI;
+                    fl[a] = fabsf(pt) > PI * 0.9f || fabsf(r) >= PI * 0.4f;
+                }
+                if (w.scale[0] != 0.f) { const float r = fl[1] ? w.scale[0] : 0.f; reward += r; term[0] = r; }
+                if (w.scale[1] != 0.f) { const float r = fl[0] ? w.scale[1] : 0.f; reward -= r; term[1] = r; }
+            } else if (w.kind == MQE_WRAP_BRIDGE) {
+                if (mode == 0) {                             // success: the opponent fell off (z < 0.5), punishment: agent 0 did, target: agent 0 is past the opponent's start x
+                    const float *aux = sg + 72;
+                    if (w.scale[0] != 0.f) { const float r = BI(1, 2) < 0.5f ? w.scale[0] : 0.f; reward += r; term[0] = r; }
+                    if (w.scale[1] != 0.f) { const float r = BI(0, 2) < 0.5f ? w.scale[1] : 0.f; reward -= r; term[1] = r; }
+                    if (w.scale[2] != 0.f) { const float r = BI(0, 0) > aux[2] ? w.scale[2] : 0.f; reward += r; term[2] = r; }
+                } else { w.last[e * 4 + 2] = BI(1, 0); w.last[e * 4 + 3] = fabsf(BI(1, 0) + BI(0, 0)); }     // target_pos = flip(base_pos) at reset() (:28-31)
+            } else if (w.kind == MQE_WRAP_ROTATION) {
+                const float T = w.scale[3];
+                if (mode == 0) {
+                    const float *aux = sg + 72;
+                    if (w.scale[0] != 0.f) { const float r = BI(0, 0) > T ? w.scale[0] : 0.f; reward += r; term[0] = r; }
+                    if (w.scale[1] != 0.f) { const float r = BI(1, 0) > T ? w.scale[1] : 0.f; reward -= r; term[1] = r; }
+                    if (w.scale[2] != 0.f) {                 // the reference subtracts the target x from BOTH x and y here (:77), from x only in reset() (:38-39)
+                        const float dx = BI(0, 0) - T, dy = BI(0, 1) - T, dis = sqrtf(dx * dx + dy * dy);
+                        const float r = dis < aux[0] ? w.scale[2] : 0.f;
+                        reward += r; term[2] = r;
+                        w.last[e * 4] = dis;
+                    }
+                } else { const float dx = BI(0, 0) - T, dy = BI(0, 1); w.last[e * 4] = sqrtf(dx * dx + dy * dy); }
+            }
 #undef BI
             if (mode == 0)
-                for (int a = 0; a < Aw; a++) w.reward[(size_t)e * Aw + a] = reward;
+                for (int a = 0; a < Aw; a++) w.reward[(size_t)e * Aw + a] = (duel && a > 0) ? 0.f : reward;
         }
     }
     if (mode != 0) return;

@@ -35,7 +35,7 @@ OBS_SLICES = {                                   # include/mqe_b200.h MQE_OBS_*
 }
 
 NPC_NONE, NPC_RIGID, NPC_SEESAW, NPC_BOX, NPC_PLATFORM = 0, 1, 2, 3, 4
-WRAP_NONE, WRAP_SHEEP, WRAP_SEESAW, WRAP_FOOTBALL_DEFENDER, WRAP_PUSHBOX = 0, 1, 2, 3, 4
+WRAP_NONE, WRAP_SHEEP, WRAP_SEESAW, WRAP_FOOTBALL_DEFENDER, WRAP_PUSHBOX, WRAP_WRESTLING, WRAP_BRIDGE, WRAP_ROTATION = range(8)
 
 
 class StepResultLayoutC(ctypes.Structure):

@@ -500,10 +500,16 @@ class Go1RotationWrapper(EmptyWrapper):
     def reset(self):
         obs_buf = self.env.reset()
         self._init_extras(obs_buf)
-        return self._obs(obs_buf)
+        if not hasattr(self, "_fused"):
+            self._fused = self._fuse(7, [self.success_reward_scale, self.punishment_scale, self.distance_reward_scale, float(self.target_pos[0])],
+                                     {"success reward": 0, "punishment": 1, "distance reward": 2, "step count": 8})
+        return self._wobs if self._fused else self._obs(obs_buf)
 
     def step(self, action):
         action[:, 1, 1:] = -action[:, 1, 1:]                  # in place, as the reference does; commutes with the clip
+        if getattr(self, "_fused", False):
+            obs, reward, termination, info = self._fused_step(action)
+            return obs, reward.reshape(self.env.num_envs, self.env.num_agents, 1), termination, info
         obs_buf, _, termination, info = self.env.step_from_wrapper(action)
         N, A = self.env.num_envs, self.env.num_agents
         base_pos = obs_buf.base_pos.reshape(N, A, -1)
@@ -560,10 +566,15 @@ class Go1WrestlingWrapper(EmptyWrapper):
     def reset(self):
         obs_buf = self.env.reset()
         self._init_extras(obs_buf)
-        return self._obs(obs_buf)
+        if not hasattr(self, "_fused"):
+            self._fused = self._fuse(5, [self.success_reward_scale, self.punishment_scale], {"success reward": 0, "punishment": 1, "step count": 8})
+        return self._wobs if self._fused else self._obs(obs_buf)
 
     def step(self, action):
         action[:, 1, 1:] = -action[:, 1, 1:]                  # in place, as the reference does
+        if getattr(self, "_fused", False):
+            obs, reward, termination, info = self._fused_step(action)
+            return obs, reward.reshape(self.env.num_envs, self.env.num_agents, 1), termination, info
         obs_buf, _, termination, info = self.env.step_from_wrapper(action)
         N, A = self.env.num_envs, self.env.num_agents
         self._acc("step count", 1)
@@ -611,10 +622,15 @@ class Go1BridgeWrapper(EmptyWrapper):
     def reset(self):
         obs_buf = self.env.reset()
         self._init_extras(obs_buf)
-        return self._obs(obs_buf)
+        if not hasattr(self, "_fused"):
+            self._fused = self._fuse(6, [self.success_reward_scale, self.punishment_scale, self.target_reward_scale],
+                                     {"success reward": 0, "punishment": 1, "target reward": 2, "step count": 8})
+        return self._wobs if self._fused else self._obs(obs_buf)
 
     def step(self, action):
         action[:, 1, 1:] = -action[:, 1, 1:]
+        if getattr(self, "_fused", False):
+            return self._fused_step(action)
         obs_buf, _, termination, info = self.env.step_from_wrapper(action)
         N, A = self.env.num_envs, self.env.num_agents
         self._acc("step count", 1)

@@ -394,7 +394,8 @@ def test_football_game_tasks(task, A):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("task", ["go1sheep-hard", "go1sheep-easy", "go1seesaw", "go1football-defender", "go1pushbox"])
+@pytest.mark.parametrize("task", ["go1sheep-hard", "go1sheep-easy", "go1seesaw", "go1football-defender", "go1pushbox", "go1wrestling", "go1bridge",
+                                  "go1revolvingdoor"])
 def test_fused_wrapper_gather_matches_torch_wrapper(task, monkeypatch):
     """csrc/wrapper.cu (one kernel inside the step graph) against the torch wrappers (pinned to the reference's own code by
     tests/test_wrappers_golden.py): two envs built from the same seed, same actions, resets included (short episodes)."""
